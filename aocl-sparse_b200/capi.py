@@ -1,0 +1,245 @@
+"""ctypes binding of the AOCL-Sparse C API for the CSR SpMV / SpMM path.
+
+The same class binds ANY shared library that exports the reference's symbols
+(library/include/aoclsparse_*.h of the reference): the product library
+``libaoclsparse_b200.so`` and, in tests only, the reference's own build
+``oracle/_ref/libaoclsparse_ref.so``.  That is what lets the parity tests run the
+identical call sequence against both.
+
+Pointers may be numpy arrays (host memory) or plain integers (CUDA device addresses,
+e.g. ``torch.Tensor.data_ptr()``); nothing here depends on torch.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libaoclsparse_b200.so")
+
+# enum values: library/include/aoclsparse_types.h of the reference
+OP_N, OP_T, OP_H = 111, 112, 113
+GENERAL, SYMMETRIC, HERMITIAN, TRIANGULAR = 0, 1, 2, 3
+LOWER, UPPER = 0, 1
+NON_UNIT, UNIT, ZERO_DIAG = 0, 1, 2
+ROW_MAJOR, COL_MAJOR = 0, 1
+DMAT, SMAT, CMAT, ZMAT = 0, 1, 2, 3
+ST = dict(success=0, not_implemented=1, invalid_pointer=2, invalid_size=3, internal_error=4,
+          invalid_value=5, invalid_index_value=6, wrong_type=9, memory_error=10,
+          invalid_operation=12, invalid_kid=14)
+
+PREFIX = {np.dtype(np.float32): "s", np.dtype(np.float64): "d",
+          np.dtype(np.complex64): "c", np.dtype(np.complex128): "z"}
+VAL_TYPE = {"d": DMAT, "s": SMAT, "c": CMAT, "z": ZMAT}
+
+
+class FloatComplex(C.Structure):
+    _fields_ = [("real", C.c_float), ("imag", C.c_float)]
+
+
+class DoubleComplex(C.Structure):
+    _fields_ = [("real", C.c_double), ("imag", C.c_double)]
+
+
+class MatrixInfo(C.Structure):
+    """aoclsparse_b200_matrix_info (include/aoclsparse_b200.h)."""
+    _fields_ = [("m", C.c_int32), ("n", C.c_int32), ("nnz", C.c_int32), ("base", C.c_int),
+                ("val_type", C.c_int), ("sort", C.c_int), ("fulldiag", C.c_int),
+                ("min_col", C.c_int32), ("max_col", C.c_int32), ("max_row_nnz", C.c_int32),
+                ("optimized", C.c_int), ("n_hints", C.c_int), ("n_copies", C.c_int),
+                ("block_nnz", C.c_int32), ("block_rows", C.c_int32), ("n_blocks", C.c_int32),
+                ("n_thread_blocks", C.c_int32), ("n_warp_blocks", C.c_int32),
+                ("n_product_blocks", C.c_int32), ("n_long_segments", C.c_int32),
+                ("n_long_rows", C.c_int32)]
+
+
+def ptr(a):
+    """numpy array | int device address | None -> c_void_p"""
+    if a is None:
+        return C.c_void_p(None)
+    if isinstance(a, (int, np.integer)):
+        return C.c_void_p(int(a))
+    if isinstance(a, np.ndarray):
+        return C.c_void_p(a.ctypes.data)
+    if hasattr(a, "data_ptr"):  # torch tensor
+        return C.c_void_p(a.data_ptr())
+    raise TypeError(type(a))
+
+
+def _scalar_by_value(prefix, v):
+    if prefix == "s":
+        return C.c_float(v)
+    if prefix == "d":
+        return C.c_double(v)
+    v = complex(v)
+    return (FloatComplex if prefix == "c" else DoubleComplex)(v.real, v.imag)
+
+
+def _scalar_by_ref(prefix, v):
+    dt = {"s": np.float32, "d": np.float64, "c": np.complex64, "z": np.complex128}[prefix]
+    return np.array([v], dtype=dt)
+
+
+class AoclSparse:
+    def __init__(self, path=LIB_PATH):
+        if not os.path.exists(path):
+            raise FileNotFoundError(
+                f"{path} is missing: build it (python -c 'import __graft_entry__ as g; g.build()'); "
+                "there is no CPU fallback")
+        self.path = path
+        self.lib = C.CDLL(path)
+        L = self.lib
+        self.is_b200 = hasattr(L, "aoclsparse_b200_set_stream")
+        L.aoclsparse_get_version.restype = C.c_char_p
+        for name in ("aoclsparse_get_mat_index_base", "aoclsparse_get_mat_type",
+                     "aoclsparse_get_mat_fill_mode", "aoclsparse_get_mat_diag_type"):
+            getattr(L, name).restype = C.c_int
+            getattr(L, name).argtypes = [C.c_void_p]
+        vp, i32, ci = C.c_void_p, C.c_int32, C.c_int
+        for p in "sdcz":
+            getattr(L, f"aoclsparse_create_{p}csr").argtypes = [C.POINTER(vp), ci, i32, i32, i32, vp, vp, vp]
+            getattr(L, f"aoclsparse_{p}mv").argtypes = [ci, vp, vp, vp, vp, vp, vp]
+            getattr(L, f"aoclsparse_{p}update_values").argtypes = [vp, i32, vp]
+        L.aoclsparse_scsrmm.argtypes = [ci, C.c_float, vp, vp, ci, vp, i32, i32, C.c_float, vp, i32]
+        L.aoclsparse_dcsrmm.argtypes = [ci, C.c_double, vp, vp, ci, vp, i32, i32, C.c_double, vp, i32]
+        L.aoclsparse_ccsrmm.argtypes = [ci, FloatComplex, vp, vp, ci, vp, i32, i32, FloatComplex, vp, i32]
+        L.aoclsparse_zcsrmm.argtypes = [ci, DoubleComplex, vp, vp, ci, vp, i32, i32, DoubleComplex, vp, i32]
+        L.aoclsparse_scsrmm_kid.argtypes = L.aoclsparse_scsrmm.argtypes + [i32]
+        L.aoclsparse_dcsrmm_kid.argtypes = L.aoclsparse_dcsrmm.argtypes + [i32]
+        L.aoclsparse_ccsrmm_kid.argtypes = L.aoclsparse_ccsrmm.argtypes + [i32]
+        L.aoclsparse_zcsrmm_kid.argtypes = L.aoclsparse_zcsrmm.argtypes + [i32]
+        L.aoclsparse_create_mat_descr.argtypes = [C.POINTER(vp)]
+        L.aoclsparse_destroy_mat_descr.argtypes = [vp]
+        L.aoclsparse_copy_mat_descr.argtypes = [vp, vp]
+        for name in ("index_base", "type", "fill_mode", "diag_type"):
+            getattr(L, f"aoclsparse_set_mat_{name}").argtypes = [vp, ci]
+        L.aoclsparse_destroy.argtypes = [C.POINTER(vp)]
+        L.aoclsparse_optimize.argtypes = [vp]
+        L.aoclsparse_set_mv_hint.argtypes = [vp, ci, vp, i32]
+        L.aoclsparse_set_mv_hint_kid.argtypes = [vp, ci, vp, i32, i32]
+        L.aoclsparse_set_mm_hint.argtypes = [vp, ci, vp, i32]
+        L.aoclsparse_set_memory_hint.argtypes = [vp, ci]
+        L.aoclsparse_spmm.argtypes = [ci, vp, vp, C.POINTER(vp)]
+        if self.is_b200:
+            L.aoclsparse_b200_set_stream.argtypes = [vp]
+            L.aoclsparse_b200_get_stream.restype = vp
+            L.aoclsparse_b200_last_error.restype = C.c_char_p
+            L.aoclsparse_b200_launch_count.restype = C.c_ulonglong
+            L.aoclsparse_b200_get_matrix_info.argtypes = [vp, C.POINTER(MatrixInfo)]
+            L.aoclsparse_b200_get_plan.argtypes = [vp, i32, vp, vp, C.POINTER(i32)]
+            L.aoclsparse_b200_doid.argtypes = [vp, ci, ci]
+            L.aoclsparse_b200_set_x_window.argtypes = [vp, i32, i32]
+            L.aoclsparse_b200_set_row_cuts.argtypes = [vp, i32, vp]
+            L.aoclsparse_b200_dmv_rows.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32]
+            L.aoclsparse_b200_smv_rows.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32]
+            L.aoclsparse_b200_gen_stencil.argtypes = [ci, i32, i32, i32, C.c_longlong, C.c_longlong,
+                                                      C.POINTER(C.c_longlong), vp, vp, vp]
+            L.aoclsparse_b200_gen_uniform.argtypes = [C.c_ulonglong, C.c_longlong, C.c_longlong, ci, vp]
+            L.aoclsparse_b200_gen_rmat_keys.argtypes = [C.c_ulonglong, ci, C.c_longlong, C.c_longlong, vp]
+            L.aoclsparse_b200_rmat_keys_to_csr.argtypes = [C.c_ulonglong, ci, C.c_longlong, vp, vp, vp, vp]
+
+    # ---- descriptor -------------------------------------------------------------------
+    def create_descr(self, mtype=GENERAL, fill=LOWER, diag=NON_UNIT, base=0):
+        d = C.c_void_p()
+        st = self.lib.aoclsparse_create_mat_descr(C.byref(d))
+        assert st == 0, st
+        assert self.lib.aoclsparse_set_mat_type(d, mtype) == 0
+        assert self.lib.aoclsparse_set_mat_fill_mode(d, fill) == 0
+        assert self.lib.aoclsparse_set_mat_diag_type(d, diag) == 0
+        assert self.lib.aoclsparse_set_mat_index_base(d, base) == 0
+        return d
+
+    def destroy_descr(self, d):
+        return self.lib.aoclsparse_destroy_mat_descr(d)
+
+    # ---- matrix -----------------------------------------------------------------------
+    def create_csr(self, prefix, base, m, n, nnz, row_ptr, col_idx, val):
+        """returns (status, handle).  Arrays: numpy (host) or int (device address)."""
+        h = C.c_void_p()
+        st = getattr(self.lib, f"aoclsparse_create_{prefix}csr")(
+            C.byref(h), base, m, n, nnz, ptr(row_ptr), ptr(col_idx), ptr(val))
+        return st, h
+
+    def destroy(self, h):
+        return self.lib.aoclsparse_destroy(C.byref(h))
+
+    def update_values(self, prefix, h, length, val):
+        return getattr(self.lib, f"aoclsparse_{prefix}update_values")(h, length, ptr(val))
+
+    def set_mv_hint(self, h, op, descr, calls):
+        return self.lib.aoclsparse_set_mv_hint(h, op, descr, calls)
+
+    def set_mv_hint_kid(self, h, op, descr, calls, kid):
+        return self.lib.aoclsparse_set_mv_hint_kid(h, op, descr, calls, kid)
+
+    def set_mm_hint(self, h, op, descr, calls):
+        return self.lib.aoclsparse_set_mm_hint(h, op, descr, calls)
+
+    def set_memory_hint(self, h, policy):
+        return self.lib.aoclsparse_set_memory_hint(h, policy)
+
+    def optimize(self, h):
+        return self.lib.aoclsparse_optimize(h)
+
+    # ---- multiply ---------------------------------------------------------------------
+    def mv(self, prefix, op, alpha, h, descr, x, beta, y):
+        a = _scalar_by_ref(prefix, alpha)
+        b = _scalar_by_ref(prefix, beta)
+        return getattr(self.lib, f"aoclsparse_{prefix}mv")(op, ptr(a), h, descr, ptr(x), ptr(b), ptr(y))
+
+    def csrmm(self, prefix, op, alpha, h, descr, order, B, n, ldb, beta, Cm, ldc, kid=None):
+        a = _scalar_by_value(prefix, alpha)
+        b = _scalar_by_value(prefix, beta)
+        if kid is None:
+            return getattr(self.lib, f"aoclsparse_{prefix}csrmm")(
+                op, a, h, descr, order, ptr(B), n, ldb, b, ptr(Cm), ldc)
+        return getattr(self.lib, f"aoclsparse_{prefix}csrmm_kid")(
+            op, a, h, descr, order, ptr(B), n, ldb, b, ptr(Cm), ldc, kid)
+
+    def spmm(self, op, a, b):
+        c = C.c_void_p()
+        return self.lib.aoclsparse_spmm(op, a, b, C.byref(c)), c
+
+    def version(self):
+        return self.lib.aoclsparse_get_version().decode()
+
+    # ---- b200 extensions ----------------------------------------------------------------
+    def set_stream(self, stream_ptr):
+        return self.lib.aoclsparse_b200_set_stream(C.c_void_p(stream_ptr))
+
+    def last_error(self):
+        return self.lib.aoclsparse_b200_last_error().decode()
+
+    def launch_count(self):
+        return int(self.lib.aoclsparse_b200_launch_count())
+
+    def matrix_info(self, h):
+        info = MatrixInfo()
+        st = self.lib.aoclsparse_b200_get_matrix_info(h, C.byref(info))
+        assert st == 0, st
+        return info
+
+    def get_plan(self, h):
+        n = C.c_int32(0)
+        st = self.lib.aoclsparse_b200_get_plan(h, 0, None, None, C.byref(n))
+        assert st == 0, st
+        desc = np.zeros((max(n.value, 1), 4), dtype=np.int32)
+        kind = np.zeros(max(n.value, 1), dtype=np.int32)
+        st = self.lib.aoclsparse_b200_get_plan(h, n.value, ptr(desc), ptr(kind), C.byref(n))
+        assert st == 0, st
+        return desc[: n.value], kind[: n.value]
+
+    def doid(self, descr, op, val_type):
+        return self.lib.aoclsparse_b200_doid(descr, op, val_type)
+
+    def set_x_window(self, h, lo, hi):
+        return self.lib.aoclsparse_b200_set_x_window(h, lo, hi)
+
+    def set_row_cuts(self, h, cuts):
+        cuts = np.ascontiguousarray(cuts, dtype=np.int32)
+        return self.lib.aoclsparse_b200_set_row_cuts(h, len(cuts), ptr(cuts))
+
+    def mv_rows(self, prefix, alpha, h, descr, x, beta, y, r0, r1):
+        a = _scalar_by_ref(prefix, alpha)
+        b = _scalar_by_ref(prefix, beta)
+        return getattr(self.lib, f"aoclsparse_b200_{prefix}mv_rows")(ptr(a), h, descr, ptr(x), ptr(b), ptr(y), r0, r1)

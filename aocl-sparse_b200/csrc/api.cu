@@ -1,0 +1,673 @@
+// api.cu -- handles, descriptors, hints, aoclsparse_optimize and the read-back extensions.
+//
+// Reference counterparts:
+//   descriptor functions   library/src/extra/aoclsparse_auxiliary.cpp:191-362
+//   create_csr<T>          library/src/create/aoclsparse_create.cpp:33-95
+//   aoclsparse_destroy     library/src/extra/aoclsparse_auxiliary.cpp:657-670
+//   set_hint / optimize    library/src/analysis/aoclsparse_analysis.cpp:426-747
+//   update_values          library/src/extra/aoclsparse_auxiliary.hpp:215-272
+//   get_doid               library/src/include/aoclsparse_mtx_dispatcher.hpp:79-143
+#include "common.hpp"
+
+#include <new>
+#include <string>
+
+namespace b200
+{
+    std::atomic<unsigned long long> g_launches{0};
+
+    namespace
+    {
+        thread_local cudaStream_t tl_stream = nullptr;
+        thread_local std::string  tl_error;
+    }
+
+    cudaStream_t current_stream()
+    {
+        return tl_stream;
+    }
+
+    void note_cuda_error(cudaError_t e, const char *where)
+    {
+        tl_error = std::string(cudaGetErrorName(e)) + ": " + cudaGetErrorString(e) + " @ " + where;
+        cudaGetLastError(); // clear the sticky-less error so later calls are judged on their own
+    }
+
+    bool is_device_accessible(const void *p)
+    {
+        cudaPointerAttributes at;
+        cudaError_t           e = cudaPointerGetAttributes(&at, p);
+        if(e != cudaSuccess)
+        {
+            cudaGetLastError();
+            return false;
+        }
+        return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+    }
+
+    // Same table as aoclsparse::get_doid<T>: [group:3][op:2], op bits 0 = conjugate, 1 = transpose
+    // (for symmetric / hermitian bit 1 = upper triangle).
+    int get_doid(bool complex_type, int descr_type, int fill_mode, int op)
+    {
+        int op_v = op - 111; // 0 none, 1 transpose, 2 conjugate transpose
+        if(op_v < 0 || op_v > 2)
+            return DOID_LEN;
+        int t = descr_type;
+        if(!complex_type)
+        {
+            if(op_v == 2)
+                op_v = 1;
+            if(t == aoclsparse_matrix_type_hermitian)
+                t = aoclsparse_matrix_type_symmetric;
+        }
+        if(t == aoclsparse_matrix_type_symmetric && op_v == 1)
+            op_v = 0;
+        else if(t == aoclsparse_matrix_type_hermitian && op_v == 2)
+            op_v = 0;
+        static const int op_bits[3] = {0, 2, 3};
+        switch(t)
+        {
+        case aoclsparse_matrix_type_general:
+            return op_bits[op_v];
+        case aoclsparse_matrix_type_symmetric:
+            return 4 + 2 * fill_mode + (op_v >> 1);
+        case aoclsparse_matrix_type_hermitian:
+            return 8 + 2 * fill_mode + (op_v ^ fill_mode);
+        case aoclsparse_matrix_type_triangular:
+            return 12 + 4 * fill_mode + op_bits[op_v];
+        default:
+            return DOID_LEN;
+        }
+    }
+
+    aoclsparse_status ensure_plan(aoclsparse_matrix A, cudaStream_t st)
+    {
+        {
+            std::shared_lock<std::shared_mutex> rl(A->guard);
+            if(A->mats[0]->plan.valid)
+                return aoclsparse_status_success;
+        }
+        std::unique_lock<std::shared_mutex> wl(A->guard);
+        if(A->mats[0]->plan.valid)
+            return aoclsparse_status_success;
+        return build_plan(*A->mats[0], value_size(A->val_type), -1, A->row_cuts, st);
+    }
+
+    namespace
+    {
+        // copies `bytes` from a host or device source into device memory on `st`
+        aoclsparse_status upload(void *dst, const void *src, size_t bytes, cudaStream_t st)
+        {
+            if(bytes == 0)
+                return aoclsparse_status_success;
+            B200_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, st));
+            return aoclsparse_status_success;
+        }
+
+        aoclsparse_status fetch_int(const aoclsparse_int *src, aoclsparse_int &out, cudaStream_t st)
+        {
+            if(is_device_accessible(src))
+            {
+                B200_CUDA(cudaMemcpyAsync(&out, src, sizeof(out), cudaMemcpyDeviceToHost, st));
+                B200_CUDA(cudaStreamSynchronize(st));
+            }
+            else
+                out = *src;
+            return aoclsparse_status_success;
+        }
+
+        template <typename T>
+        aoclsparse_status create_csr(aoclsparse_matrix    *mat,
+                                     aoclsparse_index_base base,
+                                     aoclsparse_int        M,
+                                     aoclsparse_int        N,
+                                     aoclsparse_int        nnz,
+                                     aoclsparse_int       *row_ptr,
+                                     aoclsparse_int       *col_idx,
+                                     void                 *val,
+                                     int                   val_type)
+        {
+            if(!mat)
+                return aoclsparse_status_invalid_pointer;
+            *mat = nullptr;
+            if(row_ptr == nullptr || col_idx == nullptr || val == nullptr)
+                return aoclsparse_status_invalid_pointer;
+            if(M < 0 || N < 0 || nnz < 0)
+                return aoclsparse_status_invalid_size;
+
+            cudaStream_t   st = current_stream();
+            aoclsparse_int first = 0, last = 0;
+            B200_TRY(fetch_int(row_ptr, first, st));
+            if(first - (aoclsparse_int)base != 0)
+                return aoclsparse_status_invalid_value;
+            B200_TRY(fetch_int(row_ptr + M, last, st));
+            if(last - (aoclsparse_int)base != nnz)
+                return aoclsparse_status_invalid_value;
+
+            _aoclsparse_matrix *A = new(std::nothrow) _aoclsparse_matrix;
+            b200::dev_csr      *C = new(std::nothrow) b200::dev_csr;
+            if(!A || !C)
+            {
+                delete A;
+                delete C;
+                return aoclsparse_status_memory_error;
+            }
+            A->mats.push_back(C);
+            auto fail = [&](aoclsparse_status s) {
+                delete A;
+                return s;
+            };
+            aoclsparse_status s;
+            if((s = C->row_ptr.alloc(sizeof(aoclsparse_int) * ((size_t)M + 1))) != aoclsparse_status_success)
+                return fail(s);
+            if((s = C->col_idx.alloc(sizeof(aoclsparse_int) * (size_t)nnz)) != aoclsparse_status_success)
+                return fail(s);
+            if((s = C->val.alloc(sizeof(T) * (size_t)nnz)) != aoclsparse_status_success)
+                return fail(s);
+            if((s = upload(C->row_ptr.p, row_ptr, sizeof(aoclsparse_int) * ((size_t)M + 1), st)) != aoclsparse_status_success)
+                return fail(s);
+            if((s = upload(C->col_idx.p, col_idx, sizeof(aoclsparse_int) * (size_t)nnz, st)) != aoclsparse_status_success)
+                return fail(s);
+            if((s = upload(C->val.p, val, sizeof(T) * (size_t)nnz, st)) != aoclsparse_status_success)
+                return fail(s);
+
+            b200::check_result cr;
+            if((s = b200::check_csr_device(
+                    M, N, nnz, (int)base, C->row_ptr.as<aoclsparse_int>(), C->col_idx.as<aoclsparse_int>(), cr, st))
+               != aoclsparse_status_success)
+                return fail(s);
+            if(cr.status != aoclsparse_status_success)
+                return fail(cr.status);
+            if(base == aoclsparse_index_base_one)
+            {
+                if((s = b200::rebase_to_zero(M, nnz, C->row_ptr.as<aoclsparse_int>(), C->col_idx.as<aoclsparse_int>(), st))
+                   != aoclsparse_status_success)
+                    return fail(s);
+            }
+            // the caller may free its arrays as soon as we return
+            cudaError_t e = cudaStreamSynchronize(st);
+            if(e != cudaSuccess)
+                return fail(b200::cuda_status(e, "create sync"));
+
+            C->m = M;
+            C->n = N;
+            C->nnz = nnz;
+            C->doid = b200::DOID_GN;
+            A->m = M;
+            A->n = N;
+            A->nnz = nnz;
+            A->base = base;
+            A->val_type = (aoclsparse_matrix_data_type)val_type;
+            A->input_format = aoclsparse_csr_mat;
+            A->sort = (aoclsparse_matrix_sort)cr.sort;
+            A->fulldiag = cr.fulldiag != 0;
+            A->min_col = cr.min_col;
+            A->max_col = cr.max_col;
+            A->max_row_nnz = cr.max_row_nnz;
+            cudaGetDevice(&A->device);
+            *mat = A;
+            return aoclsparse_status_success;
+        }
+
+        template <typename T>
+        aoclsparse_status update_values(aoclsparse_matrix A, aoclsparse_int len, const void *val)
+        {
+            if(A == nullptr || val == nullptr)
+                return aoclsparse_status_invalid_pointer;
+            if(A->mats.empty() || A->mats[0] == nullptr)
+                return aoclsparse_status_invalid_pointer;
+            if(len != A->nnz)
+                return aoclsparse_status_invalid_size;
+            if(A->val_type != b200::vt<T>::data_type)
+                return aoclsparse_status_wrong_type;
+            cudaStream_t                        st = current_stream();
+            std::unique_lock<std::shared_mutex> wl(A->guard);
+            B200_TRY(upload(A->mats[0]->val.p, val, sizeof(T) * (size_t)len, st));
+            B200_CUDA(cudaStreamSynchronize(st));
+            // derived copies hold stale values: drop them (the reference does the same,
+            // aoclsparse_auxiliary.hpp:260-272); the row-block plan depends on the pattern only and stays
+            for(size_t i = 1; i < A->mats.size(); ++i)
+                delete A->mats[i];
+            A->mats.resize(1);
+            for(auto &h : A->hints)
+                h.done = false;
+            return aoclsparse_status_success;
+        }
+
+        aoclsparse_status set_hint(aoclsparse_matrix          mat,
+                                   int                        act,
+                                   aoclsparse_operation       trans,
+                                   const aoclsparse_mat_descr descr,
+                                   aoclsparse_int             calls,
+                                   aoclsparse_int             kid)
+        {
+            if(!mat || mat->mats.empty() || mat->mats[0] == nullptr || descr == nullptr)
+                return aoclsparse_status_invalid_pointer;
+            if(descr->base != aoclsparse_index_base_zero && descr->base != aoclsparse_index_base_one)
+                return aoclsparse_status_invalid_value;
+            if(descr->base != mat->base)
+                return aoclsparse_status_invalid_value;
+            if(trans != aoclsparse_operation_none && trans != aoclsparse_operation_transpose
+               && trans != aoclsparse_operation_conjugate_transpose)
+                return aoclsparse_status_invalid_value;
+            if(descr->fill_mode != aoclsparse_fill_mode_lower && descr->fill_mode != aoclsparse_fill_mode_upper)
+                return aoclsparse_status_invalid_value;
+            if(descr->diag_type != aoclsparse_diag_type_non_unit && descr->diag_type != aoclsparse_diag_type_unit
+               && descr->diag_type != aoclsparse_diag_type_zero)
+                return aoclsparse_status_invalid_value;
+            if(descr->type != aoclsparse_matrix_type_general && descr->type != aoclsparse_matrix_type_symmetric
+               && descr->type != aoclsparse_matrix_type_triangular && descr->type != aoclsparse_matrix_type_hermitian)
+                return aoclsparse_status_invalid_value;
+            if(calls < 0 || (calls == 0 && kid == -1))
+                return aoclsparse_status_invalid_value;
+            b200::hint h;
+            h.act       = act;
+            h.trans     = trans;
+            h.type      = descr->type;
+            h.fill_mode = descr->fill_mode;
+            h.nop       = calls;
+            h.kid       = kid;
+            const bool cplx = mat->val_type == aoclsparse_cmat || mat->val_type == aoclsparse_zmat;
+            h.doid      = b200::get_doid(cplx, descr->type, descr->fill_mode, trans);
+            std::unique_lock<std::shared_mutex> wl(mat->guard);
+            mat->hints.insert(mat->hints.begin(), h);
+            return aoclsparse_status_success;
+        }
+    }
+}
+
+using namespace b200;
+
+extern "C" {
+
+const char *aoclsparse_get_version(void)
+{
+    return "AOCL-Sparse 5.3.2 (b200-native CSR SpMV/SpMM path, sm_100a)";
+}
+
+aoclsparse_status aoclsparse_b200_set_stream(void *cuda_stream)
+{
+    tl_stream = static_cast<cudaStream_t>(cuda_stream);
+    return aoclsparse_status_success;
+}
+
+void *aoclsparse_b200_get_stream(void)
+{
+    return tl_stream;
+}
+
+const char *aoclsparse_b200_last_error(void)
+{
+    return tl_error.c_str();
+}
+
+unsigned long long aoclsparse_b200_launch_count(void)
+{
+    return g_launches.load();
+}
+
+// ------------------------------------------------------------------ descriptor
+aoclsparse_status aoclsparse_create_mat_descr(aoclsparse_mat_descr *descr)
+{
+    if(descr == nullptr)
+        return aoclsparse_status_invalid_pointer;
+    *descr = new(std::nothrow) _aoclsparse_mat_descr;
+    return *descr ? aoclsparse_status_success : aoclsparse_status_memory_error;
+}
+
+aoclsparse_status aoclsparse_copy_mat_descr(aoclsparse_mat_descr dest, const aoclsparse_mat_descr src)
+{
+    if(dest == nullptr || src == nullptr)
+        return aoclsparse_status_invalid_pointer;
+    *dest = *src;
+    return aoclsparse_status_success;
+}
+
+aoclsparse_status aoclsparse_destroy_mat_descr(aoclsparse_mat_descr descr)
+{
+    delete descr;
+    return aoclsparse_status_success;
+}
+
+aoclsparse_status aoclsparse_set_mat_index_base(aoclsparse_mat_descr descr, aoclsparse_index_base base)
+{
+    if(descr == nullptr)
+        return aoclsparse_status_invalid_pointer;
+    if(base != aoclsparse_index_base_zero && base != aoclsparse_index_base_one)
+        return aoclsparse_status_invalid_value;
+    descr->base = base;
+    return aoclsparse_status_success;
+}
+
+aoclsparse_index_base aoclsparse_get_mat_index_base(const aoclsparse_mat_descr descr)
+{
+    return descr ? descr->base : aoclsparse_index_base_zero;
+}
+
+aoclsparse_status aoclsparse_set_mat_type(aoclsparse_mat_descr descr, aoclsparse_matrix_type type)
+{
+    if(descr == nullptr)
+        return aoclsparse_status_invalid_pointer;
+    if(type != aoclsparse_matrix_type_general && type != aoclsparse_matrix_type_symmetric
+       && type != aoclsparse_matrix_type_hermitian && type != aoclsparse_matrix_type_triangular)
+        return aoclsparse_status_invalid_value;
+    descr->type = type;
+    return aoclsparse_status_success;
+}
+
+aoclsparse_matrix_type aoclsparse_get_mat_type(const aoclsparse_mat_descr descr)
+{
+    return descr ? descr->type : aoclsparse_matrix_type_general;
+}
+
+aoclsparse_status aoclsparse_set_mat_fill_mode(aoclsparse_mat_descr descr, aoclsparse_fill_mode fill_mode)
+{
+    if(descr == nullptr)
+        return aoclsparse_status_invalid_pointer;
+    if(fill_mode != aoclsparse_fill_mode_lower && fill_mode != aoclsparse_fill_mode_upper)
+        return aoclsparse_status_invalid_value;
+    descr->fill_mode = fill_mode;
+    return aoclsparse_status_success;
+}
+
+aoclsparse_fill_mode aoclsparse_get_mat_fill_mode(const aoclsparse_mat_descr descr)
+{
+    return descr ? descr->fill_mode : aoclsparse_fill_mode_lower;
+}
+
+aoclsparse_status aoclsparse_set_mat_diag_type(aoclsparse_mat_descr descr, aoclsparse_diag_type diag_type)
+{
+    if(descr == nullptr)
+        return aoclsparse_status_invalid_pointer;
+    if(diag_type != aoclsparse_diag_type_unit && diag_type != aoclsparse_diag_type_non_unit
+       && diag_type != aoclsparse_diag_type_zero)
+        return aoclsparse_status_invalid_value;
+    descr->diag_type = diag_type;
+    return aoclsparse_status_success;
+}
+
+aoclsparse_diag_type aoclsparse_get_mat_diag_type(const aoclsparse_mat_descr descr)
+{
+    return descr ? descr->diag_type : aoclsparse_diag_type_non_unit;
+}
+
+// ------------------------------------------------------------------ matrix handle
+aoclsparse_status aoclsparse_create_scsr(aoclsparse_matrix    *mat,
+                                         aoclsparse_index_base base,
+                                         aoclsparse_int        M,
+                                         aoclsparse_int        N,
+                                         aoclsparse_int        nnz,
+                                         aoclsparse_int       *row_ptr,
+                                         aoclsparse_int       *col_idx,
+                                         float                *val)
+{
+    return create_csr<float>(mat, base, M, N, nnz, row_ptr, col_idx, val, aoclsparse_smat);
+}
+aoclsparse_status aoclsparse_create_dcsr(aoclsparse_matrix    *mat,
+                                         aoclsparse_index_base base,
+                                         aoclsparse_int        M,
+                                         aoclsparse_int        N,
+                                         aoclsparse_int        nnz,
+                                         aoclsparse_int       *row_ptr,
+                                         aoclsparse_int       *col_idx,
+                                         double               *val)
+{
+    return create_csr<double>(mat, base, M, N, nnz, row_ptr, col_idx, val, aoclsparse_dmat);
+}
+aoclsparse_status aoclsparse_create_ccsr(aoclsparse_matrix        *mat,
+                                         aoclsparse_index_base     base,
+                                         aoclsparse_int            M,
+                                         aoclsparse_int            N,
+                                         aoclsparse_int            nnz,
+                                         aoclsparse_int           *row_ptr,
+                                         aoclsparse_int           *col_idx,
+                                         aoclsparse_float_complex *val)
+{
+    return create_csr<float2>(mat, base, M, N, nnz, row_ptr, col_idx, val, aoclsparse_cmat);
+}
+aoclsparse_status aoclsparse_create_zcsr(aoclsparse_matrix         *mat,
+                                         aoclsparse_index_base      base,
+                                         aoclsparse_int             M,
+                                         aoclsparse_int             N,
+                                         aoclsparse_int             nnz,
+                                         aoclsparse_int            *row_ptr,
+                                         aoclsparse_int            *col_idx,
+                                         aoclsparse_double_complex *val)
+{
+    return create_csr<double2>(mat, base, M, N, nnz, row_ptr, col_idx, val, aoclsparse_zmat);
+}
+
+aoclsparse_status aoclsparse_destroy(aoclsparse_matrix *mat)
+{
+    if(mat && *mat)
+    {
+        delete *mat;
+        *mat = nullptr;
+    }
+    return aoclsparse_status_success;
+}
+
+aoclsparse_status aoclsparse_supdate_values(aoclsparse_matrix A, aoclsparse_int len, float *val)
+{
+    return update_values<float>(A, len, val);
+}
+aoclsparse_status aoclsparse_dupdate_values(aoclsparse_matrix A, aoclsparse_int len, double *val)
+{
+    return update_values<double>(A, len, val);
+}
+aoclsparse_status aoclsparse_cupdate_values(aoclsparse_matrix A, aoclsparse_int len, aoclsparse_float_complex *val)
+{
+    return update_values<float2>(A, len, val);
+}
+aoclsparse_status aoclsparse_zupdate_values(aoclsparse_matrix A, aoclsparse_int len, aoclsparse_double_complex *val)
+{
+    return update_values<double2>(A, len, val);
+}
+
+// ------------------------------------------------------------------ hints + optimize
+aoclsparse_status aoclsparse_set_mv_hint(aoclsparse_matrix          mat,
+                                         aoclsparse_operation       trans,
+                                         const aoclsparse_mat_descr descr,
+                                         aoclsparse_int             expected_no_of_calls)
+{
+    return set_hint(mat, 1, trans, descr, expected_no_of_calls, -1);
+}
+aoclsparse_status aoclsparse_set_mv_hint_kid(aoclsparse_matrix          mat,
+                                             aoclsparse_operation       trans,
+                                             const aoclsparse_mat_descr descr,
+                                             aoclsparse_int             expected_no_of_calls,
+                                             aoclsparse_int             kid)
+{
+    return set_hint(mat, 1, trans, descr, expected_no_of_calls, kid);
+}
+aoclsparse_status aoclsparse_set_mm_hint(aoclsparse_matrix          mat,
+                                         aoclsparse_operation       trans,
+                                         const aoclsparse_mat_descr descr,
+                                         aoclsparse_int             expected_no_of_calls)
+{
+    return set_hint(mat, 3, trans, descr, expected_no_of_calls, -1);
+}
+aoclsparse_status aoclsparse_set_memory_hint(aoclsparse_matrix mat, const aoclsparse_memory_usage policy)
+{
+    if(mat == nullptr)
+        return aoclsparse_status_invalid_pointer;
+    if(policy != aoclsparse_memory_usage_minimal && policy != aoclsparse_memory_usage_unrestricted)
+        return aoclsparse_status_invalid_value;
+    mat->mem_policy = policy;
+    return aoclsparse_status_success;
+}
+
+aoclsparse_status aoclsparse_optimize(aoclsparse_matrix A)
+{
+    if(!A)
+        return aoclsparse_status_invalid_pointer;
+    if(A->m < 0 || A->n < 0 || A->nnz < 0)
+        return aoclsparse_status_invalid_size;
+    if(A->mats.empty() || A->mats[0] == nullptr)
+        return aoclsparse_status_invalid_pointer;
+    cudaStream_t                        st = current_stream();
+    std::unique_lock<std::shared_mutex> wl(A->guard);
+    dev_csr                            &M = *A->mats[0];
+
+    // a kid >= 0 on a plain general mv hint forces the row strategy of every block
+    aoclsparse_int forced = -1;
+    for(const hint &h : A->hints)
+        if(h.act == 1 && h.doid == DOID_GN && h.kid >= 0 && h.kid <= 2)
+        {
+            forced = h.kid;
+            break;
+        }
+    if(!M.plan.valid || forced >= 0)
+        B200_TRY(build_plan(M, value_size(A->val_type), forced, A->row_cuts, st));
+
+    // transposed device copies for general transposed mv / mm hints (memory policy permitting):
+    // they turn the atomic scatter into a streaming gather
+    if(A->mem_policy == aoclsparse_memory_usage_unrestricted && A->win_hi < 0)
+    {
+        for(hint &h : A->hints)
+        {
+            if(h.done)
+                continue;
+            if((h.act == 1 || h.act == 3) && (h.doid == DOID_GT || h.doid == DOID_GH))
+            {
+                bool have = false;
+                for(size_t i = 1; i < A->mats.size(); ++i)
+                    have = have || A->mats[i]->doid == h.doid;
+                if(!have)
+                {
+                    dev_csr *C = new(std::nothrow) dev_csr;
+                    if(!C)
+                        return aoclsparse_status_memory_error;
+                    aoclsparse_status s = transpose_csr(M, A->val_type, h.doid == DOID_GH, *C, st);
+                    if(s == aoclsparse_status_success)
+                        s = build_plan(*C, value_size(A->val_type), -1, std::vector<aoclsparse_int>(), st);
+                    if(s != aoclsparse_status_success)
+                    {
+                        delete C;
+                        return s;
+                    }
+                    C->doid = h.doid;
+                    A->mats.push_back(C);
+                }
+            }
+            h.done = true;
+        }
+    }
+    B200_CUDA(cudaStreamSynchronize(st));
+    return aoclsparse_status_success;
+}
+
+// ------------------------------------------------------------------ read-back extensions
+aoclsparse_status aoclsparse_b200_get_matrix_info(const aoclsparse_matrix A, aoclsparse_b200_matrix_info *info)
+{
+    if(!A || !info)
+        return aoclsparse_status_invalid_pointer;
+    std::shared_lock<std::shared_mutex> rl(A->guard);
+    memset(info, 0, sizeof(*info));
+    info->m           = A->m;
+    info->n           = A->n;
+    info->nnz         = A->nnz;
+    info->base        = A->base;
+    info->val_type    = A->val_type;
+    info->sort        = A->sort;
+    info->fulldiag    = A->fulldiag ? 1 : 0;
+    info->min_col     = A->min_col;
+    info->max_col     = A->max_col;
+    info->max_row_nnz = A->max_row_nnz;
+    info->n_hints     = (int)A->hints.size();
+    info->n_copies    = (int)A->mats.size();
+    const row_block_plan &P = A->mats[0]->plan;
+    info->optimized         = P.valid ? 1 : 0;
+    if(P.valid)
+    {
+        info->block_nnz        = P.block_nnz;
+        info->block_rows       = P.block_rows;
+        info->n_blocks         = P.n_blocks;
+        info->n_thread_blocks  = P.n_strat[STRAT_THREAD];
+        info->n_warp_blocks    = P.n_strat[STRAT_WARP];
+        info->n_product_blocks = P.n_strat[STRAT_PRODUCT];
+        info->n_long_segments  = P.n_long_segments;
+        info->n_long_rows      = P.n_long_rows;
+    }
+    return aoclsparse_status_success;
+}
+
+aoclsparse_status aoclsparse_b200_get_plan(const aoclsparse_matrix A,
+                                           aoclsparse_int          capacity,
+                                           aoclsparse_int         *block_desc,
+                                           aoclsparse_int         *block_kind,
+                                           aoclsparse_int         *n_blocks)
+{
+    if(!A || !n_blocks)
+        return aoclsparse_status_invalid_pointer;
+    std::shared_lock<std::shared_mutex> rl(A->guard);
+    const row_block_plan               &P = A->mats[0]->plan;
+    if(!P.valid)
+        return aoclsparse_status_invalid_operation;
+    *n_blocks = P.n_blocks;
+    if(capacity < P.n_blocks)
+        return (block_desc || block_kind) ? aoclsparse_status_invalid_size : aoclsparse_status_success;
+    cudaStream_t st = current_stream();
+    if(block_desc && P.n_blocks > 0)
+        B200_CUDA(cudaMemcpyAsync(block_desc, P.desc.p, sizeof(int4) * (size_t)P.n_blocks, cudaMemcpyDeviceToHost, st));
+    if(block_kind && P.n_blocks > 0)
+        B200_CUDA(cudaMemcpyAsync(block_kind, P.kind.p, sizeof(int) * (size_t)P.n_blocks, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    return aoclsparse_status_success;
+}
+
+int aoclsparse_b200_doid(const aoclsparse_mat_descr descr, aoclsparse_operation op, int val_type)
+{
+    if(!descr)
+        return DOID_LEN;
+    const bool cplx = val_type == aoclsparse_cmat || val_type == aoclsparse_zmat;
+    return get_doid(cplx, descr->type, descr->fill_mode, op);
+}
+
+aoclsparse_status aoclsparse_b200_set_x_window(aoclsparse_matrix A, aoclsparse_int col_lo, aoclsparse_int col_hi)
+{
+    if(!A)
+        return aoclsparse_status_invalid_pointer;
+    if(col_lo < 0 || col_hi > A->n || col_lo > col_hi)
+        return aoclsparse_status_invalid_size;
+    std::unique_lock<std::shared_mutex> wl(A->guard);
+    if(col_lo == 0 && col_hi == A->n)
+    {
+        A->win_lo = 0;
+        A->win_hi = -1;
+        return aoclsparse_status_success;
+    }
+    if(A->nnz > 0 && (A->min_col < col_lo || A->max_col >= col_hi))
+        return aoclsparse_status_invalid_index_value;
+    A->win_lo = col_lo;
+    A->win_hi = col_hi;
+    return aoclsparse_status_success;
+}
+
+aoclsparse_status aoclsparse_b200_set_row_cuts(aoclsparse_matrix A, aoclsparse_int n_cuts, const aoclsparse_int *cuts)
+{
+    if(!A || (n_cuts > 0 && !cuts))
+        return aoclsparse_status_invalid_pointer;
+    if(n_cuts < 0)
+        return aoclsparse_status_invalid_size;
+    for(aoclsparse_int i = 0; i < n_cuts; ++i)
+        if(cuts[i] <= 0 || cuts[i] >= A->m || (i > 0 && cuts[i] <= cuts[i - 1]))
+            return aoclsparse_status_invalid_value;
+    std::unique_lock<std::shared_mutex> wl(A->guard);
+    A->row_cuts.assign(cuts, cuts + n_cuts);
+    A->mats[0]->plan.valid = false;
+    return aoclsparse_status_success;
+}
+
+// aoclsparse_spmm is sparse x sparse in the reference (library/src/level3/aoclsparse_spmm.cpp:27-67);
+// validation as there, computation not provided by this library.
+aoclsparse_status aoclsparse_spmm(aoclsparse_operation opA, const aoclsparse_matrix A, const aoclsparse_matrix B, aoclsparse_matrix *C)
+{
+    (void)opA;
+    if(A == nullptr || B == nullptr || C == nullptr)
+        return aoclsparse_status_invalid_pointer;
+    if(A->val_type != B->val_type)
+        return aoclsparse_status_wrong_type;
+    return aoclsparse_status_not_implemented;
+}
+}

@@ -1,0 +1,299 @@
+// plan.cu -- the GPU analysis pass behind aoclsparse_optimize (and behind the first multiply of a
+// matrix that was never optimised).
+//
+// The reference's aoclsparse_optimize (library/src/analysis/aoclsparse_analysis.cpp:426-566) picks
+// one of several CPU storage formats (blocked CSR, "br4", ELL-T hybrid).  None of that carries over.
+// What a B200 needs from the analysis is a way to give every CTA the same number of bytes to stream
+// no matter how skewed the row lengths are, and to know per CTA how its rows should be reduced.
+//
+// SPEC (tests/ and oracle/csr_oracle.c restate exactly this, and must agree bit for bit):
+//   T = block_nnz, R = block_rows (plan_parameters below), S = 64*T.
+//   Segment boundaries: row 0, row m, every forced row cut, and for k = 1.. the smallest row r with
+//   row_ptr[r] >= k*S.  Sorted, duplicates removed.
+//   Inside a segment [sa, sb), starting at r = sa and until r == sb:
+//     len = row_ptr[r+1]-row_ptr[r]
+//     if len > T: the row is LONG; emit ceil(len/T) blocks, block q covering entries
+//                 [row_ptr[r]+q*T, min(row_ptr[r]+(q+1)*T, row_ptr[r+1])); r += 1
+//     else      : r1 = largest row in (r, min(sb, r+R)] with row_ptr[r1]-row_ptr[r] <= T;
+//                 emit block rows [r, r1); r = r1
+//   Strategy of a non-LONG block with nr rows, nz entries and longest row L:
+//     forced strategy if one was given (kid hint), else
+//     THREAD  if L <= 64 and L*nr <= 2*nz + nr        (rows short and of similar length)
+//     WARP    if nz >= 48*nr and L*nr <= 4*nz         (rows long and of similar length)
+//     PRODUCT otherwise
+//   LONG segments get consecutive partial-sum slots in block order; long rows are listed in row order.
+#include "common.hpp"
+
+#include <algorithm>
+
+namespace b200
+{
+    void plan_parameters(size_t          elem_size,
+                         aoclsparse_int  m,
+                         aoclsparse_int  nnz,
+                         aoclsparse_int &block_nnz,
+                         aoclsparse_int &block_rows)
+    {
+        (void)m;
+        // staged bytes per entry = elem_size + 4 (column index)
+        aoclsparse_int T = (elem_size >= 16) ? 2048 : 4096;
+        // small matrices: keep at least ~8 CTAs per SM in the grid
+        while(T > 512 && (long long)nnz < (long long)T * 148 * 8)
+            T /= 2;
+        block_nnz  = T;
+        block_rows = 1024;
+    }
+
+    namespace
+    {
+        __global__ void grid_rows_kernel(aoclsparse_int m,
+                                         const aoclsparse_int *__restrict__ rp,
+                                         long long       S,
+                                         int             ngrid,
+                                         aoclsparse_int *out)
+        {
+            int k = blockIdx.x * blockDim.x + threadIdx.x;
+            if(k >= ngrid)
+                return;
+            long long target = (long long)(k + 1) * S;
+            // smallest r in [0, m] with rp[r] >= target
+            aoclsparse_int lo = 0, hi = m;
+            while(lo < hi)
+            {
+                aoclsparse_int mid = lo + (hi - lo) / 2;
+                if((long long)rp[mid] >= target)
+                    hi = mid;
+                else
+                    lo = mid + 1;
+            }
+            out[k] = lo;
+        }
+
+        // FILL == false: count blocks / long rows / long segments of each segment
+        // FILL == true : write the block descriptors at the scanned offsets
+        template <bool FILL>
+        __global__ void walk_segments_kernel(int nseg,
+                                             const aoclsparse_int *__restrict__ seg_start,
+                                             const aoclsparse_int *__restrict__ rp,
+                                             aoclsparse_int T,
+                                             aoclsparse_int R,
+                                             int3          *counts,    // per segment (FILL=false: out)
+                                             const int3    *offsets,   // per segment (FILL=true: in)
+                                             int4          *desc,
+                                             int           *kind,
+                                             int4          *long_rows)
+        {
+            int sidx = blockIdx.x * blockDim.x + threadIdx.x;
+            if(sidx >= nseg)
+                return;
+            const aoclsparse_int sa = seg_start[sidx], sb = seg_start[sidx + 1];
+            int nb = 0, nlr = 0, nls = 0;
+            int ob = 0, olr = 0, ols = 0;
+            if(FILL)
+            {
+                ob  = offsets[sidx].x;
+                olr = offsets[sidx].y;
+                ols = offsets[sidx].z;
+            }
+            aoclsparse_int r = sa;
+            while(r < sb)
+            {
+                const aoclsparse_int p0  = rp[r];
+                const aoclsparse_int len = rp[r + 1] - p0;
+                if(len > T)
+                {
+                    const int q = (int)(((long long)len + T - 1) / T);
+                    if(FILL)
+                    {
+                        long_rows[olr + nlr] = make_int4(r, ols + nls, q, 0);
+                        for(int s = 0; s < q; ++s)
+                        {
+                            long long a = (long long)p0 + (long long)s * T;
+                            long long b = a + T;
+                            if(b > (long long)p0 + len)
+                                b = (long long)p0 + len;
+                            desc[ob + nb + s] = make_int4(r, r + 1, (int)a, (int)b);
+                            kind[ob + nb + s] = STRAT_LONG | ((ols + nls + s) << 4);
+                        }
+                    }
+                    nb += q;
+                    nls += q;
+                    nlr += 1;
+                    r += 1;
+                }
+                else
+                {
+                    aoclsparse_int hi = (sb - r > R) ? r + R : sb;
+                    // largest r1 in (r, hi] with rp[r1] - p0 <= T ; rp[r+1]-p0 = len <= T holds
+                    aoclsparse_int lo = r + 1;
+                    const long long lim = (long long)p0 + T;
+                    while(lo < hi)
+                    {
+                        aoclsparse_int mid = lo + (hi - lo + 1) / 2;
+                        if((long long)rp[mid] <= lim)
+                            lo = mid;
+                        else
+                            hi = mid - 1;
+                    }
+                    if(FILL)
+                    {
+                        desc[ob + nb] = make_int4(r, lo, p0, rp[lo]);
+                        kind[ob + nb] = -1; // classified afterwards
+                    }
+                    nb += 1;
+                    r = lo;
+                }
+            }
+            if(!FILL)
+                counts[sidx] = make_int3(nb, nlr, nls);
+        }
+
+        // one warp per block: longest row -> strategy
+        __global__ void classify_kernel(int nblocks,
+                                        const aoclsparse_int *__restrict__ rp,
+                                        const int4 *__restrict__ desc,
+                                        int *kind,
+                                        int  forced,
+                                        int *strat_count)
+        {
+            const int lane = threadIdx.x & 31;
+            const int b    = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+            if(b >= nblocks)
+                return;
+            int k = kind[b];
+            if(k < 0)
+            {
+                const int4 d  = desc[b];
+                int        L  = 0;
+                for(int r = d.x + lane; r < d.y; r += 32)
+                    L = max(L, rp[r + 1] - rp[r]);
+                for(int off = 16; off > 0; off >>= 1)
+                    L = max(L, __shfl_xor_sync(0xffffffffu, L, off));
+                const long long nr = d.y - d.x, nz = d.w - d.z;
+                if(forced >= 0)
+                    k = forced;
+                else if(L <= 64 && (long long)L * nr <= 2 * nz + nr)
+                    k = STRAT_THREAD;
+                else if(nz >= 48 * nr && (long long)L * nr <= 4 * nz)
+                    k = STRAT_WARP;
+                else
+                    k = STRAT_PRODUCT;
+                if(lane == 0)
+                    kind[b] = k;
+            }
+            if(lane == 0)
+                atomicAdd(&strat_count[k & 15], 1);
+        }
+    }
+
+    aoclsparse_status build_plan(dev_csr                           &A,
+                                 size_t                             elem_size,
+                                 aoclsparse_int                     forced_strategy,
+                                 const std::vector<aoclsparse_int> &row_cuts,
+                                 cudaStream_t                       st)
+    {
+        row_block_plan &P = A.plan;
+        P                 = row_block_plan();
+        plan_parameters(elem_size, A.m, A.nnz, P.block_nnz, P.block_rows);
+        const aoclsparse_int T = P.block_nnz, R = P.block_rows;
+        const long long      S = 64LL * T;
+        const aoclsparse_int *rp = A.row_ptr.as<aoclsparse_int>();
+
+        if(A.m == 0)
+        {
+            P.valid = true;
+            return aoclsparse_status_success;
+        }
+
+        // ---- segment boundaries: nnz grid (device lower bounds) merged with the forced row cuts
+        const int ngrid = (int)(((long long)A.nnz + S - 1) / S) - 1 > 0 ? (int)(((long long)A.nnz + S - 1) / S) - 1 : 0;
+        std::vector<aoclsparse_int> bounds;
+        bounds.push_back(0);
+        if(ngrid > 0)
+        {
+            dev_buf g;
+            B200_TRY(g.alloc(sizeof(aoclsparse_int) * (size_t)ngrid));
+            grid_rows_kernel<<<(ngrid + 127) / 128, 128, 0, st>>>(A.m, rp, S, ngrid, g.as<aoclsparse_int>());
+            B200_LAUNCHED();
+            std::vector<aoclsparse_int> h((size_t)ngrid);
+            B200_CUDA(cudaMemcpyAsync(h.data(), g.p, sizeof(aoclsparse_int) * (size_t)ngrid, cudaMemcpyDeviceToHost, st));
+            B200_CUDA(cudaStreamSynchronize(st));
+            bounds.insert(bounds.end(), h.begin(), h.end());
+        }
+        for(aoclsparse_int c : row_cuts)
+            bounds.push_back(c);
+        bounds.push_back(A.m);
+        std::sort(bounds.begin(), bounds.end());
+        bounds.erase(std::unique(bounds.begin(), bounds.end()), bounds.end());
+        const int nseg = (int)bounds.size() - 1;
+
+        dev_buf d_seg, d_counts, d_offsets;
+        B200_TRY(d_seg.alloc(sizeof(aoclsparse_int) * bounds.size()));
+        B200_TRY(d_counts.alloc(sizeof(int3) * (size_t)nseg));
+        B200_TRY(d_offsets.alloc(sizeof(int3) * (size_t)nseg));
+        B200_CUDA(cudaMemcpyAsync(d_seg.p, bounds.data(), sizeof(aoclsparse_int) * bounds.size(), cudaMemcpyHostToDevice, st));
+
+        walk_segments_kernel<false><<<(nseg + 63) / 64, 64, 0, st>>>(
+            nseg, d_seg.as<aoclsparse_int>(), rp, T, R, d_counts.as<int3>(), nullptr, nullptr, nullptr, nullptr);
+        B200_LAUNCHED();
+        std::vector<int3> counts((size_t)nseg), offsets((size_t)nseg);
+        B200_CUDA(cudaMemcpyAsync(counts.data(), d_counts.p, sizeof(int3) * (size_t)nseg, cudaMemcpyDeviceToHost, st));
+        B200_CUDA(cudaStreamSynchronize(st));
+        long long nb = 0, nlr = 0, nls = 0;
+        for(int s = 0; s < nseg; ++s)
+        {
+            offsets[s] = make_int3((int)nb, (int)nlr, (int)nls);
+            nb += counts[s].x;
+            nlr += counts[s].y;
+            nls += counts[s].z;
+        }
+        if(nb > 0x7fffffffLL / 16)
+            return aoclsparse_status_internal_error;
+        P.n_blocks        = (aoclsparse_int)nb;
+        P.n_long_rows     = (aoclsparse_int)nlr;
+        P.n_long_segments = (aoclsparse_int)nls;
+
+        // where each row cut begins in block numbering (cuts are segment boundaries)
+        P.cut_block.clear();
+        for(aoclsparse_int c : row_cuts)
+        {
+            size_t sidx = std::lower_bound(bounds.begin(), bounds.end(), c) - bounds.begin();
+            P.cut_block.push_back(sidx < (size_t)nseg ? offsets[sidx].x : (aoclsparse_int)nb);
+        }
+
+        B200_TRY(P.desc.alloc(sizeof(int4) * (size_t)std::max<long long>(nb, 1)));
+        B200_TRY(P.kind.alloc(sizeof(int) * (size_t)std::max<long long>(nb, 1)));
+        B200_TRY(P.long_rows.alloc(sizeof(int4) * (size_t)std::max<long long>(nlr, 1)));
+        B200_TRY(P.partials.alloc(16 * (size_t)std::max<long long>(nls, 1)));
+        B200_CUDA(cudaMemcpyAsync(d_offsets.p, offsets.data(), sizeof(int3) * (size_t)nseg, cudaMemcpyHostToDevice, st));
+        walk_segments_kernel<true><<<(nseg + 63) / 64, 64, 0, st>>>(nseg,
+                                                                   d_seg.as<aoclsparse_int>(),
+                                                                   rp,
+                                                                   T,
+                                                                   R,
+                                                                   nullptr,
+                                                                   d_offsets.as<int3>(),
+                                                                   P.desc.as<int4>(),
+                                                                   P.kind.as<int>(),
+                                                                   P.long_rows.as<int4>());
+        B200_LAUNCHED();
+
+        dev_buf d_sc;
+        B200_TRY(d_sc.alloc(sizeof(int) * 16));
+        B200_CUDA(cudaMemsetAsync(d_sc.p, 0, sizeof(int) * 16, st));
+        if(nb > 0)
+        {
+            const long long threads = nb * 32;
+            classify_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(
+                (int)nb, rp, P.desc.as<int4>(), P.kind.as<int>(), (int)forced_strategy, d_sc.as<int>());
+            B200_LAUNCHED();
+        }
+        int sc[16];
+        B200_CUDA(cudaMemcpyAsync(sc, d_sc.p, sizeof(sc), cudaMemcpyDeviceToHost, st));
+        B200_CUDA(cudaStreamSynchronize(st));
+        for(int i = 0; i < 4; ++i)
+            P.n_strat[i] = sc[i];
+        P.valid = true;
+        return aoclsparse_status_success;
+    }
+}

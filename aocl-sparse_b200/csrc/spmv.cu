@@ -1,0 +1,499 @@
+// spmv.cu -- host front end of aoclsparse_{s,d,c,z}mv and the row-range extension.
+//
+// Mirrors the argument checking, quick returns and operation / descriptor handling of
+//   aoclsparse::mv<T>            library/src/level2/aoclsparse_mv.cpp:41-349
+//   aoclsparse_csrmv_t<T,false>  library/src/level2/aoclsparse_csrmv.hpp:32-450
+// and launches the sm_100a kernels of spmv_kernels.cuh.  There is no CPU path: if a launch fails the
+// call returns internal_error.
+#include "spmv_kernels.cuh"
+
+namespace b200
+{
+    namespace
+    {
+        // per-thread staging buffers for host-resident x / y (grow-only)
+        struct staging
+        {
+            dev_buf x, y;
+        };
+        staging &tls_staging()
+        {
+            static thread_local staging s;
+            return s;
+        }
+
+        template <typename T>
+        aoclsparse_status scale_vector(T *y, long long len, T beta, T alpha, const T *x, long long n_unit, cudaStream_t st)
+        {
+            if(len <= 0)
+                return aoclsparse_status_success;
+            long long blocks = (len + 255) / 256;
+            if(blocks > 148 * 16)
+                blocks = 148 * 16;
+            scale_vector_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(len, y, beta, is_zero(beta) ? 1 : 0, alpha, x, n_unit);
+            B200_LAUNCHED();
+            return aoclsparse_status_success;
+        }
+
+        template <typename T, bool GENERIC>
+        aoclsparse_status configure_kernel(size_t smem)
+        {
+            static std::atomic<size_t> configured{0};
+            if(configured.load(std::memory_order_acquire) >= smem)
+                return aoclsparse_status_success;
+            B200_CUDA(cudaFuncSetAttribute(
+                spmv_row_blocks_kernel<T, GENERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured.store(smem, std::memory_order_release);
+            return aoclsparse_status_success;
+        }
+
+        // gather pass over blocks [b0, b1) of A's plan
+        template <typename T>
+        aoclsparse_status launch_gather(const dev_csr &A,
+                                        int            b0,
+                                        int            b1,
+                                        int            row_lo,
+                                        int            row_hi,
+                                        const T       *x,
+                                        T             *y,
+                                        T              alpha,
+                                        T              beta,
+                                        bool           generic,
+                                        elem_rule      rule,
+                                        cudaStream_t   st)
+        {
+            const row_block_plan &P = A.plan;
+            if(b1 <= b0)
+                return aoclsparse_status_success;
+            const int    cap  = P.block_nnz + 8;
+            const size_t smem = spmv_smem_bytes(sizeof(T), P.block_nnz);
+            const int    bz   = is_zero(beta) ? 1 : 0;
+            if(generic)
+            {
+                B200_TRY((configure_kernel<T, true>(smem)));
+                spmv_row_blocks_kernel<T, true><<<b1 - b0, SPMV_THREADS, smem, st>>>(P.desc.as<int4>(),
+                                                                                      P.kind.as<int>(),
+                                                                                      b0,
+                                                                                      cap,
+                                                                                      A.row_ptr.as<aoclsparse_int>(),
+                                                                                      A.col_idx.as<aoclsparse_int>(),
+                                                                                      A.val.as<T>(),
+                                                                                      x,
+                                                                                      y,
+                                                                                      alpha,
+                                                                                      beta,
+                                                                                      bz,
+                                                                                      P.partials.as<T>(),
+                                                                                      rule,
+                                                                                      A.n);
+            }
+            else
+            {
+                B200_TRY((configure_kernel<T, false>(smem)));
+                spmv_row_blocks_kernel<T, false><<<b1 - b0, SPMV_THREADS, smem, st>>>(P.desc.as<int4>(),
+                                                                                       P.kind.as<int>(),
+                                                                                       b0,
+                                                                                       cap,
+                                                                                       A.row_ptr.as<aoclsparse_int>(),
+                                                                                       A.col_idx.as<aoclsparse_int>(),
+                                                                                       A.val.as<T>(),
+                                                                                       x,
+                                                                                       y,
+                                                                                       alpha,
+                                                                                       beta,
+                                                                                       bz,
+                                                                                       P.partials.as<T>(),
+                                                                                       rule,
+                                                                                       A.n);
+            }
+            B200_LAUNCHED();
+            if(P.n_long_rows > 0)
+            {
+                const long long threads = (long long)P.n_long_rows * 32;
+                finish_long_rows_kernel<T><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(
+                    P.n_long_rows,
+                    P.long_rows.as<int4>(),
+                    P.partials.as<T>(),
+                    x,
+                    y,
+                    alpha,
+                    beta,
+                    bz,
+                    (generic && rule.diag == DIAG_UNIT) ? 1 : 0,
+                    A.n,
+                    row_lo,
+                    row_hi);
+                B200_LAUNCHED();
+            }
+            return aoclsparse_status_success;
+        }
+
+        template <typename T>
+        aoclsparse_status launch_scatter(const dev_csr &A, const T *x, T *y, T alpha, elem_rule rule, cudaStream_t st)
+        {
+            const row_block_plan &P = A.plan;
+            if(P.n_blocks <= 0)
+                return aoclsparse_status_success;
+            spmv_scatter_kernel<T><<<P.n_blocks, SPMV_THREADS, 0, st>>>(P.desc.as<int4>(),
+                                                                        A.row_ptr.as<aoclsparse_int>(),
+                                                                        A.col_idx.as<aoclsparse_int>(),
+                                                                        A.val.as<T>(),
+                                                                        x,
+                                                                        y,
+                                                                        alpha,
+                                                                        rule);
+            B200_LAUNCHED();
+            return aoclsparse_status_success;
+        }
+
+        int diag_rule(aoclsparse_diag_type d)
+        {
+            return d == aoclsparse_diag_type_unit ? DIAG_UNIT : (d == aoclsparse_diag_type_zero ? DIAG_ZERO : DIAG_KEEP);
+        }
+
+        inline bool valid_op(aoclsparse_operation op)
+        {
+            return op == aoclsparse_operation_none || op == aoclsparse_operation_transpose
+                   || op == aoclsparse_operation_conjugate_transpose;
+        }
+        inline bool valid_type(aoclsparse_matrix_type t)
+        {
+            return t == aoclsparse_matrix_type_general || t == aoclsparse_matrix_type_symmetric
+                   || t == aoclsparse_matrix_type_hermitian || t == aoclsparse_matrix_type_triangular;
+        }
+    }
+
+    // The device-side multiply, x and y already device accessible.
+    template <typename T>
+    aoclsparse_status mv_device(aoclsparse_operation       op,
+                                T                          alpha,
+                                aoclsparse_matrix          A,
+                                const _aoclsparse_mat_descr &descr,
+                                const T                   *x,
+                                T                          beta,
+                                T                         *y,
+                                cudaStream_t               st)
+    {
+        B200_TRY(ensure_plan(A, st));
+        std::shared_lock<std::shared_mutex> rl(A->guard);
+        const dev_csr                      &M = *A->mats[0];
+        const bool                          cplx = vt<T>::is_complex;
+
+        if(A->win_hi >= 0)
+        {
+            // windowed x: only the plain general product is defined on a row shard
+            if(descr.type != aoclsparse_matrix_type_general || op != aoclsparse_operation_none)
+                return aoclsparse_status_not_implemented;
+            x = x - A->win_lo;
+        }
+
+        const bool conj_op = cplx && op == aoclsparse_operation_conjugate_transpose;
+        const bool trans   = op != aoclsparse_operation_none;
+        elem_rule  none_rule{MASK_NONE, DIAG_KEEP, 0, 0};
+
+        switch(descr.type)
+        {
+        case aoclsparse_matrix_type_general:
+            if(!trans)
+                return launch_gather<T>(M, 0, M.plan.n_blocks, 0, M.m, x, y, alpha, beta, false, none_rule, st);
+            else
+            {
+                // an explicitly transposed copy built by aoclsparse_optimize turns this into a gather
+                for(size_t i = 1; i < A->mats.size(); ++i)
+                {
+                    const dev_csr &C = *A->mats[i];
+                    if(C.doid == (conj_op ? DOID_GH : DOID_GT) && C.plan.valid)
+                        return launch_gather<T>(C, 0, C.plan.n_blocks, 0, C.m, x, y, alpha, beta, false, none_rule, st);
+                }
+                B200_TRY(scale_vector<T>(y, M.n, beta, alpha, x, 0, st));
+                elem_rule r{MASK_NONE, DIAG_KEEP, conj_op ? 1 : 0, conj_op ? 1 : 0};
+                return launch_scatter<T>(M, x, y, alpha, r, st);
+            }
+        case aoclsparse_matrix_type_triangular:
+        {
+            const int mask = descr.fill_mode == aoclsparse_fill_mode_lower ? MASK_LOWER : MASK_UPPER;
+            const int dg   = diag_rule(descr.diag_type);
+            if(!trans)
+            {
+                elem_rule r{mask, dg, 0, 0};
+                return launch_gather<T>(M, 0, M.plan.n_blocks, 0, M.m, x, y, alpha, beta, true, r, st);
+            }
+            // y (length n) = beta*y [+ alpha*x on the unit diagonal], then scatter the kept entries
+            const long long n_unit = (dg == DIAG_UNIT) ? (M.m < M.n ? M.m : M.n) : 0;
+            B200_TRY(scale_vector<T>(y, M.n, beta, alpha, x, n_unit, st));
+            elem_rule r{mask, dg, conj_op ? 1 : 0, conj_op ? 1 : 0};
+            return launch_scatter<T>(M, x, y, alpha, r, st);
+        }
+        case aoclsparse_matrix_type_symmetric:
+        case aoclsparse_matrix_type_hermitian:
+        {
+            const bool herm = descr.type == aoclsparse_matrix_type_hermitian;
+            const int  mask = descr.fill_mode == aoclsparse_fill_mode_lower ? MASK_LOWER : MASK_UPPER;
+            const int  dg   = diag_rule(descr.diag_type);
+            // stored triangle T, mirror S:  symmetric S = T^T, hermitian S = T^H.
+            //   symmetric: op none/T -> T + D + T^T            ; op H -> conj of all of it
+            //   hermitian: op none/H -> T + D + conj(T)^T      ; op T -> conj(T) + D + T^T
+            // (D as stored; the reference does not conjugate a hermitian diagonal,
+            //  aoclsparse_csrmv_kr.hpp:398-401,422-425, but does conjugate a symmetric one for op H, :217-218)
+            int cg, cs, cd;
+            if(!herm)
+            {
+                cg = cs = cd = conj_op ? 1 : 0;
+            }
+            else
+            {
+                const bool t = cplx && op == aoclsparse_operation_transpose;
+                cg           = t ? 1 : 0;
+                cs           = t ? 0 : 1;
+                cd           = 0;
+            }
+            // pass 1 (gather): y = beta*y + alpha*(T_strict + D) x
+            elem_rule rg{mask, dg, cg, cd};
+            B200_TRY(launch_gather<T>(M, 0, M.plan.n_blocks, 0, M.m, x, y, alpha, beta, true, rg, st));
+            // pass 2 (scatter): y[col] += alpha * op(a) * x[row] over the strict triangle
+            elem_rule rs{mask, DIAG_ZERO, cs, cs};
+            return launch_scatter<T>(M, x, y, alpha, rs, st);
+        }
+        }
+        return aoclsparse_status_invalid_value;
+    }
+
+    // Common validation + staging.  Mirrors aoclsparse::mv<T> (mv.cpp:55-121).
+    template <typename T>
+    aoclsparse_status mv_entry(aoclsparse_operation       op,
+                               const T                   *alpha,
+                               aoclsparse_matrix          A,
+                               const aoclsparse_mat_descr descr,
+                               const T                   *x,
+                               const T                   *beta,
+                               T                         *y)
+    {
+        if(alpha == nullptr || beta == nullptr)
+            return aoclsparse_status_invalid_pointer;
+        if(A == nullptr)
+            return aoclsparse_status_invalid_pointer;
+        if(descr == nullptr)
+            return aoclsparse_status_invalid_pointer;
+        if(x == nullptr || y == nullptr)
+            return aoclsparse_status_invalid_pointer;
+        if(A->mats.empty() || A->mats[0] == nullptr)
+            return aoclsparse_status_invalid_pointer;
+        if(descr->base != A->base)
+            return aoclsparse_status_invalid_value;
+        if(!valid_op(op))
+            return aoclsparse_status_invalid_value;
+        if(A->val_type != vt<T>::data_type)
+            return aoclsparse_status_wrong_type;
+        if(!valid_type(descr->type))
+            return aoclsparse_status_invalid_value;
+        if((descr->type == aoclsparse_matrix_type_symmetric || descr->type == aoclsparse_matrix_type_hermitian)
+           && A->m != A->n)
+            return aoclsparse_status_invalid_size;
+        if(!vt<T>::is_complex)
+        {
+            if(op == aoclsparse_operation_conjugate_transpose)
+                op = aoclsparse_operation_transpose;
+            if(descr->type == aoclsparse_matrix_type_hermitian)
+                return aoclsparse_status_not_implemented;
+        }
+
+        cudaStream_t    st    = current_stream();
+        const long long x_len = (A->win_hi >= 0) ? (long long)(A->win_hi - A->win_lo)
+                                                 : (op == aoclsparse_operation_none ? A->n : A->m);
+        const long long y_len = op == aoclsparse_operation_none ? A->m : A->n;
+
+        // requested kernel id (aoclsparse_set_mv_hint_kid): -1 auto, 0..2 force a row strategy
+        {
+            std::shared_lock<std::shared_mutex> rl(A->guard);
+            const int d_id = get_doid(vt<T>::is_complex, descr->type, descr->fill_mode, op);
+            for(const hint &h : A->hints)
+                if(h.act == 1 && h.doid == d_id)
+                {
+                    if(h.kid > 2)
+                        return aoclsparse_status_invalid_kid;
+                    break;
+                }
+        }
+
+        const bool x_dev = is_device_accessible(x), y_dev = is_device_accessible(y);
+        const bool empty = A->m == 0 || A->n == 0 || (A->nnz == 0 && descr->type == aoclsparse_matrix_type_general);
+
+        const T *dx = x;
+        T       *dy = y;
+        staging &sg = tls_staging();
+        if(!y_dev)
+        {
+            if(sg.y.bytes < (size_t)y_len * sizeof(T))
+                B200_TRY(sg.y.alloc((size_t)y_len * sizeof(T)));
+            dy = sg.y.as<T>();
+            if(!is_zero(*beta) && y_len > 0)
+                B200_CUDA(cudaMemcpyAsync(dy, y, (size_t)y_len * sizeof(T), cudaMemcpyHostToDevice, st));
+        }
+        if(!x_dev && !empty)
+        {
+            if(sg.x.bytes < (size_t)x_len * sizeof(T))
+                B200_TRY(sg.x.alloc((size_t)x_len * sizeof(T)));
+            B200_CUDA(cudaMemcpyAsync(sg.x.p, x, (size_t)x_len * sizeof(T), cudaMemcpyHostToDevice, st));
+            dx = sg.x.as<T>();
+        }
+
+        aoclsparse_status status;
+        if(empty)
+            status = scale_vector<T>(dy, y_len, *beta, *alpha, nullptr, 0, st); // mv.cpp:116-121
+        else
+            status = mv_device<T>(op, *alpha, A, *descr, dx, *beta, dy, st);
+        if(status != aoclsparse_status_success)
+            return status;
+
+        if(!y_dev)
+        {
+            if(y_len > 0)
+                B200_CUDA(cudaMemcpyAsync(y, dy, (size_t)y_len * sizeof(T), cudaMemcpyDeviceToHost, st));
+            B200_CUDA(cudaStreamSynchronize(st));
+        }
+        else if(!x_dev)
+            B200_CUDA(cudaStreamSynchronize(st)); // staging buffer may be reused by the next call
+        return aoclsparse_status_success;
+    }
+
+    template <typename T>
+    aoclsparse_status mv_rows_entry(const T                   *alpha,
+                                    aoclsparse_matrix          A,
+                                    const aoclsparse_mat_descr descr,
+                                    const T                   *x,
+                                    const T                   *beta,
+                                    T                         *y,
+                                    aoclsparse_int             row_begin,
+                                    aoclsparse_int             row_end)
+    {
+        if(!alpha || !beta || !A || !descr || !x || !y)
+            return aoclsparse_status_invalid_pointer;
+        if(A->mats.empty() || A->mats[0] == nullptr)
+            return aoclsparse_status_invalid_pointer;
+        if(descr->base != A->base)
+            return aoclsparse_status_invalid_value;
+        if(A->val_type != vt<T>::data_type)
+            return aoclsparse_status_wrong_type;
+        if(descr->type != aoclsparse_matrix_type_general)
+            return aoclsparse_status_not_implemented;
+        if(!is_device_accessible(x) || !is_device_accessible(y))
+            return aoclsparse_status_invalid_pointer;
+        if(row_begin < 0 || row_end > A->m || row_begin > row_end)
+            return aoclsparse_status_invalid_size;
+        cudaStream_t st = current_stream();
+        B200_TRY(ensure_plan(A, st));
+        std::shared_lock<std::shared_mutex> rl(A->guard);
+        const dev_csr                      &M = *A->mats[0];
+        auto block_of = [&](aoclsparse_int row, int &blk) -> bool {
+            if(row == 0)
+            {
+                blk = 0;
+                return true;
+            }
+            if(row == A->m)
+            {
+                blk = M.plan.n_blocks;
+                return true;
+            }
+            for(size_t i = 0; i < A->row_cuts.size(); ++i)
+                if(A->row_cuts[i] == row && i < M.plan.cut_block.size())
+                {
+                    blk = M.plan.cut_block[i];
+                    return true;
+                }
+            return false;
+        };
+        int b0, b1;
+        if(!block_of(row_begin, b0) || !block_of(row_end, b1))
+            return aoclsparse_status_invalid_value;
+        if(A->win_hi >= 0)
+            x = x - A->win_lo;
+        elem_rule none_rule{MASK_NONE, DIAG_KEEP, 0, 0};
+        return launch_gather<T>(M, b0, b1, row_begin, row_end, x, y, *alpha, *beta, false, none_rule, st);
+    }
+}
+
+using namespace b200;
+
+extern "C" {
+
+aoclsparse_status aoclsparse_smv(aoclsparse_operation       op,
+                                 const float               *alpha,
+                                 aoclsparse_matrix          A,
+                                 const aoclsparse_mat_descr descr,
+                                 const float               *x,
+                                 const float               *beta,
+                                 float                     *y)
+{
+    return mv_entry<float>(op, alpha, A, descr, x, beta, y);
+}
+
+aoclsparse_status aoclsparse_dmv(aoclsparse_operation       op,
+                                 const double              *alpha,
+                                 aoclsparse_matrix          A,
+                                 const aoclsparse_mat_descr descr,
+                                 const double              *x,
+                                 const double              *beta,
+                                 double                    *y)
+{
+    return mv_entry<double>(op, alpha, A, descr, x, beta, y);
+}
+
+aoclsparse_status aoclsparse_cmv(aoclsparse_operation            op,
+                                 const aoclsparse_float_complex *alpha,
+                                 aoclsparse_matrix               A,
+                                 const aoclsparse_mat_descr      descr,
+                                 const aoclsparse_float_complex *x,
+                                 const aoclsparse_float_complex *beta,
+                                 aoclsparse_float_complex       *y)
+{
+    return mv_entry<float2>(op,
+                            reinterpret_cast<const float2 *>(alpha),
+                            A,
+                            descr,
+                            reinterpret_cast<const float2 *>(x),
+                            reinterpret_cast<const float2 *>(beta),
+                            reinterpret_cast<float2 *>(y));
+}
+
+aoclsparse_status aoclsparse_zmv(aoclsparse_operation             op,
+                                 const aoclsparse_double_complex *alpha,
+                                 aoclsparse_matrix                A,
+                                 const aoclsparse_mat_descr       descr,
+                                 const aoclsparse_double_complex *x,
+                                 const aoclsparse_double_complex *beta,
+                                 aoclsparse_double_complex       *y)
+{
+    return mv_entry<double2>(op,
+                             reinterpret_cast<const double2 *>(alpha),
+                             A,
+                             descr,
+                             reinterpret_cast<const double2 *>(x),
+                             reinterpret_cast<const double2 *>(beta),
+                             reinterpret_cast<double2 *>(y));
+}
+
+aoclsparse_status aoclsparse_b200_dmv_rows(const double              *alpha,
+                                           aoclsparse_matrix          A,
+                                           const aoclsparse_mat_descr descr,
+                                           const double              *x,
+                                           const double              *beta,
+                                           double                    *y,
+                                           aoclsparse_int             row_begin,
+                                           aoclsparse_int             row_end)
+{
+    return mv_rows_entry<double>(alpha, A, descr, x, beta, y, row_begin, row_end);
+}
+
+aoclsparse_status aoclsparse_b200_smv_rows(const float               *alpha,
+                                           aoclsparse_matrix          A,
+                                           const aoclsparse_mat_descr descr,
+                                           const float               *x,
+                                           const float               *beta,
+                                           float                     *y,
+                                           aoclsparse_int             row_begin,
+                                           aoclsparse_int             row_end)
+{
+    return mv_rows_entry<float>(alpha, A, descr, x, beta, y, row_begin, row_end);
+}
+}

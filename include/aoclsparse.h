@@ -1,0 +1,482 @@
+/* aoclsparse.h -- C-ABI drop-in boundary of the B200-native CSR SpMV / SpMM path.
+ *
+ * Every symbol below has the SAME name, argument order, argument meaning, enum values and
+ * status codes as the AOCL-Sparse v5.3.2 entry it replaces, so that a program written against
+ * the reference's <aoclsparse.h> for this path recompiles and relinks against
+ * libaoclsparse_b200.so unchanged.  Each block cites the reference declaration it stands in
+ * for (paths relative to the reference tree).  Semantics that differ because the matrix lives
+ * in GPU memory are marked "B200:".
+ *
+ * The numeric enum values are part of the ABI (reference: library/include/aoclsparse_types.h).
+ */
+#ifndef AOCLSPARSE_H_B200_
+#define AOCLSPARSE_H_B200_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifndef DLL_PUBLIC
+#define DLL_PUBLIC __attribute__((__visibility__("default")))
+#endif
+
+/* aoclsparse_types.h:54-58 -- LP64 build (int32 indices); -Daoclsparse_ILP64 widens them. */
+#if defined(aoclsparse_ILP64)
+typedef int64_t aoclsparse_int;
+#else
+typedef int32_t aoclsparse_int;
+#endif
+
+/* aoclsparse_types.h:77-99 -- interleaved (re, im) pairs, layout-compatible with C99 / std::complex. */
+typedef struct
+{
+    float real;
+    float imag;
+} aoclsparse_float_complex;
+typedef struct
+{
+    double real;
+    double imag;
+} aoclsparse_double_complex;
+
+/* aoclsparse_types.h:114,140 -- opaque handles. */
+typedef struct _aoclsparse_mat_descr *aoclsparse_mat_descr;
+typedef struct _aoclsparse_matrix    *aoclsparse_matrix;
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* aoclsparse_types.h:151-160 */
+typedef enum aoclsparse_operation_
+{
+    aoclsparse_operation_none                = 111,
+    aoclsparse_operation_transpose           = 112,
+    aoclsparse_operation_conjugate_transpose = 113
+} aoclsparse_operation;
+
+/* aoclsparse_types.h:166-169 */
+typedef enum aoclsparse_index_base_
+{
+    aoclsparse_index_base_zero = 0,
+    aoclsparse_index_base_one  = 1
+} aoclsparse_index_base;
+
+/* aoclsparse_types.h:175-187 */
+typedef enum aoclsparse_matrix_type_
+{
+    aoclsparse_matrix_type_general    = 0,
+    aoclsparse_matrix_type_symmetric  = 1,
+    aoclsparse_matrix_type_hermitian  = 2,
+    aoclsparse_matrix_type_triangular = 3
+} aoclsparse_matrix_type;
+
+/* aoclsparse_types.h:193-199 */
+typedef enum aoclsparse_matrix_data_type_
+{
+    aoclsparse_dmat = 0,
+    aoclsparse_smat = 1,
+    aoclsparse_cmat = 2,
+    aoclsparse_zmat = 3
+} aoclsparse_matrix_data_type;
+
+/* aoclsparse_types.h:215-240 -- only aoclsparse_csr_mat is produced by this library. */
+typedef enum aoclsparse_matrix_format_type_
+{
+    aoclsparse_csr_mat          = 0,
+    aoclsparse_ell_mat          = 1,
+    aoclsparse_ellt_mat         = 2,
+    aoclsparse_ellt_csr_hyb_mat = 3,
+    aoclsparse_ell_csr_hyb_mat  = 4,
+    aoclsparse_dia_mat          = 5,
+    aoclsparse_csr_mat_br4      = 6,
+    aoclsparse_coo_mat          = 7,
+    aoclsparse_tcsr_mat         = 8,
+    aoclsparse_blkcsr_mat       = 9,
+    aoclsparse_bsr_mat          = 10,
+    aoclsparse_uninitialized_mat
+} aoclsparse_matrix_format_type;
+
+/* aoclsparse_types.h:248-257 */
+typedef enum aoclsparse_diag_type_
+{
+    aoclsparse_diag_type_non_unit = 0,
+    aoclsparse_diag_type_unit     = 1,
+    aoclsparse_diag_type_zero     = 2
+} aoclsparse_diag_type;
+
+/* aoclsparse_types.h:265-269 */
+typedef enum aoclsparse_fill_mode_
+{
+    aoclsparse_fill_mode_lower = 0,
+    aoclsparse_fill_mode_upper = 1
+} aoclsparse_fill_mode;
+
+/* aoclsparse_types.h:276-280 */
+typedef enum aoclsparse_order_
+{
+    aoclsparse_order_row    = 0,
+    aoclsparse_order_column = 1
+} aoclsparse_order;
+
+/* aoclsparse_types.h:304-324 */
+typedef enum aoclsparse_status_
+{
+    aoclsparse_status_success             = 0,
+    aoclsparse_status_not_implemented     = 1,
+    aoclsparse_status_invalid_pointer     = 2,
+    aoclsparse_status_invalid_size        = 3,
+    aoclsparse_status_internal_error      = 4,
+    aoclsparse_status_invalid_value       = 5,
+    aoclsparse_status_invalid_index_value = 6,
+    aoclsparse_status_maxit               = 7,
+    aoclsparse_status_user_stop           = 8,
+    aoclsparse_status_wrong_type          = 9,
+    aoclsparse_status_memory_error        = 10,
+    aoclsparse_status_numerical_error     = 11,
+    aoclsparse_status_invalid_operation   = 12,
+    aoclsparse_status_unsorted_input      = 13,
+    aoclsparse_status_invalid_kid         = 14
+} aoclsparse_status;
+
+/* aoclsparse_types.h:331-343 (only used by the sparse x sparse entry, aoclsparse_spmm's relatives) */
+typedef enum aoclsparse_request_
+{
+    aoclsparse_stage_nnz_count        = 0,
+    aoclsparse_stage_finalize         = 1,
+    aoclsparse_stage_full_computation = 2
+} aoclsparse_request;
+
+/* aoclsparse_types.h:384-389 */
+typedef enum aoclsparse_memory_usage_
+{
+    aoclsparse_memory_usage_minimal      = 0,
+    aoclsparse_memory_usage_unrestricted = 1
+} aoclsparse_memory_usage;
+
+/* aoclsparse_types.h:396-403 -- classification computed by aoclsparse_create_?csr. */
+typedef enum aoclsparse_matrix_sort_
+{
+    aoclsparse_unknown_sort     = 0,
+    aoclsparse_fully_sorted     = 1,
+    aoclsparse_partially_sorted = 2,
+    aoclsparse_unsorted         = 3
+} aoclsparse_matrix_sort;
+
+/* ------------------------------------------------------------------------------------------
+ * Version string.  Replaces aoclsparse_get_version (aoclsparse_auxiliary.h:47).
+ * ---------------------------------------------------------------------------------------- */
+DLL_PUBLIC const char *aoclsparse_get_version(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Matrix descriptor.  Replaces aoclsparse_auxiliary.h:131-309
+ * (implementation: library/src/extra/aoclsparse_auxiliary.cpp:191-362).
+ * Defaults: general / lower / non_unit / base zero.  Getters return the default on NULL.
+ * ---------------------------------------------------------------------------------------- */
+DLL_PUBLIC aoclsparse_status aoclsparse_create_mat_descr(aoclsparse_mat_descr *descr);
+DLL_PUBLIC aoclsparse_status aoclsparse_copy_mat_descr(aoclsparse_mat_descr       dest,
+                                                       const aoclsparse_mat_descr src);
+DLL_PUBLIC aoclsparse_status aoclsparse_destroy_mat_descr(aoclsparse_mat_descr descr);
+DLL_PUBLIC aoclsparse_status aoclsparse_set_mat_index_base(aoclsparse_mat_descr  descr,
+                                                           aoclsparse_index_base base);
+DLL_PUBLIC aoclsparse_index_base aoclsparse_get_mat_index_base(const aoclsparse_mat_descr descr);
+DLL_PUBLIC aoclsparse_status     aoclsparse_set_mat_type(aoclsparse_mat_descr   descr,
+                                                         aoclsparse_matrix_type type);
+DLL_PUBLIC aoclsparse_matrix_type aoclsparse_get_mat_type(const aoclsparse_mat_descr descr);
+DLL_PUBLIC aoclsparse_status      aoclsparse_set_mat_fill_mode(aoclsparse_mat_descr descr,
+                                                               aoclsparse_fill_mode fill_mode);
+DLL_PUBLIC aoclsparse_fill_mode aoclsparse_get_mat_fill_mode(const aoclsparse_mat_descr descr);
+DLL_PUBLIC aoclsparse_status    aoclsparse_set_mat_diag_type(aoclsparse_mat_descr descr,
+                                                             aoclsparse_diag_type diag_type);
+DLL_PUBLIC aoclsparse_diag_type aoclsparse_get_mat_diag_type(const aoclsparse_mat_descr descr);
+
+/* ------------------------------------------------------------------------------------------
+ * CSR matrix handle.  Replaces aoclsparse_create_{s,d,c,z}csr (aoclsparse_auxiliary.h:399-437;
+ * implementation library/src/create/aoclsparse_create.cpp:33-95) and aoclsparse_destroy
+ * (aoclsparse_auxiliary.h:836).
+ *
+ * Validation and its precedence are those of aoclsparse_mat_check_internal
+ * (library/src/analysis/aoclsparse_csr_util.cpp:124-279): NULL arrays -> invalid_pointer;
+ * negative M/N/nnz -> invalid_size; row_ptr[0]!=base, row_ptr[M]-base!=nnz, decreasing row_ptr ->
+ * invalid_value; then, in storage order, the first of {column out of [0,N) -> invalid_index_value,
+ * second diagonal entry in a row -> invalid_value}.  *mat is set to NULL before validating.
+ *
+ * B200: the reference handle aliases the caller's host arrays; this handle uploads them once and
+ * owns device-resident copies (row_ptr, col_idx, val) which aoclsparse_destroy frees.  row_ptr /
+ * col_idx / val may be host pointers or CUDA device/managed pointers.  Later edits to the caller's
+ * arrays are not seen; use aoclsparse_?update_values to change values.
+ * ---------------------------------------------------------------------------------------- */
+DLL_PUBLIC aoclsparse_status aoclsparse_create_scsr(aoclsparse_matrix    *mat,
+                                                    aoclsparse_index_base base,
+                                                    aoclsparse_int        M,
+                                                    aoclsparse_int        N,
+                                                    aoclsparse_int        nnz,
+                                                    aoclsparse_int       *row_ptr,
+                                                    aoclsparse_int       *col_idx,
+                                                    float                *val);
+DLL_PUBLIC aoclsparse_status aoclsparse_create_dcsr(aoclsparse_matrix    *mat,
+                                                    aoclsparse_index_base base,
+                                                    aoclsparse_int        M,
+                                                    aoclsparse_int        N,
+                                                    aoclsparse_int        nnz,
+                                                    aoclsparse_int       *row_ptr,
+                                                    aoclsparse_int       *col_idx,
+                                                    double               *val);
+DLL_PUBLIC aoclsparse_status aoclsparse_create_ccsr(aoclsparse_matrix        *mat,
+                                                    aoclsparse_index_base     base,
+                                                    aoclsparse_int            M,
+                                                    aoclsparse_int            N,
+                                                    aoclsparse_int            nnz,
+                                                    aoclsparse_int           *row_ptr,
+                                                    aoclsparse_int           *col_idx,
+                                                    aoclsparse_float_complex *val);
+DLL_PUBLIC aoclsparse_status aoclsparse_create_zcsr(aoclsparse_matrix         *mat,
+                                                    aoclsparse_index_base      base,
+                                                    aoclsparse_int             M,
+                                                    aoclsparse_int             N,
+                                                    aoclsparse_int             nnz,
+                                                    aoclsparse_int            *row_ptr,
+                                                    aoclsparse_int            *col_idx,
+                                                    aoclsparse_double_complex *val);
+DLL_PUBLIC aoclsparse_status aoclsparse_destroy(aoclsparse_matrix *mat);
+
+/* Value refresh keeping the pattern (and the analysis).  Replaces aoclsparse_?update_values
+ * (aoclsparse_auxiliary.h:311-358): len must equal nnz, val replaces all stored values. */
+DLL_PUBLIC aoclsparse_status aoclsparse_supdate_values(aoclsparse_matrix A, aoclsparse_int len, float *val);
+DLL_PUBLIC aoclsparse_status aoclsparse_dupdate_values(aoclsparse_matrix A, aoclsparse_int len, double *val);
+DLL_PUBLIC aoclsparse_status aoclsparse_cupdate_values(aoclsparse_matrix         A,
+                                                       aoclsparse_int            len,
+                                                       aoclsparse_float_complex *val);
+DLL_PUBLIC aoclsparse_status aoclsparse_zupdate_values(aoclsparse_matrix          A,
+                                                       aoclsparse_int             len,
+                                                       aoclsparse_double_complex *val);
+
+/* ------------------------------------------------------------------------------------------
+ * Hints and analysis.  Replaces aoclsparse_analysis.h:57 (optimize), :88-110 (mv / mv_kid / mm
+ * hints), :279 (memory hint); implementation library/src/analysis/aoclsparse_analysis.cpp:426-747.
+ *
+ * B200: aoclsparse_optimize is a GPU analysis pass.  It cuts the rows into nnz-balanced row blocks
+ * (<= a fixed number of non-zeros per CTA; rows longer than that are split across CTAs), bins every
+ * block by its row-length profile into a thread-per-row, warp-per-row or CTA-per-row strategy, and
+ * -- when a transposed / symmetric / hermitian mv or mm hint was given and the memory policy is
+ * unrestricted -- materialises the transposed / expanded device copy that hint needs.
+ * kid (aoclsparse_set_mv_hint_kid) forces a strategy: -1 auto, 0 thread-per-row, 1 warp-per-row,
+ * 2 CTA-wide product + segmented sum, 3 row-split (long-row) path for every row.
+ * ---------------------------------------------------------------------------------------- */
+DLL_PUBLIC aoclsparse_status aoclsparse_optimize(aoclsparse_matrix mat);
+DLL_PUBLIC aoclsparse_status aoclsparse_set_mv_hint(aoclsparse_matrix          mat,
+                                                    aoclsparse_operation       trans,
+                                                    const aoclsparse_mat_descr descr,
+                                                    aoclsparse_int             expected_no_of_calls);
+DLL_PUBLIC aoclsparse_status aoclsparse_set_mv_hint_kid(aoclsparse_matrix          mat,
+                                                        aoclsparse_operation       trans,
+                                                        const aoclsparse_mat_descr descr,
+                                                        aoclsparse_int expected_no_of_calls,
+                                                        aoclsparse_int kid);
+DLL_PUBLIC aoclsparse_status aoclsparse_set_mm_hint(aoclsparse_matrix          mat,
+                                                    aoclsparse_operation       trans,
+                                                    const aoclsparse_mat_descr descr,
+                                                    aoclsparse_int             expected_no_of_calls);
+DLL_PUBLIC aoclsparse_status aoclsparse_set_memory_hint(aoclsparse_matrix             mat,
+                                                        const aoclsparse_memory_usage policy);
+
+/* ------------------------------------------------------------------------------------------
+ * Sparse matrix - vector product  y = alpha * op(A) * x + beta * y.
+ * Replaces aoclsparse_{s,d,c,z}mv (aoclsparse_functions.h:1279-1313; front end
+ * library/src/level2/aoclsparse_mv.cpp:41-349, kernels library/src/level2/aoclsparse_csrmv_kr.hpp,
+ * aoclsparse_csrmv_avx512.cpp, aoclsparse_csrmv_kt.cpp).
+ *
+ * Error precedence (mv.cpp:55-121): NULL alpha/beta, A, descr, x/y -> invalid_pointer; descr base
+ * != matrix base -> invalid_value; bad op -> invalid_value; value type mismatch -> wrong_type; bad
+ * descr type -> invalid_value; symmetric/hermitian on non-square -> invalid_size; real type with a
+ * hermitian descr -> not_implemented; empty matrix -> y = beta*y, success.  beta == 0 overwrites y
+ * without reading it (NaN/Inf in y are ignored).
+ *
+ * B200: x and y may be device/managed pointers (used in place; the call returns after the kernel is
+ * enqueued on the calling thread's stream, see aoclsparse_b200_set_stream) or plain host pointers
+ * (staged through device scratch; the call returns after y has been copied back).
+ * ---------------------------------------------------------------------------------------- */
+DLL_PUBLIC aoclsparse_status aoclsparse_smv(aoclsparse_operation       op,
+                                            const float               *alpha,
+                                            aoclsparse_matrix          A,
+                                            const aoclsparse_mat_descr descr,
+                                            const float               *x,
+                                            const float               *beta,
+                                            float                     *y);
+DLL_PUBLIC aoclsparse_status aoclsparse_dmv(aoclsparse_operation       op,
+                                            const double              *alpha,
+                                            aoclsparse_matrix          A,
+                                            const aoclsparse_mat_descr descr,
+                                            const double              *x,
+                                            const double              *beta,
+                                            double                    *y);
+DLL_PUBLIC aoclsparse_status aoclsparse_cmv(aoclsparse_operation            op,
+                                            const aoclsparse_float_complex *alpha,
+                                            aoclsparse_matrix               A,
+                                            const aoclsparse_mat_descr      descr,
+                                            const aoclsparse_float_complex *x,
+                                            const aoclsparse_float_complex *beta,
+                                            aoclsparse_float_complex       *y);
+DLL_PUBLIC aoclsparse_status aoclsparse_zmv(aoclsparse_operation             op,
+                                            const aoclsparse_double_complex *alpha,
+                                            aoclsparse_matrix                A,
+                                            const aoclsparse_mat_descr       descr,
+                                            const aoclsparse_double_complex *x,
+                                            const aoclsparse_double_complex *beta,
+                                            aoclsparse_double_complex       *y);
+
+/* Handle-free legacy entry.  Replaces aoclsparse_{s,d}csrmv (aoclsparse_functions.h:695-721;
+ * library/src/level2/aoclsparse_csrmv.cpp:30-63, checks in aoclsparse_csrmv.hpp:63-110): general
+ * and symmetric descriptors only; m==0 / n==0 / nnz==0 return success without touching y.
+ * B200: the CSR arrays are uploaded (or used in place if they are device pointers) on every call. */
+DLL_PUBLIC aoclsparse_status aoclsparse_scsrmv(aoclsparse_operation       trans,
+                                               const float               *alpha,
+                                               aoclsparse_int             m,
+                                               aoclsparse_int             n,
+                                               aoclsparse_int             nnz,
+                                               const float               *csr_val,
+                                               const aoclsparse_int      *csr_col_ind,
+                                               const aoclsparse_int      *csr_row_ptr,
+                                               const aoclsparse_mat_descr descr,
+                                               const float               *x,
+                                               const float               *beta,
+                                               float                     *y);
+DLL_PUBLIC aoclsparse_status aoclsparse_dcsrmv(aoclsparse_operation       trans,
+                                               const double              *alpha,
+                                               aoclsparse_int             m,
+                                               aoclsparse_int             n,
+                                               aoclsparse_int             nnz,
+                                               const double              *csr_val,
+                                               const aoclsparse_int      *csr_col_ind,
+                                               const aoclsparse_int      *csr_row_ptr,
+                                               const aoclsparse_mat_descr descr,
+                                               const double              *x,
+                                               const double              *beta,
+                                               double                    *y);
+
+/* ------------------------------------------------------------------------------------------
+ * Sparse (CSR) x dense product  C = alpha * op(A) * B + beta * C.
+ * Replaces aoclsparse_{s,d,c,z}csrmm (aoclsparse_functions.h:2460-2510) and the _kid variants
+ * (:3397-3452); front end library/src/level3/aoclsparse_csrmm.hpp:429-838, kernels
+ * aoclsparse_csrmm_kt.cpp and aoclsparse_csrmm.hpp:36-427.
+ *
+ * op(A) is m x k; B is k x n and C is m x n, stored row-major (ld = row stride) or column-major
+ * (ld = column stride) as selected by order.  Error precedence (csrmm.hpp:447-618): NULL A/B/C/descr
+ * -> invalid_pointer; bad op -> invalid_value; triangular descr -> not_implemented; symmetric /
+ * hermitian on non-square -> invalid_size; bad order -> invalid_value; value type mismatch ->
+ * wrong_type; base mismatch -> invalid_value; n<0 -> invalid_size; any of m,n,k == 0 or (alpha==0 and
+ * beta==1) -> success, C untouched; ldb / ldc too small or dim*ld overflowing aoclsparse_int ->
+ * invalid_size.  Padding elements of C (between n and ldc) are never written.
+ * ---------------------------------------------------------------------------------------- */
+DLL_PUBLIC aoclsparse_status aoclsparse_scsrmm(aoclsparse_operation       op,
+                                               const float                alpha,
+                                               const aoclsparse_matrix    A,
+                                               const aoclsparse_mat_descr descr,
+                                               aoclsparse_order           order,
+                                               const float               *B,
+                                               aoclsparse_int             n,
+                                               aoclsparse_int             ldb,
+                                               const float                beta,
+                                               float                     *C,
+                                               aoclsparse_int             ldc);
+DLL_PUBLIC aoclsparse_status aoclsparse_dcsrmm(aoclsparse_operation       op,
+                                               const double               alpha,
+                                               const aoclsparse_matrix    A,
+                                               const aoclsparse_mat_descr descr,
+                                               aoclsparse_order           order,
+                                               const double              *B,
+                                               aoclsparse_int             n,
+                                               aoclsparse_int             ldb,
+                                               const double               beta,
+                                               double                    *C,
+                                               aoclsparse_int             ldc);
+DLL_PUBLIC aoclsparse_status aoclsparse_ccsrmm(aoclsparse_operation            op,
+                                               const aoclsparse_float_complex  alpha,
+                                               const aoclsparse_matrix         A,
+                                               const aoclsparse_mat_descr      descr,
+                                               aoclsparse_order                order,
+                                               const aoclsparse_float_complex *B,
+                                               aoclsparse_int                  n,
+                                               aoclsparse_int                  ldb,
+                                               const aoclsparse_float_complex  beta,
+                                               aoclsparse_float_complex       *C,
+                                               aoclsparse_int                  ldc);
+DLL_PUBLIC aoclsparse_status aoclsparse_zcsrmm(aoclsparse_operation             op,
+                                               const aoclsparse_double_complex  alpha,
+                                               const aoclsparse_matrix          A,
+                                               const aoclsparse_mat_descr       descr,
+                                               aoclsparse_order                 order,
+                                               const aoclsparse_double_complex *B,
+                                               aoclsparse_int                   n,
+                                               aoclsparse_int                   ldb,
+                                               const aoclsparse_double_complex  beta,
+                                               aoclsparse_double_complex       *C,
+                                               aoclsparse_int                   ldc);
+DLL_PUBLIC aoclsparse_status aoclsparse_scsrmm_kid(aoclsparse_operation       op,
+                                                   const float                alpha,
+                                                   const aoclsparse_matrix    A,
+                                                   const aoclsparse_mat_descr descr,
+                                                   aoclsparse_order           order,
+                                                   const float               *B,
+                                                   aoclsparse_int             n,
+                                                   aoclsparse_int             ldb,
+                                                   const float                beta,
+                                                   float                     *C,
+                                                   aoclsparse_int             ldc,
+                                                   const aoclsparse_int       kid);
+DLL_PUBLIC aoclsparse_status aoclsparse_dcsrmm_kid(aoclsparse_operation       op,
+                                                   const double               alpha,
+                                                   const aoclsparse_matrix    A,
+                                                   const aoclsparse_mat_descr descr,
+                                                   aoclsparse_order           order,
+                                                   const double              *B,
+                                                   aoclsparse_int             n,
+                                                   aoclsparse_int             ldb,
+                                                   const double               beta,
+                                                   double                    *C,
+                                                   aoclsparse_int             ldc,
+                                                   const aoclsparse_int       kid);
+DLL_PUBLIC aoclsparse_status aoclsparse_ccsrmm_kid(aoclsparse_operation            op,
+                                                   const aoclsparse_float_complex  alpha,
+                                                   const aoclsparse_matrix         A,
+                                                   const aoclsparse_mat_descr      descr,
+                                                   aoclsparse_order                order,
+                                                   const aoclsparse_float_complex *B,
+                                                   aoclsparse_int                  n,
+                                                   aoclsparse_int                  ldb,
+                                                   const aoclsparse_float_complex  beta,
+                                                   aoclsparse_float_complex       *C,
+                                                   aoclsparse_int                  ldc,
+                                                   const aoclsparse_int            kid);
+DLL_PUBLIC aoclsparse_status aoclsparse_zcsrmm_kid(aoclsparse_operation             op,
+                                                   const aoclsparse_double_complex  alpha,
+                                                   const aoclsparse_matrix          A,
+                                                   const aoclsparse_mat_descr       descr,
+                                                   aoclsparse_order                 order,
+                                                   const aoclsparse_double_complex *B,
+                                                   aoclsparse_int                   n,
+                                                   aoclsparse_int                   ldb,
+                                                   const aoclsparse_double_complex  beta,
+                                                   aoclsparse_double_complex       *C,
+                                                   aoclsparse_int                   ldc,
+                                                   const aoclsparse_int             kid);
+
+/* ------------------------------------------------------------------------------------------
+ * aoclsparse_spmm (aoclsparse_functions.h:2257-2261; library/src/level3/aoclsparse_spmm.cpp:27-67).
+ * In the reference this is sparse x sparse -> NEW sparse CSR (an SpGEMM), not sparse x dense.
+ * It is not on the measured path: the symbol is exported with the
+ * reference's argument validation (NULL A/B/C -> invalid_pointer, differing value types ->
+ * wrong_type) and returns aoclsparse_status_not_implemented for valid input.  It never silently
+ * takes csrmm semantics.
+ * ---------------------------------------------------------------------------------------- */
+DLL_PUBLIC aoclsparse_status aoclsparse_spmm(aoclsparse_operation    opA,
+                                             const aoclsparse_matrix A,
+                                             const aoclsparse_matrix B,
+                                             aoclsparse_matrix      *C);
+
+#ifdef __cplusplus
+}
+#endif
+
+#include "aoclsparse_b200.h"
+
+#endif /* AOCLSPARSE_H_B200_ */

@@ -1,0 +1,157 @@
+/* aoclsparse_b200.h -- extensions that have no counterpart in the reference API.
+ *
+ * The reference (AOCL-Sparse v5.3.2) is a single-process CPU library: it has no notion of a CUDA
+ * stream, of where x / y live, of a multi-GPU row partition, and it only exposes its analysis
+ * results to white-box tests that reach into the handle.  Everything a caller needs for those is
+ * collected here under the aoclsparse_b200_ prefix.  Plain C ABI, plain pointers and sizes.
+ */
+#ifndef AOCLSPARSE_B200_H_
+#define AOCLSPARSE_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- execution control ------------------------------------------------------------------ */
+
+/* CUDA stream (a cudaStream_t / CUstream passed as void*) on which the CALLING HOST THREAD's
+ * subsequent aoclsparse_* calls enqueue their work.  NULL selects the legacy default stream. */
+DLL_PUBLIC aoclsparse_status aoclsparse_b200_set_stream(void *cuda_stream);
+DLL_PUBLIC void             *aoclsparse_b200_get_stream(void);
+
+/* Last CUDA error text seen by the calling thread ("" if none); for diagnosing internal_error. */
+DLL_PUBLIC const char *aoclsparse_b200_last_error(void);
+
+/* Number of kernels this library has launched so far in this process (all threads). */
+DLL_PUBLIC unsigned long long aoclsparse_b200_launch_count(void);
+
+/* ---- analysis read-back (black-box replacement for the reference's white-box test hooks) ---- */
+
+/* Facts the reference stores in _aoclsparse_matrix / aoclsparse::csr and that its unit tests read
+ * directly (createcsr_tests.cpp:77-99, optimize_tests.cpp:42-58), plus the GPU plan summary. */
+typedef struct aoclsparse_b200_matrix_info_
+{
+    aoclsparse_int m, n, nnz;
+    int            base;         /* aoclsparse_index_base of the user's arrays                  */
+    int            val_type;     /* aoclsparse_matrix_data_type                                 */
+    int            sort;         /* aoclsparse_matrix_sort, as aoclsparse_mat_check_internal    */
+    int            fulldiag;     /* 1 if every row i < min(m,n) stores its diagonal             */
+    aoclsparse_int min_col;      /* smallest / largest 0-based column index present, or n / -1  */
+    aoclsparse_int max_col;
+    aoclsparse_int max_row_nnz;  /* longest row                                                 */
+    int            optimized;    /* 1 once a plan exists (aoclsparse_optimize or first use)     */
+    int            n_hints;      /* hints recorded so far                                       */
+    int            n_copies;     /* device CSR copies held (1 = the input only)                 */
+    aoclsparse_int block_nnz;    /* plan: nnz capacity of one row block (CTA)                   */
+    aoclsparse_int block_rows;   /* plan: row capacity of one row block                         */
+    aoclsparse_int n_blocks;     /* plan: number of row blocks (= CTAs of the main kernel)      */
+    aoclsparse_int n_thread_blocks; /* blocks binned thread-per-row                             */
+    aoclsparse_int n_warp_blocks;   /* blocks binned warp-per-row                               */
+    aoclsparse_int n_product_blocks; /* blocks binned CTA-wide product + segmented sum          */
+    aoclsparse_int n_long_segments; /* blocks that are one segment of a row split across CTAs   */
+    aoclsparse_int n_long_rows;     /* rows split across CTAs                                   */
+} aoclsparse_b200_matrix_info;
+
+DLL_PUBLIC aoclsparse_status aoclsparse_b200_get_matrix_info(const aoclsparse_matrix      A,
+                                                             aoclsparse_b200_matrix_info *info);
+
+/* Copies the row-block plan of the input CSR copy to host arrays (each may be NULL to skip):
+ *   block_desc[4*b + {0,1,2,3}] = first row, end row, first nnz, end nnz of block b (0-based)
+ *   block_kind[b]               = strategy (0 thread, 1 warp, 2 product, 3 long segment)
+ *                                 | (slot << 4), slot = partial-sum slot of a long segment
+ * capacity = number of blocks the arrays can hold; *n_blocks receives the true count. */
+DLL_PUBLIC aoclsparse_status aoclsparse_b200_get_plan(const aoclsparse_matrix A,
+                                                      aoclsparse_int          capacity,
+                                                      aoclsparse_int         *block_desc,
+                                                      aoclsparse_int         *block_kind,
+                                                      aoclsparse_int         *n_blocks);
+
+/* Dispatch id the reference derives from (descriptor, operation, value type):
+ * aoclsparse::get_doid<T> (library/src/include/aoclsparse_mtx_dispatcher.hpp:79-143).  Returns the
+ * same integer (0..19) or 20 for an invalid combination. */
+DLL_PUBLIC int aoclsparse_b200_doid(const aoclsparse_mat_descr descr, aoclsparse_operation op, int val_type);
+
+/* ---- row-sharded multi-GPU use (one process per GPU; the caller owns the exchange of x) ----- */
+
+/* Declares that the x passed to the following aoclsparse_?mv calls (op = none) on this handle is
+ * NOT the whole vector but the window of global columns [col_lo, col_hi): x[0] is column col_lo.
+ * The matrix keeps its global column indices.  Fails with invalid_index_value if a stored column
+ * falls outside the window.  col_lo = 0, col_hi = n restores normal behaviour. */
+DLL_PUBLIC aoclsparse_status aoclsparse_b200_set_x_window(aoclsparse_matrix A,
+                                                          aoclsparse_int    col_lo,
+                                                          aoclsparse_int    col_hi);
+
+/* Forces row-block boundaries at the given rows (ascending, within (0, m)) so that row ranges can
+ * be multiplied separately; must be called before aoclsparse_optimize. */
+DLL_PUBLIC aoclsparse_status aoclsparse_b200_set_row_cuts(aoclsparse_matrix     A,
+                                                          aoclsparse_int        n_cuts,
+                                                          const aoclsparse_int *cuts);
+
+/* y[row_begin:row_end) = alpha * A[row_begin:row_end, :] * x + beta * y[row_begin:row_end) for a
+ * general matrix, op = none.  row_begin / row_end must be 0, m or one of the row cuts.  Lets the
+ * caller overlap boundary rows, the halo exchange and interior rows on different streams. */
+DLL_PUBLIC aoclsparse_status aoclsparse_b200_dmv_rows(const double              *alpha,
+                                                      aoclsparse_matrix          A,
+                                                      const aoclsparse_mat_descr descr,
+                                                      const double              *x,
+                                                      const double              *beta,
+                                                      double                    *y,
+                                                      aoclsparse_int             row_begin,
+                                                      aoclsparse_int             row_end);
+DLL_PUBLIC aoclsparse_status aoclsparse_b200_smv_rows(const float               *alpha,
+                                                      aoclsparse_matrix          A,
+                                                      const aoclsparse_mat_descr descr,
+                                                      const float               *x,
+                                                      const float               *beta,
+                                                      float                     *y,
+                                                      aoclsparse_int             row_begin,
+                                                      aoclsparse_int             row_end);
+
+/* ---- synthetic matrices of BASELINE.json, generated directly in device memory --------------- */
+
+/* d-dimensional (dims = 2 or 3) stencil on an nx*ny*nz grid (nz = 1 for 2-D), points = 5, 7 or 27,
+ * rows [row_lo, row_hi) of the global matrix only (for sharding), diagonal = points-1, off-diagonals
+ * = -1, columns sorted, base 0.  Pass row_ptr == NULL to only get *nnz (then allocate and call
+ * again).  All pointers are DEVICE pointers; row_ptr has (row_hi-row_lo)+1 entries starting at 0. */
+DLL_PUBLIC aoclsparse_status aoclsparse_b200_gen_stencil(int             points,
+                                                         aoclsparse_int  nx,
+                                                         aoclsparse_int  ny,
+                                                         aoclsparse_int  nz,
+                                                         long long       row_lo,
+                                                         long long       row_hi,
+                                                         long long      *nnz,
+                                                         aoclsparse_int *row_ptr,
+                                                         aoclsparse_int *col_idx,
+                                                         double         *val);
+
+/* u(seed, i) = 2 * (splitmix64(seed * 0x100000001B3 ^ i) >> 11) * 2^-53 - 1 for i in [first, first+count),
+ * written to a DEVICE array as double (elem_size 8) or float (elem_size 4).  SURVEY.md section 8(d). */
+DLL_PUBLIC aoclsparse_status aoclsparse_b200_gen_uniform(unsigned long long seed,
+                                                         long long          first,
+                                                         long long          count,
+                                                         int                elem_size,
+                                                         void              *out);
+
+/* R-MAT (Graph500 parameters a,b,c,d = 0.57,0.19,0.19,0.05) edge keys  row << 32 | col  for edges
+ * [first, first+count) of a 2^scale-vertex graph, written to a DEVICE int64 array; the caller sorts and
+ * de-duplicates them (duplicate diagonal entries are rejected by create). */
+DLL_PUBLIC aoclsparse_status aoclsparse_b200_gen_rmat_keys(unsigned long long seed,
+                                                           int                scale,
+                                                           long long          first,
+                                                           long long          count,
+                                                           long long         *keys);
+
+/* Sorted, unique keys -> CSR (DEVICE arrays; row_ptr has 2^scale+1 entries, base 0) with values
+ * a_ij = (float) u(seed, i * 2^scale + j). */
+DLL_PUBLIC aoclsparse_status aoclsparse_b200_rmat_keys_to_csr(unsigned long long seed,
+                                                              int                scale,
+                                                              long long          count,
+                                                              const long long   *keys,
+                                                              aoclsparse_int    *row_ptr,
+                                                              aoclsparse_int    *col_idx,
+                                                              float             *val);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AOCLSPARSE_B200_H_ */

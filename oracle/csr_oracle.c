@@ -1,0 +1,306 @@
+/* csr_oracle.c -- TEST INFRASTRUCTURE ONLY.
+ *
+ * A scalar, single-threaded CPU restatement, in plain C, of what the reference (AOCL-Sparse v5.3.2,
+ * /root/reference) computes on the CSR SpMV / SpMM path.  It exists so that the parity tests have a
+ * checker that travels to the GPU box, where /root/reference does not exist.  Only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it; the product
+ * library (aocl-sparse_b200/) never does.
+ *
+ * PARITY IS PINNED: tests/test_oracle.py checks every function below against
+ *   (a) the reference's own golden vectors lifted into tests/golden/ (mv_tests.cpp, csrmv_tests.cpp,
+ *       csrmm_tests.cpp, createcsr_tests.cpp, doid_score_tests.cpp, sample_*.c), and
+ *   (b) outputs of the reference itself, compiled from its own sources into
+ *       oracle/_ref/libaoclsparse_ref.so (oracle/Makefile), on seeded random inputs.
+ *
+ * Each function cites the reference file:line it follows.
+ */
+#include <complex.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ---- status / enum values: library/include/aoclsparse_types.h:304-324,396-403 ---- */
+enum
+{
+    ST_SUCCESS = 0,
+    ST_INVALID_POINTER = 2,
+    ST_INVALID_SIZE = 3,
+    ST_INVALID_VALUE = 5,
+    ST_INVALID_INDEX_VALUE = 6
+};
+enum
+{
+    SORT_FULL = 1,
+    SORT_PARTIAL = 2,
+    SORT_NONE = 3
+};
+
+/* CSR validation + classification.
+ * Follows aoclsparse_mat_check_internal, library/src/analysis/aoclsparse_csr_util.cpp:124-279
+ * (shape_general, fast_chck == false): same tests in the same order, so the FIRST failing entry in
+ * storage order decides the status.  val may be any non-NULL pointer (values are never read). */
+int oracle_mat_check(int m, int n, int nnz, const int *rp, const int *col, const void *val, int base,
+                     int *sort_out, int *fulldiag_out)
+{
+    if(!rp || !col || !val)
+        return ST_INVALID_POINTER;
+    if(m < 0 || n < 0 || nnz < 0)
+        return ST_INVALID_SIZE;
+    if(rp[0] - base != 0)
+        return ST_INVALID_VALUE;
+    if(rp[m] - base != nnz)
+        return ST_INVALID_VALUE;
+    for(int i = 1; i <= m; ++i)
+        if(rp[i - 1] > rp[i])
+            return ST_INVALID_VALUE;
+    int sort = SORT_FULL, fulldiag = 1;
+    for(int i = 0; i < m; ++i)
+    {
+        int seen_diag = 0, seen_upper = 0, prev = -1;
+        for(int p = rp[i] - base; p < rp[i + 1] - base; ++p)
+        {
+            const int j = col[p] - base;
+            if(j < 0 || j > n - 1)
+                return ST_INVALID_INDEX_VALUE;
+            if(sort != SORT_NONE)
+            {
+                if(prev > j)
+                    sort = SORT_PARTIAL;
+                else
+                    prev = j;
+                if((j <= i && seen_upper) || (j < i && seen_diag))
+                    sort = SORT_NONE;
+            }
+            if(j > i)
+                seen_upper = 1;
+            else if(j == i)
+            {
+                if(seen_diag)
+                    return ST_INVALID_VALUE;
+                seen_diag = 1;
+            }
+        }
+        if(!seen_diag && i < n)
+            fulldiag = 0;
+    }
+    *sort_out     = sort;
+    *fulldiag_out = fulldiag;
+    return ST_SUCCESS;
+}
+
+/* Dispatch id of (descriptor type, fill mode, operation) for a real or complex value type.
+ * Follows aoclsparse::get_doid<T>, library/src/include/aoclsparse_mtx_dispatcher.hpp:79-143
+ * (numbering :41-74).  20 = invalid. */
+int oracle_doid(int is_complex, int type, int fill, int op)
+{
+    int opv = op - 111;
+    if(opv < 0 || opv > 2)
+        return 20;
+    if(!is_complex)
+    {
+        if(opv == 2)
+            opv = 1;
+        if(type == 2)
+            type = 1;
+    }
+    if(type == 1 && opv == 1)
+        opv = 0;
+    else if(type == 2 && opv == 2)
+        opv = 0;
+    static const int bits[3] = {0, 2, 3};
+    switch(type)
+    {
+    case 0:
+        return bits[opv];
+    case 1:
+        return 4 + 2 * fill + (opv >> 1);
+    case 2:
+        return 8 + 2 * fill + (opv ^ fill);
+    case 3:
+        return 12 + 4 * fill + bits[opv];
+    }
+    return 20;
+}
+
+/* Row-block plan: restates the SPEC at the top of aocl-sparse_b200/csrc/plan.cu (this integer
+ * metadata has no reference counterpart; the GPU analysis must reproduce it bit for bit).
+ * rp is 0-based.  desc (4 ints per block) and kind may be NULL to only count.  Returns n_blocks. */
+int oracle_plan(int m, const int *rp, int T, int R, int forced, int n_cuts, const int *cuts,
+                int capacity, int *desc, int *kind, int *n_long_rows, int *n_long_segments)
+{
+    const long long S   = 64LL * T;
+    const int       nnz = m > 0 ? rp[m] : 0;
+    int             nb = 0, nlr = 0, nls = 0;
+    if(m == 0)
+    {
+        *n_long_rows = *n_long_segments = 0;
+        return 0;
+    }
+    /* segment boundaries */
+    long long ngrid = ((long long)nnz + S - 1) / S - 1;
+    if(ngrid < 0)
+        ngrid = 0;
+    int  nbounds = 0;
+    int *bounds  = (int *)malloc(sizeof(int) * (size_t)(ngrid + n_cuts + 2));
+    bounds[nbounds++] = 0;
+    for(long long kq = 0; kq < ngrid; ++kq)
+    {
+        const long long target = (kq + 1) * S;
+        int             lo = 0, hi = m;
+        while(lo < hi)
+        {
+            int mid = lo + (hi - lo) / 2;
+            if((long long)rp[mid] >= target)
+                hi = mid;
+            else
+                lo = mid + 1;
+        }
+        bounds[nbounds++] = lo;
+    }
+    for(int c = 0; c < n_cuts; ++c)
+        bounds[nbounds++] = cuts[c];
+    bounds[nbounds++] = m;
+    /* sort + unique (insertion sort: the list is short and nearly sorted) */
+    for(int i = 1; i < nbounds; ++i)
+    {
+        int v = bounds[i], j = i - 1;
+        while(j >= 0 && bounds[j] > v)
+        {
+            bounds[j + 1] = bounds[j];
+            --j;
+        }
+        bounds[j + 1] = v;
+    }
+    int u = 0;
+    for(int i = 0; i < nbounds; ++i)
+        if(i == 0 || bounds[i] != bounds[u - 1])
+            bounds[u++] = bounds[i];
+    nbounds = u;
+
+    for(int s = 0; s + 1 < nbounds; ++s)
+    {
+        const int sb = bounds[s + 1];
+        int       r  = bounds[s];
+        while(r < sb)
+        {
+            const int p0 = rp[r], len = rp[r + 1] - rp[r];
+            if(len > T)
+            {
+                const int q = (int)(((long long)len + T - 1) / T);
+                for(int g = 0; g < q; ++g)
+                {
+                    long long a = (long long)p0 + (long long)g * T, b = a + T;
+                    if(b > (long long)p0 + len)
+                        b = (long long)p0 + len;
+                    if(desc && nb + g < capacity)
+                    {
+                        desc[4 * (nb + g) + 0] = r;
+                        desc[4 * (nb + g) + 1] = r + 1;
+                        desc[4 * (nb + g) + 2] = (int)a;
+                        desc[4 * (nb + g) + 3] = (int)b;
+                        kind[nb + g]           = 3 | ((nls + g) << 4);
+                    }
+                }
+                nb += q;
+                nls += q;
+                nlr += 1;
+                r += 1;
+            }
+            else
+            {
+                int hi = (sb - r > R) ? r + R : sb, lo = r + 1;
+                const long long lim = (long long)p0 + T;
+                while(lo < hi)
+                {
+                    int mid = lo + (hi - lo + 1) / 2;
+                    if((long long)rp[mid] <= lim)
+                        lo = mid;
+                    else
+                        hi = mid - 1;
+                }
+                if(desc && nb < capacity)
+                {
+                    int L = 0;
+                    for(int q = r; q < lo; ++q)
+                        if(rp[q + 1] - rp[q] > L)
+                            L = rp[q + 1] - rp[q];
+                    const long long nr = lo - r, nz = rp[lo] - p0;
+                    int             kk;
+                    if(forced >= 0)
+                        kk = forced;
+                    else if(L <= 64 && (long long)L * nr <= 2 * nz + nr)
+                        kk = 0;
+                    else if(nz >= 48 * nr && (long long)L * nr <= 4 * nz)
+                        kk = 1;
+                    else
+                        kk = 2;
+                    desc[4 * nb + 0] = r;
+                    desc[4 * nb + 1] = lo;
+                    desc[4 * nb + 2] = p0;
+                    desc[4 * nb + 3] = rp[lo];
+                    kind[nb]         = kk;
+                }
+                nb += 1;
+                r = lo;
+            }
+        }
+    }
+    free(bounds);
+    *n_long_rows     = nlr;
+    *n_long_segments = nls;
+    return nb;
+}
+
+/* plan_parameters of plan.cu */
+void oracle_plan_parameters(int elem_size, int nnz, int *T, int *R)
+{
+    int t = elem_size >= 16 ? 2048 : 4096;
+    while(t > 512 && (long long)nnz < (long long)t * 148 * 8)
+        t /= 2;
+    *T = t;
+    *R = 1024;
+}
+
+/* ---- multiply kernels, instantiated for the four value types ---- */
+#define CAT2(a, b) a##_##b
+#define CAT(a, b) CAT2(a, b)
+#define NAME(f) CAT(f, SUF)
+
+#define T float
+#define SUF s
+#define CONJ(v) (v)
+#define IS_COMPLEX 0
+#include "csr_oracle_impl.inc"
+#undef T
+#undef SUF
+#undef CONJ
+#undef IS_COMPLEX
+
+#define T double
+#define SUF d
+#define CONJ(v) (v)
+#define IS_COMPLEX 0
+#include "csr_oracle_impl.inc"
+#undef T
+#undef SUF
+#undef CONJ
+#undef IS_COMPLEX
+
+#define T float _Complex
+#define SUF c
+#define CONJ(v) conjf(v)
+#define IS_COMPLEX 1
+#include "csr_oracle_impl.inc"
+#undef T
+#undef SUF
+#undef CONJ
+#undef IS_COMPLEX
+
+#define T double _Complex
+#define SUF z
+#define CONJ(v) conj(v)
+#define IS_COMPLEX 1
+#include "csr_oracle_impl.inc"
+#undef T
+#undef SUF
+#undef CONJ
+#undef IS_COMPLEX

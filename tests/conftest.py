@@ -1,0 +1,115 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "aocl-sparse_b200"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    if _has_gpu():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    import oracle_py
+    return oracle_py.Oracle()
+
+
+@pytest.fixture(scope="session")
+def reflib():
+    """the reference's own build, when present (oracle/_ref travels to the GPU box as a prebuilt file)"""
+    import capi
+    import oracle_py
+    if not os.path.exists(oracle_py.REF_SO):
+        pytest.skip("oracle/_ref/libaoclsparse_ref.so not built")
+    return capi.AoclSparse(oracle_py.REF_SO)
+
+
+@pytest.fixture(scope="session")
+def lib():
+    """the product library; missing library is a hard failure, never a fallback"""
+    import capi
+    return capi.AoclSparse()
+
+
+# ---------------------------------------------------------------------------------------------
+# parity metric of SURVEY.md section 8(d): |y - y_ref| / (sum_j |a_ij||x_j| + |beta*y0_i|) per output
+# entry; 1e-12 for double / double complex, 1e-5 for float / float complex (BASELINE.json north_star)
+# ---------------------------------------------------------------------------------------------
+TOL = {np.dtype(np.float32): 1e-5, np.dtype(np.complex64): 1e-5,
+       np.dtype(np.float64): 1e-12, np.dtype(np.complex128): 1e-12}
+
+
+def effective_dense(m, n, base, rp, col, val, mtype, fill, diag):
+    """dense matrix the (descriptor, CSR) pair stands for; duplicates are summed"""
+    F = np.zeros((m, n), dtype=np.complex128)
+    for i in range(m):
+        for p in range(rp[i] - base, rp[i + 1] - base):
+            j = col[p] - base
+            v = val[p]
+            if mtype == 0:
+                F[i, j] += v
+                continue
+            if j == i:
+                if diag == 0:
+                    F[i, j] += v
+                continue
+            if (j < i) != (fill == 0):
+                continue
+            F[i, j] += v
+            if mtype == 1:
+                F[j, i] += v
+            elif mtype == 2:
+                F[j, i] += np.conj(v)
+    if mtype != 0 and diag == 1:
+        for i in range(min(m, n)):
+            F[i, i] += 1.0
+    return F
+
+
+def apply_op(F, op):
+    return F if op == 111 else (F.T if op == 112 else F.conj().T)
+
+
+def rel_err(y, y_ref, denom):
+    d = np.abs(np.asarray(y, dtype=np.complex128) - np.asarray(y_ref, dtype=np.complex128))
+    den = np.where(denom > 0, denom, 1.0)
+    return float(np.max(d / den)) if d.size else 0.0
+
+
+def mv_denominator(case, rp, col, val, x, y0):
+    """sum_j |op(F)_ij| |alpha x_j| + |beta y0_i| on the dense effective matrix (small cases only)"""
+    F = effective_dense(case["m"], case["n"], case["base"], rp, col, val, case["type"], case["fill"], case["diag"])
+    if case["type"] == 2 and not np.iscomplexobj(val):
+        F = effective_dense(case["m"], case["n"], case["base"], rp, col, val, 1, case["fill"], case["diag"])
+    A = np.abs(apply_op(F, case["op"]))
+    alpha = complex(*case["alpha"]) if isinstance(case["alpha"], (list, tuple)) else case["alpha"]
+    beta = complex(*case["beta"]) if isinstance(case["beta"], (list, tuple)) else case["beta"]
+    den = A @ np.abs(alpha * x.astype(np.complex128))
+    if beta != 0:
+        den = den + np.abs(beta * y0.astype(np.complex128))
+    return den + np.finfo(np.float64).tiny

@@ -1,0 +1,110 @@
+"""ctypes access to oracle/liboracle.so (the plain-C restatement of the reference algorithm).
+
+TEST INFRASTRUCTURE: imported by tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs only.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+ORACLE_SO = os.path.join(ORACLE_DIR, "liboracle.so")
+REF_SO = os.path.join(ORACLE_DIR, "_ref", "libaoclsparse_ref.so")
+
+_SUF = {np.dtype(np.float32): "s", np.dtype(np.float64): "d",
+        np.dtype(np.complex64): "c", np.dtype(np.complex128): "z"}
+
+
+def build_oracle():
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("csr_oracle.c", "csr_oracle_impl.inc")]
+    if not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < max(os.path.getmtime(f) for f in srcs):
+        subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "port"])
+    return ORACLE_SO
+
+
+class FC(C.Structure):
+    _fields_ = [("re", C.c_float), ("im", C.c_float)]
+
+
+class DC(C.Structure):
+    _fields_ = [("re", C.c_double), ("im", C.c_double)]
+
+
+def _scalar(suf, v):
+    if suf == "s":
+        return C.c_float(v)
+    if suf == "d":
+        return C.c_double(v)
+    v = complex(v)
+    return (FC if suf == "c" else DC)(v.real, v.imag)
+
+
+class Oracle:
+    def __init__(self):
+        self.lib = C.CDLL(build_oracle())
+        vp, ci = C.c_void_p, C.c_int
+        self.lib.oracle_mat_check.argtypes = [ci, ci, ci, vp, vp, vp, ci, C.POINTER(ci), C.POINTER(ci)]
+        self.lib.oracle_doid.argtypes = [ci, ci, ci, ci]
+        self.lib.oracle_plan.argtypes = [ci, vp, ci, ci, ci, ci, vp, ci, vp, vp, C.POINTER(ci), C.POINTER(ci)]
+        self.lib.oracle_plan_parameters.argtypes = [ci, ci, C.POINTER(ci), C.POINTER(ci)]
+        for suf, ct in (("s", C.c_float), ("d", C.c_double), ("c", FC), ("z", DC)):
+            getattr(self.lib, f"oracle_csrmv_{suf}").argtypes = [ci, ct, ci, ci, ci, vp, vp, vp, ci, ci, ci, vp, ct, vp]
+            getattr(self.lib, f"oracle_csrmm_{suf}").argtypes = [ci, ct, ci, ci, ci, vp, vp, vp, ci, ci, ci, ci, vp, ci,
+                                                                 C.c_longlong, ct, vp, C.c_longlong]
+
+    def mat_check(self, m, n, nnz, rp, col, base):
+        sort, fd = C.c_int(0), C.c_int(0)
+        dummy = np.zeros(1)
+        st = self.lib.oracle_mat_check(m, n, nnz, rp.ctypes.data, col.ctypes.data if col.size else dummy.ctypes.data,
+                                       dummy.ctypes.data, base, C.byref(sort), C.byref(fd))
+        return st, sort.value, fd.value
+
+    def doid(self, is_complex, mtype, fill, op):
+        return self.lib.oracle_doid(int(is_complex), mtype, fill, op)
+
+    def plan_parameters(self, elem_size, nnz):
+        t, r = C.c_int(0), C.c_int(0)
+        self.lib.oracle_plan_parameters(elem_size, nnz, C.byref(t), C.byref(r))
+        return t.value, r.value
+
+    def plan(self, rp0, T, R, forced=-1, cuts=()):
+        """rp0: 0-based row_ptr.  Returns (desc[nb,4], kind[nb], n_long_rows, n_long_segments)"""
+        m = len(rp0) - 1
+        rp0 = np.ascontiguousarray(rp0, dtype=np.int32)
+        cuts = np.ascontiguousarray(cuts, dtype=np.int32)
+        nlr, nls = C.c_int(0), C.c_int(0)
+        nb = self.lib.oracle_plan(m, rp0.ctypes.data, T, R, forced, len(cuts), cuts.ctypes.data, 0, None, None,
+                                  C.byref(nlr), C.byref(nls))
+        desc = np.zeros((max(nb, 1), 4), dtype=np.int32)
+        kind = np.zeros(max(nb, 1), dtype=np.int32)
+        self.lib.oracle_plan(m, rp0.ctypes.data, T, R, forced, len(cuts), cuts.ctypes.data, nb, desc.ctypes.data,
+                             kind.ctypes.data, C.byref(nlr), C.byref(nls))
+        return desc[:nb], kind[:nb], nlr.value, nls.value
+
+    def csrmv(self, op, alpha, m, n, base, rp, col, val, mtype, fill, diag, x, beta, y):
+        """in-place on y; returns 0 or 1 (not implemented)"""
+        suf = _SUF[val.dtype]
+        assert x.dtype == val.dtype and y.dtype == val.dtype
+        return getattr(self.lib, f"oracle_csrmv_{suf}")(
+            op, _scalar(suf, alpha), m, n, base, rp.ctypes.data, col.ctypes.data, val.ctypes.data, mtype, fill, diag,
+            x.ctypes.data, _scalar(suf, beta), y.ctypes.data)
+
+    def csrmm(self, op, alpha, m, k, base, rp, col, val, mtype, fill, diag, order, B, n, ldb, beta, Cm, ldc):
+        suf = _SUF[val.dtype]
+        return getattr(self.lib, f"oracle_csrmm_{suf}")(
+            op, _scalar(suf, alpha), m, k, base, rp.ctypes.data, col.ctypes.data, val.ctypes.data, mtype, fill, diag,
+            order, B.ctypes.data, n, ldb, _scalar(suf, beta), Cm.ctypes.data, ldc)
+
+
+def row_scale(rp, col, val, x, base=0, beta=0.0, y0=None):
+    """per-row sum |a_ij||x_j| (+ |beta*y0_i|): the denominator of the parity metric"""
+    m = len(rp) - 1
+    contrib = np.abs(val) * np.abs(x[col - base])
+    s = np.zeros(m)
+    rows = np.repeat(np.arange(m), np.diff(rp))
+    np.add.at(s, rows, contrib)
+    if y0 is not None and beta != 0:
+        s += np.abs(beta * y0)
+    return s
