@@ -122,10 +122,11 @@ namespace b200
                                      aoclsparse_int        M,
                                      aoclsparse_int        N,
                                      aoclsparse_int        nnz,
-                                     aoclsparse_int       *row_ptr,
-                                     aoclsparse_int       *col_idx,
-                                     void                 *val,
-                                     int                   val_type)
+                                     const aoclsparse_int *row_ptr,
+                                     const aoclsparse_int *col_idx,
+                                     const void           *val,
+                                     int                   val_type,
+                                     bool                  validate = true)
         {
             if(!mat)
                 return aoclsparse_status_invalid_pointer;
@@ -176,8 +177,8 @@ namespace b200
                     M, N, nnz, (int)base, C->row_ptr.as<aoclsparse_int>(), C->col_idx.as<aoclsparse_int>(), cr, st))
                != aoclsparse_status_success)
                 return fail(s);
-            if(cr.status != aoclsparse_status_success)
-                return fail(cr.status);
+            if(cr.status != aoclsparse_status_success && (validate || cr.status != aoclsparse_status_invalid_value))
+                return fail(cr.status); // (the handle-free legacy entry tolerates duplicate diagonals)
             if(base == aoclsparse_index_base_one)
             {
                 if((s = b200::rebase_to_zero(M, nnz, C->row_ptr.as<aoclsparse_int>(), C->col_idx.as<aoclsparse_int>(), st))
@@ -209,6 +210,25 @@ namespace b200
             return aoclsparse_status_success;
         }
 
+    }
+
+    aoclsparse_status create_temp_csr(aoclsparse_matrix    *mat,
+                                      int                   val_type,
+                                      aoclsparse_index_base base,
+                                      aoclsparse_int        M,
+                                      aoclsparse_int        N,
+                                      aoclsparse_int        nnz,
+                                      const aoclsparse_int *row_ptr,
+                                      const aoclsparse_int *col_idx,
+                                      const void           *val)
+    {
+        if(val_type == aoclsparse_smat)
+            return create_csr<float>(mat, base, M, N, nnz, row_ptr, col_idx, val, val_type, false);
+        return create_csr<double>(mat, base, M, N, nnz, row_ptr, col_idx, val, val_type, false);
+    }
+
+    namespace
+    {
         template <typename T>
         aoclsparse_status update_values(aoclsparse_matrix A, aoclsparse_int len, const void *val)
         {
@@ -622,6 +642,30 @@ int aoclsparse_b200_doid(const aoclsparse_mat_descr descr, aoclsparse_operation 
         return DOID_LEN;
     const bool cplx = val_type == aoclsparse_cmat || val_type == aoclsparse_zmat;
     return get_doid(cplx, descr->type, descr->fill_mode, op);
+}
+
+// ids are [family:3][variant:2]; family 0 general, 1 symmetric, 2 hermitian, 3 / 4 triangular lower / upper
+int aoclsparse_b200_effective_doid(int mat_doid, int req_doid)
+{
+    if(mat_doid < 0 || mat_doid >= DOID_LEN || req_doid < 0 || req_doid >= DOID_LEN)
+        return DOID_LEN;
+    const int mf = mat_doid >> 2, rf = req_doid >> 2, mv = mat_doid & 3, rv = req_doid & 3;
+    if(mf == rf)
+    {
+        // same family: what is left to do is the difference of the two variants; a symmetric /
+        // hermitian copy cannot be turned into the other triangle
+        const bool tri_or_gen = (mf == 0 || mf >= 3);
+        return (tri_or_gen || (mv ^ rv) <= 1) ? (mv ^ rv) : DOID_LEN;
+    }
+    if(mf != 0)
+        return DOID_LEN; // only a general copy can serve another family
+    if(rf >= 3)
+    {
+        // a stored transpose swaps the triangle and the transpose bit, a stored conjugate flips bit 0
+        static const int flip[4] = {0, 1, 6, 7};
+        return 12 + ((req_doid - 12) ^ flip[mv]);
+    }
+    return req_doid ^ mv;
 }
 
 aoclsparse_status aoclsparse_b200_set_x_window(aoclsparse_matrix A, aoclsparse_int col_lo, aoclsparse_int col_hi)

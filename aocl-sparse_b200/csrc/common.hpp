@@ -455,6 +455,17 @@ namespace b200
                                         const dev_csr              *&out,
                                         cudaStream_t                 st);
 
+    // api.cu -- device handle for the handle-free legacy entry (no structural rejection of duplicates)
+    aoclsparse_status create_temp_csr(aoclsparse_matrix    *mat,
+                                      int                   val_type,
+                                      aoclsparse_index_base base,
+                                      aoclsparse_int        M,
+                                      aoclsparse_int        N,
+                                      aoclsparse_int        nnz,
+                                      const aoclsparse_int *row_ptr,
+                                      const aoclsparse_int *col_idx,
+                                      const void           *val);
+
     // obtains (building on first use) the plan of mats[0]
     aoclsparse_status ensure_plan(aoclsparse_matrix A, cudaStream_t st);
 }

@@ -296,6 +296,12 @@ namespace b200
             if(descr->type == aoclsparse_matrix_type_hermitian)
                 return aoclsparse_status_not_implemented;
         }
+        // Reference quirk kept for drop-in fidelity: a GENERAL descriptor whose diag_type is unit / zero
+        // makes the plain product fail with invalid_pointer (mv.cpp:221-226 calls aoclsparse_set_mat_diag on
+        // a matrix that has no diagonal bookkeeping, csr_util.hpp:478-480); transposed products ignore it.
+        if(descr->type == aoclsparse_matrix_type_general && op == aoclsparse_operation_none
+           && descr->diag_type != aoclsparse_diag_type_non_unit && !(A->m == 0 || A->n == 0 || A->nnz == 0))
+            return aoclsparse_status_invalid_pointer;
 
         cudaStream_t    st    = current_stream();
         const long long x_len = (A->win_hi >= 0) ? (long long)(A->win_hi - A->win_lo)
@@ -413,9 +419,96 @@ namespace b200
     }
 }
 
+namespace b200
+{
+    // Handle-free legacy entry: aoclsparse_csrmv_t<T, true> (csrmv.hpp:63-110 for the checks).
+    template <typename T>
+    aoclsparse_status csrmv_legacy(aoclsparse_operation       trans,
+                                   const T                   *alpha,
+                                   aoclsparse_int             m,
+                                   aoclsparse_int             n,
+                                   aoclsparse_int             nnz,
+                                   const T                   *csr_val,
+                                   const aoclsparse_int      *csr_col_ind,
+                                   const aoclsparse_int      *csr_row_ptr,
+                                   const aoclsparse_mat_descr descr,
+                                   const T                   *x,
+                                   const T                   *beta,
+                                   T                         *y)
+    {
+        if(alpha == nullptr || beta == nullptr)
+            return aoclsparse_status_invalid_pointer;
+        if(descr == nullptr)
+            return aoclsparse_status_invalid_pointer;
+        if(descr->base != aoclsparse_index_base_zero && descr->base != aoclsparse_index_base_one)
+            return aoclsparse_status_invalid_value;
+        if(!valid_type(descr->type))
+            return aoclsparse_status_invalid_value;
+        if(!valid_op(trans))
+            return aoclsparse_status_invalid_value;
+        if(descr->type != aoclsparse_matrix_type_general && descr->type != aoclsparse_matrix_type_symmetric)
+            return aoclsparse_status_not_implemented;
+        if(descr->type == aoclsparse_matrix_type_symmetric && m != n)
+            return aoclsparse_status_invalid_size;
+        if(m < 0 || n < 0 || nnz < 0)
+            return aoclsparse_status_invalid_size;
+        if(csr_val == nullptr || csr_row_ptr == nullptr || csr_col_ind == nullptr || x == nullptr || y == nullptr)
+            return aoclsparse_status_invalid_pointer;
+
+        aoclsparse_matrix A = nullptr;
+        B200_TRY(create_temp_csr(&A, vt<T>::data_type, descr->base, m, n, nnz, csr_row_ptr, csr_col_ind, csr_val));
+        _aoclsparse_mat_descr d = *descr;
+        if(d.type == aoclsparse_matrix_type_symmetric)
+        {
+            // the legacy symmetric kernel (aoclsparse_csrmv_symm, csrmv_kr.hpp:41-91) reads the stored LOWER
+            // triangle with its diagonal and ignores fill_mode / diag_type
+            d.fill_mode = aoclsparse_fill_mode_lower;
+            d.diag_type = aoclsparse_diag_type_non_unit;
+        }
+        else
+            d.diag_type = aoclsparse_diag_type_non_unit;
+        aoclsparse_status s = mv_entry<T>(trans, alpha, A, &d, x, beta, y);
+        cudaStreamSynchronize(current_stream());
+        delete A;
+        return s;
+    }
+}
+
 using namespace b200;
 
 extern "C" {
+
+aoclsparse_status aoclsparse_scsrmv(aoclsparse_operation       trans,
+                                    const float               *alpha,
+                                    aoclsparse_int             m,
+                                    aoclsparse_int             n,
+                                    aoclsparse_int             nnz,
+                                    const float               *csr_val,
+                                    const aoclsparse_int      *csr_col_ind,
+                                    const aoclsparse_int      *csr_row_ptr,
+                                    const aoclsparse_mat_descr descr,
+                                    const float               *x,
+                                    const float               *beta,
+                                    float                     *y)
+{
+    return csrmv_legacy<float>(trans, alpha, m, n, nnz, csr_val, csr_col_ind, csr_row_ptr, descr, x, beta, y);
+}
+
+aoclsparse_status aoclsparse_dcsrmv(aoclsparse_operation       trans,
+                                    const double              *alpha,
+                                    aoclsparse_int             m,
+                                    aoclsparse_int             n,
+                                    aoclsparse_int             nnz,
+                                    const double              *csr_val,
+                                    const aoclsparse_int      *csr_col_ind,
+                                    const aoclsparse_int      *csr_row_ptr,
+                                    const aoclsparse_mat_descr descr,
+                                    const double              *x,
+                                    const double              *beta,
+                                    double                    *y)
+{
+    return csrmv_legacy<double>(trans, alpha, m, n, nnz, csr_val, csr_col_ind, csr_row_ptr, descr, x, beta, y);
+}
 
 aoclsparse_status aoclsparse_smv(aoclsparse_operation       op,
                                  const float               *alpha,

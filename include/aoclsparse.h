@@ -259,8 +259,9 @@ DLL_PUBLIC aoclsparse_status aoclsparse_zupdate_values(aoclsparse_matrix        
  * block by its row-length profile into a thread-per-row, warp-per-row or CTA-per-row strategy, and
  * -- when a transposed / symmetric / hermitian mv or mm hint was given and the memory policy is
  * unrestricted -- materialises the transposed / expanded device copy that hint needs.
- * kid (aoclsparse_set_mv_hint_kid) forces a strategy: -1 auto, 0 thread-per-row, 1 warp-per-row,
- * 2 CTA-wide product + segmented sum, 3 row-split (long-row) path for every row.
+ * kid (aoclsparse_set_mv_hint_kid) forces the strategy of every row block: -1 auto, 0 thread-per-row,
+ * 1 warp-per-row, 2 CTA-wide product + segmented sum; any other kid makes aoclsparse_?mv return
+ * aoclsparse_status_invalid_kid, as an unavailable kernel id does in the reference.
  * ---------------------------------------------------------------------------------------- */
 DLL_PUBLIC aoclsparse_status aoclsparse_optimize(aoclsparse_matrix mat);
 DLL_PUBLIC aoclsparse_status aoclsparse_set_mv_hint(aoclsparse_matrix          mat,
@@ -326,8 +327,11 @@ DLL_PUBLIC aoclsparse_status aoclsparse_zmv(aoclsparse_operation             op,
 
 /* Handle-free legacy entry.  Replaces aoclsparse_{s,d}csrmv (aoclsparse_functions.h:695-721;
  * library/src/level2/aoclsparse_csrmv.cpp:30-63, checks in aoclsparse_csrmv.hpp:63-110): general
- * and symmetric descriptors only; m==0 / n==0 / nnz==0 return success without touching y.
- * B200: the CSR arrays are uploaded (or used in place if they are device pointers) on every call. */
+ * and symmetric descriptors only (others: not_implemented); a symmetric descriptor means "lower
+ * triangle with its diagonal stored", fill_mode / diag_type are ignored (aoclsparse_csrmv_symm,
+ * library/src/level2/aoclsparse_csrmv_kr.hpp:41-91).
+ * B200: the CSR arrays are uploaded and analysed on every call -- correct, and as slow as that sounds;
+ * iterated use belongs on aoclsparse_create_?csr + aoclsparse_?mv. */
 DLL_PUBLIC aoclsparse_status aoclsparse_scsrmv(aoclsparse_operation       trans,
                                                const float               *alpha,
                                                aoclsparse_int             m,

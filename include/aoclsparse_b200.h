@@ -71,6 +71,11 @@ DLL_PUBLIC aoclsparse_status aoclsparse_b200_get_plan(const aoclsparse_matrix A,
  * same integer (0..19) or 20 for an invalid combination. */
 DLL_PUBLIC int aoclsparse_b200_doid(const aoclsparse_mat_descr descr, aoclsparse_operation op, int val_type);
 
+/* Dispatch id a kernel must run with when the stored copy has id mat_doid and the request is
+ * req_doid: aoclsparse::get_effective_doid (aoclsparse_mtx_dispatcher.hpp:311-353; table pinned by
+ * tests/unit_tests/doid_score_tests.cpp:236-286).  20 = incompatible. */
+DLL_PUBLIC int aoclsparse_b200_effective_doid(int mat_doid, int req_doid);
+
 /* ---- row-sharded multi-GPU use (one process per GPU; the caller owns the exchange of x) ----- */
 
 /* Declares that the x passed to the following aoclsparse_?mv calls (op = none) on this handle is

@@ -30,35 +30,38 @@ def uniform(seed, first, count, dtype=np.float64):
 
 def stencil(points, nx, ny, nz=1, row_lo=0, row_hi=None, dtype=np.float64):
     """5-point (2-D), 7-point or 27-point (3-D) stencil rows [row_lo,row_hi): diag = points-1, off = -1,
-    columns ascending, base 0.  Returns (row_ptr, col, val) with row_ptr starting at 0."""
+    columns ascending, base 0.  Returns (row_ptr, col, val) with row_ptr starting at 0.
+    Offsets are visited in ascending column order, so an entry's slot in its row is the number of
+    earlier offsets that fall inside the grid: no sort is needed."""
     total = nx * ny * nz
     if row_hi is None:
         row_hi = total
     r = np.arange(row_lo, row_hi, dtype=np.int64)
     ix, iy, iz = r % nx, (r // nx) % ny, r // (nx * ny)
-    cols, vals, rows = [], [], []
+    offs = []
     for dz in (-1, 0, 1):
         for dy in (-1, 0, 1):
             for dx in (-1, 0, 1):
                 off = (dx != 0) + (dy != 0) + (dz != 0)
-                if points != 27 and off > 1:
+                if (points != 27 and off > 1) or (nz == 1 and dz != 0):
                     continue
-                if nz == 1 and dz != 0:
-                    continue
-                x, y, z = ix + dx, iy + dy, iz + dz
-                ok = (x >= 0) & (x < nx) & (y >= 0) & (y < ny) & (z >= 0) & (z < nz)
-                rows.append((r - row_lo)[ok])
-                cols.append(((z * ny + y) * nx + x)[ok])
-                vals.append(np.full(int(ok.sum()), float(points - 1) if off == 0 else -1.0))
-    rows = np.concatenate(rows)
-    cols = np.concatenate(cols)
-    vals = np.concatenate(vals)
-    order = np.lexsort((cols, rows))
-    rows, cols, vals = rows[order], cols[order], vals[order]
-    rp = np.zeros(row_hi - row_lo + 1, dtype=np.int32)
-    np.add.at(rp, rows + 1, 1)
-    rp = np.cumsum(rp, dtype=np.int64).astype(np.int32)
-    return rp, cols.astype(np.int32), vals.astype(dtype)
+                offs.append((dx, dy, dz, off))
+    oks = []
+    cnt = np.zeros(len(r), dtype=np.int64)
+    for (dx, dy, dz, off) in offs:
+        x, y, z = ix + dx, iy + dy, iz + dz
+        ok = (x >= 0) & (x < nx) & (y >= 0) & (y < ny) & (z >= 0) & (z < nz)
+        oks.append((ok, cnt.copy()))
+        cnt += ok
+    rp = np.zeros(len(r) + 1, dtype=np.int64)
+    np.cumsum(cnt, out=rp[1:])
+    col = np.empty(rp[-1], dtype=np.int32)
+    val = np.empty(rp[-1], dtype=dtype)
+    for (dx, dy, dz, off), (ok, before) in zip(offs, oks):
+        pos = (rp[:-1] + before)[ok]
+        col[pos] = (((iz + dz) * ny + (iy + dy)) * nx + (ix + dx))[ok]
+        val[pos] = float(points - 1) if off == 0 else -1.0
+    return rp.astype(np.int32), col, val
 
 
 def rmat_keys(seed, scale, first, count):
