@@ -9,6 +9,7 @@
 //   get_doid               library/src/include/aoclsparse_mtx_dispatcher.hpp:79-143
 #include "common.hpp"
 
+#include <cstdlib>
 #include <new>
 #include <string>
 
@@ -537,6 +538,8 @@ aoclsparse_status aoclsparse_optimize(aoclsparse_matrix A)
             forced = h.kid;
             break;
         }
+    if(const char *e = getenv("AOCLSPARSE_B200_FORCE_KID")) // tuning knob for experiments
+        forced = atoi(e);
     if(!M.plan.valid || forced >= 0)
         B200_TRY(build_plan(M, value_size(A->val_type), forced, A->row_cuts, st));
 

@@ -345,6 +345,8 @@ namespace b200
         aoclsparse_int n_long_rows = 0;
         aoclsparse_int n_long_segments = 0;
         aoclsparse_int n_strat[4] = {0, 0, 0, 0};
+        int            threads     = 256; // CTA size of the multiply kernel (tuning knob)
+        int            stream_hint = 1;   // tag the val/col stream evict-first in L2 (tuning knob)
         dev_buf        desc;      // int4 per block: first row, end row, first nnz, end nnz
         dev_buf        kind;      // int per block: strategy | slot << 4
         dev_buf        long_rows; // int4 per long row: row, first slot, n segments, unused

@@ -73,20 +73,59 @@ namespace b200
                     const int s = rp[r] - a, e = rp[r + 1] - a;
                     for(int c0 = 0; c0 < n; c0 += 128)
                     {
+                        // lanes own columns c0+lane+32q of B / C; 4 non-zeros (4 independent B-row reads per
+                        // owned column) are in flight before the first multiply-add retires
                         T acc[4];
 #pragma unroll
                         for(int q = 0; q < 4; ++q)
                             acc[q] = vt<T>::zero();
-                        for(int j = s; j < e; ++j)
+                        const bool q1 = c0 + lane + 32 < n, q2 = c0 + lane + 64 < n, q3 = c0 + lane + 96 < n;
+                        const bool q0 = c0 + lane < n;
+                        int        j  = s;
+                        for(; j + 4 <= e; j += 4)
+                        {
+                            T        v[4];
+                            const T *br[4];
+#pragma unroll
+                            for(int u = 0; u < 4; ++u)
+                            {
+                                v[u] = sval[j + u];
+                                if(CONJ)
+                                    v[u] = cj(v[u]);
+                                br[u] = B + (long long)scol[j + u] * ldb + c0 + lane;
+                            }
+                            T b0[4], b1[4], b2[4], b3[4];
+#pragma unroll
+                            for(int u = 0; u < 4; ++u)
+                            {
+                                b0[u] = q0 ? ldg_ro(br[u]) : vt<T>::zero();
+                                b1[u] = q1 ? ldg_ro(br[u] + 32) : vt<T>::zero();
+                                b2[u] = q2 ? ldg_ro(br[u] + 64) : vt<T>::zero();
+                                b3[u] = q3 ? ldg_ro(br[u] + 96) : vt<T>::zero();
+                            }
+#pragma unroll
+                            for(int u = 0; u < 4; ++u)
+                            {
+                                acc[0] = mad(v[u], b0[u], acc[0]);
+                                acc[1] = mad(v[u], b1[u], acc[1]);
+                                acc[2] = mad(v[u], b2[u], acc[2]);
+                                acc[3] = mad(v[u], b3[u], acc[3]);
+                            }
+                        }
+                        for(; j < e; ++j)
                         {
                             T v = sval[j];
                             if(CONJ)
                                 v = cj(v);
                             const T *brow = B + (long long)scol[j] * ldb + c0 + lane;
-#pragma unroll
-                            for(int q = 0; q < 4; ++q)
-                                if(c0 + lane + 32 * q < n)
-                                    acc[q] = mad(v, ldg_ro(brow + 32 * q), acc[q]);
+                            if(q0)
+                                acc[0] = mad(v, ldg_ro(brow), acc[0]);
+                            if(q1)
+                                acc[1] = mad(v, ldg_ro(brow + 32), acc[1]);
+                            if(q2)
+                                acc[2] = mad(v, ldg_ro(brow + 64), acc[2]);
+                            if(q3)
+                                acc[3] = mad(v, ldg_ro(brow + 96), acc[3]);
                         }
                         T *crow = C + (long long)r * ldc + c0 + lane;
 #pragma unroll

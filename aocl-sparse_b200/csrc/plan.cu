@@ -25,6 +25,7 @@
 #include "common.hpp"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace b200
 {
@@ -35,11 +36,22 @@ namespace b200
                          aoclsparse_int &block_rows)
     {
         (void)m;
-        // staged bytes per entry = elem_size + 4 (column index)
-        aoclsparse_int T = (elem_size >= 16) ? 2048 : 4096;
+        // staged bytes per entry = elem_size + 4 (column index); ~24 KB per CTA keeps 8 CTAs resident per SM,
+        // which measured best on the 27-point stencil (profiles/r01_sweep_c2.txt): 2048 entries for 8-byte
+        // values, 3072 for 4-byte, 1024 for 16-byte
+        aoclsparse_int T = (aoclsparse_int)((24576 / (elem_size + 4)) / 512 * 512);
+        if(T < 512)
+            T = 512;
         // small matrices: keep at least ~8 CTAs per SM in the grid
         while(T > 512 && (long long)nnz < (long long)T * 148 * 8)
-            T /= 2;
+            T -= 512;
+        // tuning knob for experiments (never set in tests / bench defaults)
+        if(const char *e = getenv("AOCLSPARSE_B200_BLOCK_NNZ"))
+        {
+            const long v = atol(e);
+            if(v >= 256 && v <= 16384)
+                T = (aoclsparse_int)(v & ~3L);
+        }
         block_nnz  = T;
         block_rows = 1024;
     }
@@ -195,6 +207,14 @@ namespace b200
         row_block_plan &P = A.plan;
         P                 = row_block_plan();
         plan_parameters(elem_size, A.m, A.nnz, P.block_nnz, P.block_rows);
+        if(const char *e = getenv("AOCLSPARSE_B200_THREADS"))
+        {
+            const int v = atoi(e);
+            if(v == 128 || v == 256 || v == 512)
+                P.threads = v;
+        }
+        if(const char *e = getenv("AOCLSPARSE_B200_L2HINT"))
+            P.stream_hint = atoi(e) ? 1 : 0;
         const aoclsparse_int T = P.block_nnz, R = P.block_rows;
         const long long      S = 64LL * T;
         const aoclsparse_int *rp = A.row_ptr.as<aoclsparse_int>();

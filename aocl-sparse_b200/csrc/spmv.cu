@@ -35,15 +35,44 @@ namespace b200
             return aoclsparse_status_success;
         }
 
-        template <typename T, bool GENERIC>
-        aoclsparse_status configure_kernel(size_t smem)
+        template <typename T, bool GENERIC, int NT>
+        aoclsparse_status launch_row_blocks(const dev_csr &A,
+                                            int            b0,
+                                            int            b1,
+                                            const T       *x,
+                                            T             *y,
+                                            T              alpha,
+                                            T              beta,
+                                            elem_rule      rule,
+                                            cudaStream_t   st)
         {
+            const row_block_plan &P    = A.plan;
+            const int             cap  = P.block_nnz + 8;
+            const size_t          smem = spmv_smem_bytes(sizeof(T), P.block_nnz);
             static std::atomic<size_t> configured{0};
-            if(configured.load(std::memory_order_acquire) >= smem)
-                return aoclsparse_status_success;
-            B200_CUDA(cudaFuncSetAttribute(
-                spmv_row_blocks_kernel<T, GENERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured.store(smem, std::memory_order_release);
+            if(configured.load(std::memory_order_acquire) < smem)
+            {
+                B200_CUDA(cudaFuncSetAttribute(
+                    spmv_row_blocks_kernel<T, GENERIC, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                configured.store(smem, std::memory_order_release);
+            }
+            spmv_row_blocks_kernel<T, GENERIC, NT><<<b1 - b0, NT, smem, st>>>(P.desc.as<int4>(),
+                                                                               P.kind.as<int>(),
+                                                                               b0,
+                                                                               cap,
+                                                                               A.row_ptr.as<aoclsparse_int>(),
+                                                                               A.col_idx.as<aoclsparse_int>(),
+                                                                               A.val.as<T>(),
+                                                                               x,
+                                                                               y,
+                                                                               alpha,
+                                                                               beta,
+                                                                               is_zero(beta) ? 1 : 0,
+                                                                               P.partials.as<T>(),
+                                                                               rule,
+                                                                               A.n,
+                                                                               P.stream_hint);
+            B200_LAUNCHED();
             return aoclsparse_status_success;
         }
 
@@ -65,48 +94,15 @@ namespace b200
             const row_block_plan &P = A.plan;
             if(b1 <= b0)
                 return aoclsparse_status_success;
-            const int    cap  = P.block_nnz + 8;
-            const size_t smem = spmv_smem_bytes(sizeof(T), P.block_nnz);
-            const int    bz   = is_zero(beta) ? 1 : 0;
+            const int bz = is_zero(beta) ? 1 : 0;
             if(generic)
-            {
-                B200_TRY((configure_kernel<T, true>(smem)));
-                spmv_row_blocks_kernel<T, true><<<b1 - b0, SPMV_THREADS, smem, st>>>(P.desc.as<int4>(),
-                                                                                      P.kind.as<int>(),
-                                                                                      b0,
-                                                                                      cap,
-                                                                                      A.row_ptr.as<aoclsparse_int>(),
-                                                                                      A.col_idx.as<aoclsparse_int>(),
-                                                                                      A.val.as<T>(),
-                                                                                      x,
-                                                                                      y,
-                                                                                      alpha,
-                                                                                      beta,
-                                                                                      bz,
-                                                                                      P.partials.as<T>(),
-                                                                                      rule,
-                                                                                      A.n);
-            }
+                B200_TRY((launch_row_blocks<T, true, 256>(A, b0, b1, x, y, alpha, beta, rule, st)));
+            else if(P.threads == 128)
+                B200_TRY((launch_row_blocks<T, false, 128>(A, b0, b1, x, y, alpha, beta, rule, st)));
+            else if(P.threads == 512)
+                B200_TRY((launch_row_blocks<T, false, 512>(A, b0, b1, x, y, alpha, beta, rule, st)));
             else
-            {
-                B200_TRY((configure_kernel<T, false>(smem)));
-                spmv_row_blocks_kernel<T, false><<<b1 - b0, SPMV_THREADS, smem, st>>>(P.desc.as<int4>(),
-                                                                                       P.kind.as<int>(),
-                                                                                       b0,
-                                                                                       cap,
-                                                                                       A.row_ptr.as<aoclsparse_int>(),
-                                                                                       A.col_idx.as<aoclsparse_int>(),
-                                                                                       A.val.as<T>(),
-                                                                                       x,
-                                                                                       y,
-                                                                                       alpha,
-                                                                                       beta,
-                                                                                       bz,
-                                                                                       P.partials.as<T>(),
-                                                                                       rule,
-                                                                                       A.n);
-            }
-            B200_LAUNCHED();
+                B200_TRY((launch_row_blocks<T, false, 256>(A, b0, b1, x, y, alpha, beta, rule, st)));
             if(P.n_long_rows > 0)
             {
                 const long long threads = (long long)P.n_long_rows * 32;

@@ -90,6 +90,20 @@ namespace b200
                      "r"(smem_u32(bar))
                      : "memory");
     }
+    // same copy, tagged evict-first in L2: the matrix stream is read once per multiply and must not push
+    // x (which every CTA re-reads) out of the 126 MB L2
+    __device__ __forceinline__ void bulk_load_stream(void *dst_smem, const void *src_gmem, unsigned bytes, uint64_t *bar)
+    {
+        uint64_t policy;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                         smem_u32(dst_smem)),
+                     "l"(src_gmem),
+                     "r"(bytes),
+                     "r"(smem_u32(bar)),
+                     "l"(policy)
+                     : "memory");
+    }
     __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
     {
         asm volatile("{\n"
@@ -158,8 +172,8 @@ namespace b200
 
     // GENERIC == false: general matrix, no conjugation (the measured hot path)
     // GENERIC == true : entries filtered / conjugated by `rule` (triangular, symmetric, hermitian parts)
-    template <typename T, bool GENERIC>
-    __global__ void __launch_bounds__(SPMV_THREADS) spmv_row_blocks_kernel(const int4 *__restrict__ desc,
+    template <typename T, bool GENERIC, int NT>
+    __global__ void __launch_bounds__(NT) spmv_row_blocks_kernel(const int4 *__restrict__ desc,
                                                                           const int *__restrict__ kind,
                                                                           int block_first,
                                                                           int cap, // staged capacity in entries
@@ -173,7 +187,8 @@ namespace b200
                                                                           int       beta_zero,
                                                                           T        *partials,
                                                                           elem_rule rule,
-                                                                          int       n_cols)
+                                                                          int       n_cols,
+                                                                          int       stream_hint)
     {
         extern __shared__ __align__(16) unsigned char smem_raw[];
         uint64_t       *bar  = reinterpret_cast<uint64_t *>(smem_raw);
@@ -200,8 +215,16 @@ namespace b200
             if(cnt > 0)
             {
                 mbar_expect_tx(bar, (unsigned)(cnt * (sizeof(T) + sizeof(aoclsparse_int))));
-                bulk_load(sval, val + a, (unsigned)(cnt * sizeof(T)), bar);
-                bulk_load(scol, col + a, (unsigned)(cnt * sizeof(aoclsparse_int)), bar);
+                if(stream_hint)
+                {
+                    bulk_load_stream(sval, val + a, (unsigned)(cnt * sizeof(T)), bar);
+                    bulk_load_stream(scol, col + a, (unsigned)(cnt * sizeof(aoclsparse_int)), bar);
+                }
+                else
+                {
+                    bulk_load(sval, val + a, (unsigned)(cnt * sizeof(T)), bar);
+                    bulk_load(scol, col + a, (unsigned)(cnt * sizeof(aoclsparse_int)), bar);
+                }
             }
         }
         __syncthreads();
@@ -210,7 +233,7 @@ namespace b200
 
         if(strat == STRAT_THREAD)
         {
-            for(int r = d.x + tid; r < d.y; r += SPMV_THREADS)
+            for(int r = d.x + tid; r < d.y; r += NT)
             {
                 int       j   = rp[r] - a;
                 const int e   = rp[r + 1] - a;
@@ -241,7 +264,7 @@ namespace b200
         }
         else if(strat == STRAT_WARP)
         {
-            for(int r = d.x + warp; r < d.y; r += SPMV_THREADS / 32)
+            for(int r = d.x + warp; r < d.y; r += NT / 32)
             {
                 const int s = rp[r] - a, e = rp[r + 1] - a;
                 T         acc = vt<T>::zero();
@@ -270,7 +293,7 @@ namespace b200
             if constexpr(!GENERIC)
             {
                 const int first = ns - a, total = ne - ns;
-                for(int i = tid; i < total; i += SPMV_THREADS)
+                for(int i = tid; i < total; i += NT)
                 {
                     const int j = first + i;
                     sval[j]     = mul(sval[j], ldg_ro(x + scol[j]));
@@ -278,7 +301,7 @@ namespace b200
                 __syncthreads();
             }
             // phase B: per-row sums; 32 consecutive rows per warp pass
-            for(int rb = d.x + warp * 32; rb < d.y; rb += SPMV_THREADS)
+            for(int rb = d.x + warp * 32; rb < d.y; rb += NT)
             {
                 const int  r     = rb + lane;
                 const bool valid = r < d.y;
@@ -333,7 +356,7 @@ namespace b200
             const int first = ns - a, total = ne - ns;
             const int r     = d.x;
             T         acc   = vt<T>::zero();
-            for(int i = tid; i < total; i += SPMV_THREADS)
+            for(int i = tid; i < total; i += NT)
             {
                 const int j = first + i;
                 const int c = scol[j];
@@ -343,7 +366,7 @@ namespace b200
                     acc = generic_term(rule, r, c, sval[j], x, acc);
             }
             acc = warp_sum(acc);
-            __shared__ T s_part[SPMV_THREADS / 32];
+            __shared__ T s_part[NT / 32];
             if(lane == 0)
                 s_part[warp] = acc;
             __syncthreads();
@@ -351,7 +374,7 @@ namespace b200
             {
                 T tot = s_part[0];
 #pragma unroll
-                for(int w = 1; w < SPMV_THREADS / 32; ++w)
+                for(int w = 1; w < NT / 32; ++w)
                     tot = add(tot, s_part[w]);
                 partials[k >> 4] = tot;
             }

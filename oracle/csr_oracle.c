@@ -253,9 +253,11 @@ int oracle_plan(int m, const int *rp, int T, int R, int forced, int n_cuts, cons
 /* plan_parameters of plan.cu */
 void oracle_plan_parameters(int elem_size, int nnz, int *T, int *R)
 {
-    int t = elem_size >= 16 ? 2048 : 4096;
+    int t = (24576 / (elem_size + 4)) / 512 * 512;
+    if(t < 512)
+        t = 512;
     while(t > 512 && (long long)nnz < (long long)t * 148 * 8)
-        t /= 2;
+        t -= 512;
     *T = t;
     *R = 1024;
 }
