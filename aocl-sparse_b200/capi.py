@@ -15,7 +15,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libaoclsparse_b200.so")
+LIB_PATH = os.environ.get("AOCLSPARSE_B200_LIB", os.path.join(HERE, "libaoclsparse_b200.so"))
 
 # enum values: library/include/aoclsparse_types.h of the reference
 OP_N, OP_T, OP_H = 111, 112, 113

@@ -91,7 +91,7 @@ namespace b200
         std::unique_lock<std::shared_mutex> wl(A->guard);
         if(A->mats[0]->plan.valid)
             return aoclsparse_status_success;
-        return build_plan(*A->mats[0], value_size(A->val_type), -1, A->row_cuts, st);
+        return build_plan(*A->mats[0], value_size(A->val_type), A->max_row_nnz, -1, A->row_cuts, st);
     }
 
     namespace
@@ -541,7 +541,7 @@ aoclsparse_status aoclsparse_optimize(aoclsparse_matrix A)
     if(const char *e = getenv("AOCLSPARSE_B200_FORCE_KID")) // tuning knob for experiments
         forced = atoi(e);
     if(!M.plan.valid || forced >= 0)
-        B200_TRY(build_plan(M, value_size(A->val_type), forced, A->row_cuts, st));
+        B200_TRY(build_plan(M, value_size(A->val_type), A->max_row_nnz, forced, A->row_cuts, st));
 
     // transposed device copies for general transposed mv / mm hints (memory policy permitting):
     // they turn the atomic scatter into a streaming gather
@@ -563,7 +563,7 @@ aoclsparse_status aoclsparse_optimize(aoclsparse_matrix A)
                         return aoclsparse_status_memory_error;
                     aoclsparse_status s = transpose_csr(M, A->val_type, h.doid == DOID_GH, *C, st);
                     if(s == aoclsparse_status_success)
-                        s = build_plan(*C, value_size(A->val_type), -1, std::vector<aoclsparse_int>(), st);
+                        s = build_plan(*C, value_size(A->val_type), -1, -1, std::vector<aoclsparse_int>(), st);
                     if(s != aoclsparse_status_success)
                     {
                         delete C;

@@ -345,6 +345,7 @@ namespace b200
         aoclsparse_int n_long_rows = 0;
         aoclsparse_int n_long_segments = 0;
         aoclsparse_int n_strat[4] = {0, 0, 0, 0};
+        aoclsparse_int max_block_rows = 0; // most rows any block holds (sizes the staged row_ptr slice)
         int            threads     = 256; // CTA size of the multiply kernel (tuning knob)
         int            stream_hint = 1;   // tag the val/col stream evict-first in L2 (tuning knob)
         dev_buf        desc;      // int4 per block: first row, end row, first nnz, end nnz
@@ -437,12 +438,14 @@ namespace b200
     // plan.cu -- row-block analysis
     aoclsparse_status build_plan(dev_csr                           &A,
                                  size_t                             elem_size,
+                                 aoclsparse_int                     max_row_nnz, // longest row, < 0 if unknown
                                  aoclsparse_int                     forced_strategy,
                                  const std::vector<aoclsparse_int> &row_cuts,
                                  cudaStream_t                       st);
     void              plan_parameters(size_t          elem_size,
                                       aoclsparse_int  m,
                                       aoclsparse_int  nnz,
+                                      aoclsparse_int  max_row_nnz,
                                       aoclsparse_int &block_nnz,
                                       aoclsparse_int &block_rows);
 

@@ -16,6 +16,8 @@
 // beta == 0 overwrites C without reading it.
 #include "spmv_kernels.cuh"
 
+#include <cstdint>
+
 namespace b200
 {
     namespace
@@ -139,6 +141,202 @@ namespace b200
             {
                 // one segment of a long row: warps split the entries, results are added atomically to
                 // the row of C that scale_dense_kernel already multiplied by beta
+                const int r = d.x, first = ns - a, total = ne - ns;
+                for(int c0 = 0; c0 < n; c0 += 32)
+                {
+                    T acc = vt<T>::zero();
+                    if(c0 + lane < n)
+                        for(int i = warp; i < total; i += MM_THREADS / 32)
+                        {
+                            T v = sval[first + i];
+                            if(CONJ)
+                                v = cj(v);
+                            acc = mad(v, ldg_ro(B + (long long)scol[first + i] * ldb + c0 + lane), acc);
+                        }
+                    if(c0 + lane < n)
+                        atomic_accumulate(C + (long long)r * ldc + c0 + lane, mul(alpha, acc));
+                }
+            }
+        }
+
+        // 16-byte vectors of T
+        template <typename T>
+        struct vec16
+        {
+            static constexpr int N = 16 / sizeof(T);
+            T                    v[N];
+        };
+        template <typename T>
+        __device__ __forceinline__ vec16<T> load_vec(const T *p)
+        {
+            const int4 raw = __ldg(reinterpret_cast<const int4 *>(p));
+            vec16<T>   r;
+            memcpy(&r, &raw, 16);
+            return r;
+        }
+        template <typename T>
+        __device__ __forceinline__ void store_vec(T *p, const vec16<T> &v)
+        {
+            int4 raw;
+            memcpy(&raw, &v, 16);
+            *reinterpret_cast<int4 *>(p) = raw;
+        }
+
+        // ROW MAJOR, vectorised: LPR lanes share one row of A and together own LPR*2 16-byte vectors of the
+        // B / C row (n = 32 doubles: 8 lanes x 2 vectors x 2 doubles), so a warp advances 32/LPR rows of A at a
+        // time and every non-zero costs two 128-bit loads per lane instead of one 64-bit load per column.
+        // Needs 16-byte aligned B / C rows and n a multiple of the vector width (checked by the launcher).
+        template <typename T, bool CONJ, int LPR>
+        __global__ void __launch_bounds__(MM_THREADS) csrmm_row_major_vec_kernel(const int4 *__restrict__ desc,
+                                                                                const int *__restrict__ kind,
+                                                                                int cap,
+                                                                                const aoclsparse_int *__restrict__ rp,
+                                                                                const aoclsparse_int *__restrict__ col,
+                                                                                const T *__restrict__ val,
+                                                                                const T *__restrict__ B,
+                                                                                long long ldb,
+                                                                                T *__restrict__ C,
+                                                                                long long ldc,
+                                                                                int       n,
+                                                                                T         alpha,
+                                                                                T         beta,
+                                                                                int       beta_zero)
+        {
+            constexpr int VEC = vec16<T>::N;
+            constexpr int RPW = 32 / LPR;        // rows of A per warp pass
+            constexpr int CPP = LPR * 2 * VEC;   // columns of B per pass
+            extern __shared__ __align__(16) unsigned char smem_raw[];
+            uint64_t       *bar  = reinterpret_cast<uint64_t *>(smem_raw);
+            T              *sval = reinterpret_cast<T *>(smem_raw + SMEM_HEADER);
+            aoclsparse_int *scol = reinterpret_cast<aoclsparse_int *>(smem_raw + SMEM_HEADER + (size_t)cap * sizeof(T));
+
+            const int  tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+            const int  sub = lane / LPR, sl = lane % LPR;
+            const int4 d     = desc[blockIdx.x];
+            const int  strat = kind[blockIdx.x] & 15;
+            const int  ns = d.z, ne = d.w;
+            const int  a   = ns & ~3;
+            const int  cnt = ((ne - a) + 3) & ~3;
+            if(tid == 0)
+            {
+                mbar_init(bar, 1);
+                mbar_init_fence();
+                if(cnt > 0)
+                {
+                    mbar_expect_tx(bar, (unsigned)(cnt * (sizeof(T) + sizeof(aoclsparse_int))));
+                    bulk_load_stream(sval, val + a, (unsigned)(cnt * sizeof(T)), bar);
+                    bulk_load_stream(scol, col + a, (unsigned)(cnt * sizeof(aoclsparse_int)), bar);
+                }
+            }
+            __syncthreads();
+            if(cnt > 0)
+                mbar_wait(bar, 0);
+
+            if(strat != STRAT_LONG)
+            {
+                for(int rb = d.x + warp * RPW; rb < d.y; rb += (MM_THREADS / 32) * RPW)
+                {
+                    const int  r     = rb + sub;
+                    const bool valid = r < d.y;
+                    int        s = 0, e = 0;
+                    if(valid)
+                    {
+                        s = rp[r] - a;
+                        e = rp[r + 1] - a;
+                    }
+                    for(int c0 = 0; c0 < n; c0 += CPP)
+                    {
+                        const int  ca = c0 + sl * VEC, cb = c0 + (LPR + sl) * VEC;
+                        const bool pa = ca < n, pb = cb < n;
+                        vec16<T>   acc_a, acc_b;
+#pragma unroll
+                        for(int q = 0; q < VEC; ++q)
+                            acc_a.v[q] = acc_b.v[q] = vt<T>::zero();
+                        int j = s;
+                        for(; j + 2 <= e; j += 2)
+                        {
+                            T v0 = sval[j], v1 = sval[j + 1];
+                            if(CONJ)
+                            {
+                                v0 = cj(v0);
+                                v1 = cj(v1);
+                            }
+                            const T *b0 = B + (long long)scol[j] * ldb;
+                            const T *b1 = B + (long long)scol[j + 1] * ldb;
+                            vec16<T> x0a, x0b, x1a, x1b;
+                            if(pa)
+                            {
+                                x0a = load_vec(b0 + ca);
+                                x1a = load_vec(b1 + ca);
+                            }
+                            if(pb)
+                            {
+                                x0b = load_vec(b0 + cb);
+                                x1b = load_vec(b1 + cb);
+                            }
+                            if(pa)
+                            {
+#pragma unroll
+                                for(int q = 0; q < VEC; ++q)
+                                    acc_a.v[q] = mad(v1, x1a.v[q], mad(v0, x0a.v[q], acc_a.v[q]));
+                            }
+                            if(pb)
+                            {
+#pragma unroll
+                                for(int q = 0; q < VEC; ++q)
+                                    acc_b.v[q] = mad(v1, x1b.v[q], mad(v0, x0b.v[q], acc_b.v[q]));
+                            }
+                        }
+                        if(j < e)
+                        {
+                            T v0 = sval[j];
+                            if(CONJ)
+                                v0 = cj(v0);
+                            const T *b0 = B + (long long)scol[j] * ldb;
+                            if(pa)
+                            {
+                                const vec16<T> x0a = load_vec(b0 + ca);
+#pragma unroll
+                                for(int q = 0; q < VEC; ++q)
+                                    acc_a.v[q] = mad(v0, x0a.v[q], acc_a.v[q]);
+                            }
+                            if(pb)
+                            {
+                                const vec16<T> x0b = load_vec(b0 + cb);
+#pragma unroll
+                                for(int q = 0; q < VEC; ++q)
+                                    acc_b.v[q] = mad(v0, x0b.v[q], acc_b.v[q]);
+                            }
+                        }
+                        if(valid)
+                        {
+                            T *crow = C + (long long)r * ldc;
+                            if(pa)
+                            {
+                                vec16<T> o;
+                                if(!beta_zero)
+                                    o = load_vec(crow + ca);
+#pragma unroll
+                                for(int q = 0; q < VEC; ++q)
+                                    o.v[q] = axpby_out(alpha, acc_a.v[q], beta, beta_zero != 0, &o.v[q]);
+                                store_vec(crow + ca, o);
+                            }
+                            if(pb)
+                            {
+                                vec16<T> o;
+                                if(!beta_zero)
+                                    o = load_vec(crow + cb);
+#pragma unroll
+                                for(int q = 0; q < VEC; ++q)
+                                    o.v[q] = axpby_out(alpha, acc_b.v[q], beta, beta_zero != 0, &o.v[q]);
+                                store_vec(crow + cb, o);
+                            }
+                        }
+                    }
+                }
+            }
+            else
+            {
                 const int r = d.x, first = ns - a, total = ne - ns;
                 for(int c0 = 0; c0 < n; c0 += 32)
                 {
@@ -363,7 +561,48 @@ namespace b200
                                                                          P.n_long_rows);
                 B200_LAUNCHED();
             }
-            if(order == aoclsparse_order_row)
+            constexpr int VEC = 16 / (int)sizeof(T);
+            const bool    vec_ok = order == aoclsparse_order_row && (n % VEC) == 0 && (ldb % VEC) == 0 && (ldc % VEC) == 0
+                                && ((uintptr_t)B % 16) == 0 && ((uintptr_t)C % 16) == 0;
+            if(vec_ok)
+            {
+                const int vecs = n / VEC; // 16-byte vectors per row; LPR lanes x 2 vectors per pass
+                const int lpr  = vecs <= 8 ? 4 : (vecs <= 16 ? 8 : (vecs <= 32 ? 16 : 32));
+#define B200_MM_VEC(L)                                                                                               \
+    {                                                                                                                \
+        static std::atomic<size_t> cfg{0};                                                                           \
+        if(cfg.load() < smem)                                                                                        \
+        {                                                                                                            \
+            B200_CUDA(cudaFuncSetAttribute(                                                                          \
+                csrmm_row_major_vec_kernel<T, CONJ, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+            cfg.store(smem);                                                                                         \
+        }                                                                                                            \
+        csrmm_row_major_vec_kernel<T, CONJ, L><<<P.n_blocks, MM_THREADS, smem, st>>>(P.desc.as<int4>(),            \
+                                                                                      P.kind.as<int>(),             \
+                                                                                      cap,                          \
+                                                                                      A.row_ptr.as<aoclsparse_int>(), \
+                                                                                      A.col_idx.as<aoclsparse_int>(), \
+                                                                                      A.val.as<T>(),                \
+                                                                                      B,                            \
+                                                                                      ldb,                          \
+                                                                                      C,                            \
+                                                                                      ldc,                          \
+                                                                                      n,                            \
+                                                                                      alpha,                        \
+                                                                                      beta,                         \
+                                                                                      bz);                          \
+    }
+                if(lpr == 4)
+                    B200_MM_VEC(4)
+                else if(lpr == 8)
+                    B200_MM_VEC(8)
+                else if(lpr == 16)
+                    B200_MM_VEC(16)
+                else
+                    B200_MM_VEC(32)
+#undef B200_MM_VEC
+            }
+            else if(order == aoclsparse_order_row)
             {
                 static std::atomic<size_t> cfg{0};
                 if(cfg.load() < smem)
@@ -589,7 +828,7 @@ namespace b200
                                 return aoclsparse_status_memory_error;
                             status = transpose_csr(*A->mats[0], A->val_type, conj_op, *Cn, st);
                             if(status == aoclsparse_status_success)
-                                status = build_plan(*Cn, sizeof(T), -1, std::vector<aoclsparse_int>(), st);
+                                status = build_plan(*Cn, sizeof(T), -1, -1, std::vector<aoclsparse_int>(), st);
                             Cn->doid = want;
                             if(status == aoclsparse_status_success && Cn != &temp)
                                 A->mats.push_back(Cn);

@@ -284,7 +284,7 @@ namespace b200
             break;
         }
         if(s == aoclsparse_status_success)
-            s = build_plan(*F, value_size(A->val_type), -1, std::vector<aoclsparse_int>(), st);
+            s = build_plan(*F, value_size(A->val_type), -1, -1, std::vector<aoclsparse_int>(), st);
         if(s != aoclsparse_status_success)
         {
             delete F;

@@ -32,14 +32,20 @@ namespace b200
     void plan_parameters(size_t          elem_size,
                          aoclsparse_int  m,
                          aoclsparse_int  nnz,
+                         aoclsparse_int  max_row_nnz,
                          aoclsparse_int &block_nnz,
                          aoclsparse_int &block_rows)
     {
-        (void)m;
         // staged bytes per entry = elem_size + 4 (column index); ~24 KB per CTA keeps 8 CTAs resident per SM,
         // which measured best on the 27-point stencil (profiles/r01_sweep_c2.txt): 2048 entries for 8-byte
         // values, 3072 for 4-byte, 1024 for 16-byte
         aoclsparse_int T = (aoclsparse_int)((24576 / (elem_size + 4)) / 512 * 512);
+        // skewed row lengths (longest row > 16x the mean): x[col] is a random gather and the multiply is bound by
+        // L1 misses (profiles/r01_microbench_gather.txt: 0.9 sectors/clk/SM on a miss, 2.7 on a hit), so leave
+        // more of the 228 KB to L1: ~16 KB staged per CTA (profiles/r01_sweep_c3.txt: 1.09 ms vs 2.03 ms on R-MAT)
+        const long long mean = m > 0 ? (long long)nnz / m : 0;
+        if((long long)max_row_nnz > 16 * (mean > 1 ? mean : 1))
+            T = (aoclsparse_int)((16384 / (elem_size + 4)) / 512 * 512);
         if(T < 512)
             T = 512;
         // small matrices: keep at least ~8 CTAs per SM in the grid
@@ -191,7 +197,10 @@ namespace b200
                 else
                     k = STRAT_PRODUCT;
                 if(lane == 0)
+                {
                     kind[b] = k;
+                    atomicMax(&strat_count[8], d.y - d.x);
+                }
             }
             if(lane == 0)
                 atomicAdd(&strat_count[k & 15], 1);
@@ -200,13 +209,14 @@ namespace b200
 
     aoclsparse_status build_plan(dev_csr                           &A,
                                  size_t                             elem_size,
+                                 aoclsparse_int                     max_row_nnz,
                                  aoclsparse_int                     forced_strategy,
                                  const std::vector<aoclsparse_int> &row_cuts,
                                  cudaStream_t                       st)
     {
         row_block_plan &P = A.plan;
         P                 = row_block_plan();
-        plan_parameters(elem_size, A.m, A.nnz, P.block_nnz, P.block_rows);
+        plan_parameters(elem_size, A.m, A.nnz, max_row_nnz, P.block_nnz, P.block_rows);
         if(const char *e = getenv("AOCLSPARSE_B200_THREADS"))
         {
             const int v = atoi(e);
@@ -313,6 +323,8 @@ namespace b200
         B200_CUDA(cudaStreamSynchronize(st));
         for(int i = 0; i < 4; ++i)
             P.n_strat[i] = sc[i];
+        P.max_block_rows = sc[8] > 1 ? sc[8] : 1;
+
         P.valid = true;
         return aoclsparse_status_success;
     }

@@ -228,6 +228,16 @@ namespace b200
             }
         }
         __syncthreads();
+        // the first row's bounds (and its y for beta != 0) are fetched while the bulk copies are in flight
+        int  pre_s = 0, pre_e = 0;
+        T    pre_y = vt<T>::zero();
+        if(strat == STRAT_THREAD && d.x + tid < d.y)
+        {
+            pre_s = rp[d.x + tid];
+            pre_e = rp[d.x + tid + 1];
+            if(!beta_zero)
+                pre_y = y[d.x + tid];
+        }
         if(cnt > 0)
             mbar_wait(bar, 0);
 
@@ -235,9 +245,10 @@ namespace b200
         {
             for(int r = d.x + tid; r < d.y; r += NT)
             {
-                int       j   = rp[r] - a;
-                const int e   = rp[r + 1] - a;
-                T         acc = vt<T>::zero();
+                const bool first = r == d.x + tid;
+                int        j     = (first ? pre_s : rp[r]) - a;
+                const int  e     = (first ? pre_e : rp[r + 1]) - a;
+                T          acc   = vt<T>::zero();
                 if constexpr(!GENERIC)
                 {
                     for(; j + 4 <= e; j += 4)
@@ -259,7 +270,7 @@ namespace b200
                     if(rule.diag == DIAG_UNIT && r < n_cols)
                         acc = add(acc, ldg_ro(x + r));
                 }
-                y[r] = axpby_out(alpha, acc, beta, beta_zero != 0, y + r);
+                y[r] = axpby_out(alpha, acc, beta, beta_zero != 0, first ? &pre_y : y + r);
             }
         }
         else if(strat == STRAT_WARP)

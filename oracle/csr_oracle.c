@@ -251,9 +251,12 @@ int oracle_plan(int m, const int *rp, int T, int R, int forced, int n_cuts, cons
 }
 
 /* plan_parameters of plan.cu */
-void oracle_plan_parameters(int elem_size, int nnz, int *T, int *R)
+void oracle_plan_parameters(int elem_size, int m, int nnz, int max_row_nnz, int *T, int *R)
 {
-    int t = (24576 / (elem_size + 4)) / 512 * 512;
+    int             t    = (24576 / (elem_size + 4)) / 512 * 512;
+    const long long mean = m > 0 ? (long long)nnz / m : 0;
+    if((long long)max_row_nnz > 16 * (mean > 1 ? mean : 1))
+        t = (16384 / (elem_size + 4)) / 512 * 512;
     if(t < 512)
         t = 512;
     while(t > 512 && (long long)nnz < (long long)t * 148 * 8)

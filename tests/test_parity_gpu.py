@@ -401,7 +401,7 @@ def test_plan_bit_exact(lib, oracle):
                 assert lib.set_mv_hint(h, 111, d, 1) == 0
             assert lib.optimize(h) == 0, lib.last_error()
             info = lib.matrix_info(h)
-            T, R = oracle.plan_parameters(8, len(col))
+            T, R = oracle.plan_parameters(8, m, len(col), int(np.max(np.diff(rp))))
             assert (info.block_nnz, info.block_rows) == (T, R)
             desc, kind = lib.get_plan(h)
             odesc, okind, nlr, nls = oracle.plan(rp, T, R, forced, cuts)
