@@ -132,6 +132,14 @@ class AoclSparse:
             L.aoclsparse_b200_set_row_cuts.argtypes = [vp, i32, vp]
             L.aoclsparse_b200_dmv_rows.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32]
             L.aoclsparse_b200_smv_rows.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32]
+            L.aoclsparse_b200_dmv_rows_push.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, vp]
+            L.aoclsparse_b200_signal.argtypes = [vp, C.c_uint]
+            L.aoclsparse_b200_wait.argtypes = [vp, C.c_uint, vp]
+            L.aoclsparse_b200_ipc_alloc.argtypes = [C.c_size_t, C.POINTER(vp), C.c_char_p]
+            L.aoclsparse_b200_ipc_open.argtypes = [C.c_char_p, C.POINTER(vp)]
+            L.aoclsparse_b200_ipc_close.argtypes = [vp]
+            L.aoclsparse_b200_ipc_free.argtypes = [vp]
+            L.aoclsparse_b200_memcpy.argtypes = [vp, vp, C.c_size_t]
             L.aoclsparse_b200_gen_stencil.argtypes = [ci, i32, i32, i32, C.c_longlong, C.c_longlong,
                                                       C.POINTER(C.c_longlong), vp, vp, vp]
             L.aoclsparse_b200_gen_uniform.argtypes = [C.c_ulonglong, C.c_longlong, C.c_longlong, ci, vp]
@@ -243,3 +251,31 @@ class AoclSparse:
         a = _scalar_by_ref(prefix, alpha)
         b = _scalar_by_ref(prefix, beta)
         return getattr(self.lib, f"aoclsparse_b200_{prefix}mv_rows")(ptr(a), h, descr, ptr(x), ptr(b), ptr(y), r0, r1)
+
+    def mv_rows_push(self, alpha, h, descr, x, beta, y, r0, r1, push_dst):
+        a = _scalar_by_ref("d", alpha)
+        b = _scalar_by_ref("d", beta)
+        return self.lib.aoclsparse_b200_dmv_rows_push(ptr(a), h, descr, ptr(x), ptr(b), ptr(y), r0, r1, ptr(push_dst))
+
+    def signal(self, flag_ptr, value):
+        return self.lib.aoclsparse_b200_signal(C.c_void_p(flag_ptr), value)
+
+    def wait(self, flag_ptr, value, timed_out_ptr=None):
+        return self.lib.aoclsparse_b200_wait(C.c_void_p(flag_ptr), value, C.c_void_p(timed_out_ptr))
+
+    def ipc_alloc(self, nbytes):
+        p = C.c_void_p()
+        h = C.create_string_buffer(64)
+        st = self.lib.aoclsparse_b200_ipc_alloc(nbytes, C.byref(p), h)
+        assert st == 0, (st, self.last_error())
+        return p.value, h.raw
+
+    def memcpy(self, dst, src, nbytes):
+        return self.lib.aoclsparse_b200_memcpy(C.c_void_p(dst), C.c_void_p(src), nbytes)
+
+    def ipc_open(self, handle):
+        p = C.c_void_p()
+        st = self.lib.aoclsparse_b200_ipc_open(handle, C.byref(p))
+        assert st == 0, (st, self.last_error())
+        return p.value
+

@@ -35,7 +35,7 @@ namespace b200
             return aoclsparse_status_success;
         }
 
-        template <typename T, bool GENERIC, int NT>
+        template <typename T, bool GENERIC, int NT, bool PUSH = false>
         aoclsparse_status launch_row_blocks(const dev_csr &A,
                                             int            b0,
                                             int            b1,
@@ -44,7 +44,9 @@ namespace b200
                                             T              alpha,
                                             T              beta,
                                             elem_rule      rule,
-                                            cudaStream_t   st)
+                                            cudaStream_t   st,
+                                            T             *push_dst  = nullptr,
+                                            int            push_row0 = 0)
         {
             const row_block_plan &P    = A.plan;
             const int             cap  = P.block_nnz + 8;
@@ -53,10 +55,10 @@ namespace b200
             if(configured.load(std::memory_order_acquire) < smem)
             {
                 B200_CUDA(cudaFuncSetAttribute(
-                    spmv_row_blocks_kernel<T, GENERIC, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    spmv_row_blocks_kernel<T, GENERIC, NT, PUSH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 configured.store(smem, std::memory_order_release);
             }
-            spmv_row_blocks_kernel<T, GENERIC, NT><<<b1 - b0, NT, smem, st>>>(P.desc.as<int4>(),
+            spmv_row_blocks_kernel<T, GENERIC, NT, PUSH><<<b1 - b0, NT, smem, st>>>(P.desc.as<int4>(),
                                                                                P.kind.as<int>(),
                                                                                b0,
                                                                                cap,
@@ -71,7 +73,9 @@ namespace b200
                                                                                P.partials.as<T>(),
                                                                                rule,
                                                                                A.n,
-                                                                               P.stream_hint);
+                                                                               P.stream_hint,
+                                                                               push_dst,
+                                                                               push_row0);
             B200_LAUNCHED();
             return aoclsparse_status_success;
         }
@@ -89,13 +93,16 @@ namespace b200
                                         T              beta,
                                         bool           generic,
                                         elem_rule      rule,
-                                        cudaStream_t   st)
+                                        cudaStream_t   st,
+                                        T             *push_dst = nullptr)
         {
             const row_block_plan &P = A.plan;
             if(b1 <= b0)
                 return aoclsparse_status_success;
             const int bz = is_zero(beta) ? 1 : 0;
-            if(generic)
+            if(push_dst)
+                B200_TRY((launch_row_blocks<T, false, 256, true>(A, b0, b1, x, y, alpha, beta, rule, st, push_dst, row_lo)));
+            else if(generic)
                 B200_TRY((launch_row_blocks<T, true, 256>(A, b0, b1, x, y, alpha, beta, rule, st)));
             else if(P.threads == 128)
                 B200_TRY((launch_row_blocks<T, false, 128>(A, b0, b1, x, y, alpha, beta, rule, st)));
@@ -118,7 +125,9 @@ namespace b200
                     (generic && rule.diag == DIAG_UNIT) ? 1 : 0,
                     A.n,
                     row_lo,
-                    row_hi);
+                    row_hi,
+                    push_dst,
+                    row_lo);
                 B200_LAUNCHED();
             }
             return aoclsparse_status_success;
@@ -366,7 +375,8 @@ namespace b200
                                     const T                   *beta,
                                     T                         *y,
                                     aoclsparse_int             row_begin,
-                                    aoclsparse_int             row_end)
+                                    aoclsparse_int             row_end,
+                                    T                         *push_dst = nullptr)
     {
         if(!alpha || !beta || !A || !descr || !x || !y)
             return aoclsparse_status_invalid_pointer;
@@ -411,7 +421,7 @@ namespace b200
         if(A->win_hi >= 0)
             x = x - A->win_lo;
         elem_rule none_rule{MASK_NONE, DIAG_KEEP, 0, 0};
-        return launch_gather<T>(M, b0, b1, row_begin, row_end, x, y, *alpha, *beta, false, none_rule, st);
+        return launch_gather<T>(M, b0, b1, row_begin, row_end, x, y, *alpha, *beta, false, none_rule, st, push_dst);
     }
 }
 
@@ -584,5 +594,85 @@ aoclsparse_status aoclsparse_b200_smv_rows(const float               *alpha,
                                            aoclsparse_int             row_end)
 {
     return mv_rows_entry<float>(alpha, A, descr, x, beta, y, row_begin, row_end);
+}
+
+aoclsparse_status aoclsparse_b200_dmv_rows_push(const double              *alpha,
+                                                aoclsparse_matrix          A,
+                                                const aoclsparse_mat_descr descr,
+                                                const double              *x,
+                                                const double              *beta,
+                                                double                    *y,
+                                                aoclsparse_int             row_begin,
+                                                aoclsparse_int             row_end,
+                                                double                    *push_dst)
+{
+    if(!push_dst)
+        return aoclsparse_status_invalid_pointer;
+    return mv_rows_entry<double>(alpha, A, descr, x, beta, y, row_begin, row_end, push_dst);
+}
+
+aoclsparse_status aoclsparse_b200_signal(void *flag, unsigned value)
+{
+    if(!flag)
+        return aoclsparse_status_invalid_pointer;
+    signal_flag_kernel<<<1, 1, 0, current_stream()>>>(static_cast<volatile unsigned *>(flag), value);
+    B200_LAUNCHED();
+    return aoclsparse_status_success;
+}
+
+aoclsparse_status aoclsparse_b200_wait(const void *flag, unsigned value, unsigned *timed_out)
+{
+    if(!flag)
+        return aoclsparse_status_invalid_pointer;
+    wait_flag_kernel<<<1, 1, 0, current_stream()>>>(static_cast<const volatile unsigned *>(flag), value, timed_out);
+    B200_LAUNCHED();
+    return aoclsparse_status_success;
+}
+
+// device memory that other processes on this node can map (cudaIpc*): the x windows and flags of the
+// row-sharded iteration live in such buffers so that neighbours can store into them over NVLink
+aoclsparse_status aoclsparse_b200_ipc_alloc(size_t bytes, void **dptr, unsigned char handle[64])
+{
+    if(!dptr || !handle)
+        return aoclsparse_status_invalid_pointer;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+    B200_CUDA(cudaMalloc(dptr, bytes));
+    B200_CUDA(cudaMemset(*dptr, 0, bytes));
+    cudaIpcMemHandle_t h;
+    B200_CUDA(cudaIpcGetMemHandle(&h, *dptr));
+    memcpy(handle, &h, 64);
+    return aoclsparse_status_success;
+}
+
+aoclsparse_status aoclsparse_b200_ipc_open(const unsigned char handle[64], void **dptr)
+{
+    if(!dptr || !handle)
+        return aoclsparse_status_invalid_pointer;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    B200_CUDA(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return aoclsparse_status_success;
+}
+
+aoclsparse_status aoclsparse_b200_memcpy(void *dst, const void *src, size_t bytes)
+{
+    if(!dst || !src)
+        return aoclsparse_status_invalid_pointer;
+    B200_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, current_stream()));
+    return aoclsparse_status_success;
+}
+
+aoclsparse_status aoclsparse_b200_ipc_close(void *dptr)
+{
+    if(dptr)
+        B200_CUDA(cudaIpcCloseMemHandle(dptr));
+    return aoclsparse_status_success;
+}
+
+aoclsparse_status aoclsparse_b200_ipc_free(void *dptr)
+{
+    if(dptr)
+        B200_CUDA(cudaFree(dptr));
+    return aoclsparse_status_success;
 }
 }

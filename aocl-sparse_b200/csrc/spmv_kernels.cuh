@@ -172,7 +172,10 @@ namespace b200
 
     // GENERIC == false: general matrix, no conjugation (the measured hot path)
     // GENERIC == true : entries filtered / conjugated by `rule` (triangular, symmetric, hermitian parts)
-    template <typename T, bool GENERIC, int NT>
+    // PUSH == true: every computed y[r] is also stored to push_dst[r - push_row0], a buffer that may live in a
+    //                PEER GPU's memory (mapped over NVLink): the boundary rows of a row-sharded matrix write the
+    //                neighbour's halo of the next x directly from this epilogue -- no separate copy or collective.
+    template <typename T, bool GENERIC, int NT, bool PUSH = false>
     __global__ void __launch_bounds__(NT) spmv_row_blocks_kernel(const int4 *__restrict__ desc,
                                                                           const int *__restrict__ kind,
                                                                           int block_first,
@@ -188,7 +191,9 @@ namespace b200
                                                                           T        *partials,
                                                                           elem_rule rule,
                                                                           int       n_cols,
-                                                                          int       stream_hint)
+                                                                          int       stream_hint,
+                                                                          T        *push_dst  = nullptr,
+                                                                          int       push_row0 = 0)
     {
         extern __shared__ __align__(16) unsigned char smem_raw[];
         uint64_t       *bar  = reinterpret_cast<uint64_t *>(smem_raw);
@@ -270,7 +275,10 @@ namespace b200
                     if(rule.diag == DIAG_UNIT && r < n_cols)
                         acc = add(acc, ldg_ro(x + r));
                 }
-                y[r] = axpby_out(alpha, acc, beta, beta_zero != 0, first ? &pre_y : y + r);
+                const T out = axpby_out(alpha, acc, beta, beta_zero != 0, first ? &pre_y : y + r);
+                y[r]        = out;
+                if constexpr(PUSH)
+                    push_dst[r - push_row0] = out;
             }
         }
         else if(strat == STRAT_WARP)
@@ -293,7 +301,10 @@ namespace b200
                     if constexpr(GENERIC)
                         if(rule.diag == DIAG_UNIT && r < n_cols)
                             acc = add(acc, ldg_ro(x + r));
-                    y[r] = axpby_out(alpha, acc, beta, beta_zero != 0, y + r);
+                    const T out = axpby_out(alpha, acc, beta, beta_zero != 0, y + r);
+                    y[r]        = out;
+                    if constexpr(PUSH)
+                        push_dst[r - push_row0] = out;
                 }
             }
         }
@@ -358,7 +369,10 @@ namespace b200
                     if constexpr(GENERIC)
                         if(rule.diag == DIAG_UNIT && r < n_cols)
                             acc = add(acc, ldg_ro(x + r));
-                    y[r] = axpby_out(alpha, acc, beta, beta_zero != 0, y + r);
+                    const T out = axpby_out(alpha, acc, beta, beta_zero != 0, y + r);
+                    y[r]        = out;
+                    if constexpr(PUSH)
+                        push_dst[r - push_row0] = out;
                 }
             }
         }
@@ -405,7 +419,9 @@ namespace b200
                                             int unit_diag,
                                             int n_cols,
                                             int row_lo,
-                                            int row_hi)
+                                            int row_hi,
+                                            T  *push_dst  = nullptr,
+                                            int push_row0 = 0)
     {
         const int lane = threadIdx.x & 31;
         const int w    = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -423,7 +439,10 @@ namespace b200
         {
             if(unit_diag && lr.x < n_cols)
                 acc = add(acc, x[lr.x]);
-            y[lr.x] = axpby_out(alpha, acc, beta, beta_zero != 0, y + lr.x);
+            const T out = axpby_out(alpha, acc, beta, beta_zero != 0, y + lr.x);
+            y[lr.x]     = out;
+            if(push_dst)
+                push_dst[lr.x - push_row0] = out;
         }
     }
 
@@ -440,6 +459,31 @@ namespace b200
                 r = mad(alpha, x[i], r);
             y[i] = r;
         }
+    }
+
+    // cross-GPU flags for the row-sharded iteration: a rank publishes "iteration k done" into a word that lives in
+    // (or is mapped from) its neighbour's memory; the neighbour's stream spins on it before it reuses the buffers
+    static __global__ void signal_flag_kernel(volatile unsigned *flag, unsigned value)
+    {
+        __threadfence_system(); // everything this stream wrote before (peer stores included) is visible first
+        *flag = value;
+        __threadfence_system();
+    }
+    static __global__ void wait_flag_kernel(const volatile unsigned *flag, unsigned value, unsigned *timed_out)
+    {
+        // counts up (iteration numbers), so ">=" tolerates a neighbour that is already further ahead
+        long long spins = 0;
+        while((int)(*flag - value) < 0)
+        {
+            __nanosleep(200);
+            if(++spins > 10000000LL) // a few seconds: a lost peer must not hang the GPU
+            {
+                if(timed_out)
+                    *timed_out = 1;
+                return;
+            }
+        }
+        __threadfence_system();
     }
 
     __device__ __forceinline__ void atomic_accumulate(float *p, float v)

@@ -87,3 +87,100 @@ def allgather_x(slab, own, full, group=None):
     the length-n destination; slabs must be equal-sized for all_gather_into_tensor."""
     dist.all_gather_into_tensor(full, own, group=group)
     return full
+
+
+class PeerHalo:
+    """Halo exchange fused into the multiply: the boundary rows of a slab store their results straight into the
+    neighbours' next-x windows over NVLink (aoclsparse_b200_dmv_rows_push), ordered by stream flags
+    (aoclsparse_b200_signal / _wait) that live in ipc-mapped memory.  No NCCL call on the iteration path.
+
+    Per rank: two x windows W[0], W[1] (ping-pong) and four flag words
+        F[0] left neighbour pushed iteration k      F[1] right neighbour pushed iteration k
+        F[2] left neighbour finished iteration k    F[3] right neighbour finished iteration k
+    Iteration k (cur = W[(k-1)%2], nxt = W[k%2]), all on the compute stream:
+        wait F[2],F[3] >= k-1   neighbours are done reading the buffers I am about to store into
+        wait F[0],F[1] >= k-1   my halos of cur are complete
+        boundary rows -> nxt, pushed into the neighbours' nxt halos;  signal "pushed k" to both
+        interior rows -> nxt;                                         signal "finished k" to both
+    """
+
+    def __init__(self, lib, slab, elem_size=8, group=None):
+        self.lib, self.slab = lib, slab
+        wbytes = (slab.win_hi - slab.win_lo) * elem_size
+        self.w_ptr, self.f_ptr, handles = [], None, []
+        for _ in range(2):
+            p, h = lib.ipc_alloc(wbytes)
+            self.w_ptr.append(p)
+            handles.append(h)
+        self.f_ptr, hf = lib.ipc_alloc(256)
+        handles.append(hf)
+        self.timeout_ptr = self.f_ptr + 128
+        gathered = [None] * slab.world
+        dist.all_gather_object(gathered, handles, group=group)
+        self.peer = {}
+        for nb in (slab.rank - 1, slab.rank + 1):
+            if 0 <= nb < slab.world and slab.halo > 0:
+                hs = gathered[nb]
+                self.peer[nb] = dict(w=[lib.ipc_open(hs[0]), lib.ipc_open(hs[1])], f=lib.ipc_open(hs[2]))
+        self.elem = elem_size
+        # geometry of the neighbours' windows (same construction as ours)
+        self.geo = {nb: make_slab(slab.n_rows_global, slab.world, nb, slab.halo, slab.halo) for nb in self.peer}
+
+    def own_ptr(self, which):
+        return self.w_ptr[which] + self.slab.own_offset * self.elem
+
+    def left_push_dst(self, which):
+        """address of the LEFT neighbour's right halo in its window `which`"""
+        nb = self.slab.rank - 1
+        g = self.geo[nb]
+        return self.peer[nb]["w"][which] + (g.own_offset + g.rows) * self.elem
+
+    def right_push_dst(self, which):
+        """address of the RIGHT neighbour's left halo in its window `which`"""
+        nb = self.slab.rank + 1
+        g = self.geo[nb]
+        return self.peer[nb]["w"][which] + (g.own_offset - self.slab.halo) * self.elem
+
+    def iteration(self, k, alpha, A, descr, beta=0.0):
+        """enqueue iteration k >= 1 on the library's current stream"""
+        lib, s = self.lib, self.slab
+        h, m = s.halo, s.rows
+        cur, nxt = (k - 1) % 2, k % 2
+        L, R = s.rank - 1, s.rank + 1
+        for nb, fin, pushed in ((L, 2, 0), (R, 3, 1)):
+            if nb in self.peer:
+                lib.wait(self.f_ptr + 4 * fin, k - 1, self.timeout_ptr)
+                lib.wait(self.f_ptr + 4 * pushed, k - 1, self.timeout_ptr)
+        x = self.w_ptr[cur]
+        y = self.own_ptr(nxt)
+        if L in self.peer:
+            st = lib.mv_rows_push(alpha, A, descr, x, beta, y, 0, h, self.left_push_dst(nxt))
+        else:
+            st = lib.mv_rows("d", alpha, A, descr, x, beta, y, 0, h)
+        assert st == 0, (st, lib.last_error())
+        if R in self.peer:
+            st = lib.mv_rows_push(alpha, A, descr, x, beta, y, m - h, m, self.right_push_dst(nxt))
+        else:
+            st = lib.mv_rows("d", alpha, A, descr, x, beta, y, m - h, m)
+        assert st == 0, (st, lib.last_error())
+        if L in self.peer:
+            lib.signal(self.peer[L]["f"] + 4 * 1, k)  # I am L's right neighbour
+        if R in self.peer:
+            lib.signal(self.peer[R]["f"] + 4 * 0, k)  # I am R's left neighbour
+        st = lib.mv_rows("d", alpha, A, descr, x, beta, y, h, m - h)
+        assert st == 0, (st, lib.last_error())
+        if L in self.peer:
+            lib.signal(self.peer[L]["f"] + 4 * 3, k)
+        if R in self.peer:
+            lib.signal(self.peer[R]["f"] + 4 * 2, k)
+
+    def initial_push(self, which=0):
+        """one-off: copy my boundary planes of window `which` into the neighbours' halos (before iteration 1)"""
+        import torch
+        s, e = self.slab, self.elem
+        h, m = s.halo, s.rows
+        for nb, src_off in ((s.rank - 1, 0), (s.rank + 1, m - h)):
+            if nb in self.peer:
+                d = self.left_push_dst(which) if nb < s.rank else self.right_push_dst(which)
+                assert self.lib.memcpy(d, self.own_ptr(which) + src_off * e, h * e) == 0, self.lib.last_error()
+        torch.cuda.synchronize()

@@ -343,17 +343,33 @@ def run_gpu(args, wl):
     else:
         wlen = slab.win_hi - slab.win_lo
         off = slab.own_offset
-        bufs = [torch.zeros(wlen, dtype=tdt, device="cuda") for _ in range(2)]
-        lib.lib.aoclsparse_b200_gen_uniform(1, slab.row_lo, m, elem, bufs[0][off:].data_ptr())
+        halo_mode = "none" if world == 1 else os.environ.get("BENCH_HALO", "p2p-push")
+        peer = None
+        if halo_mode == "p2p-push":
+            # x windows live in ipc memory; boundary rows store into the neighbours' halos from the kernel epilogue
+            peer = sharding.PeerHalo(lib, slab, elem)
+            lib.lib.aoclsparse_b200_gen_uniform(1, slab.row_lo, m, elem, C.c_void_p(peer.own_ptr(0)))
+            torch.cuda.synchronize()
+            dist.barrier()
+            peer.initial_push(0)
+            dist.barrier()
+            bufs = None
+        else:
+            bufs = [torch.zeros(wlen, dtype=tdt, device="cuda") for _ in range(2)]
+            lib.lib.aoclsparse_b200_gen_uniform(1, slab.row_lo, m, elem, bufs[0][off:].data_ptr())
         comm_stream = torch.cuda.Stream()
-        state = {"cur": 0, "pending": []}
-        if world > 1:
+        state = {"cur": 0, "k": 0}
+        if world > 1 and peer is None:
             for r in sharding.exchange_halo(slab, bufs[0]):
                 r.wait()
             torch.cuda.synchronize()
             dist.barrier()
 
         def step(i):
+            if peer is not None:
+                state["k"] += 1
+                peer.iteration(state["k"], alpha, A, d, beta)
+                return
             cur, nxt = bufs[state["cur"]], bufs[1 - state["cur"]]
             ydst = nxt[off:].data_ptr()
             if world == 1:
@@ -380,7 +396,7 @@ def run_gpu(args, wl):
             dist.all_reduce(nnz_t)
         g_nnz = int(nnz_t.item())
         g_bytes, g_flops = spmv_bytes_flops(n_glob, n_glob, g_nnz, elem, beta != 0)
-        launches_per_step = 1 if world == 1 else 3
+        launches_per_step = 1 if world == 1 else (3 if peer is None else 3 + 4 * len(peer.peer) + 2 * len(peer.peer))
 
     def barrier():
         if world > 1:
@@ -434,7 +450,11 @@ def run_gpu(args, wl):
         xlen = (slab.win_hi - slab.win_lo) if sharded else n_glob
         hx = torch.empty(xlen, dtype=tdt).pin_memory()
         hy = torch.zeros(m, dtype=tdt).pin_memory()
-        hx.copy_(bufs[0] if sharded else x)
+        if sharded and bufs is None:
+            assert lib.memcpy(hx.data_ptr(), peer.w_ptr[0], xlen * elem) == 0
+            torch.cuda.synchronize()
+        else:
+            hx.copy_(bufs[0] if sharded else x)
         hxp, hyp = hx.data_ptr(), hy.data_ptr()
         call = lambda: lib.mv(p, 111, alpha, A, d, hxp, beta, hyp)  # noqa: E731
         h2d, d2h = xlen * elem + (m * elem if beta != 0 else 0), m * elem
@@ -508,7 +528,7 @@ def run_gpu(args, wl):
         "scaling": "strong" if sharded else "weak", "vs_baseline": None,
         "dtype": {"s": "f32", "d": "f64"}[p], "data": "synthetic",
         "config": {"workload": wl["name"], "rows": int(n_glob if sharded else m), "nnz": int(g_nnz if sharded else nnz),
-                   "parallelism": f"row slabs x{world}, halo exchange" if sharded else "single GPU",
+                   "parallelism": (f"row slabs x{world}, halo: {halo_mode}" if sharded else "single GPU"),
                    "l2": ("operands larger than L2: %.0f MB streamed per step vs 126 MB L2" % (l_bytes / 1e6))
                    if (sharded or wl["kind"] == "mm" or n_sets == 1) else
                    ("rotating over %d independent (A,x,y) sets, %.0f MB in total vs 126 MB L2" % (n_sets, n_sets * l_bytes / 1e6)),

@@ -112,6 +112,34 @@ DLL_PUBLIC aoclsparse_status aoclsparse_b200_smv_rows(const float               
                                                       aoclsparse_int             row_begin,
                                                       aoclsparse_int             row_end);
 
+/* Fused compute + halo push: as aoclsparse_b200_dmv_rows, and every computed y[r] is ALSO stored to
+ * push_dst[r - row_begin].  push_dst may be memory of a PEER GPU mapped into this process
+ * (aoclsparse_b200_ipc_open): the boundary rows of a slab write the neighbour's halo of the next x
+ * straight from the multiply kernel's epilogue over NVLink, with no separate copy or collective. */
+DLL_PUBLIC aoclsparse_status aoclsparse_b200_dmv_rows_push(const double              *alpha,
+                                                           aoclsparse_matrix          A,
+                                                           const aoclsparse_mat_descr descr,
+                                                           const double              *x,
+                                                           const double              *beta,
+                                                           double                    *y,
+                                                           aoclsparse_int             row_begin,
+                                                           aoclsparse_int             row_end,
+                                                           double                    *push_dst);
+
+/* Stream-ordered cross-GPU flags (32-bit words in ipc memory): signal stores `value` after everything the
+ * calling thread's stream did before is visible system-wide; wait holds the stream until *flag >= value
+ * (wrap-safe), setting *timed_out (may be NULL) and giving up after ~4 s. */
+DLL_PUBLIC aoclsparse_status aoclsparse_b200_signal(void *flag, unsigned value);
+DLL_PUBLIC aoclsparse_status aoclsparse_b200_wait(const void *flag, unsigned value, unsigned *timed_out);
+
+/* Device buffers other processes of this node can map (cudaIpcGetMemHandle / cudaIpcOpenMemHandle). */
+DLL_PUBLIC aoclsparse_status aoclsparse_b200_ipc_alloc(size_t bytes, void **dptr, unsigned char handle[64]);
+DLL_PUBLIC aoclsparse_status aoclsparse_b200_ipc_open(const unsigned char handle[64], void **dptr);
+DLL_PUBLIC aoclsparse_status aoclsparse_b200_ipc_close(void *dptr);
+/* cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault) on the calling thread's stream (local or ipc-mapped memory) */
+DLL_PUBLIC aoclsparse_status aoclsparse_b200_memcpy(void *dst, const void *src, size_t bytes);
+DLL_PUBLIC aoclsparse_status aoclsparse_b200_ipc_free(void *dptr);
+
 /* ---- synthetic matrices of BASELINE.json, generated directly in device memory --------------- */
 
 /* d-dimensional (dims = 2 or 3) stencil on an nx*ny*nz grid (nz = 1 for 2-D), points = 5, 7 or 27,

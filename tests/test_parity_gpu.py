@@ -599,6 +599,43 @@ def test_row_sharded_window_and_row_ranges(lib, oracle):
     lib.destroy_descr(d)
 
 
+def test_fused_push_and_flags_single_gpu(lib, oracle):
+    """the fused halo push stores the computed rows to a second buffer (here local memory); the stream flags order
+    work across streams (the 2-GPU path is tests/test_multi_gpu.py)"""
+    import torch
+    rp, col, val = gen_np.stencil(7, 20, 20, 12)
+    m = len(rp) - 1
+    plane = 400
+    x = gen_np.uniform(1, 0, m)
+    st, h = lib.create_csr("d", 0, m, m, len(col), rp, col, val)
+    d = lib.create_descr()
+    assert lib.set_row_cuts(h, [plane, m - plane]) == 0 and lib.optimize(h) == 0
+    dx = torch.from_numpy(x).cuda()
+    dy = torch.zeros(m, dtype=torch.float64, device="cuda")
+    push = torch.full((plane,), float("nan"), dtype=torch.float64, device="cuda")
+    assert lib.mv_rows_push(0.5, h, d, dx.data_ptr(), 0.0, dy.data_ptr(), m - plane, m, push.data_ptr()) == 0
+    torch.cuda.synchronize()
+    yo = np.zeros(m)
+    oracle.csrmv(111, 0.5, m, m, 0, rp, col, val, 0, 0, 0, x, 0.0, yo)
+    assert torch.equal(push, dy[m - plane:])
+    assert np.max(np.abs(push.cpu().numpy() - yo[m - plane:]) / (0.5 * oracle_py.row_scale(rp, col, val, x)[m - plane:])) <= 1e-12
+    # flags: a wait on an already published value passes, values count up (">=" semantics), and a wait that is
+    # never satisfied gives up and reports it instead of hanging the GPU.  (Signal and wait are meant for
+    # DIFFERENT GPUs; on one GPU two streams may share a hardware queue, so a pending wait can block the signal.)
+    flag = torch.zeros(64, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    assert lib.signal(flag.data_ptr(), 3) == 0
+    assert lib.wait(flag.data_ptr(), 3, flag[32:].data_ptr()) == 0
+    assert lib.wait(flag.data_ptr(), 2, flag[32:].data_ptr()) == 0
+    torch.cuda.synchronize()
+    assert (int(flag[0].item()), int(flag[32].item())) == (3, 0)
+    assert lib.wait(flag.data_ptr(), 4, flag[32:].data_ptr()) == 0  # nobody publishes 4
+    torch.cuda.synchronize()
+    assert int(flag[32].item()) == 1
+    lib.destroy(h)
+    lib.destroy_descr(d)
+
+
 # ------------------------------------------------------------------------------------------------
 # full BASELINE sizes: size-independent properties
 # ------------------------------------------------------------------------------------------------
