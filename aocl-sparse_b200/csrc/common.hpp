@@ -346,6 +346,10 @@ namespace b200
         aoclsparse_int n_long_segments = 0;
         aoclsparse_int n_strat[4] = {0, 0, 0, 0};
         aoclsparse_int max_block_rows = 0; // most rows any block holds (sizes the staged row_ptr slice)
+        int            pdl              = 1; // programmatic dependent launch of the multiply kernel (tuning knob)
+        int            pipelined        = 0; // use the persistent pipelined kernel when every block is thread-per-row
+        int            pipe_stages      = 4; // ring depth of that kernel
+        int            pipe_ctas_per_sm = 2;
         int            threads     = 256; // CTA size of the multiply kernel (tuning knob)
         int            stream_hint = 1;   // tag the val/col stream evict-first in L2 (tuning knob)
         dev_buf        desc;      // int4 per block: first row, end row, first nnz, end nnz

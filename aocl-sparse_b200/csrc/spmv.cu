@@ -5,7 +5,7 @@
 //   aoclsparse_csrmv_t<T,false>  library/src/level2/aoclsparse_csrmv.hpp:32-450
 // and launches the sm_100a kernels of spmv_kernels.cuh.  There is no CPU path: if a launch fails the
 // call returns internal_error.
-#include "spmv_kernels.cuh"
+#include "spmv_pipelined.cuh"
 
 namespace b200
 {
@@ -58,24 +58,82 @@ namespace b200
                     spmv_row_blocks_kernel<T, GENERIC, NT, PUSH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 configured.store(smem, std::memory_order_release);
             }
-            spmv_row_blocks_kernel<T, GENERIC, NT, PUSH><<<b1 - b0, NT, smem, st>>>(P.desc.as<int4>(),
-                                                                               P.kind.as<int>(),
-                                                                               b0,
-                                                                               cap,
-                                                                               A.row_ptr.as<aoclsparse_int>(),
-                                                                               A.col_idx.as<aoclsparse_int>(),
-                                                                               A.val.as<T>(),
-                                                                               x,
-                                                                               y,
-                                                                               alpha,
-                                                                               beta,
-                                                                               is_zero(beta) ? 1 : 0,
-                                                                               P.partials.as<T>(),
-                                                                               rule,
-                                                                               A.n,
-                                                                               P.stream_hint,
-                                                                               push_dst,
-                                                                               push_row0);
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim            = dim3((unsigned)(b1 - b0));
+            cfg.blockDim           = dim3(NT);
+            cfg.dynamicSmemBytes   = smem;
+            cfg.stream             = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id                                         = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs                                          = attr;
+            cfg.numAttrs                                       = P.pdl ? 1 : 0;
+            B200_CUDA(cudaLaunchKernelEx(&cfg,
+                                         spmv_row_blocks_kernel<T, GENERIC, NT, PUSH>,
+                                         (const int4 *)P.desc.as<int4>(),
+                                         (const int *)P.kind.as<int>(),
+                                         b0,
+                                         cap,
+                                         (const aoclsparse_int *)A.row_ptr.as<aoclsparse_int>(),
+                                         (const aoclsparse_int *)A.col_idx.as<aoclsparse_int>(),
+                                         (const T *)A.val.as<T>(),
+                                         x,
+                                         y,
+                                         alpha,
+                                         beta,
+                                         is_zero(beta) ? 1 : 0,
+                                         P.partials.as<T>(),
+                                         rule,
+                                         (int)A.n,
+                                         P.stream_hint,
+                                         push_dst,
+                                         push_row0));
+            B200_LAUNCHED();
+            return aoclsparse_status_success;
+        }
+
+        // persistent pipelined kernel (spmv_pipelined.cuh) over blocks [b0, b1): all of them thread-per-row
+        template <typename T>
+        aoclsparse_status launch_pipelined(const dev_csr &A,
+                                           int            b0,
+                                           int            b1,
+                                           const T       *x,
+                                           T             *y,
+                                           T              alpha,
+                                           T              beta,
+                                           cudaStream_t   st,
+                                           T             *push_dst,
+                                           int            push_row0)
+        {
+            const row_block_plan &P      = A.plan;
+            const int             cap    = P.block_nnz + 8;
+            const int             stages = P.pipe_stages;
+            const size_t          smem   = pipe_smem_bytes(sizeof(T), P.block_nnz, stages);
+            static std::atomic<size_t> configured{0};
+            if(configured.load(std::memory_order_acquire) < smem)
+            {
+                B200_CUDA(cudaFuncSetAttribute(
+                    spmv_thread_pipelined_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                configured.store(smem, std::memory_order_release);
+            }
+            int grid = P.pipe_ctas_per_sm * 148;
+            if(grid > b1 - b0)
+                grid = b1 - b0;
+            spmv_thread_pipelined_kernel<T><<<grid, PIPE_THREADS, smem, st>>>(P.desc.as<int4>(),
+                                                                              b0,
+                                                                              b1,
+                                                                              cap,
+                                                                              stages,
+                                                                              A.row_ptr.as<aoclsparse_int>(),
+                                                                              A.col_idx.as<aoclsparse_int>(),
+                                                                              A.val.as<T>(),
+                                                                              x,
+                                                                              y,
+                                                                              alpha,
+                                                                              beta,
+                                                                              is_zero(beta) ? 1 : 0,
+                                                                              push_dst,
+                                                                              push_row0);
             B200_LAUNCHED();
             return aoclsparse_status_success;
         }
@@ -100,6 +158,8 @@ namespace b200
             if(b1 <= b0)
                 return aoclsparse_status_success;
             const int bz = is_zero(beta) ? 1 : 0;
+            if(!generic && P.pipelined && P.n_strat[STRAT_THREAD] == P.n_blocks)
+                return launch_pipelined<T>(A, b0, b1, x, y, alpha, beta, st, push_dst, row_lo);
             if(push_dst)
                 B200_TRY((launch_row_blocks<T, false, 256, true>(A, b0, b1, x, y, alpha, beta, rule, st, push_dst, row_lo)));
             else if(generic)

@@ -208,6 +208,11 @@ namespace b200
         const int  k    = kind[b];
         const int  strat = k & 15;
 
+        // programmatic dependent launch: let the next kernel in the stream start its own prologue (descriptor
+        // read, bulk copies of ITS matrix slice -- none of which depends on this kernel's output) while this grid
+        // drains; see griddepcontrol.wait below
+        asm volatile("griddepcontrol.launch_dependents;");
+
         // staged window: [a, a+cnt) with a 16-byte aligned for both arrays
         const int ns = d.z, ne = d.w;
         const int a   = ns & ~3;
@@ -240,9 +245,12 @@ namespace b200
         {
             pre_s = rp[d.x + tid];
             pre_e = rp[d.x + tid + 1];
-            if(!beta_zero)
-                pre_y = y[d.x + tid];
         }
+        // everything above touched only the matrix; x and y may be the previous kernel's output (iterated
+        // products), so wait here until the grid this launch depends on has completed and flushed
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        if(strat == STRAT_THREAD && d.x + tid < d.y && !beta_zero)
+            pre_y = y[d.x + tid];
         if(cnt > 0)
             mbar_wait(bar, 0);
 

@@ -562,6 +562,44 @@ def test_config4_csrmm(lib, oracle, order):
     lib.destroy_descr(d)
 
 
+@pytest.mark.parametrize("p", ["s", "d", "c", "z"])
+def test_csrmm_vector_paths(lib, oracle, p):
+    """row-major csrmm: every lanes-per-row variant of the 128-bit kernel, the scalar fallback (odd n, padded /
+    unaligned leading dimensions), long rows split across CTAs, beta != 0, device and host operands"""
+    import torch
+    rng = np.random.default_rng(23)
+    dt = DT[p]
+    rp, col, val = _skewed(rng, 3000, 3)
+    val = val.astype(dt)
+    if p in "cz":
+        val = (val + 1j * rng.normal(size=len(val))).astype(dt)
+    m = len(rp) - 1
+    st, h = lib.create_csr(p, 0, m, m, len(col), rp, col, val)
+    assert st == 0
+    d = lib.create_descr()
+    import scipy.sparse as sp
+    Aabs = sp.csr_matrix((np.abs(val), col, rp), shape=(m, m))
+    for n, pad in ((2, 0), (4, 0), (8, 0), (16, 0), (32, 0), (64, 0), (100, 0), (128, 0), (200, 0), (37, 0), (32, 3), (32, 4)):
+        ldb = ldc = n + pad
+        B = rng.normal(size=m * ldb).astype(dt)
+        C0 = rng.normal(size=m * ldc).astype(dt)
+        if p in "cz":
+            B = (B + 1j * rng.normal(size=len(B))).astype(dt)
+        alpha, beta = (0.5, -1.5) if n % 3 else (1.0, 0.0)
+        Co = C0.copy()
+        assert oracle.csrmm(111, alpha, m, m, 0, rp, col, val, 0, 0, 0, 0, B, n, ldb, beta, Co, ldc) == 0
+        dB, dC = torch.from_numpy(B).cuda(), torch.from_numpy(C0).cuda()
+        assert lib.csrmm(p, 111, alpha, h, d, 0, dB.data_ptr(), n, ldb, beta, dC.data_ptr(), ldc) == 0, lib.last_error()
+        torch.cuda.synchronize()
+        got = dC.cpu().numpy().reshape(m, ldc)
+        want = Co.reshape(m, ldc)
+        den = abs(alpha) * (Aabs @ np.abs(B.reshape(m, ldb)[:, :n])) + np.abs(beta * C0.reshape(m, ldc)[:, :n]) + 1e-300
+        assert np.all(np.abs(got[:, :n] - want[:, :n]) <= TOL[np.dtype(dt)] * den), (p, n, pad)
+        assert np.array_equal(got[:, n:], C0.reshape(m, ldc)[:, n:])  # padding untouched
+    lib.destroy(h)
+    lib.destroy_descr(d)
+
+
 def test_row_sharded_window_and_row_ranges(lib, oracle):
     """config 5 shape: a row slab of the 3D 7-point stencil multiplied against a halo window of x,
     boundary rows and interior rows launched separately (the extension used by bench.py --gpus N)"""
