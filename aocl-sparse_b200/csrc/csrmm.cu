@@ -17,6 +17,7 @@
 #include "spmv_kernels.cuh"
 
 #include <cstdint>
+#include <cstdlib>
 
 namespace b200
 {
@@ -186,7 +187,7 @@ namespace b200
         // B / C row (n = 32 doubles: 8 lanes x 2 vectors x 2 doubles), so a warp advances 32/LPR rows of A at a
         // time and every non-zero costs two 128-bit loads per lane instead of one 64-bit load per column.
         // Needs 16-byte aligned B / C rows and n a multiple of the vector width (checked by the launcher).
-        template <typename T, bool CONJ, int LPR>
+        template <typename T, bool CONJ, int LPR, int U>
         __global__ void __launch_bounds__(MM_THREADS) csrmm_row_major_vec_kernel(const int4 *__restrict__ desc,
                                                                                 const int *__restrict__ kind,
                                                                                 int cap,
@@ -253,41 +254,49 @@ namespace b200
                         for(int q = 0; q < VEC; ++q)
                             acc_a.v[q] = acc_b.v[q] = vt<T>::zero();
                         int j = s;
-                        for(; j + 2 <= e; j += 2)
+                        for(; j + U <= e; j += U)
                         {
-                            T v0 = sval[j], v1 = sval[j + 1];
-                            if(CONJ)
+                            T        v[U];
+                            const T *bp[U];
+#pragma unroll
+                            for(int u = 0; u < U; ++u)
                             {
-                                v0 = cj(v0);
-                                v1 = cj(v1);
+                                v[u] = sval[j + u];
+                                if(CONJ)
+                                    v[u] = cj(v[u]);
+                                bp[u] = B + (long long)scol[j + u] * ldb;
                             }
-                            const T *b0 = B + (long long)scol[j] * ldb;
-                            const T *b1 = B + (long long)scol[j + 1] * ldb;
-                            vec16<T> x0a, x0b, x1a, x1b;
-                            if(pa)
-                            {
-                                x0a = load_vec(b0 + ca);
-                                x1a = load_vec(b1 + ca);
-                            }
-                            if(pb)
-                            {
-                                x0b = load_vec(b0 + cb);
-                                x1b = load_vec(b1 + cb);
-                            }
+                            vec16<T> xa[U], xb[U];
                             if(pa)
                             {
 #pragma unroll
-                                for(int q = 0; q < VEC; ++q)
-                                    acc_a.v[q] = mad(v1, x1a.v[q], mad(v0, x0a.v[q], acc_a.v[q]));
+                                for(int u = 0; u < U; ++u)
+                                    xa[u] = load_vec(bp[u] + ca);
                             }
                             if(pb)
                             {
 #pragma unroll
-                                for(int q = 0; q < VEC; ++q)
-                                    acc_b.v[q] = mad(v1, x1b.v[q], mad(v0, x0b.v[q], acc_b.v[q]));
+                                for(int u = 0; u < U; ++u)
+                                    xb[u] = load_vec(bp[u] + cb);
+                            }
+                            if(pa)
+                            {
+#pragma unroll
+                                for(int u = 0; u < U; ++u)
+#pragma unroll
+                                    for(int q = 0; q < VEC; ++q)
+                                        acc_a.v[q] = mad(v[u], xa[u].v[q], acc_a.v[q]);
+                            }
+                            if(pb)
+                            {
+#pragma unroll
+                                for(int u = 0; u < U; ++u)
+#pragma unroll
+                                    for(int q = 0; q < VEC; ++q)
+                                        acc_b.v[q] = mad(v[u], xb[u].v[q], acc_b.v[q]);
                             }
                         }
-                        if(j < e)
+                        for(; j < e; ++j)
                         {
                             T v0 = sval[j];
                             if(CONJ)
@@ -567,17 +576,22 @@ namespace b200
             if(vec_ok)
             {
                 const int vecs = n / VEC; // 16-byte vectors per row; LPR lanes x 2 vectors per pass
-                const int lpr  = vecs <= 8 ? 4 : (vecs <= 16 ? 8 : (vecs <= 32 ? 16 : 32));
-#define B200_MM_VEC(L)                                                                                               \
+                int       lpr  = vecs <= 8 ? 4 : (vecs <= 16 ? 8 : (vecs <= 32 ? 16 : 32));
+                static const int env_lpr = getenv("AOCLSPARSE_B200_MM_LPR") ? atoi(getenv("AOCLSPARSE_B200_MM_LPR")) : 0;
+                static const int env_u   = getenv("AOCLSPARSE_B200_MM_UNROLL") ? atoi(getenv("AOCLSPARSE_B200_MM_UNROLL")) : 2;
+                if(env_lpr == 4 || env_lpr == 8 || env_lpr == 16 || env_lpr == 32)
+                    if(env_lpr * 2 >= vecs)
+                        lpr = env_lpr;
+#define B200_MM_VEC(L, UU)                                                                                               \
     {                                                                                                                \
         static std::atomic<size_t> cfg{0};                                                                           \
         if(cfg.load() < smem)                                                                                        \
         {                                                                                                            \
             B200_CUDA(cudaFuncSetAttribute(                                                                          \
-                csrmm_row_major_vec_kernel<T, CONJ, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+                csrmm_row_major_vec_kernel<T, CONJ, L, UU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
             cfg.store(smem);                                                                                         \
         }                                                                                                            \
-        csrmm_row_major_vec_kernel<T, CONJ, L><<<P.n_blocks, MM_THREADS, smem, st>>>(P.desc.as<int4>(),            \
+        csrmm_row_major_vec_kernel<T, CONJ, L, UU><<<P.n_blocks, MM_THREADS, smem, st>>>(P.desc.as<int4>(),        \
                                                                                       P.kind.as<int>(),             \
                                                                                       cap,                          \
                                                                                       A.row_ptr.as<aoclsparse_int>(), \
@@ -592,14 +606,28 @@ namespace b200
                                                                                       beta,                         \
                                                                                       bz);                          \
     }
-                if(lpr == 4)
-                    B200_MM_VEC(4)
-                else if(lpr == 8)
-                    B200_MM_VEC(8)
-                else if(lpr == 16)
-                    B200_MM_VEC(16)
+                if(env_u == 4)
+                {
+                    if(lpr == 4)
+                        B200_MM_VEC(4, 4)
+                    else if(lpr == 8)
+                        B200_MM_VEC(8, 4)
+                    else if(lpr == 16)
+                        B200_MM_VEC(16, 4)
+                    else
+                        B200_MM_VEC(32, 4)
+                }
                 else
-                    B200_MM_VEC(32)
+                {
+                    if(lpr == 4)
+                        B200_MM_VEC(4, 2)
+                    else if(lpr == 8)
+                        B200_MM_VEC(8, 2)
+                    else if(lpr == 16)
+                        B200_MM_VEC(16, 2)
+                    else
+                        B200_MM_VEC(32, 2)
+                }
 #undef B200_MM_VEC
             }
             else if(order == aoclsparse_order_row)
