@@ -128,6 +128,7 @@ class AoclSparse:
             L.aoclsparse_b200_get_matrix_info.argtypes = [vp, C.POINTER(MatrixInfo)]
             L.aoclsparse_b200_get_plan.argtypes = [vp, i32, vp, vp, C.POINTER(i32)]
             L.aoclsparse_b200_doid.argtypes = [vp, ci, ci]
+            L.aoclsparse_b200_get_clean_csr.argtypes = [vp, C.POINTER(i32), C.POINTER(ci), vp, vp, vp, vp, vp]
             L.aoclsparse_b200_set_x_window.argtypes = [vp, i32, i32]
             L.aoclsparse_b200_set_row_cuts.argtypes = [vp, i32, vp]
             L.aoclsparse_b200_dmv_rows.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32]
@@ -236,6 +237,21 @@ class AoclSparse:
         st = self.lib.aoclsparse_b200_get_plan(h, n.value, ptr(desc), ptr(kind), C.byref(n))
         assert st == 0, st
         return desc[: n.value], kind[: n.value]
+
+    def get_clean_csr(self, h, m, dtype=np.float64):
+        nnz, isint = C.c_int32(0), C.c_int(0)
+        st = self.lib.aoclsparse_b200_get_clean_csr(h, C.byref(nnz), C.byref(isint), None, None, None, None, None)
+        assert st == 0, (st, self.last_error())
+        rp = np.zeros(m + 1, np.int32)
+        col = np.zeros(max(nnz.value, 1), np.int32)
+        val = np.zeros(max(nnz.value, 1), dtype)
+        idiag = np.zeros(max(m, 1), np.int32)
+        iurow = np.zeros(max(m, 1), np.int32)
+        st = self.lib.aoclsparse_b200_get_clean_csr(h, C.byref(nnz), C.byref(isint), ptr(rp), ptr(col), ptr(val),
+                                                    ptr(idiag), ptr(iurow))
+        assert st == 0, (st, self.last_error())
+        return dict(is_internal=isint.value, rp=rp, col=col[: nnz.value], val=val[: nnz.value], idiag=idiag[:m],
+                    iurow=iurow[:m])
 
     def doid(self, descr, op, val_type):
         return self.lib.aoclsparse_b200_doid(descr, op, val_type)

@@ -250,6 +250,7 @@ namespace b200
             for(size_t i = 1; i < A->mats.size(); ++i)
                 delete A->mats[i];
             A->mats.resize(1);
+            A->clean = b200::clean_csr();
             for(auto &h : A->hints)
                 h.done = false;
             return aoclsparse_status_success;

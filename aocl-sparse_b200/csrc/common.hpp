@@ -369,6 +369,15 @@ namespace b200
         row_block_plan plan;
     };
 
+    // "clean CSR" of the reference's analysis (clean.cu): rows grouped lower | diagonal | upper, diagonals present
+    struct clean_csr
+    {
+        bool           valid       = false;
+        bool           is_internal = false; // false: the input already is the clean matrix (arrays below unused)
+        aoclsparse_int nnz         = 0;
+        dev_buf        row_ptr, col_idx, val, idiag, iurow;
+    };
+
     struct hint
     {
         int            act; // 1 mv, 3 mm, ... (aoclsparse_hinted_action numbering)
@@ -404,6 +413,7 @@ struct _aoclsparse_matrix
 
     std::vector<b200::hint>       hints; // most recent first, like the reference's linked list
     std::vector<b200::dev_csr *>  mats;  // mats[0] is the user's matrix
+    b200::clean_csr               clean; // built on demand (aoclsparse_b200_get_clean_csr)
     std::vector<aoclsparse_int>   row_cuts;
     aoclsparse_int                win_lo = 0, win_hi = -1; // x window (win_hi < 0: whole vector)
     mutable std::shared_mutex     guard;
@@ -474,6 +484,9 @@ namespace b200
                                       const aoclsparse_int *row_ptr,
                                       const aoclsparse_int *col_idx,
                                       const void           *val);
+
+    // clean.cu
+    aoclsparse_status ensure_clean(aoclsparse_matrix A, cudaStream_t st);
 
     // obtains (building on first use) the plan of mats[0]
     aoclsparse_status ensure_plan(aoclsparse_matrix A, cudaStream_t st);

@@ -66,6 +66,22 @@ DLL_PUBLIC aoclsparse_status aoclsparse_b200_get_plan(const aoclsparse_matrix A,
                                                       aoclsparse_int         *block_kind,
                                                       aoclsparse_int         *n_blocks);
 
+/* The reference's "clean CSR" (aoclsparse_csr_csc_optimize, library/src/analysis/aoclsparse_csr_util.hpp:765-967;
+ * golden tables tests/unit_tests/hint_tests.cpp:72-140): rows grouped lower | diagonal | upper, an explicit zero
+ * inserted for every missing diagonal of rows i < n, idiag[i] / iurow[i] = position of the diagonal / of the first
+ * strictly-upper entry of row i.  Built on the device on first request.  *is_internal = 0 means the input already
+ * was clean (arrays are the caller's own, in the caller's index base, positions based likewise), 1 means a sorted /
+ * filled base-0 copy.  Host output arrays, each may be NULL; call once with NULLs to learn *nnz.  val has the
+ * matrix' value type.  The multiply kernels do not use this structure (they filter by comparing col with row). */
+DLL_PUBLIC aoclsparse_status aoclsparse_b200_get_clean_csr(aoclsparse_matrix A,
+                                                           aoclsparse_int   *nnz,
+                                                           int              *is_internal,
+                                                           aoclsparse_int   *row_ptr,
+                                                           aoclsparse_int   *col_idx,
+                                                           void             *val,
+                                                           aoclsparse_int   *idiag,
+                                                           aoclsparse_int   *iurow);
+
 /* Dispatch id the reference derives from (descriptor, operation, value type):
  * aoclsparse::get_doid<T> (library/src/include/aoclsparse_mtx_dispatcher.hpp:79-143).  Returns the
  * same integer (0..19) or 20 for an invalid combination. */

@@ -121,6 +121,131 @@ int oracle_doid(int is_complex, int type, int fill, int op)
     return 20;
 }
 
+/* "Clean CSR" of a double matrix: rows grouped lower | diagonal | upper, missing diagonals of rows i < n inserted as
+ * explicit zeros, idiag / iurow positions.  Follows aoclsparse_csr_csc_optimize<T>
+ * (library/src/analysis/aoclsparse_csr_util.hpp:765-967): if the input is group-ordered
+ * (aoclsparse_csr_csc_check_sort_diag, aoclsparse_csr_util.cpp:290-364) with a full diagonal it IS the clean matrix
+ * (is_internal = 0, the caller's base kept); otherwise a base-0 copy is made, rows are sorted by column when not
+ * group-ordered (aoclsparse_sort_idx_val, csr_util.hpp:99-160) and diagonals are filled in front of the first
+ * upper entry (aoclsparse_csr_csc_fill_diag, csr_util.hpp:166-279); indices from aoclsparse_csr_csc_indices
+ * (aoclsparse_csr_util.cpp:389-458).  Output arrays must hold nnz + min(m,n) entries.  Returns the clean nnz. */
+int oracle_clean_csr(int m, int n, int base, const int *rp, const int *col, const double *val, int *is_internal,
+                     int *orp, int *ocol, double *oval, int *idiag, int *iurow)
+{
+    int grouped = 1, fulldiag = 1;
+    for(int i = 0; i < m && grouped; ++i)
+    {
+        int lower = 1, found = 0;
+        for(int p = rp[i] - base; p < rp[i + 1] - base; ++p)
+        {
+            const int j = col[p] - base;
+            if(j == i)
+            {
+                found   = 1;
+                grouped = grouped && lower;
+                lower   = 0;
+            }
+            else if(lower)
+                lower = j < i;
+            else
+                grouped = grouped && (j > i);
+        }
+        if(!found && i < n)
+            fulldiag = 0;
+    }
+    if(!grouped)
+    {
+        fulldiag = 1;
+        for(int i = 0; i < m; ++i)
+        {
+            int found = 0;
+            for(int p = rp[i] - base; p < rp[i + 1] - base; ++p)
+                found = found || (col[p] - base == i);
+            if(!found && i < n)
+                fulldiag = 0;
+        }
+    }
+    const int nnz = rp[m] - base;
+    int       ob  = 0; /* base of the output */
+    if(grouped && fulldiag)
+    {
+        *is_internal = 0;
+        ob           = base;
+        for(int i = 0; i <= m; ++i)
+            orp[i] = rp[i];
+        for(int p = 0; p < nnz; ++p)
+        {
+            ocol[p] = col[p];
+            oval[p] = val[p];
+        }
+    }
+    else
+    {
+        *is_internal = 1;
+        /* copy to base 0, insertion-sort rows by column when not group-ordered */
+        int    *c0 = (int *)malloc(sizeof(int) * (size_t)(nnz > 0 ? nnz : 1));
+        double *v0 = (double *)malloc(sizeof(double) * (size_t)(nnz > 0 ? nnz : 1));
+        for(int p = 0; p < nnz; ++p)
+        {
+            c0[p] = col[p] - base;
+            v0[p] = val[p];
+        }
+        if(!grouped)
+            for(int i = 0; i < m; ++i)
+                for(int p = rp[i] - base + 1; p < rp[i + 1] - base; ++p)
+                {
+                    int    cc = c0[p], q = p - 1;
+                    double vv = v0[p];
+                    while(q >= rp[i] - base && c0[q] > cc)
+                    {
+                        c0[q + 1] = c0[q];
+                        v0[q + 1] = v0[q];
+                        --q;
+                    }
+                    c0[q + 1] = cc;
+                    v0[q + 1] = vv;
+                }
+        int q = 0;
+        for(int i = 0; i < m; ++i)
+        {
+            orp[i]   = q;
+            int done = !(i < n), has = 0;
+            for(int p = rp[i] - base; p < rp[i + 1] - base; ++p)
+                has = has || (c0[p] == i);
+            done = done || has;
+            for(int p = rp[i] - base; p < rp[i + 1] - base; ++p)
+            {
+                if(!done && c0[p] > i)
+                {
+                    ocol[q]   = i;
+                    oval[q++] = 0.0;
+                    done      = 1;
+                }
+                ocol[q]   = c0[p];
+                oval[q++] = v0[p];
+            }
+            if(!done)
+            {
+                ocol[q]   = i;
+                oval[q++] = 0.0;
+            }
+        }
+        orp[m] = q;
+        free(c0);
+        free(v0);
+    }
+    for(int i = 0; i < m; ++i)
+    {
+        int p = orp[i] - ob;
+        const int e = orp[i + 1] - ob;
+        while(p < e && ocol[p] - ob < i)
+            ++p;
+        idiag[i] = p + ob;
+        iurow[i] = ((p < e && ocol[p] - ob == i) ? p + 1 : p) + ob;
+    }
+    return orp[m] - ob;
+}
+
 /* Row-block plan: restates the SPEC at the top of aocl-sparse_b200/csrc/plan.cu (this integer
  * metadata has no reference counterpart; the GPU analysis must reproduce it bit for bit).
  * rp is 0-based.  desc (4 ints per block) and kind may be NULL to only count.  Returns n_blocks. */

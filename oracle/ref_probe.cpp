@@ -24,6 +24,43 @@ __attribute__((visibility("default"))) int probe_matrix_facts(aoclsparse_matrix 
     return 0;
 }
 
+// clean CSR produced by aoclsparse_optimize / csr_csc_optimize: the first csr in A->mats with is_optimized set
+// (what tests/unit_tests/hint_tests.cpp:179-197 reads).  Arrays may be NULL to query sizes only.
+__attribute__((visibility("default"))) int probe_clean_csr(aoclsparse_matrix A, int *nnz, int *is_internal, int *base,
+                                                           int *ptr, int *ind, double *val, int *idiag, int *iurow)
+{
+    if(!A)
+        return -1;
+    for(auto *mat : A->mats)
+    {
+        auto *c = dynamic_cast<aoclsparse::csr *>(mat);
+        if(c && c->is_optimized)
+        {
+            const int nz = c->ptr[A->m] - (int)c->base;
+            *nnz         = nz;
+            *is_internal = (mat != A->mats[0]) ? 1 : 0; // a copy was made (hint_tests.cpp opt_csr_is_internal)
+            *base        = (int)c->base;
+            if(ptr)
+                for(int i = 0; i <= A->m; ++i)
+                    ptr[i] = c->ptr[i];
+            if(ind)
+                for(int i = 0; i < nz; ++i)
+                    ind[i] = c->ind[i];
+            if(val)
+                for(int i = 0; i < nz; ++i)
+                    val[i] = ((double *)c->val)[i];
+            if(idiag)
+                for(int i = 0; i < A->m; ++i)
+                    idiag[i] = c->idiag[i];
+            if(iurow)
+                for(int i = 0; i < A->m; ++i)
+                    iurow[i] = c->iurow[i];
+            return 0;
+        }
+    }
+    return 1;
+}
+
 __attribute__((visibility("default"))) int probe_get_doid(int is_complex, int type, int fill, int op)
 {
     _aoclsparse_mat_descr d;

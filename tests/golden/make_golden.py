@@ -92,6 +92,91 @@ KAT_CREATE = [
 ]
 
 
+# tests/unit_tests/hint_tests.cpp:72-140 (expected clean CSR) with the inputs of common_data_utils.h:610-735
+KAT_CLEAN = [
+    dict(cite="hint_tests.cpp:78-85 N5_full_sorted (common_data_utils.h:610-622)", m=5, n=5,
+         rp=[0, 2, 3, 4, 7, 8], col=[0, 3, 1, 2, 1, 3, 4, 4], val=[1, 2, 3, 4, 5, 6, 7, 8],
+         orp=[0, 2, 3, 4, 7, 8], ocol=[0, 3, 1, 2, 1, 3, 4, 4], oval=[1, 2, 3, 4, 5, 6, 7, 8],
+         idiag=[0, 2, 3, 5, 7], iurow=[1, 3, 4, 6, 8], is_internal=0),
+    dict(cite="hint_tests.cpp:86-93 N5_full_unsorted (common_data_utils.h:624-631)", m=5, n=5,
+         rp=[0, 2, 3, 4, 7, 8], col=[3, 0, 1, 2, 3, 1, 4, 4], val=[2, 1, 3, 4, 6, 5, 7, 8],
+         orp=[0, 2, 3, 4, 7, 8], ocol=[0, 3, 1, 2, 1, 3, 4, 4], oval=[1, 2, 3, 4, 5, 6, 7, 8],
+         idiag=[0, 2, 3, 5, 7], iurow=[1, 3, 4, 6, 8], is_internal=1),
+    dict(cite="hint_tests.cpp:94-101 N59_partial_sort (common_data_utils.h:633-646)", m=5, n=5,
+         rp=[0, 2, 3, 4, 8, 9], col=[0, 3, 1, 2, 2, 1, 3, 4, 4], val=[1, 2, 3, 4, 9, 5, 6, 7, 8],
+         orp=[0, 2, 3, 4, 8, 9], ocol=[0, 3, 1, 2, 2, 1, 3, 4, 4], oval=[1, 2, 3, 4, 9, 5, 6, 7, 8],
+         idiag=[0, 2, 3, 6, 8], iurow=[1, 3, 4, 7, 9], is_internal=0),
+    dict(cite="hint_tests.cpp:102-109 N5_1_hole (common_data_utils.h:648-655)", m=5, n=5,
+         rp=[0, 2, 3, 4, 6, 7], col=[3, 0, 1, 2, 1, 4, 4], val=[2, 1, 3, 4, 5, 7, 8],
+         orp=[0, 2, 3, 4, 7, 8], ocol=[0, 3, 1, 2, 1, 3, 4, 4], oval=[1, 2, 3, 4, 5, 0, 7, 8],
+         idiag=[0, 2, 3, 5, 7], iurow=[1, 3, 4, 6, 8], is_internal=1),
+    dict(cite="hint_tests.cpp:110-117 N5_empty_rows (common_data_utils.h:657-664)", m=5, n=5,
+         rp=[0, 2, 2, 3, 5, 5], col=[3, 0, 2, 1, 4], val=[2, 1, 4, 5, 7],
+         orp=[0, 2, 3, 4, 7, 8], ocol=[0, 3, 1, 2, 1, 3, 4, 4], oval=[1, 2, 0, 4, 5, 0, 7, 0],
+         idiag=[0, 2, 3, 5, 7], iurow=[1, 3, 4, 6, 8], is_internal=1),
+    dict(cite="hint_tests.cpp:134-141 M5_rect_N7 (common_data_utils.h:679-692)", m=5, n=7,
+         rp=[0, 3, 5, 6, 10, 13], col=[0, 3, 5, 1, 5, 2, 1, 3, 4, 6, 4, 5, 6], val=[1, 2, 1, 3, 2, 4, 5, 6, 7, 3, 8, 4, 5],
+         orp=[0, 3, 5, 6, 10, 13], ocol=[0, 3, 5, 1, 5, 2, 1, 3, 4, 6, 4, 5, 6], oval=[1, 2, 1, 3, 2, 4, 5, 6, 7, 3, 8, 4, 5],
+         idiag=[0, 3, 5, 7, 10], iurow=[1, 4, 6, 8, 11], is_internal=0),
+    dict(cite="hint_tests.cpp:142-149 M5_rect_N7_2holes (common_data_utils.h:694-702)", m=5, n=7,
+         rp=[0, 3, 5, 5, 9, 11], col=[0, 3, 5, 1, 5, 1, 3, 4, 6, 5, 6], val=[1, 2, 1, 3, 2, 5, 6, 7, 3, 4, 5],
+         orp=[0, 3, 5, 6, 10, 13], ocol=[0, 3, 5, 1, 5, 2, 1, 3, 4, 6, 4, 5, 6], oval=[1, 2, 1, 3, 2, 0, 5, 6, 7, 3, 0, 4, 5],
+         idiag=[0, 3, 5, 7, 10], iurow=[1, 4, 6, 8, 11], is_internal=1),
+    dict(cite="hint_tests.cpp:150-157 M7_rect_N5 (common_data_utils.h:704-719)", m=7, n=5,
+         rp=[0, 2, 3, 4, 7, 8, 10, 12], col=[0, 3, 1, 2, 1, 3, 4, 4, 1, 2, 0, 3], val=[1, 2, 3, 4, 5, 6, 7, 8, 1, 2, 3, 4],
+         orp=[0, 2, 3, 4, 7, 8, 10, 12], ocol=[0, 3, 1, 2, 1, 3, 4, 4, 1, 2, 0, 3], oval=[1, 2, 3, 4, 5, 6, 7, 8, 1, 2, 3, 4],
+         idiag=[0, 2, 3, 5, 7], iurow=[1, 3, 4, 6, 8], is_internal=0),
+]
+
+PROBE.probe_clean_csr.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)] + [C.c_void_p] * 5
+
+
+def ref_clean(base, m, n, rp, col, val):
+    """clean CSR the reference builds in aoclsparse_optimize (read through the probe)"""
+    # the reference aliases these arrays: they must outlive the handle
+    col_keep = np.concatenate([col, [0]]).astype(np.int32)
+    val_keep = np.concatenate([val, [0.0]])
+    st, h = REF.create_csr("d", base, m, n, len(col), rp, col_keep, val_keep)
+    assert st == 0, st
+    d = REF.create_descr(base=base)
+    assert REF.set_mm_hint(h, 111, d, 5) == 0  # any non-mv hint routes optimize to csr_csc_optimize (analysis.cpp:513-553)
+    assert REF.optimize(h) == 0
+    REF.destroy_descr(d)
+    nnz, isint, ob = C.c_int(0), C.c_int(0), C.c_int(0)
+    assert PROBE.probe_clean_csr(h, C.byref(nnz), C.byref(isint), C.byref(ob), None, None, None, None, None) == 0
+    orp = np.zeros(m + 1, np.int32)
+    ocol = np.zeros(max(nnz.value, 1), np.int32)
+    oval = np.zeros(max(nnz.value, 1))
+    idiag = np.zeros(max(m, 1), np.int32)
+    iurow = np.zeros(max(m, 1), np.int32)
+    PROBE.probe_clean_csr(h, C.byref(nnz), C.byref(isint), C.byref(ob), orp.ctypes.data, ocol.ctypes.data,
+                          oval.ctypes.data, idiag.ctypes.data, iurow.ctypes.data)
+    REF.destroy(h)
+    return dict(is_internal=isint.value, base=ob.value, rp=orp.tolist(), col=ocol[:nnz.value].tolist(),
+                val=oval[:nnz.value].tolist(), idiag=idiag[:m].tolist(), iurow=iurow[:m].tolist())
+
+
+def clean_table(rng):
+    for k in KAT_CLEAN:
+        got = ref_clean(0, k["m"], k["n"], np.array(k["rp"], np.int32), np.array(k["col"], np.int32),
+                        np.array(k["val"], np.float64))
+        d = min(k["m"], k["n"])
+        assert got["rp"] == k["orp"] and got["col"] == k["ocol"] and got["val"] == k["oval"], (k["cite"], got)
+        assert got["idiag"][:d] == k["idiag"] and got["iurow"][:d] == k["iurow"], (k["cite"], got)
+        assert got["is_internal"] == k["is_internal"], k["cite"]
+    cases = []
+    for i in range(90):
+        base = i % 2
+        m, n = int(rng.integers(1, 14)), int(rng.integers(1, 14))
+        rp, col, val = gen_np.random_csr(rng, m, n, 0.35, np.float64, ("full", "partial", "none")[i % 3],
+                                         ensure_diag=(i % 4 < 2), base=base, empty_rows=0.15)
+        # distinct columns per row (the reference's row sort is not stable for duplicates)
+        got = ref_clean(base, m, n, rp, col, val)
+        cases.append(dict(m=m, n=n, base=base, rp=rp.tolist(), col=col.tolist(), val=val.tolist(), out=got))
+    json.dump(cases, open(os.path.join(HERE, "ref_clean.json"), "w"))
+    print("clean-CSR table:", len(cases), "cases; internal copies:", sum(c["out"]["is_internal"] for c in cases))
+
+
 def run_mv(lib, p, case, rp, col, val, x, y0):
     base = case["base"]
     st, h = lib.create_csr(p, base, case["m"], case["n"], len(col), rp, col, val)
@@ -419,11 +504,13 @@ def status_table():
 
 if __name__ == "__main__":
     check_kats()
-    json.dump(dict(mv=KAT_MV, mm=KAT_MM, create=KAT_CREATE), open(os.path.join(HERE, "kat.json"), "w"), indent=0)
+    json.dump(dict(mv=KAT_MV, mm=KAT_MM, create=KAT_CREATE, clean=KAT_CLEAN), open(os.path.join(HERE, "kat.json"), "w"),
+              indent=0)
     rng = np.random.default_rng(69069)  # the reference's own test seed (tests/common/aoclsparse_utility.cpp:44-45)
     mv_sweep(rng)
     mm_sweep(rng)
     create_table(rng)
+    clean_table(rng)
     doid_tables()
     status_table()
     print("golden fixtures written to", HERE)

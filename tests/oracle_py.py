@@ -61,6 +61,25 @@ class Oracle:
                                        dummy.ctypes.data, base, C.byref(sort), C.byref(fd))
         return st, sort.value, fd.value
 
+    def clean_csr(self, m, n, base, rp, col, val):
+        """returns dict(is_internal, rp, col, val, idiag, iurow) of the reference's clean CSR (double values)"""
+        nnz = int(rp[m] - base) if m >= 0 else 0
+        cap = nnz + min(m, n) + 1
+        orp = np.zeros(m + 1, np.int32)
+        ocol = np.zeros(cap, np.int32)
+        oval = np.zeros(cap, np.float64)
+        idiag = np.zeros(max(m, 1), np.int32)
+        iurow = np.zeros(max(m, 1), np.int32)
+        isint = C.c_int(0)
+        self.lib.oracle_clean_csr.argtypes = [C.c_int] * 3 + [C.c_void_p] * 3 + [C.POINTER(C.c_int)] + [C.c_void_p] * 5
+        rp = np.ascontiguousarray(rp, np.int32)
+        col = np.ascontiguousarray(np.concatenate([col, [0]]), np.int32)
+        val = np.ascontiguousarray(np.concatenate([val, [0.0]]), np.float64)
+        nz = self.lib.oracle_clean_csr(m, n, base, rp.ctypes.data, col.ctypes.data, val.ctypes.data, C.byref(isint),
+                                       orp.ctypes.data, ocol.ctypes.data, oval.ctypes.data, idiag.ctypes.data,
+                                       iurow.ctypes.data)
+        return dict(is_internal=isint.value, rp=orp, col=ocol[:nz], val=oval[:nz], idiag=idiag[:m], iurow=iurow[:m])
+
     def doid(self, is_complex, mtype, fill, op):
         return self.lib.oracle_doid(int(is_complex), mtype, fill, op)
 

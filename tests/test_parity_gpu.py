@@ -114,6 +114,47 @@ def test_create_status_sort_fulldiag_bit_exact(lib):
             assert not h.value  # *mat is NULL on failure (create.cpp:46)
 
 
+def test_clean_csr_bit_exact(lib, oracle):
+    """device-built clean CSR + idiag / iurow against hint_tests.cpp:72-140, 90 reference-run cases and the oracle"""
+    def check(got, rp, col, val, idiag, iurow, internal, d, tag):
+        assert got["is_internal"] == internal, tag
+        assert got["rp"].tolist() == list(rp) and got["col"].tolist() == list(col), tag
+        assert got["val"].tolist() == list(val), tag
+        assert got["idiag"][:d].tolist() == list(idiag)[:d] and got["iurow"][:d].tolist() == list(iurow)[:d], tag
+
+    kat = json.load(open(os.path.join(GOLDEN, "kat.json")))["clean"]
+    for k in kat:
+        rp, col, val = np.array(k["rp"], np.int32), np.array(k["col"], np.int32), np.array(k["val"], np.float64)
+        st, h = lib.create_csr("d", 0, k["m"], k["n"], len(col), rp, col, val)
+        assert st == 0
+        check(lib.get_clean_csr(h, k["m"]), k["orp"], k["ocol"], k["oval"], k["idiag"], k["iurow"], k["is_internal"],
+              min(k["m"], k["n"]), k["cite"])
+        lib.destroy(h)
+    for c in json.load(open(os.path.join(GOLDEN, "ref_clean.json"))):
+        rp = np.array(c["rp"], np.int32)
+        col = np.array(c["col"] + [0], np.int32)
+        val = np.array(c["val"] + [0.0], np.float64)
+        st, h = lib.create_csr("d", c["base"], c["m"], c["n"], len(c["col"]), rp, col, val)
+        assert st == 0
+        o = c["out"]
+        check(lib.get_clean_csr(h, c["m"]), o["rp"], o["col"], o["val"], o["idiag"], o["iurow"], o["is_internal"],
+              c["m"], c)
+        lib.destroy(h)
+    # a larger unsorted matrix with holes, against the oracle's restatement; other value types carry values along
+    rng = np.random.default_rng(31)
+    rp, col, val = gen_np.random_csr(rng, 700, 650, 0.02, np.float64, "none", empty_rows=0.2)
+    want = oracle.clean_csr(700, 650, 0, rp, col, val)
+    for p in "dsz":
+        v = val.astype(DT[p])
+        st, h = lib.create_csr(p, 0, 700, 650, len(col), rp, col, v)
+        assert st == 0
+        got = lib.get_clean_csr(h, 700, DT[p])
+        assert got["rp"].tolist() == want["rp"].tolist() and got["col"].tolist() == want["col"].tolist()
+        assert got["idiag"].tolist() == want["idiag"].tolist() and got["iurow"].tolist() == want["iurow"].tolist()
+        assert np.array_equal(got["val"], want["val"].astype(DT[p]))
+        lib.destroy(h)
+
+
 def test_mv_sweep_vs_reference_outputs(lib, oracle):
     meta = json.load(open(os.path.join(GOLDEN, "ref_mv_sweep.json")))
     data = np.load(os.path.join(GOLDEN, "ref_mv_sweep.npz"))
