@@ -207,6 +207,76 @@ namespace b200
         }
     }
 
+    // CTAs of the multiply kernel that are resident at once on the whole chip for block size T
+    long long ctas_per_wave(size_t elem_size, aoclsparse_int T)
+    {
+        const long long smem = 16 + (long long)(T + 8) * (long long)(elem_size + 4) + 1024; // + 1 KB reserved per CTA
+        long long       c    = 232448 / smem;
+        if(c > 8)
+            c = 8; // 2048 threads per SM / 256
+        if(c < 1)
+            c = 1;
+        return 148 * c;
+    }
+    bool wave_search_applies(size_t elem_size, aoclsparse_int nnz, aoclsparse_int T)
+    {
+        return (long long)nnz < 8 * ctas_per_wave(elem_size, T) * (long long)T && (long long)nnz >= ctas_per_wave(elem_size, T) * (long long)T;
+    }
+
+    namespace
+    {
+        // segment boundaries for block size T and, per segment, the number of blocks / long rows / long segments
+        aoclsparse_status count_pass(const dev_csr                     &A,
+                                     aoclsparse_int                     T,
+                                     aoclsparse_int                     R,
+                                     const std::vector<aoclsparse_int> &row_cuts,
+                                     cudaStream_t                       st,
+                                     std::vector<aoclsparse_int>       &bounds,
+                                     std::vector<int3>                 &counts,
+                                     dev_buf                           &d_seg,
+                                     dev_buf                           &d_grid,
+                                     dev_buf                           &d_counts)
+        {
+            const long long       S  = 64LL * T;
+            const aoclsparse_int *rp = A.row_ptr.as<aoclsparse_int>();
+            bounds.clear();
+        // ---- segment boundaries: nnz grid (device lower bounds) merged with the forced row cuts
+        const int ngrid = (int)(((long long)A.nnz + S - 1) / S) - 1 > 0 ? (int)(((long long)A.nnz + S - 1) / S) - 1 : 0;
+        bounds.push_back(0);
+        if(ngrid > 0)
+        {
+            if(d_grid.bytes < sizeof(aoclsparse_int) * (size_t)ngrid)
+                B200_TRY(d_grid.alloc(sizeof(aoclsparse_int) * (size_t)ngrid));
+            grid_rows_kernel<<<(ngrid + 127) / 128, 128, 0, st>>>(A.m, rp, S, ngrid, d_grid.as<aoclsparse_int>());
+            B200_LAUNCHED();
+            std::vector<aoclsparse_int> h((size_t)ngrid);
+            B200_CUDA(cudaMemcpyAsync(h.data(), d_grid.p, sizeof(aoclsparse_int) * (size_t)ngrid, cudaMemcpyDeviceToHost, st));
+            B200_CUDA(cudaStreamSynchronize(st));
+            bounds.insert(bounds.end(), h.begin(), h.end());
+        }
+        for(aoclsparse_int c : row_cuts)
+            bounds.push_back(c);
+        bounds.push_back(A.m);
+        std::sort(bounds.begin(), bounds.end());
+        bounds.erase(std::unique(bounds.begin(), bounds.end()), bounds.end());
+        const int nseg = (int)bounds.size() - 1;
+
+        if(d_seg.bytes < sizeof(aoclsparse_int) * bounds.size())
+            B200_TRY(d_seg.alloc(sizeof(aoclsparse_int) * bounds.size() * 2));
+        if(d_counts.bytes < sizeof(int3) * (size_t)nseg)
+            B200_TRY(d_counts.alloc(sizeof(int3) * (size_t)nseg * 2));
+        B200_CUDA(cudaMemcpyAsync(d_seg.p, bounds.data(), sizeof(aoclsparse_int) * bounds.size(), cudaMemcpyHostToDevice, st));
+
+        walk_segments_kernel<false><<<(nseg + 63) / 64, 64, 0, st>>>(
+            nseg, d_seg.as<aoclsparse_int>(), rp, T, R, d_counts.as<int3>(), nullptr, nullptr, nullptr, nullptr);
+        B200_LAUNCHED();
+        counts.assign((size_t)nseg, make_int3(0, 0, 0));
+        B200_CUDA(cudaMemcpyAsync(counts.data(), d_counts.p, sizeof(int3) * (size_t)nseg, cudaMemcpyDeviceToHost, st));
+        B200_CUDA(cudaStreamSynchronize(st));
+            return aoclsparse_status_success;
+        }
+    }
+
     aoclsparse_status build_plan(dev_csr                           &A,
                                  size_t                             elem_size,
                                  aoclsparse_int                     max_row_nnz,
@@ -241,8 +311,6 @@ namespace b200
             if(v >= 1 && v <= 4)
                 P.pipe_ctas_per_sm = v;
         }
-        const aoclsparse_int T = P.block_nnz, R = P.block_rows;
-        const long long      S = 64LL * T;
         const aoclsparse_int *rp = A.row_ptr.as<aoclsparse_int>();
 
         if(A.m == 0)
@@ -251,40 +319,41 @@ namespace b200
             return aoclsparse_status_success;
         }
 
-        // ---- segment boundaries: nnz grid (device lower bounds) merged with the forced row cuts
-        const int ngrid = (int)(((long long)A.nnz + S - 1) / S) - 1 > 0 ? (int)(((long long)A.nnz + S - 1) / S) - 1 : 0;
+        // ---- wave-aware block size (small matrices only): with fewer than ~8 waves of CTAs the partial last wave is
+        // a visible fraction of the run (2D Laplacian 1000^2: 2478 blocks = 2.09 waves), so candidates T0 + 32k are
+        // tried and the one minimising ceil(blocks / CTAs per wave) * T is kept (profiles/r01_summary.md)
         std::vector<aoclsparse_int> bounds;
-        bounds.push_back(0);
-        if(ngrid > 0)
+        std::vector<int3>           counts;
+        dev_buf                     d_seg, d_grid, d_cnt;
+        aoclsparse_int              T = P.block_nnz;
+        const aoclsparse_int        R = P.block_rows;
+        if(wave_search_applies(elem_size, A.nnz, T) && !getenv("AOCLSPARSE_B200_BLOCK_NNZ"))
         {
-            dev_buf g;
-            B200_TRY(g.alloc(sizeof(aoclsparse_int) * (size_t)ngrid));
-            grid_rows_kernel<<<(ngrid + 127) / 128, 128, 0, st>>>(A.m, rp, S, ngrid, g.as<aoclsparse_int>());
-            B200_LAUNCHED();
-            std::vector<aoclsparse_int> h((size_t)ngrid);
-            B200_CUDA(cudaMemcpyAsync(h.data(), g.p, sizeof(aoclsparse_int) * (size_t)ngrid, cudaMemcpyDeviceToHost, st));
-            B200_CUDA(cudaStreamSynchronize(st));
-            bounds.insert(bounds.end(), h.begin(), h.end());
+            long long      best_cost = -1;
+            aoclsparse_int best_T    = T;
+            for(int k = 0; k <= 16; ++k)
+            {
+                const aoclsparse_int Tk = T + 32 * k;
+                B200_TRY(count_pass(A, Tk, R, row_cuts, st, bounds, counts, d_seg, d_grid, d_cnt));
+                long long nbk = 0;
+                for(const int3 &c : counts)
+                    nbk += c.x;
+                const long long wave  = ctas_per_wave(elem_size, Tk);
+                // 1.5 % slack: a last wave that is only just full still ends late (measured, profiles/r01_summary.md)
+                const long long cost  = (((nbk * 203 + 199) / 200 + wave - 1) / wave) * (long long)Tk;
+                if(best_cost < 0 || cost < best_cost)
+                {
+                    best_cost = cost;
+                    best_T    = Tk;
+                }
+            }
+            T = P.block_nnz = best_T;
         }
-        for(aoclsparse_int c : row_cuts)
-            bounds.push_back(c);
-        bounds.push_back(A.m);
-        std::sort(bounds.begin(), bounds.end());
-        bounds.erase(std::unique(bounds.begin(), bounds.end()), bounds.end());
+        B200_TRY(count_pass(A, T, R, row_cuts, st, bounds, counts, d_seg, d_grid, d_cnt));
         const int nseg = (int)bounds.size() - 1;
-
-        dev_buf d_seg, d_counts, d_offsets;
-        B200_TRY(d_seg.alloc(sizeof(aoclsparse_int) * bounds.size()));
-        B200_TRY(d_counts.alloc(sizeof(int3) * (size_t)nseg));
+        dev_buf   d_offsets;
         B200_TRY(d_offsets.alloc(sizeof(int3) * (size_t)nseg));
-        B200_CUDA(cudaMemcpyAsync(d_seg.p, bounds.data(), sizeof(aoclsparse_int) * bounds.size(), cudaMemcpyHostToDevice, st));
-
-        walk_segments_kernel<false><<<(nseg + 63) / 64, 64, 0, st>>>(
-            nseg, d_seg.as<aoclsparse_int>(), rp, T, R, d_counts.as<int3>(), nullptr, nullptr, nullptr, nullptr);
-        B200_LAUNCHED();
-        std::vector<int3> counts((size_t)nseg), offsets((size_t)nseg);
-        B200_CUDA(cudaMemcpyAsync(counts.data(), d_counts.p, sizeof(int3) * (size_t)nseg, cudaMemcpyDeviceToHost, st));
-        B200_CUDA(cudaStreamSynchronize(st));
+        std::vector<int3> offsets((size_t)nseg);
         long long nb = 0, nlr = 0, nls = 0;
         for(int s = 0; s < nseg; ++s)
         {

@@ -375,8 +375,20 @@ int oracle_plan(int m, const int *rp, int T, int R, int forced, int n_cuts, cons
     return nb;
 }
 
-/* plan_parameters of plan.cu */
-void oracle_plan_parameters(int elem_size, int m, int nnz, int max_row_nnz, int *T, int *R)
+/* plan_parameters + wave-aware block size of plan.cu (same arithmetic, same candidate order) */
+static long long ctas_per_wave(int elem_size, int T)
+{
+    const long long smem = 16 + (long long)(T + 8) * (long long)(elem_size + 4) + 1024;
+    long long       c    = 232448 / smem;
+    if(c > 8)
+        c = 8;
+    if(c < 1)
+        c = 1;
+    return 148 * c;
+}
+
+void oracle_plan_parameters(int elem_size, int m, int nnz, int max_row_nnz, const int *rp, int n_cuts, const int *cuts,
+                            int *T, int *R)
 {
     int             t    = (24576 / (elem_size + 4)) / 512 * 512;
     const long long mean = m > 0 ? (long long)nnz / m : 0;
@@ -386,8 +398,28 @@ void oracle_plan_parameters(int elem_size, int m, int nnz, int max_row_nnz, int 
         t = 512;
     while(t > 512 && (long long)nnz < (long long)t * 148 * 8)
         t -= 512;
-    *T = t;
     *R = 1024;
+    if(m > 0 && rp && (long long)nnz < 8 * ctas_per_wave(elem_size, t) * (long long)t
+       && (long long)nnz >= ctas_per_wave(elem_size, t) * (long long)t)
+    {
+        long long best_cost = -1;
+        int       best_t    = t;
+        for(int k = 0; k <= 16; ++k)
+        {
+            const int       tk = t + 32 * k;
+            int             a, b;
+            const long long nb   = oracle_plan(m, rp, tk, *R, -1, n_cuts, cuts, 0, 0, 0, &a, &b);
+            const long long wave = ctas_per_wave(elem_size, tk);
+            const long long cost = (((nb * 203 + 199) / 200 + wave - 1) / wave) * (long long)tk;
+            if(best_cost < 0 || cost < best_cost)
+            {
+                best_cost = cost;
+                best_t    = tk;
+            }
+        }
+        t = best_t;
+    }
+    *T = t;
 }
 
 /* ---- multiply kernels, instantiated for the four value types ---- */

@@ -48,7 +48,7 @@ class Oracle:
         self.lib.oracle_mat_check.argtypes = [ci, ci, ci, vp, vp, vp, ci, C.POINTER(ci), C.POINTER(ci)]
         self.lib.oracle_doid.argtypes = [ci, ci, ci, ci]
         self.lib.oracle_plan.argtypes = [ci, vp, ci, ci, ci, ci, vp, ci, vp, vp, C.POINTER(ci), C.POINTER(ci)]
-        self.lib.oracle_plan_parameters.argtypes = [ci, ci, ci, ci, C.POINTER(ci), C.POINTER(ci)]
+        self.lib.oracle_plan_parameters.argtypes = [ci, ci, ci, ci, vp, ci, vp, C.POINTER(ci), C.POINTER(ci)]
         for suf, ct in (("s", C.c_float), ("d", C.c_double), ("c", FC), ("z", DC)):
             getattr(self.lib, f"oracle_csrmv_{suf}").argtypes = [ci, ct, ci, ci, ci, vp, vp, vp, ci, ci, ci, vp, ct, vp]
             getattr(self.lib, f"oracle_csrmm_{suf}").argtypes = [ci, ct, ci, ci, ci, vp, vp, vp, ci, ci, ci, ci, vp, ci,
@@ -83,9 +83,16 @@ class Oracle:
     def doid(self, is_complex, mtype, fill, op):
         return self.lib.oracle_doid(int(is_complex), mtype, fill, op)
 
-    def plan_parameters(self, elem_size, m, nnz, max_row_nnz):
+    def plan_parameters(self, elem_size, rp0, cuts=()):
+        """block nnz / row capacity the analysis picks for a 0-based row_ptr (incl. the wave-aware search)"""
+        rp0 = np.ascontiguousarray(rp0, dtype=np.int32)
+        cuts = np.ascontiguousarray(cuts, dtype=np.int32)
+        m = len(rp0) - 1
+        nnz = int(rp0[m])
+        mx = int(np.max(np.diff(rp0))) if m > 0 else 0
         t, r = C.c_int(0), C.c_int(0)
-        self.lib.oracle_plan_parameters(elem_size, m, nnz, max_row_nnz, C.byref(t), C.byref(r))
+        self.lib.oracle_plan_parameters(elem_size, m, nnz, mx, rp0.ctypes.data, len(cuts), cuts.ctypes.data,
+                                        C.byref(t), C.byref(r))
         return t.value, r.value
 
     def plan(self, rp0, T, R, forced=-1, cuts=()):

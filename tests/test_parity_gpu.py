@@ -427,7 +427,7 @@ def _skewed(rng, m, heavy):
 def test_plan_bit_exact(lib, oracle):
     rng = np.random.default_rng(5)
     mats = [gen_np.stencil(27, 20, 20, 20), gen_np.stencil(5, 300, 300), gen_np.rmat_csr(13, dtype=np.float64),
-            _skewed(rng, 9000, 6), _skewed(rng, 20000, 0)]
+            _skewed(rng, 9000, 6), _skewed(rng, 20000, 0), gen_np.stencil(5, 1000, 1000)]  # last: wave-aware block size
     for idx, (rp, col, val) in enumerate(mats):
         m = len(rp) - 1
         for forced, cuts in ((-1, ()), (2, ()), (-1, (m // 3, m // 2))):
@@ -442,7 +442,7 @@ def test_plan_bit_exact(lib, oracle):
                 assert lib.set_mv_hint(h, 111, d, 1) == 0
             assert lib.optimize(h) == 0, lib.last_error()
             info = lib.matrix_info(h)
-            T, R = oracle.plan_parameters(8, m, len(col), int(np.max(np.diff(rp))))
+            T, R = oracle.plan_parameters(8, rp, cuts)
             assert (info.block_nnz, info.block_rows) == (T, R)
             desc, kind = lib.get_plan(h)
             odesc, okind, nlr, nls = oracle.plan(rp, T, R, forced, cuts)
