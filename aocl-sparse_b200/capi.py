@@ -53,6 +53,12 @@ class MatrixInfo(C.Structure):
                 ("n_long_rows", C.c_int32)]
 
 
+class HaloCtl(C.Structure):
+    """aoclsparse_b200_halo_ctl (include/aoclsparse_b200.h)"""
+    _fields_ = [(n, C.c_void_p) for n in ("left_done", "right_done", "to_left_done", "to_right_done", "counters",
+                                          "push_left", "push_right")] + [("k", C.c_uint)]
+
+
 def ptr(a):
     """numpy array | int device address | None -> c_void_p"""
     if a is None:
@@ -134,6 +140,7 @@ class AoclSparse:
             L.aoclsparse_b200_dmv_rows.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32]
             L.aoclsparse_b200_smv_rows.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32]
             L.aoclsparse_b200_dmv_rows_push.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, vp]
+            L.aoclsparse_b200_dmv_sharded_step.argtypes = [vp, vp, vp, vp, vp, C.POINTER(HaloCtl)]
             L.aoclsparse_b200_signal.argtypes = [vp, C.c_uint]
             L.aoclsparse_b200_wait.argtypes = [vp, C.c_uint, vp]
             L.aoclsparse_b200_ipc_alloc.argtypes = [C.c_size_t, C.POINTER(vp), C.c_char_p]
@@ -272,6 +279,10 @@ class AoclSparse:
         a = _scalar_by_ref("d", alpha)
         b = _scalar_by_ref("d", beta)
         return self.lib.aoclsparse_b200_dmv_rows_push(ptr(a), h, descr, ptr(x), ptr(b), ptr(y), r0, r1, ptr(push_dst))
+
+    def mv_sharded_step(self, alpha, h, descr, x, y, ctl):
+        a = _scalar_by_ref("d", alpha)
+        return self.lib.aoclsparse_b200_dmv_sharded_step(ptr(a), h, descr, ptr(x), ptr(y), C.byref(ctl))
 
     def signal(self, flag_ptr, value):
         return self.lib.aoclsparse_b200_signal(C.c_void_p(flag_ptr), value)

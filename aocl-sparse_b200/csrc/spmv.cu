@@ -6,6 +6,7 @@
 // and launches the sm_100a kernels of spmv_kernels.cuh.  There is no CPU path: if a launch fails the
 // call returns internal_error.
 #include "spmv_pipelined.cuh"
+#include "spmv_sharded.cuh"
 
 namespace b200
 {
@@ -733,6 +734,84 @@ aoclsparse_status aoclsparse_b200_ipc_free(void *dptr)
 {
     if(dptr)
         B200_CUDA(cudaFree(dptr));
+    return aoclsparse_status_success;
+}
+
+// One launch per iteration of the row-sharded product: multiply + halo push + flags (spmv_sharded.cuh).
+aoclsparse_status aoclsparse_b200_dmv_sharded_step(const double                  *alpha,
+                                                   aoclsparse_matrix              A,
+                                                   const aoclsparse_mat_descr     descr,
+                                                   const double                  *x,
+                                                   double                        *y,
+                                                   const aoclsparse_b200_halo_ctl *ctl)
+{
+    if(!alpha || !A || !descr || !x || !y || !ctl || !ctl->counters)
+        return aoclsparse_status_invalid_pointer;
+    if(A->mats.empty() || A->mats[0] == nullptr)
+        return aoclsparse_status_invalid_pointer;
+    if(descr->base != A->base)
+        return aoclsparse_status_invalid_value;
+    if(A->val_type != aoclsparse_dmat)
+        return aoclsparse_status_wrong_type;
+    if(descr->type != aoclsparse_matrix_type_general || ctl->k == 0)
+        return aoclsparse_status_invalid_value;
+    cudaStream_t st = current_stream();
+    B200_TRY(ensure_plan(A, st));
+    std::shared_lock<std::shared_mutex> rl(A->guard);
+    const dev_csr                      &M = *A->mats[0];
+    const row_block_plan               &P = M.plan;
+    // needs exactly the cuts [h, m-h] and a plan whose blocks are all thread-per-row
+    if(A->row_cuts.size() != 2 || P.cut_block.size() != 2 || P.n_strat[STRAT_THREAD] != P.n_blocks)
+        return aoclsparse_status_not_implemented;
+    halo_ctl hc;
+    hc.left_done     = static_cast<const unsigned *>(ctl->left_done);
+    hc.right_done    = static_cast<const unsigned *>(ctl->right_done);
+    hc.to_left_done  = static_cast<unsigned *>(ctl->to_left_done);
+    hc.to_right_done = static_cast<unsigned *>(ctl->to_right_done);
+    hc.counters      = static_cast<unsigned *>(ctl->counters);
+    hc.k                 = ctl->k;
+    hc.n_first           = P.cut_block[0];
+    hc.last_begin        = P.cut_block[1];
+    hc.n_last            = P.n_blocks - P.cut_block[1];
+    hc.n_blocks          = P.n_blocks;
+    hc.first_rows        = A->row_cuts[0];
+    hc.last_row0         = A->row_cuts[1];
+    if((hc.left_done && !ctl->push_left) || (hc.right_done && !ctl->push_right))
+        return aoclsparse_status_invalid_pointer;
+    if(A->win_hi >= 0)
+        x = x - A->win_lo;
+    const int    cap  = P.block_nnz + 8;
+    const size_t smem = spmv_smem_bytes(sizeof(double), P.block_nnz);
+    static std::atomic<size_t> configured{0};
+    if(configured.load() < smem)
+    {
+        B200_CUDA(cudaFuncSetAttribute(spmv_sharded_step_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured.store(smem);
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim            = dim3((unsigned)P.n_blocks);
+    cfg.blockDim           = dim3(256);
+    cfg.dynamicSmemBytes   = smem;
+    cfg.stream             = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id                                         = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs                                          = attr;
+    cfg.numAttrs                                       = P.pdl ? 1 : 0;
+    B200_CUDA(cudaLaunchKernelEx(&cfg,
+                                 spmv_sharded_step_kernel<double>,
+                                 (const int4 *)P.desc.as<int4>(),
+                                 cap,
+                                 (const aoclsparse_int *)M.row_ptr.as<aoclsparse_int>(),
+                                 (const aoclsparse_int *)M.col_idx.as<aoclsparse_int>(),
+                                 (const double *)M.val.as<double>(),
+                                 x,
+                                 y,
+                                 *alpha,
+                                 static_cast<double *>(ctl->push_left),
+                                 static_cast<double *>(ctl->push_right),
+                                 hc));
+    B200_LAUNCHED();
     return aoclsparse_status_success;
 }
 }

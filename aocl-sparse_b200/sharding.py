@@ -174,6 +174,38 @@ class PeerHalo:
         if R in self.peer:
             lib.signal(self.peer[R]["f"] + 4 * 2, k)
 
+    def iteration_fused(self, k, alpha, A, descr):
+        """iteration k >= 1 as ONE kernel launch (aoclsparse_b200_dmv_sharded_step): the boundary CTAs wait for the
+        flags in-kernel, push their rows to the neighbours and publish the flags themselves.  Returns the status
+        (not_implemented when the plan is not all thread-per-row: fall back to iteration())."""
+        import capi
+        s = self.slab
+        cur, nxt = (k - 1) % 2, k % 2
+        L, R = s.rank - 1, s.rank + 1
+        c = capi.HaloCtl()
+        f = self.f_ptr
+        # words 16 / 20 of the flag block: "left / right neighbour's facing boundary completed iteration k"
+        if L in self.peer:
+            c.left_done = f + 16
+            c.to_left_done = self.peer[L]["f"] + 20  # I am L's right neighbour
+            c.push_left = self.left_push_dst(nxt)
+        if R in self.peer:
+            c.right_done = f + 20
+            c.to_right_done = self.peer[R]["f"] + 16  # I am R's left neighbour
+            c.push_right = self.right_push_dst(nxt)
+        c.counters = f + 64
+        c.k = k
+        return self.lib.mv_sharded_step(alpha, A, descr, self.w_ptr[cur], self.own_ptr(nxt), c)
+
+    def timed_out(self):
+        """1 if any flag wait (stream wait kernel or in-kernel spin) gave up"""
+        import torch
+        t = torch.zeros(2, dtype=torch.int32, device="cuda")
+        assert self.lib.memcpy(t.data_ptr(), self.timeout_ptr, 4) == 0
+        assert self.lib.memcpy(t[1:].data_ptr(), self.f_ptr + 64 + 12, 4) == 0
+        torch.cuda.synchronize()
+        return int(t[0].item()) | int(t[1].item())
+
     def initial_push(self, which=0):
         """one-off: copy my boundary planes of window `which` into the neighbours' halos (before iteration 1)"""
         import torch

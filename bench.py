@@ -343,9 +343,12 @@ def run_gpu(args, wl):
     else:
         wlen = slab.win_hi - slab.win_lo
         off = slab.own_offset
-        halo_mode = "none" if world == 1 else os.environ.get("BENCH_HALO", "p2p-push")
+        # halo exchange: p2p-fused (default) = one kernel per iteration that multiplies, stores the boundary rows into
+        # the neighbours' x windows over NVLink and publishes the flags; p2p-push = same stores, separate boundary /
+        # interior launches and flag kernels; nccl = send/recv baseline
+        halo_mode = "none" if world == 1 else os.environ.get("BENCH_HALO", "p2p-fused")
         peer = None
-        if halo_mode == "p2p-push":
+        if halo_mode in ("p2p-push", "p2p-fused"):
             # x windows live in ipc memory; boundary rows store into the neighbours' halos from the kernel epilogue
             peer = sharding.PeerHalo(lib, slab, elem)
             lib.lib.aoclsparse_b200_gen_uniform(1, slab.row_lo, m, elem, C.c_void_p(peer.own_ptr(0)))
@@ -368,7 +371,11 @@ def run_gpu(args, wl):
         def step(i):
             if peer is not None:
                 state["k"] += 1
-                peer.iteration(state["k"], alpha, A, d, beta)
+                if halo_mode == "p2p-fused":
+                    s = peer.iteration_fused(state["k"], alpha, A, d)
+                    assert s == 0, (s, lib.last_error())
+                else:
+                    peer.iteration(state["k"], alpha, A, d, beta)
                 return
             cur, nxt = bufs[state["cur"]], bufs[1 - state["cur"]]
             ydst = nxt[off:].data_ptr()
@@ -396,7 +403,8 @@ def run_gpu(args, wl):
             dist.all_reduce(nnz_t)
         g_nnz = int(nnz_t.item())
         g_bytes, g_flops = spmv_bytes_flops(n_glob, n_glob, g_nnz, elem, beta != 0)
-        launches_per_step = 1 if world == 1 else (3 if peer is None else 3 + 4 * len(peer.peer) + 2 * len(peer.peer))
+        launches_per_step = 1 if (world == 1 or halo_mode == "p2p-fused") else (
+            3 if peer is None else 3 + 4 * len(peer.peer) + 2 * len(peer.peer))
 
     def barrier():
         if world > 1:

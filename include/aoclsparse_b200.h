@@ -142,6 +142,28 @@ DLL_PUBLIC aoclsparse_status aoclsparse_b200_dmv_rows_push(const double         
                                                            aoclsparse_int             row_end,
                                                            double                    *push_dst);
 
+/* The whole iteration x_{k+1}[own rows] = alpha * A_local * x_k in ONE launch: boundary CTAs (grid order: first
+ * boundary, last boundary, interior) wait in-kernel until the facing boundary of the neighbour has completed
+ * iteration k-1, store their results both locally and into the neighbour's halo over NVLink, and the last CTA of each
+ * side publishes "boundary done k" to that neighbour; interior CTAs overlap with all of that.
+ * Needs row cuts {h, m-h}, every row block binned thread-per-row (else aoclsparse_status_not_implemented: use the
+ * _rows / _rows_push / _signal / _wait calls), beta = 0.  Flags are 32-bit words in ipc memory; counters are 4 words
+ * of local device memory zeroed once before iteration 1 ([3] is set if a flag wait gave up). */
+typedef struct aoclsparse_b200_halo_ctl_
+{
+    const void *left_done, *right_done;       /* local flags written by the neighbours; NULL = no neighbour       */
+    void       *to_left_done, *to_right_done; /* the neighbours' flags this rank writes                            */
+    void       *counters;
+    void       *push_left, *push_right; /* neighbours' halo of x_{k+1} receiving my first / last boundary rows     */
+    unsigned    k;                      /* iteration number, 1, 2, 3, ...                                          */
+} aoclsparse_b200_halo_ctl;
+DLL_PUBLIC aoclsparse_status aoclsparse_b200_dmv_sharded_step(const double                  *alpha,
+                                                              aoclsparse_matrix              A,
+                                                              const aoclsparse_mat_descr     descr,
+                                                              const double                  *x,
+                                                              double                        *y,
+                                                              const aoclsparse_b200_halo_ctl *ctl);
+
 /* Stream-ordered cross-GPU flags (32-bit words in ipc memory): signal stores `value` after everything the
  * calling thread's stream did before is visible system-wide; wait holds the stream until *flag >= value
  * (wrap-safe), setting *timed_out (may be NULL) and giving up after ~4 s. */

@@ -73,6 +73,23 @@ def main():
     assert int(tout.item()) == 0, "a flag wait timed out"
     results["push"] = out.cpu().numpy()
 
+    # (c) the whole iteration in one kernel: multiply + push + flags
+    peer2 = sharding.PeerHalo(lib, slab, 8)
+    assert lib.memcpy(peer2.own_ptr(0), torch.from_numpy(x0).cuda().data_ptr(), m * 8) == 0
+    torch.cuda.synchronize()
+    dist.barrier()
+    peer2.initial_push(0)
+    dist.barrier()
+    for k in range(1, iters + 1):
+        assert peer2.iteration_fused(k, 1.0 / 12, A, d) == 0, lib.last_error()
+    torch.cuda.synchronize()
+    dist.barrier()
+    assert peer2.timed_out() == 0, "a flag wait timed out"
+    out2 = torch.empty(m, dtype=torch.float64, device="cuda")
+    assert lib.memcpy(out2.data_ptr(), peer2.own_ptr(iters % 2), m * 8) == 0
+    torch.cuda.synchronize()
+    results["fused"] = out2.cpu().numpy()
+
     # un-sharded truth on the host
     import scipy.sparse as sp
     rpg, colg, valg = gen_np.stencil(7, nx, ny, nz)
@@ -85,7 +102,8 @@ def main():
     for mode, got in results.items():
         err = float(np.max(np.abs(got - want)) / scale)
         assert err <= 1e-12 * iters, (mode, err)
-    assert np.array_equal(results["nccl"], results["push"])  # same kernels, same order: bit-identical
+    assert np.array_equal(results["nccl"], results["push"])  # same arithmetic in the same order: bit-identical
+    assert np.array_equal(results["nccl"], results["fused"])
     dist.barrier()
     if rank == 0:
         print("MULTI_GPU_CHECK_OK world=%d" % world)
