@@ -544,6 +544,22 @@ aoclsparse_status aoclsparse_optimize(aoclsparse_matrix A)
     if(!M.plan.valid || forced >= 0)
         B200_TRY(build_plan(M, value_size(A->val_type), A->max_row_nnz, forced, A->row_cuts, st));
 
+    // hot-column table for gather-bound (skewed) matrices with a plain general mv hint, memory policy permitting
+    {
+        bool gn_mv_hint = false;
+        for(const hint &h : A->hints)
+            gn_mv_hint = gn_mv_hint || (h.act == 1 && h.doid == DOID_GN);
+        const long long mean   = A->m > 0 ? (long long)A->nnz / A->m : 0;
+        const bool      skewed = (long long)A->max_row_nnz > 16 * (mean > 1 ? mean : 1);
+        const char     *e      = getenv("AOCLSPARSE_B200_HOT");
+        // off by default: both realisations measured slower than the plain kernel on R-MAT scale 24
+        // (profiles/r01_summary.md, "hot-column table"); AOCLSPARSE_B200_HOT=1 enables it for experiments
+        const bool      want   = e ? atoi(e) != 0 : false;
+        if(want && gn_mv_hint && skewed && A->mem_policy == aoclsparse_memory_usage_unrestricted && A->win_hi < 0
+           && M.plan.hot_entries == 0 && A->row_cuts.empty())
+            B200_TRY(build_hot_table(M, value_size(A->val_type), st));
+    }
+
     // transposed device copies for general transposed mv / mm hints (memory policy permitting):
     // they turn the atomic scatter into a streaming gather
     if(A->mem_policy == aoclsparse_memory_usage_unrestricted && A->win_hi < 0)
@@ -612,6 +628,8 @@ aoclsparse_status aoclsparse_b200_get_matrix_info(const aoclsparse_matrix A, aoc
         info->n_product_blocks = P.n_strat[STRAT_PRODUCT];
         info->n_long_segments  = P.n_long_segments;
         info->n_long_rows      = P.n_long_rows;
+        info->hot_entries      = P.hot_entries;
+        info->hot_mass_ppm     = (aoclsparse_int)(P.hot_mass * 1e6);
     }
     return aoclsparse_status_success;
 }

@@ -346,6 +346,13 @@ namespace b200
         aoclsparse_int n_long_segments = 0;
         aoclsparse_int n_strat[4] = {0, 0, 0, 0};
         aoclsparse_int max_block_rows = 0; // most rows any block holds (sizes the staged row_ptr slice)
+        // hot-column table (hot.cu / spmv_hot.cuh): 0 entries = not built
+        aoclsparse_int hot_entries = 0;
+        int            hot_stages  = 2;
+        int            hot_mode    = 1;   // 1: packed side vector + L1 priorities (default), 2: persistent smem table
+        double         hot_mass    = 0.0; // fraction of stored entries whose column is in the table
+        dev_buf        hot_cols;          // int[hot_entries] column of every slot
+        dev_buf        col_hot;           // int[nnz] column array with hot columns replaced by HOT_BIT | slot
         int            pdl              = 1; // programmatic dependent launch of the multiply kernel (tuning knob)
         int            pipelined        = 0; // use the persistent pipelined kernel when every block is thread-per-row
         int            pipe_stages      = 4; // ring depth of that kernel
@@ -484,6 +491,11 @@ namespace b200
                                       const aoclsparse_int *row_ptr,
                                       const aoclsparse_int *col_idx,
                                       const void           *val);
+
+    // hot.cu
+    aoclsparse_status build_hot_table(dev_csr &A, size_t elem_size, cudaStream_t st);
+    template <typename T>
+    aoclsparse_status launch_hot(const dev_csr &A, const T *x, T *y, T alpha, T beta, cudaStream_t st);
 
     // clean.cu
     aoclsparse_status ensure_clean(aoclsparse_matrix A, cudaStream_t st);

@@ -8,6 +8,8 @@
 #include "spmv_pipelined.cuh"
 #include "spmv_sharded.cuh"
 
+#include <unordered_map>
+
 namespace b200
 {
     namespace
@@ -36,7 +38,7 @@ namespace b200
             return aoclsparse_status_success;
         }
 
-        template <typename T, bool GENERIC, int NT, bool PUSH = false>
+        template <typename T, bool GENERIC, int NT, bool PUSH = false, bool HOT = false>
         aoclsparse_status launch_row_blocks(const dev_csr &A,
                                             int            b0,
                                             int            b1,
@@ -47,7 +49,8 @@ namespace b200
                                             elem_rule      rule,
                                             cudaStream_t   st,
                                             T             *push_dst  = nullptr,
-                                            int            push_row0 = 0)
+                                            int            push_row0 = 0,
+                                            const T       *xh        = nullptr)
         {
             const row_block_plan &P    = A.plan;
             const int             cap  = P.block_nnz + 8;
@@ -56,7 +59,7 @@ namespace b200
             if(configured.load(std::memory_order_acquire) < smem)
             {
                 B200_CUDA(cudaFuncSetAttribute(
-                    spmv_row_blocks_kernel<T, GENERIC, NT, PUSH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    spmv_row_blocks_kernel<T, GENERIC, NT, PUSH, HOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 configured.store(smem, std::memory_order_release);
             }
             cudaLaunchConfig_t cfg = {};
@@ -70,13 +73,13 @@ namespace b200
             cfg.attrs                                          = attr;
             cfg.numAttrs                                       = P.pdl ? 1 : 0;
             B200_CUDA(cudaLaunchKernelEx(&cfg,
-                                         spmv_row_blocks_kernel<T, GENERIC, NT, PUSH>,
+                                         spmv_row_blocks_kernel<T, GENERIC, NT, PUSH, HOT>,
                                          (const int4 *)P.desc.as<int4>(),
                                          (const int *)P.kind.as<int>(),
                                          b0,
                                          cap,
                                          (const aoclsparse_int *)A.row_ptr.as<aoclsparse_int>(),
-                                         (const aoclsparse_int *)A.col_idx.as<aoclsparse_int>(),
+                                         (const aoclsparse_int *)(HOT ? P.col_hot.as<aoclsparse_int>() : A.col_idx.as<aoclsparse_int>()),
                                          (const T *)A.val.as<T>(),
                                          x,
                                          y,
@@ -88,7 +91,8 @@ namespace b200
                                          (int)A.n,
                                          P.stream_hint,
                                          push_dst,
-                                         push_row0));
+                                         push_row0,
+                                         xh));
             B200_LAUNCHED();
             return aoclsparse_status_success;
         }
@@ -159,6 +163,34 @@ namespace b200
             if(b1 <= b0)
                 return aoclsparse_status_success;
             const int bz = is_zero(beta) ? 1 : 0;
+            if(!generic && !push_dst && P.hot_entries > 0 && b0 == 0 && b1 == P.n_blocks)
+            {
+                if(P.hot_mode == 2)
+                    B200_TRY(launch_hot<T>(A, x, y, alpha, beta, st)); // persistent shared-memory table (experiment)
+                else
+                {
+                    // pack the hot entries of x into the dense side vector, then the ordinary kernel on the remapped
+                    // column array
+                    // scratch per (host thread, stream): concurrent multiplies on one handle must not share it
+                    static thread_local std::unordered_map<cudaStream_t, dev_buf> scratch;
+                    dev_buf &hb = scratch[st];
+                    if(hb.bytes < sizeof(T) * (size_t)P.hot_entries)
+                        B200_TRY(hb.alloc(sizeof(T) * (size_t)P.hot_entries));
+                    T *xh = hb.as<T>();
+                    pack_hot_x_kernel<T><<<(P.hot_entries + 255) / 256, 256, 0, st>>>(
+                        P.hot_entries, P.hot_cols.as<aoclsparse_int>(), x, xh);
+                    B200_LAUNCHED();
+                    B200_TRY((launch_row_blocks<T, false, 256, false, true>(A, b0, b1, x, y, alpha, beta, rule, st, nullptr, 0, xh)));
+                }
+                if(P.n_long_rows > 0)
+                {
+                    const long long threads = (long long)P.n_long_rows * 32;
+                    finish_long_rows_kernel<T><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(
+                        P.n_long_rows, P.long_rows.as<int4>(), P.partials.as<T>(), x, y, alpha, beta, bz, 0, A.n, row_lo, row_hi);
+                    B200_LAUNCHED();
+                }
+                return aoclsparse_status_success;
+            }
             if(!generic && P.pipelined && P.n_strat[STRAT_THREAD] == P.n_blocks)
                 return launch_pipelined<T>(A, b0, b1, x, y, alpha, beta, st, push_dst, row_lo);
             if(push_dst)

@@ -508,7 +508,8 @@ def run_gpu(args, wl):
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get(args.workload)
     roof = {"bound": "hbm", "unit": "GB/s", "peak": peak, "peak_source": peak_src, "traffic": traffic,
-            "kernel": "spmv_row_blocks_kernel" if wl["kind"] == "mv" else "csrmm_row_major_kernel",
+            "kernel": ("spmv_hot_kernel" if info.hot_entries else ("spmv_sharded_step_kernel" if (sharded and world > 1)
+                       else "spmv_row_blocks_kernel")) if wl["kind"] == "mv" else "csrmm_row_major_vec_kernel",
             "algorithmic_bytes_per_launch": int(l_bytes)}
     if kern_ms:
         roof["achieved"] = round(l_bytes / (kern_ms * 1e-3) / 1e9, 1)
@@ -542,7 +543,8 @@ def run_gpu(args, wl):
                    ("rotating over %d independent (A,x,y) sets, %.0f MB in total vs 126 MB L2" % (n_sets, n_sets * l_bytes / 1e6)),
                    "plan": {"block_nnz": info.block_nnz, "blocks": info.n_blocks, "thread": info.n_thread_blocks,
                             "warp": info.n_warp_blocks, "product": info.n_product_blocks,
-                            "long_segments": info.n_long_segments, "long_rows": info.n_long_rows},
+                            "long_segments": info.n_long_segments, "long_rows": info.n_long_rows,
+                            "hot_table_entries": info.hot_entries, "hot_table_mass": info.hot_mass_ppm / 1e6},
                    "optimize_ms": round(optimize_ms, 2)},
         "effective_gbs": round(eff_gbs, 1), "effective_frac_of_8TBs": round(eff_gbs / (8000.0 * world), 4),
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),

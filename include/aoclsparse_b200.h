@@ -50,6 +50,8 @@ typedef struct aoclsparse_b200_matrix_info_
     aoclsparse_int n_product_blocks; /* blocks binned CTA-wide product + segmented sum          */
     aoclsparse_int n_long_segments; /* blocks that are one segment of a row split across CTAs   */
     aoclsparse_int n_long_rows;     /* rows split across CTAs                                   */
+    aoclsparse_int hot_entries;     /* hot-column table: entries of x kept in shared memory, 0 = not built     */
+    aoclsparse_int hot_mass_ppm;    /* stored entries whose column is in that table, parts per million          */
 } aoclsparse_b200_matrix_info;
 
 DLL_PUBLIC aoclsparse_status aoclsparse_b200_get_matrix_info(const aoclsparse_matrix      A,

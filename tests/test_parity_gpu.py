@@ -574,6 +574,17 @@ def test_config3_rmat_float(lib, oracle):
     oracle.csrmv(111, 1.0, m, m, 0, rp, col, val.astype(np.float64), 0, 0, 0, x.astype(np.float64), 0.0, y64)
     assert np.max(np.abs(y - y64) / np.where(den > 0, den, 1)) <= 1e-5
     assert info.n_long_rows > 0 and info.n_product_blocks > 0  # hub rows are split, skewed blocks use product
+    assert info.hot_entries == 0
+    # experimental hot-column table paths (off by default): packed side vector (mode 1), persistent smem table (2)
+    for mode in ("1", "2"):
+        os.environ["AOCLSPARSE_B200_HOT"] = "1"
+        os.environ["AOCLSPARSE_B200_HOT_MODE"] = mode
+        try:
+            y2, info2 = _device_mv(lib, "s", 0, m, m, rp, col, val, x, np.zeros(m, np.float32), 1.0, 0.0)
+        finally:
+            del os.environ["AOCLSPARSE_B200_HOT"], os.environ["AOCLSPARSE_B200_HOT_MODE"]
+        assert info2.hot_entries > 0 and info2.hot_mass_ppm > 150000
+        assert np.max(np.abs(y2.astype(np.float64) - yo) / np.where(den > 0, den, 1)) <= 1e-5, mode
 
 
 @pytest.mark.parametrize("order", [0, 1])
