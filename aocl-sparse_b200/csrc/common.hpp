@@ -364,6 +364,14 @@ namespace b200
         dev_buf        long_rows; // int4 per long row: row, first slot, n segments, unused
         dev_buf        partials;  // one value per long segment
         std::vector<aoclsparse_int> cut_block; // block index at which each row cut starts (+ ends)
+        // host-staged multiplies (x, y in host memory): the blocks cut into a few chunks with the x prefix each needs,
+        // so that H2D of x, the kernels and D2H of y pipeline on three streams (spmv.cu: mv_host_pipelined)
+        struct host_chunk
+        {
+            aoclsparse_int b0, b1, row0, row1, x_hi; // blocks, rows, one past the largest column used so far
+        };
+        std::vector<host_chunk> host_chunks;
+        bool                    host_chunks_ready = false;
         bool           valid = false;
     };
 

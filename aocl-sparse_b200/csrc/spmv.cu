@@ -8,6 +8,7 @@
 #include "spmv_pipelined.cuh"
 #include "spmv_sharded.cuh"
 
+#include <cstdlib>
 #include <unordered_map>
 
 namespace b200
@@ -273,6 +274,28 @@ namespace b200
                                 cudaStream_t               st)
     {
         B200_TRY(ensure_plan(A, st));
+        // symmetric / hermitian descriptor that was hinted (aoclsparse_set_mv_hint + aoclsparse_optimize): multiply with
+        // the expanded general copy (the reference materialises the same copy in aoclsparse_matrix_transform,
+        // csr_util.hpp:620-745) -- a plain streaming gather instead of gather + atomic scatter
+        if((descr.type == aoclsparse_matrix_type_symmetric || descr.type == aoclsparse_matrix_type_hermitian)
+           && A->mem_policy == aoclsparse_memory_usage_unrestricted && A->win_hi < 0)
+        {
+            const int d_id  = get_doid(vt<T>::is_complex, descr.type, descr.fill_mode, op);
+            bool      hinted = false;
+            {
+                std::shared_lock<std::shared_mutex> rl0(A->guard);
+                for(const hint &h : A->hints)
+                    hinted = hinted || (h.act == 1 && h.doid == d_id && h.done);
+            }
+            if(hinted)
+            {
+                const dev_csr *F = nullptr;
+                B200_TRY(get_expanded_copy(A, descr, op, F, st));
+                std::shared_lock<std::shared_mutex> rl1(A->guard);
+                elem_rule none_rule{MASK_NONE, DIAG_KEEP, 0, 0};
+                return launch_gather<T>(*F, 0, F->plan.n_blocks, 0, F->m, x, y, alpha, beta, false, none_rule, st);
+            }
+        }
         std::shared_lock<std::shared_mutex> rl(A->guard);
         const dev_csr                      &M = *A->mats[0];
         const bool                          cplx = vt<T>::is_complex;
@@ -356,6 +379,162 @@ namespace b200
         return aoclsparse_status_invalid_value;
     }
 
+    namespace
+    {
+        __global__ void block_maxcol_kernel(int nblocks, const int4 *__restrict__ desc, const aoclsparse_int *__restrict__ col, int *out)
+        {
+            const int lane = threadIdx.x & 31;
+            const int b    = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+            if(b >= nblocks)
+                return;
+            const int4 d = desc[b];
+            int        mx = -1;
+            for(int p = d.z + lane; p < d.w; p += 32)
+                mx = max(mx, col[p]);
+            for(int off = 16; off > 0; off >>= 1)
+                mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+            if(lane == 0)
+                out[b] = mx;
+        }
+
+        // builds (once per plan) the chunk table of the host-staged pipeline
+        aoclsparse_status ensure_host_chunks(aoclsparse_matrix A, size_t elem_size, cudaStream_t st)
+        {
+            std::unique_lock<std::shared_mutex> wl(A->guard);
+            dev_csr                            &M = *A->mats[0];
+            row_block_plan                     &P = M.plan;
+            if(P.host_chunks_ready)
+                return aoclsparse_status_success;
+            P.host_chunks.clear();
+            P.host_chunks_ready = true;
+            // only plans without split rows (their partial sums are finished per launch) and big enough to matter
+            const size_t vec_bytes = ((size_t)M.m + (size_t)M.n) * elem_size;
+            if(P.n_long_rows > 0 || P.n_blocks < 64 || vec_bytes < (size_t)(4u << 20))
+                return aoclsparse_status_success;
+            dev_buf d_mx;
+            B200_TRY(d_mx.alloc(sizeof(int) * (size_t)P.n_blocks));
+            const long long threads = (long long)P.n_blocks * 32;
+            block_maxcol_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(
+                P.n_blocks, P.desc.as<int4>(), M.col_idx.as<aoclsparse_int>(), d_mx.as<int>());
+            B200_LAUNCHED();
+            std::vector<int>  mx((size_t)P.n_blocks);
+            std::vector<int4> hd((size_t)P.n_blocks);
+            B200_CUDA(cudaMemcpyAsync(mx.data(), d_mx.p, sizeof(int) * mx.size(), cudaMemcpyDeviceToHost, st));
+            B200_CUDA(cudaMemcpyAsync(hd.data(), P.desc.p, sizeof(int4) * hd.size(), cudaMemcpyDeviceToHost, st));
+            B200_CUDA(cudaStreamSynchronize(st));
+            // ~4 MB of vector traffic per chunk, 2..8 chunks (measured on C2: 2 chunks 0.594 ms, 8 chunks 0.546 ms,
+            // 16 chunks 0.62 ms; un-pipelined 0.755 ms)
+            int n_chunks = (int)(vec_bytes / (size_t)(4u << 20));
+            n_chunks     = n_chunks < 2 ? 2 : (n_chunks > 8 ? 8 : n_chunks);
+            if(const char *e = getenv("AOCLSPARSE_B200_HOST_CHUNKS"))
+                n_chunks = atoi(e) < 1 ? 1 : (atoi(e) > 16 ? 16 : atoi(e));
+            int run_max  = -1;
+            for(int c = 0; c < n_chunks; ++c)
+            {
+                row_block_plan::host_chunk h;
+                h.b0 = (aoclsparse_int)((long long)P.n_blocks * c / n_chunks);
+                h.b1 = (aoclsparse_int)((long long)P.n_blocks * (c + 1) / n_chunks);
+                if(h.b1 <= h.b0)
+                    continue;
+                for(int b = h.b0; b < h.b1; ++b)
+                    run_max = mx[b] > run_max ? mx[b] : run_max;
+                h.row0 = hd[h.b0].x;
+                h.row1 = hd[h.b1 - 1].y;
+                h.x_hi = run_max + 1;
+                P.host_chunks.push_back(h);
+            }
+            if(P.host_chunks.size() < 2)
+                P.host_chunks.clear();
+            return aoclsparse_status_success;
+        }
+
+        struct host_pipe
+        {
+            cudaStream_t h2d = nullptr, d2h = nullptr;
+            cudaEvent_t  ev_x[16] = {}, ev_k[16] = {}, ev_start = nullptr;
+            bool         ready = false;
+            aoclsparse_status init()
+            {
+                if(ready)
+                    return aoclsparse_status_success;
+                B200_CUDA(cudaStreamCreateWithFlags(&h2d, cudaStreamNonBlocking));
+                B200_CUDA(cudaStreamCreateWithFlags(&d2h, cudaStreamNonBlocking));
+                for(int i = 0; i < 16; ++i)
+                {
+                    B200_CUDA(cudaEventCreateWithFlags(&ev_x[i], cudaEventDisableTiming));
+                    B200_CUDA(cudaEventCreateWithFlags(&ev_k[i], cudaEventDisableTiming));
+                }
+                B200_CUDA(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
+                ready = true;
+                return aoclsparse_status_success;
+            }
+        };
+        host_pipe &tls_pipe()
+        {
+            static thread_local host_pipe p;
+            return p;
+        }
+
+        // y = alpha*A*x + beta*y with x and y in HOST memory, general matrix, op = none: x arrives in pieces, each
+        // chunk of row blocks starts as soon as the prefix of x it reads is on the device, and its slice of y leaves
+        // while later chunks still compute -- H2D, kernels and D2H overlap (PCIe is full duplex)
+        template <typename T>
+        aoclsparse_status mv_host_pipelined(aoclsparse_matrix A, T alpha, const T *hx, T beta, T *hy, cudaStream_t st, bool &done)
+        {
+            done = false;
+            B200_TRY(ensure_plan(A, st));
+            B200_TRY(ensure_host_chunks(A, sizeof(T), st));
+            std::shared_lock<std::shared_mutex> rl(A->guard);
+            const dev_csr                      &M = *A->mats[0];
+            const row_block_plan               &P = M.plan;
+            if(P.host_chunks.empty())
+                return aoclsparse_status_success;
+            host_pipe &hp = tls_pipe();
+            B200_TRY(hp.init());
+            staging &sg = tls_staging();
+            if(sg.x.bytes < (size_t)M.n * sizeof(T))
+                B200_TRY(sg.x.alloc((size_t)M.n * sizeof(T)));
+            if(sg.y.bytes < (size_t)M.m * sizeof(T))
+                B200_TRY(sg.y.alloc((size_t)M.m * sizeof(T)));
+            T         *dx = sg.x.as<T>(), *dy = sg.y.as<T>();
+            const bool bz = is_zero(beta);
+            elem_rule  none_rule{MASK_NONE, DIAG_KEEP, 0, 0};
+            // the side streams start after whatever the caller's stream was doing
+            B200_CUDA(cudaEventRecord(hp.ev_start, st));
+            B200_CUDA(cudaStreamWaitEvent(hp.h2d, hp.ev_start, 0));
+            B200_CUDA(cudaStreamWaitEvent(hp.d2h, hp.ev_start, 0));
+            const int nc    = (int)P.host_chunks.size();
+            int       x_lo  = 0;
+            for(int c = 0; c < nc; ++c)
+            {
+                const auto &h   = P.host_chunks[c];
+                int         xhi = c == nc - 1 ? M.n : (h.x_hi > x_lo ? h.x_hi : x_lo); // the tail of x goes with the last chunk
+                if(xhi > x_lo)
+                    B200_CUDA(cudaMemcpyAsync(dx + x_lo, hx + x_lo, (size_t)(xhi - x_lo) * sizeof(T), cudaMemcpyHostToDevice, hp.h2d));
+                x_lo = xhi;
+                if(!bz && h.row1 > h.row0)
+                    B200_CUDA(cudaMemcpyAsync(
+                        dy + h.row0, hy + h.row0, (size_t)(h.row1 - h.row0) * sizeof(T), cudaMemcpyHostToDevice, hp.h2d));
+                B200_CUDA(cudaEventRecord(hp.ev_x[c], hp.h2d));
+            }
+            for(int c = 0; c < nc; ++c)
+            {
+                const auto &h = P.host_chunks[c];
+                B200_CUDA(cudaStreamWaitEvent(st, hp.ev_x[c], 0));
+                B200_TRY(launch_gather<T>(M, h.b0, h.b1, h.row0, h.row1, dx, dy, alpha, beta, false, none_rule, st));
+                B200_CUDA(cudaEventRecord(hp.ev_k[c], st));
+                B200_CUDA(cudaStreamWaitEvent(hp.d2h, hp.ev_k[c], 0));
+                if(h.row1 > h.row0)
+                    B200_CUDA(cudaMemcpyAsync(
+                        hy + h.row0, dy + h.row0, (size_t)(h.row1 - h.row0) * sizeof(T), cudaMemcpyDeviceToHost, hp.d2h));
+            }
+            B200_CUDA(cudaStreamSynchronize(hp.d2h));
+            B200_CUDA(cudaStreamSynchronize(st));
+            done = true;
+            return aoclsparse_status_success;
+        }
+    }
+
     // Common validation + staging.  Mirrors aoclsparse::mv<T> (mv.cpp:55-121).
     template <typename T>
     aoclsparse_status mv_entry(aoclsparse_operation       op,
@@ -421,6 +600,18 @@ namespace b200
 
         const bool x_dev = is_device_accessible(x), y_dev = is_device_accessible(y);
         const bool empty = A->m == 0 || A->n == 0 || (A->nnz == 0 && descr->type == aoclsparse_matrix_type_general);
+
+        // both vectors on the host, plain general product: chunked pipeline over three streams
+        if(!x_dev && !y_dev && !empty && descr->type == aoclsparse_matrix_type_general && op == aoclsparse_operation_none
+           && A->win_hi < 0)
+        {
+            bool              done = false;
+            aoclsparse_status ps   = mv_host_pipelined<T>(A, *alpha, x, *beta, y, st, done);
+            if(ps != aoclsparse_status_success)
+                return ps;
+            if(done)
+                return aoclsparse_status_success;
+        }
 
         const T *dx = x;
         T       *dy = y;
