@@ -106,6 +106,9 @@ class AoclSparse:
             getattr(L, f"aoclsparse_create_{p}csr").argtypes = [C.POINTER(vp), ci, i32, i32, i32, vp, vp, vp]
             getattr(L, f"aoclsparse_{p}mv").argtypes = [ci, vp, vp, vp, vp, vp, vp]
             getattr(L, f"aoclsparse_{p}update_values").argtypes = [vp, i32, vp]
+        for p, ct in (("s", C.c_float), ("d", C.c_double), ("c", FloatComplex), ("z", DoubleComplex)):
+            getattr(L, f"aoclsparse_{p}dotmv").argtypes = [ci, ct, vp, vp, vp, ct, vp, vp]
+            getattr(L, f"aoclsparse_{p}set_value").argtypes = [vp, i32, i32, ct]
         L.aoclsparse_scsrmm.argtypes = [ci, C.c_float, vp, vp, ci, vp, i32, i32, C.c_float, vp, i32]
         L.aoclsparse_dcsrmm.argtypes = [ci, C.c_double, vp, vp, ci, vp, i32, i32, C.c_double, vp, i32]
         L.aoclsparse_ccsrmm.argtypes = [ci, FloatComplex, vp, vp, ci, vp, i32, i32, FloatComplex, vp, i32]
@@ -211,6 +214,13 @@ class AoclSparse:
                 op, a, h, descr, order, ptr(B), n, ldb, b, ptr(Cm), ldc)
         return getattr(self.lib, f"aoclsparse_{prefix}csrmm_kid")(
             op, a, h, descr, order, ptr(B), n, ldb, b, ptr(Cm), ldc, kid)
+
+    def dotmv(self, prefix, op, alpha, h, descr, x, beta, y, d):
+        return getattr(self.lib, f"aoclsparse_{prefix}dotmv")(
+            op, _scalar_by_value(prefix, alpha), h, descr, ptr(x), _scalar_by_value(prefix, beta), ptr(y), ptr(d))
+
+    def set_value(self, prefix, h, row, col, val):
+        return getattr(self.lib, f"aoclsparse_{prefix}set_value")(h, row, col, _scalar_by_value(prefix, val))
 
     def spmm(self, op, a, b):
         c = C.c_void_p()

@@ -764,9 +764,186 @@ namespace b200
     }
 }
 
+namespace b200
+{
+    namespace
+    {
+        // d = sum_i conj(x_i) * y_i, deterministic two-level reduction (aoclsparse::dense_dot,
+        // library/src/level1/aoclsparse_dense_dot_kt.cpp:30-66)
+        template <typename T>
+        __global__ void dotc_partial_kernel(long long n, const T *__restrict__ x, const T *__restrict__ y, T *partial)
+        {
+            __shared__ T sh[8];
+            T            acc = vt<T>::zero();
+            for(long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+                acc = mad(cj(x[i]), y[i], acc);
+            acc = warp_sum(acc);
+            if((threadIdx.x & 31) == 0)
+                sh[threadIdx.x >> 5] = acc;
+            __syncthreads();
+            if(threadIdx.x == 0)
+            {
+                T t = sh[0];
+                for(int w = 1; w < (int)(blockDim.x >> 5); ++w)
+                    t = add(t, sh[w]);
+                partial[blockIdx.x] = t;
+            }
+        }
+        template <typename T>
+        __global__ void dotc_final_kernel(int n, const T *__restrict__ partial, T *out)
+        {
+            T acc = vt<T>::zero();
+            for(int i = threadIdx.x; i < n; i += 32)
+                acc = add(acc, partial[i]);
+            acc = warp_sum(acc);
+            if(threadIdx.x == 0)
+                *out = acc;
+        }
+    }
+
+    // y = alpha*op(A)*x + beta*y, d = x^H y over the first min(m,n) entries: aoclsparse_dotmv_t
+    // (library/src/level2/aoclsparse_dotmv.hpp:30-62)
+    template <typename T>
+    aoclsparse_status dotmv_entry(aoclsparse_operation       op,
+                                  T                          alpha,
+                                  aoclsparse_matrix          A,
+                                  const aoclsparse_mat_descr descr,
+                                  const T                   *x,
+                                  T                          beta,
+                                  T                         *y,
+                                  T                         *d)
+    {
+        if(d == nullptr || A == nullptr)
+            return aoclsparse_status_invalid_pointer;
+        B200_TRY(mv_entry<T>(op, &alpha, A, descr, x, &beta, y));
+        cudaStream_t    st  = current_stream();
+        const long long len = A->m < A->n ? A->m : A->n;
+        const bool      x_dev = is_device_accessible(x), y_dev = is_device_accessible(y), d_dev = is_device_accessible(d);
+        dev_buf         tx, ty, part;
+        const T        *dx = x;
+        const T        *dy = y;
+        if(!x_dev && len > 0)
+        {
+            B200_TRY(tx.alloc(sizeof(T) * (size_t)len));
+            B200_CUDA(cudaMemcpyAsync(tx.p, x, sizeof(T) * (size_t)len, cudaMemcpyHostToDevice, st));
+            dx = tx.as<T>();
+        }
+        if(!y_dev && len > 0)
+        {
+            B200_TRY(ty.alloc(sizeof(T) * (size_t)len));
+            B200_CUDA(cudaMemcpyAsync(ty.p, y, sizeof(T) * (size_t)len, cudaMemcpyHostToDevice, st));
+            dy = ty.as<T>();
+        }
+        const int nb = 148 * 4;
+        B200_TRY(part.alloc(sizeof(T) * (size_t)(nb + 1)));
+        dotc_partial_kernel<T><<<nb, 256, 0, st>>>(len, dx, dy, part.as<T>());
+        B200_LAUNCHED();
+        T *dout = d_dev ? d : part.as<T>() + nb;
+        dotc_final_kernel<T><<<1, 32, 0, st>>>(nb, part.as<T>(), dout);
+        B200_LAUNCHED();
+        if(!d_dev)
+            B200_CUDA(cudaMemcpyAsync(d, dout, sizeof(T), cudaMemcpyDeviceToHost, st));
+        B200_CUDA(cudaStreamSynchronize(st)); // temporaries are freed on return
+        return aoclsparse_status_success;
+    }
+
+    // aoclsparse_set_value_t (library/src/extra/aoclsparse_auxiliary.hpp:388-473): overwrite one stored entry
+    namespace
+    {
+        template <typename T>
+        __global__ void set_value_kernel(const aoclsparse_int *__restrict__ rp, const aoclsparse_int *__restrict__ col, T *val, int row, int c, T v, int *found)
+        {
+            // first match in storage order, like the reference's scan
+            int hit = -1;
+            for(int p = rp[row]; p < rp[row + 1]; ++p)
+                if(col[p] == c)
+                {
+                    hit = p;
+                    break;
+                }
+            if(hit >= 0)
+                val[hit] = v;
+            *found = hit >= 0 ? 1 : 0;
+        }
+    }
+
+    template <typename T>
+    aoclsparse_status set_value_entry(aoclsparse_matrix A, aoclsparse_int row_idx, aoclsparse_int col_idx, T v)
+    {
+        if(A == nullptr)
+            return aoclsparse_status_invalid_pointer;
+        if(A->mats.empty() || A->mats[0] == nullptr)
+            return aoclsparse_status_invalid_pointer;
+        const aoclsparse_int base = A->base;
+        if(A->m + base <= row_idx || row_idx < base || A->n + base <= col_idx || col_idx < base)
+            return aoclsparse_status_invalid_value;
+        if(A->val_type != vt<T>::data_type)
+            return aoclsparse_status_wrong_type;
+        cudaStream_t                        st = current_stream();
+        std::unique_lock<std::shared_mutex> wl(A->guard);
+        dev_csr                            &M = *A->mats[0];
+        dev_buf                             flag;
+        B200_TRY(flag.alloc(sizeof(int)));
+        set_value_kernel<T><<<1, 1, 0, st>>>(M.row_ptr.as<aoclsparse_int>(),
+                                             M.col_idx.as<aoclsparse_int>(),
+                                             M.val.as<T>(),
+                                             (int)(row_idx - base),
+                                             (int)(col_idx - base),
+                                             v,
+                                             flag.as<int>());
+        B200_LAUNCHED();
+        int found = 0;
+        B200_CUDA(cudaMemcpyAsync(&found, flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        B200_CUDA(cudaStreamSynchronize(st));
+        if(!found)
+            return aoclsparse_status_invalid_index_value;
+        // derived copies hold the old value (the reference drops them too, auxiliary.hpp:463-471)
+        for(size_t i = 1; i < A->mats.size(); ++i)
+            delete A->mats[i];
+        A->mats.resize(1);
+        A->clean = clean_csr();
+        for(auto &h : A->hints)
+            h.done = false;
+        return aoclsparse_status_success;
+    }
+}
+
 using namespace b200;
 
 extern "C" {
+
+aoclsparse_status aoclsparse_sdotmv(const aoclsparse_operation op, const float alpha, aoclsparse_matrix A, const aoclsparse_mat_descr descr, const float *x, const float beta, float *y, float *d)
+{
+    return dotmv_entry<float>(op, alpha, A, descr, x, beta, y, d);
+}
+aoclsparse_status aoclsparse_ddotmv(const aoclsparse_operation op, const double alpha, aoclsparse_matrix A, const aoclsparse_mat_descr descr, const double *x, const double beta, double *y, double *d)
+{
+    return dotmv_entry<double>(op, alpha, A, descr, x, beta, y, d);
+}
+aoclsparse_status aoclsparse_cdotmv(const aoclsparse_operation op, const aoclsparse_float_complex alpha, aoclsparse_matrix A, const aoclsparse_mat_descr descr, const aoclsparse_float_complex *x, const aoclsparse_float_complex beta, aoclsparse_float_complex *y, aoclsparse_float_complex *d)
+{
+    return dotmv_entry<float2>(op, make_float2(alpha.real, alpha.imag), A, descr, reinterpret_cast<const float2 *>(x), make_float2(beta.real, beta.imag), reinterpret_cast<float2 *>(y), reinterpret_cast<float2 *>(d));
+}
+aoclsparse_status aoclsparse_zdotmv(const aoclsparse_operation op, const aoclsparse_double_complex alpha, aoclsparse_matrix A, const aoclsparse_mat_descr descr, const aoclsparse_double_complex *x, const aoclsparse_double_complex beta, aoclsparse_double_complex *y, aoclsparse_double_complex *d)
+{
+    return dotmv_entry<double2>(op, make_double2(alpha.real, alpha.imag), A, descr, reinterpret_cast<const double2 *>(x), make_double2(beta.real, beta.imag), reinterpret_cast<double2 *>(y), reinterpret_cast<double2 *>(d));
+}
+aoclsparse_status aoclsparse_sset_value(aoclsparse_matrix A, aoclsparse_int row_idx, aoclsparse_int col_idx, float val)
+{
+    return set_value_entry<float>(A, row_idx, col_idx, val);
+}
+aoclsparse_status aoclsparse_dset_value(aoclsparse_matrix A, aoclsparse_int row_idx, aoclsparse_int col_idx, double val)
+{
+    return set_value_entry<double>(A, row_idx, col_idx, val);
+}
+aoclsparse_status aoclsparse_cset_value(aoclsparse_matrix A, aoclsparse_int row_idx, aoclsparse_int col_idx, aoclsparse_float_complex val)
+{
+    return set_value_entry<float2>(A, row_idx, col_idx, make_float2(val.real, val.imag));
+}
+aoclsparse_status aoclsparse_zset_value(aoclsparse_matrix A, aoclsparse_int row_idx, aoclsparse_int col_idx, aoclsparse_double_complex val)
+{
+    return set_value_entry<double2>(A, row_idx, col_idx, make_double2(val.real, val.imag));
+}
 
 aoclsparse_status aoclsparse_scsrmv(aoclsparse_operation       trans,
                                     const float               *alpha,

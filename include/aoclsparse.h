@@ -250,6 +250,21 @@ DLL_PUBLIC aoclsparse_status aoclsparse_zupdate_values(aoclsparse_matrix        
                                                        aoclsparse_int             len,
                                                        aoclsparse_double_complex *val);
 
+/* Single-entry update.  Replaces aoclsparse_?set_value (aoclsparse_auxiliary.h:700-746; implementation
+ * library/src/extra/aoclsparse_auxiliary.hpp:388-473): (row_idx, col_idx) are given in the matrix' index base;
+ * out of range -> invalid_value, value type mismatch -> wrong_type, entry not stored -> invalid_index_value.
+ * B200: updates the device copy in place (first match in storage order) and drops derived copies. */
+DLL_PUBLIC aoclsparse_status aoclsparse_sset_value(aoclsparse_matrix A, aoclsparse_int row_idx, aoclsparse_int col_idx, float val);
+DLL_PUBLIC aoclsparse_status aoclsparse_dset_value(aoclsparse_matrix A, aoclsparse_int row_idx, aoclsparse_int col_idx, double val);
+DLL_PUBLIC aoclsparse_status aoclsparse_cset_value(aoclsparse_matrix        A,
+                                                   aoclsparse_int           row_idx,
+                                                   aoclsparse_int           col_idx,
+                                                   aoclsparse_float_complex val);
+DLL_PUBLIC aoclsparse_status aoclsparse_zset_value(aoclsparse_matrix         A,
+                                                   aoclsparse_int            row_idx,
+                                                   aoclsparse_int            col_idx,
+                                                   aoclsparse_double_complex val);
+
 /* ------------------------------------------------------------------------------------------
  * Hints and analysis.  Replaces aoclsparse_analysis.h:57 (optimize), :88-110 (mv / mv_kid / mm
  * hints), :279 (memory hint); implementation library/src/analysis/aoclsparse_analysis.cpp:426-747.
@@ -324,6 +339,43 @@ DLL_PUBLIC aoclsparse_status aoclsparse_zmv(aoclsparse_operation             op,
                                             const aoclsparse_double_complex *x,
                                             const aoclsparse_double_complex *beta,
                                             aoclsparse_double_complex       *y);
+
+/* Fused product and dot:  y = alpha * op(A) * x + beta * y,  *d = sum_{i < min(m,n)} conj(x_i) * y_i.
+ * Replaces aoclsparse_{s,d,c,z}dotmv (aoclsparse_functions.h:1761-1800; library/src/level2/aoclsparse_dotmv.hpp:30-62:
+ * NULL d or A -> invalid_pointer, then every check of aoclsparse_?mv).  alpha / beta by value.  d may be a host or a
+ * device pointer. */
+DLL_PUBLIC aoclsparse_status aoclsparse_sdotmv(const aoclsparse_operation op,
+                                               const float                alpha,
+                                               aoclsparse_matrix          A,
+                                               const aoclsparse_mat_descr descr,
+                                               const float               *x,
+                                               const float                beta,
+                                               float                     *y,
+                                               float                     *d);
+DLL_PUBLIC aoclsparse_status aoclsparse_ddotmv(const aoclsparse_operation op,
+                                               const double               alpha,
+                                               aoclsparse_matrix          A,
+                                               const aoclsparse_mat_descr descr,
+                                               const double              *x,
+                                               const double               beta,
+                                               double                    *y,
+                                               double                    *d);
+DLL_PUBLIC aoclsparse_status aoclsparse_cdotmv(const aoclsparse_operation      op,
+                                               const aoclsparse_float_complex  alpha,
+                                               aoclsparse_matrix               A,
+                                               const aoclsparse_mat_descr      descr,
+                                               const aoclsparse_float_complex *x,
+                                               const aoclsparse_float_complex  beta,
+                                               aoclsparse_float_complex       *y,
+                                               aoclsparse_float_complex       *d);
+DLL_PUBLIC aoclsparse_status aoclsparse_zdotmv(const aoclsparse_operation       op,
+                                               const aoclsparse_double_complex  alpha,
+                                               aoclsparse_matrix                A,
+                                               const aoclsparse_mat_descr       descr,
+                                               const aoclsparse_double_complex *x,
+                                               const aoclsparse_double_complex  beta,
+                                               aoclsparse_double_complex       *y,
+                                               aoclsparse_double_complex       *d);
 
 /* Handle-free legacy entry.  Replaces aoclsparse_{s,d}csrmv (aoclsparse_functions.h:695-721;
  * library/src/level2/aoclsparse_csrmv.cpp:30-63, checks in aoclsparse_csrmv.hpp:63-110): general

@@ -357,6 +357,74 @@ def test_update_values_refreshes_device_copy(lib, oracle):
     lib.destroy_descr(d)
 
 
+@pytest.mark.parametrize("p", ["s", "d", "c", "z"])
+def test_dotmv_and_set_value(lib, oracle, p):
+    """aoclsparse_?dotmv (dotmv.hpp:30-62) and aoclsparse_?set_value (auxiliary.hpp:388-473); formulas pinned on the
+    reference in tests/test_oracle.py::test_live_reference_dotmv_and_set_value"""
+    import torch
+    rng = np.random.default_rng(78)
+    dt = DT[p]
+    tol = TOL[np.dtype(dt)]
+    for base in (0, 1):
+        for op in (111, 112):
+            m, n = 300, 260
+            rp, col, val = gen_np.random_csr(rng, m, n, 0.05, dt, "full", base=base)
+            xl, yl = (n, m) if op == 111 else (m, n)
+            x = rng.normal(size=xl).astype(dt)
+            y0 = rng.normal(size=yl).astype(dt)
+            if p in "cz":
+                x = (x + 1j * rng.normal(size=xl)).astype(dt)
+            st, h = lib.create_csr(p, base, m, n, len(col), rp, col, val)
+            assert st == 0
+            d = lib.create_descr(base=base)
+            yo = y0.copy()
+            oracle.csrmv(op, 0.5, m, n, base, rp, col, val, 0, 0, 0, x, -1.5, yo)
+            k = min(m, n)
+            want = np.vdot(x[:k].astype(np.complex128), yo[:k].astype(np.complex128))
+            scale = np.sum(np.abs(x[:k].astype(np.complex128)) * np.abs(yo[:k].astype(np.complex128))) + 1e-300
+            # host operands
+            y, dot = y0.copy(), np.zeros(1, dt)
+            assert lib.dotmv(p, op, 0.5, h, d, x, -1.5, y, dot) == 0, lib.last_error()
+            assert abs(complex(dot[0]) - want) <= 50 * tol * scale
+            # device operands, device d
+            dx, dy = torch.from_numpy(x).cuda(), torch.from_numpy(y0).cuda()
+            dd = torch.zeros(2, dtype=torch.float64, device="cuda")
+            assert lib.dotmv(p, op, 0.5, h, d, dx.data_ptr(), -1.5, dy.data_ptr(), dd.data_ptr()) == 0
+            torch.cuda.synchronize()
+            got = np.frombuffer(dd.cpu().numpy().tobytes(), dtype=dt)[0]
+            assert abs(complex(got) - want) <= 50 * tol * scale
+            assert lib.dotmv(p, op, 0.5, h, d, x, -1.5, y, None) == capi.ST["invalid_pointer"]
+            lib.destroy_descr(d)
+            lib.destroy(h)
+    # set_value
+    m = n = 50
+    rp, col, val = gen_np.random_csr(rng, m, n, 0.2, dt, "none", ensure_diag=True, base=1)
+    st, h = lib.create_csr(p, 1, m, n, len(col), rp, col, val)
+    d = lib.create_descr(base=1)
+    assert lib.set_mv_hint(h, 112, d, 5) == 0 and lib.optimize(h) == 0  # a transposed copy exists and must be dropped
+    r = 17
+    c = int(col[rp[r] - 1 + 1]) if rp[r + 1] - rp[r] > 1 else int(col[rp[r] - 1])
+    pos = (rp[r] - 1) + int(np.argmax(col[rp[r] - 1: rp[r + 1] - 1] == c))
+    assert lib.set_value(p, h, r + 1, c, 3.25) == 0
+    val2 = val.copy()
+    val2[pos] = 3.25
+    missing = next(j for j in range(1, n + 1) if j not in col[rp[r] - 1: rp[r + 1] - 1])
+    assert lib.set_value(p, h, r + 1, missing, 1.0) == capi.ST["invalid_index_value"]
+    assert lib.set_value(p, h, m + 1, 1, 1.0) == capi.ST["invalid_value"]
+    assert lib.set_value(p, h, 1, 0, 1.0) == capi.ST["invalid_value"]
+    assert lib.set_value("s" if p != "s" else "d", h, 1, 1, 1.0) == capi.ST["wrong_type"]
+    x = rng.normal(size=n).astype(dt)
+    for op in (111, 112):
+        y = np.zeros(m, dt)
+        assert lib.mv(p, op, 1.0, h, d, x, 0.0, y) == 0
+        yo = np.zeros(m, dt)
+        oracle.csrmv(op, 1.0, m, n, 1, rp, col, val2, 0, 0, 0, x, 0.0, yo)
+        c_ = dict(m=m, n=n, base=1, type=0, fill=0, diag=0, op=op, alpha=1.0, beta=0.0)
+        assert rel_err(y, yo, mv_denominator(c_, rp, col, val2, x, y)) <= tol
+    lib.destroy_descr(d)
+    lib.destroy(h)
+
+
 def test_concurrent_mv_on_one_handle(lib, oracle):
     """tests/examples/sample_spmv_multi_instance.c:49-88: 4 threads x 10 calls on one handle"""
     rp, col, val = gen_np.stencil(27, 16, 16, 16)
