@@ -104,6 +104,7 @@ class AoclSparse:
         vp, i32, ci = C.c_void_p, C.c_int32, C.c_int
         for p in "sdcz":
             getattr(L, f"aoclsparse_create_{p}csr").argtypes = [C.POINTER(vp), ci, i32, i32, i32, vp, vp, vp]
+            getattr(L, f"aoclsparse_create_{p}csc").argtypes = [C.POINTER(vp), ci, i32, i32, i32, vp, vp, vp]
             getattr(L, f"aoclsparse_{p}mv").argtypes = [ci, vp, vp, vp, vp, vp, vp]
             getattr(L, f"aoclsparse_{p}update_values").argtypes = [vp, i32, vp]
         for p, ct in (("s", C.c_float), ("d", C.c_double), ("c", FloatComplex), ("z", DoubleComplex)):
@@ -177,6 +178,13 @@ class AoclSparse:
         h = C.c_void_p()
         st = getattr(self.lib, f"aoclsparse_create_{prefix}csr")(
             C.byref(h), base, m, n, nnz, ptr(row_ptr), ptr(col_idx), ptr(val))
+        return st, h
+
+    def create_csc(self, prefix, base, m, n, nnz, col_ptr, row_idx, val):
+        """CSC input (m x n matrix given by columns); returns (status, handle)"""
+        h = C.c_void_p()
+        st = getattr(self.lib, f"aoclsparse_create_{prefix}csc")(
+            C.byref(h), base, m, n, nnz, ptr(col_ptr), ptr(row_idx), ptr(val))
         return st, h
 
     def destroy(self, h):

@@ -127,8 +127,17 @@ namespace b200
                                      const aoclsparse_int *col_idx,
                                      const void           *val,
                                      int                   val_type,
-                                     bool                  validate = true)
+                                     bool                  validate = true,
+                                     bool                  csc      = false)
         {
+            // CSC input (aoclsparse_create_csc_t, library/src/extra/aoclsparse_auxiliary.cpp:1030-1089): the arrays
+            // are the CSR of the transpose; they are validated and stored as such (N rows, M columns)
+            const aoclsparse_int M_user = M, N_user = N;
+            if(csc)
+            {
+                M = N_user;
+                N = M_user;
+            }
             if(!mat)
                 return aoclsparse_status_invalid_pointer;
             *mat = nullptr;
@@ -195,8 +204,9 @@ namespace b200
             C->n = N;
             C->nnz = nnz;
             C->doid = b200::DOID_GN;
-            A->m = M;
-            A->n = N;
+            A->m = M_user;
+            A->n = N_user;
+            A->is_csc = csc;
             A->nnz = nnz;
             A->base = base;
             A->val_type = (aoclsparse_matrix_data_type)val_type;
@@ -459,6 +469,23 @@ aoclsparse_status aoclsparse_create_zcsr(aoclsparse_matrix         *mat,
     return create_csr<double2>(mat, base, M, N, nnz, row_ptr, col_idx, val, aoclsparse_zmat);
 }
 
+aoclsparse_status aoclsparse_create_scsc(aoclsparse_matrix *mat, aoclsparse_index_base base, aoclsparse_int M, aoclsparse_int N, aoclsparse_int nnz, aoclsparse_int *col_ptr, aoclsparse_int *row_idx, float *val)
+{
+    return create_csr<float>(mat, base, M, N, nnz, col_ptr, row_idx, val, aoclsparse_smat, true, true);
+}
+aoclsparse_status aoclsparse_create_dcsc(aoclsparse_matrix *mat, aoclsparse_index_base base, aoclsparse_int M, aoclsparse_int N, aoclsparse_int nnz, aoclsparse_int *col_ptr, aoclsparse_int *row_idx, double *val)
+{
+    return create_csr<double>(mat, base, M, N, nnz, col_ptr, row_idx, val, aoclsparse_dmat, true, true);
+}
+aoclsparse_status aoclsparse_create_ccsc(aoclsparse_matrix *mat, aoclsparse_index_base base, aoclsparse_int M, aoclsparse_int N, aoclsparse_int nnz, aoclsparse_int *col_ptr, aoclsparse_int *row_idx, aoclsparse_float_complex *val)
+{
+    return create_csr<float2>(mat, base, M, N, nnz, col_ptr, row_idx, val, aoclsparse_cmat, true, true);
+}
+aoclsparse_status aoclsparse_create_zcsc(aoclsparse_matrix *mat, aoclsparse_index_base base, aoclsparse_int M, aoclsparse_int N, aoclsparse_int nnz, aoclsparse_int *col_ptr, aoclsparse_int *row_idx, aoclsparse_double_complex *val)
+{
+    return create_csr<double2>(mat, base, M, N, nnz, col_ptr, row_idx, val, aoclsparse_zmat, true, true);
+}
+
 aoclsparse_status aoclsparse_destroy(aoclsparse_matrix *mat)
 {
     if(mat && *mat)
@@ -555,7 +582,7 @@ aoclsparse_status aoclsparse_optimize(aoclsparse_matrix A)
         // off by default: both realisations measured slower than the plain kernel on R-MAT scale 24
         // (profiles/r01_summary.md, "hot-column table"); AOCLSPARSE_B200_HOT=1 enables it for experiments
         const bool      want   = e ? atoi(e) != 0 : false;
-        if(want && gn_mv_hint && skewed && A->mem_policy == aoclsparse_memory_usage_unrestricted && A->win_hi < 0
+        if(want && gn_mv_hint && !A->is_csc && skewed && A->mem_policy == aoclsparse_memory_usage_unrestricted && A->win_hi < 0
            && M.plan.hot_entries == 0 && A->row_cuts.empty())
             B200_TRY(build_hot_table(M, value_size(A->val_type), st));
     }
@@ -568,17 +595,19 @@ aoclsparse_status aoclsparse_optimize(aoclsparse_matrix A)
         {
             if(h.done)
                 continue;
-            if((h.act == 1 || h.act == 3) && (h.doid == DOID_GT || h.doid == DOID_GH))
+            // a CSC handle stores the transpose: its plain product is the transposed product of what is stored
+            const int want = A->is_csc ? (h.doid == DOID_GN ? DOID_GT : DOID_LEN) : h.doid;
+            if((h.act == 1 || h.act == 3) && (want == DOID_GT || want == DOID_GH))
             {
                 bool have = false;
                 for(size_t i = 1; i < A->mats.size(); ++i)
-                    have = have || A->mats[i]->doid == h.doid;
+                    have = have || A->mats[i]->doid == want;
                 if(!have)
                 {
                     dev_csr *C = new(std::nothrow) dev_csr;
                     if(!C)
                         return aoclsparse_status_memory_error;
-                    aoclsparse_status s = transpose_csr(M, A->val_type, h.doid == DOID_GH, *C, st);
+                    aoclsparse_status s = transpose_csr(M, A->val_type, want == DOID_GH, *C, st);
                     if(s == aoclsparse_status_success)
                         s = build_plan(*C, value_size(A->val_type), -1, -1, std::vector<aoclsparse_int>(), st);
                     if(s != aoclsparse_status_success)
@@ -586,7 +615,7 @@ aoclsparse_status aoclsparse_optimize(aoclsparse_matrix A)
                         delete C;
                         return s;
                     }
-                    C->doid = h.doid;
+                    C->doid = want;
                     A->mats.push_back(C);
                 }
             }
@@ -694,6 +723,8 @@ aoclsparse_status aoclsparse_b200_set_x_window(aoclsparse_matrix A, aoclsparse_i
 {
     if(!A)
         return aoclsparse_status_invalid_pointer;
+    if(A->is_csc)
+        return aoclsparse_status_not_implemented;
     if(col_lo < 0 || col_hi > A->n || col_lo > col_hi)
         return aoclsparse_status_invalid_size;
     std::unique_lock<std::shared_mutex> wl(A->guard);

@@ -425,6 +425,7 @@ struct _aoclsparse_matrix
     aoclsparse_int                min_col = 0, max_col = -1, max_row_nnz = 0;
     aoclsparse_memory_usage       mem_policy = aoclsparse_memory_usage_unrestricted;
     int                           device     = 0;
+    bool                          is_csc     = false; // created from CSC arrays: mats[0] stores the TRANSPOSE (n x m CSR)
 
     std::vector<b200::hint>       hints; // most recent first, like the reference's linked list
     std::vector<b200::dev_csr *>  mats;  // mats[0] is the user's matrix

@@ -828,12 +828,17 @@ namespace b200
             {
                 const bool cplx    = vt<T>::is_complex;
                 const bool conj_op = cplx && op == aoclsparse_operation_conjugate_transpose;
+                // on the stored matrix (a CSC handle stores the transpose, csrmm.hpp:496-504)
+                const bool trans_s = none == A->is_csc;
                 if(descr->type != aoclsparse_matrix_type_general)
                     status = csrmm_symmetric<T>(op, alpha, A, *descr, order, dB, ldb, beta, dC, ldc, n, st);
-                else if(none)
+                else if(!trans_s)
                 {
                     std::shared_lock<std::shared_mutex> rl(A->guard);
-                    status = launch_mm<T, false>(*A->mats[0], order, dB, ldb, dC, ldc, n, alpha, beta, st);
+                    if(conj_op)
+                        status = launch_mm<T, true>(*A->mats[0], order, dB, ldb, dC, ldc, n, alpha, beta, st);
+                    else
+                        status = launch_mm<T, false>(*A->mats[0], order, dB, ldb, dC, ldc, n, alpha, beta, st);
                 }
                 else
                 {

@@ -232,12 +232,22 @@ namespace b200
     }
 
     aoclsparse_status get_expanded_copy(aoclsparse_matrix            A,
-                                        const _aoclsparse_mat_descr &descr,
+                                        const _aoclsparse_mat_descr &descr_in,
                                         aoclsparse_operation         op,
                                         const dev_csr              *&out,
                                         cudaStream_t                 st)
     {
-        const bool cplx = A->val_type == aoclsparse_cmat || A->val_type == aoclsparse_zmat;
+        const bool            cplx  = A->val_type == aoclsparse_cmat || A->val_type == aoclsparse_zmat;
+        _aoclsparse_mat_descr descr = descr_in;
+        if(A->is_csc)
+        {
+            // the stored arrays are those of A^T: the named triangle sits on the other side, and for a hermitian
+            // matrix A^T = conj(A), i.e. op none <-> op transpose (trans_doid, csrmm.hpp:542-555)
+            descr.fill_mode = descr_in.fill_mode == aoclsparse_fill_mode_lower ? aoclsparse_fill_mode_upper
+                                                                               : aoclsparse_fill_mode_lower;
+            if(cplx && descr.type == aoclsparse_matrix_type_hermitian)
+                op = op == aoclsparse_operation_transpose ? aoclsparse_operation_none : aoclsparse_operation_transpose;
+        }
         const int  d_id = get_doid(cplx, descr.type, descr.fill_mode, op);
         if(d_id < 4 || d_id > 11)
             return aoclsparse_status_invalid_value;

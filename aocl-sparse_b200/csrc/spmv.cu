@@ -308,15 +308,29 @@ namespace b200
             x = x - A->win_lo;
         }
 
+        // what has to be applied to the STORED matrix S: a CSC handle stores S = A^T, so the transposition flips and the
+        // stored triangle is the other one; conjugation is unaffected (op H on a CSC handle = conj(S) without transpose)
         const bool conj_op = cplx && op == aoclsparse_operation_conjugate_transpose;
-        const bool trans   = op != aoclsparse_operation_none;
-        elem_rule  none_rule{MASK_NONE, DIAG_KEEP, 0, 0};
+        bool       trans   = op != aoclsparse_operation_none;
+        int        fill    = descr.fill_mode;
+        if(A->is_csc)
+        {
+            trans = !trans;
+            fill  = fill == aoclsparse_fill_mode_lower ? aoclsparse_fill_mode_upper : aoclsparse_fill_mode_lower;
+        }
+        elem_rule none_rule{MASK_NONE, DIAG_KEEP, 0, 0};
+        const int cj_flag = conj_op ? 1 : 0;
 
         switch(descr.type)
         {
         case aoclsparse_matrix_type_general:
             if(!trans)
-                return launch_gather<T>(M, 0, M.plan.n_blocks, 0, M.m, x, y, alpha, beta, false, none_rule, st);
+            {
+                if(!conj_op)
+                    return launch_gather<T>(M, 0, M.plan.n_blocks, 0, M.m, x, y, alpha, beta, false, none_rule, st);
+                elem_rule r{MASK_NONE, DIAG_KEEP, 1, 1}; // conj(S) x
+                return launch_gather<T>(M, 0, M.plan.n_blocks, 0, M.m, x, y, alpha, beta, true, r, st);
+            }
             else
             {
                 // an explicitly transposed copy built by aoclsparse_optimize turns this into a gather
@@ -327,43 +341,44 @@ namespace b200
                         return launch_gather<T>(C, 0, C.plan.n_blocks, 0, C.m, x, y, alpha, beta, false, none_rule, st);
                 }
                 B200_TRY(scale_vector<T>(y, M.n, beta, alpha, x, 0, st));
-                elem_rule r{MASK_NONE, DIAG_KEEP, conj_op ? 1 : 0, conj_op ? 1 : 0};
+                elem_rule r{MASK_NONE, DIAG_KEEP, cj_flag, cj_flag};
                 return launch_scatter<T>(M, x, y, alpha, r, st);
             }
         case aoclsparse_matrix_type_triangular:
         {
-            const int mask = descr.fill_mode == aoclsparse_fill_mode_lower ? MASK_LOWER : MASK_UPPER;
+            const int mask = fill == aoclsparse_fill_mode_lower ? MASK_LOWER : MASK_UPPER;
             const int dg   = diag_rule(descr.diag_type);
             if(!trans)
             {
-                elem_rule r{mask, dg, 0, 0};
+                elem_rule r{mask, dg, cj_flag, cj_flag};
                 return launch_gather<T>(M, 0, M.plan.n_blocks, 0, M.m, x, y, alpha, beta, true, r, st);
             }
             // y (length n) = beta*y [+ alpha*x on the unit diagonal], then scatter the kept entries
             const long long n_unit = (dg == DIAG_UNIT) ? (M.m < M.n ? M.m : M.n) : 0;
             B200_TRY(scale_vector<T>(y, M.n, beta, alpha, x, n_unit, st));
-            elem_rule r{mask, dg, conj_op ? 1 : 0, conj_op ? 1 : 0};
+            elem_rule r{mask, dg, cj_flag, cj_flag};
             return launch_scatter<T>(M, x, y, alpha, r, st);
         }
         case aoclsparse_matrix_type_symmetric:
         case aoclsparse_matrix_type_hermitian:
         {
             const bool herm = descr.type == aoclsparse_matrix_type_hermitian;
-            const int  mask = descr.fill_mode == aoclsparse_fill_mode_lower ? MASK_LOWER : MASK_UPPER;
+            const int  mask = fill == aoclsparse_fill_mode_lower ? MASK_LOWER : MASK_UPPER;
             const int  dg   = diag_rule(descr.diag_type);
-            // stored triangle T, mirror S:  symmetric S = T^T, hermitian S = T^H.
-            //   symmetric: op none/T -> T + D + T^T            ; op H -> conj of all of it
-            //   hermitian: op none/H -> T + D + conj(T)^T      ; op T -> conj(T) + D + T^T
+            // stored triangle T of S, mirror:  symmetric T^T, hermitian T^H;  F_S = T + D + mirror.
+            //   symmetric: F_A = F_S whether CSR or CSC; op none/T -> F_S ; op H -> conj of all of it
+            //   hermitian: CSR F_A = F_S, CSC F_A = conj(F_S);  op T conjugates once more, op H does nothing
+            //              => conj(T) + D + T^T  when (CSC xor op == T), else T + D + conj(T)^T
             // (D as stored; the reference does not conjugate a hermitian diagonal,
             //  aoclsparse_csrmv_kr.hpp:398-401,422-425, but does conjugate a symmetric one for op H, :217-218)
             int cg, cs, cd;
             if(!herm)
             {
-                cg = cs = cd = conj_op ? 1 : 0;
+                cg = cs = cd = cj_flag;
             }
             else
             {
-                const bool t = cplx && op == aoclsparse_operation_transpose;
+                const bool t = cplx && ((op == aoclsparse_operation_transpose) != A->is_csc);
                 cg           = t ? 1 : 0;
                 cs           = t ? 0 : 1;
                 cd           = 0;
@@ -576,7 +591,9 @@ namespace b200
         // Reference quirk kept for drop-in fidelity: a GENERAL descriptor whose diag_type is unit / zero
         // makes the plain product fail with invalid_pointer (mv.cpp:221-226 calls aoclsparse_set_mat_diag on
         // a matrix that has no diagonal bookkeeping, csr_util.hpp:478-480); transposed products ignore it.
-        if(descr->type == aoclsparse_matrix_type_general && op == aoclsparse_operation_none
+        // (for a CSC handle the stored matrix is the transpose, so it is the TRANSPOSED product that trips it)
+        if(descr->type == aoclsparse_matrix_type_general
+           && op == (A->is_csc ? aoclsparse_operation_transpose : aoclsparse_operation_none)
            && descr->diag_type != aoclsparse_diag_type_non_unit && !(A->m == 0 || A->n == 0 || A->nnz == 0))
             return aoclsparse_status_invalid_pointer;
 
@@ -601,9 +618,24 @@ namespace b200
         const bool x_dev = is_device_accessible(x), y_dev = is_device_accessible(y);
         const bool empty = A->m == 0 || A->n == 0 || (A->nnz == 0 && descr->type == aoclsparse_matrix_type_general);
 
+        // Reference behaviour kept (tests/golden/ref_csc_sweep.json): the conjugate-transposed product of a complex
+        // CSC handle needs conj(S) x without a transposition, which its general / triangular kernels do not provide
+        // (get_effective_doid -> gc; aoclsparse_csrmv.hpp dispatch) -> not_implemented.  mv_device can compute it
+        // (the gather kernel's conjugating element rule); set AOCLSPARSE_B200_CSC_CONJ=1 to get the product instead.
+        if(A->is_csc && vt<T>::is_complex && op == aoclsparse_operation_conjugate_transpose && !empty
+           && (descr->type == aoclsparse_matrix_type_general || descr->type == aoclsparse_matrix_type_triangular))
+        {
+            static const bool allow = [] {
+                const char *e = getenv("AOCLSPARSE_B200_CSC_CONJ");
+                return e && atoi(e) != 0;
+            }();
+            if(!allow)
+                return aoclsparse_status_not_implemented;
+        }
+
         // both vectors on the host, plain general product: chunked pipeline over three streams
         if(!x_dev && !y_dev && !empty && descr->type == aoclsparse_matrix_type_general && op == aoclsparse_operation_none
-           && A->win_hi < 0)
+           && A->win_hi < 0 && !A->is_csc)
         {
             bool              done = false;
             aoclsparse_status ps   = mv_host_pipelined<T>(A, *alpha, x, *beta, y, st, done);
@@ -670,7 +702,7 @@ namespace b200
             return aoclsparse_status_invalid_value;
         if(A->val_type != vt<T>::data_type)
             return aoclsparse_status_wrong_type;
-        if(descr->type != aoclsparse_matrix_type_general)
+        if(descr->type != aoclsparse_matrix_type_general || A->is_csc)
             return aoclsparse_status_not_implemented;
         if(!is_device_accessible(x) || !is_device_accessible(y))
             return aoclsparse_status_invalid_pointer;
@@ -877,6 +909,12 @@ namespace b200
         const aoclsparse_int base = A->base;
         if(A->m + base <= row_idx || row_idx < base || A->n + base <= col_idx || col_idx < base)
             return aoclsparse_status_invalid_value;
+        if(A->is_csc) // the stored arrays are those of the transpose (auxiliary.hpp:444-447)
+        {
+            const aoclsparse_int t = row_idx;
+            row_idx                = col_idx;
+            col_idx                = t;
+        }
         if(A->val_type != vt<T>::data_type)
             return aoclsparse_status_wrong_type;
         cudaStream_t                        st = current_stream();
@@ -1155,6 +1193,8 @@ aoclsparse_status aoclsparse_b200_dmv_sharded_step(const double                 
         return aoclsparse_status_wrong_type;
     if(descr->type != aoclsparse_matrix_type_general || ctl->k == 0)
         return aoclsparse_status_invalid_value;
+    if(A->is_csc)
+        return aoclsparse_status_not_implemented;
     cudaStream_t st = current_stream();
     B200_TRY(ensure_plan(A, st));
     std::shared_lock<std::shared_mutex> rl(A->guard);

@@ -237,6 +237,48 @@ DLL_PUBLIC aoclsparse_status aoclsparse_create_zcsr(aoclsparse_matrix         *m
                                                     aoclsparse_int            *row_ptr,
                                                     aoclsparse_int            *col_idx,
                                                     aoclsparse_double_complex *val);
+
+/* CSC input: the M x N matrix is given by columns (col_ptr of N+1 entries, row_idx, val).  Replaces
+ * aoclsparse_create_?csc (aoclsparse_auxiliary.h:843-917; aoclsparse_create_csc_t,
+ * library/src/extra/aoclsparse_auxiliary.cpp:1030-1089).  As in the reference the arrays are validated
+ * and kept as the CSR of the transpose (N rows, M columns); aoclsparse_?mv (every descriptor type and
+ * operation), aoclsparse_?dotmv, aoclsparse_?csrmm (general / symmetric / hermitian),
+ * aoclsparse_?set_value and aoclsparse_?update_values then work on the handle exactly as on a CSR one
+ * (aoclsparse_mv.cpp:160-200 and aoclsparse_csrmm.hpp:496-555 describe the transposition rules).
+ * B200-only extensions that need the rows of A (x windows, row cuts, ?mv_rows, the sharded step)
+ * return aoclsparse_status_not_implemented for a CSC handle. */
+DLL_PUBLIC aoclsparse_status aoclsparse_create_scsc(aoclsparse_matrix    *mat,
+                                                    aoclsparse_index_base base,
+                                                    aoclsparse_int        M,
+                                                    aoclsparse_int        N,
+                                                    aoclsparse_int        nnz,
+                                                    aoclsparse_int       *col_ptr,
+                                                    aoclsparse_int       *row_idx,
+                                                    float                *val);
+DLL_PUBLIC aoclsparse_status aoclsparse_create_dcsc(aoclsparse_matrix    *mat,
+                                                    aoclsparse_index_base base,
+                                                    aoclsparse_int        M,
+                                                    aoclsparse_int        N,
+                                                    aoclsparse_int        nnz,
+                                                    aoclsparse_int       *col_ptr,
+                                                    aoclsparse_int       *row_idx,
+                                                    double               *val);
+DLL_PUBLIC aoclsparse_status aoclsparse_create_ccsc(aoclsparse_matrix        *mat,
+                                                    aoclsparse_index_base     base,
+                                                    aoclsparse_int            M,
+                                                    aoclsparse_int            N,
+                                                    aoclsparse_int            nnz,
+                                                    aoclsparse_int           *col_ptr,
+                                                    aoclsparse_int           *row_idx,
+                                                    aoclsparse_float_complex *val);
+DLL_PUBLIC aoclsparse_status aoclsparse_create_zcsc(aoclsparse_matrix         *mat,
+                                                    aoclsparse_index_base      base,
+                                                    aoclsparse_int             M,
+                                                    aoclsparse_int             N,
+                                                    aoclsparse_int             nnz,
+                                                    aoclsparse_int            *col_ptr,
+                                                    aoclsparse_int            *row_idx,
+                                                    aoclsparse_double_complex *val);
 DLL_PUBLIC aoclsparse_status aoclsparse_destroy(aoclsparse_matrix *mat);
 
 /* Value refresh keeping the pattern (and the analysis).  Replaces aoclsparse_?update_values

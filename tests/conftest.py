@@ -91,6 +91,24 @@ def effective_dense(m, n, base, rp, col, val, mtype, fill, diag):
     return F
 
 
+def csc_to_csr(m, n, base, cp, ri, val):
+    """0-based CSR arrays of the m x n matrix given by columns (duplicates kept, stable)"""
+    cols = np.repeat(np.arange(n), np.diff(cp))
+    rows = np.asarray(ri) - base
+    order = np.lexsort((np.arange(len(rows)), rows))
+    rp = np.zeros(m + 1, np.int64)
+    np.add.at(rp, rows + 1, 1)
+    return np.cumsum(rp), cols[order], np.asarray(val)[order]
+
+
+def csc_case_scale(c, cp, ri, val):
+    """(op(F), |op(F)|) of a CSC fixture case on the dense effective matrix"""
+    rp, col, v = csc_to_csr(c["m"], c["n"], c["base"], cp, ri, val)
+    mt = 1 if (c["type"] == 2 and not np.iscomplexobj(val)) else c["type"]
+    F = apply_op(effective_dense(c["m"], c["n"], 0, rp, col, v, mt, c["fill"], c["diag"]), c["op"])
+    return F, np.abs(F)
+
+
 def apply_op(F, op):
     return F if op == 111 else (F.T if op == 112 else F.conj().T)
 

@@ -355,6 +355,126 @@ def mm_sweep(rng):
     print("mm sweep:", idx, "cases; statuses", sorted(set(m["status"] for m in meta)))
 
 
+def csc_sweep(rng):
+    """aoclsparse_create_?csc handles through ?mv and ?csrmm on the reference (the reference's own
+    checks are mv_tests.cpp:1361-1457, CSC against CSR of the same matrix).  The fixture arrays are the CSC arrays
+    (cp = column pointers of n+1 entries, ri = row indices); the logical matrix is m x n."""
+    out, meta, defects = {}, [], []
+    idx = 0
+    scal = [(1.0, 0.0), (0.75, -0.5), (-2.0, 1.0)]
+    cscal = [(1.0, 0.0), (1 + 1j, -1 + 2j), (1 - 2j, 0.0)]
+    for kind in ("mv", "mm"):
+        for p in "sdcz":
+            dt = DT[p]
+            cplx = p in "cz"
+            for mtype in ((0, 1, 2, 3) if kind == "mv" else (0, 1, 2)):
+                for op in (111, 112, 113):
+                    for fill in ((0,) if mtype == 0 else (0, 1)):
+                        for diag in ((0,) if mtype == 0 else (0, 1, 2)):
+                            base = idx % 2
+                            sortm = ("full", "partial", "none")[idx % 3]
+                            square = mtype != 0 or idx % 3 == 0
+                            m = int(rng.integers(1, 22))
+                            n = m if square else int(rng.integers(1, 22))
+                            # CSC arrays of the m x n matrix = CSR arrays of its n x m transpose
+                            cp, ri, val = gen_np.random_csr(rng, n, m, 0.3, dt, sortm, ensure_diag=(idx % 4 == 0),
+                                                            base=base)
+                            if mtype == 2 and cplx:
+                                cols = np.repeat(np.arange(n), np.diff(cp))
+                                val[(ri - base) == cols] = val[(ri - base) == cols].real
+                            alpha, beta = (cscal if cplx else scal)[idx % 3]
+                            st, h = REF.create_csc(p, base, m, n, len(ri), cp, ri, val)
+                            assert st == 0, st
+                            d = REF.create_descr(mtype, fill, diag, base)
+                            case = dict(kind=kind, p=p, m=m, n=n, base=base, type=mtype, fill=fill, diag=diag, op=op)
+                            # the logical matrix in CSR form, for the exact product
+                            import scipy.sparse as sp
+                            Acsr = sp.csc_matrix((val, ri - base, cp - base), shape=(m, n))
+                            rows = np.repeat(np.arange(n), np.diff(cp))  # column index of every stored entry
+                            order_ = np.lexsort((np.arange(len(ri)), ri))  # stable by row: keeps duplicates apart
+                            rp2 = np.zeros(m + 1, np.int64)
+                            np.add.at(rp2, (ri - base) + 1, 1)
+                            rp2 = np.cumsum(rp2)
+                            col2, val2 = rows[order_], val[order_]
+                            mt = 1 if (mtype == 2 and not cplx) else mtype
+                            F = apply_op(effective_dense(m, n, 0, rp2, col2, val2, mt, fill, diag), op)
+                            k = f"c{idx}"
+                            if kind == "mv":
+                                xl, yl = (n, m) if op == 111 else (m, n)
+                                x = rng.normal(size=xl).astype(dt)
+                                y0 = rng.normal(size=yl).astype(dt)
+                                if cplx:
+                                    x = (x + 1j * rng.normal(size=xl)).astype(dt)
+                                    y0 = (y0 + 1j * rng.normal(size=yl)).astype(dt)
+                                if beta == 0:
+                                    y0[:] = np.nan
+                                y = y0.copy()
+                                st = REF.mv(p, op, alpha, h, d, x, beta, y)
+                                if st == 0:
+                                    exact = alpha * (F @ x.astype(np.complex128))
+                                    den = np.abs(alpha) * (np.abs(F) @ np.abs(x.astype(np.complex128)))
+                                    if beta != 0:
+                                        exact = exact + beta * y0.astype(np.complex128)
+                                        den = den + np.abs(beta) * np.abs(y0)
+                                    e = rel_err(y, exact, den)
+                                    if e > 100 * TOL[np.dtype(dt)]:
+                                        defects.append(dict(case, sort=sortm, rel_err=e, alpha=str(alpha), beta=str(beta)))
+                                        idx += 1
+                                        REF.destroy_descr(d)
+                                        REF.destroy(h)
+                                        continue
+                                out[k + "_x"], out[k + "_y0"], out[k + "_y"] = x, y0, y
+                                extra = {}
+                            else:
+                                order = idx % 2
+                                nn = int(rng.integers(1, 9)) if idx % 5 else 37
+                                br, cr = (n, m) if op == 111 else (m, n)
+                                pad = idx % 3
+                                ldb = (nn if order == 0 else br) + pad
+                                ldc = (nn if order == 0 else cr) + pad
+                                nb = ldb * (br if order == 0 else nn)
+                                nc = ldc * (cr if order == 0 else nn)
+                                B = rng.normal(size=nb).astype(dt)
+                                C0 = rng.normal(size=nc).astype(dt)
+                                if cplx:
+                                    B = (B + 1j * rng.normal(size=nb)).astype(dt)
+                                    C0 = (C0 + 1j * rng.normal(size=nc)).astype(dt)
+                                Cm = C0.copy()
+                                st = REF.csrmm(p, op, alpha, h, d, order, B, nn, ldb, beta, Cm, ldc)
+                                if st == 0:
+                                    Bm = (B.reshape(br, ldb)[:, :nn] if order == 0 else B.reshape(nn, ldb)[:, :br].T)
+                                    C0m = (C0.reshape(cr, ldc)[:, :nn] if order == 0 else C0.reshape(nn, ldc)[:, :cr].T)
+                                    Cg = (Cm.reshape(cr, ldc)[:, :nn] if order == 0 else Cm.reshape(nn, ldc)[:, :cr].T)
+                                    exact = alpha * (F @ Bm.astype(np.complex128))
+                                    den = np.abs(alpha) * (np.abs(F) @ np.abs(Bm.astype(np.complex128)))
+                                    if beta != 0:
+                                        exact = exact + beta * C0m
+                                        den = den + np.abs(beta) * np.abs(C0m)
+                                    e = rel_err(Cg, exact, den)
+                                    if e > 100 * TOL[np.dtype(dt)]:
+                                        defects.append(dict(case, sort=sortm, order=order, n_rhs=nn, rel_err=e,
+                                                            alpha=str(alpha), beta=str(beta)))
+                                        idx += 1
+                                        REF.destroy_descr(d)
+                                        REF.destroy(h)
+                                        continue
+                                out[k + "_B"], out[k + "_C0"], out[k + "_C"] = B, C0, Cm
+                                extra = dict(order=order, n_rhs=nn, ldb=ldb, ldc=ldc)
+                            REF.destroy_descr(d)
+                            REF.destroy(h)
+                            out[k + "_cp"], out[k + "_ri"], out[k + "_val"] = cp, ri, val
+                            meta.append(dict(key=k, status=int(st), sort=sortm,
+                                             alpha=[complex(alpha).real, complex(alpha).imag],
+                                             beta=[complex(beta).real, complex(beta).imag], **case, **extra))
+                            idx += 1
+    np.savez_compressed(os.path.join(HERE, "ref_csc_sweep.npz"), **out)
+    json.dump(meta, open(os.path.join(HERE, "ref_csc_sweep.json"), "w"), indent=0)
+    json.dump(defects, open(os.path.join(HERE, "ref_csc_defects.json"), "w"), indent=0)
+    from collections import Counter
+    print("csc sweep:", idx, "cases; statuses", Counter((m["kind"], m["status"]) for m in meta),
+          "; reference defects:", len(defects))
+
+
 def create_table(rng):
     """status / sort / fulldiag of the reference's create on valid, unsorted and corrupted inputs"""
     cases = []
@@ -503,6 +623,9 @@ def status_table():
 
 
 if __name__ == "__main__":
+    if "--only-csc" in sys.argv:
+        csc_sweep(np.random.default_rng(69070))
+        sys.exit(0)
     check_kats()
     json.dump(dict(mv=KAT_MV, mm=KAT_MM, create=KAT_CREATE, clean=KAT_CLEAN), open(os.path.join(HERE, "kat.json"), "w"),
               indent=0)
@@ -513,4 +636,5 @@ if __name__ == "__main__":
     clean_table(rng)
     doid_tables()
     status_table()
+    csc_sweep(np.random.default_rng(69070))
     print("golden fixtures written to", HERE)

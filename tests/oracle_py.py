@@ -53,6 +53,8 @@ class Oracle:
             getattr(self.lib, f"oracle_csrmv_{suf}").argtypes = [ci, ct, ci, ci, ci, vp, vp, vp, ci, ci, ci, vp, ct, vp]
             getattr(self.lib, f"oracle_csrmm_{suf}").argtypes = [ci, ct, ci, ci, ci, vp, vp, vp, ci, ci, ci, ci, vp, ci,
                                                                  C.c_longlong, ct, vp, C.c_longlong]
+            getattr(self.lib, f"oracle_cscmv_{suf}").argtypes = [ci, ct, ci, ci, ci, vp, vp, vp, ci, ci, ci, vp, ct, vp, ci]
+            getattr(self.lib, f"oracle_cscmm_{suf}").argtypes = getattr(self.lib, f"oracle_csrmm_{suf}").argtypes
 
     def mat_check(self, m, n, nnz, rp, col, base):
         sort, fd = C.c_int(0), C.c_int(0)
@@ -121,6 +123,19 @@ class Oracle:
         suf = _SUF[val.dtype]
         return getattr(self.lib, f"oracle_csrmm_{suf}")(
             op, _scalar(suf, alpha), m, k, base, rp.ctypes.data, col.ctypes.data, val.ctypes.data, mtype, fill, diag,
+            order, B.ctypes.data, n, ldb, _scalar(suf, beta), Cm.ctypes.data, ldc)
+
+    def cscmv(self, op, alpha, m, n, base, cp, ri, val, mtype, fill, diag, x, beta, y):
+        """the product for a handle made by aoclsparse_create_?csc (m x n, by columns); in-place on y"""
+        suf = _SUF[val.dtype]
+        return getattr(self.lib, f"oracle_cscmv_{suf}")(
+            op, _scalar(suf, alpha), m, n, base, cp.ctypes.data, ri.ctypes.data, val.ctypes.data, mtype, fill, diag,
+            x.ctypes.data, _scalar(suf, beta), y.ctypes.data, 0)
+
+    def cscmm(self, op, alpha, m, k, base, cp, ri, val, mtype, fill, diag, order, B, n, ldb, beta, Cm, ldc):
+        suf = _SUF[val.dtype]
+        return getattr(self.lib, f"oracle_cscmm_{suf}")(
+            op, _scalar(suf, alpha), m, k, base, cp.ctypes.data, ri.ctypes.data, val.ctypes.data, mtype, fill, diag,
             order, B.ctypes.data, n, ldb, _scalar(suf, beta), Cm.ctypes.data, ldc)
 
 

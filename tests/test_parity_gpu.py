@@ -17,7 +17,7 @@ import pytest
 import capi
 import gen_np
 import oracle_py
-from conftest import GOLDEN, TOL, apply_op, effective_dense, mv_denominator, rel_err
+from conftest import GOLDEN, TOL, csc_case_scale, csc_to_csr, apply_op, effective_dense, mv_denominator, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -423,6 +423,181 @@ def test_dotmv_and_set_value(lib, oracle, p):
         assert rel_err(y, yo, mv_denominator(c_, rp, col, val2, x, y)) <= tol
     lib.destroy_descr(d)
     lib.destroy(h)
+
+
+# ------------------------------------------------------------------------------------------------
+# CSC input: aoclsparse_create_?csc handles through ?mv / ?csrmm / ?set_value
+# ------------------------------------------------------------------------------------------------
+def _csc_views(c, B, mats):
+    br, cr = (c["n"], c["m"]) if c["op"] == 111 else (c["m"], c["n"])
+    nn = c["n_rhs"]
+    if c["order"] == 0:
+        return B.reshape(br, c["ldb"])[:, :nn], [M.reshape(cr, c["ldc"])[:, :nn] for M in mats]
+    return B.reshape(nn, c["ldb"])[:, :br].T, [M.reshape(nn, c["ldc"])[:, :cr].T for M in mats]
+
+
+def test_csc_sweep_vs_reference_outputs(lib, oracle):
+    """statuses and outputs of the reference on CSC handles (tests/golden/ref_csc_sweep.*): value type x descriptor type
+    x op x fill x diag x base x sortedness, mv and csrmm, every second case hinted + optimized"""
+    meta = json.load(open(os.path.join(GOLDEN, "ref_csc_sweep.json")))
+    data = np.load(os.path.join(GOLDEN, "ref_csc_sweep.npz"))
+    for i, c in enumerate(meta):
+        k, p = c["key"], c["p"]
+        dt = DT[p]
+        tol = TOL[np.dtype(dt)]
+        cp, ri, val = data[k + "_cp"], data[k + "_ri"], data[k + "_val"]
+        alpha, beta = _scal(c["alpha"], dt), _scal(c["beta"], dt)
+        st, h = lib.create_csc(p, c["base"], c["m"], c["n"], len(ri), cp, ri, val)
+        assert st == 0, (c, st, lib.last_error())
+        d = lib.create_descr(c["type"], c["fill"], c["diag"], c["base"])
+        if i % 2:
+            hint = lib.set_mv_hint if c["kind"] == "mv" else lib.set_mm_hint
+            assert hint(h, c["op"], d, 10) == 0
+            assert lib.optimize(h) == 0, lib.last_error()
+        F, Fa = csc_case_scale(c, cp, ri, val)
+        if c["kind"] == "mv":
+            x, y0, yref = data[k + "_x"], data[k + "_y0"], data[k + "_y"]
+            y = y0.copy()
+            st = lib.mv(p, c["op"], alpha, h, d, x, beta, y)
+            assert st == c["status"], (c, st, lib.last_error())
+            if st == 0:
+                den = abs(_c(c["alpha"])) * (Fa @ np.abs(x))
+                if _c(c["beta"]) != 0:
+                    den = den + np.abs(_c(c["beta"]) * y0)
+                assert rel_err(y, yref, den) <= tol, (c, rel_err(y, yref, den))
+                yo = y0.copy()
+                assert oracle.cscmv(c["op"], alpha, c["m"], c["n"], c["base"], cp, ri, val, c["type"], c["fill"],
+                                    c["diag"], x, beta, yo) == 0
+                assert rel_err(y, yo, den) <= tol, c
+        else:
+            B, C0, Cref = data[k + "_B"], data[k + "_C0"], data[k + "_C"]
+            Cm = C0.copy()
+            st = lib.csrmm(p, c["op"], alpha, h, d, c["order"], B, c["n_rhs"], c["ldb"], beta, Cm, c["ldc"])
+            assert st == c["status"] == 0, (c, st, lib.last_error())
+            Bd, (C0v, Cv, Crefv) = _csc_views(c, B, [C0, Cm, Cref])
+            den = abs(_c(c["alpha"])) * (Fa @ np.abs(Bd))
+            if _c(c["beta"]) != 0:
+                den = den + np.abs(_c(c["beta"]) * C0v)
+            assert rel_err(Cv, Crefv, den) <= tol, (c, rel_err(Cv, Crefv, den))
+            pad = np.ones(Cm.shape, bool)
+            _, (pv,) = _csc_views(c, B, [pad])
+            pv[...] = False
+            assert np.array_equal(Cm[pad], C0[pad], equal_nan=True), c
+        lib.destroy_descr(d)
+        lib.destroy(h)
+
+
+@pytest.mark.parametrize("p", ["d", "z", "s"])
+def test_csc_handle_equals_csr_handle(lib, oracle, p):
+    """the reference's own CSC check (mv_tests.cpp:1361-1457): the CSC and the CSR handle of one matrix give the same
+    product -- at a size where every row strategy and the scatter kernel are exercised -- plus set_value, update_values,
+    the B200 extensions' refusal, and the status quirks of the transposed storage"""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(4242)
+    dt = DT[p]
+    tol = TOL[np.dtype(dt)]
+    cplx = p in "cz"
+    m, n = 3000, 2600
+    rp, col, val = gen_np.random_csr(rng, m, n, 0.004, dt, "full", base=0)
+    A = sp.csr_matrix((val, col, rp), shape=(m, n))
+    Ac = A.tocsc()
+    cp, ri, cv = Ac.indptr.astype(np.int32), Ac.indices.astype(np.int32), Ac.data.astype(dt)
+    st, hc = lib.create_csc(p, 0, m, n, len(ri), cp, ri, cv)
+    assert st == 0, lib.last_error()
+    st, hr = lib.create_csr(p, 0, m, n, len(col), rp, col, val)
+    assert st == 0
+    info = lib.matrix_info(hc)
+    assert (info.m, info.n, info.nnz) == (m, n, len(ri))
+    d = lib.create_descr()
+    for hinted in (False, True):
+        for op in (111, 112, 113):
+            if hinted:
+                assert lib.set_mv_hint(hc, op, d, 100) == 0 and lib.optimize(hc) == 0, lib.last_error()
+            xl, yl = (n, m) if op == 111 else (m, n)
+            x = rng.normal(size=xl).astype(dt)
+            y0 = rng.normal(size=yl).astype(dt)
+            if cplx:
+                x = (x + 1j * rng.normal(size=xl)).astype(dt)
+            yc, yr = y0.copy(), y0.copy()
+            stc = lib.mv(p, op, 0.5, hc, d, x, -2.0, yc)
+            assert lib.mv(p, op, 0.5, hr, d, x, -2.0, yr) == 0
+            if cplx and op == 113:
+                assert stc == capi.ST["not_implemented"]  # reference behaviour, see spmv.cu mv_entry
+                continue
+            assert stc == 0, lib.last_error()
+            Fa = abs(A) if op == 111 else abs(A).T
+            den = 0.5 * (Fa @ np.abs(x)) + 2.0 * np.abs(y0)
+            assert rel_err(yc, yr, den) <= tol, (op, hinted, rel_err(yc, yr, den))
+            yo = y0.copy()
+            assert oracle.cscmv(op, 0.5, m, n, 0, cp, ri, cv, 0, 0, 0, x, -2.0, yo) == 0
+            assert rel_err(yc, yo, den) <= tol
+    # csrmm: C = A B and A^T B through both handles
+    for op in (111, 112, 113):
+        for order in (0, 1):
+            nn = 8
+            br, cr = (n, m) if op == 111 else (m, n)
+            B = rng.normal(size=br * nn).astype(dt)
+            C0 = rng.normal(size=cr * nn).astype(dt)
+            ldb, ldc = (nn, nn) if order == 0 else (br, cr)
+            Cc, Cr = C0.copy(), C0.copy()
+            assert lib.csrmm(p, op, 1.5, hc, d, order, B, nn, ldb, 0.25, Cc, ldc) == 0, lib.last_error()
+            assert lib.csrmm(p, op, 1.5, hr, d, order, B, nn, ldb, 0.25, Cr, ldc) == 0
+            Bd = B.reshape(br, nn) if order == 0 else B.reshape(nn, br).T
+            Fa = abs(A) if op == 111 else abs(A).T
+            den = 1.5 * (Fa @ np.abs(Bd)) + 0.25 * np.abs(C0.reshape(cr, nn) if order == 0 else C0.reshape(nn, cr).T)
+            view = (lambda M: M.reshape(cr, nn)) if order == 0 else (lambda M: M.reshape(nn, cr).T)
+            assert rel_err(view(Cc), view(Cr), den) <= tol, (op, order)
+    # set_value addresses the logical (row, col) (auxiliary.hpp:444-447) and invalidates the transposed copy
+    i, j = int(ri[cp[7]]), 7
+    assert lib.set_value(p, hc, i, j, 9.5) == 0 and lib.set_value(p, hr, i, j, 9.5) == 0
+    x = rng.normal(size=n).astype(dt)
+    yc, yr = np.zeros(m, dt), np.zeros(m, dt)
+    assert lib.mv(p, 111, 1.0, hc, d, x, 0.0, yc) == 0 and lib.mv(p, 111, 1.0, hr, d, x, 0.0, yr) == 0
+    A2 = A.tolil()
+    A2[i, j] = 9.5
+    assert rel_err(yc, yr, abs(A2.tocsr()) @ np.abs(x)) <= tol
+    assert abs(yc[i] - (A2.tocsr() @ x)[i]) <= 100 * tol * (abs(A2.tocsr()) @ np.abs(x))[i]
+    missing = next(r for r in range(m) if r not in ri[cp[7]:cp[8]])
+    assert lib.set_value(p, hc, missing, 7, 1.0) == capi.ST["invalid_index_value"]
+    assert lib.set_value(p, hc, m, 0, 1.0) == capi.ST["invalid_value"]
+    # update_values takes the values in CSC order
+    cv2 = (cv * 2).astype(dt)
+    assert lib.update_values(p, hc, len(cv2), cv2) == 0
+    assert lib.mv(p, 111, 1.0, hc, d, x, 0.0, yc) == 0
+    assert rel_err(yc, (2 * A) @ x, 2 * (abs(A) @ np.abs(x))) <= 10 * tol
+    # status quirk moves with the storage: general + unit diagonal fails on the TRANSPOSED product of a CSC handle
+    du = lib.create_descr(0, 0, 1, 0)
+    xm = rng.normal(size=m).astype(dt)
+    yn = np.zeros(n, dt)
+    assert lib.mv(p, 111, 1.0, hc, du, x, 0.0, yc) == 0
+    assert lib.mv(p, 112, 1.0, hc, du, xm, 0.0, yn) == capi.ST["invalid_pointer"]
+    # extensions that need rows of A refuse a CSC handle
+    assert lib.lib.aoclsparse_b200_set_x_window(hc, 0, n) == capi.ST["not_implemented"]
+    for dd in (d, du):
+        lib.destroy_descr(dd)
+    lib.destroy(hc)
+    lib.destroy(hr)
+
+
+def test_csc_create_validation(lib):
+    """create_?csc validates the arrays as an N x M CSR (auxiliary.cpp:1044-1052): row index bound is M, pointer array
+    has N+1 entries"""
+    cp = np.array([0, 2, 3], np.int32)           # 2 columns
+    ri = np.array([0, 4, 2], np.int32)           # rows < 5
+    v = np.array([1.0, 2.0, 3.0])
+    st, h = lib.create_csc("d", 0, 5, 2, 3, cp, ri, v)
+    assert st == 0
+    x, y = np.array([1.0, 10.0]), np.zeros(5)
+    d = lib.create_descr()
+    assert lib.mv("d", 111, 1.0, h, d, x, 0.0, y) == 0
+    assert np.array_equal(y, [1.0, 0, 30.0, 0, 2.0])
+    lib.destroy(h)
+    assert lib.create_csc("d", 0, 4, 2, 3, cp, ri, v)[0] == capi.ST["invalid_index_value"]  # row 4 out of [0,4)
+    cp4 = np.array([0, 2, 3, 2], np.int32)
+    assert lib.create_csc("d", 0, 5, 3, 3, cp4, ri, v)[0] == capi.ST["invalid_value"]       # cp[N] != nnz
+    assert lib.create_csc("d", 0, 5, 2, 3, None, ri, v)[0] == capi.ST["invalid_pointer"]
+    assert lib.create_csc("d", 0, -1, 2, 3, cp, ri, v)[0] == capi.ST["invalid_size"]
+    lib.destroy_descr(d)
 
 
 def test_concurrent_mv_on_one_handle(lib, oracle):
