@@ -261,6 +261,9 @@ namespace b200
                 delete A->mats[i];
             A->mats.resize(1);
             A->clean = b200::clean_csr();
+            A->mats[0]->grouped.reset(); // rebuilt by the next csrmm call (pattern, hence eligibility, unchanged)
+            if(A->mats[0]->group_k > 0)
+                A->mats[0]->group_k = 0;
             for(auto &h : A->hints)
                 h.done = false;
             return aoclsparse_status_success;
@@ -622,6 +625,12 @@ aoclsparse_status aoclsparse_optimize(aoclsparse_matrix A)
             h.done = true;
         }
     }
+    // row-grouped copy for the row-major csrmm kernel when the hinted product runs on the stored matrix itself
+    for(const hint &h : A->hints)
+        if(h.act == 3 && h.doid == (A->is_csc ? DOID_GT : DOID_GN))
+            A->want_grouped = true;
+    if(A->want_grouped)
+        B200_TRY(ensure_grouped(A, st));
     B200_CUDA(cudaStreamSynchronize(st));
     return aoclsparse_status_success;
 }
@@ -658,6 +667,10 @@ aoclsparse_status aoclsparse_b200_get_matrix_info(const aoclsparse_matrix A, aoc
         info->n_long_segments  = P.n_long_segments;
         info->n_long_rows      = P.n_long_rows;
         info->hot_entries      = P.hot_entries;
+        info->group_k          = A->mats[0]->group_k;
+        info->group_entries    = A->mats[0]->grouped ? A->mats[0]->grouped->nnz : 0;
+        info->group_blocks     = A->mats[0]->grouped ? A->mats[0]->grouped->plan.n_blocks : 0;
+        info->group_block_nnz  = A->mats[0]->grouped ? A->mats[0]->grouped->plan.block_nnz : 0;
         info->hot_mass_ppm     = (aoclsparse_int)(P.hot_mass * 1e6);
     }
     return aoclsparse_status_success;

@@ -16,6 +16,7 @@
 #include <cstring>
 #include <mutex>
 #include <shared_mutex>
+#include <memory>
 #include <vector>
 
 namespace b200
@@ -382,6 +383,10 @@ namespace b200
         int            doid = DOID_GN; // what this copy represents relative to the user's matrix
         dev_buf        row_ptr, col_idx, val;
         row_block_plan plan;
+        // row-grouped copy for csrmm (group.cu): K rows per group, row_ptr = group pointers, col_idx = column | row
+        // mask << 27, val = K values per entry.  group_k: 0 not analysed yet, -1 analysed and not used, else K.
+        std::unique_ptr<dev_csr> grouped;
+        int                      group_k = 0;
     };
 
     // "clean CSR" of the reference's analysis (clean.cu): rows grouped lower | diagonal | upper, diagonals present
@@ -425,6 +430,7 @@ struct _aoclsparse_matrix
     aoclsparse_int                min_col = 0, max_col = -1, max_row_nnz = 0;
     aoclsparse_memory_usage       mem_policy = aoclsparse_memory_usage_unrestricted;
     int                           device     = 0;
+    bool                          want_grouped = false; // a mm hint on the stored matrix was optimized (group.cu)
     bool                          is_csc     = false; // created from CSC arrays: mats[0] stores the TRANSPOSE (n x m CSR)
 
     std::vector<b200::hint>       hints; // most recent first, like the reference's linked list
@@ -471,7 +477,8 @@ namespace b200
                                  aoclsparse_int                     max_row_nnz, // longest row, < 0 if unknown
                                  aoclsparse_int                     forced_strategy,
                                  const std::vector<aoclsparse_int> &row_cuts,
-                                 cudaStream_t                       st);
+                                 cudaStream_t                       st,
+                                 aoclsparse_int                     block_nnz_override = 0);
     void              plan_parameters(size_t          elem_size,
                                       aoclsparse_int  m,
                                       aoclsparse_int  nnz,
@@ -505,6 +512,9 @@ namespace b200
     aoclsparse_status build_hot_table(dev_csr &A, size_t elem_size, cudaStream_t st);
     template <typename T>
     aoclsparse_status launch_hot(const dev_csr &A, const T *x, T *y, T alpha, T beta, cudaStream_t st);
+
+    // group.cu -- row-grouped copy of mats[0] for the row-major csrmm kernel (caller holds the write lock)
+    aoclsparse_status ensure_grouped(aoclsparse_matrix A, cudaStream_t st);
 
     // clean.cu
     aoclsparse_status ensure_clean(aoclsparse_matrix A, cudaStream_t st);

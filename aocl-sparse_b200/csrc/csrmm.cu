@@ -364,6 +364,186 @@ namespace b200
             }
         }
 
+        // the K values of one group entry: one or more 16-byte shared-memory loads (8 bytes for two floats)
+        template <typename T, int K>
+        __device__ __forceinline__ void load_group_vals(const T *p, T (&a)[K])
+        {
+            constexpr int BYTES = K * (int)sizeof(T);
+            if constexpr(BYTES >= 16)
+            {
+                uint4 buf[BYTES / 16];
+#pragma unroll
+                for(int q = 0; q < BYTES / 16; ++q)
+                    buf[q] = reinterpret_cast<const uint4 *>(p)[q];
+                memcpy(a, buf, BYTES);
+            }
+            else
+            {
+                const uint2 b = *reinterpret_cast<const uint2 *>(p);
+                memcpy(a, &b, BYTES);
+            }
+        }
+
+        template <typename T, bool CONJ, int K, int NV>
+        __device__ __forceinline__ void group_entry_fma(int w, const T *sv, const vec16<T> (&x)[NV], const bool (&pv)[NV],
+                                                        vec16<T> (&acc)[K][NV])
+        {
+            constexpr int VEC = vec16<T>::N;
+            T             a[K];
+            load_group_vals<T, K>(sv, a);
+#pragma unroll
+            for(int i = 0; i < K; ++i)
+            {
+                if(w & (1 << (27 + i)))
+                {
+                    const T ai = CONJ ? cj(a[i]) : a[i];
+#pragma unroll
+                    for(int v = 0; v < NV; ++v)
+                        if(pv[v])
+                        {
+#pragma unroll
+                            for(int q = 0; q < VEC; ++q)
+                                acc[i][v].v[q] = mad(ai, x[v].v[q], acc[i][v].v[q]);
+                        }
+                }
+            }
+        }
+
+        // ROW MAJOR on the row-grouped copy (group.cu): K rows of A advance together over the union of their column
+        // indices, so every B row named by the group is loaded ONCE into registers and multiplied into up to K
+        // accumulators.  LPR lanes share one group; each lane owns NV 16-byte vectors of the B / C row.  The group
+        // entries (column | row mask << 27, K values) are staged in shared memory by two TMA bulk copies, as above.
+        template <typename T, bool CONJ, int K, int LPR, int NV>
+        __global__ void __launch_bounds__(MM_THREADS) csrmm_grouped_kernel(const int4 *__restrict__ desc,
+                                                                          int cap,
+                                                                          const aoclsparse_int *__restrict__ gp,
+                                                                          const aoclsparse_int *__restrict__ gcol,
+                                                                          const T *__restrict__ gval,
+                                                                          const T *__restrict__ B,
+                                                                          long long ldb,
+                                                                          T *__restrict__ C,
+                                                                          long long ldc,
+                                                                          int       n,
+                                                                          int       m,
+                                                                          T         alpha,
+                                                                          T         beta,
+                                                                          int       beta_zero)
+        {
+            constexpr int VEC      = vec16<T>::N;
+            constexpr int RPW      = 32 / LPR;       // groups per warp pass
+            constexpr int CPP      = LPR * NV * VEC; // columns of B per pass
+            constexpr int COL_MASK = (1 << 27) - 1;
+            extern __shared__ __align__(16) unsigned char smem_raw[];
+            uint64_t       *bar  = reinterpret_cast<uint64_t *>(smem_raw);
+            T              *sval = reinterpret_cast<T *>(smem_raw + SMEM_HEADER);
+            aoclsparse_int *scol = reinterpret_cast<aoclsparse_int *>(smem_raw + SMEM_HEADER + (size_t)cap * K * sizeof(T));
+
+            const int  tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+            const int  sub = lane / LPR, sl = lane % LPR;
+            const int4 d   = desc[blockIdx.x];
+            const int  ns = d.z, ne = d.w;
+            const int  a   = ns & ~3;
+            const int  cnt = ((ne - a) + 3) & ~3;
+            if(tid == 0)
+            {
+                mbar_init(bar, 1);
+                mbar_init_fence();
+                if(cnt > 0)
+                {
+                    mbar_expect_tx(bar, (unsigned)(cnt * (K * sizeof(T) + sizeof(aoclsparse_int))));
+                    bulk_load_stream(sval, gval + (size_t)a * K, (unsigned)(cnt * K * sizeof(T)), bar);
+                    bulk_load_stream(scol, gcol + a, (unsigned)(cnt * sizeof(aoclsparse_int)), bar);
+                }
+            }
+            __syncthreads();
+            if(cnt > 0)
+                mbar_wait(bar, 0);
+
+            for(int gb = d.x + warp * RPW; gb < d.y; gb += (MM_THREADS / 32) * RPW)
+            {
+                const int  g     = gb + sub;
+                const bool valid = g < d.y;
+                int        s = 0, e = 0;
+                if(valid)
+                {
+                    s = gp[g] - a;
+                    e = gp[g + 1] - a;
+                }
+                for(int c0 = 0; c0 < n; c0 += CPP)
+                {
+                    int  cofs[NV];
+                    bool pv[NV];
+#pragma unroll
+                    for(int v = 0; v < NV; ++v)
+                    {
+                        cofs[v] = c0 + (v * LPR + sl) * VEC;
+                        pv[v]   = cofs[v] < n;
+                    }
+                    vec16<T> acc[K][NV];
+#pragma unroll
+                    for(int i = 0; i < K; ++i)
+#pragma unroll
+                        for(int v = 0; v < NV; ++v)
+#pragma unroll
+                            for(int q = 0; q < VEC; ++q)
+                                acc[i][v].v[q] = vt<T>::zero();
+                    int j = s;
+                    for(; j + 2 <= e; j += 2)
+                    {
+                        const int w0 = scol[j], w1 = scol[j + 1];
+                        const T  *b0 = B + (long long)(w0 & COL_MASK) * ldb;
+                        const T  *b1 = B + (long long)(w1 & COL_MASK) * ldb;
+                        vec16<T>  x0[NV], x1[NV];
+#pragma unroll
+                        for(int v = 0; v < NV; ++v)
+                            if(pv[v])
+                            {
+                                x0[v] = load_vec(b0 + cofs[v]);
+                                x1[v] = load_vec(b1 + cofs[v]);
+                            }
+                        const T *sv = sval + (size_t)j * K;
+                        group_entry_fma<T, CONJ, K, NV>(w0, sv, x0, pv, acc);
+                        group_entry_fma<T, CONJ, K, NV>(w1, sv + K, x1, pv, acc);
+                    }
+                    if(j < e)
+                    {
+                        const int w0 = scol[j];
+                        const T  *b0 = B + (long long)(w0 & COL_MASK) * ldb;
+                        vec16<T>  x0[NV];
+#pragma unroll
+                        for(int v = 0; v < NV; ++v)
+                            if(pv[v])
+                                x0[v] = load_vec(b0 + cofs[v]);
+                        group_entry_fma<T, CONJ, K, NV>(w0, sval + (size_t)j * K, x0, pv, acc);
+                    }
+                    if(valid)
+                    {
+#pragma unroll
+                        for(int i = 0; i < K; ++i)
+                        {
+                            const long long r = (long long)g * K + i;
+                            if(r < m)
+                            {
+                                T *crow = C + r * ldc;
+#pragma unroll
+                                for(int v = 0; v < NV; ++v)
+                                    if(pv[v])
+                                    {
+                                        vec16<T> o;
+                                        if(!beta_zero)
+                                            o = load_vec(crow + cofs[v]);
+#pragma unroll
+                                        for(int q = 0; q < VEC; ++q)
+                                            o.v[q] = axpby_out(alpha, acc[i][v].v[q], beta, beta_zero != 0, &o.v[q]);
+                                        store_vec(crow + cofs[v], o);
+                                    }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+
         // COLUMN MAJOR: B is (k x n) with column stride ldb, C is (m x n) with column stride ldc
         template <typename T, bool CONJ>
         __global__ void __launch_bounds__(MM_THREADS) csrmm_col_major_kernel(const int4 *__restrict__ desc,
@@ -535,6 +715,81 @@ namespace b200
             return aoclsparse_status_success;
         }
 
+        template <typename T, bool CONJ, int K, int LPR, int NV>
+        aoclsparse_status launch_grouped_inst(const dev_csr &G,
+                                              int            m,
+                                              const T       *B,
+                                              long long      ldb,
+                                              T             *C,
+                                              long long      ldc,
+                                              int            n,
+                                              T              alpha,
+                                              T              beta,
+                                              cudaStream_t   st)
+        {
+            const row_block_plan &P    = G.plan;
+            const int             cap  = P.block_nnz + 8;
+            const size_t          smem = SMEM_HEADER + (size_t)cap * (K * sizeof(T) + sizeof(aoclsparse_int));
+            static std::atomic<size_t> cfg{0};
+            if(cfg.load() < smem)
+            {
+                B200_CUDA(cudaFuncSetAttribute(
+                    csrmm_grouped_kernel<T, CONJ, K, LPR, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                cfg.store(smem);
+            }
+            csrmm_grouped_kernel<T, CONJ, K, LPR, NV><<<P.n_blocks, MM_THREADS, smem, st>>>(P.desc.as<int4>(),
+                                                                                         cap,
+                                                                                         G.row_ptr.as<aoclsparse_int>(),
+                                                                                         G.col_idx.as<aoclsparse_int>(),
+                                                                                         G.val.as<T>(),
+                                                                                         B,
+                                                                                         ldb,
+                                                                                         C,
+                                                                                         ldc,
+                                                                                         n,
+                                                                                         m,
+                                                                                         alpha,
+                                                                                         beta,
+                                                                                         is_zero(beta) ? 1 : 0);
+            B200_LAUNCHED();
+            return aoclsparse_status_success;
+        }
+
+        // lanes per group: enough for the whole B row in one pass when it fits a warp
+        template <typename T, bool CONJ, int K>
+        aoclsparse_status launch_grouped(const dev_csr &G,
+                                         int            m,
+                                         const T       *B,
+                                         long long      ldb,
+                                         T             *C,
+                                         long long      ldc,
+                                         int            n,
+                                         T              alpha,
+                                         T              beta,
+                                         cudaStream_t   st)
+        {
+            constexpr int    VEC  = 16 / (int)sizeof(T);
+            const int        vecs = n / VEC;
+            const int        env_nv = getenv("AOCLSPARSE_B200_MM_GROUP_NV") ? atoi(getenv("AOCLSPARSE_B200_MM_GROUP_NV")) : 2;
+            if(env_nv == 1)
+            {
+                if(vecs <= 4)
+                    return launch_grouped_inst<T, CONJ, K, 4, 1>(G, m, B, ldb, C, ldc, n, alpha, beta, st);
+                if(vecs <= 8)
+                    return launch_grouped_inst<T, CONJ, K, 8, 1>(G, m, B, ldb, C, ldc, n, alpha, beta, st);
+                if(vecs <= 16)
+                    return launch_grouped_inst<T, CONJ, K, 16, 1>(G, m, B, ldb, C, ldc, n, alpha, beta, st);
+                return launch_grouped_inst<T, CONJ, K, 32, 1>(G, m, B, ldb, C, ldc, n, alpha, beta, st);
+            }
+            if(vecs <= 8)
+                return launch_grouped_inst<T, CONJ, K, 4, 2>(G, m, B, ldb, C, ldc, n, alpha, beta, st);
+            if(vecs <= 16)
+                return launch_grouped_inst<T, CONJ, K, 8, 2>(G, m, B, ldb, C, ldc, n, alpha, beta, st);
+            if(vecs <= 32)
+                return launch_grouped_inst<T, CONJ, K, 16, 2>(G, m, B, ldb, C, ldc, n, alpha, beta, st);
+            return launch_grouped_inst<T, CONJ, K, 32, 2>(G, m, B, ldb, C, ldc, n, alpha, beta, st);
+        }
+
         template <typename T, bool CONJ>
         aoclsparse_status launch_mm(const dev_csr   &A,
                                     aoclsparse_order order,
@@ -550,6 +805,17 @@ namespace b200
             const row_block_plan &P = A.plan;
             if(P.n_blocks <= 0)
                 return aoclsparse_status_success;
+            {
+                // row-grouped copy (built by aoclsparse_optimize after a mm hint): every B row is read once per K rows
+                constexpr int VEC0 = 16 / (int)sizeof(T);
+                if(A.group_k > 0 && A.grouped && order == aoclsparse_order_row && (n % VEC0) == 0 && (ldb % VEC0) == 0
+                   && (ldc % VEC0) == 0 && ((uintptr_t)B % 16) == 0 && ((uintptr_t)C % 16) == 0 && n >= 2 * VEC0)
+                {
+                    if(A.group_k == 2)
+                        return launch_grouped<T, CONJ, 2>(*A.grouped, A.m, B, ldb, C, ldc, n, alpha, beta, st);
+                    return launch_grouped<T, CONJ, 4>(*A.grouped, A.m, B, ldb, C, ldc, n, alpha, beta, st);
+                }
+            }
             const int    cap  = P.block_nnz + 8;
             const size_t smem = spmv_smem_bytes(sizeof(T), P.block_nnz);
             const int    bz   = is_zero(beta) ? 1 : 0;
@@ -834,7 +1100,24 @@ namespace b200
                     status = csrmm_symmetric<T>(op, alpha, A, *descr, order, dB, ldb, beta, dC, ldc, n, st);
                 else if(!trans_s)
                 {
+                    if(A->want_grouped)
+                    {
+                        // values were replaced since aoclsparse_optimize: rebuild the row-grouped copy
+                        bool missing;
+                        {
+                            std::shared_lock<std::shared_mutex> rl0(A->guard);
+                            missing = A->mats[0]->group_k == 0;
+                        }
+                        if(missing)
+                        {
+                            std::unique_lock<std::shared_mutex> wl(A->guard);
+                            status = ensure_grouped(A, st);
+                        }
+                    }
                     std::shared_lock<std::shared_mutex> rl(A->guard);
+                    if(status != aoclsparse_status_success)
+                        ;
+                    else
                     if(conj_op)
                         status = launch_mm<T, true>(*A->mats[0], order, dB, ldb, dC, ldc, n, alpha, beta, st);
                     else

@@ -282,11 +282,14 @@ namespace b200
                                  aoclsparse_int                     max_row_nnz,
                                  aoclsparse_int                     forced_strategy,
                                  const std::vector<aoclsparse_int> &row_cuts,
-                                 cudaStream_t                       st)
+                                 cudaStream_t                       st,
+                                 aoclsparse_int                     block_nnz_override)
     {
         row_block_plan &P = A.plan;
         P                 = row_block_plan();
         plan_parameters(elem_size, A.m, A.nnz, max_row_nnz, P.block_nnz, P.block_rows);
+        if(block_nnz_override > 0)
+            P.block_nnz = block_nnz_override;
         if(const char *e = getenv("AOCLSPARSE_B200_THREADS"))
         {
             const int v = atoi(e);
@@ -327,7 +330,7 @@ namespace b200
         dev_buf                     d_seg, d_grid, d_cnt;
         aoclsparse_int              T = P.block_nnz;
         const aoclsparse_int        R = P.block_rows;
-        if(wave_search_applies(elem_size, A.nnz, T) && !getenv("AOCLSPARSE_B200_BLOCK_NNZ"))
+        if(block_nnz_override <= 0 && wave_search_applies(elem_size, A.nnz, T) && !getenv("AOCLSPARSE_B200_BLOCK_NNZ"))
         {
             long long      best_cost = -1;
             aoclsparse_int best_T    = T;

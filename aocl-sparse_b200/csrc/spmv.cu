@@ -940,6 +940,9 @@ namespace b200
             delete A->mats[i];
         A->mats.resize(1);
         A->clean = clean_csr();
+        A->mats[0]->grouped.reset();
+        if(A->mats[0]->group_k > 0)
+            A->mats[0]->group_k = 0;
         for(auto &h : A->hints)
             h.done = false;
         return aoclsparse_status_success;

@@ -52,6 +52,10 @@ typedef struct aoclsparse_b200_matrix_info_
     aoclsparse_int n_long_rows;     /* rows split across CTAs                                   */
     aoclsparse_int hot_entries;     /* hot-column table: entries of x kept in shared memory, 0 = not built     */
     aoclsparse_int hot_mass_ppm;    /* stored entries whose column is in that table, parts per million          */
+    aoclsparse_int group_k;         /* row-grouped csrmm copy: rows per group (2 / 4); 0 not analysed, -1 not used */
+    aoclsparse_int group_entries;   /* its entries = sum over groups of the distinct columns in the group       */
+    aoclsparse_int group_blocks;    /* its row blocks                                                           */
+    aoclsparse_int group_block_nnz; /* entries staged per block                                                 */
 } aoclsparse_b200_matrix_info;
 
 DLL_PUBLIC aoclsparse_status aoclsparse_b200_get_matrix_info(const aoclsparse_matrix      A,
