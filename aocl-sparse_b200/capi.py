@@ -132,6 +132,10 @@ class AoclSparse:
         L.aoclsparse_set_mm_hint.argtypes = [vp, ci, vp, i32]
         L.aoclsparse_set_memory_hint.argtypes = [vp, ci]
         L.aoclsparse_spmm.argtypes = [ci, vp, vp, C.POINTER(vp)]
+        L.aoclsparse_sp2m.argtypes = [ci, vp, vp, ci, vp, vp, ci, C.POINTER(vp)]
+        L.aoclsparse_order_mat.argtypes = [vp]
+        for p in "sdcz":
+            getattr(L, f"aoclsparse_export_{p}csr").argtypes = [vp] + [vp] * 7
         if self.is_b200:
             L.aoclsparse_b200_set_stream.argtypes = [vp]
             L.aoclsparse_b200_get_stream.restype = vp
@@ -235,6 +239,31 @@ class AoclSparse:
     def spmm(self, op, a, b):
         c = C.c_void_p()
         return self.lib.aoclsparse_spmm(op, a, b, C.byref(c)), c
+
+    def sp2m(self, opA, dA, a, opB, dB, b, request, c=None):
+        """returns (status, C handle); pass the handle of the nnz_count stage as c for the finalize stage"""
+        c = C.c_void_p() if c is None else c
+        return self.lib.aoclsparse_sp2m(opA, dA, a, opB, dB, b, request, C.byref(c)), c
+
+    def order_mat(self, h):
+        return self.lib.aoclsparse_order_mat(h)
+
+    def export_csr(self, prefix, h):
+        """returns (status, base, m, n, nnz, row_ptr, col_ind, val) with numpy COPIES of the exported arrays"""
+        dt = {"s": np.float32, "d": np.float64, "c": np.complex64, "z": np.complex128}[prefix]
+        base, m, n, nnz = C.c_int(0), C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        rp, ci_, v = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        st = getattr(self.lib, f"aoclsparse_export_{prefix}csr")(
+            h, C.byref(base), C.byref(m), C.byref(n), C.byref(nnz), C.byref(rp), C.byref(ci_), C.byref(v))
+        if st != 0:
+            return st, None, None, None, None, None, None, None
+        def arr(p, count, dtype):
+            if count == 0 or not p.value:
+                return np.zeros(0, dtype)
+            buf = (C.c_char * (count * np.dtype(dtype).itemsize)).from_address(p.value)
+            return np.frombuffer(buf, dtype=dtype).copy()
+        return (st, base.value, m.value, n.value, nnz.value, arr(rp, m.value + 1, np.int32),
+                arr(ci_, nnz.value, np.int32), arr(v, nnz.value, dt))
 
     def version(self):
         return self.lib.aoclsparse_get_version().decode()

@@ -769,15 +769,4 @@ aoclsparse_status aoclsparse_b200_set_row_cuts(aoclsparse_matrix A, aoclsparse_i
     return aoclsparse_status_success;
 }
 
-// aoclsparse_spmm is sparse x sparse in the reference (library/src/level3/aoclsparse_spmm.cpp:27-67);
-// validation as there, computation not provided by this library.
-aoclsparse_status aoclsparse_spmm(aoclsparse_operation opA, const aoclsparse_matrix A, const aoclsparse_matrix B, aoclsparse_matrix *C)
-{
-    (void)opA;
-    if(A == nullptr || B == nullptr || C == nullptr)
-        return aoclsparse_status_invalid_pointer;
-    if(A->val_type != B->val_type)
-        return aoclsparse_status_wrong_type;
-    return aoclsparse_status_not_implemented;
-}
 }

@@ -438,6 +438,9 @@ struct _aoclsparse_matrix
     b200::clean_csr               clean; // built on demand (aoclsparse_b200_get_clean_csr)
     std::vector<aoclsparse_int>   row_cuts;
     aoclsparse_int                win_lo = 0, win_hi = -1; // x window (win_hi < 0: whole vector)
+    // host mirror handed out by aoclsparse_export_?csr (refreshed by every export call, owned by the handle)
+    std::vector<aoclsparse_int>   host_row_ptr, host_col;
+    std::vector<unsigned char>    host_val;
     mutable std::shared_mutex     guard;
 
     ~_aoclsparse_matrix()

@@ -559,17 +559,85 @@ DLL_PUBLIC aoclsparse_status aoclsparse_zcsrmm_kid(aoclsparse_operation         
                                                    const aoclsparse_int             kid);
 
 /* ------------------------------------------------------------------------------------------
- * aoclsparse_spmm (aoclsparse_functions.h:2257-2261; library/src/level3/aoclsparse_spmm.cpp:27-67).
- * In the reference this is sparse x sparse -> NEW sparse CSR (an SpGEMM), not sparse x dense.
- * It is not on the measured path: the symbol is exported with the
- * reference's argument validation (NULL A/B/C -> invalid_pointer, differing value types ->
- * wrong_type) and returns aoclsparse_status_not_implemented for valid input.  It never silently
- * takes csrmm semantics.
+ * Sparse x sparse -> NEW sparse CSR matrix (SpGEMM), SURVEY.md section 8(f) row 4.
+ *
+ * aoclsparse_sp2m  C = op(A) op(B)   (aoclsparse_functions.h:2103-2210; aoclsparse::sp2m<T>,
+ *                                     library/src/level3/aoclsparse_csr2m.cpp:592-860)
+ * aoclsparse_spmm  C = op(A) B       (aoclsparse_functions.h:2212-2261;
+ *                                     library/src/level3/aoclsparse_spmm.cpp:27-67)
+ * A and B are CSR or CSC handles of the same value type, general descriptors only.  request selects
+ * the single-stage product (aoclsparse_stage_full_computation) or the two-stage one: nnz_count
+ * creates *C with its row pointers (column / value arrays allocated, not filled), finalize fills
+ * them and may be repeated after the VALUES of A / B changed.  *C is library-owned (free it with
+ * aoclsparse_destroy), always zero-based.  Validation order and codes follow the reference: NULL
+ * A/B/C -> invalid_pointer; differing value types -> wrong_type; NULL descriptor ->
+ * invalid_pointer; descriptor base != matrix base -> invalid_value; non-general descriptor ->
+ * not_implemented; bad op -> invalid_value; inner dimensions differ -> invalid_size; an empty
+ * operand gives an empty C (success); more than 2^31-1 entries in C -> invalid_size.
+ *
+ * B200: the product is computed on the device with per-row hash tables (csrc/spgemm.cu); the arrays
+ * of *C live in device memory and the handle can be used directly with aoclsparse_?mv /
+ * aoclsparse_?csrmm / aoclsparse_sp2m.  Unlike the reference (first-touch order) the column indices
+ * of every row of C are ascending.  Value sums are accumulated with atomic adds: their rounding may
+ * differ in the last bits between runs.
  * ---------------------------------------------------------------------------------------- */
+DLL_PUBLIC aoclsparse_status aoclsparse_sp2m(aoclsparse_operation       opA,
+                                             const aoclsparse_mat_descr descrA,
+                                             const aoclsparse_matrix    A,
+                                             aoclsparse_operation       opB,
+                                             const aoclsparse_mat_descr descrB,
+                                             const aoclsparse_matrix    B,
+                                             const aoclsparse_request   request,
+                                             aoclsparse_matrix         *C);
 DLL_PUBLIC aoclsparse_status aoclsparse_spmm(aoclsparse_operation    opA,
                                              const aoclsparse_matrix A,
                                              const aoclsparse_matrix B,
                                              aoclsparse_matrix      *C);
+
+/* Read access to the CSR arrays of a handle.  Replaces aoclsparse_export_?csr
+ * (aoclsparse_auxiliary.h:744-820; aoclsparse_export_csr_t, library/src/extra/
+ * aoclsparse_auxiliary.cpp:1303-1350): NULL argument -> invalid_pointer, value type mismatch ->
+ * wrong_type, a handle without CSR arrays (created from CSC) -> invalid_value.  The arrays are in
+ * the handle's own index base, owned by the handle and valid until the next export call on it or
+ * aoclsparse_destroy.  B200: the handle's arrays live on the device, so every call copies them into
+ * a host mirror; aoclsparse_b200_export_device_csr (aoclsparse_b200.h) returns the device arrays. */
+DLL_PUBLIC aoclsparse_status aoclsparse_export_scsr(const aoclsparse_matrix mat,
+                                                    aoclsparse_index_base  *base,
+                                                    aoclsparse_int         *m,
+                                                    aoclsparse_int         *n,
+                                                    aoclsparse_int         *nnz,
+                                                    aoclsparse_int        **row_ptr,
+                                                    aoclsparse_int        **col_ind,
+                                                    float                 **val);
+DLL_PUBLIC aoclsparse_status aoclsparse_export_dcsr(const aoclsparse_matrix mat,
+                                                    aoclsparse_index_base  *base,
+                                                    aoclsparse_int         *m,
+                                                    aoclsparse_int         *n,
+                                                    aoclsparse_int         *nnz,
+                                                    aoclsparse_int        **row_ptr,
+                                                    aoclsparse_int        **col_ind,
+                                                    double                **val);
+DLL_PUBLIC aoclsparse_status aoclsparse_export_ccsr(const aoclsparse_matrix    mat,
+                                                    aoclsparse_index_base     *base,
+                                                    aoclsparse_int            *m,
+                                                    aoclsparse_int            *n,
+                                                    aoclsparse_int            *nnz,
+                                                    aoclsparse_int           **row_ptr,
+                                                    aoclsparse_int           **col_ind,
+                                                    aoclsparse_float_complex **val);
+DLL_PUBLIC aoclsparse_status aoclsparse_export_zcsr(const aoclsparse_matrix     mat,
+                                                    aoclsparse_index_base      *base,
+                                                    aoclsparse_int             *m,
+                                                    aoclsparse_int             *n,
+                                                    aoclsparse_int             *nnz,
+                                                    aoclsparse_int            **row_ptr,
+                                                    aoclsparse_int            **col_ind,
+                                                    aoclsparse_double_complex **val);
+
+/* Ascending column indices inside every row (row indices inside every column for a CSC handle), values
+ * moved along.  Replaces aoclsparse_order_mat (aoclsparse_auxiliary.h:1015-1035; library/src/extra/
+ * aoclsparse_auxiliary.cpp:840-878).  B200: sorts the device copy; the caller's arrays are not touched. */
+DLL_PUBLIC aoclsparse_status aoclsparse_order_mat(aoclsparse_matrix mat);
 
 #ifdef __cplusplus
 }

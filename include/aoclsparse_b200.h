@@ -58,6 +58,17 @@ typedef struct aoclsparse_b200_matrix_info_
     aoclsparse_int group_block_nnz; /* entries staged per block                                                 */
 } aoclsparse_b200_matrix_info;
 
+/* Device view (always zero-based) of a handle's stored arrays -- e.g. the result of aoclsparse_sp2m --
+ * for consumers that stay on the GPU.  For a handle created from CSC arrays these are the arrays of
+ * the transpose (n rows).  Valid until the handle is modified or destroyed. */
+DLL_PUBLIC aoclsparse_status aoclsparse_b200_export_device_csr(const aoclsparse_matrix mat,
+                                                               aoclsparse_int         *m,
+                                                               aoclsparse_int         *n,
+                                                               aoclsparse_int         *nnz,
+                                                               const aoclsparse_int  **row_ptr,
+                                                               const aoclsparse_int  **col_ind,
+                                                               const void            **val);
+
 DLL_PUBLIC aoclsparse_status aoclsparse_b200_get_matrix_info(const aoclsparse_matrix      A,
                                                              aoclsparse_b200_matrix_info *info);
 

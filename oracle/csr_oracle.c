@@ -423,6 +423,40 @@ void oracle_plan_parameters(int elem_size, int m, int nnz, int max_row_nnz, cons
 }
 
 /* ---- multiply kernels, instantiated for the four value types ---- */
+/* Row pointers of C = A B for two CSR operands in the orientation of the product: the number of distinct column
+ * indices reached from every row of A (aoclsparse_csr2m_nnz_count, library/src/level3/aoclsparse_csr2m.cpp:46-305),
+ * then a 64-bit prefix sum.  Returns 0, or 3 (invalid size) when the total does not fit a 32-bit int (:236-241). */
+int oracle_csr2m_count(int m, int n, int baseA, const int *rpA, const int *colA, int baseB, const int *rpB,
+                       const int *colB, int *rpC)
+{
+    int *mark = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+    for(int j = 0; j < n; ++j)
+        mark[j] = -1;
+    long long run = 0;
+    rpC[0]        = 0;
+    for(int i = 0; i < m; ++i)
+    {
+        int cnt = 0;
+        for(int p = rpA[i] - baseA; p < rpA[i + 1] - baseA; ++p)
+        {
+            const int k = colA[p] - baseA;
+            for(int q = rpB[k] - baseB; q < rpB[k + 1] - baseB; ++q)
+            {
+                const int j = colB[q] - baseB;
+                if(mark[j] != i)
+                {
+                    mark[j] = i;
+                    ++cnt;
+                }
+            }
+        }
+        run += cnt;
+        rpC[i + 1] = (int)run;
+    }
+    free(mark);
+    return run > 2147483647LL ? 3 : 0;
+}
+
 #define CAT2(a, b) a##_##b
 #define CAT(a, b) CAT2(a, b)
 #define NAME(f) CAT(f, SUF)

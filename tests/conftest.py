@@ -109,6 +109,33 @@ def csc_case_scale(c, cp, ri, val):
     return F, np.abs(F)
 
 
+def sp2m_operand(fmt, base, shape, ptr, ind, val, op):
+    """op(X) of a sp2m fixture operand as (scipy CSR of X or X^T without conjugation, conj flag)"""
+    import scipy.sparse as sp
+    ctor = sp.csr_matrix if fmt == "csr" else sp.csc_matrix
+    X = ctor((val, np.asarray(ind) - base, np.asarray(ptr) - base), shape=shape)
+    if op != 111:
+        X = X.T
+    X = X.tocsr()
+    X.sort_indices()
+    return X, int(op == 113 and np.iscomplexobj(val))
+
+
+def canonical_rows(rp, col, val):
+    """CSR rows sorted by column (stable): the form sparse products are compared in"""
+    col, val = np.array(col), np.array(val)
+    for i in range(len(rp) - 1):
+        a, b = rp[i], rp[i + 1]
+        o = np.argsort(col[a:b], kind="stable")
+        col[a:b], val[a:b] = col[a:b][o], val[a:b][o]
+    return col, val
+
+
+def sp2m_value_scale(XA, cA, XB, cB):
+    """|op(A)| |op(B)| as a dense array: the denominator of the per-entry error of C"""
+    return (abs(XA) @ abs(XB)).toarray()
+
+
 def apply_op(F, op):
     return F if op == 111 else (F.T if op == 112 else F.conj().T)
 

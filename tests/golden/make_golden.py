@@ -475,6 +475,117 @@ def csc_sweep(rng):
           "; reference defects:", len(defects))
 
 
+def canonical_rows(rp, col, val):
+    """rows sorted by column (stable), the form C is compared in: the reference leaves first-touch order"""
+    col, val = col.copy(), val.copy()
+    for i in range(len(rp) - 1):
+        a, b = rp[i], rp[i + 1]
+        o = np.argsort(col[a:b], kind="stable")
+        col[a:b], val[a:b] = col[a:b][o], val[a:b][o]
+    return col, val
+
+
+def sp2m_sweep(rng):
+    """aoclsparse_sp2m / aoclsparse_spmm on the reference: value type x storage of A and B (CSR /
+    CSC) x opA x opB x bases x single / two-stage; C exported with aoclsparse_export_?csr and stored with the columns
+    of every row ascending.  Also the status codes of the error paths (sp2m_tests.cpp / spmm_tests.cpp:272-345)."""
+    out, meta = {}, []
+    idx = 0
+    for p in "sdcz":
+        dt = DT[p]
+        cplx = p in "cz"
+        for fmtA in ("csr", "csc"):
+            for fmtB in ("csr", "csc"):
+                for opA in (111, 112, 113):
+                    for opB in (111, 112, 113):
+                        baseA, baseB = idx % 2, (idx // 2) % 2
+                        two_stage = idx % 3 == 1
+                        use_spmm = opB == 111 and idx % 4 == 0
+                        m, k, n = (int(rng.integers(1, 26)) for _ in range(3))
+                        if idx % 17 == 5:
+                            k = 0 if idx % 2 else k  # an empty inner dimension now and then
+                        shapeA = (m, k) if opA == 111 else (k, m)
+                        shapeB = (k, n) if opB == 111 else (n, k)
+
+                        def make(shape, fmt, base):
+                            r, c = shape if fmt == "csr" else shape[::-1]
+                            ptr, ind, val = gen_np.random_csr(rng, r, c, 0.25, dt, ("full", "none")[idx % 2], base=base)
+                            create = REF.create_csr if fmt == "csr" else REF.create_csc
+                            st, h = create(p, base, shape[0], shape[1], len(ind), ptr, ind, val)
+                            assert st == 0, st
+                            return h, ptr, ind, val
+                        hA, pA, iA, vA = make(shapeA, fmtA, baseA)
+                        hB, pB, iB, vB = make(shapeB, fmtB, baseB)
+                        dA = REF.create_descr(0, 0, 0, baseA)
+                        dB = REF.create_descr(0, 0, 0, baseB)
+                        if use_spmm:
+                            st, hC = REF.spmm(opA, hA, hB)
+                        elif two_stage:
+                            st, hC = REF.sp2m(opA, dA, hA, opB, dB, hB, 0)
+                            assert st == 0, st
+                            st, hC = REF.sp2m(opA, dA, hA, opB, dB, hB, 1, hC)
+                        else:
+                            st, hC = REF.sp2m(opA, dA, hA, opB, dB, hB, 2)
+                        kk = f"c{idx}"
+                        case = dict(key=kk, p=p, fmtA=fmtA, fmtB=fmtB, opA=opA, opB=opB, baseA=baseA, baseB=baseB, m=m,
+                                    k=k, n=n, two_stage=int(two_stage), spmm=int(use_spmm), status=int(st))
+                        if st == 0:
+                            st2, base, cm, cn, cnnz, rp, col, val = REF.export_csr(p, hC)
+                            assert st2 == 0 and base == 0 and (cm, cn) == (m, n), (st2, base, cm, cn, m, n)
+                            col, val = canonical_rows(rp, col, val)
+                            out[kk + "_Crp"], out[kk + "_Ccol"], out[kk + "_Cval"] = rp, col, val
+                            REF.destroy(hC)
+                        out[kk + "_Ap"], out[kk + "_Ai"], out[kk + "_Av"] = pA, iA, vA
+                        out[kk + "_Bp"], out[kk + "_Bi"], out[kk + "_Bv"] = pB, iB, vB
+                        meta.append(case)
+                        for d in (dA, dB):
+                            REF.destroy_descr(d)
+                        REF.destroy(hA)
+                        REF.destroy(hB)
+                        idx += 1
+    # status codes
+    res = {}
+    rp, col, val = gen_np.random_csr(rng, 6, 5, 0.4, np.float64, "full", base=0)
+    rp1, col1, val1 = gen_np.random_csr(rng, 5, 4, 0.4, np.float64, "full", base=1)
+    _, A = REF.create_csr("d", 0, 6, 5, len(col), rp, col, val)
+    _, B1 = REF.create_csr("d", 1, 5, 4, len(col1), rp1, col1, val1)
+    _, Af = REF.create_csr("s", 0, 6, 5, len(col), rp, col, val.astype(np.float32))
+    d0, d1 = REF.create_descr(0, 0, 0, 0), REF.create_descr(0, 0, 0, 1)
+    dsym = REF.create_descr(1, 0, 0, 0)
+    null = C.c_void_p(None)
+    res["null_A"] = REF.sp2m(111, d0, null, 111, d1, B1, 2)[0]
+    res["null_B"] = REF.sp2m(111, d0, A, 111, d1, null, 2)[0]
+    res["null_descrA"] = REF.sp2m(111, null, A, 111, d1, B1, 2)[0]
+    res["null_descrB"] = REF.sp2m(111, d0, A, 111, null, B1, 2)[0]
+    res["null_C"] = REF.lib.aoclsparse_sp2m(111, d0, A, 111, d1, B1, 2, None)
+    res["wrong_type"] = REF.sp2m(111, d0, Af, 111, d1, B1, 2)[0]
+    res["base_mismatch_A"] = REF.sp2m(111, d1, A, 111, d1, B1, 2)[0]
+    res["base_mismatch_B"] = REF.sp2m(111, d0, A, 111, d0, B1, 2)[0]
+    res["symmetric_descr"] = REF.sp2m(111, dsym, A, 111, d1, B1, 2)[0]
+    res["bad_opA"] = REF.sp2m(110, d0, A, 111, d1, B1, 2)[0]
+    res["bad_opB"] = REF.sp2m(111, d0, A, 114, d1, B1, 2)[0]
+    res["dim_mismatch"] = REF.sp2m(112, d0, A, 111, d1, B1, 2)[0]
+    res["bad_request"] = REF.sp2m(111, d0, A, 111, d1, B1, 7)[0]
+    res["finalize_null_C"] = REF.sp2m(111, d0, A, 111, d1, B1, 1)[0]
+    res["ok_full"] = REF.sp2m(111, d0, A, 111, d1, B1, 2)[0]
+    res["spmm_null_C"] = REF.lib.aoclsparse_spmm(111, A, B1, None)
+    res["spmm_wrong_type"] = REF.spmm(111, Af, B1)[0]
+    res["spmm_dim_mismatch"] = REF.spmm(112, A, B1)[0]
+    res["spmm_ok"] = REF.spmm(111, A, B1)[0]
+    # export
+    _, Acsc = REF.create_csc("d", 0, 5, 6, len(col), rp, col, val)
+    res["export_ok"] = REF.export_csr("d", A)[0]
+    res["export_wrong_type"] = REF.export_csr("s", A)[0]
+    res["export_csc_handle"] = REF.export_csr("d", Acsc)[0]
+    res["export_null"] = REF.lib.aoclsparse_export_dcsr(A, None, None, None, None, None, None, None)
+    res["order_null"] = REF.lib.aoclsparse_order_mat(None)
+    res["order_ok"] = REF.order_mat(A)
+    np.savez_compressed(os.path.join(HERE, "ref_sp2m_sweep.npz"), **out)
+    json.dump(dict(cases=meta, status=res), open(os.path.join(HERE, "ref_sp2m_sweep.json"), "w"), indent=0)
+    from collections import Counter
+    print("sp2m sweep:", idx, "cases; statuses", Counter(c["status"] for c in meta), "; status table", res)
+
+
 def create_table(rng):
     """status / sort / fulldiag of the reference's create on valid, unsorted and corrupted inputs"""
     cases = []
@@ -626,6 +737,9 @@ if __name__ == "__main__":
     if "--only-csc" in sys.argv:
         csc_sweep(np.random.default_rng(69070))
         sys.exit(0)
+    if "--only-sp2m" in sys.argv:
+        sp2m_sweep(np.random.default_rng(69071))
+        sys.exit(0)
     check_kats()
     json.dump(dict(mv=KAT_MV, mm=KAT_MM, create=KAT_CREATE, clean=KAT_CLEAN), open(os.path.join(HERE, "kat.json"), "w"),
               indent=0)
@@ -637,4 +751,5 @@ if __name__ == "__main__":
     doid_tables()
     status_table()
     csc_sweep(np.random.default_rng(69070))
+    sp2m_sweep(np.random.default_rng(69071))
     print("golden fixtures written to", HERE)

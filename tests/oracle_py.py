@@ -47,12 +47,15 @@ class Oracle:
         vp, ci = C.c_void_p, C.c_int
         self.lib.oracle_mat_check.argtypes = [ci, ci, ci, vp, vp, vp, ci, C.POINTER(ci), C.POINTER(ci)]
         self.lib.oracle_doid.argtypes = [ci, ci, ci, ci]
+        self.lib.oracle_csr2m_count.argtypes = [ci, ci, ci, vp, vp, ci, vp, vp, vp]
         self.lib.oracle_plan.argtypes = [ci, vp, ci, ci, ci, ci, vp, ci, vp, vp, C.POINTER(ci), C.POINTER(ci)]
         self.lib.oracle_plan_parameters.argtypes = [ci, ci, ci, ci, vp, ci, vp, C.POINTER(ci), C.POINTER(ci)]
         for suf, ct in (("s", C.c_float), ("d", C.c_double), ("c", FC), ("z", DC)):
             getattr(self.lib, f"oracle_csrmv_{suf}").argtypes = [ci, ct, ci, ci, ci, vp, vp, vp, ci, ci, ci, vp, ct, vp]
             getattr(self.lib, f"oracle_csrmm_{suf}").argtypes = [ci, ct, ci, ci, ci, vp, vp, vp, ci, ci, ci, ci, vp, ci,
                                                                  C.c_longlong, ct, vp, C.c_longlong]
+            getattr(self.lib, f"oracle_csr2m_fill_{suf}").argtypes = [ci, ci, ci, vp, vp, vp, ci, ci, vp, vp, vp, ci, vp,
+                                                                      vp, vp]
             getattr(self.lib, f"oracle_cscmv_{suf}").argtypes = [ci, ct, ci, ci, ci, vp, vp, vp, ci, ci, ci, vp, ct, vp, ci]
             getattr(self.lib, f"oracle_cscmm_{suf}").argtypes = getattr(self.lib, f"oracle_csrmm_{suf}").argtypes
 
@@ -137,6 +140,24 @@ class Oracle:
         return getattr(self.lib, f"oracle_cscmm_{suf}")(
             op, _scalar(suf, alpha), m, k, base, cp.ctypes.data, ri.ctypes.data, val.ctypes.data, mtype, fill, diag,
             order, B.ctypes.data, n, ldb, _scalar(suf, beta), Cm.ctypes.data, ldc)
+
+    def csr2m(self, m, n, baseA, rpA, colA, valA, conjA, baseB, rpB, colB, valB, conjB):
+        """C = A B for CSR operands in the orientation of the product; returns (status, rpC, colC, valC), zero-based,
+        columns in first-touch order"""
+        suf = _SUF[valA.dtype]
+        rpA, colA, rpB, colB = (np.ascontiguousarray(a, dtype=np.int32) for a in (rpA, colA, rpB, colB))
+        valA, valB = np.ascontiguousarray(valA), np.ascontiguousarray(valB)
+        rpC = np.zeros(m + 1, np.int32)
+        rc = self.lib.oracle_csr2m_count(m, n, baseA, rpA.ctypes.data, colA.ctypes.data, baseB, rpB.ctypes.data,
+                                         colB.ctypes.data, rpC.ctypes.data)
+        if rc:
+            return rc, rpC, None, None
+        colC = np.zeros(max(int(rpC[m]), 1), np.int32)
+        valC = np.zeros(max(int(rpC[m]), 1), valA.dtype)
+        rc = getattr(self.lib, f"oracle_csr2m_fill_{suf}")(
+            m, n, baseA, rpA.ctypes.data, colA.ctypes.data, valA.ctypes.data, int(conjA), baseB, rpB.ctypes.data,
+            colB.ctypes.data, valB.ctypes.data, int(conjB), rpC.ctypes.data, colC.ctypes.data, valC.ctypes.data)
+        return rc, rpC, colC[:rpC[m]], valC[:rpC[m]]
 
 
 def row_scale(rp, col, val, x, base=0, beta=0.0, y0=None):
