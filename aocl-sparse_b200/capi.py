@@ -136,6 +136,7 @@ class AoclSparse:
         L.aoclsparse_order_mat.argtypes = [vp]
         for p in "sdcz":
             getattr(L, f"aoclsparse_export_{p}csr").argtypes = [vp] + [vp] * 7
+            getattr(L, f"aoclsparse_{p}csr2csc").argtypes = [i32, i32, i32, vp, ci, vp, vp, vp, vp, vp, vp]
         if self.is_b200:
             L.aoclsparse_b200_set_stream.argtypes = [vp]
             L.aoclsparse_b200_get_stream.restype = vp
@@ -244,6 +245,10 @@ class AoclSparse:
         """returns (status, C handle); pass the handle of the nnz_count stage as c for the finalize stage"""
         c = C.c_void_p() if c is None else c
         return self.lib.aoclsparse_sp2m(opA, dA, a, opB, dB, b, request, C.byref(c)), c
+
+    def csr2csc(self, prefix, m, n, nnz, descr, base_csc, rp, col, val, row_ind, col_ptr, csc_val):
+        return getattr(self.lib, f"aoclsparse_{prefix}csr2csc")(
+            m, n, nnz, descr, base_csc, ptr(rp), ptr(col), ptr(val), ptr(row_ind), ptr(col_ptr), ptr(csc_val))
 
     def order_mat(self, h):
         return self.lib.aoclsparse_order_mat(h)

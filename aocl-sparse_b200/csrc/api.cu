@@ -700,6 +700,11 @@ aoclsparse_status aoclsparse_b200_get_plan(const aoclsparse_matrix A,
     return aoclsparse_status_success;
 }
 
+int aoclsparse_b200_value_type(const aoclsparse_matrix A)
+{
+    return A ? (int)A->val_type : -1;
+}
+
 int aoclsparse_b200_doid(const aoclsparse_mat_descr descr, aoclsparse_operation op, int val_type)
 {
     if(!descr)

@@ -157,3 +157,102 @@ namespace b200
         return aoclsparse_status_success;
     }
 }
+
+// ------------------------------------------------------------------------------------------------
+// aoclsparse_?csr2csc (aoclsparse_convert.h:430-530; aoclsparse_csr2csc_template, library/src/conversion/
+// aoclsparse_convert.hpp:553-660): array-level CSR -> CSC conversion.  Input and output arrays may be host or device
+// memory; the work is the device transposition above (stable: row indices ascend inside every column and repeated
+// entries keep their order, as the reference's counting sort does).
+// ------------------------------------------------------------------------------------------------
+namespace b200
+{
+    namespace
+    {
+        __global__ void add_const_kernel(long long n, int *v, int c)
+        {
+            long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+            for(; i < n; i += (long long)gridDim.x * blockDim.x)
+                v[i] += c;
+        }
+
+        template <typename T>
+        aoclsparse_status csr2csc_t(aoclsparse_int             m,
+                                    aoclsparse_int             n,
+                                    aoclsparse_int             nnz,
+                                    const aoclsparse_mat_descr descr,
+                                    aoclsparse_index_base      baseCSC,
+                                    const aoclsparse_int      *csr_row_ptr,
+                                    const aoclsparse_int      *csr_col_ind,
+                                    const T                   *csr_val,
+                                    aoclsparse_int            *csc_row_ind,
+                                    aoclsparse_int            *csc_col_ptr,
+                                    T                         *csc_val,
+                                    int                        val_type)
+        {
+            if(descr == nullptr)
+                return aoclsparse_status_invalid_pointer;
+            if(m < 0 || n < 0 || nnz < 0)
+                return aoclsparse_status_invalid_size;
+            cudaStream_t st = current_stream();
+            if(m == 0 || n == 0 || nnz == 0)
+            {
+                if(csc_col_ptr == nullptr)
+                    return aoclsparse_status_invalid_pointer; // (the reference writes through it unchecked)
+                std::vector<aoclsparse_int> fill((size_t)n + 1, (aoclsparse_int)baseCSC);
+                B200_CUDA(cudaMemcpyAsync(csc_col_ptr, fill.data(), sizeof(aoclsparse_int) * ((size_t)n + 1), cudaMemcpyDefault, st));
+                B200_CUDA(cudaStreamSynchronize(st));
+                return aoclsparse_status_success;
+            }
+            const aoclsparse_index_base baseCSR = descr->base;
+            if((baseCSR != aoclsparse_index_base_zero && baseCSR != aoclsparse_index_base_one)
+               || (baseCSC != aoclsparse_index_base_zero && baseCSC != aoclsparse_index_base_one))
+                return aoclsparse_status_invalid_value;
+            if(!csr_val || !csr_row_ptr || !csr_col_ind || !csc_val || !csc_row_ind || !csc_col_ptr)
+                return aoclsparse_status_invalid_pointer;
+            dev_csr A, Tr;
+            A.m   = m;
+            A.n   = n;
+            A.nnz = nnz;
+            B200_TRY(A.row_ptr.alloc(sizeof(int) * ((size_t)m + 1)));
+            B200_TRY(A.col_idx.alloc(sizeof(int) * (size_t)nnz));
+            B200_TRY(A.val.alloc(sizeof(T) * (size_t)nnz));
+            B200_CUDA(cudaMemcpyAsync(A.row_ptr.p, csr_row_ptr, sizeof(int) * ((size_t)m + 1), cudaMemcpyDefault, st));
+            B200_CUDA(cudaMemcpyAsync(A.col_idx.p, csr_col_ind, sizeof(int) * (size_t)nnz, cudaMemcpyDefault, st));
+            B200_CUDA(cudaMemcpyAsync(A.val.p, csr_val, sizeof(T) * (size_t)nnz, cudaMemcpyDefault, st));
+            if(baseCSR == aoclsparse_index_base_one)
+                B200_TRY(rebase_to_zero(m, nnz, A.row_ptr.as<aoclsparse_int>(), A.col_idx.as<aoclsparse_int>(), st));
+            B200_TRY(transpose_csr(A, val_type, false, Tr, st));
+            if(baseCSC == aoclsparse_index_base_one)
+            {
+                add_const_kernel<<<grid_for((long long)n + 1, 256), 256, 0, st>>>((long long)n + 1, Tr.row_ptr.as<int>(), 1);
+                B200_LAUNCHED();
+                add_const_kernel<<<grid_for(nnz, 256), 256, 0, st>>>(nnz, Tr.col_idx.as<int>(), 1);
+                B200_LAUNCHED();
+            }
+            B200_CUDA(cudaMemcpyAsync(csc_col_ptr, Tr.row_ptr.p, sizeof(int) * ((size_t)n + 1), cudaMemcpyDefault, st));
+            B200_CUDA(cudaMemcpyAsync(csc_row_ind, Tr.col_idx.p, sizeof(int) * (size_t)nnz, cudaMemcpyDefault, st));
+            B200_CUDA(cudaMemcpyAsync(csc_val, Tr.val.p, sizeof(T) * (size_t)nnz, cudaMemcpyDefault, st));
+            B200_CUDA(cudaStreamSynchronize(st));
+            return aoclsparse_status_success;
+        }
+    }
+}
+
+extern "C" {
+aoclsparse_status aoclsparse_scsr2csc(aoclsparse_int m, aoclsparse_int n, aoclsparse_int nnz, const aoclsparse_mat_descr descr, aoclsparse_index_base baseCSC, const aoclsparse_int *csr_row_ptr, const aoclsparse_int *csr_col_ind, const float *csr_val, aoclsparse_int *csc_row_ind, aoclsparse_int *csc_col_ptr, float *csc_val)
+{
+    return b200::csr2csc_t<float>(m, n, nnz, descr, baseCSC, csr_row_ptr, csr_col_ind, csr_val, csc_row_ind, csc_col_ptr, csc_val, aoclsparse_smat);
+}
+aoclsparse_status aoclsparse_dcsr2csc(aoclsparse_int m, aoclsparse_int n, aoclsparse_int nnz, const aoclsparse_mat_descr descr, aoclsparse_index_base baseCSC, const aoclsparse_int *csr_row_ptr, const aoclsparse_int *csr_col_ind, const double *csr_val, aoclsparse_int *csc_row_ind, aoclsparse_int *csc_col_ptr, double *csc_val)
+{
+    return b200::csr2csc_t<double>(m, n, nnz, descr, baseCSC, csr_row_ptr, csr_col_ind, csr_val, csc_row_ind, csc_col_ptr, csc_val, aoclsparse_dmat);
+}
+aoclsparse_status aoclsparse_ccsr2csc(aoclsparse_int m, aoclsparse_int n, aoclsparse_int nnz, const aoclsparse_mat_descr descr, aoclsparse_index_base baseCSC, const aoclsparse_int *csr_row_ptr, const aoclsparse_int *csr_col_ind, const aoclsparse_float_complex *csr_val, aoclsparse_int *csc_row_ind, aoclsparse_int *csc_col_ptr, aoclsparse_float_complex *csc_val)
+{
+    return b200::csr2csc_t<float2>(m, n, nnz, descr, baseCSC, csr_row_ptr, csr_col_ind, reinterpret_cast<const float2 *>(csr_val), csc_row_ind, csc_col_ptr, reinterpret_cast<float2 *>(csc_val), aoclsparse_cmat);
+}
+aoclsparse_status aoclsparse_zcsr2csc(aoclsparse_int m, aoclsparse_int n, aoclsparse_int nnz, const aoclsparse_mat_descr descr, aoclsparse_index_base baseCSC, const aoclsparse_int *csr_row_ptr, const aoclsparse_int *csr_col_ind, const aoclsparse_double_complex *csr_val, aoclsparse_int *csc_row_ind, aoclsparse_int *csc_col_ptr, aoclsparse_double_complex *csc_val)
+{
+    return b200::csr2csc_t<double2>(m, n, nnz, descr, baseCSC, csr_row_ptr, csr_col_ind, reinterpret_cast<const double2 *>(csr_val), csc_row_ind, csc_col_ptr, reinterpret_cast<double2 *>(csc_val), aoclsparse_zmat);
+}
+}

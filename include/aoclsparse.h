@@ -634,6 +634,57 @@ DLL_PUBLIC aoclsparse_status aoclsparse_export_zcsr(const aoclsparse_matrix     
                                                     aoclsparse_int            **col_ind,
                                                     aoclsparse_double_complex **val);
 
+/* Array-level CSR -> CSC conversion.  Replaces aoclsparse_?csr2csc (aoclsparse_convert.h:430-530;
+ * aoclsparse_csr2csc_template, library/src/conversion/aoclsparse_convert.hpp:553-660): only the index
+ * base of descr is used; NULL descr -> invalid_pointer, negative sizes -> invalid_size, an empty matrix
+ * fills csc_col_ptr with baseCSC, bad bases -> invalid_value, NULL arrays -> invalid_pointer.  Row
+ * indices ascend inside every column; repeated entries keep their order.  B200: the conversion runs on
+ * the device (csrc/transpose.cu); every array may be host or device memory. */
+DLL_PUBLIC aoclsparse_status aoclsparse_scsr2csc(aoclsparse_int             m,
+                                                 aoclsparse_int             n,
+                                                 aoclsparse_int             nnz,
+                                                 const aoclsparse_mat_descr descr,
+                                                 aoclsparse_index_base      baseCSC,
+                                                 const aoclsparse_int      *csr_row_ptr,
+                                                 const aoclsparse_int      *csr_col_ind,
+                                                 const float *csr_val,
+                                                 aoclsparse_int            *csc_row_ind,
+                                                 aoclsparse_int            *csc_col_ptr,
+                                                 float *csc_val);
+DLL_PUBLIC aoclsparse_status aoclsparse_dcsr2csc(aoclsparse_int             m,
+                                                 aoclsparse_int             n,
+                                                 aoclsparse_int             nnz,
+                                                 const aoclsparse_mat_descr descr,
+                                                 aoclsparse_index_base      baseCSC,
+                                                 const aoclsparse_int      *csr_row_ptr,
+                                                 const aoclsparse_int      *csr_col_ind,
+                                                 const double *csr_val,
+                                                 aoclsparse_int            *csc_row_ind,
+                                                 aoclsparse_int            *csc_col_ptr,
+                                                 double *csc_val);
+DLL_PUBLIC aoclsparse_status aoclsparse_ccsr2csc(aoclsparse_int             m,
+                                                 aoclsparse_int             n,
+                                                 aoclsparse_int             nnz,
+                                                 const aoclsparse_mat_descr descr,
+                                                 aoclsparse_index_base      baseCSC,
+                                                 const aoclsparse_int      *csr_row_ptr,
+                                                 const aoclsparse_int      *csr_col_ind,
+                                                 const aoclsparse_float_complex *csr_val,
+                                                 aoclsparse_int            *csc_row_ind,
+                                                 aoclsparse_int            *csc_col_ptr,
+                                                 aoclsparse_float_complex *csc_val);
+DLL_PUBLIC aoclsparse_status aoclsparse_zcsr2csc(aoclsparse_int             m,
+                                                 aoclsparse_int             n,
+                                                 aoclsparse_int             nnz,
+                                                 const aoclsparse_mat_descr descr,
+                                                 aoclsparse_index_base      baseCSC,
+                                                 const aoclsparse_int      *csr_row_ptr,
+                                                 const aoclsparse_int      *csr_col_ind,
+                                                 const aoclsparse_double_complex *csr_val,
+                                                 aoclsparse_int            *csc_row_ind,
+                                                 aoclsparse_int            *csc_col_ptr,
+                                                 aoclsparse_double_complex *csc_val);
+
 /* Ascending column indices inside every row (row indices inside every column for a CSC handle), values
  * moved along.  Replaces aoclsparse_order_mat (aoclsparse_auxiliary.h:1015-1035; library/src/extra/
  * aoclsparse_auxiliary.cpp:840-878).  B200: sorts the device copy; the caller's arrays are not touched. */

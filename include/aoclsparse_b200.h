@@ -58,6 +58,9 @@ typedef struct aoclsparse_b200_matrix_info_
     aoclsparse_int group_block_nnz; /* entries staged per block                                                 */
 } aoclsparse_b200_matrix_info;
 
+/* value type of a handle (aoclsparse_matrix_data_type), -1 for NULL */
+DLL_PUBLIC int aoclsparse_b200_value_type(const aoclsparse_matrix A);
+
 /* Device view (always zero-based) of a handle's stored arrays -- e.g. the result of aoclsparse_sp2m --
  * for consumers that stay on the GPU.  For a handle created from CSC arrays these are the arrays of
  * the transpose (n rows).  Valid until the handle is modified or destroyed. */

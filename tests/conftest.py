@@ -121,6 +121,16 @@ def sp2m_operand(fmt, base, shape, ptr, ind, val, op):
     return X, int(op == 113 and np.iscomplexobj(val))
 
 
+def csr2csc_numpy(m, n, base_csr, base_csc, rp, col, val):
+    """stable counting-sort transposition (aoclsparse_csr2csc_template, conversion/aoclsparse_convert.hpp:553-660)"""
+    rp0, col0 = np.asarray(rp) - base_csr, np.asarray(col) - base_csr
+    rows = np.repeat(np.arange(m), np.diff(rp0))
+    order = np.argsort(col0, kind="stable")
+    cp = np.zeros(n + 1, np.int32)
+    np.add.at(cp, col0 + 1, 1)
+    return (np.cumsum(cp) + base_csc).astype(np.int32), (rows[order] + base_csc).astype(np.int32), np.asarray(val)[order]
+
+
 def canonical_rows(rp, col, val):
     """CSR rows sorted by column (stable): the form sparse products are compared in"""
     col, val = np.array(col), np.array(val)

@@ -110,3 +110,27 @@ def test_doid_table_bit_exact(lib):
         lib.destroy_descr(d)
     for mat, req, want in tab["effective_doid"]:
         assert lib.lib.aoclsparse_b200_effective_doid(mat, req) == want, (mat, req)
+
+
+def test_cxx_template_instantiations_are_exported(lib):
+    """aoclsparse::mv<T>, create_csr<T>, sp2m<T> (aoclsparse.hpp:85-147) under the reference's mangled names
+    (tests/golden/cxx_symbols.json, read from the reference's own build)"""
+    names = json.load(open(os.path.join(GOLDEN, "cxx_symbols.json")))
+    assert len(names) == 12
+    missing = [n for n in names if not hasattr(lib.lib, n)]
+    assert not missing, missing
+
+
+def test_cxx_caller_links_and_validates(tmp_path):
+    """a C++ caller of the reference's aoclsparse.hpp front ends compiles against include/aoclsparse.hpp, links against
+    the library and gets the reference's status for NULL handles (no device work)"""
+    import shutil
+    import subprocess
+    cxx = shutil.which("g++") or "/usr/bin/g++"
+    exe = str(tmp_path / "cxx_link_check")
+    libdir = os.path.dirname(capi.LIB_PATH)
+    subprocess.run([cxx, "-std=c++17", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cxx_link_check.cpp"),
+                    "-L", libdir, "-laoclsparse_b200", f"-Wl,-rpath,{libdir}", "-o", exe], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.split() == ["2", "2", "2", "2"]

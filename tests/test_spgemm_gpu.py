@@ -15,7 +15,7 @@ import scipy.sparse as sp
 
 import capi
 import gen_np
-from conftest import GOLDEN, TOL, canonical_rows, rel_err, sp2m_operand, sp2m_value_scale
+from conftest import GOLDEN, TOL, csr2csc_numpy, canonical_rows, rel_err, sp2m_operand, sp2m_value_scale
 
 pytestmark = pytest.mark.gpu
 
@@ -253,3 +253,44 @@ def test_export_and_order_mat(lib):
             assert rel_err(y, Aref @ x, abs(Aref) @ np.abs(x)) <= 4 * TOL[np.dtype(dt)]
             lib.destroy_descr(d)
             lib.destroy(h)
+
+
+def test_csr2csc_arrays(lib):
+    """aoclsparse_?csr2csc against the counting-sort restatement (pinned on the reference in
+    tests/test_oracle.py::test_live_reference_csr2csc): host and device arrays, all base pairs, empty matrix, statuses"""
+    import torch
+    rng = np.random.default_rng(22)
+    ST = capi.ST
+    for p in "sdcz":
+        dt = DT[p]
+        for b_in in (0, 1):
+            for b_out in (0, 1):
+                m, n = 2300, 1700
+                rp, col, val = gen_np.random_csr(rng, m, n, 0.01, dt, "none", base=b_in)
+                d = lib.create_descr(base=b_in)
+                ri, cp, cv = np.zeros(len(col), np.int32), np.zeros(n + 1, np.int32), np.zeros(len(col), dt)
+                assert lib.csr2csc(p, m, n, len(col), d, b_out, rp, col, val, ri, cp, cv) == 0, lib.last_error()
+                wcp, wri, wv = csr2csc_numpy(m, n, b_in, b_out, rp, col, val)
+                assert np.array_equal(cp, wcp) and np.array_equal(ri, wri) and np.array_equal(cv, wv)
+                lib.destroy_descr(d)
+    # device arrays in, device arrays out
+    m, n = 500, 400
+    rp, col, val = gen_np.random_csr(rng, m, n, 0.05, np.float64, "full", base=0)
+    d = lib.create_descr()
+    drp, dcol, dval = (torch.from_numpy(a).cuda() for a in (rp, col, val))
+    ori = torch.zeros(len(col), dtype=torch.int32, device="cuda")
+    ocp = torch.zeros(n + 1, dtype=torch.int32, device="cuda")
+    ov = torch.zeros(len(col), dtype=torch.float64, device="cuda")
+    assert lib.csr2csc("d", m, n, len(col), d, 0, drp.data_ptr(), dcol.data_ptr(), dval.data_ptr(), ori.data_ptr(),
+                       ocp.data_ptr(), ov.data_ptr()) == 0
+    wcp, wri, wv = csr2csc_numpy(m, n, 0, 0, rp, col, val)
+    assert np.array_equal(ocp.cpu().numpy(), wcp) and np.array_equal(ori.cpu().numpy(), wri)
+    assert np.array_equal(ov.cpu().numpy(), wv)
+    cp = np.full(6, -7, np.int32)
+    z, zi = np.zeros(1), np.zeros(1, np.int32)
+    assert lib.csr2csc("d", 0, 5, 0, d, 1, zi, zi, z, zi, cp, z) == 0 and np.array_equal(cp, np.ones(6))
+    assert lib.csr2csc("d", -1, 5, 0, d, 0, zi, zi, z, zi, cp, z) == ST["invalid_size"]
+    assert lib.csr2csc("d", 1, 1, 1, None, 0, zi, zi, z, zi, cp, z) == ST["invalid_pointer"]
+    assert lib.csr2csc("d", 1, 1, 1, d, 0, zi, zi, None, zi, cp, z) == ST["invalid_pointer"]
+    assert lib.csr2csc("d", 1, 1, 1, d, 3, zi, zi, z, zi, cp, z) == ST["invalid_value"]
+    lib.destroy_descr(d)
