@@ -281,8 +281,10 @@ def test_status_codes_match_reference(lib):
     got["update_ok"] = L.update_values("d", A, 8, val)
     for k, v in got.items():
         assert v == want[k], (k, v, want[k])
-    # spmm on valid input: exported, validated, not provided (sparse x sparse)
-    assert L.spmm(111, A, A)[0] == capi.ST["not_implemented"]
+    # spmm on valid input is the sparse x sparse product (tests/test_spgemm_gpu.py)
+    st_c, hC = L.spmm(111, A, A)
+    assert st_c == 0 and L.matrix_info(hC).m == 5
+    L.destroy(hC)
     # kernel id outside the available strategies (mv_tests.cpp:295-301)
     assert L.set_mv_hint_kid(A, 111, d0, 10, 7) == 0
     assert L.mv("d", 111, 1.0, A, d0, x, 0.0, y) == capi.ST["invalid_kid"]
