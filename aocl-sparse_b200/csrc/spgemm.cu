@@ -24,15 +24,51 @@
 #include <cub/device/device_segmented_sort.cuh>
 
 #include <algorithm>
+#include <chrono>
 
 namespace b200
 {
     namespace
     {
+        // AOCLSPARSE_B200_SPGEMM_TRACE=1: per-phase wall times (stream-synchronised) on stderr, for profiles/
+        struct phase_trace
+        {
+            bool                                           on;
+            cudaStream_t                                   st;
+            std::chrono::time_point<std::chrono::steady_clock> t0;
+            explicit phase_trace(cudaStream_t s)
+                : on(getenv("AOCLSPARSE_B200_SPGEMM_TRACE") && atoi(getenv("AOCLSPARSE_B200_SPGEMM_TRACE")) != 0)
+                , st(s)
+            {
+                if(on)
+                {
+                    cudaStreamSynchronize(st);
+                    t0 = std::chrono::steady_clock::now();
+                }
+            }
+            void mark(const char *what)
+            {
+                if(!on)
+                    return;
+                cudaStreamSynchronize(st);
+                const auto t1 = std::chrono::steady_clock::now();
+                fprintf(stderr, "[spgemm] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+                t0 = t1;
+            }
+        };
+
         constexpr int TIER_NONE = 0, TIER_WARP = 1, TIER_CTA_S = 2, TIER_CTA_L = 3, TIER_GLOBAL = 4, N_TIERS = 5;
         constexpr int TAB_WARP = 128, UB_WARP = 96;
         constexpr int TAB_S = 1024, UB_S = 768, THREADS_S = 128;
-        constexpr int TAB_L = 8192, UB_L = 6144, THREADS_L = 256;
+        constexpr int THREADS_L = 256;
+        // large CTA tier: 8192 slots for values of up to 8 bytes, 4096 for 16-byte values (shared memory budget)
+        template <typename T>
+        struct large_tier
+        {
+            static constexpr int TAB = sizeof(T) > 8 ? 4096 : 8192;
+            static constexpr int UB  = TAB / 4 * 3;
+        };
+        constexpr int RANK_LIMIT = 1024; // rows up to this length are ordered by counting ranks, longer ones bitonically
         constexpr int THREADS_W = 128; // four rows per CTA in the warp tier
 
         __device__ __forceinline__ unsigned first_slot(int key, unsigned mask)
@@ -94,6 +130,7 @@ namespace b200
                                             const int *__restrict__ rpA,
                                             const int *__restrict__ colA,
                                             const int *__restrict__ rpB,
+                                            int ub_large,
                                             int *__restrict__ ub,
                                             unsigned char *__restrict__ tier,
                                             int *__restrict__ hist)
@@ -112,7 +149,7 @@ namespace b200
                     s += rpB[c + 1] - rpB[c];
                 }
                 const int t = s == 0 ? TIER_NONE
-                                     : (s <= UB_WARP ? TIER_WARP : (s <= UB_S ? TIER_CTA_S : (s <= UB_L ? TIER_CTA_L : TIER_GLOBAL)));
+                                     : (s <= UB_WARP ? TIER_WARP : (s <= UB_S ? TIER_CTA_S : (s <= ub_large ? TIER_CTA_L : TIER_GLOBAL)));
                 ub[i]   = s > 0x7fffffffLL ? 0x7fffffff : (int)s;
                 tier[i] = (unsigned char)t;
                 atomicAdd(&h[t], 1);
@@ -261,30 +298,107 @@ namespace b200
                 return;
             }
             if(GLOBAL)
-                __threadfence(); // global table written by other threads of the CTA
-            group_sync<TPR>();
-            if(live)
             {
-                const int base = rpC[i], len = rpC[i + 1] - base;
-                for(int s = lane; s < size; s += TPR)
+                // global tables: compact in slot order; these (few, long) rows are ordered afterwards by a segmented sort
+                __threadfence();
+                group_sync<TPR>();
+                if(live)
                 {
-                    const int key = keys[s];
-                    if(key != -1)
+                    const int base = rpC[i], len = rpC[i + 1] - base;
+                    for(int s = lane; s < size; s += TPR)
                     {
-                        const int p = atomicAdd(&counter[gl], 1);
-                        if(p < len)
+                        const int key = keys[s];
+                        if(key != -1)
                         {
-                            colC[base + p] = key;
-                            valC[base + p] = vals[s];
+                            const int p = atomicAdd(&counter[gl], 1);
+                            if(p < len)
+                            {
+                                colC[base + p] = key;
+                                valC[base + p] = vals[s];
+                            }
                         }
                     }
+                    group_sync<TPR>();
+                    if(lane == 0 && counter[gl] != len)
+                        atomicExch(err, 1); // the pattern changed between the two stages (csr2m.cpp:521-522)
                 }
-                group_sync<TPR>();
-                if(lane == 0 && counter[gl] != len)
-                    atomicExch(err, 1); // the pattern changed between the two stages (csr2m.cpp:521-522)
+                else
+                    group_sync<TPR>();
+                return;
+            }
+            // shared-memory tables: compact (key, slot) pairs, then write the row in ascending column order
+            int            *ckey  = reinterpret_cast<int *>(smem_raw + (size_t)GROUPS * TABLE * (sizeof(int) + sizeof(T))) + gl * TABLE;
+            unsigned short *cslot = reinterpret_cast<unsigned short *>(smem_raw + (size_t)GROUPS * TABLE * (2 * sizeof(int) + sizeof(T)))
+                                    + gl * TABLE;
+            group_sync<TPR>();
+            for(int s = lane; s < TABLE; s += TPR)
+            {
+                const int key = keys[s];
+                if(key != -1)
+                {
+                    const int p = atomicAdd(&counter[gl], 1);
+                    ckey[p]     = key;
+                    cslot[p]    = (unsigned short)s;
+                }
+            }
+            group_sync<TPR>();
+            const int L    = counter[gl];
+            const int base = live ? rpC[i] : 0;
+            const int len  = live ? rpC[i + 1] - base : 0;
+            if(live && lane == 0 && L != len)
+                atomicExch(err, 1); // the pattern changed between the two stages (csr2m.cpp:521-522)
+            if(L != len)
+                return; // uniform over the group
+            if(L <= RANK_LIMIT)
+            {
+                // distinct keys: the rank of a key is the number of smaller ones
+                for(int e = lane; e < L; e += TPR)
+                {
+                    const int k    = ckey[e];
+                    int       rank = 0;
+                    for(int f = 0; f < L; ++f)
+                        rank += ckey[f] < k ? 1 : 0;
+                    colC[base + rank] = k;
+                    valC[base + rank] = vals[cslot[e]];
+                }
             }
             else
+            {
+                // bitonic sort of the pairs, padded with +inf keys to a power of two (<= TABLE)
+                int P = 1;
+                while(P < L)
+                    P <<= 1;
+                for(int e = L + lane; e < P; e += TPR)
+                    ckey[e] = 0x7fffffff;
                 group_sync<TPR>();
+                for(int k2 = 2; k2 <= P; k2 <<= 1)
+                    for(int j = k2 >> 1; j > 0; j >>= 1)
+                    {
+                        for(int e = lane; e < P; e += TPR)
+                        {
+                            const int x = e ^ j;
+                            if(x > e)
+                            {
+                                const int  ka = ckey[e], kb = ckey[x];
+                                const bool up = (e & k2) == 0;
+                                if((ka > kb) == up)
+                                {
+                                    ckey[e]                 = kb;
+                                    ckey[x]                 = ka;
+                                    const unsigned short sa = cslot[e];
+                                    cslot[e]                = cslot[x];
+                                    cslot[x]                = sa;
+                                }
+                            }
+                        }
+                        group_sync<TPR>();
+                    }
+                for(int e = lane; e < L; e += TPR)
+                {
+                    colC[base + e] = ckey[e];
+                    valC[base + e] = vals[cslot[e]];
+                }
+            }
         }
 
         __global__ void sum64_kernel(int m, const int *__restrict__ v, unsigned long long *out)
@@ -351,7 +465,7 @@ namespace b200
             int     start[N_TIERS] = {0, 0, 0, 0, 0};
         };
 
-        aoclsparse_status make_tiers(const dev_csr &A, const dev_csr &B, tier_lists &L, cudaStream_t st)
+        aoclsparse_status make_tiers(const dev_csr &A, const dev_csr &B, int ub_large, tier_lists &L, cudaStream_t st)
         {
             const int m = A.m;
             dev_buf   hist;
@@ -364,7 +478,7 @@ namespace b200
             if(m > 0)
             {
                 spgemm_bound_kernel<<<grid, 256, 0, st>>>(
-                    m, A.row_ptr.as<int>(), A.col_idx.as<int>(), B.row_ptr.as<int>(), L.ub.as<int>(),
+                    m, A.row_ptr.as<int>(), A.col_idx.as<int>(), B.row_ptr.as<int>(), ub_large, L.ub.as<int>(),
                     L.tier.as<unsigned char>(), hist.as<int>());
                 B200_LAUNCHED();
             }
@@ -395,7 +509,9 @@ namespace b200
                 return aoclsparse_status_success;
             constexpr int THREADS = TPR == 32 ? THREADS_W : TPR;
             constexpr int GROUPS  = THREADS / TPR;
-            const size_t  smem    = (size_t)GROUPS * TABLE * (sizeof(int) + (NUMERIC ? sizeof(T) : 0));
+            // keys [+ values + compacted keys + compacted slot ids]
+            const size_t  smem    = (size_t)GROUPS * TABLE
+                                 * (sizeof(int) + (NUMERIC ? sizeof(T) + sizeof(int) + sizeof(unsigned short) : 0));
             auto          kern    = spgemm_row_kernel<T, TPR, TABLE, NUMERIC, false>;
             if(smem > 48 * 1024)
                 B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -501,7 +617,7 @@ namespace b200
                 rows + L.start[TIER_WARP], L.count[TIER_WARP], A, B, conjA, conjB, nnz_row, rpC, colC, valC, err, st)));
             B200_TRY((launch_smem_tier<T, THREADS_S, TAB_S, NUMERIC>(
                 rows + L.start[TIER_CTA_S], L.count[TIER_CTA_S], A, B, conjA, conjB, nnz_row, rpC, colC, valC, err, st)));
-            B200_TRY((launch_smem_tier<T, THREADS_L, TAB_L, NUMERIC>(
+            B200_TRY((launch_smem_tier<T, THREADS_L, large_tier<T>::TAB, NUMERIC>(
                 rows + L.start[TIER_CTA_L], L.count[TIER_CTA_L], A, B, conjA, conjB, nnz_row, rpC, colC, valC, err, st)));
             const int ng = L.count[TIER_GLOBAL];
             if(ng > 0)
@@ -520,19 +636,21 @@ namespace b200
 
         // pass 1: P.row_ptr (m+1, exclusive scan of the row lengths), P.nnz; col / val allocated, not filled
         template <typename T>
-        aoclsparse_status symbolic(const dev_csr &A, const dev_csr &B, dev_csr &P, cudaStream_t st)
+        aoclsparse_status symbolic(const dev_csr &A, const dev_csr &B, dev_csr &P, tier_lists &L, cudaStream_t st)
         {
             const int m = A.m;
             P.m         = m;
             P.n         = B.n;
-            tier_lists L;
-            B200_TRY(make_tiers(A, B, L, st));
+            phase_trace tr(st);
+            B200_TRY(make_tiers(A, B, large_tier<T>::UB, L, st));
+            tr.mark("count: bounds + tiers");
             dev_buf nnz_row, total, temp;
             B200_TRY(nnz_row.alloc(sizeof(int) * ((size_t)m + 1)));
             B200_TRY(total.alloc(sizeof(unsigned long long)));
             B200_CUDA(cudaMemsetAsync(nnz_row.p, 0, sizeof(int) * ((size_t)m + 1), st));
             B200_CUDA(cudaMemsetAsync(total.p, 0, sizeof(unsigned long long), st));
             B200_TRY((run_tiers<T, false>(A, B, 0, 0, L, nnz_row.as<int>(), nullptr, nullptr, nullptr, nullptr, st)));
+            tr.mark("count: hash kernels");
             sum64_kernel<<<blocks_for(m, 256), 256, 0, st>>>(m, nnz_row.as<int>(), total.as<unsigned long long>());
             B200_LAUNCHED();
             unsigned long long h_total = 0;
@@ -550,6 +668,7 @@ namespace b200
             B200_TRY(P.col_idx.alloc(sizeof(int) * (size_t)P.nnz));
             B200_TRY(P.val.alloc(sizeof(T) * (size_t)P.nnz));
             B200_CUDA(cudaStreamSynchronize(st));
+            tr.mark("count: scan + allocate C");
             return aoclsparse_status_success;
         }
 
@@ -599,15 +718,89 @@ namespace b200
             return aoclsparse_status_success;
         }
 
+        __global__ void segment_bounds_kernel(int n, const int *__restrict__ rows, const int *__restrict__ rp,
+                                              int *__restrict__ beg, int *__restrict__ end)
+        {
+            const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+            if(g < n)
+            {
+                beg[g] = rp[rows[g]];
+                end[g] = rp[rows[g] + 1];
+            }
+        }
+
+        // one CTA per listed row: phase 0 gathers the permuted values into vtmp, phase 1 copies keys / values back
+        template <typename T>
+        __global__ void segment_apply_kernel(const int *__restrict__ beg, const int *__restrict__ end, int phase,
+                                             const int *__restrict__ col_sorted, const int *__restrict__ perm,
+                                             int *__restrict__ col, T *__restrict__ val, T *__restrict__ vtmp)
+        {
+            const int b = beg[blockIdx.x], e = end[blockIdx.x];
+            for(int p = b + threadIdx.x; p < e; p += blockDim.x)
+            {
+                if(phase == 0)
+                    vtmp[p] = val[perm[p]];
+                else
+                {
+                    col[p] = col_sorted[p];
+                    val[p] = vtmp[p];
+                }
+            }
+        }
+
+        // ascending column order for the listed rows only (the rows of the global-table tier)
+        template <typename T>
+        aoclsparse_status sort_row_subset(const int *rows, int n_rows, long long nnz, const int *rp, dev_buf &col, dev_buf &val,
+                                          cudaStream_t st)
+        {
+            if(n_rows <= 0 || nnz <= 0)
+                return aoclsparse_status_success;
+            dev_buf beg, end, col_out, idx_in, idx_out, vtmp, temp;
+            B200_TRY(beg.alloc(sizeof(int) * (size_t)n_rows));
+            B200_TRY(end.alloc(sizeof(int) * (size_t)n_rows));
+            B200_TRY(col_out.alloc(sizeof(int) * (size_t)nnz));
+            B200_TRY(idx_in.alloc(sizeof(int) * (size_t)nnz));
+            B200_TRY(idx_out.alloc(sizeof(int) * (size_t)nnz));
+            B200_TRY(vtmp.alloc(sizeof(T) * (size_t)nnz));
+            segment_bounds_kernel<<<(unsigned)((n_rows + 255) / 256), 256, 0, st>>>(n_rows, rows, rp, beg.as<int>(), end.as<int>());
+            B200_LAUNCHED();
+            iota_int_kernel<<<blocks_for(nnz, 256), 256, 0, st>>>(nnz, idx_in.as<int>());
+            B200_LAUNCHED();
+            size_t temp_bytes = 0;
+            B200_CUDA(cub::DeviceSegmentedSort::StableSortPairs(nullptr, temp_bytes, col.as<int>(), col_out.as<int>(),
+                                                                idx_in.as<int>(), idx_out.as<int>(), (int)nnz, n_rows,
+                                                                beg.as<int>(), end.as<int>(), st));
+            B200_TRY(temp.alloc(temp_bytes));
+            B200_CUDA(cub::DeviceSegmentedSort::StableSortPairs(temp.p, temp_bytes, col.as<int>(), col_out.as<int>(),
+                                                                idx_in.as<int>(), idx_out.as<int>(), (int)nnz, n_rows,
+                                                                beg.as<int>(), end.as<int>(), st));
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            for(int phase = 0; phase < 2; ++phase)
+            {
+                segment_apply_kernel<T><<<(unsigned)n_rows, 256, 0, st>>>(beg.as<int>(), end.as<int>(), phase, col_out.as<int>(),
+                                                                         idx_out.as<int>(), col.as<int>(), val.as<T>(), vtmp.as<T>());
+                B200_LAUNCHED();
+            }
+            B200_CUDA(cudaStreamSynchronize(st));
+            return aoclsparse_status_success;
+        }
+
         // pass 2: fills P.col_idx / P.val for the row_ptr of pass 1; rows sorted by column
         template <typename T>
-        aoclsparse_status numeric(const dev_csr &A, const dev_csr &B, int conjA, int conjB, dev_csr &P, cudaStream_t st)
+        aoclsparse_status numeric(const dev_csr &A, const dev_csr &B, int conjA, int conjB, dev_csr &P, tier_lists *have,
+                                  cudaStream_t st)
         {
             const int m = A.m;
             if(P.nnz == 0 || m == 0)
                 return aoclsparse_status_success;
-            tier_lists L;
-            B200_TRY(make_tiers(A, B, L, st));
+            phase_trace tr(st);
+            tier_lists  own;
+            if(!have) // the finalize stage on its own: the tiers depend on the patterns only, recompute them
+            {
+                B200_TRY(make_tiers(A, B, large_tier<T>::UB, own, st));
+                tr.mark("fill: bounds + tiers");
+            }
+            tier_lists &L = have ? *have : own;
             dev_buf nnz_row, err;
             B200_TRY(err.alloc(sizeof(int)));
             B200_CUDA(cudaMemsetAsync(err.p, 0, sizeof(int), st));
@@ -621,7 +814,12 @@ namespace b200
             B200_CUDA(cudaStreamSynchronize(st));
             if(h_err)
                 return aoclsparse_status_internal_error;
-            return sort_rows<T>(m, P.nnz, P.row_ptr.as<int>(), P.col_idx, P.val, st);
+            tr.mark("fill: hash kernels");
+            // the shared-memory tiers wrote their rows in order; only the global-table rows are still in slot order
+            const aoclsparse_status ss = sort_row_subset<T>(L.rows.as<int>() + L.start[TIER_GLOBAL], L.count[TIER_GLOBAL], P.nnz,
+                                                            P.row_ptr.as<int>(), P.col_idx, P.val, st);
+            tr.mark("fill: order global-tier rows");
+            return ss;
         }
 
         // a general handle around device arrays that are already in place (base 0)
@@ -787,6 +985,8 @@ namespace b200
             }
 
             // ---- stages
+            tier_lists tiers;
+            bool       have_tiers = false;
             if(request == aoclsparse_stage_finalize)
             {
                 if(*C == nullptr || (*C)->mats.empty() || !(*C)->mats[0])
@@ -798,7 +998,8 @@ namespace b200
             {
                 B200_TRY(new_result_handle(C, vt<T>::data_type, m_a, n_b));
                 dev_csr          *P = opflag == 3 ? new(std::nothrow) dev_csr : (*C)->mats[0];
-                aoclsparse_status s = P ? symbolic<T>(*L.M, *R.M, *P, st) : aoclsparse_status_memory_error;
+                aoclsparse_status s = P ? symbolic<T>(*L.M, *R.M, *P, tiers, st) : aoclsparse_status_memory_error;
+                have_tiers          = s == aoclsparse_status_success;
                 if(s == aoclsparse_status_success && opflag == 3)
                 {
                     // the product is kept beside the result until it is finalized; the result's own arrays are sized now
@@ -835,7 +1036,7 @@ namespace b200
                 if(H->mats.size() < 2 || H->mats[1]->doid != DOID_GT)
                     return aoclsparse_status_invalid_pointer;
                 dev_csr &P = *H->mats[1];
-                B200_TRY(numeric<T>(*L.M, *R.M, L.conj, R.conj, P, st));
+                B200_TRY(numeric<T>(*L.M, *R.M, L.conj, R.conj, P, have_tiers ? &tiers : nullptr, st));
                 dev_csr Tr;
                 B200_TRY(transpose_csr(P, H->val_type, false, Tr, st));
                 dev_csr &M = *H->mats[0];
@@ -849,10 +1050,12 @@ namespace b200
                 dev_csr &M = *H->mats[0];
                 if(M.m != L.M->m || M.n != R.M->n || !M.row_ptr.p)
                     return aoclsparse_status_invalid_pointer;
-                B200_TRY(numeric<T>(*L.M, *R.M, L.conj, R.conj, M, st));
+                B200_TRY(numeric<T>(*L.M, *R.M, L.conj, R.conj, M, have_tiers ? &tiers : nullptr, st));
             }
+            phase_trace tr(st);
             B200_TRY(finish_handle(H, true, st));
             B200_CUDA(cudaStreamSynchronize(st));
+            tr.mark("classify result (check.cu)");
             return aoclsparse_status_success;
         }
 

@@ -182,6 +182,9 @@ def test_sp2m_every_table_tier(lib, oracle, p):
     A = rnd((700, 900), 0.06, 1)   # ~54 per row x ~60 per row of B = ~3200 products
     B = rnd((900, 1100), 0.055, 2)
     _check_product(lib, oracle, p, A, B, "random: large CTA tier")
+    A = rnd((200, 1500), 0.04, 5)   # ~60 x ~99 = ~5900 products, ~3500 distinct columns per row: large CTA tier with the
+    B = rnd((1500, 6000), 0.0165, 6)  # bitonic ordering (rows longer than 1024), some rows spilling to global tables
+    _check_product(lib, oracle, p, A, B, "random: large CTA tier, long rows")
     A = rnd((300, 2000), 0.1, 3)   # 200 x 150 = 30000 products per row: global tables
     B = rnd((2000, 5000), 0.03, 4)
     A.data[A.indptr[7]:A.indptr[8]] = 0
