@@ -46,6 +46,19 @@ namespace b200
         return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
     }
 
+    // device-side address of page-locked (pinned / registered) host memory, nullptr for anything else
+    void *pinned_host_device_ptr(const void *p)
+    {
+        cudaPointerAttributes at;
+        cudaError_t           e = cudaPointerGetAttributes(&at, p);
+        if(e != cudaSuccess)
+        {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+    }
+
     // Same table as aoclsparse::get_doid<T>: [group:3][op:2], op bits 0 = conjugate, 1 = transpose
     // (for symmetric / hermitian bit 1 = upper triangle).
     int get_doid(bool complex_type, int descr_type, int fill_mode, int op)

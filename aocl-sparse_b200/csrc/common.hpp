@@ -122,6 +122,7 @@ namespace b200
 
     // true if the pointer can be dereferenced by a kernel running on the current device
     bool is_device_accessible(const void *p);
+    void *pinned_host_device_ptr(const void *p); // device address of page-locked host memory, else nullptr
 
     // ---------------------------------------------------------------- value-type algebra
     template <typename T>

@@ -514,6 +514,12 @@ namespace b200
             T         *dx = sg.x.as<T>(), *dy = sg.y.as<T>();
             const bool bz = is_zero(beta);
             elem_rule  none_rule{MASK_NONE, DIAG_KEEP, 0, 0};
+            // experiment, OFF by default (AOCLSPARSE_B200_HOST_DIRECT=1): with page-locked y and beta == 0 the kernels
+            // store y straight into host memory instead of D2H copies.  Measured SLOWER on C2 (0.82 ms against 0.58 ms
+            // with the copies): SM-issued posted writes over PCIe run well below the copy engine's 53 GB/s and hold the
+            // CTAs resident while they drain.
+            static const bool direct_ok = getenv("AOCLSPARSE_B200_HOST_DIRECT") && atoi(getenv("AOCLSPARSE_B200_HOST_DIRECT")) != 0;
+            T                *y_direct  = (bz && direct_ok) ? static_cast<T *>(pinned_host_device_ptr(hy)) : nullptr;
             // the side streams start after whatever the caller's stream was doing
             B200_CUDA(cudaEventRecord(hp.ev_start, st));
             B200_CUDA(cudaStreamWaitEvent(hp.h2d, hp.ev_start, 0));
@@ -536,6 +542,11 @@ namespace b200
             {
                 const auto &h = P.host_chunks[c];
                 B200_CUDA(cudaStreamWaitEvent(st, hp.ev_x[c], 0));
+                if(y_direct)
+                {
+                    B200_TRY(launch_gather<T>(M, h.b0, h.b1, h.row0, h.row1, dx, y_direct, alpha, beta, false, none_rule, st));
+                    continue;
+                }
                 B200_TRY(launch_gather<T>(M, h.b0, h.b1, h.row0, h.row1, dx, dy, alpha, beta, false, none_rule, st));
                 B200_CUDA(cudaEventRecord(hp.ev_k[c], st));
                 B200_CUDA(cudaStreamWaitEvent(hp.d2h, hp.ev_k[c], 0));
@@ -543,7 +554,8 @@ namespace b200
                     B200_CUDA(cudaMemcpyAsync(
                         hy + h.row0, dy + h.row0, (size_t)(h.row1 - h.row0) * sizeof(T), cudaMemcpyDeviceToHost, hp.d2h));
             }
-            B200_CUDA(cudaStreamSynchronize(hp.d2h));
+            if(!y_direct)
+                B200_CUDA(cudaStreamSynchronize(hp.d2h));
             B200_CUDA(cudaStreamSynchronize(st));
             done = true;
             return aoclsparse_status_success;

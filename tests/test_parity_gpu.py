@@ -833,12 +833,20 @@ def test_config3_rmat_float(lib, oracle):
 
 
 @pytest.mark.parametrize("beta", [0.0, -0.75])
-def test_host_vectors_pipelined_staging(lib, oracle, beta):
-    """x and y in host memory, large enough for the chunked H2D / kernel / D2H pipeline of aoclsparse_dmv"""
+@pytest.mark.parametrize("pinned", [False, True])
+def test_host_vectors_pipelined_staging(lib, oracle, beta, pinned, monkeypatch):
+    """x and y in host memory, large enough for the chunked H2D / kernel / D2H pipeline of aoclsparse_dmv; pageable and
+    page-locked vectors (the latter also through the direct-store experiment, AOCLSPARSE_B200_HOST_DIRECT=1)"""
+    import torch
+    if pinned:
+        monkeypatch.setenv("AOCLSPARSE_B200_HOST_DIRECT", "1")
     rp, col, val = gen_np.stencil(27, 72, 72, 72)
     m = len(rp) - 1
     x = gen_np.uniform(1, 0, m)
     y0 = gen_np.uniform(2, 0, m) if beta else np.full(m, np.nan)
+    if pinned:
+        keep = [torch.from_numpy(x.copy()).pin_memory(), torch.from_numpy(y0.copy()).pin_memory()]
+        x, y0 = keep[0].numpy(), keep[1].numpy()
     st, h = lib.create_csr("d", 0, m, m, len(col), rp, col, val)
     assert st == 0
     d = lib.create_descr()
@@ -847,7 +855,11 @@ def test_host_vectors_pipelined_staging(lib, oracle, beta):
     oracle.csrmv(111, 1.25, m, m, 0, rp, col, val, 0, 0, 0, x, beta, yo)
     den = 1.25 * oracle_py.row_scale(rp, col, val, x) + (np.abs(beta * y0) if beta else 0)
     for rep in range(3):  # repeated calls reuse the staging buffers and events
-        y = y0.copy()
+        if pinned:
+            ybuf = torch.from_numpy(y0.copy()).pin_memory()
+            y = ybuf.numpy()
+        else:
+            y = y0.copy()
         assert lib.mv("d", 111, 1.25, h, d, x, beta, y) == 0, lib.last_error()
         assert np.max(np.abs(y - yo) / den) <= 1e-12
     lib.destroy(h)
