@@ -518,7 +518,7 @@ namespace b200
             // store y straight into host memory instead of D2H copies.  Measured SLOWER on C2 (0.82 ms against 0.58 ms
             // with the copies): SM-issued posted writes over PCIe run well below the copy engine's 53 GB/s and hold the
             // CTAs resident while they drain.
-            static const bool direct_ok = getenv("AOCLSPARSE_B200_HOST_DIRECT") && atoi(getenv("AOCLSPARSE_B200_HOST_DIRECT")) != 0;
+            const bool        direct_ok = getenv("AOCLSPARSE_B200_HOST_DIRECT") && atoi(getenv("AOCLSPARSE_B200_HOST_DIRECT")) != 0;
             T                *y_direct  = (bz && direct_ok) ? static_cast<T *>(pinned_host_device_ptr(hy)) : nullptr;
             // the side streams start after whatever the caller's stream was doing
             B200_CUDA(cudaEventRecord(hp.ev_start, st));
