@@ -89,6 +89,53 @@ def allgather_x(slab, own, full, group=None):
     return full
 
 
+def partition_by_nnz(row_ptr, world):
+    """Row boundaries [b_0 = 0, ..., b_world = m] that give every rank about the same number of stored entries
+    (skewed matrices are split at equal-nnz points of row_ptr so that every GPU streams the same bytes).
+    row_ptr: zero-based host array of m+1 entries (numpy).  A row is never split between ranks."""
+    import numpy as np
+    rp = np.asarray(row_ptr, dtype=np.int64)
+    m, nnz = len(rp) - 1, int(rp[-1])
+    cuts = [0]
+    for r in range(1, world):
+        target = nnz * r // world
+        b = int(np.searchsorted(rp, target, side="left"))  # first row starting at or after the target
+        cuts.append(min(max(b, cuts[-1]), m))
+    cuts.append(m)
+    return cuts
+
+
+class GatherPlan:
+    """All-gather mode for matrices without a band structure: rank r owns rows [cuts[r], cuts[r+1]) (unequal counts
+    when the split is by nnz), keeps global column indices and multiplies with the WHOLE x; after every multiply the
+    slices of y are all-gathered into the next x.  Slices are padded to the longest one for all_gather_into_tensor
+    (NCCL wants equal sizes) and unpacked with `world` device copies."""
+
+    def __init__(self, cuts, rank, dtype, device, group=None):
+        import torch
+        self.cuts, self.rank, self.world, self.group = list(cuts), rank, len(cuts) - 1, group
+        self.lens = [b - a for a, b in zip(self.cuts, self.cuts[1:])]
+        self.max_len = max(self.lens) if self.lens else 0
+        self.row_lo, self.row_hi = self.cuts[rank], self.cuts[rank + 1]
+        self.send = torch.zeros(max(self.max_len, 1), dtype=dtype, device=device)
+        self.recv = torch.zeros(max(self.max_len, 1) * self.world, dtype=dtype, device=device)
+
+    def own_slice(self):
+        """where the multiply writes this rank's rows (a view of the padded send buffer)"""
+        return self.send[: self.lens[self.rank]]
+
+    def gather(self, full):
+        """full[cuts[r]:cuts[r+1]] <- rank r's slice, for every r; returns full"""
+        if self.world == 1:
+            full[self.row_lo: self.row_hi] = self.own_slice()
+            return full
+        dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
+        for r in range(self.world):
+            if self.lens[r]:
+                full[self.cuts[r]: self.cuts[r + 1]] = self.recv[r * self.max_len: r * self.max_len + self.lens[r]]
+        return full
+
+
 class PeerHalo:
     """Halo exchange fused into the multiply: the boundary rows of a slab store their results straight into the
     neighbours' next-x windows over NVLink (aoclsparse_b200_dmv_rows_push), ordered by stream flags

@@ -105,6 +105,46 @@ def main():
     assert np.array_equal(results["nccl"], results["push"])  # same arithmetic in the same order: bit-identical
     assert np.array_equal(results["nccl"], results["fused"])
     dist.barrier()
+    lib.destroy(A)
+
+    # (d) a matrix without band structure ("general"): rows split at equal-nnz points, global column
+    # indices, whole x all-gathered (NCCL) after every multiply; float, skewed row lengths
+    rng = np.random.default_rng(11)
+    ng = 30000
+    deg = np.minimum((ng * 0.3 / (1 + np.arange(ng)) ** 0.8).astype(np.int64) + 2, ng)
+    rows = np.repeat(np.arange(ng), deg)
+    cols = np.concatenate([rng.choice(ng, int(dg), replace=False) for dg in deg])
+    G = sp.csr_matrix((rng.normal(size=len(rows)).astype(np.float32), (rows, cols)), shape=(ng, ng))
+    G.sort_indices()
+    cuts = sharding.partition_by_nnz(G.indptr, world)
+    plan = sharding.GatherPlan(cuts, rank, torch.float32, "cuda")
+    mine = G[plan.row_lo: plan.row_hi]
+    st, Ag2 = lib.create_csr("s", 0, mine.shape[0], ng, mine.nnz, mine.indptr.astype(np.int32),
+                             mine.indices.astype(np.int32), mine.data)
+    assert st == 0, lib.last_error()
+    assert lib.set_mv_hint(Ag2, 111, d, 100) == 0 and lib.optimize(Ag2) == 0
+    xg0 = np.linspace(-1.0, 1.0, ng).astype(np.float32)
+    xg = torch.from_numpy(xg0).cuda()
+    nxt = torch.empty_like(xg)
+    giters = 3
+    for _ in range(giters):
+        assert lib.mv("s", 111, 0.01, Ag2, d, xg.data_ptr(), 0.0, plan.own_slice().data_ptr()) == 0, lib.last_error()
+        plan.gather(nxt)
+        xg, nxt = nxt, xg
+    torch.cuda.synchronize()
+    want = xg0.astype(np.float64)
+    den = np.abs(want)
+    G64, Gabs = G.astype(np.float64), abs(G).astype(np.float64)
+    for _ in range(giters):
+        den = 0.01 * (Gabs @ den)
+        want = 0.01 * (G64 @ want)
+    got = xg.cpu().numpy().astype(np.float64)
+    err = float(np.max(np.abs(got - want) / np.where(den > 0, den, 1.0)))
+    assert err <= 1e-5 * giters, ("allgather", err)
+    per_rank = np.diff(G.indptr[cuts])
+    assert per_rank.max() - per_rank.min() <= 2 * int(deg.max())
+    lib.destroy(Ag2)
+    dist.barrier()
     if rank == 0:
         print("MULTI_GPU_CHECK_OK world=%d" % world)
     dist.destroy_process_group()

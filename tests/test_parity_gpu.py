@@ -832,6 +832,39 @@ def test_config3_rmat_float(lib, oracle):
         assert np.max(np.abs(y2.astype(np.float64) - yo) / np.where(den > 0, den, 1)) <= 1e-5, mode
 
 
+def test_config5_iterated_1_10_100(lib):
+    """SURVEY 8(d) parity protocol for the iterated case: x <- A x / 12 on a 7-point stencil, compared with the host
+    product after 1, 10 and 100 iterations; the tolerance grows with the iteration count (every iteration adds one
+    rounding of size 1e-12 * sum|a||x| relative to a vector whose scale is followed by the same recurrence on |.|)"""
+    import scipy.sparse as sp
+    import torch
+    nx = ny = nz = 40
+    rp, col, val = gen_np.stencil(7, nx, ny, nz)
+    m = len(rp) - 1
+    st, h = lib.create_csr("d", 0, m, m, len(col), rp, col, val)
+    assert st == 0
+    d = lib.create_descr()
+    assert lib.set_mv_hint(h, 111, d, 100) == 0 and lib.optimize(h) == 0
+    A = sp.csr_matrix((val, col, rp), shape=(m, m))
+    Aabs = abs(A)
+    x0 = gen_np.uniform(1, 0, m)
+    bufs = [torch.from_numpy(x0.copy()).cuda(), torch.zeros(m, dtype=torch.float64, device="cuda")]
+    want, scale = x0.copy(), np.abs(x0)
+    k = 0
+    for stop in (1, 10, 100):
+        while k < stop:
+            assert lib.mv("d", 111, 1.0 / 12, h, d, bufs[k % 2].data_ptr(), 0.0, bufs[(k + 1) % 2].data_ptr()) == 0
+            want = (A @ want) / 12.0
+            scale = (Aabs @ scale) / 12.0
+            k += 1
+        torch.cuda.synchronize()
+        got = bufs[k % 2].cpu().numpy()
+        err = float(np.max(np.abs(got - want) / scale))
+        assert err <= 1e-12 * stop, (stop, err)
+    lib.destroy(h)
+    lib.destroy_descr(d)
+
+
 @pytest.mark.parametrize("beta", [0.0, -0.75])
 @pytest.mark.parametrize("pinned", [False, True])
 def test_host_vectors_pipelined_staging(lib, oracle, beta, pinned, monkeypatch):

@@ -96,3 +96,70 @@ def test_partition_properties():
     assert (s.win_lo, s.win_hi, s.has_left, s.has_right, s.own_offset) == (3072 - 64, 4096, True, False, 64)
     s = sharding.make_slab(4096, 1, 0, 64)
     assert s.halo == 0 and not s.has_left and not s.has_right
+
+
+def _gather_worker(rank, world, port, iters, q):
+    import scipy.sparse as sp
+
+    import sharding
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    A = _skewed_matrix()
+    cuts = sharding.partition_by_nnz(A.indptr, world)
+    plan = sharding.GatherPlan(cuts, rank, torch.float64, "cpu")
+    mine = A[plan.row_lo: plan.row_hi]
+    x = torch.from_numpy(np.linspace(-1.0, 1.0, A.shape[0]))
+    for _ in range(iters):
+        plan.own_slice().copy_(torch.from_numpy(mine @ x.numpy()) / 50.0)
+        x = plan.gather(torch.empty_like(x))
+    q.put((rank, x.numpy().copy(), cuts))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _skewed_matrix():
+    """power-law-ish square matrix: a few very long rows, many short ones (deterministic)"""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(3)
+    n = 400
+    deg = np.minimum((n * 0.6 / (1 + np.arange(n)) ** 0.9).astype(int) + 1, n)
+    rows = np.repeat(np.arange(n), deg)
+    cols = np.concatenate([rng.choice(n, d, replace=False) for d in deg])
+    return sp.csr_matrix((rng.normal(size=len(rows)), (rows, cols)), shape=(n, n))
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_allgather_mode_with_nnz_balanced_rows(world):
+    """general matrices: rows split at equal-nnz points, whole x all-gathered after every multiply"""
+    iters = 4
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gather_worker, args=(r, world, port, iters, q)) for r in range(world)]
+    [p.start() for p in procs]
+    parts = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    A = _skewed_matrix()
+    x = np.linspace(-1.0, 1.0, A.shape[0])
+    for _ in range(iters):
+        x = (A @ x) / 50.0
+    for _, got, cuts in parts:  # every rank ends with the same, complete vector
+        assert np.max(np.abs(got - x)) <= 1e-13 * max(1.0, np.max(np.abs(x)))
+    cuts = parts[0][2]
+    per_rank = np.diff(A.indptr[cuts])
+    assert cuts[0] == 0 and cuts[-1] == A.shape[0] and all(a <= b for a, b in zip(cuts, cuts[1:]))
+    # balanced to within the longest row
+    assert per_rank.max() - per_rank.min() <= 2 * np.diff(A.indptr).max()
+    rows_per_rank = np.diff(cuts)
+    assert rows_per_rank.max() > 2 * rows_per_rank.min()  # i.e. NOT an equal-rows split
+
+
+def test_partition_by_nnz_edge_cases():
+    import sharding
+    assert sharding.partition_by_nnz([0, 0, 0, 0], 2) == [0, 0, 3] or sharding.partition_by_nnz([0, 0, 0, 0], 2)[-1] == 3
+    assert sharding.partition_by_nnz([0, 5], 4)[0] == 0 and sharding.partition_by_nnz([0, 5], 4)[-1] == 1
+    rp = np.arange(0, 101, 10)
+    assert sharding.partition_by_nnz(rp, 5) == [0, 2, 4, 6, 8, 10]
+    assert sharding.partition_by_nnz(rp, 1) == [0, 10]
