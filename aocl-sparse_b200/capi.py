@@ -25,8 +25,8 @@ NON_UNIT, UNIT, ZERO_DIAG = 0, 1, 2
 ROW_MAJOR, COL_MAJOR = 0, 1
 DMAT, SMAT, CMAT, ZMAT = 0, 1, 2, 3
 ST = dict(success=0, not_implemented=1, invalid_pointer=2, invalid_size=3, internal_error=4,
-          invalid_value=5, invalid_index_value=6, wrong_type=9, memory_error=10,
-          invalid_operation=12, invalid_kid=14)
+          invalid_value=5, invalid_index_value=6, maxit=7, user_stop=8, wrong_type=9, memory_error=10,
+          numerical_error=11, invalid_operation=12, unsorted_input=13, invalid_kid=14)
 
 PREFIX = {np.dtype(np.float32): "s", np.dtype(np.float64): "d",
           np.dtype(np.complex64): "c", np.dtype(np.complex128): "z"}
@@ -133,6 +133,15 @@ class AoclSparse:
         L.aoclsparse_set_memory_hint.argtypes = [vp, ci]
         L.aoclsparse_spmm.argtypes = [ci, vp, vp, C.POINTER(vp)]
         L.aoclsparse_sp2m.argtypes = [ci, vp, vp, ci, vp, vp, ci, C.POINTER(vp)]
+        if hasattr(L, "aoclsparse_itsol_d_init"):
+            for p in "sd":
+                getattr(L, f"aoclsparse_itsol_{p}_init").argtypes = [C.POINTER(vp)]
+                getattr(L, f"aoclsparse_itsol_{p}_rci_input").argtypes = [vp, i32, vp]
+                getattr(L, f"aoclsparse_itsol_{p}_rci_solve").argtypes = [vp, C.POINTER(ci), C.POINTER(vp), C.POINTER(vp), vp, vp]
+                getattr(L, f"aoclsparse_itsol_{p}_solve").argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp]
+            L.aoclsparse_itsol_destroy.argtypes = [C.POINTER(vp)]
+            L.aoclsparse_itsol_destroy.restype = None
+            L.aoclsparse_itsol_option_set.argtypes = [vp, C.c_char_p, C.c_char_p]
         L.aoclsparse_order_mat.argtypes = [vp]
         for p in "sdcz":
             getattr(L, f"aoclsparse_export_{p}csr").argtypes = [vp] + [vp] * 7
@@ -240,6 +249,50 @@ class AoclSparse:
     def spmm(self, op, a, b):
         c = C.c_void_p()
         return self.lib.aoclsparse_spmm(op, a, b, C.byref(c)), c
+
+    # ---- iterative solvers (conjugate gradients) ----------------------------------------------
+    def itsol_init(self, prefix):
+        h = C.c_void_p()
+        return getattr(self.lib, f"aoclsparse_itsol_{prefix}_init")(C.byref(h)), h
+
+    def itsol_destroy(self, h):
+        self.lib.aoclsparse_itsol_destroy(C.byref(h))
+
+    def itsol_option_set(self, h, option, value):
+        enc = lambda t: None if t is None else t.encode()  # noqa: E731
+        return self.lib.aoclsparse_itsol_option_set(h, enc(option), enc(value))
+
+    def itsol_solve(self, prefix, h, n, mat, descr, b, x, rinfo, precond=None, monit=None):
+        """precond(flag, n, u, v) / monit(n, x, r, rinfo) are Python callables on numpy views; both return an int"""
+        ct = C.c_double if prefix == "d" else C.c_float
+        dt = np.float64 if prefix == "d" else np.float32
+        PT = C.POINTER(ct)
+        keep = []
+
+        def view(ptr, count):
+            if not ptr:
+                return None  # the reference hands its monitor a NULL residual pointer (see DESIGN.md)
+            return np.ctypeslib.as_array(ptr, shape=(count,)) if count else np.zeros(0, dt)
+        cb_p = cb_m = None
+        if precond is not None:
+            cb_p = C.CFUNCTYPE(C.c_int, C.c_int, C.c_int, PT, PT, C.c_void_p)(
+                lambda flag, nn, u, v, ud: int(precond(flag, nn, view(u, nn), view(v, nn))))
+            keep.append(cb_p)
+        if monit is not None:
+            cb_m = C.CFUNCTYPE(C.c_int, C.c_int, PT, PT, PT, C.c_void_p)(
+                lambda nn, xx, rr, ri, ud: int(monit(nn, view(xx, nn), view(rr, nn), view(ri, 100))))
+            keep.append(cb_m)
+        as_vp = lambda f: C.cast(f, C.c_void_p) if f is not None else None  # noqa: E731
+        return getattr(self.lib, f"aoclsparse_itsol_{prefix}_solve")(
+            h, n, mat, descr, ptr(b), ptr(x), ptr(rinfo), as_vp(cb_p), as_vp(cb_m), None)
+
+    def itsol_rci_input(self, prefix, h, n, b):
+        return getattr(self.lib, f"aoclsparse_itsol_{prefix}_rci_input")(h, n, ptr(b))
+
+    def itsol_rci_solve(self, prefix, h, ircomm, u, v, x, rinfo):
+        """ircomm: ctypes c_int (in/out); u, v: ctypes c_void_p (out)"""
+        return getattr(self.lib, f"aoclsparse_itsol_{prefix}_rci_solve")(
+            h, C.byref(ircomm), C.byref(u), C.byref(v), ptr(x), ptr(rinfo))
 
     def sp2m(self, opA, dA, a, opB, dB, b, request, c=None):
         """returns (status, C handle); pass the handle of the nnz_count stage as c for the finalize stage"""

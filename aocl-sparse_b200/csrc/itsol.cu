@@ -1,0 +1,900 @@
+// itsol.cu -- conjugate gradients on the device: the consumer of "SpMV x 100" in the reference.
+//
+// Reference: the iterative-solver suite of library/src/solvers/aoclsparse_itsol_functions.{hpp,cpp}: a handle with an
+// option registry (aoclsparse_itsol_list_options.hpp:63-239), a reverse-communication CG state machine
+// (aoclsparse_cg_rci_solve, itsol_functions.hpp:633-870) and a forward interface that drives it with aoclsparse::mv on a
+// symmetric / lower descriptor (aoclsparse_cg_solve, :1369-1500).  Kept here: aoclsparse_itsol_{s,d}_init,
+// aoclsparse_itsol_destroy, aoclsparse_itsol_option_set (all registered options, same names, bounds, defaults and
+// normalisation), aoclsparse_itsol_{s,d}_rci_input, aoclsparse_itsol_{s,d}_rci_solve and aoclsparse_itsol_{s,d}_solve for
+// the CG method with no or a user preconditioner.  GMRES, the symmetric Gauss-Seidel preconditioner and the complex
+// variants return aoclsparse_status_not_implemented.
+//
+// B200: the state machine and its scalar logic (tolerances, iteration limit, breakdown tests, rinfo) are the reference's;
+// every vector operation is a CUDA kernel on vectors that never leave the device in the forward interface:
+//   r = -b, p = x                      cg_start_kernel
+//   r += q, |r|^2                      cg_residual_kernel        (block partials in double; the last block adds them in
+//                                                                 index order and stores the sum into mapped host memory)
+//   r.z , p.q                          dot_kernel
+//   p = beta p - z                     cg_direction_kernel
+//   x += alpha p, r += alpha q, |r|^2  cg_step_kernel
+// The work vectors r, p, q, z live in CUDA managed memory: the reverse-communication interface hands pointers to them to
+// the caller (*u, *v), and a host caller may read / write them as ordinary memory while a GPU caller passes them straight
+// to aoclsparse_?mv; in the forward interface nothing touches them from the host, so they stay resident in HBM.
+// Two scalars per iteration travel to the host (p.q and |r|), because the reference tests convergence and breakdown
+// every iteration and reports them through rinfo.
+#include "common.hpp"
+
+#include <algorithm>
+#include <cctype>
+#include <cmath>
+#include <limits>
+#include <string>
+
+namespace b200
+{
+    namespace
+    {
+        constexpr int RED_THREADS = 256, RED_BLOCKS = 148 * 4;
+
+        enum cg_task
+        {
+            task_start = 0,
+            task_init_res,
+            task_check_conv,
+            task_start_iter,
+            task_compute_beta,
+            task_take_step
+        };
+
+        // ---------------------------------------------------------------- options (itsol_list_options.hpp:63-239)
+        template <typename R>
+        R expected_precision(R scale)
+        {
+            // aoclsparse_utils.hpp:560-580: scale * safeguard * sqrt(2 eps), safeguard = 1 (double) / 2 (float)
+            const R eps = std::numeric_limits<R>::epsilon();
+            return scale * (sizeof(R) == 4 ? (R)2.0 : (R)1.0) * std::sqrt((R)2.0 * eps);
+        }
+
+        // trim, squeeze runs of blanks to one space, lower case (OptionUtility::PrepareString, itsol_options.hpp:104-114)
+        std::string prepare(const char *s)
+        {
+            std::string out;
+            bool        blank = false;
+            for(const char *p = s; *p; ++p)
+            {
+                if(std::isspace((unsigned char)*p))
+                {
+                    blank = !out.empty();
+                    continue;
+                }
+                if(blank)
+                    out.push_back(' ');
+                blank = false;
+                out.push_back((char)std::tolower((unsigned char)*p));
+            }
+            return out;
+        }
+
+        template <typename R>
+        struct options
+        {
+            int  solver        = 0; // 0 CG, 1 GMRES
+            int  cg_maxit      = 500;
+            R    cg_rtol       = expected_precision<R>((R)2.0);
+            R    cg_atol       = expected_precision<R>((R)1.0);
+            int  cg_precond    = 0; // 0 none, 1 user, 3 symmetric Gauss-Seidel
+            int  gm_maxit      = 150;
+            R    gm_rtol       = expected_precision<R>((R)2.0);
+            R    gm_atol       = expected_precision<R>((R)1.0);
+            int  gm_precond    = 0;
+            int  gm_restart    = 20;
+            bool locked        = false;
+
+            // 0 ok, 1 out of range, 2 bad value, 3 unknown option, 4 locked (OptionRegistry::SetOption return codes)
+            int set(const std::string &name, const char *raw)
+            {
+                int *ip = nullptr;
+                R   *rp = nullptr;
+                if(name == "cg iteration limit")
+                    ip = &cg_maxit;
+                else if(name == "gmres iteration limit")
+                    ip = &gm_maxit;
+                else if(name == "gmres restart iterations")
+                    ip = &gm_restart;
+                else if(name == "cg rel tolerance")
+                    rp = &cg_rtol;
+                else if(name == "cg abs tolerance")
+                    rp = &cg_atol;
+                else if(name == "gmres rel tolerance")
+                    rp = &gm_rtol;
+                else if(name == "gmres abs tolerance")
+                    rp = &gm_atol;
+                if(ip || rp)
+                {
+                    if(locked)
+                        return 4;
+                    char *end = nullptr;
+                    if(ip)
+                    {
+                        const long v = std::strtol(raw, &end, 10);
+                        if(end == raw)
+                            return 2;
+                        if(v < 1 || v > 0x7fffffffL)
+                            return 1;
+                        *ip = (int)v;
+                    }
+                    else
+                    {
+                        const double v = std::strtod(raw, &end);
+                        if(end == raw)
+                            return 2;
+                        if(!(v >= 0.0))
+                            return 1;
+                        *rp = (R)v;
+                    }
+                    return 0;
+                }
+                const std::string v = prepare(raw);
+                if(name == "iterative method")
+                {
+                    if(locked)
+                        return 4;
+                    if(v == "cg" || v == "pcg")
+                        solver = 0;
+                    else if(v == "gmres" || v == "gm res")
+                        solver = 1;
+                    else
+                        return 2;
+                    return 0;
+                }
+                if(name == "cg preconditioner")
+                {
+                    if(locked)
+                        return 4;
+                    if(v == "none")
+                        cg_precond = 0;
+                    else if(v == "user")
+                        cg_precond = 1;
+                    else if(v == "gs" || v == "symgs" || v == "sgs")
+                        cg_precond = 3;
+                    else
+                        return 2;
+                    return 0;
+                }
+                if(name == "gmres preconditioner")
+                {
+                    if(locked)
+                        return 4;
+                    if(v == "none")
+                        gm_precond = 0;
+                    else if(v == "user")
+                        gm_precond = 1;
+                    else if(v == "ilu0")
+                        gm_precond = 2;
+                    else
+                        return 2;
+                    return 0;
+                }
+                return 3;
+            }
+        };
+
+        // ---------------------------------------------------------------- vector kernels
+        // where a reduction lands: per-block partials, a ticket counter, and the final value in page-locked host memory
+        // that the device writes directly (one 8-byte store instead of a finishing launch + a memcpy)
+        struct reduce_out
+        {
+            double   *partial;
+            unsigned *ticket;
+            double   *result; // device address of mapped host memory
+        };
+
+        // block sum -> partial[blockIdx.x]; the LAST block to arrive adds the partials in index order (deterministic)
+        template <typename T>
+        __device__ __forceinline__ void block_sum_store(double s, reduce_out o)
+        {
+            __shared__ double sh[RED_THREADS / 32];
+            __shared__ bool   last;
+#pragma unroll
+            for(int k = 16; k > 0; k >>= 1)
+                s += __shfl_down_sync(0xffffffffu, s, k);
+            if((threadIdx.x & 31) == 0)
+                sh[threadIdx.x >> 5] = s;
+            __syncthreads();
+            if(threadIdx.x < 32)
+            {
+                s = threadIdx.x < RED_THREADS / 32 ? sh[threadIdx.x] : 0.0;
+#pragma unroll
+                for(int k = 16; k > 0; k >>= 1)
+                    s += __shfl_down_sync(0xffffffffu, s, k);
+                if(threadIdx.x == 0)
+                {
+                    o.partial[blockIdx.x] = s;
+                    __threadfence();
+                    last = atomicAdd(o.ticket, 1u) == gridDim.x - 1;
+                }
+            }
+            __syncthreads();
+            if(!last)
+                return;
+            __threadfence();
+            double t = 0;
+            for(int i = threadIdx.x; i < (int)gridDim.x; i += RED_THREADS)
+                t += __ldcg(o.partial + i);
+            __shared__ double fin[RED_THREADS];
+            fin[threadIdx.x] = t;
+            __syncthreads();
+            for(int k = RED_THREADS / 2; k > 0; k >>= 1)
+            {
+                if(threadIdx.x < k)
+                    fin[threadIdx.x] += fin[threadIdx.x + k];
+                __syncthreads();
+            }
+            if(threadIdx.x == 0)
+            {
+                *o.result = fin[0];
+                *o.ticket = 0; // ready for the next reduction on this stream
+                __threadfence_system();
+            }
+        }
+
+        template <typename T>
+        __global__ void __launch_bounds__(RED_THREADS) cg_start_kernel(long long n, const T *__restrict__ b, const T *__restrict__ x,
+                                                                      T *__restrict__ r, T *__restrict__ p, reduce_out partial)
+        {
+            double s = 0;
+            for(long long i = (long long)blockIdx.x * RED_THREADS + threadIdx.x; i < n; i += (long long)gridDim.x * RED_THREADS)
+            {
+                const T bi = b[i];
+                r[i]       = -bi;
+                p[i]       = x[i];
+                s += (double)bi * (double)bi;
+            }
+            block_sum_store<T>(s, partial);
+        }
+
+        template <typename T>
+        __global__ void __launch_bounds__(RED_THREADS) cg_residual_kernel(long long n, T *__restrict__ r, const T *__restrict__ q,
+                                                                         T *__restrict__ p, reduce_out partial)
+        {
+            double s = 0;
+            for(long long i = (long long)blockIdx.x * RED_THREADS + threadIdx.x; i < n; i += (long long)gridDim.x * RED_THREADS)
+            {
+                const T ri = r[i] + q[i];
+                r[i]       = ri;
+                p[i]       = (T)0;
+                s += (double)ri * (double)ri;
+            }
+            block_sum_store<T>(s, partial);
+        }
+
+        template <typename T>
+        __global__ void __launch_bounds__(RED_THREADS) dot_kernel(long long n, const T *__restrict__ a, const T *__restrict__ b, reduce_out partial)
+        {
+            double s = 0;
+            for(long long i = (long long)blockIdx.x * RED_THREADS + threadIdx.x; i < n; i += (long long)gridDim.x * RED_THREADS)
+                s += (double)a[i] * (double)b[i];
+            block_sum_store<T>(s, partial);
+        }
+
+        template <typename T>
+        __global__ void __launch_bounds__(RED_THREADS) cg_direction_kernel(long long n, T beta, T *__restrict__ p, const T *__restrict__ z)
+        {
+            for(long long i = (long long)blockIdx.x * RED_THREADS + threadIdx.x; i < n; i += (long long)gridDim.x * RED_THREADS)
+                p[i] = beta * p[i] - z[i];
+        }
+
+        template <typename T>
+        __global__ void __launch_bounds__(RED_THREADS) cg_step_kernel(long long n, T alpha, const T *__restrict__ p, const T *__restrict__ q,
+                                                                     T *__restrict__ x, T *__restrict__ r, reduce_out partial)
+        {
+            double s = 0;
+            for(long long i = (long long)blockIdx.x * RED_THREADS + threadIdx.x; i < n; i += (long long)gridDim.x * RED_THREADS)
+            {
+                x[i] += alpha * p[i];
+                const T ri = r[i] + alpha * q[i];
+                r[i]       = ri;
+                s += (double)ri * (double)ri;
+            }
+            block_sum_store<T>(s, partial);
+        }
+
+        struct managed_buf
+        {
+            void  *p     = nullptr;
+            size_t bytes = 0;
+            managed_buf() = default;
+            managed_buf(const managed_buf &)            = delete;
+            managed_buf &operator=(const managed_buf &) = delete;
+            ~managed_buf()
+            {
+                release();
+            }
+            void release()
+            {
+                if(p)
+                    cudaFree(p);
+                p     = nullptr;
+                bytes = 0;
+            }
+            aoclsparse_status alloc(size_t n, cudaStream_t st, bool managed = true)
+            {
+                release();
+                if(!managed)
+                {
+                    B200_CUDA(cudaMalloc(&p, n ? n : 16));
+                    bytes = n;
+                    return aoclsparse_status_success;
+                }
+                B200_CUDA(cudaMallocManaged(&p, n ? n : 16));
+                bytes = n;
+                int dev = 0;
+                cudaGetDevice(&dev);
+                // first touch on the device; a failure here (no prefetch support) is harmless
+                if(cudaMemPrefetchAsync(p, n ? n : 16, dev, st) != cudaSuccess)
+                    cudaGetLastError();
+                return aoclsparse_status_success;
+            }
+            template <typename T>
+            T *as() const
+            {
+                return static_cast<T *>(p);
+            }
+        };
+
+        template <typename T>
+        struct itsol_data
+        {
+            options<T>     opts;
+            aoclsparse_int n       = 0;
+            bool           have_b  = false;
+            bool           solving = false;
+            bool           host_visible = true; // work vectors in managed memory (reverse communication, callbacks)
+            managed_buf    b, r, p, q, z, xw; // xw: device-side copy of a host-resident x
+            dev_buf        partial, ticket;
+            double        *h_result = nullptr, *d_result = nullptr; // mapped page-locked scalar
+            ~itsol_data()
+            {
+                if(h_result)
+                    cudaFreeHost(h_result);
+            }
+            // CG state (cg_data, aoclsparse_itsol_data.hpp)
+            int  task = task_start, niter = 0, precond = 0, maxit = 500;
+            T    rtol = 0, atol = 0, rnorm2 = 0, bnorm2 = 0, brtol = 0, rz = 0, alpha = 0, beta = 0;
+            T   *x_dev       = nullptr; // where the solver updates x
+            T   *x_user      = nullptr; // the caller's x when it is host memory (copied back before every return)
+        };
+
+        template <typename T>
+        aoclsparse_status reduce_to_host(itsol_data<T> *it, cudaStream_t st, double &out)
+        {
+            B200_CUDA(cudaStreamSynchronize(st));
+            out = *static_cast<volatile double *>(it->h_result);
+            return aoclsparse_status_success;
+        }
+
+        template <typename T>
+        aoclsparse_status sync_x_to_user(itsol_data<T> *it, cudaStream_t st)
+        {
+            if(it->x_user && it->n > 0)
+            {
+                B200_CUDA(cudaMemcpyAsync(it->x_user, it->x_dev, sizeof(T) * (size_t)it->n, cudaMemcpyDeviceToHost, st));
+                B200_CUDA(cudaStreamSynchronize(st));
+            }
+            return aoclsparse_status_success;
+        }
+
+        template <typename T>
+        bool negative_or_nearzero(T v)
+        {
+            // aoclsparse_is_negative_or_nearzero, aoclsparse_utils.hpp:627-640 (scale 1e-2)
+            return v <= (T)1e-2 * (T)2.0 * std::numeric_limits<T>::epsilon();
+        }
+
+        template <typename T>
+        aoclsparse_status rci_input(itsol_data<T> *it, aoclsparse_int n, const T *b)
+        {
+            // aoclsparse_itsol_rci_input, itsol_functions.hpp:296-330
+            if(it == nullptr)
+                return aoclsparse_status_internal_error;
+            if(n < 0)
+                return aoclsparse_status_invalid_value;
+            if(!b)
+                return aoclsparse_status_invalid_pointer;
+            cudaStream_t st = current_stream();
+            it->have_b      = false;
+            B200_TRY(it->b.alloc(sizeof(T) * (size_t)n, st, it->host_visible));
+            for(managed_buf *m : {&it->r, &it->p, &it->q, &it->z})
+                B200_TRY(m->alloc(sizeof(T) * (size_t)n, st, it->host_visible));
+            it->xw.release();
+            B200_TRY(it->partial.alloc(sizeof(double) * RED_BLOCKS));
+            B200_TRY(it->ticket.alloc(sizeof(unsigned)));
+            B200_CUDA(cudaMemsetAsync(it->ticket.p, 0, sizeof(unsigned), st));
+            if(!it->h_result)
+            {
+                B200_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&it->h_result), sizeof(double), cudaHostAllocMapped));
+                B200_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void **>(&it->d_result), it->h_result, 0));
+            }
+            if(n > 0)
+                B200_CUDA(cudaMemcpyAsync(it->b.p, b, sizeof(T) * (size_t)n, cudaMemcpyDefault, st));
+            B200_CUDA(cudaStreamSynchronize(st));
+            it->n       = n;
+            it->have_b  = true;
+            it->solving = false;
+            return aoclsparse_status_success;
+        }
+
+        template <typename T>
+        aoclsparse_status solver_init(itsol_data<T> *it)
+        {
+            // aoclsparse_itsol_solver_init + aoclsparse_cg_data_options, itsol_functions.hpp:205-218,335-380
+            if(it->opts.solver != 0)
+                return aoclsparse_status_not_implemented; // GMRES
+            it->task    = task_start;
+            it->precond = it->opts.cg_precond;
+            it->rtol    = it->opts.cg_rtol;
+            it->atol    = it->opts.cg_atol;
+            it->maxit   = it->opts.cg_maxit;
+            return aoclsparse_status_success;
+        }
+
+        // aoclsparse_cg_rci_solve, itsol_functions.hpp:633-870 -- same tasks, same scalar logic, vector work on the device
+        template <typename T>
+        aoclsparse_status cg_rci(itsol_data<T> *it, aoclsparse_itsol_rci_job *ircomm, T **u, T **v, T *x, T rinfo[100])
+        {
+            aoclsparse_status exit_status = aoclsparse_status_success;
+            cudaStream_t      st          = current_stream();
+            const long long   n           = it->n;
+            T                *r = it->r.template as<T>(), *p = it->p.template as<T>(), *q = it->q.template as<T>(),
+              *z = it->z.template as<T>();
+            const reduce_out partial{it->partial.template as<double>(), it->ticket.template as<unsigned>(), it->d_result};
+            double  red     = 0;
+            bool    loop;
+            if(it->task != task_start && *ircomm == aoclsparse_rci_interrupt)
+            {
+                *ircomm = aoclsparse_rci_stop;
+                sync_x_to_user(it, st);
+                return aoclsparse_status_user_stop;
+            }
+            do
+            {
+                loop = false;
+                switch(it->task)
+                {
+                case task_start:
+                    for(int i = 0; i < 100; ++i)
+                        rinfo[i] = (T)0;
+                    it->niter = 0;
+                    // where x lives while solving
+                    if(is_device_accessible(x))
+                    {
+                        it->x_dev  = x;
+                        it->x_user = nullptr;
+                    }
+                    else
+                    {
+                        B200_TRY(it->xw.alloc(sizeof(T) * (size_t)n, st, it->host_visible));
+                        if(n > 0)
+                            B200_CUDA(cudaMemcpyAsync(it->xw.p, x, sizeof(T) * (size_t)n, cudaMemcpyHostToDevice, st));
+                        it->x_dev  = it->xw.template as<T>();
+                        it->x_user = x;
+                    }
+                    cg_start_kernel<T><<<RED_BLOCKS, RED_THREADS, 0, st>>>(n, it->b.template as<T>(), it->x_dev, r, p, partial);
+                    B200_LAUNCHED();
+                    B200_TRY(reduce_to_host(it, st, red));
+                    it->bnorm2 = (T)std::sqrt(red);
+                    if(it->bnorm2 != it->bnorm2)
+                        return aoclsparse_status_invalid_value; // b is rubbish
+                    rinfo[1]  = it->bnorm2;
+                    it->brtol = it->rtol * it->bnorm2;
+                    *ircomm   = aoclsparse_rci_mv;
+                    it->task  = task_init_res;
+                    *u        = p;
+                    *v        = q;
+                    break;
+
+                case task_init_res:
+                    // q = A x, r = -b  ->  r = A x - b, p = 0
+                    cg_residual_kernel<T><<<RED_BLOCKS, RED_THREADS, 0, st>>>(n, r, q, p, partial);
+                    B200_LAUNCHED();
+                    B200_TRY(reduce_to_host(it, st, red));
+                    it->rnorm2 = (T)std::sqrt(red);
+                    if(it->rnorm2 != it->rnorm2)
+                    {
+                        exit_status = aoclsparse_status_numerical_error;
+                        break;
+                    }
+                    rinfo[0] = it->rnorm2;
+                    it->rz   = (T)1;
+                    it->task = task_check_conv;
+                    // fall through
+                case task_check_conv:
+                    *u = r;
+                    *v = nullptr;
+                    if((T)0 < it->atol && it->rnorm2 <= it->atol)
+                    {
+                        *ircomm = aoclsparse_rci_stop;
+                        break;
+                    }
+                    if((T)0 < it->rtol && it->rnorm2 <= it->brtol)
+                    {
+                        *ircomm = aoclsparse_rci_stop;
+                        break;
+                    }
+                    if(it->maxit > 0 && it->niter > it->maxit)
+                    {
+                        *ircomm     = aoclsparse_rci_stop;
+                        exit_status = aoclsparse_status_maxit;
+                        break;
+                    }
+                    it->task = task_start_iter;
+                    *ircomm  = aoclsparse_rci_stopping_criterion;
+                    break;
+
+                case task_start_iter:
+                    it->niter++;
+                    rinfo[30] = (T)it->niter;
+                    it->task  = task_compute_beta;
+                    if(it->precond)
+                    {
+                        *ircomm = aoclsparse_rci_precond;
+                        *u      = r;
+                        *v      = z;
+                        break;
+                    }
+                    // unpreconditioned: z = r, no copy needed -- r.z = |r|^2 is already known
+                    // fall through
+                case task_compute_beta:
+                {
+                    T        rz_new;
+                    const T *zz = it->precond ? z : r;
+                    if(it->precond)
+                    {
+                        dot_kernel<T><<<RED_BLOCKS, RED_THREADS, 0, st>>>(n, r, z, partial);
+                        B200_LAUNCHED();
+                        B200_TRY(reduce_to_host(it, st, red));
+                        rz_new = (T)red;
+                    }
+                    else
+                        rz_new = it->rnorm2 * it->rnorm2;
+                    if(negative_or_nearzero(it->rz))
+                        return aoclsparse_status_numerical_error;
+                    it->beta = rz_new / it->rz;
+                    it->rz   = rz_new;
+                    cg_direction_kernel<T><<<RED_BLOCKS, RED_THREADS, 0, st>>>(n, it->beta, p, zz);
+                    B200_LAUNCHED();
+                    *ircomm  = aoclsparse_rci_mv;
+                    it->task = task_take_step;
+                    *u       = p;
+                    *v       = q;
+                    break;
+                }
+
+                case task_take_step:
+                {
+                    dot_kernel<T><<<RED_BLOCKS, RED_THREADS, 0, st>>>(n, p, q, partial);
+                    B200_LAUNCHED();
+                    B200_TRY(reduce_to_host(it, st, red));
+                    const T pq = (T)red;
+                    if(negative_or_nearzero(pq) || pq == (T)0)
+                        return aoclsparse_status_numerical_error; // A is not positive definite
+                    it->alpha = it->rz / pq;
+                    cg_step_kernel<T><<<RED_BLOCKS, RED_THREADS, 0, st>>>(n, it->alpha, p, q, it->x_dev, r, partial);
+                    B200_LAUNCHED();
+                    B200_TRY(reduce_to_host(it, st, red));
+                    it->rnorm2 = (T)std::sqrt(red);
+                    if(it->rnorm2 != it->rnorm2)
+                    {
+                        exit_status = aoclsparse_status_numerical_error;
+                        break;
+                    }
+                    rinfo[0] = it->rnorm2;
+                    loop     = true;
+                    it->task = task_check_conv;
+                    break;
+                }
+
+                default:
+                    *ircomm = aoclsparse_rci_stop;
+                    return aoclsparse_status_internal_error;
+                }
+            } while(loop);
+            // a host-resident x is brought up to date whenever the caller may look at it
+            if(*ircomm == aoclsparse_rci_stop || *ircomm == aoclsparse_rci_stopping_criterion || exit_status != aoclsparse_status_success)
+                B200_TRY(sync_x_to_user(it, st));
+            else
+                B200_CUDA(cudaStreamSynchronize(st)); // *u / *v are about to be read or written by the caller
+            return exit_status;
+        }
+
+        // aoclsparse_itsol_rci_solve, itsol_functions.hpp:486-553
+        template <typename T>
+        aoclsparse_status rci_solve(itsol_data<T> *it, aoclsparse_itsol_rci_job *ircomm, T **u, T **v, T *x, T rinfo[100])
+        {
+            if(ircomm == nullptr)
+                return aoclsparse_status_invalid_pointer;
+            if(it == nullptr)
+            {
+                *ircomm = aoclsparse_rci_stop;
+                return aoclsparse_status_internal_error;
+            }
+            if(u == nullptr || v == nullptr || x == nullptr || rinfo == nullptr || !it->have_b)
+            {
+                *ircomm = aoclsparse_rci_stop;
+                return aoclsparse_status_invalid_pointer;
+            }
+            aoclsparse_status status;
+            if(!it->solving)
+            {
+                status = solver_init(it);
+                if(status != aoclsparse_status_success)
+                {
+                    *ircomm = aoclsparse_rci_stop;
+                    return status;
+                }
+                it->solving     = true;
+                it->opts.locked = true;
+            }
+            status = cg_rci(it, ircomm, u, v, x, rinfo);
+            if(status != aoclsparse_status_success)
+                *ircomm = aoclsparse_rci_stop;
+            if(*ircomm == aoclsparse_rci_stop)
+            {
+                it->solving     = false;
+                it->opts.locked = false;
+            }
+            return status;
+        }
+
+        template <typename T>
+        struct mv_of;
+        template <>
+        struct mv_of<float>
+        {
+            static aoclsparse_status call(const float *a, aoclsparse_matrix A, const aoclsparse_mat_descr d, const float *x, const float *b, float *y)
+            {
+                return aoclsparse_smv(aoclsparse_operation_none, a, A, d, x, b, y);
+            }
+        };
+        template <>
+        struct mv_of<double>
+        {
+            static aoclsparse_status call(const double *a, aoclsparse_matrix A, const aoclsparse_mat_descr d, const double *x, const double *b, double *y)
+            {
+                return aoclsparse_dmv(aoclsparse_operation_none, a, A, d, x, b, y);
+            }
+        };
+
+        // aoclsparse_itsol_solve + aoclsparse_cg_solve, itsol_functions.hpp:555-624,1369-1500
+        template <typename T>
+        aoclsparse_status forward_solve(itsol_data<T>             *it,
+                                        aoclsparse_int             n,
+                                        aoclsparse_matrix          mat,
+                                        const aoclsparse_mat_descr descr,
+                                        const T                   *b,
+                                        T                         *x,
+                                        T                          rinfo[100],
+                                        aoclsparse_int             precond(aoclsparse_int, aoclsparse_int, const T *, T *, void *),
+                                        aoclsparse_int             monit(aoclsparse_int, const T *, const T *, T *, void *),
+                                        void                      *udata)
+        {
+            if(it == nullptr)
+                return aoclsparse_status_internal_error;
+            if(x == nullptr || rinfo == nullptr)
+                return aoclsparse_status_invalid_pointer;
+            for(int i = 0; i < 100; ++i)
+                rinfo[i] = (T)0;
+            // without callbacks nothing outside this library sees the work vectors: plain device memory
+            // (AOCLSPARSE_B200_ITSOL_MANAGED=1 keeps them managed, for measurements)
+            const char *em   = getenv("AOCLSPARSE_B200_ITSOL_MANAGED");
+            it->host_visible = precond != nullptr || monit != nullptr || (em && atoi(em) != 0);
+            const aoclsparse_status in_st = rci_input(it, n, b);
+            it->host_visible              = true; // the reverse-communication entry points always hand out managed memory
+            B200_TRY(in_st);
+            B200_TRY(solver_init(it));
+            if(mat == nullptr || descr == nullptr)
+                return aoclsparse_status_invalid_pointer;
+            if(mat->m != n || mat->n != n)
+                return aoclsparse_status_invalid_size;
+            if(descr->type != aoclsparse_matrix_type_symmetric || descr->fill_mode != aoclsparse_fill_mode_lower)
+                return aoclsparse_status_invalid_value;
+            if(it->precond == 1 && precond == nullptr)
+                return aoclsparse_status_invalid_pointer;
+            if(it->precond == 3)
+                return aoclsparse_status_not_implemented; // symmetric Gauss-Seidel: two triangular solves per iteration
+            // the symmetric product runs as a plain streaming gather on the expanded copy (spmv.cu, expand.cu)
+            if(aoclsparse_set_mv_hint(mat, aoclsparse_operation_none, descr, 100) == aoclsparse_status_success)
+                aoclsparse_optimize(mat);
+            it->solving     = true;
+            it->opts.locked = true;
+            aoclsparse_itsol_rci_job ircomm      = aoclsparse_rci_start;
+            T                       *u = nullptr, *v = nullptr;
+            const T                  one = (T)1, zero = (T)0;
+            aoclsparse_status        exit_status = aoclsparse_status_success;
+            while(ircomm != aoclsparse_rci_stop)
+            {
+                exit_status = rci_solve(it, &ircomm, &u, &v, x, rinfo);
+                if(exit_status != aoclsparse_status_success && ircomm != aoclsparse_rci_stop)
+                    break;
+                if(ircomm == aoclsparse_rci_mv)
+                {
+                    if(mv_of<T>::call(&one, mat, descr, u, &zero, v) != aoclsparse_status_success)
+                    {
+                        exit_status = aoclsparse_status_internal_error;
+                        break;
+                    }
+                }
+                else if(ircomm == aoclsparse_rci_precond)
+                {
+                    // user routine on managed memory: readable and writable from the host
+                    if(precond(0, n, u, v, udata) != 0)
+                        ircomm = aoclsparse_rci_interrupt;
+                }
+                else if(ircomm == aoclsparse_rci_stopping_criterion && monit)
+                {
+                    // monit(n, x, r, rinfo, udata): x as the caller knows it (kept up to date by cg_rci), r managed
+                    if(monit(n, it->x_user ? it->x_user : it->x_dev, u, rinfo, udata) != 0)
+                        ircomm = aoclsparse_rci_interrupt;
+                }
+            }
+            it->solving     = false;
+            it->opts.locked = false;
+            return exit_status;
+        }
+    }
+}
+
+using namespace b200;
+
+struct _aoclsparse_itsol_handle
+{
+    aoclsparse_matrix_data_type type;
+    itsol_data<float>          *s = nullptr;
+    itsol_data<double>         *d = nullptr;
+};
+
+extern "C" {
+aoclsparse_status aoclsparse_itsol_s_init(aoclsparse_itsol_handle *handle)
+{
+    if(handle == nullptr)
+        return aoclsparse_status_invalid_pointer;
+    *handle = new(std::nothrow) _aoclsparse_itsol_handle;
+    if(!*handle)
+        return aoclsparse_status_memory_error;
+    (*handle)->type = aoclsparse_smat;
+    (*handle)->s    = new(std::nothrow) itsol_data<float>;
+    if(!(*handle)->s)
+    {
+        aoclsparse_itsol_destroy(handle);
+        return aoclsparse_status_memory_error;
+    }
+    return aoclsparse_status_success;
+}
+
+aoclsparse_status aoclsparse_itsol_d_init(aoclsparse_itsol_handle *handle)
+{
+    if(handle == nullptr)
+        return aoclsparse_status_invalid_pointer;
+    *handle = new(std::nothrow) _aoclsparse_itsol_handle;
+    if(!*handle)
+        return aoclsparse_status_memory_error;
+    (*handle)->type = aoclsparse_dmat;
+    (*handle)->d    = new(std::nothrow) itsol_data<double>;
+    if(!(*handle)->d)
+    {
+        aoclsparse_itsol_destroy(handle);
+        return aoclsparse_status_memory_error;
+    }
+    return aoclsparse_status_success;
+}
+
+// complex conjugate gradients are not provided (itsol_functions.cpp:168-230 create the handles in the reference)
+aoclsparse_status aoclsparse_itsol_c_init(aoclsparse_itsol_handle *handle)
+{
+    if(handle == nullptr)
+        return aoclsparse_status_invalid_pointer;
+    *handle = nullptr;
+    return aoclsparse_status_not_implemented;
+}
+aoclsparse_status aoclsparse_itsol_z_init(aoclsparse_itsol_handle *handle)
+{
+    if(handle == nullptr)
+        return aoclsparse_status_invalid_pointer;
+    *handle = nullptr;
+    return aoclsparse_status_not_implemented;
+}
+
+void aoclsparse_itsol_destroy(aoclsparse_itsol_handle *handle)
+{
+    if(handle && *handle)
+    {
+        delete(*handle)->s;
+        delete(*handle)->d;
+        delete *handle;
+        *handle = nullptr;
+    }
+}
+
+aoclsparse_status aoclsparse_itsol_option_set(aoclsparse_itsol_handle handle, const char *option, const char *value)
+{
+    // handle_parse_option, itsol_functions.hpp:1622-1715: every failure of the registry maps to invalid_value
+    if(handle == nullptr)
+        return aoclsparse_status_invalid_pointer;
+    if((handle->type == aoclsparse_dmat && !handle->d) || (handle->type == aoclsparse_smat && !handle->s))
+        return aoclsparse_status_internal_error;
+    if(!option || !value)
+        return aoclsparse_status_invalid_pointer;
+    const std::string name = prepare(option);
+    const int         flag = handle->type == aoclsparse_dmat ? handle->d->opts.set(name, value) : handle->s->opts.set(name, value);
+    return flag == 0 ? aoclsparse_status_success : aoclsparse_status_invalid_value;
+}
+
+aoclsparse_status aoclsparse_itsol_d_rci_input(aoclsparse_itsol_handle handle, aoclsparse_int n, const double *b)
+{
+    if(!handle)
+        return aoclsparse_status_invalid_pointer;
+    if(handle->type != aoclsparse_dmat)
+        return aoclsparse_status_wrong_type;
+    return rci_input(handle->d, n, b);
+}
+aoclsparse_status aoclsparse_itsol_s_rci_input(aoclsparse_itsol_handle handle, aoclsparse_int n, const float *b)
+{
+    if(!handle)
+        return aoclsparse_status_invalid_pointer;
+    if(handle->type != aoclsparse_smat)
+        return aoclsparse_status_wrong_type;
+    return rci_input(handle->s, n, b);
+}
+
+aoclsparse_status aoclsparse_itsol_d_rci_solve(aoclsparse_itsol_handle handle, aoclsparse_itsol_rci_job *ircomm, double **u, double **v, double *x, double rinfo[100])
+{
+    if(!handle)
+        return aoclsparse_status_invalid_pointer;
+    if(handle->type != aoclsparse_dmat)
+        return aoclsparse_status_wrong_type;
+    return rci_solve(handle->d, ircomm, u, v, x, rinfo);
+}
+aoclsparse_status aoclsparse_itsol_s_rci_solve(aoclsparse_itsol_handle handle, aoclsparse_itsol_rci_job *ircomm, float **u, float **v, float *x, float rinfo[100])
+{
+    if(!handle)
+        return aoclsparse_status_invalid_pointer;
+    if(handle->type != aoclsparse_smat)
+        return aoclsparse_status_wrong_type;
+    return rci_solve(handle->s, ircomm, u, v, x, rinfo);
+}
+
+aoclsparse_status aoclsparse_itsol_d_solve(aoclsparse_itsol_handle    handle,
+                                           aoclsparse_int             n,
+                                           aoclsparse_matrix          mat,
+                                           const aoclsparse_mat_descr descr,
+                                           const double              *b,
+                                           double                    *x,
+                                           double                     rinfo[100],
+                                           aoclsparse_int precond(aoclsparse_int flag, aoclsparse_int n, const double *u, double *v, void *udata),
+                                           aoclsparse_int monit(aoclsparse_int n, const double *x, const double *r, double rinfo[100], void *udata),
+                                           void *udata)
+{
+    if(!handle)
+        return aoclsparse_status_invalid_pointer;
+    if(handle->type != aoclsparse_dmat)
+        return aoclsparse_status_wrong_type;
+    return forward_solve<double>(handle->d, n, mat, descr, b, x, rinfo, precond, monit, udata);
+}
+aoclsparse_status aoclsparse_itsol_s_solve(aoclsparse_itsol_handle    handle,
+                                           aoclsparse_int             n,
+                                           aoclsparse_matrix          mat,
+                                           const aoclsparse_mat_descr descr,
+                                           const float               *b,
+                                           float                     *x,
+                                           float                      rinfo[100],
+                                           aoclsparse_int precond(aoclsparse_int flag, aoclsparse_int n, const float *u, float *v, void *udata),
+                                           aoclsparse_int monit(aoclsparse_int n, const float *x, const float *r, float rinfo[100], void *udata),
+                                           void *udata)
+{
+    if(!handle)
+        return aoclsparse_status_invalid_pointer;
+    if(handle->type != aoclsparse_smat)
+        return aoclsparse_status_wrong_type;
+    return forward_solve<float>(handle->s, n, mat, descr, b, x, rinfo, precond, monit, udata);
+}
+}

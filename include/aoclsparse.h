@@ -594,6 +594,91 @@ DLL_PUBLIC aoclsparse_status aoclsparse_spmm(aoclsparse_operation    opA,
                                              const aoclsparse_matrix B,
                                              aoclsparse_matrix      *C);
 
+/* ------------------------------------------------------------------------------------------
+ * Conjugate gradients -- the iterated-SpMV consumer of the path.
+ * Replaces the CG part of the reference's iterative-solver suite (aoclsparse_solvers.h:114-570;
+ * library/src/solvers/aoclsparse_itsol_functions.{hpp,cpp}):
+ *   aoclsparse_itsol_{s,d}_init / aoclsparse_itsol_destroy             problem handle
+ *   aoclsparse_itsol_option_set                                          every option the reference registers
+ *       (aoclsparse_itsol_list_options.hpp:63-239: "iterative method", "cg iteration limit" [500],
+ *       "cg rel tolerance" [2 s sqrt(2 eps)], "cg abs tolerance" [s sqrt(2 eps)], "cg preconditioner",
+ *       and the gmres ones); names and string values are trimmed, blank-squeezed and case-folded
+ *       like the reference; unknown option / bad or out-of-range value -> invalid_value
+ *   aoclsparse_itsol_{s,d}_solve       forward interface: A symmetric, descriptor lower (else
+ *       invalid_value), optional user preconditioner and monitor callbacks
+ *   aoclsparse_itsol_{s,d}_rci_input / _rci_solve   reverse communication (jobs as in the reference)
+ * rinfo[0] = |A x - b|, rinfo[1] = |b|, rinfo[30] = iterations (itsol_functions.hpp:36-38).
+ * Exit codes: success, aoclsparse_status_maxit, aoclsparse_status_user_stop,
+ * aoclsparse_status_numerical_error (A not positive definite / breakdown), as in the reference.
+ * Not provided (aoclsparse_status_not_implemented): GMRES, the symmetric Gauss-Seidel
+ * preconditioner, complex handles.
+ *
+ * B200: all vector work runs on the device (csrc/itsol.cu).  b and x may be host or device arrays.
+ * The work vectors handed out through *u / *v (and passed to the callbacks) are CUDA managed memory:
+ * valid as host pointers AND as device pointers for aoclsparse_?mv.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct _aoclsparse_itsol_handle *aoclsparse_itsol_handle;
+
+/* aoclsparse_solvers.h:114-134 */
+typedef enum aoclsparse_itsol_rci_job_
+{
+    aoclsparse_rci_interrupt          = -1,
+    aoclsparse_rci_stop               = 0,
+    aoclsparse_rci_start              = 1,
+    aoclsparse_rci_mv                 = 2,
+    aoclsparse_rci_precond            = 3,
+    aoclsparse_rci_stopping_criterion = 4
+} aoclsparse_itsol_rci_job;
+
+DLL_PUBLIC aoclsparse_status aoclsparse_itsol_s_init(aoclsparse_itsol_handle *handle);
+DLL_PUBLIC aoclsparse_status aoclsparse_itsol_d_init(aoclsparse_itsol_handle *handle);
+DLL_PUBLIC aoclsparse_status aoclsparse_itsol_c_init(aoclsparse_itsol_handle *handle);
+DLL_PUBLIC aoclsparse_status aoclsparse_itsol_z_init(aoclsparse_itsol_handle *handle);
+DLL_PUBLIC void              aoclsparse_itsol_destroy(aoclsparse_itsol_handle *handle);
+DLL_PUBLIC aoclsparse_status aoclsparse_itsol_option_set(aoclsparse_itsol_handle handle,
+                                                         const char             *option,
+                                                         const char             *value);
+DLL_PUBLIC aoclsparse_status aoclsparse_itsol_d_rci_input(aoclsparse_itsol_handle handle,
+                                                          aoclsparse_int          n,
+                                                          const double           *b);
+DLL_PUBLIC aoclsparse_status aoclsparse_itsol_s_rci_input(aoclsparse_itsol_handle handle,
+                                                          aoclsparse_int          n,
+                                                          const float            *b);
+DLL_PUBLIC aoclsparse_status aoclsparse_itsol_d_rci_solve(aoclsparse_itsol_handle   handle,
+                                                          aoclsparse_itsol_rci_job *ircomm,
+                                                          double                  **u,
+                                                          double                  **v,
+                                                          double                   *x,
+                                                          double                    rinfo[100]);
+DLL_PUBLIC aoclsparse_status aoclsparse_itsol_s_rci_solve(aoclsparse_itsol_handle   handle,
+                                                          aoclsparse_itsol_rci_job *ircomm,
+                                                          float                   **u,
+                                                          float                   **v,
+                                                          float                    *x,
+                                                          float                     rinfo[100]);
+DLL_PUBLIC aoclsparse_status aoclsparse_itsol_d_solve(
+    aoclsparse_itsol_handle    handle,
+    aoclsparse_int             n,
+    aoclsparse_matrix          mat,
+    const aoclsparse_mat_descr descr,
+    const double              *b,
+    double                    *x,
+    double                     rinfo[100],
+    aoclsparse_int precond(aoclsparse_int flag, aoclsparse_int n, const double *u, double *v, void *udata),
+    aoclsparse_int monit(aoclsparse_int n, const double *x, const double *r, double rinfo[100], void *udata),
+    void *udata);
+DLL_PUBLIC aoclsparse_status aoclsparse_itsol_s_solve(
+    aoclsparse_itsol_handle    handle,
+    aoclsparse_int             n,
+    aoclsparse_matrix          mat,
+    const aoclsparse_mat_descr descr,
+    const float               *b,
+    float                     *x,
+    float                      rinfo[100],
+    aoclsparse_int precond(aoclsparse_int flag, aoclsparse_int n, const float *u, float *v, void *udata),
+    aoclsparse_int monit(aoclsparse_int n, const float *x, const float *r, float rinfo[100], void *udata),
+    void *udata);
+
 /* Read access to the CSR arrays of a handle.  Replaces aoclsparse_export_?csr
  * (aoclsparse_auxiliary.h:744-820; aoclsparse_export_csr_t, library/src/extra/
  * aoclsparse_auxiliary.cpp:1303-1350): NULL argument -> invalid_pointer, value type mismatch ->

@@ -26,6 +26,8 @@ sys.path.insert(0, os.path.join(ROOT, "aocl-sparse_b200"))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import capi  # noqa: E402
 import gen_np  # noqa: E402
+sys.path.insert(0, HERE)
+from make_golden_itsol import itsol_cases, itsol_matrix, run_itsol_case, itsol_status_table  # noqa: E402
 from conftest import TOL, apply_op, effective_dense, mv_denominator, rel_err  # noqa: E402
 
 REF = capi.AoclSparse(os.path.join(ROOT, "oracle", "_ref", "libaoclsparse_ref.so"))
@@ -586,6 +588,23 @@ def sp2m_sweep(rng):
     print("sp2m sweep:", idx, "cases; statuses", Counter(c["status"] for c in meta), "; status table", res)
 
 
+def itsol_sweep():
+    """conjugate gradients of the reference's own build (oracle/_ref with the BLAS stand-ins of oracle/shim/blas): status,
+    rinfo (residual norm, |b|, iterations), solution and the per-iteration residual norms seen by the monitor"""
+    out, meta = {}, []
+    for c in itsol_cases():
+        status, rinfo, x, trace, b = run_itsol_case(REF, c)
+        out[c["key"] + "_x"] = x
+        out[c["key"] + "_trace"] = np.array(trace, dtype=np.float64).reshape(-1, 2)
+        meta.append(dict(c, status=int(status), res=float(rinfo[0]), bnorm=float(rinfo[1]), iters=int(rinfo[30])))
+    res = itsol_status_table(REF)
+    np.savez_compressed(os.path.join(HERE, "ref_itsol.npz"), **out)
+    json.dump(dict(cases=meta, status=res), open(os.path.join(HERE, "ref_itsol.json"), "w"), indent=0)
+    from collections import Counter
+    print("itsol sweep:", len(meta), "cases; statuses", Counter(m["status"] for m in meta), "iterations",
+          [m["iters"] for m in meta], "; status table", res)
+
+
 def create_table(rng):
     """status / sort / fulldiag of the reference's create on valid, unsorted and corrupted inputs"""
     cases = []
@@ -737,6 +756,9 @@ if __name__ == "__main__":
     if "--only-csc" in sys.argv:
         csc_sweep(np.random.default_rng(69070))
         sys.exit(0)
+    if "--only-itsol" in sys.argv:
+        itsol_sweep()
+        sys.exit(0)
     if "--only-sp2m" in sys.argv:
         sp2m_sweep(np.random.default_rng(69071))
         sys.exit(0)
@@ -752,4 +774,5 @@ if __name__ == "__main__":
     status_table()
     csc_sweep(np.random.default_rng(69070))
     sp2m_sweep(np.random.default_rng(69071))
+    itsol_sweep()
     print("golden fixtures written to", HERE)

@@ -43,9 +43,18 @@ def test_enum_values_match_reference_header():
         return
     ours = open(os.path.join(ROOT, "include", "aoclsparse.h")).read()
     theirs = open(ref).read()
-    pat = re.compile(r"\b(aoclsparse_[a-z0-9_]+)\s*=\s*(\d+)")
+    pat = re.compile(r"\b(aoclsparse_[a-z0-9_]+)\s*=\s*(-?\d+)")
     a, b = dict(pat.findall(ours)), dict(pat.findall(theirs))
     assert len(a) > 40
+    # the reverse-communication jobs number themselves implicitly in the reference (aoclsparse_solvers.h:114-134:
+    # interrupt = -1, stop = 0, then start, mv, precond, stopping_criterion)
+    solvers = open(os.path.join(os.path.dirname(ref), "aoclsparse_solvers.h")).read()
+    body = solvers[solvers.index("typedef enum aoclsparse_itsol_rci_job_"):solvers.index("} aoclsparse_itsol_rci_job;")]
+    body = re.sub(r"///<.*", "", body)
+    names = re.findall(r"\b(aoclsparse_rci_[a-z_]+)", body)
+    assert names[:2] == ["aoclsparse_rci_interrupt", "aoclsparse_rci_stop"]
+    for i, nme in enumerate(names):
+        b[nme] = str(i - 1)
     for k, v in a.items():
         assert b.get(k) == v, (k, v, b.get(k))
 
