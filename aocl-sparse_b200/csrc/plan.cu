@@ -40,6 +40,10 @@ namespace b200
         // which measured best on the 27-point stencil (profiles/r01_sweep_c2.txt): 2048 entries for 8-byte
         // values, 3072 for 4-byte, 1024 for 16-byte
         aoclsparse_int T = (aoclsparse_int)((24576 / (elem_size + 4)) / 512 * 512);
+        // 16-byte values (double complex): 1536 entries (30 KB) measured best on the 27-point stencil, together with
+        // 128-thread CTAs (build_plan): 4 109 -> 5 779 GB/s (tools/z_sweep.py, profiles/r01_summary.md)
+        if(elem_size >= 16)
+            T = 1536;
         // skewed row lengths (longest row > 16x the mean): x[col] is a random gather and the multiply is bound by
         // L1 misses (profiles/r01_microbench_gather.txt: 0.9 sectors/clk/SM on a miss, 2.7 on a hit), so leave
         // more of the 228 KB to L1: ~16 KB staged per CTA (profiles/r01_sweep_c3.txt: 1.09 ms vs 2.03 ms on R-MAT)
@@ -290,6 +294,13 @@ namespace b200
         plan_parameters(elem_size, A.m, A.nnz, max_row_nnz, P.block_nnz, P.block_rows);
         if(block_nnz_override > 0)
             P.block_nnz = block_nnz_override;
+        // few rows per block (long rows or wide values): the thread-per-row strategy keeps only one lane per row busy, so
+        // smaller CTAs put more of them -- hence more rows in flight -- on an SM
+        {
+            const long long mean = A.m > 0 ? (long long)A.nnz / A.m : 0;
+            if(mean > 0 && (long long)P.block_nnz / mean <= 64)
+                P.threads = 128;
+        }
         if(const char *e = getenv("AOCLSPARSE_B200_THREADS"))
         {
             const int v = atoi(e);

@@ -391,6 +391,8 @@ void oracle_plan_parameters(int elem_size, int m, int nnz, int max_row_nnz, cons
                             int *T, int *R)
 {
     int             t    = (24576 / (elem_size + 4)) / 512 * 512;
+    if(elem_size >= 16)
+        t = 1536; /* 16-byte values: measured best, with 128-thread CTAs */
     const long long mean = m > 0 ? (long long)nnz / m : 0;
     if((long long)max_row_nnz > 16 * (mean > 1 ? mean : 1))
         t = (16384 / (elem_size + 4)) / 512 * 512;
