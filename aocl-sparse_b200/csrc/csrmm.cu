@@ -24,7 +24,7 @@ namespace b200
     namespace
     {
         constexpr int MM_THREADS = 256;
-        constexpr int COL_TILE   = 4;
+        constexpr int COL_TILE   = 8;
 
         // ROW_MAJOR: B is (k x n) with row stride ldb, C is (m x n) with row stride ldc
         template <typename T, bool CONJ>
@@ -589,15 +589,35 @@ namespace b200
 
             if(strat == STRAT_THREAD)
             {
-                for(int r = d.x + tid; r < d.y; r += MM_THREADS)
+                // work item = (row, tile of COL_TILE columns of B / C); consecutive threads take consecutive rows of the
+                // same tile, so the gathers B[col + j*ldb] of a warp fall into a few lines (banded matrices) and every
+                // thread of the CTA is busy even when the block holds fewer rows than threads
+                const int nrows = d.y - d.x;
+                const int tiles = (n + COL_TILE - 1) / COL_TILE;
+                for(int item = tid; item < nrows * tiles; item += MM_THREADS)
                 {
+                    const int r  = d.x + item % nrows;
+                    const int j0 = (item / nrows) * COL_TILE;
                     const int s = rp[r] - a, e = rp[r + 1] - a;
-                    for(int j0 = 0; j0 < n; j0 += COL_TILE)
-                    {
-                        T acc[COL_TILE];
+                    T         acc[COL_TILE];
 #pragma unroll
-                        for(int q = 0; q < COL_TILE; ++q)
-                            acc[q] = vt<T>::zero();
+                    for(int q = 0; q < COL_TILE; ++q)
+                        acc[q] = vt<T>::zero();
+                    if(j0 + COL_TILE <= n)
+                    {
+                        for(int j = s; j < e; ++j)
+                        {
+                            T v = sval[j];
+                            if(CONJ)
+                                v = cj(v);
+                            const T *bp = B + scol[j] + (long long)j0 * ldb;
+#pragma unroll
+                            for(int q = 0; q < COL_TILE; ++q)
+                                acc[q] = mad(v, ldg_ro(bp + (long long)q * ldb), acc[q]);
+                        }
+                    }
+                    else
+                    {
                         for(int j = s; j < e; ++j)
                         {
                             T v = sval[j];
@@ -609,14 +629,14 @@ namespace b200
                                 if(j0 + q < n)
                                     acc[q] = mad(v, ldg_ro(bp + (long long)q * ldb), acc[q]);
                         }
-#pragma unroll
-                        for(int q = 0; q < COL_TILE; ++q)
-                            if(j0 + q < n)
-                            {
-                                T *cp = C + r + (long long)(j0 + q) * ldc;
-                                *cp   = axpby_out(alpha, acc[q], beta, beta_zero != 0, cp);
-                            }
                     }
+#pragma unroll
+                    for(int q = 0; q < COL_TILE; ++q)
+                        if(j0 + q < n)
+                        {
+                            T *cp = C + r + (long long)(j0 + q) * ldc;
+                            *cp   = axpby_out(alpha, acc[q], beta, beta_zero != 0, cp);
+                        }
                 }
             }
             else if(strat != STRAT_LONG)
