@@ -431,6 +431,7 @@ struct _aoclsparse_matrix
     aoclsparse_int                min_col = 0, max_col = -1, max_row_nnz = 0;
     aoclsparse_memory_usage       mem_policy = aoclsparse_memory_usage_unrestricted;
     int                           device     = 0;
+    std::atomic<int>              lazy_copy_calls{0};   // un-hinted products that would profit from a derived copy (spmv.cu)
     bool                          want_grouped = false; // a mm hint on the stored matrix was optimized (group.cu)
     bool                          is_csc     = false; // created from CSC arrays: mats[0] stores the TRANSPOSE (n x m CSR)
 

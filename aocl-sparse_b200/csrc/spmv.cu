@@ -263,6 +263,11 @@ namespace b200
     }
 
     // The device-side multiply, x and y already device accessible.
+    // calls of an un-hinted transposed / symmetric / hermitian product on one handle after which the derived copy is built.
+    // Building it costs about as much as a hundred products save (a device sort of all entries, ~25 ms on 56 M entries
+    // against 0.2-0.3 ms saved per product), so only a handle that is clearly being iterated on gets one.
+    constexpr int LAZY_COPY_AFTER = 32;
+
     template <typename T>
     aoclsparse_status mv_device(aoclsparse_operation       op,
                                 T                          alpha,
@@ -287,6 +292,11 @@ namespace b200
                 for(const hint &h : A->hints)
                     hinted = hinted || (h.act == 1 && h.doid == d_id && h.done);
             }
+            // no hint, but the same kind of product keeps coming: build the copy after a few calls, as the reference's
+            // mv lazily builds its optimised CSR (csr_util.hpp:812-825).  Gather + atomic scatter costs ~3.7x the
+            // streaming gather on the 27-point stencil (profiles/r01_mm_sweep.txt).
+            if(!hinted && A->lazy_copy_calls.fetch_add(1, std::memory_order_relaxed) + 1 >= LAZY_COPY_AFTER)
+                hinted = true;
             if(hinted)
             {
                 const dev_csr *F = nullptr;
@@ -294,6 +304,41 @@ namespace b200
                 std::shared_lock<std::shared_mutex> rl1(A->guard);
                 elem_rule none_rule{MASK_NONE, DIAG_KEEP, 0, 0};
                 return launch_gather<T>(*F, 0, F->plan.n_blocks, 0, F->m, x, y, alpha, beta, false, none_rule, st);
+            }
+        }
+        // un-hinted transposed general products: same lazy policy, a transposed copy turns the atomic scatter into a gather
+        if(descr.type == aoclsparse_matrix_type_general && A->mem_policy == aoclsparse_memory_usage_unrestricted && A->win_hi < 0
+           && (op != aoclsparse_operation_none) != A->is_csc)
+        {
+            const int want = (vt<T>::is_complex && op == aoclsparse_operation_conjugate_transpose) ? DOID_GH : DOID_GT;
+            bool      have = false;
+            {
+                std::shared_lock<std::shared_mutex> rl0(A->guard);
+                for(size_t i = 1; i < A->mats.size(); ++i)
+                    have = have || (A->mats[i]->doid == want && A->mats[i]->plan.valid);
+            }
+            if(!have && A->lazy_copy_calls.fetch_add(1, std::memory_order_relaxed) + 1 >= LAZY_COPY_AFTER)
+            {
+                std::unique_lock<std::shared_mutex> wl(A->guard);
+                for(size_t i = 1; i < A->mats.size(); ++i)
+                    have = have || (A->mats[i]->doid == want && A->mats[i]->plan.valid);
+                if(!have)
+                {
+                    dev_csr *C = new(std::nothrow) dev_csr;
+                    if(C)
+                    {
+                        aoclsparse_status s = transpose_csr(*A->mats[0], A->val_type, want == DOID_GH, *C, st);
+                        if(s == aoclsparse_status_success)
+                            s = build_plan(*C, sizeof(T), -1, -1, std::vector<aoclsparse_int>(), st);
+                        if(s == aoclsparse_status_success)
+                        {
+                            C->doid = want;
+                            A->mats.push_back(C);
+                        }
+                        else
+                            delete C; // no room: keep scattering
+                    }
+                }
             }
         }
         std::shared_lock<std::shared_mutex> rl(A->guard);

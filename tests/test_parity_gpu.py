@@ -602,6 +602,36 @@ def test_csc_create_validation(lib):
     lib.destroy_descr(d)
 
 
+def test_lazy_copies_for_repeated_unhinted_products(lib, oracle):
+    """a handle that keeps being multiplied transposed / as a symmetric matrix WITHOUT hints gets the derived copy after
+    32 such calls (spmv.cu LAZY_COPY_AFTER); results before and after agree with the oracle; the minimal memory policy
+    never builds one"""
+    rng = np.random.default_rng(91)
+    m = 500
+    rp, col, val = gen_np.random_csr(rng, m, m, 0.03, np.float64, "full", ensure_diag=True, base=0)
+    x = rng.normal(size=m)
+    for policy_minimal in (False, True):
+        st, h = lib.create_csr("d", 0, m, m, len(col), rp, col, val)
+        assert st == 0
+        if policy_minimal:
+            assert lib.set_memory_hint(h, 0) == 0  # aoclsparse_memory_usage_minimal
+        for mtype, op in ((0, 112), (1, 111)):
+            d = lib.create_descr(mtype, 0, 0, 0)
+            yo = np.zeros(m)
+            oracle.csrmv(op, 1.0, m, m, 0, rp, col, val, mtype, 0, 0, x, 0.0, yo)
+            c_ = dict(m=m, n=m, base=0, type=mtype, fill=0, diag=0, op=op, alpha=1.0, beta=0.0)
+            den = mv_denominator(c_, rp, col, val, x, yo)
+            before = lib.matrix_info(h).n_copies
+            for k in range(40):
+                y = np.zeros(m)
+                assert lib.mv("d", op, 1.0, h, d, x, 0.0, y) == 0, lib.last_error()
+                assert rel_err(y, yo, den) <= 1e-12, (mtype, op, k)
+            after = lib.matrix_info(h).n_copies
+            assert after == (before if policy_minimal else before + 1), (policy_minimal, mtype, before, after)
+            lib.destroy_descr(d)
+        lib.destroy(h)
+
+
 def test_concurrent_mv_on_one_handle(lib, oracle):
     """tests/examples/sample_spmv_multi_instance.c:49-88: 4 threads x 10 calls on one handle"""
     rp, col, val = gen_np.stencil(27, 16, 16, 16)

@@ -18,7 +18,7 @@ TY = {"s": (np.float32, 4), "d": (np.float64, 8), "c": (np.complex64, 8), "z": (
 
 def timeit(fn, reps):
     import torch
-    for _ in range(3):
+    for _ in range(40):  # past the lazy-copy threshold of un-hinted transposed / symmetric products
         assert fn() == 0
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
