@@ -632,6 +632,23 @@ def test_lazy_copies_for_repeated_unhinted_products(lib, oracle):
         lib.destroy(h)
 
 
+def test_c_example_program(tmp_path):
+    """examples/spmv_c.c -- the reference's sample call sequence from plain C -- compiles against include/aoclsparse.h,
+    links against the library and prints the sample's result (tests/examples/sample_spmv_c.c:40-60)"""
+    import shutil
+    import subprocess
+    from conftest import ROOT
+    cc = shutil.which("gcc") or shutil.which("cc") or "/usr/bin/gcc"
+    exe = str(tmp_path / "spmv_c")
+    libdir = os.path.dirname(capi.LIB_PATH)
+    subprocess.run([cc, os.path.join(ROOT, "examples", "spmv_c.c"), "-I", os.path.join(ROOT, "include"), "-L", libdir,
+                    "-laoclsparse_b200", f"-Wl,-rpath,{libdir}", "-o", exe], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert [l for l in out.stdout.splitlines() if l.startswith("y[")] == [
+        "y[0] = 9", "y[1] = 6", "y[2] = 12", "y[3] = 69", "y[4] = 40"]
+
+
 def test_concurrent_mv_on_one_handle(lib, oracle):
     """tests/examples/sample_spmv_multi_instance.c:49-88: 4 threads x 10 calls on one handle"""
     rp, col, val = gen_np.stencil(27, 16, 16, 16)
