@@ -297,3 +297,31 @@ def test_csr2csc_arrays(lib):
     assert lib.csr2csc("d", 1, 1, 1, d, 0, zi, zi, None, zi, cp, z) == ST["invalid_pointer"]
     assert lib.csr2csc("d", 1, 1, 1, d, 3, zi, zi, z, zi, cp, z) == ST["invalid_value"]
     lib.destroy_descr(d)
+
+
+def test_sp2m_power_law_matrix(lib, oracle):
+    """R-MAT (scale 15, edge factor 16) squared: hub rows with up to ~10^6 products next to thousands of tiny rows --
+    every tier at once, global-memory tables in several batches; structure bit-exact against the oracle's Gustavson pass"""
+    rp, col, val = gen_np.rmat_csr(15, dtype=np.float64)
+    n = len(rp) - 1
+    A = sp.csr_matrix((val, col, rp), shape=(n, n))
+    st, h = lib.create_csr("d", 0, n, n, len(col), rp, col, val)
+    assert st == 0, lib.last_error()
+    st, hC = lib.spmm(111, h, h)
+    assert st == 0, lib.last_error()
+    st, base, m, nc, nnz, crp, ccol, cval = lib.export_csr("d", hC)
+    assert st == 0 and (m, nc) == (n, n)
+    rc, rpo, colo, valo = oracle.csr2m(n, n, 0, rp, col, val, 0, 0, rp, col, val, 0)
+    assert rc == 0
+    colo, valo = canonical_rows(rpo, colo, valo)
+    assert np.array_equal(crp, rpo) and np.array_equal(ccol, colo)
+    D = (abs(A) @ abs(A)).tocsr()
+    D.sort_indices()
+    assert np.array_equal(D.indptr, crp)
+    assert rel_err(cval, valo, D.data) <= 4e-12
+    lens = np.diff(crp)
+    products = np.diff(rp)[col]
+    per_row = np.add.reduceat(products, rp[:-1][np.diff(rp) > 0]) if len(col) else np.zeros(0)
+    assert per_row.max() > 6144 and lens.max() > 1024  # the global and the bitonic paths were really taken
+    lib.destroy(hC)
+    lib.destroy(h)
