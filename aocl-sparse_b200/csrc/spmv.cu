@@ -8,6 +8,7 @@
 #include "spmv_pipelined.cuh"
 #include "spmv_sharded.cuh"
 
+#include <chrono>
 #include <cstdlib>
 #include <unordered_map>
 
@@ -512,7 +513,8 @@ namespace b200
         {
             cudaStream_t h2d = nullptr, d2h = nullptr;
             cudaEvent_t  ev_x[16] = {}, ev_k[16] = {}, ev_start = nullptr;
-            bool         ready = false;
+            cudaEvent_t  tr_x[16] = {}, tr_k[16] = {}, tr_y[16] = {}, tr_0 = nullptr; // AOCLSPARSE_B200_HOST_TRACE=1 only
+            bool         ready = false, trace = false;
             aoclsparse_status init()
             {
                 if(ready)
@@ -525,6 +527,17 @@ namespace b200
                     B200_CUDA(cudaEventCreateWithFlags(&ev_k[i], cudaEventDisableTiming));
                 }
                 B200_CUDA(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
+                trace = getenv("AOCLSPARSE_B200_HOST_TRACE") && atoi(getenv("AOCLSPARSE_B200_HOST_TRACE")) != 0;
+                if(trace)
+                {
+                    B200_CUDA(cudaEventCreate(&tr_0));
+                    for(int i = 0; i < 16; ++i)
+                    {
+                        B200_CUDA(cudaEventCreate(&tr_x[i]));
+                        B200_CUDA(cudaEventCreate(&tr_k[i]));
+                        B200_CUDA(cudaEventCreate(&tr_y[i]));
+                    }
+                }
                 ready = true;
                 return aoclsparse_status_success;
             }
@@ -566,11 +579,17 @@ namespace b200
             const bool        direct_ok = getenv("AOCLSPARSE_B200_HOST_DIRECT") && atoi(getenv("AOCLSPARSE_B200_HOST_DIRECT")) != 0;
             T                *y_direct  = (bz && direct_ok) ? static_cast<T *>(pinned_host_device_ptr(hy)) : nullptr;
             // the side streams start after whatever the caller's stream was doing
+            const auto host_t0 = std::chrono::steady_clock::now();
+            if(hp.trace)
+                B200_CUDA(cudaEventRecord(hp.tr_0, st));
             B200_CUDA(cudaEventRecord(hp.ev_start, st));
             B200_CUDA(cudaStreamWaitEvent(hp.h2d, hp.ev_start, 0));
             B200_CUDA(cudaStreamWaitEvent(hp.d2h, hp.ev_start, 0));
             const int nc    = (int)P.host_chunks.size();
             int       x_lo  = 0;
+            // one loop: the copy of chunk c's slice of x is followed at once by chunk c's kernel and read-back, so the
+            // first kernel is already queued when its data lands (enqueueing all copies first cost ~30 us of start-up;
+            // profiles/r01_summary.md, host-resident vectors)
             for(int c = 0; c < nc; ++c)
             {
                 const auto &h   = P.host_chunks[c];
@@ -582,10 +601,8 @@ namespace b200
                     B200_CUDA(cudaMemcpyAsync(
                         dy + h.row0, hy + h.row0, (size_t)(h.row1 - h.row0) * sizeof(T), cudaMemcpyHostToDevice, hp.h2d));
                 B200_CUDA(cudaEventRecord(hp.ev_x[c], hp.h2d));
-            }
-            for(int c = 0; c < nc; ++c)
-            {
-                const auto &h = P.host_chunks[c];
+                if(hp.trace)
+                    B200_CUDA(cudaEventRecord(hp.tr_x[c], hp.h2d));
                 B200_CUDA(cudaStreamWaitEvent(st, hp.ev_x[c], 0));
                 if(y_direct)
                 {
@@ -594,14 +611,34 @@ namespace b200
                 }
                 B200_TRY(launch_gather<T>(M, h.b0, h.b1, h.row0, h.row1, dx, dy, alpha, beta, false, none_rule, st));
                 B200_CUDA(cudaEventRecord(hp.ev_k[c], st));
+                if(hp.trace)
+                    B200_CUDA(cudaEventRecord(hp.tr_k[c], st));
                 B200_CUDA(cudaStreamWaitEvent(hp.d2h, hp.ev_k[c], 0));
                 if(h.row1 > h.row0)
                     B200_CUDA(cudaMemcpyAsync(
                         hy + h.row0, dy + h.row0, (size_t)(h.row1 - h.row0) * sizeof(T), cudaMemcpyDeviceToHost, hp.d2h));
+                if(hp.trace)
+                    B200_CUDA(cudaEventRecord(hp.tr_y[c], hp.d2h));
             }
+            const auto host_t1 = std::chrono::steady_clock::now();
             if(!y_direct)
                 B200_CUDA(cudaStreamSynchronize(hp.d2h));
             B200_CUDA(cudaStreamSynchronize(st));
+            if(hp.trace && !y_direct)
+            {
+                const auto host_t2 = std::chrono::steady_clock::now();
+                fprintf(stderr, "[host pipe] enqueue %.1f us, total %.1f us on the host; device times since start (us):\n",
+                        std::chrono::duration<double, std::micro>(host_t1 - host_t0).count(),
+                        std::chrono::duration<double, std::micro>(host_t2 - host_t0).count());
+                for(int c = 0; c < nc; ++c)
+                {
+                    float tx = 0, tk = 0, ty = 0;
+                    cudaEventElapsedTime(&tx, hp.tr_0, hp.tr_x[c]);
+                    cudaEventElapsedTime(&tk, hp.tr_0, hp.tr_k[c]);
+                    cudaEventElapsedTime(&ty, hp.tr_0, hp.tr_y[c]);
+                    fprintf(stderr, "   chunk %d: x arrived %7.1f  kernel done %7.1f  y delivered %7.1f\n", c, tx * 1e3, tk * 1e3, ty * 1e3);
+                }
+            }
             done = true;
             return aoclsparse_status_success;
         }
