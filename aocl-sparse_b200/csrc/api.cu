@@ -684,6 +684,8 @@ aoclsparse_status aoclsparse_b200_get_matrix_info(const aoclsparse_matrix A, aoc
         info->group_entries    = A->mats[0]->grouped ? A->mats[0]->grouped->nnz : 0;
         info->group_blocks     = A->mats[0]->grouped ? A->mats[0]->grouped->plan.n_blocks : 0;
         info->group_block_nnz  = A->mats[0]->grouped ? A->mats[0]->grouped->plan.block_nnz : 0;
+        info->mm_tile_state    = A->mats[0]->tiles_state;
+        info->mm_tile_max_rows = A->mats[0]->tiles ? A->mats[0]->tiles->max_uniq : 0;
         info->hot_mass_ppm     = (aoclsparse_int)(P.hot_mass * 1e6);
     }
     return aoclsparse_status_success;

@@ -377,6 +377,20 @@ namespace b200
         bool           valid = false;
     };
 
+    // csrmm, row-major: per small row block the distinct columns it names (as runs of consecutive columns) and, per stored
+    // entry, the slot of its column in that list -- the kernel stages the named B rows once into shared memory with TMA
+    // and multiplies out of it (csrmm.cu, "tiled" kernel)
+    struct mm_tiles
+    {
+        aoclsparse_int block_nnz = 0; // entries per row block of this plan
+        row_block_plan plan;
+        dev_buf        run_ptr;       // int[n_blocks + 1]
+        dev_buf        runs;          // int4 per run: first column, slot of that column, length, unused
+        dev_buf        uniq;          // int[n_blocks]: distinct columns of the block
+        dev_buf        lidx;          // uint16 per stored entry
+        aoclsparse_int max_uniq = 0;
+    };
+
     // one device-resident CSR (always 0-based on the device)
     struct dev_csr
     {
@@ -388,6 +402,9 @@ namespace b200
         // mask << 27, val = K values per entry.  group_k: 0 not analysed yet, -1 analysed and not used, else K.
         std::unique_ptr<dev_csr> grouped;
         int                      group_k = 0;
+        // tile plan of the row-major csrmm kernel: 0 not analysed, -1 analysed and not usable, else its block size
+        std::unique_ptr<mm_tiles> tiles;
+        int                       tiles_state = 0;
     };
 
     // "clean CSR" of the reference's analysis (clean.cu): rows grouped lower | diagonal | upper, diagonals present

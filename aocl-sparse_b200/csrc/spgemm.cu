@@ -1238,8 +1238,10 @@ aoclsparse_status aoclsparse_order_mat(aoclsparse_matrix mat)
     mat->mats.resize(1);
     mat->clean = clean_csr();
     M.grouped.reset();
-    M.group_k    = 0;
-    M.plan.valid = false;
+    M.group_k     = 0;
+    M.tiles.reset();
+    M.tiles_state = 0;
+    M.plan.valid  = false;
     for(auto &h : mat->hints)
         h.done = false;
     mat->sort = aoclsparse_fully_sorted;

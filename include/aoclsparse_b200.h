@@ -56,6 +56,8 @@ typedef struct aoclsparse_b200_matrix_info_
     aoclsparse_int group_entries;   /* its entries = sum over groups of the distinct columns in the group       */
     aoclsparse_int group_blocks;    /* its row blocks                                                           */
     aoclsparse_int group_block_nnz; /* entries staged per block                                                 */
+    aoclsparse_int mm_tile_state;   /* tiled csrmm plan: 0 not analysed, -1 not usable, else entries per row block */
+    aoclsparse_int mm_tile_max_rows; /* most distinct B rows any of its blocks stages                           */
 } aoclsparse_b200_matrix_info;
 
 /* value type of a handle (aoclsparse_matrix_data_type), -1 for NULL */

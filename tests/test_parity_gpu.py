@@ -1057,6 +1057,75 @@ def test_csrmm_row_grouped_copy(lib, oracle, p, k, monkeypatch):
     lib.destroy_descr(d)
 
 
+@pytest.mark.parametrize("p", ["d", "s", "z", "c"])
+def test_csrmm_tiled_kernel(lib, oracle, p, monkeypatch):
+    """(experiment, enabled by AOCLSPARSE_B200_MM_TILES=1) row-major csrmm on a hinted mesh matrix runs the tiled kernel (B rows staged once per row block by TMA): several
+    widths, tight and padded leading dimensions, beta = 0 / != 0, against the exact product; matrices whose blocks name
+    scattered columns keep the plain kernel; values may be replaced without re-analysis"""
+    import scipy.sparse as sp
+    monkeypatch.setenv("AOCLSPARSE_B200_MM_TILES", "1")
+    dt = DT[p]
+    tol = TOL[np.dtype(dt)]
+    cplx = p in "cz"
+    rng = np.random.default_rng(123)
+    rp, col, _ = gen_np.stencil(27, 20, 19, 18)
+    m = len(rp) - 1
+    val = rng.normal(size=len(col)).astype(dt)
+    if cplx:
+        val = (val + 1j * rng.normal(size=len(col))).astype(dt)
+    A = sp.csr_matrix((val, col, rp), shape=(m, m))
+    Aabs = abs(A)
+    st, h = lib.create_csr(p, 0, m, m, len(col), rp, col, val)
+    assert st == 0
+    d = lib.create_descr()
+    assert lib.set_mm_hint(h, 111, d, 100) == 0 and lib.optimize(h) == 0, lib.last_error()
+    vec = 16 // np.dtype(dt).itemsize
+    first = True
+    for n in (2 * vec, 32, 40):
+        for pad in (0, vec):
+            for alpha, beta in ((1.0, 0.0), (-0.5, 2.0)):
+                ld = n + pad
+                B = rng.normal(size=m * ld).astype(dt)
+                C0 = rng.normal(size=m * ld).astype(dt)
+                if cplx:
+                    B = (B + 1j * rng.normal(size=m * ld)).astype(dt)
+                Cm = C0.copy() if beta != 0 else np.full(m * ld, np.nan, dt)
+                assert lib.csrmm(p, 111, alpha, h, d, 0, B, n, ld, beta, Cm, ld) == 0, lib.last_error()
+                if first:
+                    info = lib.matrix_info(h)
+                    assert info.mm_tile_state == 512 and 0 < info.mm_tile_max_rows <= 512, (info.mm_tile_state, info.mm_tile_max_rows)
+                    first = False
+                Bd, C0d, Cd = (M.reshape(m, ld)[:, :n] for M in (B, C0, Cm))
+                want = alpha * (A @ Bd.astype(np.complex128))
+                den = abs(alpha) * (Aabs @ np.abs(Bd))
+                if beta != 0:
+                    want = want + beta * C0d
+                    den = den + abs(beta) * np.abs(C0d)
+                assert rel_err(Cd, want, den) <= 4 * tol, (p, n, pad, alpha)
+                if beta != 0 and pad:
+                    assert np.array_equal(Cm.reshape(m, ld)[:, n:], C0.reshape(m, ld)[:, n:])  # padding untouched
+    # new values, same pattern: the tile plan stays
+    val2 = (val * 2).astype(dt)
+    assert lib.update_values(p, h, len(val2), val2) == 0
+    n = 32
+    B = rng.normal(size=m * n).astype(dt)
+    Cm = np.zeros(m * n, dt)
+    assert lib.csrmm(p, 111, 1.0, h, d, 0, B, n, n, 0.0, Cm, n) == 0
+    assert lib.matrix_info(h).mm_tile_state == 512
+    assert rel_err(Cm.reshape(m, n), 2 * (A @ B.reshape(m, n).astype(np.complex128)), 2 * (Aabs @ np.abs(B.reshape(m, n)))) <= 4 * tol
+    lib.destroy(h)
+    # scattered columns: analysed, not used
+    rp, col, val = gen_np.random_csr(rng, 5000, 5000, 0.004, dt, "full", base=0)
+    st, h = lib.create_csr(p, 0, 5000, 5000, len(col), rp, col, val)
+    assert lib.set_mm_hint(h, 111, d, 100) == 0 and lib.optimize(h) == 0
+    B = rng.normal(size=5000 * 32).astype(dt)
+    Cm = np.zeros(5000 * 32, dt)
+    assert lib.csrmm(p, 111, 1.0, h, d, 0, B, 32, 32, 0.0, Cm, 32) == 0
+    assert lib.matrix_info(h).mm_tile_state == -1
+    lib.destroy(h)
+    lib.destroy_descr(d)
+
+
 @pytest.mark.parametrize("p", ["s", "d", "c", "z"])
 def test_csrmm_vector_paths(lib, oracle, p):
     """row-major csrmm: every lanes-per-row variant of the 128-bit kernel, the scalar fallback (odd n, padded /
