@@ -263,3 +263,35 @@ class PeerHalo:
                 d = self.left_push_dst(which) if nb < s.rank else self.right_push_dst(which)
                 assert self.lib.memcpy(d, self.own_ptr(which) + src_off * e, h * e) == 0, self.lib.last_error()
         torch.cuda.synchronize()
+
+
+class TransposedPlan:
+    """y = A^T x on row shards ("transposed op"): rank r owns rows [cuts[r], cuts[r+1]) of A and the matching
+    slice of x; its shard contributes a FULL-length partial vector A_r^T x_r, and a reduce-scatter leaves every rank with
+    its slice of y (column range [ycuts[r], ycuts[r+1]) of A).  reduce_scatter_tensor wants equal slices, so the partial
+    vector is laid out in `world` padded slots of the longest slice."""
+
+    def __init__(self, ycuts, rank, dtype, device, group=None):
+        import torch
+        self.ycuts, self.rank, self.world, self.group = list(ycuts), rank, len(ycuts) - 1, group
+        self.lens = [b - a for a, b in zip(self.ycuts, self.ycuts[1:])]
+        self.max_len = max(max(self.lens), 1)
+        self.partial = torch.zeros(self.ycuts[-1], dtype=dtype, device=device)       # A_r^T x_r, natural layout
+        self.padded = torch.zeros(self.max_len * self.world, dtype=dtype, device=device)
+        self.out = torch.zeros(self.max_len, dtype=dtype, device=device)
+
+    def reduce(self):
+        """sums the ranks' partial vectors; returns this rank's slice of y (a view of an internal buffer)"""
+        if self.world == 1:
+            return self.partial
+        self.padded.zero_()
+        for r in range(self.world):
+            if self.lens[r]:
+                self.padded[r * self.max_len: r * self.max_len + self.lens[r]] = self.partial[self.ycuts[r]: self.ycuts[r + 1]]
+        if dist.get_backend(self.group) == "gloo":
+            # gloo has no reduce_scatter: all-reduce the padded vector and keep the own slot
+            dist.all_reduce(self.padded, group=self.group)
+            self.out.copy_(self.padded[self.rank * self.max_len: (self.rank + 1) * self.max_len])
+        else:
+            dist.reduce_scatter_tensor(self.out, self.padded, group=self.group)
+        return self.out[: self.lens[self.rank]]

@@ -143,6 +143,17 @@ def main():
     assert err <= 1e-5 * giters, ("allgather", err)
     per_rank = np.diff(G.indptr[cuts])
     assert per_rank.max() - per_rank.min() <= 2 * int(deg.max())
+    # (e) transposed product on the same row shards: full-length partial vectors, NCCL reduce-scatter
+    ycuts = [ng * r // world for r in range(world + 1)]
+    tplan = sharding.TransposedPlan(ycuts, rank, torch.float32, "cuda")
+    x_own = torch.from_numpy(xg0[plan.row_lo: plan.row_hi].copy()).cuda()
+    assert lib.mv("s", 112, 1.0, Ag2, d, x_own.data_ptr(), 0.0, tplan.partial.data_ptr()) == 0, lib.last_error()
+    y_own = tplan.reduce()
+    torch.cuda.synchronize()
+    want_t = (G64.T @ xg0.astype(np.float64))[ycuts[rank]: ycuts[rank + 1]]
+    den_t = (Gabs.T @ np.abs(xg0.astype(np.float64)))[ycuts[rank]: ycuts[rank + 1]]
+    err_t = float(np.max(np.abs(y_own.cpu().numpy().astype(np.float64) - want_t) / np.where(den_t > 0, den_t, 1.0)))
+    assert err_t <= 1e-5, ("transposed", err_t)
     lib.destroy(Ag2)
     dist.barrier()
     if rank == 0:

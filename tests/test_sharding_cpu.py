@@ -163,3 +163,40 @@ def test_partition_by_nnz_edge_cases():
     rp = np.arange(0, 101, 10)
     assert sharding.partition_by_nnz(rp, 5) == [0, 2, 4, 6, 8, 10]
     assert sharding.partition_by_nnz(rp, 1) == [0, 10]
+
+
+def _transposed_worker(rank, world, port, q):
+    import sharding
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    A = _skewed_matrix()
+    n = A.shape[0]
+    cuts = sharding.partition_by_nnz(A.indptr, world)
+    ycuts = [n * r // world for r in range(world + 1)]
+    plan = sharding.TransposedPlan(ycuts, rank, torch.float64, "cpu")
+    mine = A[cuts[rank]: cuts[rank + 1]]
+    x = np.linspace(-1.0, 1.0, n)[cuts[rank]: cuts[rank + 1]]
+    plan.partial.copy_(torch.from_numpy(mine.T @ x))
+    y = plan.reduce()
+    q.put((rank, y.numpy().copy(), ycuts))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_transposed_product_on_row_shards(world):
+    """y = A^T x with A and x row-sharded: full-length partial products reduced and scattered"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_transposed_worker, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in procs]
+    parts = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    A = _skewed_matrix()
+    want = A.T @ np.linspace(-1.0, 1.0, A.shape[0])
+    got = np.concatenate([p[1] for p in parts])
+    assert got.shape == want.shape
+    assert np.max(np.abs(got - want)) <= 1e-12 * max(1.0, np.max(np.abs(want)))
