@@ -299,6 +299,216 @@ namespace b200
             block_sum_store<T>(s, partial);
         }
 
+        // ---------------------------------------------------------------- device-driven solve (forward interface, no callbacks)
+        // The scalar logic of the state machine moves to the device: the LAST block of every reduction kernel runs it
+        // (same comparisons, same order, same precision as cg_rci below), so an iteration needs no host round trip; the
+        // host enqueues iterations in small batches and looks at `status` after each batch.  Kernels of iterations that
+        // come after the stopping one see status != 0 and do nothing (the products in between are wasted, never used).
+        template <typename T>
+        struct cg_dev_state
+        {
+            T   rz, alpha, beta, rnorm2, bnorm2, brtol, atol, rtol;
+            int niter, maxit;
+            int status; // 0 running, 1 converged, 2 iteration limit, 3 breakdown, 4 NaN in b, 5 NaN residual
+        };
+
+        template <typename T>
+        __device__ __forceinline__ bool dev_nearzero_or_negative(T v)
+        {
+            return v <= (T)1e-2 * (T)2.0 * (sizeof(T) == 4 ? (T)1.1920928955078125e-7 : (T)2.220446049250313e-16);
+        }
+
+        // task_check_conv + task_start_iter + the scalar part of task_compute_beta (unpreconditioned: z = r, r.z = |r|^2)
+        template <typename T>
+        __device__ __forceinline__ void cg_check_advance(cg_dev_state<T> *st)
+        {
+            if((T)0 < st->atol && st->rnorm2 <= st->atol)
+                st->status = 1;
+            else if((T)0 < st->rtol && st->rnorm2 <= st->brtol)
+                st->status = 1;
+            else if(st->maxit > 0 && st->niter > st->maxit)
+                st->status = 2;
+            else
+            {
+                st->niter++;
+                const T rz_new = st->rnorm2 * st->rnorm2;
+                if(dev_nearzero_or_negative(st->rz))
+                    st->status = 3;
+                else
+                {
+                    st->beta = rz_new / st->rz;
+                    st->rz   = rz_new;
+                }
+            }
+        }
+
+        enum
+        {
+            EPI_START = 0, // sum = |b|^2
+            EPI_RESID,     // sum = |r0|^2
+            EPI_PQ,        // sum = p.q
+            EPI_STEP       // sum = |r|^2 after the update
+        };
+
+        template <typename T, int EPI>
+        __device__ __forceinline__ void cg_epilogue(cg_dev_state<T> *st, double sum)
+        {
+            if(EPI == EPI_START)
+            {
+                st->bnorm2 = (T)sqrt(sum);
+                if(st->bnorm2 != st->bnorm2)
+                    st->status = 4;
+                st->brtol = st->rtol * st->bnorm2;
+                st->niter = 0;
+            }
+            else if(EPI == EPI_RESID || EPI == EPI_STEP)
+            {
+                st->rnorm2 = (T)sqrt(sum);
+                if(st->rnorm2 != st->rnorm2)
+                {
+                    st->status = 5;
+                    return;
+                }
+                if(EPI == EPI_RESID)
+                    st->rz = (T)1;
+                cg_check_advance(st);
+            }
+            else
+            {
+                const T pq = (T)sum;
+                if(dev_nearzero_or_negative(pq) || pq == (T)0)
+                    st->status = 3; // A is not positive definite
+                else
+                    st->alpha = st->rz / pq;
+            }
+        }
+
+        // block partial -> last block: ordered sum -> scalar logic on the device
+        template <typename T, int EPI>
+        __device__ __forceinline__ void block_sum_epilogue(double s, double *partial, unsigned *ticket, cg_dev_state<T> *st)
+        {
+            __shared__ double sh[RED_THREADS / 32];
+            __shared__ bool   last;
+            __shared__ double fin[RED_THREADS];
+#pragma unroll
+            for(int k = 16; k > 0; k >>= 1)
+                s += __shfl_down_sync(0xffffffffu, s, k);
+            if((threadIdx.x & 31) == 0)
+                sh[threadIdx.x >> 5] = s;
+            __syncthreads();
+            if(threadIdx.x < 32)
+            {
+                s = threadIdx.x < RED_THREADS / 32 ? sh[threadIdx.x] : 0.0;
+#pragma unroll
+                for(int k = 16; k > 0; k >>= 1)
+                    s += __shfl_down_sync(0xffffffffu, s, k);
+                if(threadIdx.x == 0)
+                {
+                    partial[blockIdx.x] = s;
+                    __threadfence();
+                    last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+                }
+            }
+            __syncthreads();
+            if(!last)
+                return;
+            __threadfence();
+            double t = 0;
+            for(int i = threadIdx.x; i < (int)gridDim.x; i += RED_THREADS)
+                t += __ldcg(partial + i);
+            fin[threadIdx.x] = t;
+            __syncthreads();
+            for(int k = RED_THREADS / 2; k > 0; k >>= 1)
+            {
+                if(threadIdx.x < k)
+                    fin[threadIdx.x] += fin[threadIdx.x + k];
+                __syncthreads();
+            }
+            if(threadIdx.x == 0)
+            {
+                cg_epilogue<T, EPI>(st, fin[0]);
+                *ticket = 0;
+                __threadfence();
+            }
+        }
+
+        template <typename T>
+        __global__ void __launch_bounds__(RED_THREADS) cgd_start_kernel(long long n, const T *__restrict__ b, const T *__restrict__ x,
+                                                                       T *__restrict__ r, T *__restrict__ p, double *partial,
+                                                                       unsigned *ticket, cg_dev_state<T> *st)
+        {
+            double s = 0;
+            for(long long i = (long long)blockIdx.x * RED_THREADS + threadIdx.x; i < n; i += (long long)gridDim.x * RED_THREADS)
+            {
+                const T bi = b[i];
+                r[i]       = -bi;
+                p[i]       = x[i];
+                s += (double)bi * (double)bi;
+            }
+            block_sum_epilogue<T, EPI_START>(s, partial, ticket, st);
+        }
+
+        template <typename T>
+        __global__ void __launch_bounds__(RED_THREADS) cgd_residual_kernel(long long n, T *__restrict__ r, const T *__restrict__ q,
+                                                                          T *__restrict__ p, double *partial, unsigned *ticket,
+                                                                          cg_dev_state<T> *st)
+        {
+            if(st->status)
+                return;
+            double s = 0;
+            for(long long i = (long long)blockIdx.x * RED_THREADS + threadIdx.x; i < n; i += (long long)gridDim.x * RED_THREADS)
+            {
+                const T ri = r[i] + q[i];
+                r[i]       = ri;
+                p[i]       = (T)0;
+                s += (double)ri * (double)ri;
+            }
+            block_sum_epilogue<T, EPI_RESID>(s, partial, ticket, st);
+        }
+
+        template <typename T>
+        __global__ void __launch_bounds__(RED_THREADS) cgd_direction_kernel(long long n, T *__restrict__ p, const T *__restrict__ r,
+                                                                           const cg_dev_state<T> *st)
+        {
+            if(st->status)
+                return;
+            const T beta = st->beta;
+            for(long long i = (long long)blockIdx.x * RED_THREADS + threadIdx.x; i < n; i += (long long)gridDim.x * RED_THREADS)
+                p[i] = beta * p[i] - r[i];
+        }
+
+        template <typename T>
+        __global__ void __launch_bounds__(RED_THREADS) cgd_dot_kernel(long long n, const T *__restrict__ p, const T *__restrict__ q,
+                                                                     double *partial, unsigned *ticket, cg_dev_state<T> *st)
+        {
+            if(st->status)
+                return;
+            double s = 0;
+            for(long long i = (long long)blockIdx.x * RED_THREADS + threadIdx.x; i < n; i += (long long)gridDim.x * RED_THREADS)
+                s += (double)p[i] * (double)q[i];
+            block_sum_epilogue<T, EPI_PQ>(s, partial, ticket, st);
+        }
+
+        template <typename T>
+        __global__ void __launch_bounds__(RED_THREADS) cgd_step_kernel(long long n, const T *__restrict__ p, const T *__restrict__ q,
+                                                                      T *__restrict__ x, T *__restrict__ r, double *partial,
+                                                                      unsigned *ticket, cg_dev_state<T> *st)
+        {
+            if(st->status)
+                return;
+            const T alpha = st->alpha;
+            double  s     = 0;
+            for(long long i = (long long)blockIdx.x * RED_THREADS + threadIdx.x; i < n; i += (long long)gridDim.x * RED_THREADS)
+            {
+                x[i] += alpha * p[i];
+                const T ri = r[i] + alpha * q[i];
+                r[i]       = ri;
+                s += (double)ri * (double)ri;
+            }
+            block_sum_epilogue<T, EPI_STEP>(s, partial, ticket, st);
+        }
+
+
         struct managed_buf
         {
             void  *p     = nullptr;
@@ -665,6 +875,81 @@ namespace b200
             }
         };
 
+        // Unpreconditioned CG without callbacks, driven from the device (see cg_dev_state above).  `it` has been prepared by
+        // rci_input + solver_init; the matrix has been hinted and optimized.
+        template <typename T>
+        aoclsparse_status device_driven_cg(itsol_data<T> *it, aoclsparse_matrix mat, const aoclsparse_mat_descr descr, T *x, T rinfo[100])
+        {
+            cudaStream_t    st = current_stream();
+            const long long n  = it->n;
+            T              *r = it->r.template as<T>(), *p = it->p.template as<T>(), *q = it->q.template as<T>();
+            T              *xd     = x;
+            bool            x_host = false;
+            if(!is_device_accessible(x))
+            {
+                B200_TRY(it->xw.alloc(sizeof(T) * (size_t)n, st, false));
+                if(n > 0)
+                    B200_CUDA(cudaMemcpyAsync(it->xw.p, x, sizeof(T) * (size_t)n, cudaMemcpyHostToDevice, st));
+                xd     = it->xw.template as<T>();
+                x_host = true;
+            }
+            dev_buf dstate;
+            B200_TRY(dstate.alloc(sizeof(cg_dev_state<T>)));
+            cg_dev_state<T> h{};
+            h.atol  = it->atol;
+            h.rtol  = it->rtol;
+            h.maxit = it->maxit;
+            B200_CUDA(cudaMemcpyAsync(dstate.p, &h, sizeof(h), cudaMemcpyHostToDevice, st));
+            cg_dev_state<T> *ds      = dstate.as<cg_dev_state<T>>();
+            double          *partial = it->partial.template as<double>();
+            unsigned        *ticket  = it->ticket.template as<unsigned>();
+            const T          one = (T)1, zero = (T)0;
+            cgd_start_kernel<T><<<RED_BLOCKS, RED_THREADS, 0, st>>>(n, it->b.template as<T>(), xd, r, p, partial, ticket, ds);
+            B200_LAUNCHED();
+            if(mv_of<T>::call(&one, mat, descr, p, &zero, q) != aoclsparse_status_success)
+                return aoclsparse_status_internal_error;
+            cgd_residual_kernel<T><<<RED_BLOCKS, RED_THREADS, 0, st>>>(n, r, q, p, partial, ticket, ds);
+            B200_LAUNCHED();
+            constexpr int BATCH = 4;
+            while(true)
+            {
+                B200_CUDA(cudaMemcpyAsync(&h, dstate.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+                B200_CUDA(cudaStreamSynchronize(st));
+                if(h.status != 0)
+                    break;
+                for(int k = 0; k < BATCH; ++k)
+                {
+                    cgd_direction_kernel<T><<<RED_BLOCKS, RED_THREADS, 0, st>>>(n, p, r, ds);
+                    B200_LAUNCHED();
+                    if(mv_of<T>::call(&one, mat, descr, p, &zero, q) != aoclsparse_status_success)
+                        return aoclsparse_status_internal_error;
+                    cgd_dot_kernel<T><<<RED_BLOCKS, RED_THREADS, 0, st>>>(n, p, q, partial, ticket, ds);
+                    B200_LAUNCHED();
+                    cgd_step_kernel<T><<<RED_BLOCKS, RED_THREADS, 0, st>>>(n, p, q, xd, r, partial, ticket, ds);
+                    B200_LAUNCHED();
+                }
+            }
+            if(x_host && n > 0)
+            {
+                B200_CUDA(cudaMemcpyAsync(x, xd, sizeof(T) * (size_t)n, cudaMemcpyDeviceToHost, st));
+                B200_CUDA(cudaStreamSynchronize(st));
+            }
+            rinfo[0]  = h.rnorm2;
+            rinfo[1]  = h.bnorm2;
+            rinfo[30] = (T)h.niter;
+            switch(h.status)
+            {
+            case 1:
+                return aoclsparse_status_success;
+            case 2:
+                return aoclsparse_status_maxit;
+            case 4:
+                return aoclsparse_status_invalid_value;
+            default:
+                return aoclsparse_status_numerical_error;
+            }
+        }
+
         // aoclsparse_itsol_solve + aoclsparse_cg_solve, itsol_functions.hpp:555-624,1369-1500
         template <typename T>
         aoclsparse_status forward_solve(itsol_data<T>             *it,
@@ -705,6 +990,13 @@ namespace b200
             // the symmetric product runs as a plain streaming gather on the expanded copy (spmv.cu, expand.cu)
             if(aoclsparse_set_mv_hint(mat, aoclsparse_operation_none, descr, 100) == aoclsparse_status_success)
                 aoclsparse_optimize(mat);
+            // no callback, no preconditioner: the whole loop runs without host round trips
+            // (AOCLSPARSE_B200_ITSOL_HOST_DRIVEN=1 keeps the host-driven state machine, for comparison)
+            {
+                const char *eh = getenv("AOCLSPARSE_B200_ITSOL_HOST_DRIVEN");
+                if(!precond && !monit && it->precond == 0 && !(eh && atoi(eh) != 0))
+                    return device_driven_cg<T>(it, mat, descr, x, rinfo);
+            }
             it->solving     = true;
             it->opts.locked = true;
             aoclsparse_itsol_rci_job ircomm      = aoclsparse_rci_start;

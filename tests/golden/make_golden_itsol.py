@@ -54,8 +54,10 @@ def itsol_matrix(kind, dt):
     return n, A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data.astype(dt)
 
 
-def run_itsol_case(lib, c):
-    """one CG solve through `lib` (any library exporting the ABI); returns (status, rinfo, x, monitor trace)"""
+def run_itsol_case(lib, c, callbacks=True):
+    """one CG solve through `lib` (any library exporting the ABI); returns (status, rinfo, x, monitor trace).
+    callbacks=False leaves out the monitor (and needs a case without preconditioner / monitor stop): the CUDA library then
+    runs its device-driven loop"""
     dt = DT[c["p"]]
     n, rp, col, val = itsol_matrix(c["mat"], dt)
     st, A = lib.create_csr(c["p"], 0, n, n, len(col), rp, col, val)
@@ -83,7 +85,7 @@ def run_itsol_case(lib, c):
         trace.append((float(ri[30]), float(ri[0])))
         return 1 if (c["stop_at"] is not None and ri[30] >= c["stop_at"]) else 0
     status = lib.itsol_solve(c["p"], h, n, A, d, b, x, rinfo, precond=precond if c["precond"] == "jacobi" else None,
-                             monit=monit)
+                             monit=monit if callbacks else None)
     lib.itsol_destroy(h)
     lib.destroy_descr(d)
     lib.destroy(A)

@@ -41,6 +41,12 @@ def test_cg_cases_match_reference(lib):
         assert np.max(np.abs(got[:, 1] - ref_trace[:, 1])) <= 50 * eps * scale, c  # residual history
         xr = data[c["key"] + "_x"]
         assert np.max(np.abs(x - xr)) <= 200 * eps * max(1.0, np.max(np.abs(xr))), (c, np.max(np.abs(x - xr)))
+        if c["precond"] == "none" and c["stop_at"] is None:
+            # the same case without callbacks runs the device-driven loop: same status, same iteration count, same x
+            status2, rinfo2, x2, _, _ = mg.run_itsol_case(lib, c, callbacks=False)
+            assert status2 == c["status"] and int(rinfo2[30]) == c["iters"], (c, status2, rinfo2[30])
+            assert abs(rinfo2[0] - c["res"]) <= 50 * eps * scale and abs(rinfo2[1] - c["bnorm"]) <= 1e-6 * c["bnorm"]
+            assert np.max(np.abs(x2 - xr)) <= 200 * eps * max(1.0, np.max(np.abs(xr))), c
 
 
 def test_cg_status_codes_match_reference(lib):
@@ -74,6 +80,14 @@ def test_cg_device_resident_and_reverse_communication(lib):
     iters = int(rinfo[30])
     assert 10 < iters < 200 and rinfo[0] <= 1e-11 * rinfo[1]
     assert lib.launch_count() - launches0 >= 4 * iters  # mv + dot + step + direction per iteration
+    # the host-driven state machine (callbacks, reverse communication) takes the same number of iterations
+    os.environ["AOCLSPARSE_B200_ITSOL_HOST_DRIVEN"] = "1"
+    dx2 = torch.zeros(n, dtype=torch.float64, device="cuda")
+    rinfo_h = np.zeros(100)
+    assert lib.itsol_solve("d", it, n, h, d, db.data_ptr(), dx2.data_ptr(), rinfo_h) == 0
+    del os.environ["AOCLSPARSE_B200_ITSOL_HOST_DRIVEN"]
+    assert int(rinfo_h[30]) == iters and abs(rinfo_h[0] - rinfo[0]) <= 1e-12 * rinfo[1]
+    assert torch.max(torch.abs(dx2 - dx)).item() <= 1e-10
     torch.cuda.synchronize()
     x = dx.cpu().numpy()
     assert np.linalg.norm(A @ x - b) <= 1e-10 * np.linalg.norm(b)
