@@ -560,6 +560,7 @@ namespace b200
             bool           have_b  = false;
             bool           solving = false;
             bool           host_visible = true; // work vectors in managed memory (reverse communication, callbacks)
+            bool           vectors_managed = true; // what the vectors currently allocated are
             managed_buf    b, r, p, q, z, xw; // xw: device-side copy of a host-resident x
             dev_buf        partial, ticket;
             double        *h_result = nullptr, *d_result = nullptr; // mapped page-locked scalar
@@ -613,10 +614,15 @@ namespace b200
                 return aoclsparse_status_invalid_pointer;
             cudaStream_t st = current_stream();
             it->have_b      = false;
-            B200_TRY(it->b.alloc(sizeof(T) * (size_t)n, st, it->host_visible));
-            for(managed_buf *m : {&it->r, &it->p, &it->q, &it->z})
-                B200_TRY(m->alloc(sizeof(T) * (size_t)n, st, it->host_visible));
-            it->xw.release();
+            // the work vectors are kept from one solve to the next when size and memory kind are unchanged
+            if(it->n != n || !it->b.p || it->vectors_managed != it->host_visible)
+            {
+                B200_TRY(it->b.alloc(sizeof(T) * (size_t)n, st, it->host_visible));
+                for(managed_buf *m : {&it->r, &it->p, &it->q, &it->z})
+                    B200_TRY(m->alloc(sizeof(T) * (size_t)n, st, it->host_visible));
+                it->vectors_managed = it->host_visible;
+                it->xw.release();
+            }
             B200_TRY(it->partial.alloc(sizeof(double) * RED_BLOCKS));
             B200_TRY(it->ticket.alloc(sizeof(unsigned)));
             B200_CUDA(cudaMemsetAsync(it->ticket.p, 0, sizeof(unsigned), st));
@@ -887,7 +893,8 @@ namespace b200
             bool            x_host = false;
             if(!is_device_accessible(x))
             {
-                B200_TRY(it->xw.alloc(sizeof(T) * (size_t)n, st, false));
+                if(!it->xw.p || it->xw.bytes != sizeof(T) * (size_t)n)
+                    B200_TRY(it->xw.alloc(sizeof(T) * (size_t)n, st, false));
                 if(n > 0)
                     B200_CUDA(cudaMemcpyAsync(it->xw.p, x, sizeof(T) * (size_t)n, cudaMemcpyHostToDevice, st));
                 xd     = it->xw.template as<T>();
@@ -987,9 +994,19 @@ namespace b200
                 return aoclsparse_status_invalid_pointer;
             if(it->precond == 3)
                 return aoclsparse_status_not_implemented; // symmetric Gauss-Seidel: two triangular solves per iteration
-            // the symmetric product runs as a plain streaming gather on the expanded copy (spmv.cu, expand.cu)
-            if(aoclsparse_set_mv_hint(mat, aoclsparse_operation_none, descr, 100) == aoclsparse_status_success)
-                aoclsparse_optimize(mat);
+            // the symmetric product runs as a plain streaming gather on the expanded copy (spmv.cu, expand.cu): hint and
+            // optimize once per matrix
+            {
+                const int want  = get_doid(false, descr->type, descr->fill_mode, aoclsparse_operation_none);
+                bool      ready = false;
+                {
+                    std::shared_lock<std::shared_mutex> rl(mat->guard);
+                    for(const hint &hh : mat->hints)
+                        ready = ready || (hh.act == 1 && hh.doid == want && hh.done);
+                }
+                if(!ready && aoclsparse_set_mv_hint(mat, aoclsparse_operation_none, descr, 100) == aoclsparse_status_success)
+                    aoclsparse_optimize(mat);
+            }
             // no callback, no preconditioner: the whole loop runs without host round trips
             // (AOCLSPARSE_B200_ITSOL_HOST_DRIVEN=1 keeps the host-driven state machine, for comparison)
             {
