@@ -50,9 +50,7 @@ class MatrixInfo(C.Structure):
                 ("block_nnz", C.c_int32), ("block_rows", C.c_int32), ("n_blocks", C.c_int32),
                 ("n_thread_blocks", C.c_int32), ("n_warp_blocks", C.c_int32),
                 ("n_product_blocks", C.c_int32), ("n_long_segments", C.c_int32),
-                ("n_long_rows", C.c_int32), ("hot_entries", C.c_int32), ("hot_mass_ppm", C.c_int32),
-                ("group_k", C.c_int32), ("group_entries", C.c_int32), ("group_blocks", C.c_int32),
-                ("group_block_nnz", C.c_int32), ("mm_tile_state", C.c_int32), ("mm_tile_max_rows", C.c_int32)]
+                ("n_long_rows", C.c_int32), ("n_diag_codes", C.c_int32), ("sorted_blocks", C.c_int32)]
 
 
 class HaloCtl(C.Structure):

@@ -251,6 +251,16 @@ namespace b200
         return create_csr<double>(mat, base, M, N, nnz, row_ptr, col_idx, val, val_type, false);
     }
 
+    void drop_derived_copies(aoclsparse_matrix A)
+    {
+        for(size_t i = 1; i < A->mats.size(); ++i)
+            delete A->mats[i];
+        A->mats.resize(1);
+        A->clean = b200::clean_csr();
+        for(auto &h : A->hints)
+            h.done = false;
+    }
+
     namespace
     {
         template <typename T>
@@ -270,15 +280,7 @@ namespace b200
             B200_CUDA(cudaStreamSynchronize(st));
             // derived copies hold stale values: drop them (the reference does the same,
             // aoclsparse_auxiliary.hpp:260-272); the row-block plan depends on the pattern only and stays
-            for(size_t i = 1; i < A->mats.size(); ++i)
-                delete A->mats[i];
-            A->mats.resize(1);
-            A->clean = b200::clean_csr();
-            A->mats[0]->grouped.reset(); // rebuilt by the next csrmm call (pattern, hence eligibility, unchanged)
-            if(A->mats[0]->group_k > 0)
-                A->mats[0]->group_k = 0;
-            for(auto &h : A->hints)
-                h.done = false;
+            drop_derived_copies(A);
             return aoclsparse_status_success;
         }
 
@@ -587,22 +589,6 @@ aoclsparse_status aoclsparse_optimize(aoclsparse_matrix A)
     if(!M.plan.valid || forced >= 0)
         B200_TRY(build_plan(M, value_size(A->val_type), A->max_row_nnz, forced, A->row_cuts, st));
 
-    // hot-column table for gather-bound (skewed) matrices with a plain general mv hint, memory policy permitting
-    {
-        bool gn_mv_hint = false;
-        for(const hint &h : A->hints)
-            gn_mv_hint = gn_mv_hint || (h.act == 1 && h.doid == DOID_GN);
-        const long long mean   = A->m > 0 ? (long long)A->nnz / A->m : 0;
-        const bool      skewed = (long long)A->max_row_nnz > 16 * (mean > 1 ? mean : 1);
-        const char     *e      = getenv("AOCLSPARSE_B200_HOT");
-        // off by default: both realisations measured slower than the plain kernel on R-MAT scale 24
-        // (profiles/r01_summary.md, "hot-column table"); AOCLSPARSE_B200_HOT=1 enables it for experiments
-        const bool      want   = e ? atoi(e) != 0 : false;
-        if(want && gn_mv_hint && !A->is_csc && skewed && A->mem_policy == aoclsparse_memory_usage_unrestricted && A->win_hi < 0
-           && M.plan.hot_entries == 0 && A->row_cuts.empty())
-            B200_TRY(build_hot_table(M, value_size(A->val_type), st));
-    }
-
     // transposed device copies for general transposed mv / mm hints (memory policy permitting):
     // they turn the atomic scatter into a streaming gather
     if(A->mem_policy == aoclsparse_memory_usage_unrestricted && A->win_hi < 0)
@@ -638,12 +624,6 @@ aoclsparse_status aoclsparse_optimize(aoclsparse_matrix A)
             h.done = true;
         }
     }
-    // row-grouped copy for the row-major csrmm kernel when the hinted product runs on the stored matrix itself
-    for(const hint &h : A->hints)
-        if(h.act == 3 && h.doid == (A->is_csc ? DOID_GT : DOID_GN))
-            A->want_grouped = true;
-    if(A->want_grouped)
-        B200_TRY(ensure_grouped(A, st));
     B200_CUDA(cudaStreamSynchronize(st));
     return aoclsparse_status_success;
 }
@@ -679,14 +659,6 @@ aoclsparse_status aoclsparse_b200_get_matrix_info(const aoclsparse_matrix A, aoc
         info->n_product_blocks = P.n_strat[STRAT_PRODUCT];
         info->n_long_segments  = P.n_long_segments;
         info->n_long_rows      = P.n_long_rows;
-        info->hot_entries      = P.hot_entries;
-        info->group_k          = A->mats[0]->group_k;
-        info->group_entries    = A->mats[0]->grouped ? A->mats[0]->grouped->nnz : 0;
-        info->group_blocks     = A->mats[0]->grouped ? A->mats[0]->grouped->plan.n_blocks : 0;
-        info->group_block_nnz  = A->mats[0]->grouped ? A->mats[0]->grouped->plan.block_nnz : 0;
-        info->mm_tile_state    = A->mats[0]->tiles_state;
-        info->mm_tile_max_rows = A->mats[0]->tiles ? A->mats[0]->tiles->max_uniq : 0;
-        info->hot_mass_ppm     = (aoclsparse_int)(P.hot_mass * 1e6);
     }
     return aoclsparse_status_success;
 }

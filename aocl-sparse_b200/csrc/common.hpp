@@ -348,17 +348,7 @@ namespace b200
         aoclsparse_int n_long_segments = 0;
         aoclsparse_int n_strat[4] = {0, 0, 0, 0};
         aoclsparse_int max_block_rows = 0; // most rows any block holds (sizes the staged row_ptr slice)
-        // hot-column table (hot.cu / spmv_hot.cuh): 0 entries = not built
-        aoclsparse_int hot_entries = 0;
-        int            hot_stages  = 2;
-        int            hot_mode    = 1;   // 1: packed side vector + L1 priorities (default), 2: persistent smem table
-        double         hot_mass    = 0.0; // fraction of stored entries whose column is in the table
-        dev_buf        hot_cols;          // int[hot_entries] column of every slot
-        dev_buf        col_hot;           // int[nnz] column array with hot columns replaced by HOT_BIT | slot
         int            pdl              = 1; // programmatic dependent launch of the multiply kernel (tuning knob)
-        int            pipelined        = 0; // use the persistent pipelined kernel when every block is thread-per-row
-        int            pipe_stages      = 4; // ring depth of that kernel
-        int            pipe_ctas_per_sm = 2;
         int            threads     = 256; // CTA size of the multiply kernel (tuning knob)
         int            stream_hint = 1;   // tag the val/col stream evict-first in L2 (tuning knob)
         dev_buf        desc;      // int4 per block: first row, end row, first nnz, end nnz
@@ -377,20 +367,6 @@ namespace b200
         bool           valid = false;
     };
 
-    // csrmm, row-major: per small row block the distinct columns it names (as runs of consecutive columns) and, per stored
-    // entry, the slot of its column in that list -- the kernel stages the named B rows once into shared memory with TMA
-    // and multiplies out of it (csrmm.cu, "tiled" kernel)
-    struct mm_tiles
-    {
-        aoclsparse_int block_nnz = 0; // entries per row block of this plan
-        row_block_plan plan;
-        dev_buf        run_ptr;       // int[n_blocks + 1]
-        dev_buf        runs;          // int4 per run: first column, slot of that column, length, unused
-        dev_buf        uniq;          // int[n_blocks]: distinct columns of the block
-        dev_buf        lidx;          // uint16 per stored entry
-        aoclsparse_int max_uniq = 0;
-    };
-
     // one device-resident CSR (always 0-based on the device)
     struct dev_csr
     {
@@ -398,13 +374,6 @@ namespace b200
         int            doid = DOID_GN; // what this copy represents relative to the user's matrix
         dev_buf        row_ptr, col_idx, val;
         row_block_plan plan;
-        // row-grouped copy for csrmm (group.cu): K rows per group, row_ptr = group pointers, col_idx = column | row
-        // mask << 27, val = K values per entry.  group_k: 0 not analysed yet, -1 analysed and not used, else K.
-        std::unique_ptr<dev_csr> grouped;
-        int                      group_k = 0;
-        // tile plan of the row-major csrmm kernel: 0 not analysed, -1 analysed and not usable, else its block size
-        std::unique_ptr<mm_tiles> tiles;
-        int                       tiles_state = 0;
     };
 
     // "clean CSR" of the reference's analysis (clean.cu): rows grouped lower | diagonal | upper, diagonals present
@@ -449,11 +418,13 @@ struct _aoclsparse_matrix
     aoclsparse_memory_usage       mem_policy = aoclsparse_memory_usage_unrestricted;
     int                           device     = 0;
     std::atomic<int>              lazy_copy_calls{0};   // un-hinted products that would profit from a derived copy (spmv.cu)
-    bool                          want_grouped = false; // a mm hint on the stored matrix was optimized (group.cu)
     bool                          is_csc     = false; // created from CSC arrays: mats[0] stores the TRANSPOSE (n x m CSR)
 
     std::vector<b200::hint>       hints; // most recent first, like the reference's linked list
     std::vector<b200::dev_csr *>  mats;  // mats[0] is the user's matrix
+    // aoclsparse_sp2m, both operands transposed: the product (B A) whose transpose is this matrix, kept between the
+    // nnz_count and finalize stages (and for repeated finalize calls)
+    std::unique_ptr<b200::dev_csr> sp2m_product;
     b200::clean_csr               clean; // built on demand (aoclsparse_b200_get_clean_csr)
     std::vector<aoclsparse_int>   row_cuts;
     aoclsparse_int                win_lo = 0, win_hi = -1; // x window (win_hi < 0: whole vector)
@@ -530,16 +501,13 @@ namespace b200
                                       const aoclsparse_int *col_idx,
                                       const void           *val);
 
-    // hot.cu
-    aoclsparse_status build_hot_table(dev_csr &A, size_t elem_size, cudaStream_t st);
-    template <typename T>
-    aoclsparse_status launch_hot(const dev_csr &A, const T *x, T *y, T alpha, T beta, cudaStream_t st);
-
-    // group.cu -- row-grouped copy of mats[0] for the row-major csrmm kernel (caller holds the write lock)
-    aoclsparse_status ensure_grouped(aoclsparse_matrix A, cudaStream_t st);
-
     // clean.cu
     aoclsparse_status ensure_clean(aoclsparse_matrix A, cudaStream_t st);
+
+    // api.cu -- after the stored VALUES changed: derived copies (transposed / expanded / clean) hold stale values and are
+    // dropped, hints become pending again; the row-block plan depends on the pattern only and stays (caller holds the
+    // write lock)
+    void drop_derived_copies(aoclsparse_matrix A);
 
     // obtains (building on first use) the plan of mats[0]
     aoclsparse_status ensure_plan(aoclsparse_matrix A, cudaStream_t st);

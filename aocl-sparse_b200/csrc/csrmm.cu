@@ -364,522 +364,6 @@ namespace b200
             }
         }
 
-        // the K values of one group entry: one or more 16-byte shared-memory loads (8 bytes for two floats)
-        template <typename T, int K>
-        __device__ __forceinline__ void load_group_vals(const T *p, T (&a)[K])
-        {
-            constexpr int BYTES = K * (int)sizeof(T);
-            if constexpr(BYTES >= 16)
-            {
-                uint4 buf[BYTES / 16];
-#pragma unroll
-                for(int q = 0; q < BYTES / 16; ++q)
-                    buf[q] = reinterpret_cast<const uint4 *>(p)[q];
-                memcpy(a, buf, BYTES);
-            }
-            else
-            {
-                const uint2 b = *reinterpret_cast<const uint2 *>(p);
-                memcpy(a, &b, BYTES);
-            }
-        }
-
-        template <typename T, bool CONJ, int K, int NV>
-        __device__ __forceinline__ void group_entry_fma(int w, const T *sv, const vec16<T> (&x)[NV], const bool (&pv)[NV],
-                                                        vec16<T> (&acc)[K][NV])
-        {
-            constexpr int VEC = vec16<T>::N;
-            T             a[K];
-            load_group_vals<T, K>(sv, a);
-#pragma unroll
-            for(int i = 0; i < K; ++i)
-            {
-                if(w & (1 << (27 + i)))
-                {
-                    const T ai = CONJ ? cj(a[i]) : a[i];
-#pragma unroll
-                    for(int v = 0; v < NV; ++v)
-                        if(pv[v])
-                        {
-#pragma unroll
-                            for(int q = 0; q < VEC; ++q)
-                                acc[i][v].v[q] = mad(ai, x[v].v[q], acc[i][v].v[q]);
-                        }
-                }
-            }
-        }
-
-        // ROW MAJOR on the row-grouped copy (group.cu): K rows of A advance together over the union of their column
-        // indices, so every B row named by the group is loaded ONCE into registers and multiplied into up to K
-        // accumulators.  LPR lanes share one group; each lane owns NV 16-byte vectors of the B / C row.  The group
-        // entries (column | row mask << 27, K values) are staged in shared memory by two TMA bulk copies, as above.
-        template <typename T, bool CONJ, int K, int LPR, int NV>
-        __global__ void __launch_bounds__(MM_THREADS) csrmm_grouped_kernel(const int4 *__restrict__ desc,
-                                                                          int cap,
-                                                                          const aoclsparse_int *__restrict__ gp,
-                                                                          const aoclsparse_int *__restrict__ gcol,
-                                                                          const T *__restrict__ gval,
-                                                                          const T *__restrict__ B,
-                                                                          long long ldb,
-                                                                          T *__restrict__ C,
-                                                                          long long ldc,
-                                                                          int       n,
-                                                                          int       m,
-                                                                          T         alpha,
-                                                                          T         beta,
-                                                                          int       beta_zero)
-        {
-            constexpr int VEC      = vec16<T>::N;
-            constexpr int RPW      = 32 / LPR;       // groups per warp pass
-            constexpr int CPP      = LPR * NV * VEC; // columns of B per pass
-            constexpr int COL_MASK = (1 << 27) - 1;
-            extern __shared__ __align__(16) unsigned char smem_raw[];
-            uint64_t       *bar  = reinterpret_cast<uint64_t *>(smem_raw);
-            T              *sval = reinterpret_cast<T *>(smem_raw + SMEM_HEADER);
-            aoclsparse_int *scol = reinterpret_cast<aoclsparse_int *>(smem_raw + SMEM_HEADER + (size_t)cap * K * sizeof(T));
-
-            const int  tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-            const int  sub = lane / LPR, sl = lane % LPR;
-            const int4 d   = desc[blockIdx.x];
-            const int  ns = d.z, ne = d.w;
-            const int  a   = ns & ~3;
-            const int  cnt = ((ne - a) + 3) & ~3;
-            if(tid == 0)
-            {
-                mbar_init(bar, 1);
-                mbar_init_fence();
-                if(cnt > 0)
-                {
-                    mbar_expect_tx(bar, (unsigned)(cnt * (K * sizeof(T) + sizeof(aoclsparse_int))));
-                    bulk_load_stream(sval, gval + (size_t)a * K, (unsigned)(cnt * K * sizeof(T)), bar);
-                    bulk_load_stream(scol, gcol + a, (unsigned)(cnt * sizeof(aoclsparse_int)), bar);
-                }
-            }
-            __syncthreads();
-            if(cnt > 0)
-                mbar_wait(bar, 0);
-
-            for(int gb = d.x + warp * RPW; gb < d.y; gb += (MM_THREADS / 32) * RPW)
-            {
-                const int  g     = gb + sub;
-                const bool valid = g < d.y;
-                int        s = 0, e = 0;
-                if(valid)
-                {
-                    s = gp[g] - a;
-                    e = gp[g + 1] - a;
-                }
-                for(int c0 = 0; c0 < n; c0 += CPP)
-                {
-                    int  cofs[NV];
-                    bool pv[NV];
-#pragma unroll
-                    for(int v = 0; v < NV; ++v)
-                    {
-                        cofs[v] = c0 + (v * LPR + sl) * VEC;
-                        pv[v]   = cofs[v] < n;
-                    }
-                    vec16<T> acc[K][NV];
-#pragma unroll
-                    for(int i = 0; i < K; ++i)
-#pragma unroll
-                        for(int v = 0; v < NV; ++v)
-#pragma unroll
-                            for(int q = 0; q < VEC; ++q)
-                                acc[i][v].v[q] = vt<T>::zero();
-                    int j = s;
-                    for(; j + 2 <= e; j += 2)
-                    {
-                        const int w0 = scol[j], w1 = scol[j + 1];
-                        const T  *b0 = B + (long long)(w0 & COL_MASK) * ldb;
-                        const T  *b1 = B + (long long)(w1 & COL_MASK) * ldb;
-                        vec16<T>  x0[NV], x1[NV];
-#pragma unroll
-                        for(int v = 0; v < NV; ++v)
-                            if(pv[v])
-                            {
-                                x0[v] = load_vec(b0 + cofs[v]);
-                                x1[v] = load_vec(b1 + cofs[v]);
-                            }
-                        const T *sv = sval + (size_t)j * K;
-                        group_entry_fma<T, CONJ, K, NV>(w0, sv, x0, pv, acc);
-                        group_entry_fma<T, CONJ, K, NV>(w1, sv + K, x1, pv, acc);
-                    }
-                    if(j < e)
-                    {
-                        const int w0 = scol[j];
-                        const T  *b0 = B + (long long)(w0 & COL_MASK) * ldb;
-                        vec16<T>  x0[NV];
-#pragma unroll
-                        for(int v = 0; v < NV; ++v)
-                            if(pv[v])
-                                x0[v] = load_vec(b0 + cofs[v]);
-                        group_entry_fma<T, CONJ, K, NV>(w0, sval + (size_t)j * K, x0, pv, acc);
-                    }
-                    if(valid)
-                    {
-#pragma unroll
-                        for(int i = 0; i < K; ++i)
-                        {
-                            const long long r = (long long)g * K + i;
-                            if(r < m)
-                            {
-                                T *crow = C + r * ldc;
-#pragma unroll
-                                for(int v = 0; v < NV; ++v)
-                                    if(pv[v])
-                                    {
-                                        vec16<T> o;
-                                        if(!beta_zero)
-                                            o = load_vec(crow + cofs[v]);
-#pragma unroll
-                                        for(int q = 0; q < VEC; ++q)
-                                            o.v[q] = axpby_out(alpha, acc[i][v].v[q], beta, beta_zero != 0, &o.v[q]);
-                                        store_vec(crow + cofs[v], o);
-                                    }
-                            }
-                        }
-                    }
-                }
-            }
-        }
-
-        // ---------------------------------------------------------------------------------------------------------
-        // ROW MAJOR, tiled: the B rows a small row block names are staged ONCE into shared memory by TMA bulk copies
-        // (one per run of consecutive columns when ldb == n) and every product reads its B row from there.  The
-        // plain kernel above reads 256 bytes through L1 per stored entry and sits at the L1 line rate;
-        // shared memory delivers 128 B/clk/SM and the staging traffic is only the DISTINCT rows of the block.
-        // Analysis (ensure_mm_tiles): per block the sorted distinct columns, their runs, and a 16-bit slot per entry.
-        // ---------------------------------------------------------------------------------------------------------
-        constexpr int TILE_MAX_NNZ = 512;
-
-        template <bool FILL>
-        __global__ void __launch_bounds__(256) tile_analyse_kernel(const int4 *__restrict__ desc,
-                                                                   const int *__restrict__ col,
-                                                                   int *__restrict__ uniq,
-                                                                   int *__restrict__ nruns,
-                                                                   const int *__restrict__ run_ptr,
-                                                                   int4 *__restrict__ runs,
-                                                                   unsigned short *__restrict__ lidx)
-        {
-            __shared__ int key[TILE_MAX_NNZ], ukey[TILE_MAX_NNZ];
-            __shared__ int n_u, n_r;
-            const int4 d   = desc[blockIdx.x];
-            const int  ns = d.z, cnt = d.w - d.z;
-            const int  tid = threadIdx.x;
-            for(int i = tid; i < TILE_MAX_NNZ; i += 256)
-                key[i] = i < cnt ? col[ns + i] : 0x7fffffff;
-            __syncthreads();
-            for(int k2 = 2; k2 <= TILE_MAX_NNZ; k2 <<= 1)
-                for(int j = k2 >> 1; j > 0; j >>= 1)
-                {
-                    for(int e = tid; e < TILE_MAX_NNZ; e += 256)
-                    {
-                        const int x = e ^ j;
-                        if(x > e)
-                        {
-                            const int  ka = key[e], kb = key[x];
-                            const bool up = (e & k2) == 0;
-                            if((ka > kb) == up)
-                            {
-                                key[e] = kb;
-                                key[x] = ka;
-                            }
-                        }
-                    }
-                    __syncthreads();
-                }
-            if(tid == 0)
-            {
-                // one-time analysis: a serial pass over <= 512 sorted keys is cheap enough
-                int u = 0, r = 0;
-                for(int i = 0; i < cnt; ++i)
-                    if(i == 0 || key[i] != key[i - 1])
-                    {
-                        if(u == 0 || key[i] != ukey[u - 1] + 1)
-                        {
-                            if(FILL)
-                                runs[run_ptr[blockIdx.x] + r] = make_int4(key[i], u, 0, 0);
-                            ++r;
-                        }
-                        ukey[u++] = key[i];
-                    }
-                n_u = u;
-                n_r = r;
-                if(!FILL)
-                {
-                    uniq[blockIdx.x]  = u;
-                    nruns[blockIdx.x] = r;
-                }
-            }
-            __syncthreads();
-            if(!FILL)
-                return;
-            const int U = n_u, R = n_r;
-            // run lengths: next run's slot (or U) minus this run's slot
-            for(int r = tid; r < R; r += 256)
-            {
-                int4 *me   = runs + run_ptr[blockIdx.x] + r;
-                const int nx = (r + 1 < R) ? runs[run_ptr[blockIdx.x] + r + 1].y : U;
-                me->z      = nx - me->y;
-            }
-            // slot of every stored entry: position of its column among the distinct ones
-            for(int i = tid; i < cnt; i += 256)
-            {
-                const int c  = col[ns + i];
-                int       lo = 0, hi = U - 1;
-                while(lo < hi)
-                {
-                    const int mid = (lo + hi) >> 1;
-                    if(ukey[mid] < c)
-                        lo = mid + 1;
-                    else
-                        hi = mid;
-                }
-                lidx[ns + i] = (unsigned short)lo;
-            }
-        }
-
-        template <typename T>
-        __device__ __forceinline__ vec16<T> lds_vec(const T *p)
-        {
-            const int4 raw = *reinterpret_cast<const int4 *>(p);
-            vec16<T>   r;
-            memcpy(&r, &raw, 16);
-            return r;
-        }
-
-        template <typename T, bool CONJ, int LPR, int NT>
-        __global__ void __launch_bounds__(NT) csrmm_tiled_kernel(const int4 *__restrict__ desc,
-                                                                        int cap,
-                                                                        int tile_rows,
-                                                                        const aoclsparse_int *__restrict__ rp,
-                                                                        const T *__restrict__ val,
-                                                                        const unsigned short *__restrict__ lidx,
-                                                                        const int *__restrict__ run_ptr,
-                                                                        const int4 *__restrict__ runs,
-                                                                        const int *__restrict__ uniq,
-                                                                        const T *__restrict__ B,
-                                                                        long long ldb,
-                                                                        T *__restrict__ C,
-                                                                        long long ldc,
-                                                                        int       n,
-                                                                        T         alpha,
-                                                                        T         beta,
-                                                                        int       beta_zero)
-        {
-            constexpr int VEC = vec16<T>::N;
-            constexpr int RPW = 32 / LPR;
-            constexpr int CPP = LPR * 2 * VEC;
-            constexpr int U   = 2;
-            extern __shared__ __align__(16) unsigned char smem_raw[];
-            uint64_t       *bar   = reinterpret_cast<uint64_t *>(smem_raw);
-            T              *sval  = reinterpret_cast<T *>(smem_raw + SMEM_HEADER);
-            unsigned short *sidx  = reinterpret_cast<unsigned short *>(smem_raw + SMEM_HEADER + (size_t)cap * sizeof(T));
-            T              *tile  = reinterpret_cast<T *>(smem_raw + SMEM_HEADER + (size_t)cap * (sizeof(T) + sizeof(unsigned short)));
-
-            const int  tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-            const int  sub = lane / LPR, sl = lane % LPR;
-            const int4 d   = desc[blockIdx.x];
-            const int  ns = d.z, ne = d.w;
-            const int  a   = ns & ~7; // 8 entries: 16 bytes of 16-bit slots
-            const int  cnt = ((ne - a) + 7) & ~7;
-            const int  r0 = run_ptr[blockIdx.x], nr = run_ptr[blockIdx.x + 1] - r0;
-            const unsigned row_bytes = (unsigned)(n * sizeof(T));
-            if(tid == 0)
-            {
-                mbar_init(bar, 1);
-                mbar_init_fence();
-                mbar_expect_tx(bar, (unsigned)(cnt * (sizeof(T) + sizeof(unsigned short))) + (unsigned)uniq[blockIdx.x] * row_bytes);
-                if(cnt > 0)
-                {
-                    bulk_load_stream(sval, val + a, (unsigned)(cnt * sizeof(T)), bar);
-                    bulk_load_stream(sidx, lidx + a, (unsigned)(cnt * sizeof(unsigned short)), bar);
-                }
-            }
-            __syncthreads(); // the transaction count is posted before any copy below can complete
-            if(ldb == n)
-            {
-                for(int r = tid; r < nr; r += NT)
-                {
-                    const int4 run = runs[r0 + r];
-                    bulk_load(tile + (size_t)run.y * n, B + (long long)run.x * ldb, (unsigned)run.z * row_bytes, bar);
-                }
-            }
-            else
-            {
-                // padded leading dimension: the rows of a run are not contiguous, one copy per row
-                for(int r = warp; r < nr; r += NT / 32)
-                {
-                    const int4 run = runs[r0 + r];
-                    for(int k = lane; k < run.z; k += 32)
-                        bulk_load(tile + (size_t)(run.y + k) * n, B + (long long)(run.x + k) * ldb, row_bytes, bar);
-                }
-            }
-            mbar_wait(bar, 0);
-
-            for(int rb = d.x + warp * RPW; rb < d.y; rb += (NT / 32) * RPW)
-            {
-                const int  r     = rb + sub;
-                const bool valid = r < d.y;
-                int        s = 0, e = 0;
-                if(valid)
-                {
-                    s = rp[r] - a;
-                    e = rp[r + 1] - a;
-                }
-                for(int c0 = 0; c0 < n; c0 += CPP)
-                {
-                    const int  ca = c0 + sl * VEC, cb = c0 + (LPR + sl) * VEC;
-                    const bool pa = ca < n, pb = cb < n;
-                    vec16<T>   acc_a, acc_b;
-#pragma unroll
-                    for(int q = 0; q < VEC; ++q)
-                        acc_a.v[q] = acc_b.v[q] = vt<T>::zero();
-                    int j = s;
-                    for(; j + U <= e; j += U)
-                    {
-                        T        v[U];
-                        const T *bp[U];
-#pragma unroll
-                        for(int u = 0; u < U; ++u)
-                        {
-                            v[u] = sval[j + u];
-                            if(CONJ)
-                                v[u] = cj(v[u]);
-                            bp[u] = tile + (size_t)sidx[j + u] * n;
-                        }
-                        vec16<T> xa[U], xb[U];
-                        if(pa)
-                        {
-#pragma unroll
-                            for(int u = 0; u < U; ++u)
-                                xa[u] = lds_vec(bp[u] + ca);
-                        }
-                        if(pb)
-                        {
-#pragma unroll
-                            for(int u = 0; u < U; ++u)
-                                xb[u] = lds_vec(bp[u] + cb);
-                        }
-                        if(pa)
-                        {
-#pragma unroll
-                            for(int u = 0; u < U; ++u)
-#pragma unroll
-                                for(int q = 0; q < VEC; ++q)
-                                    acc_a.v[q] = mad(v[u], xa[u].v[q], acc_a.v[q]);
-                        }
-                        if(pb)
-                        {
-#pragma unroll
-                            for(int u = 0; u < U; ++u)
-#pragma unroll
-                                for(int q = 0; q < VEC; ++q)
-                                    acc_b.v[q] = mad(v[u], xb[u].v[q], acc_b.v[q]);
-                        }
-                    }
-                    for(; j < e; ++j)
-                    {
-                        T v0 = sval[j];
-                        if(CONJ)
-                            v0 = cj(v0);
-                        const T *b0 = tile + (size_t)sidx[j] * n;
-                        if(pa)
-                        {
-                            const vec16<T> x0a = lds_vec(b0 + ca);
-#pragma unroll
-                            for(int q = 0; q < VEC; ++q)
-                                acc_a.v[q] = mad(v0, x0a.v[q], acc_a.v[q]);
-                        }
-                        if(pb)
-                        {
-                            const vec16<T> x0b = lds_vec(b0 + cb);
-#pragma unroll
-                            for(int q = 0; q < VEC; ++q)
-                                acc_b.v[q] = mad(v0, x0b.v[q], acc_b.v[q]);
-                        }
-                    }
-                    if(valid)
-                    {
-                        T *crow = C + (long long)r * ldc;
-                        if(pa)
-                        {
-                            vec16<T> o;
-                            if(!beta_zero)
-                                o = load_vec(crow + ca);
-#pragma unroll
-                            for(int q = 0; q < VEC; ++q)
-                                o.v[q] = axpby_out(alpha, acc_a.v[q], beta, beta_zero != 0, &o.v[q]);
-                            store_vec(crow + ca, o);
-                        }
-                        if(pb)
-                        {
-                            vec16<T> o;
-                            if(!beta_zero)
-                                o = load_vec(crow + cb);
-#pragma unroll
-                            for(int q = 0; q < VEC; ++q)
-                                o.v[q] = axpby_out(alpha, acc_b.v[q], beta, beta_zero != 0, &o.v[q]);
-                            store_vec(crow + cb, o);
-                        }
-                    }
-                }
-            }
-        }
-
-        // shared memory the tiled kernel may use for B rows (two CTAs of ~100 KB per SM)
-        constexpr size_t TILE_BUDGET = 80 * 1024;
-
-        template <typename T, bool CONJ, int LPR, int NT>
-        aoclsparse_status launch_tiled_nt(const dev_csr &A, const T *B, long long ldb, T *C, long long ldc, int n, T alpha, T beta,
-                                          cudaStream_t st)
-        {
-            const mm_tiles &Tl   = *A.tiles;
-            const int       cap  = Tl.block_nnz + 16;
-            const size_t    smem = SMEM_HEADER + (size_t)cap * (sizeof(T) + sizeof(unsigned short)) + (size_t)Tl.max_uniq * n * sizeof(T);
-            static std::atomic<size_t> cfg{0};
-            if(cfg.load() < smem)
-            {
-                B200_CUDA(cudaFuncSetAttribute(csrmm_tiled_kernel<T, CONJ, LPR, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                cfg.store(smem);
-            }
-            csrmm_tiled_kernel<T, CONJ, LPR, NT><<<Tl.plan.n_blocks, NT, smem, st>>>(Tl.plan.desc.as<int4>(),
-                                                                                    cap,
-                                                                                    Tl.max_uniq,
-                                                                                    A.row_ptr.as<aoclsparse_int>(),
-                                                                                    A.val.as<T>(),
-                                                                                    Tl.lidx.as<unsigned short>(),
-                                                                                    Tl.run_ptr.as<int>(),
-                                                                                    Tl.runs.as<int4>(),
-                                                                                    Tl.uniq.as<int>(),
-                                                                                    B,
-                                                                                    ldb,
-                                                                                    C,
-                                                                                    ldc,
-                                                                                    n,
-                                                                                    alpha,
-                                                                                    beta,
-                                                                                    is_zero(beta) ? 1 : 0);
-            B200_LAUNCHED();
-            return aoclsparse_status_success;
-        }
-
-        // CTA size: enough sub-warp slots (32 / LPR per warp) for the rows a block holds
-        template <typename T, bool CONJ, int LPR>
-        aoclsparse_status launch_tiled_inst(const dev_csr &A, const T *B, long long ldb, T *C, long long ldc, int n, T alpha, T beta,
-                                            cudaStream_t st)
-        {
-            static const int env_nt = getenv("AOCLSPARSE_B200_MM_TILE_THREADS") ? atoi(getenv("AOCLSPARSE_B200_MM_TILE_THREADS")) : 0;
-            const long long  rows_per_block = A.tiles->plan.n_blocks > 0 ? (long long)A.m / A.tiles->plan.n_blocks + 1 : 1;
-            int              nt = rows_per_block * LPR <= 128 ? 128 : 256;
-            if(env_nt == 128 || env_nt == 256)
-                nt = env_nt;
-            if(nt == 128)
-                return launch_tiled_nt<T, CONJ, LPR, 128>(A, B, ldb, C, ldc, n, alpha, beta, st);
-            return launch_tiled_nt<T, CONJ, LPR, 256>(A, B, ldb, C, ldc, n, alpha, beta, st);
-        }
-
         // COLUMN MAJOR: B is (k x n) with column stride ldb, C is (m x n) with column stride ldc
         template <typename T, bool CONJ>
         __global__ void __launch_bounds__(MM_THREADS) csrmm_col_major_kernel(const int4 *__restrict__ desc,
@@ -1071,81 +555,6 @@ namespace b200
             return aoclsparse_status_success;
         }
 
-        template <typename T, bool CONJ, int K, int LPR, int NV>
-        aoclsparse_status launch_grouped_inst(const dev_csr &G,
-                                              int            m,
-                                              const T       *B,
-                                              long long      ldb,
-                                              T             *C,
-                                              long long      ldc,
-                                              int            n,
-                                              T              alpha,
-                                              T              beta,
-                                              cudaStream_t   st)
-        {
-            const row_block_plan &P    = G.plan;
-            const int             cap  = P.block_nnz + 8;
-            const size_t          smem = SMEM_HEADER + (size_t)cap * (K * sizeof(T) + sizeof(aoclsparse_int));
-            static std::atomic<size_t> cfg{0};
-            if(cfg.load() < smem)
-            {
-                B200_CUDA(cudaFuncSetAttribute(
-                    csrmm_grouped_kernel<T, CONJ, K, LPR, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                cfg.store(smem);
-            }
-            csrmm_grouped_kernel<T, CONJ, K, LPR, NV><<<P.n_blocks, MM_THREADS, smem, st>>>(P.desc.as<int4>(),
-                                                                                         cap,
-                                                                                         G.row_ptr.as<aoclsparse_int>(),
-                                                                                         G.col_idx.as<aoclsparse_int>(),
-                                                                                         G.val.as<T>(),
-                                                                                         B,
-                                                                                         ldb,
-                                                                                         C,
-                                                                                         ldc,
-                                                                                         n,
-                                                                                         m,
-                                                                                         alpha,
-                                                                                         beta,
-                                                                                         is_zero(beta) ? 1 : 0);
-            B200_LAUNCHED();
-            return aoclsparse_status_success;
-        }
-
-        // lanes per group: enough for the whole B row in one pass when it fits a warp
-        template <typename T, bool CONJ, int K>
-        aoclsparse_status launch_grouped(const dev_csr &G,
-                                         int            m,
-                                         const T       *B,
-                                         long long      ldb,
-                                         T             *C,
-                                         long long      ldc,
-                                         int            n,
-                                         T              alpha,
-                                         T              beta,
-                                         cudaStream_t   st)
-        {
-            constexpr int    VEC  = 16 / (int)sizeof(T);
-            const int        vecs = n / VEC;
-            const int        env_nv = getenv("AOCLSPARSE_B200_MM_GROUP_NV") ? atoi(getenv("AOCLSPARSE_B200_MM_GROUP_NV")) : 2;
-            if(env_nv == 1)
-            {
-                if(vecs <= 4)
-                    return launch_grouped_inst<T, CONJ, K, 4, 1>(G, m, B, ldb, C, ldc, n, alpha, beta, st);
-                if(vecs <= 8)
-                    return launch_grouped_inst<T, CONJ, K, 8, 1>(G, m, B, ldb, C, ldc, n, alpha, beta, st);
-                if(vecs <= 16)
-                    return launch_grouped_inst<T, CONJ, K, 16, 1>(G, m, B, ldb, C, ldc, n, alpha, beta, st);
-                return launch_grouped_inst<T, CONJ, K, 32, 1>(G, m, B, ldb, C, ldc, n, alpha, beta, st);
-            }
-            if(vecs <= 8)
-                return launch_grouped_inst<T, CONJ, K, 4, 2>(G, m, B, ldb, C, ldc, n, alpha, beta, st);
-            if(vecs <= 16)
-                return launch_grouped_inst<T, CONJ, K, 8, 2>(G, m, B, ldb, C, ldc, n, alpha, beta, st);
-            if(vecs <= 32)
-                return launch_grouped_inst<T, CONJ, K, 16, 2>(G, m, B, ldb, C, ldc, n, alpha, beta, st);
-            return launch_grouped_inst<T, CONJ, K, 32, 2>(G, m, B, ldb, C, ldc, n, alpha, beta, st);
-        }
-
         template <typename T, bool CONJ>
         aoclsparse_status launch_mm(const dev_csr   &A,
                                     aoclsparse_order order,
@@ -1161,34 +570,6 @@ namespace b200
             const row_block_plan &P = A.plan;
             if(P.n_blocks <= 0)
                 return aoclsparse_status_success;
-            {
-                // tiled kernel: B rows staged once per small row block (plan built by ensure_mm_tiles after a mm hint)
-                constexpr int VEC1 = 16 / (int)sizeof(T);
-                if(A.tiles_state > 0 && A.tiles && order == aoclsparse_order_row && (n % VEC1) == 0 && (ldb % VEC1) == 0
-                   && (ldc % VEC1) == 0 && ((uintptr_t)B % 16) == 0 && ((uintptr_t)C % 16) == 0
-                   && (size_t)A.tiles->max_uniq * n * sizeof(T) <= TILE_BUDGET)
-                {
-                    const int vecs = n / VEC1;
-                    if(vecs <= 8)
-                        return launch_tiled_inst<T, CONJ, 4>(A, B, ldb, C, ldc, n, alpha, beta, st);
-                    if(vecs <= 16)
-                        return launch_tiled_inst<T, CONJ, 8>(A, B, ldb, C, ldc, n, alpha, beta, st);
-                    if(vecs <= 32)
-                        return launch_tiled_inst<T, CONJ, 16>(A, B, ldb, C, ldc, n, alpha, beta, st);
-                    return launch_tiled_inst<T, CONJ, 32>(A, B, ldb, C, ldc, n, alpha, beta, st);
-                }
-            }
-            {
-                // row-grouped copy (built by aoclsparse_optimize after a mm hint): every B row is read once per K rows
-                constexpr int VEC0 = 16 / (int)sizeof(T);
-                if(A.group_k > 0 && A.grouped && order == aoclsparse_order_row && (n % VEC0) == 0 && (ldb % VEC0) == 0
-                   && (ldc % VEC0) == 0 && ((uintptr_t)B % 16) == 0 && ((uintptr_t)C % 16) == 0 && n >= 2 * VEC0)
-                {
-                    if(A.group_k == 2)
-                        return launch_grouped<T, CONJ, 2>(*A.grouped, A.m, B, ldb, C, ldc, n, alpha, beta, st);
-                    return launch_grouped<T, CONJ, 4>(*A.grouped, A.m, B, ldb, C, ldc, n, alpha, beta, st);
-                }
-            }
             const int    cap  = P.block_nnz + 8;
             const size_t smem = spmv_smem_bytes(sizeof(T), P.block_nnz);
             const int    bz   = is_zero(beta) ? 1 : 0;
@@ -1368,88 +749,6 @@ namespace b200
         return launch_mm<T, false>(*F, order, B, ldb, C, ldc, n, alpha, beta, st);
     }
 
-    // Builds (once per handle) the tile plan of the stored matrix: row blocks of <= 512 entries, their distinct columns as
-    // runs, a 16-bit slot per entry.  Usable only when every block is an ordinary one (no split rows).  tiles_state:
-    // 0 not analysed, -1 not usable, else the block size.  Caller holds the write lock.
-    aoclsparse_status ensure_mm_tiles(aoclsparse_matrix A, cudaStream_t st)
-    {
-        dev_csr &M = *A->mats[0];
-        if(M.tiles_state != 0)
-            return aoclsparse_status_success;
-        M.tiles_state = -1;
-        // OFF by default (AOCLSPARSE_B200_MM_TILES=1 enables it): correct for all four value types
-        // (tests/test_parity_gpu.py::test_csrmm_tiled_kernel) but measured slower than the plain kernel on the 27-point
-        // stencil x 32 doubles -- 1.07 ms at best (512-entry blocks, 256 threads) against 0.81 ms, profiles/r01_mm_sweep.txt:
-        // a CTA stages, then multiplies, and with ~50 KB of tile only two or three CTAs per SM overlap those phases.
-        const char *en = getenv("AOCLSPARSE_B200_MM_TILES");
-        if(!(en && atoi(en) != 0) || A->mem_policy != aoclsparse_memory_usage_unrestricted || M.nnz == 0 || M.m < 1024)
-            return aoclsparse_status_success;
-        std::unique_ptr<mm_tiles> Tl(new(std::nothrow) mm_tiles);
-        if(!Tl)
-            return aoclsparse_status_success;
-        int tile_nnz = TILE_MAX_NNZ;
-        if(const char *e = getenv("AOCLSPARSE_B200_MM_TILE_NNZ"))
-        {
-            const int v = atoi(e);
-            if(v >= 64 && v <= TILE_MAX_NNZ)
-                tile_nnz = v & ~7;
-        }
-        Tl->block_nnz = tile_nnz;
-        {
-            // a second row-block plan over the same row_ptr: lend the array to a temporary for the build
-            dev_csr tmp;
-            tmp.m       = M.m;
-            tmp.n       = M.n;
-            tmp.nnz     = M.nnz;
-            tmp.row_ptr = std::move(M.row_ptr);
-            const aoclsparse_status s = build_plan(tmp, value_size(A->val_type), -1, -1, std::vector<aoclsparse_int>(), st, tile_nnz);
-            M.row_ptr                 = std::move(tmp.row_ptr);
-            if(s != aoclsparse_status_success)
-                return s == aoclsparse_status_memory_error ? aoclsparse_status_success : s;
-            Tl->plan = std::move(tmp.plan);
-        }
-        const int nb = Tl->plan.n_blocks;
-        if(Tl->plan.n_long_rows > 0 || nb <= 0)
-            return aoclsparse_status_success;
-        dev_buf nruns;
-        if(Tl->uniq.alloc(sizeof(int) * (size_t)nb) != aoclsparse_status_success || nruns.alloc(sizeof(int) * (size_t)nb) != aoclsparse_status_success
-           || Tl->run_ptr.alloc(sizeof(int) * ((size_t)nb + 1)) != aoclsparse_status_success
-           || Tl->lidx.alloc(sizeof(unsigned short) * (size_t)M.nnz) != aoclsparse_status_success)
-            return aoclsparse_status_success; // no room: keep the plain kernel
-        tile_analyse_kernel<false><<<nb, 256, 0, st>>>(
-            Tl->plan.desc.as<int4>(), M.col_idx.as<int>(), Tl->uniq.as<int>(), nruns.as<int>(), nullptr, nullptr, nullptr);
-        B200_LAUNCHED();
-        std::vector<int> hu((size_t)nb), hr((size_t)nb), hp((size_t)nb + 1);
-        B200_CUDA(cudaMemcpyAsync(hu.data(), Tl->uniq.p, sizeof(int) * (size_t)nb, cudaMemcpyDeviceToHost, st));
-        B200_CUDA(cudaMemcpyAsync(hr.data(), nruns.p, sizeof(int) * (size_t)nb, cudaMemcpyDeviceToHost, st));
-        B200_CUDA(cudaStreamSynchronize(st));
-        long long total_runs = 0, total_uniq = 0;
-        int       mx         = 0;
-        for(int b = 0; b < nb; ++b)
-        {
-            hp[(size_t)b] = (int)total_runs;
-            total_runs += hr[(size_t)b];
-            total_uniq += hu[(size_t)b];
-            mx = hu[(size_t)b] > mx ? hu[(size_t)b] : mx;
-        }
-        hp[(size_t)nb] = (int)total_runs;
-        // worth it only if the blocks name clearly fewer B rows than they hold entries, in runs long enough for bulk
-        // copies (banded / mesh matrices); scattered patterns keep the plain kernel
-        if(total_runs > 0x7fffffffLL || total_uniq * 2 > (long long)M.nnz || total_runs * 4 > total_uniq)
-            return aoclsparse_status_success;
-        if(Tl->runs.alloc(sizeof(int4) * (size_t)(total_runs > 0 ? total_runs : 1)) != aoclsparse_status_success)
-            return aoclsparse_status_success;
-        B200_CUDA(cudaMemcpyAsync(Tl->run_ptr.p, hp.data(), sizeof(int) * ((size_t)nb + 1), cudaMemcpyHostToDevice, st));
-        tile_analyse_kernel<true><<<nb, 256, 0, st>>>(Tl->plan.desc.as<int4>(), M.col_idx.as<int>(), nullptr, nullptr, Tl->run_ptr.as<int>(),
-                                                      Tl->runs.as<int4>(), Tl->lidx.as<unsigned short>());
-        B200_LAUNCHED();
-        B200_CUDA(cudaStreamSynchronize(st));
-        Tl->max_uniq  = mx;
-        M.tiles_state = tile_nnz;
-        M.tiles       = std::move(Tl);
-        return aoclsparse_status_success;
-    }
-
     template <typename T>
     aoclsparse_status csrmm_entry(aoclsparse_operation       op,
                                   T                          alpha,
@@ -1555,27 +854,7 @@ namespace b200
                     status = csrmm_symmetric<T>(op, alpha, A, *descr, order, dB, ldb, beta, dC, ldc, n, st);
                 else if(!trans_s)
                 {
-                    if(A->want_grouped)
-                    {
-                        // a mm hint was optimized: the derived plans of the stored matrix are built on first use (and the
-                        // row-grouped copy again after its values were replaced)
-                        bool missing;
-                        {
-                            std::shared_lock<std::shared_mutex> rl0(A->guard);
-                            missing = A->mats[0]->group_k == 0 || A->mats[0]->tiles_state == 0;
-                        }
-                        if(missing)
-                        {
-                            std::unique_lock<std::shared_mutex> wl(A->guard);
-                            status = ensure_grouped(A, st);
-                            if(status == aoclsparse_status_success)
-                                status = ensure_mm_tiles(A, st);
-                        }
-                    }
                     std::shared_lock<std::shared_mutex> rl(A->guard);
-                    if(status != aoclsparse_status_success)
-                        ;
-                    else
                     if(conj_op)
                         status = launch_mm<T, true>(*A->mats[0], order, dB, ldb, dC, ldc, n, alpha, beta, st);
                     else

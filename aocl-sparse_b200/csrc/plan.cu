@@ -311,20 +311,6 @@ namespace b200
             P.stream_hint = atoi(e) ? 1 : 0;
         if(const char *e = getenv("AOCLSPARSE_B200_PDL"))
             P.pdl = atoi(e) ? 1 : 0;
-        if(const char *e = getenv("AOCLSPARSE_B200_PIPELINE"))
-            P.pipelined = atoi(e) ? 1 : 0;
-        if(const char *e = getenv("AOCLSPARSE_B200_PIPE_STAGES"))
-        {
-            const int v = atoi(e);
-            if(v >= 2 && v <= 8)
-                P.pipe_stages = v;
-        }
-        if(const char *e = getenv("AOCLSPARSE_B200_PIPE_CTAS"))
-        {
-            const int v = atoi(e);
-            if(v >= 1 && v <= 4)
-                P.pipe_ctas_per_sm = v;
-        }
         const aoclsparse_int *rp = A.row_ptr.as<aoclsparse_int>();
 
         if(A.m == 0)

@@ -1002,18 +1002,21 @@ namespace b200
                 have_tiers          = s == aoclsparse_status_success;
                 if(s == aoclsparse_status_success && opflag == 3)
                 {
-                    // the product is kept beside the result until it is finalized; the result's own arrays are sized now
-                    (*C)->mats.push_back(P);
-                    P->doid    = DOID_GT;
-                    dev_csr &M = *(*C)->mats[0];
-                    M.nnz      = P->nnz;
-                    s          = M.row_ptr.alloc(sizeof(int) * ((size_t)m_a + 1));
+                    // the product B A is kept in the handle (its own field: value updates of C drop the derived copies
+                    // in mats[1..], not this) until and across finalize calls; the result's pattern is its transpose,
+                    // so row_ptr / col_idx are already the final ones after the count stage (values: finalize)
+                    (*C)->sp2m_product.reset(P);
+                    P->doid = DOID_GT;
+                    dev_csr Tr;
+                    s = transpose_csr(*P, (*C)->val_type, false, Tr, st);
                     if(s == aoclsparse_status_success)
-                        s = M.col_idx.alloc(sizeof(int) * (size_t)P->nnz);
-                    if(s == aoclsparse_status_success)
-                        s = M.val.alloc(sizeof(T) * (size_t)P->nnz);
-                    if(s == aoclsparse_status_success)
-                        s = cuda_status(cudaMemsetAsync(M.row_ptr.p, 0, sizeof(int) * ((size_t)m_a + 1), st), "spgemm memset");
+                    {
+                        dev_csr &M = *(*C)->mats[0];
+                        M.row_ptr  = std::move(Tr.row_ptr);
+                        M.col_idx  = std::move(Tr.col_idx);
+                        M.val      = std::move(Tr.val);
+                        M.nnz      = P->nnz;
+                    }
                 }
                 else if(opflag == 3)
                     delete P;
@@ -1033,9 +1036,9 @@ namespace b200
             aoclsparse_matrix H = *C;
             if(opflag == 3)
             {
-                if(H->mats.size() < 2 || H->mats[1]->doid != DOID_GT)
+                if(!H->sp2m_product)
                     return aoclsparse_status_invalid_pointer;
-                dev_csr &P = *H->mats[1];
+                dev_csr &P = *H->sp2m_product;
                 B200_TRY(numeric<T>(*L.M, *R.M, L.conj, R.conj, P, have_tiers ? &tiers : nullptr, st));
                 dev_csr Tr;
                 B200_TRY(transpose_csr(P, H->val_type, false, Tr, st));
@@ -1053,6 +1056,12 @@ namespace b200
                 B200_TRY(numeric<T>(*L.M, *R.M, L.conj, R.conj, M, have_tiers ? &tiers : nullptr, st));
             }
             phase_trace tr(st);
+            {
+                // a repeated finalize is the documented way to refresh the values of C: copies derived from the old
+                // values (transposed / expanded / clean, built by earlier mv / csrmm calls on C) must not survive it
+                std::unique_lock<std::shared_mutex> wl(H->guard);
+                drop_derived_copies(H);
+            }
             B200_TRY(finish_handle(H, true, st));
             B200_CUDA(cudaStreamSynchronize(st));
             tr.mark("classify result (check.cu)");
@@ -1233,17 +1242,8 @@ aoclsparse_status aoclsparse_order_mat(aoclsparse_matrix mat)
     if(s != aoclsparse_status_success)
         return s;
     // derived copies and analyses follow the old entry order
-    for(size_t i = 1; i < mat->mats.size(); ++i)
-        delete mat->mats[i];
-    mat->mats.resize(1);
-    mat->clean = clean_csr();
-    M.grouped.reset();
-    M.group_k     = 0;
-    M.tiles.reset();
-    M.tiles_state = 0;
+    drop_derived_copies(mat);
     M.plan.valid  = false;
-    for(auto &h : mat->hints)
-        h.done = false;
     mat->sort = aoclsparse_fully_sorted;
     return aoclsparse_status_success;
 }

@@ -5,11 +5,11 @@
 //   aoclsparse_csrmv_t<T,false>  library/src/level2/aoclsparse_csrmv.hpp:32-450
 // and launches the sm_100a kernels of spmv_kernels.cuh.  There is no CPU path: if a launch fails the
 // call returns internal_error.
-#include "spmv_pipelined.cuh"
 #include "spmv_sharded.cuh"
 
 #include <chrono>
 #include <cstdlib>
+#include <map>
 #include <unordered_map>
 
 namespace b200
@@ -40,7 +40,29 @@ namespace b200
             return aoclsparse_status_success;
         }
 
-        template <typename T, bool GENERIC, int NT, bool PUSH = false, bool HOT = false>
+        // CTAs of `kernel` that can be resident on the whole device at once (per kernel / shared-memory size, cached)
+        template <typename K>
+        long long resident_ctas(K kernel, int threads, size_t smem)
+        {
+            static std::mutex                       mu;
+            static std::map<std::pair<const void *, size_t>, long long> cache;
+            std::lock_guard<std::mutex>             lk(mu);
+            const auto                              key = std::make_pair(reinterpret_cast<const void *>(kernel), smem);
+            auto                                    it  = cache.find(key);
+            if(it != cache.end())
+                return it->second;
+            int per_sm = 0, sms = 148, dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1)
+            {
+                cudaGetLastError();
+                per_sm = 32; // unknown: assume the hardware maximum, i.e. be conservative about overlapping launches
+            }
+            return cache[key] = (long long)per_sm * sms;
+        }
+
+        template <typename T, bool GENERIC, int NT, bool PUSH = false>
         aoclsparse_status launch_row_blocks(const dev_csr &A,
                                             int            b0,
                                             int            b1,
@@ -51,8 +73,7 @@ namespace b200
                                             elem_rule      rule,
                                             cudaStream_t   st,
                                             T             *push_dst  = nullptr,
-                                            int            push_row0 = 0,
-                                            const T       *xh        = nullptr)
+                                            int            push_row0 = 0)
         {
             const row_block_plan &P    = A.plan;
             const int             cap  = P.block_nnz + 8;
@@ -61,7 +82,7 @@ namespace b200
             if(configured.load(std::memory_order_acquire) < smem)
             {
                 B200_CUDA(cudaFuncSetAttribute(
-                    spmv_row_blocks_kernel<T, GENERIC, NT, PUSH, HOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    spmv_row_blocks_kernel<T, GENERIC, NT, PUSH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 configured.store(smem, std::memory_order_release);
             }
             cudaLaunchConfig_t cfg = {};
@@ -73,15 +94,21 @@ namespace b200
             attr[0].id                                         = cudaLaunchAttributeProgrammaticStreamSerialization;
             attr[0].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs                                          = attr;
-            cfg.numAttrs                                       = P.pdl ? 1 : 0;
+            // Programmatic dependent launch only for grids of more than one wave.  The kernel signals
+            // launch_dependents at entry, so with a sub-wave grid three consecutive launches of an iterated product
+            // could be resident at once, and launch k-2 (still reading the buffer launch k-1 is about to overwrite)
+            // could leave lines in an SM's L1 that launch k then hits through ld.global.nc after its
+            // griddepcontrol.wait.  With more CTAs than fit the chip, the last CTA of launch k-1 cannot start before
+            // launch k-2 has completed, so launch k (which starts after it) never overlaps k-2.
+            cfg.numAttrs = (P.pdl && (long long)(b1 - b0) > resident_ctas(spmv_row_blocks_kernel<T, GENERIC, NT, PUSH>, NT, smem)) ? 1 : 0;
             B200_CUDA(cudaLaunchKernelEx(&cfg,
-                                         spmv_row_blocks_kernel<T, GENERIC, NT, PUSH, HOT>,
+                                         spmv_row_blocks_kernel<T, GENERIC, NT, PUSH>,
                                          (const int4 *)P.desc.as<int4>(),
                                          (const int *)P.kind.as<int>(),
                                          b0,
                                          cap,
                                          (const aoclsparse_int *)A.row_ptr.as<aoclsparse_int>(),
-                                         (const aoclsparse_int *)(HOT ? P.col_hot.as<aoclsparse_int>() : A.col_idx.as<aoclsparse_int>()),
+                                         (const aoclsparse_int *)A.col_idx.as<aoclsparse_int>(),
                                          (const T *)A.val.as<T>(),
                                          x,
                                          y,
@@ -93,54 +120,7 @@ namespace b200
                                          (int)A.n,
                                          P.stream_hint,
                                          push_dst,
-                                         push_row0,
-                                         xh));
-            B200_LAUNCHED();
-            return aoclsparse_status_success;
-        }
-
-        // persistent pipelined kernel (spmv_pipelined.cuh) over blocks [b0, b1): all of them thread-per-row
-        template <typename T>
-        aoclsparse_status launch_pipelined(const dev_csr &A,
-                                           int            b0,
-                                           int            b1,
-                                           const T       *x,
-                                           T             *y,
-                                           T              alpha,
-                                           T              beta,
-                                           cudaStream_t   st,
-                                           T             *push_dst,
-                                           int            push_row0)
-        {
-            const row_block_plan &P      = A.plan;
-            const int             cap    = P.block_nnz + 8;
-            const int             stages = P.pipe_stages;
-            const size_t          smem   = pipe_smem_bytes(sizeof(T), P.block_nnz, stages);
-            static std::atomic<size_t> configured{0};
-            if(configured.load(std::memory_order_acquire) < smem)
-            {
-                B200_CUDA(cudaFuncSetAttribute(
-                    spmv_thread_pipelined_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                configured.store(smem, std::memory_order_release);
-            }
-            int grid = P.pipe_ctas_per_sm * 148;
-            if(grid > b1 - b0)
-                grid = b1 - b0;
-            spmv_thread_pipelined_kernel<T><<<grid, PIPE_THREADS, smem, st>>>(P.desc.as<int4>(),
-                                                                              b0,
-                                                                              b1,
-                                                                              cap,
-                                                                              stages,
-                                                                              A.row_ptr.as<aoclsparse_int>(),
-                                                                              A.col_idx.as<aoclsparse_int>(),
-                                                                              A.val.as<T>(),
-                                                                              x,
-                                                                              y,
-                                                                              alpha,
-                                                                              beta,
-                                                                              is_zero(beta) ? 1 : 0,
-                                                                              push_dst,
-                                                                              push_row0);
+                                         push_row0));
             B200_LAUNCHED();
             return aoclsparse_status_success;
         }
@@ -165,36 +145,6 @@ namespace b200
             if(b1 <= b0)
                 return aoclsparse_status_success;
             const int bz = is_zero(beta) ? 1 : 0;
-            if(!generic && !push_dst && P.hot_entries > 0 && b0 == 0 && b1 == P.n_blocks)
-            {
-                if(P.hot_mode == 2)
-                    B200_TRY(launch_hot<T>(A, x, y, alpha, beta, st)); // persistent shared-memory table (experiment)
-                else
-                {
-                    // pack the hot entries of x into the dense side vector, then the ordinary kernel on the remapped
-                    // column array
-                    // scratch per (host thread, stream): concurrent multiplies on one handle must not share it
-                    static thread_local std::unordered_map<cudaStream_t, dev_buf> scratch;
-                    dev_buf &hb = scratch[st];
-                    if(hb.bytes < sizeof(T) * (size_t)P.hot_entries)
-                        B200_TRY(hb.alloc(sizeof(T) * (size_t)P.hot_entries));
-                    T *xh = hb.as<T>();
-                    pack_hot_x_kernel<T><<<(P.hot_entries + 255) / 256, 256, 0, st>>>(
-                        P.hot_entries, P.hot_cols.as<aoclsparse_int>(), x, xh);
-                    B200_LAUNCHED();
-                    B200_TRY((launch_row_blocks<T, false, 256, false, true>(A, b0, b1, x, y, alpha, beta, rule, st, nullptr, 0, xh)));
-                }
-                if(P.n_long_rows > 0)
-                {
-                    const long long threads = (long long)P.n_long_rows * 32;
-                    finish_long_rows_kernel<T><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(
-                        P.n_long_rows, P.long_rows.as<int4>(), P.partials.as<T>(), x, y, alpha, beta, bz, 0, A.n, row_lo, row_hi);
-                    B200_LAUNCHED();
-                }
-                return aoclsparse_status_success;
-            }
-            if(!generic && P.pipelined && P.n_strat[STRAT_THREAD] == P.n_blocks)
-                return launch_pipelined<T>(A, b0, b1, x, y, alpha, beta, st, push_dst, row_lo);
             if(push_dst)
                 B200_TRY((launch_row_blocks<T, false, 256, true>(A, b0, b1, x, y, alpha, beta, rule, st, push_dst, row_lo)));
             else if(generic)
@@ -1030,15 +980,7 @@ namespace b200
         if(!found)
             return aoclsparse_status_invalid_index_value;
         // derived copies hold the old value (the reference drops them too, auxiliary.hpp:463-471)
-        for(size_t i = 1; i < A->mats.size(); ++i)
-            delete A->mats[i];
-        A->mats.resize(1);
-        A->clean = clean_csr();
-        A->mats[0]->grouped.reset();
-        if(A->mats[0]->group_k > 0)
-            A->mats[0]->group_k = 0;
-        for(auto &h : A->hints)
-            h.done = false;
+        drop_derived_copies(A);
         return aoclsparse_status_success;
     }
 }
@@ -1334,7 +1276,8 @@ aoclsparse_status aoclsparse_b200_dmv_sharded_step(const double                 
     attr[0].id                                         = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs                                          = attr;
-    cfg.numAttrs                                       = P.pdl ? 1 : 0;
+    // more than one wave only: see launch_row_blocks
+    cfg.numAttrs = (P.pdl && (long long)P.n_blocks > resident_ctas(spmv_sharded_step_kernel<double>, 256, smem)) ? 1 : 0;
     B200_CUDA(cudaLaunchKernelEx(&cfg,
                                  spmv_sharded_step_kernel<double>,
                                  (const int4 *)P.desc.as<int4>(),

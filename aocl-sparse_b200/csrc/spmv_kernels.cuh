@@ -124,87 +124,6 @@ namespace b200
         return __ldg(p);
     }
 
-    // x[c] for the measured hot path.  HOT: the analysis (hot.cu) replaced the most frequent columns by
-    // (0x80000000 | slot); their x values were packed by a small pre-pass into the dense side vector xh, which is
-    // small enough (<= 96 KB) to live in L1.  Packed entries are loaded with L1 evict-last priority, the scattered rest
-    // with evict-first, so the random traffic does not push the packed lines out.
-    template <typename T>
-    __device__ __forceinline__ T ld_l1_evict_last(const T *p);
-    template <>
-    __device__ __forceinline__ float ld_l1_evict_last<float>(const float *p)
-    {
-        float v;
-        asm volatile("ld.global.nc.L1::evict_last.f32 %0, [%1];" : "=f"(v) : "l"(p));
-        return v;
-    }
-    template <>
-    __device__ __forceinline__ double ld_l1_evict_last<double>(const double *p)
-    {
-        double v;
-        asm volatile("ld.global.nc.L1::evict_last.f64 %0, [%1];" : "=d"(v) : "l"(p));
-        return v;
-    }
-    template <>
-    __device__ __forceinline__ float2 ld_l1_evict_last<float2>(const float2 *p)
-    {
-        float2 v;
-        asm volatile("ld.global.nc.L1::evict_last.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
-        return v;
-    }
-    template <>
-    __device__ __forceinline__ double2 ld_l1_evict_last<double2>(const double2 *p)
-    {
-        double2 v;
-        asm volatile("ld.global.nc.L1::evict_last.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
-        return v;
-    }
-    template <typename T>
-    __device__ __forceinline__ T ld_l1_evict_first(const T *p);
-    template <>
-    __device__ __forceinline__ float ld_l1_evict_first<float>(const float *p)
-    {
-        float v;
-        asm volatile("ld.global.nc.L1::evict_first.f32 %0, [%1];" : "=f"(v) : "l"(p));
-        return v;
-    }
-    template <>
-    __device__ __forceinline__ double ld_l1_evict_first<double>(const double *p)
-    {
-        double v;
-        asm volatile("ld.global.nc.L1::evict_first.f64 %0, [%1];" : "=d"(v) : "l"(p));
-        return v;
-    }
-    template <>
-    __device__ __forceinline__ float2 ld_l1_evict_first<float2>(const float2 *p)
-    {
-        float2 v;
-        asm volatile("ld.global.nc.L1::evict_first.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
-        return v;
-    }
-    template <>
-    __device__ __forceinline__ double2 ld_l1_evict_first<double2>(const double2 *p)
-    {
-        double2 v;
-        asm volatile("ld.global.nc.L1::evict_first.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
-        return v;
-    }
-    template <typename T, bool HOT>
-    __device__ __forceinline__ T xgather(const T *__restrict__ x, const T *__restrict__ xh, int c)
-    {
-        if constexpr(HOT)
-        {
-#ifdef B200_HOT_L1_PRIORITIES
-            return c < 0 ? ld_l1_evict_last(xh + (c & 0x7fffffff)) : ld_l1_evict_first(x + c);
-#else
-            // one load instruction for both cases: the packed vector and x are just two base addresses
-            const T *p = c < 0 ? xh + (c & 0x7fffffff) : x + c;
-            return ldg_ro(p);
-#endif
-        }
-        else
-            return ldg_ro(x + c);
-    }
-
     // acc + op(v) * x[col] if the entry (row, col) takes part under `rl`, else acc
     template <typename T>
     __device__ __forceinline__ T generic_term(const elem_rule &rl, int row, int col, T v, const T *__restrict__ x, T acc)
@@ -256,8 +175,7 @@ namespace b200
     // PUSH == true: every computed y[r] is also stored to push_dst[r - push_row0], a buffer that may live in a
     //                PEER GPU's memory (mapped over NVLink): the boundary rows of a row-sharded matrix write the
     //                neighbour's halo of the next x directly from this epilogue -- no separate copy or collective.
-    // HOT == true (never together with GENERIC / PUSH): `col` is the remapped column array, xh the packed hot x values
-    template <typename T, bool GENERIC, int NT, bool PUSH = false, bool HOT = false>
+    template <typename T, bool GENERIC, int NT, bool PUSH = false>
     __global__ void __launch_bounds__(NT) spmv_row_blocks_kernel(const int4 *__restrict__ desc,
                                                                           const int *__restrict__ kind,
                                                                           int block_first,
@@ -275,8 +193,7 @@ namespace b200
                                                                           int       n_cols,
                                                                           int       stream_hint,
                                                                           T        *push_dst  = nullptr,
-                                                                          int       push_row0 = 0,
-                                                                          const T *__restrict__ xh = nullptr)
+                                                                          int       push_row0 = 0)
     {
         extern __shared__ __align__(16) unsigned char smem_raw[];
         uint64_t       *bar  = reinterpret_cast<uint64_t *>(smem_raw);
@@ -350,15 +267,15 @@ namespace b200
                     for(; j + 4 <= e; j += 4)
                     {
                         const int c0 = scol[j], c1 = scol[j + 1], c2 = scol[j + 2], c3 = scol[j + 3];
-                        const T   x0 = xgather<T, HOT>(x, xh, c0), x1 = xgather<T, HOT>(x, xh, c1), x2 = xgather<T, HOT>(x, xh, c2),
-                                  x3 = xgather<T, HOT>(x, xh, c3);
+                        const T   x0 = ldg_ro(x + c0), x1 = ldg_ro(x + c1), x2 = ldg_ro(x + c2),
+                                  x3 = ldg_ro(x + c3);
                         acc          = mad(sval[j], x0, acc);
                         acc          = mad(sval[j + 1], x1, acc);
                         acc          = mad(sval[j + 2], x2, acc);
                         acc          = mad(sval[j + 3], x3, acc);
                     }
                     for(; j < e; ++j)
-                        acc = mad(sval[j], xgather<T, HOT>(x, xh, scol[j]), acc);
+                        acc = mad(sval[j], ldg_ro(x + scol[j]), acc);
                 }
                 else
                 {
@@ -383,7 +300,7 @@ namespace b200
                 {
                     const int c = scol[j];
                     if constexpr(!GENERIC)
-                        acc = mad(sval[j], xgather<T, HOT>(x, xh, c), acc);
+                        acc = mad(sval[j], ldg_ro(x + c), acc);
                     else
                         acc = generic_term(rule, r, c, sval[j], x, acc);
                 }
@@ -410,7 +327,7 @@ namespace b200
                 for(int i = tid; i < total; i += NT)
                 {
                     const int j = first + i;
-                    sval[j]     = mul(sval[j], xgather<T, HOT>(x, xh, scol[j]));
+                    sval[j]     = mul(sval[j], ldg_ro(x + scol[j]));
                 }
                 __syncthreads();
             }
@@ -478,7 +395,7 @@ namespace b200
                 const int j = first + i;
                 const int c = scol[j];
                 if constexpr(!GENERIC)
-                    acc = mad(sval[j], xgather<T, HOT>(x, xh, c), acc);
+                    acc = mad(sval[j], ldg_ro(x + c), acc);
                 else
                     acc = generic_term(rule, r, c, sval[j], x, acc);
             }
@@ -551,15 +468,6 @@ namespace b200
                 r = mad(alpha, x[i], r);
             y[i] = r;
         }
-    }
-
-    // pre-pass of the hot-column path: xh[slot] = x[hot_cols[slot]]
-    template <typename T>
-    static __global__ void pack_hot_x_kernel(int k, const aoclsparse_int *__restrict__ hot_cols, const T *__restrict__ x, T *__restrict__ xh)
-    {
-        const int i = blockIdx.x * blockDim.x + threadIdx.x;
-        if(i < k)
-            xh[i] = x[hot_cols[i]];
     }
 
     // cross-GPU flags for the row-sharded iteration: a rank publishes "iteration k done" into a word that lives in

@@ -127,27 +127,57 @@ namespace b200
 
         T *push = side == 0 ? push_left : (side == 1 ? push_right : nullptr);
         const int push_row0 = side == 0 ? 0 : hc.last_row0;
-        for(int r = d.x + tid; r < d.y; r += NT)
+        if(side == 2)
         {
-            const bool first = r == d.x + tid;
-            int        j     = (first ? pre_s : rp[r]) - a;
-            const int  e     = (first ? pre_e : rp[r + 1]) - a;
-            T          acc   = vt<T>::zero();
-            for(; j + 4 <= e; j += 4)
+            // interior rows: every x entry they name was written by the previous LOCAL launch, which has completed
+            // (griddepcontrol.wait) -> read-only path through L1
+            for(int r = d.x + tid; r < d.y; r += NT)
             {
-                const int c0 = scol[j], c1 = scol[j + 1], c2 = scol[j + 2], c3 = scol[j + 3];
-                const T   x0 = ldg_ro(x + c0), x1 = ldg_ro(x + c1), x2 = ldg_ro(x + c2), x3 = ldg_ro(x + c3);
-                acc          = mad(sval[j], x0, acc);
-                acc          = mad(sval[j + 1], x1, acc);
-                acc          = mad(sval[j + 2], x2, acc);
-                acc          = mad(sval[j + 3], x3, acc);
+                const bool first = r == d.x + tid;
+                int        j     = (first ? pre_s : rp[r]) - a;
+                const int  e     = (first ? pre_e : rp[r + 1]) - a;
+                T          acc   = vt<T>::zero();
+                for(; j + 4 <= e; j += 4)
+                {
+                    const int c0 = scol[j], c1 = scol[j + 1], c2 = scol[j + 2], c3 = scol[j + 3];
+                    const T   x0 = ldg_ro(x + c0), x1 = ldg_ro(x + c1), x2 = ldg_ro(x + c2), x3 = ldg_ro(x + c3);
+                    acc          = mad(sval[j], x0, acc);
+                    acc          = mad(sval[j + 1], x1, acc);
+                    acc          = mad(sval[j + 2], x2, acc);
+                    acc          = mad(sval[j + 3], x3, acc);
+                }
+                for(; j < e; ++j)
+                    acc = mad(sval[j], ldg_ro(x + scol[j]), acc);
+                y[r] = mul(alpha, acc);
             }
-            for(; j < e; ++j)
-                acc = mad(sval[j], ldg_ro(x + scol[j]), acc);
-            const T out = mul(alpha, acc);
-            y[r]        = out;
-            if(push)
-                push[r - push_row0] = out;
+        }
+        else
+        {
+            // boundary rows: the halo part of x is stored by the PEER GPU while this grid is already running, so it
+            // must not go through the non-coherent path (ld.global.nc requires the data to be read-only for the
+            // kernel's lifetime): ld.global.cg reads at the L2, the coherence point the peer's stores arrive at
+            for(int r = d.x + tid; r < d.y; r += NT)
+            {
+                const bool first = r == d.x + tid;
+                int        j     = (first ? pre_s : rp[r]) - a;
+                const int  e     = (first ? pre_e : rp[r + 1]) - a;
+                T          acc   = vt<T>::zero();
+                for(; j + 4 <= e; j += 4)
+                {
+                    const int c0 = scol[j], c1 = scol[j + 1], c2 = scol[j + 2], c3 = scol[j + 3];
+                    const T   x0 = __ldcg(x + c0), x1 = __ldcg(x + c1), x2 = __ldcg(x + c2), x3 = __ldcg(x + c3);
+                    acc          = mad(sval[j], x0, acc);
+                    acc          = mad(sval[j + 1], x1, acc);
+                    acc          = mad(sval[j + 2], x2, acc);
+                    acc          = mad(sval[j + 3], x3, acc);
+                }
+                for(; j < e; ++j)
+                    acc = mad(sval[j], __ldcg(x + scol[j]), acc);
+                const T out = mul(alpha, acc);
+                y[r]        = out;
+                if(push)
+                    push[r - push_row0] = out;
+            }
         }
 
         // ---- completion bookkeeping (boundary CTAs only): the last one of a side tells that neighbour

@@ -7,18 +7,26 @@ A "step" is one pass of the hot path (one aoclsparse_?mv / aoclsparse_dcsrmm cal
 matrix of a BASELINE.json configuration (SURVEY.md section 8(d) defines the inputs):
 
   c1  2D 5-point Laplacian 1000^2, double, y = A x + 0.5 y
-  c2  3D 27-point stencil 128^3, double, set_mv_hint + optimize, y = A x          <- default at N = 1
+  c2  3D 27-point stencil 128^3, double, set_mv_hint + optimize, y = A x
   c3  R-MAT scale 24 edge factor 16, float, y = A x
   c4  csrmm: c2's matrix times a dense 2 097 152 x 32 row-major block, double
   c5  3D 7-point stencil 512^3, double, rows sharded over the N GPUs, x_{k+1} = A x_k / 12 with a halo
-      exchange per step (NCCL send/recv between neighbouring ranks)                <- default at N > 1
+      exchange per step                                                     <- the line's `value` at every N
+
+BASELINE.json quotes its metric "at 1/2/4/8 B200", i.e. on c5 (it fits one GPU: 11.3 GB of CSR), so c5 is what
+`value` measures at N = 1 as well: the 1 -> 8 series is one workload.  With no --workload at N = 1 the other four
+configurations are measured in the same run and carried in the `configs` object (each with its own value,
+ms_per_step, roofline, e2e and cpu_baseline).
 
 Keys follow the driver contract: `value` = whole-job GFLOP/s with operands resident in HBM, timed with
-CUDA events, max over ranks; `e2e` = the same metric through the C ABI with HOST x / y (pinned), the
-host<->device copies inside the timed region; `roofline` = algorithmic bytes per launch (the reference's
-own byte model, tests/include/aoclsparse_gbyte.hpp:39-86) / measured launch duration against the measured
-HBM copy bandwidth; `cpu_baseline` = the reference's own CPU implementation (oracle/_ref, built from the
-reference's sources) timed on this box's host cores.  --impl reference prints that CPU run as its own line.
+CUDA events, max over ranks; `e2e` = the same metric through the C ABI with HOST x / y (pinned; the pageable
+figure beside it), the host<->device copies inside the timed region; `roofline` = algorithmic bytes per launch
+(the reference's own byte model, tests/include/aoclsparse_gbyte.hpp:39-86) / measured launch duration against
+the measured HBM copy bandwidth; `cpu_baseline` = the reference's own CPU implementation (oracle/_ref, built
+from the reference's sources) timed on this box's host cores in a child process with the OpenMP environment of
+SURVEY.md section 8(d).  --impl reference prints that CPU run as its own line.  At N > 1 the timed loop is followed
+by a bitwise check of the fused multiply + halo-push kernel against the un-fused aoclsparse_dmv + NCCL halo path
+(`parity`).
 """
 import argparse
 import ctypes as C
@@ -36,6 +44,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import numpy as np  # noqa: E402
 
+METRIC = "CSR dmv GFLOP/s + effective HBM GB/s (% of 8 TB/s) at 1/2/4/8 B200"
 WORKLOADS = {
     "c1": dict(name="c1: 2D 5-point Laplacian 1000^2, CSR double, y=A*x+0.5*y (aoclsparse_dmv)", kind="mv",
                stencil=(5, 1000, 1000, 1), prefix="d", alpha=1.0, beta=0.5),
@@ -50,6 +59,7 @@ WORKLOADS = {
 }
 ELEM = {"s": 4, "d": 8, "c": 8, "z": 16}
 L2_BYTES = 126 * 1000 * 1000
+C5_SAMPLE_PLANES = 64  # CPU arm on c5: the slab one of 8 ranks owns (1/8 of the matrix, 16.8 M rows, 117 M entries)
 
 
 def spmv_bytes_flops(m, n, nnz, elem, beta_nonzero):
@@ -128,40 +138,101 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the reference's own CPU implementation on the host cores
 # --------------------------------------------------------------------------------------------------
-def host_matrix(wl, sample_planes=None):
-    """numpy CSR of the workload (or of a slab of it for c5 / a smaller scale for c3), plus a description"""
+def host_topology():
+    """(cpu model, {socket: [one hardware thread per physical core]}) restricted to the CPUs this process may use"""
+    model = "unknown"
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                model = ln.split(":", 1)[1].strip()
+                break
+    except OSError:
+        pass
+    allowed = sorted(os.sched_getaffinity(0))
+    sockets = {}
+    seen = set()
+    for c in allowed:
+        base = f"/sys/devices/system/cpu/cpu{c}/topology"
+        try:
+            pkg = int(open(f"{base}/physical_package_id").read())
+            core = int(open(f"{base}/core_id").read())
+        except (OSError, ValueError):
+            pkg, core = 0, c
+        if (pkg, core) in seen:
+            continue
+        seen.add((pkg, core))
+        sockets.setdefault(pkg, []).append(c)
+    return model, sockets, len(allowed)
+
+
+def reference_env():
+    """OpenMP environment of SURVEY.md 8(d) for the reference's kernels: all physical cores of one socket, bound.
+    Returns (env updates, cpus to pin the process to, description)."""
+    model, sockets, logical = host_topology()
+    pkg = min(sockets) if sockets else 0
+    cpus = sockets.get(pkg, sorted(os.sched_getaffinity(0)))
+    nt = len(cpus)
+    env = {"OMP_NUM_THREADS": str(nt), "AOCLSPARSE_NUM_THREADS": str(nt), "OMP_PROC_BIND": "close",
+           "OMP_PLACES": "cores", "OMP_DYNAMIC": "false"}
+    desc = {"cpu_model": model, "sockets": len(sockets) or 1, "physical_cores_socket0": nt, "logical_cpus": logical}
+    return env, cpus, desc
+
+
+def host_matrix(wl):
+    """numpy CSR of the workload (a slab of it for c5 / a smaller scale for c3), plus a description"""
     import gen_np
     if "stencil" in wl:
         pts, nx, ny, nz = wl["stencil"]
-        if sample_planes and nz > sample_planes:
+        if wl.get("sharded") and nz > C5_SAMPLE_PLANES:
             lo = (nz // 2) * nx * ny
-            hi = lo + sample_planes * nx * ny
+            hi = lo + C5_SAMPLE_PLANES * nx * ny
             rp, col, val = gen_np.stencil(pts, nx, ny, nz, lo, hi)
-            return rp, col, val, hi - lo, nx * ny * nz, f"rows [{lo},{hi}) ({sample_planes} of {nz} grid planes) of the matrix"
+            return rp, col, val, hi - lo, nx * ny * nz, (f"SAMPLE: rows [{lo},{hi}) ({C5_SAMPLE_PLANES} of {nz} grid planes, the slab "
+                                                        f"one of {nz // C5_SAMPLE_PLANES} ranks owns) of the matrix, whole x")
         rp, col, val = gen_np.stencil(pts, nx, ny, nz)
         return rp, col, val, len(rp) - 1, len(rp) - 1, "the full matrix"
     scale = min(wl["rmat"], 20)
     rp, col, val = gen_np.rmat_csr(scale)
-    return rp, col, val, len(rp) - 1, len(rp) - 1, f"R-MAT scale {scale} (same generator, fewer vertices)"
+    return rp, col, val, len(rp) - 1, len(rp) - 1, f"SAMPLE: R-MAT scale {scale} (same generator, fewer vertices)"
 
 
 def run_reference_cpu(wl, steps, warmup):
     """times oracle/_ref/libaoclsparse_ref.so (the reference compiled from its own sources); falls back to
-    the scalar oracle port only if that file is absent.  Returns (gflops, ms_per_step, info dict)."""
+    the scalar oracle port only if that file is absent.  Returns (gflops, ms_per_step, info dict).  Runs inside the
+    child process prepared by reference_child(): pinned to the physical cores of one socket before the arrays are
+    first touched, OpenMP environment set before libgomp loads."""
     import capi
     import gen_np
     import oracle_py
     p = wl["prefix"]
     dt = {"s": np.float32, "d": np.float64}[p]
-    rp, col, val, m, n, sample = host_matrix(wl, sample_planes=32 if wl.get("sharded") else None)
+    rp, col, val, m, n, sample = host_matrix(wl)
     nnz = len(col)
-    cores = os.cpu_count() or 1
     x = gen_np.uniform(1, 0, n, dt)
-    times = []
+    if wl["kind"] == "mv":
+        _, flops = spmv_bytes_flops(m, n, nnz, ELEM[p], wl["beta"] != 0)
+    else:
+        _, flops = spmm_bytes_flops(m, n, wl["n_rhs"], nnz, ELEM[p], wl["beta"] != 0)
+
+    def timed(call, w, k):
+        ts = []
+        for i in range(w + k):
+            t0 = time.perf_counter()
+            assert call() == 0
+            if i >= w:
+                ts.append(time.perf_counter() - t0)
+        return ts
+    extra = {}
     if os.path.exists(oracle_py.REF_SO):
         kind = "reference"
         ref = capi.AoclSparse(oracle_py.REF_SO)
+        nt = C.c_int32(0)
+        isa, tl, arch, upd = C.create_string_buffer(32), C.create_string_buffer(32), C.create_string_buffer(32), C.c_bool(False)
+        ref.lib.aoclsparse_debug_get(isa, C.byref(nt), tl, C.byref(upd), arch)  # what the reference itself will use
+        threads = int(nt.value)
+        t0 = time.perf_counter()
         st, h = ref.create_csr(p, 0, m, n, nnz, rp, col, val)
+        extra["create_ms"] = round((time.perf_counter() - t0) * 1e3, 3)  # the serial O(nnz) validation scan
         assert st == 0, st
         d = ref.create_descr()
         if wl["kind"] == "mv":
@@ -172,42 +243,68 @@ def run_reference_cpu(wl, steps, warmup):
             B = gen_np.uniform(3, 0, n * nr, dt)
             Cm = np.zeros(m * nr, dt)
             call = lambda: ref.csrmm(p, 111, wl["alpha"], h, d, 0, B, nr, nr, wl["beta"], Cm, nr)  # noqa: E731
-        for i in range(warmup + steps):
-            t0 = time.perf_counter()
-            assert call() == 0
-            if i >= warmup:
-                times.append(time.perf_counter() - t0)
+        times = timed(call, warmup, steps)
         note = "no optimize"
-        if wl["kind"] == "mv" and p == "d":
-            # time hint+optimize as well for double and report the faster
+        if wl["kind"] == "mv":
+            # time hint+optimize as well and report the faster (double: br4 format, float: clean copy)
+            t0 = time.perf_counter()
             assert ref.set_mv_hint(h, 111, d, 1000) == 0 and ref.optimize(h) == 0
-            t2 = []
-            for i in range(warmup + steps):
-                t0 = time.perf_counter()
-                assert call() == 0
-                if i >= warmup:
-                    t2.append(time.perf_counter() - t0)
+            extra["optimize_ms"] = round((time.perf_counter() - t0) * 1e3, 2)
+            t2 = timed(call, warmup, steps)
+            extra["ms_no_optimize"] = round(statistics.median(times) * 1e3, 4)
+            extra["ms_after_optimize"] = round(statistics.median(t2) * 1e3, 4)
             if statistics.median(t2) < statistics.median(times):
                 times, note = t2, "after set_mv_hint+optimize"
         ref.destroy(h)
-        threads = cores
+        extra["isa"] = isa.value.decode(errors="replace")
     else:
         kind, threads, note = "port", 1, "scalar oracle port"
         orc = oracle_py.Oracle()
         y = np.zeros(m, dt)
-        for i in range(min(warmup, 1) + min(steps, 3)):
-            t0 = time.perf_counter()
-            orc.csrmv(111, wl["alpha"], m, n, 0, rp, col, val, 0, 0, 0, x, wl["beta"], y)
-            if i >= min(warmup, 1):
-                times.append(time.perf_counter() - t0)
+        times = timed(lambda: orc.csrmv(111, wl["alpha"], m, n, 0, rp, col, val, 0, 0, 0, x, wl["beta"], y) or 0,
+                      min(warmup, 1), min(steps, 3))
     t = statistics.median(times)
-    if wl["kind"] == "mv":
-        _, flops = spmv_bytes_flops(m, n, nnz, ELEM[p], wl["beta"] != 0)
-    else:
-        _, flops = spmm_bytes_flops(m, n, wl["n_rhs"], nnz, ELEM[p], wl["beta"] != 0)
     info = {"kind": kind, "cores": threads,
-            "sample": f"{sample}; median of {len(times)} calls, {note}; host has {cores} logical cores"}
+            "sample": f"{sample}; median of {len(times)} calls (best {min(times) * 1e3:.3f} ms), {note}", **extra}
     return flops / t / 1e9, t * 1e3, info
+
+
+def reference_child(workload, steps, warmup, one_thread=False, timeout=900):
+    """runs `bench.py --impl reference` on one workload in a child process whose OpenMP environment and CPU affinity
+    are set BEFORE anything loads libgomp (torch.distributed.run exports OMP_NUM_THREADS=1; torch itself loads an
+    OpenMP runtime) and returns the parsed JSON line"""
+    env = dict(os.environ)
+    upd, cpus, desc = reference_env()
+    env.update(upd)
+    if one_thread:
+        env.update({"OMP_NUM_THREADS": "1", "AOCLSPARSE_NUM_THREADS": "1"})
+        cpus = cpus[:1]
+    env["BENCH_REF_CHILD"] = ",".join(str(c) for c in cpus)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        env.pop(k, None)
+    out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", workload,
+                          "--steps", str(steps), "--warmup", str(warmup)], capture_output=True, text=True, env=env,
+                         timeout=timeout)
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    if out.returncode != 0 or not lines:
+        raise RuntimeError(f"reference child failed rc={out.returncode}: {out.stderr[-800:]}")
+    return json.loads(lines[-1])
+
+
+def cpu_baseline_for(workload):
+    """cpu_baseline object of a GPU line: the reference on the physical cores of one socket + a 1-thread figure"""
+    try:
+        j = reference_child(workload, steps=10, warmup=3)
+        cpu = dict(j["cpu_baseline"])
+        cpu["ms_per_step"] = j["ms_per_step"]
+        try:
+            j1 = reference_child(workload, steps=3, warmup=1, one_thread=True)
+            cpu["one_thread"] = {"value": j1["value"], "ms_per_step": j1["ms_per_step"]}
+        except Exception as ex:
+            cpu["one_thread"] = {"value": None, "error": repr(ex)[:200]}
+        return cpu
+    except Exception as ex:  # the baseline is a reported number, not a gate
+        return {"value": None, "unit": "GFLOP/s", "cores": 0, "kind": "reference", "sample": f"failed: {ex!r}"[:400]}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -246,29 +343,81 @@ def device_matrix(lib, wl, row_lo=None, row_hi=None):
     return n, n, nnz, rp, col, val
 
 
-def run_gpu(args, wl):
+def sharded_parity(lib, wl, slab, A, d, peer_factory, iters):
+    """fused multiply + halo push (one launch per iteration, flags in-kernel) against the un-fused path (plain
+    aoclsparse_dmv on the windowed handle + NCCL send/recv of the halos) from the same x_0 for `iters` iterations:
+    the two own slices must be bit-identical on every rank.  Returns the parity object of the JSON line."""
+    import torch
+    import torch.distributed as dist
+
+    import sharding
+    elem = ELEM[wl["prefix"]]
+    m, off, wlen = slab.rows, slab.own_offset, slab.win_hi - slab.win_lo
+    alpha = wl["alpha"]
+    # un-fused: plain product, halos by NCCL
+    bufs = [torch.zeros(wlen, dtype=torch.float64, device="cuda") for _ in range(2)]
+    lib.lib.aoclsparse_b200_gen_uniform(1, slab.row_lo, m, elem, bufs[0][off:].data_ptr())
+    for r in sharding.exchange_halo(slab, bufs[0]):
+        r.wait()
+    cur = 0
+    for _ in range(iters):
+        s = lib.mv("d", 111, alpha, A, d, bufs[cur].data_ptr(), 0.0, bufs[1 - cur][off:].data_ptr())
+        assert s == 0, (s, lib.last_error())
+        for r in sharding.exchange_halo(slab, bufs[1 - cur]):
+            r.wait()
+        cur = 1 - cur
+    torch.cuda.synchronize()
+    plain = bufs[cur][off: off + m]
+    # fused: fresh windows and flags
+    peer = peer_factory()
+    lib.lib.aoclsparse_b200_gen_uniform(1, slab.row_lo, m, elem, C.c_void_p(peer.own_ptr(0)))
+    torch.cuda.synchronize()
+    dist.barrier()
+    peer.initial_push(0)
+    dist.barrier()
+    for k in range(1, iters + 1):
+        s = peer.iteration_fused(k, alpha, A, d)
+        assert s == 0, (s, lib.last_error())
+    torch.cuda.synchronize()
+    dist.barrier()
+    fused = torch.empty(m, dtype=torch.float64, device="cuda")
+    assert lib.memcpy(fused.data_ptr(), peer.own_ptr(iters % 2), m * elem) == 0
+    torch.cuda.synchronize()
+    mism = int((fused.view(torch.int64) != plain.view(torch.int64)).sum().item())
+    err = float((fused - plain).abs().max().item())
+    stats = torch.tensor([float(mism), err, float(peer.timed_out())], dtype=torch.float64, device="cuda")
+    dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+    nrm = torch.tensor([float((fused * fused).sum().item())], dtype=torch.float64, device="cuda")
+    dist.all_reduce(nrm)
+    return {"checked": True, "iterations": iters, "mismatching_entries_max_over_ranks": int(stats[0].item()),
+            "max_err": float(stats[1].item()), "flag_wait_timed_out": int(stats[2].item()),
+            "x_norm2": float(nrm.item()) ** 0.5,
+            "what": "fused spmv_sharded_step_kernel (peer stores + in-kernel flags) vs plain aoclsparse_dmv + NCCL halo "
+                    "send/recv from the same x_0, own slices compared bitwise on every rank"}
+
+
+def measure(args, key, primary):
+    """one workload on the GPU(s); returns the JSON object of that workload"""
     import torch
     import torch.distributed as dist
 
     import capi
     import sharding
 
+    wl = WORKLOADS[key]
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch N>1 with torch.distributed.run"
-    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = capi.AoclSparse()
     p = wl["prefix"]
     tdt = torch.float64 if p == "d" else torch.float32
     elem = ELEM[p]
     stream = torch.cuda.current_stream()
     lib.set_stream(stream.cuda_stream)
+    steps = args.steps if primary else min(args.steps, 50)
+    warmup = args.warmup if primary else min(args.warmup, 10)
 
-    # ---- matrix, handle, analysis (outside the timed region; the analysis time is reported)
+    # ---- matrix, handle, analysis (outside the timed region; their times are reported)
     sharded = bool(wl.get("sharded"))
     if sharded:
         pts, nx, ny, nz = wl["stencil"]
@@ -276,11 +425,27 @@ def run_gpu(args, wl):
         slab = sharding.make_slab(nx * ny * nz, world, rank, halo=plane, granularity=plane)
         m, n_glob, nnz, rp, col, val = device_matrix(lib, wl, slab.row_lo, slab.row_hi)
     else:
-        assert world == 1, f"workload {args.workload} does not shard: run it with --gpus 1"
+        assert world == 1, f"workload {key} does not shard: run it with --gpus 1"
         m, n_glob, nnz, rp, col, val = device_matrix(lib, wl)
         slab = None
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
     st, A = lib.create_csr(p, 0, m, n_glob, nnz, rp.data_ptr(), col.data_ptr(), val.data_ptr())
+    torch.cuda.synchronize()
+    create_ms = (time.perf_counter() - t0) * 1e3
     assert st == 0, (st, lib.last_error())
+    create_host_ms = None
+    if not sharded:
+        # the drop-in call: CSR arrays in pageable HOST memory (upload + validation + classification)
+        hrp, hcol, hval = rp.cpu().numpy(), col.cpu().numpy(), val.cpu().numpy()
+        t0 = time.perf_counter()
+        st2, A2 = lib.create_csr(p, 0, m, n_glob, nnz, hrp, hcol, hval)
+        torch.cuda.synchronize()
+        create_host_ms = (time.perf_counter() - t0) * 1e3
+        assert st2 == 0
+        lib.destroy(A2)
+        del hrp, hcol, hval
+    handles = [A]
     del rp, col, val  # the handle owns device copies
     torch.cuda.empty_cache()
     d = lib.create_descr()
@@ -301,6 +466,7 @@ def run_gpu(args, wl):
     info = lib.matrix_info(A)
 
     alpha, beta = wl["alpha"], wl["beta"]
+    halo_mode, peer, bufs, n_sets = "none", None, None, 1
     # ---- operands resident in HBM
     if wl["kind"] == "mm":
         nr = wl["n_rhs"]
@@ -312,9 +478,11 @@ def run_gpu(args, wl):
             s = lib.csrmm(p, 111, alpha, A, d, 0, B.data_ptr(), nr, nr, beta, Cm.data_ptr(), nr)
             assert s == 0, (s, lib.last_error())
         g_bytes, g_flops = spmm_bytes_flops(m, n_glob, nr, nnz, elem, beta != 0)
+        g_nnz = nnz
         launches_per_step = 1
     elif not sharded:
         g_bytes, g_flops = spmv_bytes_flops(m, n_glob, nnz, elem, beta != 0)
+        g_nnz = nnz
         # cold-L2 protocol: a working set below 2x L2 would be served from the 126 MB L2 on
         # back-to-back launches, so rotate over enough independent (A, x, y) sets to exceed it
         n_sets = 1 if g_bytes > 2 * L2_BYTES else int(-(-3 * L2_BYTES // g_bytes))
@@ -328,6 +496,7 @@ def run_gpu(args, wl):
                 assert stk == 0
                 del rpk, colk, valk
                 assert lib.set_mv_hint(Ak, 111, d, 1000) == 0 and lib.optimize(Ak) == 0
+                handles.append(Ak)
             xk = torch.empty(n_glob, dtype=tdt, device="cuda")
             lib.lib.aoclsparse_b200_gen_uniform(1, 0, n_glob, elem, xk.data_ptr())
             yk = torch.empty(m, dtype=tdt, device="cuda")
@@ -347,7 +516,6 @@ def run_gpu(args, wl):
         # the neighbours' x windows over NVLink and publishes the flags; p2p-push = same stores, separate boundary /
         # interior launches and flag kernels; nccl = send/recv baseline
         halo_mode = "none" if world == 1 else os.environ.get("BENCH_HALO", "p2p-fused")
-        peer = None
         if halo_mode in ("p2p-push", "p2p-fused"):
             # x windows live in ipc memory; boundary rows store into the neighbours' halos from the kernel epilogue
             peer = sharding.PeerHalo(lib, slab, elem)
@@ -356,7 +524,6 @@ def run_gpu(args, wl):
             dist.barrier()
             peer.initial_push(0)
             dist.barrier()
-            bufs = None
         else:
             bufs = [torch.zeros(wlen, dtype=tdt, device="cuda") for _ in range(2)]
             lib.lib.aoclsparse_b200_gen_uniform(1, slab.row_lo, m, elem, bufs[0][off:].data_ptr())
@@ -412,7 +579,7 @@ def run_gpu(args, wl):
         torch.cuda.synchronize()
 
     # ---- warm-up, then K timed steps bracketed by barrier + synchronize, CUDA events on the launch stream
-    for i in range(args.warmup):
+    for i in range(warmup):
         step(i)
     barrier()
     sampler = ClockSampler(local_rank)
@@ -423,7 +590,7 @@ def run_gpu(args, wl):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
-    for i in range(args.steps):
+    for i in range(steps):
         step(i)
     e1.record(stream)
     barrier()
@@ -433,7 +600,7 @@ def run_gpu(args, wl):
     t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_per_step = float(t.item()) / args.steps
+    ms_per_step = float(t.item()) / steps
 
     # ---- launch duration for the roofline: a step is one launch of the dominant kernel (plus, for split rows,
     # the small finish kernel), so the average over the timed region (CUDA events on the launch stream) is the
@@ -441,9 +608,9 @@ def run_gpu(args, wl):
     if sharded and world > 1:
         kern_ms, iso_ms = None, None
     else:
-        kern_ms = dev_ms / args.steps
+        kern_ms = dev_ms / steps
         ks = []
-        for i in range(min(args.steps, 20)):
+        for i in range(min(steps, 20)):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(stream)
             step(i)
@@ -452,31 +619,32 @@ def run_gpu(args, wl):
             ks.append(a.elapsed_time(b))
         iso_ms = statistics.median(ks)
 
-    # ---- end to end through the C ABI with HOST buffers (pinned): H2D x, multiply, D2H y per step
-    e2e = None
-    if getattr(args, "_nested", False):
-        pass  # the scaling-base measurement inside the default N=1 run: device-resident number only
-    elif wl["kind"] == "mv":
+    # ---- end to end through the C ABI with HOST buffers: H2D x, multiply, D2H y per step; page-locked buffers
+    # (the headline) and plain pageable ones (what an unmodified caller's malloc'ed arrays are)
+    if wl["kind"] == "mv":
         xlen = (slab.win_hi - slab.win_lo) if sharded else n_glob
         hx = torch.empty(xlen, dtype=tdt).pin_memory()
         hy = torch.zeros(m, dtype=tdt).pin_memory()
-        if sharded and bufs is None:
+        if sharded and bufs is None and peer is not None:
             assert lib.memcpy(hx.data_ptr(), peer.w_ptr[0], xlen * elem) == 0
             torch.cuda.synchronize()
         else:
             hx.copy_(bufs[0] if sharded else x)
-        hxp, hyp = hx.data_ptr(), hy.data_ptr()
-        call = lambda: lib.mv(p, 111, alpha, A, d, hxp, beta, hyp)  # noqa: E731
+        px, py = hx.numpy().copy(), np.zeros(m, hx.numpy().dtype)
+        calls = {"pinned": (lambda: lib.mv(p, 111, alpha, A, d, hx.data_ptr(), beta, hy.data_ptr())),
+                 "pageable": (lambda: lib.mv(p, 111, alpha, A, d, px, beta, py))}
         h2d, d2h = xlen * elem + (m * elem if beta != 0 else 0), m * elem
     else:
         hB = torch.empty(n_glob * nr, dtype=tdt).pin_memory()
         hB.copy_(B)
         hC = torch.zeros(m * nr, dtype=tdt).pin_memory()
-        hBp, hCp = hB.data_ptr(), hC.data_ptr()
-        call = lambda: lib.csrmm(p, 111, alpha, A, d, 0, hBp, nr, nr, beta, hCp, nr)  # noqa: E731
-        h2d, d2h = (n_glob * nr + m * nr) * elem, m * nr * elem
-    if not getattr(args, "_nested", False):
-        e2e_steps = max(3, min(args.steps, 20))
+        pB, pC = hB.numpy().copy(), np.zeros(m * nr, hB.numpy().dtype)
+        calls = {"pinned": (lambda: lib.csrmm(p, 111, alpha, A, d, 0, hB.data_ptr(), nr, nr, beta, hC.data_ptr(), nr)),
+                 "pageable": (lambda: lib.csrmm(p, 111, alpha, A, d, 0, pB, nr, nr, beta, pC, nr))}
+        h2d, d2h = (n_glob * nr + (m * nr if beta != 0 else 0)) * elem, m * nr * elem
+    e2e_res = {}
+    for name, call in calls.items():
+        e2e_steps = max(3, min(steps, 20)) if name == "pinned" else max(3, min(steps, 5))
         for _ in range(2):
             assert call() == 0, lib.last_error()
         barrier()
@@ -488,17 +656,26 @@ def run_gpu(args, wl):
         t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
-        e2e = {"value": round(g_flops / (e2e_ms * 1e-3) / 1e9, 3), "unit": "GFLOP/s", "ms_per_step": round(e2e_ms, 4),
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "how": "aoclsparse_?mv / csrmm called with pinned HOST x,y (B,C): chunked H2D / kernel / D2H pipeline "
-                      "on three streams inside the call, result on the host when it returns"}
+        e2e_res[name] = (float(t.item()), e2e_steps)
+    e2e_ms = e2e_res["pinned"][0]
+    e2e = {"value": round(g_flops / (e2e_ms * 1e-3) / 1e9, 3), "unit": "GFLOP/s", "ms_per_step": round(e2e_ms, 4),
+           "steps": e2e_res["pinned"][1], "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+           "pageable": {"value": round(g_flops / (e2e_res["pageable"][0] * 1e-3) / 1e9, 3),
+                        "ms_per_step": round(e2e_res["pageable"][0], 4), "steps": e2e_res["pageable"][1],
+                        "how": "same call, x / y (B / C) in plain malloc'ed (numpy) host memory"},
+           "how": "aoclsparse_?mv / csrmm called with page-locked HOST x,y (B,C): chunked H2D / kernel / D2H pipeline "
+                  "on three streams inside the call, result on the host when it returns"}
 
+    # ---- N > 1: bitwise check of the fused path against the un-fused one (both from x_0, >= 100 iterations)
+    parity = None
+    if sharded and world > 1 and halo_mode == "p2p-fused":
+        parity = sharded_parity(lib, wl, slab, A, d, lambda: sharding.PeerHalo(lib, slab, elem), max(100, steps))
+
+    for hdl in handles:
+        lib.destroy(hdl)
+    lib.destroy_descr(d)
     if rank != 0:
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
-        return
+        return None
 
     peak, peak_src = measured_peak()
     value = g_flops / (ms_per_step * 1e-3) / 1e9
@@ -507,13 +684,17 @@ def run_gpu(args, wl):
         l_bytes, _ = spmv_bytes_flops(m, slab.win_hi - slab.win_lo, nnz, elem, beta != 0)
     else:
         l_bytes = g_bytes
-    traffic = None
+    traffic, traffic_src = None, None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get(args.workload)
+        tj = json.load(open(tp))
+        traffic = tj.get(key)
+        traffic_src = ("static: profiles/traffic.json (dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full "
+                       "capture of this kernel, " + str(tj.get("_captured", "round 1")) + "); not re-measured in this run")
     roof = {"bound": "hbm", "unit": "GB/s", "peak": peak, "peak_source": peak_src, "traffic": traffic,
-            "kernel": ("spmv_hot_kernel" if info.hot_entries else ("spmv_sharded_step_kernel" if (sharded and world > 1)
-                       else "spmv_row_blocks_kernel")) if wl["kind"] == "mv" else "csrmm_row_major_vec_kernel",
+            "traffic_source": traffic_src,
+            "kernel": ("spmv_sharded_step_kernel" if (sharded and world > 1 and halo_mode == "p2p-fused")
+                       else "spmv_row_blocks_kernel") if wl["kind"] == "mv" else "csrmm_row_major_vec_kernel",
             "algorithmic_bytes_per_launch": int(l_bytes)}
     if kern_ms:
         roof["achieved"] = round(l_bytes / (kern_ms * 1e-3) / 1e9, 1)
@@ -522,81 +703,115 @@ def run_gpu(args, wl):
     else:
         roof["achieved"] = round(eff_gbs / world, 1)
         roof["launch_ms"] = None
-        roof["note"] = "per-GPU share of the step (interior + boundary launches overlap the halo exchange)"
+        roof["note"] = "per-GPU share of the step (interior + boundary CTAs of one launch overlap the halo exchange)"
     roof["frac"] = round(roof["achieved"] / peak, 4)
     roof["frac_of_nominal_8TBs"] = round(roof["achieved"] / 8000.0, 4)
 
-    cpu = None
-    if world == 1 and not args.no_cpu_baseline:
-        try:
-            gf, ms, cinfo = run_reference_cpu(wl, steps=10, warmup=3)
-            cpu = dict(value=round(gf, 3), unit="GFLOP/s", ms_per_step=round(ms, 3), **cinfo)
-        except Exception as ex:  # the baseline is a reported number, not a gate
-            cpu = {"value": None, "unit": "GFLOP/s", "cores": 0, "kind": "reference", "sample": f"failed: {ex!r}"}
-
     out = {
-        "metric": "CSR dmv GFLOP/s + effective HBM GB/s (% of 8 TB/s) at 1/2/4/8 B200",
-        "value": round(value, 3), "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": METRIC,
+        "value": round(value, 3), "unit": "GFLOP/s", "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": round(ms_per_step, 5), "higher_is_better": True,
         "scaling": "strong" if sharded else "weak", "vs_baseline": None,
         "dtype": {"s": "f32", "d": "f64"}[p], "data": "synthetic",
-        "config": {"workload": wl["name"], "rows": int(n_glob if sharded else m), "nnz": int(g_nnz if sharded else nnz),
+        "config": {"workload": wl["name"], "rows": int(n_glob if sharded else m), "nnz": int(g_nnz),
                    "parallelism": (f"row slabs x{world}, halo: {halo_mode}" if sharded else "single GPU"),
                    "l2": ("operands larger than L2: %.0f MB streamed per step vs 126 MB L2" % (l_bytes / 1e6))
                    if (sharded or wl["kind"] == "mm" or n_sets == 1) else
                    ("rotating over %d independent (A,x,y) sets, %.0f MB in total vs 126 MB L2" % (n_sets, n_sets * l_bytes / 1e6)),
                    "plan": {"block_nnz": info.block_nnz, "blocks": info.n_blocks, "thread": info.n_thread_blocks,
                             "warp": info.n_warp_blocks, "product": info.n_product_blocks,
-                            "long_segments": info.n_long_segments, "long_rows": info.n_long_rows,
-                            "hot_table_entries": info.hot_entries, "hot_table_mass": info.hot_mass_ppm / 1e6},
-                   "optimize_ms": round(optimize_ms, 2)},
+                            "long_segments": info.n_long_segments, "long_rows": info.n_long_rows},
+                   "optimize_ms": round(optimize_ms, 2),
+                   "create_ms": round(create_ms, 2),
+                   "create_from_pageable_host_ms": None if create_host_ms is None else round(create_host_ms, 2)},
         "effective_gbs": round(eff_gbs, 1), "effective_frac_of_8TBs": round(eff_gbs / (8000.0 * world), 4),
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-        "gpu_launches_per_step": launches_per_step, "roofline": roof, "cpu_baseline": cpu,
+        "gpu_launches_per_step": launches_per_step, "roofline": roof,
     }
-    if getattr(args, "_nested", False):
-        return out
-    if sharded and world > 1:
-        out["scaling_note"] = ("strong scaling of BASELINE.json configs[4]; its one-GPU point is the 'scaling_base' object of "
-                               "the default N=1 line (whose own workload is configs[1]), or `bench.py --gpus 1 --workload c5`")
-    if getattr(args, "_default_workload", False) and world == 1:
-        # BASELINE.json's configs[4] asks for the row-sharded 512^3 case "at 1/2/4/8 B200"; the default single-GPU line
-        # is configs[1] (c2), so the one-GPU point of that scaling series is measured here as well and reported
-        # beside it (device-resident, same protocol, fewer steps)
-        try:
-            import copy
-            a2 = copy.copy(args)
-            a2.workload, a2.steps, a2.warmup, a2.no_cpu_baseline = "c5", min(args.steps, 20), 3, True
-            a2._nested, a2._default_workload = True, False
-            o5 = run_gpu(a2, WORKLOADS["c5"])
-            out["scaling_base"] = {"what": "the N=1 point of the multi-GPU series (bench.py --gpus N>1 runs this workload)",
-                                   "workload": o5["config"]["workload"], "n_gpus": 1, "value": o5["value"],
-                                   "unit": "GFLOP/s", "ms_per_step": o5["ms_per_step"], "steps": o5["steps"],
-                                   "effective_gbs": o5["effective_gbs"], "roofline_frac": o5["roofline"]["frac"]}
-        except Exception as ex:  # an extra, never a gate
-            out["scaling_base"] = {"value": None, "error": repr(ex)}
-    print(json.dumps(out))
+    if parity is not None:
+        out["parity"] = parity
+    return out
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch N>1 with torch.distributed.run"
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    primary = args.workload or "c5"
+    out = measure(args, primary, True)
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline_for(primary)
+        else:
+            out["cpu_baseline"] = None
+        if args.workload is None and world == 1:
+            # the other BASELINE.json configurations, same protocol, in the same run
+            out["configs"] = {}
+            for key in ("c1", "c2", "c3", "c4"):
+                try:
+                    o = measure(args, key, False)
+                    sub = {k: o[k] for k in ("value", "unit", "ms_per_step", "steps", "warmup", "dtype", "effective_gbs",
+                                             "effective_frac_of_8TBs", "roofline", "e2e", "gpu_launches", "config")}
+                    sub["cpu_baseline"] = None if args.no_cpu_baseline else cpu_baseline_for(key)
+                    out["configs"][key] = sub
+                    out["gpu_launches"] += o["gpu_launches"]
+                except Exception as ex:  # an extra line must never take the primary one down
+                    out["configs"][key] = {"value": None, "error": repr(ex)[:400]}
+                torch.cuda.empty_cache()
+        print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
-def run_reference(args, wl):
+def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    key = args.workload or "c5"
+    wl = WORKLOADS[key]
+    if "BENCH_REF_CHILD" not in os.environ:
+        # re-run in a child whose OpenMP environment / affinity is right from the first instruction
+        j = reference_child(key, args.steps, args.warmup)
+        j["n_gpus"] = args.gpus
+        try:
+            j1 = reference_child(key, steps=3, warmup=1, one_thread=True)
+            j["cpu_baseline"]["one_thread"] = {"value": j1["value"], "ms_per_step": j1["ms_per_step"]}
+        except Exception as ex:
+            j["cpu_baseline"]["one_thread"] = {"value": None, "error": repr(ex)[:200]}
+        print(json.dumps(j), flush=True)
+        return
+    cpus = [int(c) for c in os.environ["BENCH_REF_CHILD"].split(",") if c]
+    _, _, desc = reference_env()
+    if cpus:
+        try:
+            os.sched_setaffinity(0, cpus)  # before the arrays are first touched: pages land next to the threads
+        except OSError:
+            pass
     gf, ms, info = run_reference_cpu(wl, steps=args.steps, warmup=args.warmup)
+    info.update({"host": desc, "omp": {k: os.environ.get(k) for k in ("OMP_NUM_THREADS", "AOCLSPARSE_NUM_THREADS",
+                                                                      "OMP_PROC_BIND", "OMP_PLACES")},
+                 "pinned_to_cpus": len(cpus),
+                 "first_touch": "process pinned to the cores its OpenMP threads run on before the arrays are generated"})
     out = {
         "impl": "reference",
-        "metric": "CSR dmv GFLOP/s + effective HBM GB/s (% of 8 TB/s) at 1/2/4/8 B200",
+        "metric": METRIC,
         "value": round(gf, 3), "unit": "GFLOP/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": "strong" if wl.get("sharded") else "weak",
         "vs_baseline": None, "dtype": {"s": "f32", "d": "f64"}[wl["prefix"]], "data": "synthetic",
-        "config": {"workload": wl["name"]},
+        "config": {"workload": wl["name"], "sample": info["sample"].split(";")[0]},
         "cpu_baseline": dict(value=round(gf, 3), unit="GFLOP/s", **info),
         "e2e": {"value": round(gf, 3), "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(out))
+    print(json.dumps(out), flush=True)
 
 
 def main():
@@ -609,14 +824,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
-    args._default_workload = args.workload is None
-    if args.workload is None:
-        args.workload = "c2" if args.gpus == 1 else "c5"
-    wl = WORKLOADS[args.workload]
     if args.impl == "reference":
-        run_reference(args, wl)
+        run_reference(args)
     else:
-        run_gpu(args, wl)
+        run_gpu(args)
 
 
 if __name__ == "__main__":

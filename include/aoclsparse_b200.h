@@ -50,14 +50,10 @@ typedef struct aoclsparse_b200_matrix_info_
     aoclsparse_int n_product_blocks; /* blocks binned CTA-wide product + segmented sum          */
     aoclsparse_int n_long_segments; /* blocks that are one segment of a row split across CTAs   */
     aoclsparse_int n_long_rows;     /* rows split across CTAs                                   */
-    aoclsparse_int hot_entries;     /* hot-column table: entries of x kept in shared memory, 0 = not built     */
-    aoclsparse_int hot_mass_ppm;    /* stored entries whose column is in that table, parts per million          */
-    aoclsparse_int group_k;         /* row-grouped csrmm copy: rows per group (2 / 4); 0 not analysed, -1 not used */
-    aoclsparse_int group_entries;   /* its entries = sum over groups of the distinct columns in the group       */
-    aoclsparse_int group_blocks;    /* its row blocks                                                           */
-    aoclsparse_int group_block_nnz; /* entries staged per block                                                 */
-    aoclsparse_int mm_tile_state;   /* tiled csrmm plan: 0 not analysed, -1 not usable, else entries per row block */
-    aoclsparse_int mm_tile_max_rows; /* most distinct B rows any of its blocks stages                           */
+    aoclsparse_int n_diag_codes;    /* diagonal-code copy of col_idx (one byte per entry indexing a table of the
+                                       distinct col - row offsets): table entries, 0 = not built / not applicable */
+    aoclsparse_int sorted_blocks;   /* product blocks whose entries are also stored sorted by column (gather
+                                       locality for skewed matrices), 0 = not built                              */
 } aoclsparse_b200_matrix_info;
 
 /* value type of a handle (aoclsparse_matrix_data_type), -1 for NULL */

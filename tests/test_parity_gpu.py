@@ -866,17 +866,6 @@ def test_config3_rmat_float(lib, oracle):
     oracle.csrmv(111, 1.0, m, m, 0, rp, col, val.astype(np.float64), 0, 0, 0, x.astype(np.float64), 0.0, y64)
     assert np.max(np.abs(y - y64) / np.where(den > 0, den, 1)) <= 1e-5
     assert info.n_long_rows > 0 and info.n_product_blocks > 0  # hub rows are split, skewed blocks use product
-    assert info.hot_entries == 0
-    # experimental hot-column table paths (off by default): packed side vector (mode 1), persistent smem table (2)
-    for mode in ("1", "2"):
-        os.environ["AOCLSPARSE_B200_HOT"] = "1"
-        os.environ["AOCLSPARSE_B200_HOT_MODE"] = mode
-        try:
-            y2, info2 = _device_mv(lib, "s", 0, m, m, rp, col, val, x, np.zeros(m, np.float32), 1.0, 0.0)
-        finally:
-            del os.environ["AOCLSPARSE_B200_HOT"], os.environ["AOCLSPARSE_B200_HOT_MODE"]
-        assert info2.hot_entries > 0 and info2.hot_mass_ppm > 150000
-        assert np.max(np.abs(y2.astype(np.float64) - yo) / np.where(den > 0, den, 1)) <= 1e-5, mode
 
 
 def test_config5_iterated_1_10_100(lib):
@@ -969,159 +958,6 @@ def test_config4_csrmm(lib, oracle, order):
     got = got.reshape(m, n) if order == 0 else got.reshape(n, m).T
     Cv = Co.reshape(m, n) if order == 0 else Co.reshape(n, m).T
     assert np.max(np.abs(got - Cv) / den) <= 1e-12
-    lib.destroy(h)
-    lib.destroy_descr(d)
-
-
-@pytest.mark.parametrize("p", ["s", "d", "c", "z"])
-@pytest.mark.parametrize("k", [4, 2])
-def test_csrmm_row_grouped_copy(lib, oracle, p, k, monkeypatch):
-    """the row-grouped copy built by aoclsparse_optimize after a mm hint (group.cu): same product as the plain kernel
-    and the oracle for every value type, K = 2 / 4, several widths and both vector layouts; Inf in B must not leak
-    into rows that do not hold that column (absent group entries are masked, not multiplied by zero); the copy is
-    rebuilt after update_values; matrices without shared columns keep the plain kernel"""
-    import scipy.sparse as sp
-    monkeypatch.setenv("AOCLSPARSE_B200_MM_GROUP", str(k))
-    dt = DT[p]
-    tol = TOL[np.dtype(dt)]
-    cplx = p in "cz"
-    rng = np.random.default_rng(99 + k)
-    rp, col, val0 = gen_np.stencil(27, 20, 19, 18)
-    m = len(rp) - 1
-    val = rng.normal(size=len(col)).astype(dt)
-    if cplx:
-        val = (val + 1j * rng.normal(size=len(col))).astype(dt)
-    A = sp.csr_matrix((val, col, rp), shape=(m, m))
-    Aabs = abs(A)
-    st, h = lib.create_csr(p, 0, m, m, len(col), rp, col, val)
-    assert st == 0
-    d = lib.create_descr()
-    assert lib.set_mm_hint(h, 111, d, 100) == 0 and lib.optimize(h) == 0, lib.last_error()
-    info = lib.matrix_info(h)
-    assert info.group_k == k and 0 < info.group_entries < 0.7 * len(col), (info.group_k, info.group_entries)
-    vec = 16 // np.dtype(dt).itemsize
-    for nv in ("2", "1"):
-        monkeypatch.setenv("AOCLSPARSE_B200_MM_GROUP_NV", nv)
-        for n in (2 * vec, 32, 40, 8 * vec * 9):
-            for alpha, beta in ((1.0, 0.0), (-0.5, 2.0)):
-                B = rng.normal(size=m * n).astype(dt)
-                C0 = rng.normal(size=m * n).astype(dt)
-                if cplx:
-                    B = (B + 1j * rng.normal(size=m * n)).astype(dt)
-                for op in (111, 113) if cplx else (111,):
-                    Cm = C0.copy() if beta != 0 else np.full(m * n, np.nan, dt)
-                    assert lib.csrmm(p, op, alpha, h, d, 0, B, n, n, beta, Cm, n) == 0, lib.last_error()
-                    F = A if op == 111 else A.conj().T
-                    want = alpha * (F @ B.reshape(m, n).astype(np.complex128))
-                    den = abs(alpha) * ((Aabs if op == 111 else Aabs.T) @ np.abs(B.reshape(m, n)))
-                    if beta != 0:
-                        want = want + beta * C0.reshape(m, n)
-                        den = den + abs(beta) * np.abs(C0.reshape(m, n))
-                    assert rel_err(Cm.reshape(m, n), want, den) <= 4 * tol, (p, k, nv, n, op)
-    # Inf / NaN in one B row reach exactly the rows of A that hold that column
-    n = 32
-    B = rng.normal(size=m * n).astype(dt)
-    j = 777
-    B.reshape(m, n)[j, 3] = np.inf
-    Cm = np.zeros(m * n, dt)
-    assert lib.csrmm(p, 111, 1.0, h, d, 0, B, n, n, 0.0, Cm, n) == 0
-    bad = ~np.isfinite(Cm.reshape(m, n)).all(axis=1)
-    holders = np.zeros(m, bool)
-    holders[A.tocsc().indices[A.tocsc().indptr[j]:A.tocsc().indptr[j + 1]]] = True
-    assert np.array_equal(bad, holders)
-    # update_values drops the copy; the next call rebuilds it from the new values
-    val2 = (val * 3).astype(dt)
-    assert lib.update_values(p, h, len(val2), val2) == 0
-    assert lib.matrix_info(h).group_k == 0
-    B = rng.normal(size=m * n).astype(dt)
-    Cm = np.zeros(m * n, dt)
-    assert lib.csrmm(p, 111, 1.0, h, d, 0, B, n, n, 0.0, Cm, n) == 0
-    assert lib.matrix_info(h).group_k == k
-    assert rel_err(Cm.reshape(m, n), 3 * (A @ B.reshape(m, n).astype(np.complex128)),
-                   3 * (Aabs @ np.abs(B.reshape(m, n)))) <= 4 * tol
-    lib.destroy(h)
-    # no shared columns between neighbouring rows: analysed, not used
-    rp, col, val = gen_np.random_csr(rng, 6000, 6000, 0.002, dt, "full", base=0)
-    st, h = lib.create_csr(p, 0, 6000, 6000, len(col), rp, col, val)
-    assert lib.set_mm_hint(h, 111, d, 100) == 0 and lib.optimize(h) == 0
-    assert lib.matrix_info(h).group_k == -1
-    lib.destroy(h)
-    # unsorted rows: not eligible
-    rp, col, val0 = gen_np.stencil(27, 20, 19, 18)
-    col2 = col.copy()
-    col2[rp[5]:rp[6]] = col2[rp[5]:rp[6]][::-1]
-    st, h = lib.create_csr(p, 0, m, m, len(col2), rp, col2, val)
-    assert st == 0 and lib.set_mm_hint(h, 111, d, 100) == 0 and lib.optimize(h) == 0
-    assert lib.matrix_info(h).group_k == -1
-    lib.destroy(h)
-    lib.destroy_descr(d)
-
-
-@pytest.mark.parametrize("p", ["d", "s", "z", "c"])
-def test_csrmm_tiled_kernel(lib, oracle, p, monkeypatch):
-    """(experiment, enabled by AOCLSPARSE_B200_MM_TILES=1) row-major csrmm on a hinted mesh matrix runs the tiled kernel (B rows staged once per row block by TMA): several
-    widths, tight and padded leading dimensions, beta = 0 / != 0, against the exact product; matrices whose blocks name
-    scattered columns keep the plain kernel; values may be replaced without re-analysis"""
-    import scipy.sparse as sp
-    monkeypatch.setenv("AOCLSPARSE_B200_MM_TILES", "1")
-    dt = DT[p]
-    tol = TOL[np.dtype(dt)]
-    cplx = p in "cz"
-    rng = np.random.default_rng(123)
-    rp, col, _ = gen_np.stencil(27, 20, 19, 18)
-    m = len(rp) - 1
-    val = rng.normal(size=len(col)).astype(dt)
-    if cplx:
-        val = (val + 1j * rng.normal(size=len(col))).astype(dt)
-    A = sp.csr_matrix((val, col, rp), shape=(m, m))
-    Aabs = abs(A)
-    st, h = lib.create_csr(p, 0, m, m, len(col), rp, col, val)
-    assert st == 0
-    d = lib.create_descr()
-    assert lib.set_mm_hint(h, 111, d, 100) == 0 and lib.optimize(h) == 0, lib.last_error()
-    vec = 16 // np.dtype(dt).itemsize
-    first = True
-    for n in (2 * vec, 32, 40):
-        for pad in (0, vec):
-            for alpha, beta in ((1.0, 0.0), (-0.5, 2.0)):
-                ld = n + pad
-                B = rng.normal(size=m * ld).astype(dt)
-                C0 = rng.normal(size=m * ld).astype(dt)
-                if cplx:
-                    B = (B + 1j * rng.normal(size=m * ld)).astype(dt)
-                Cm = C0.copy() if beta != 0 else np.full(m * ld, np.nan, dt)
-                assert lib.csrmm(p, 111, alpha, h, d, 0, B, n, ld, beta, Cm, ld) == 0, lib.last_error()
-                if first:
-                    info = lib.matrix_info(h)
-                    assert info.mm_tile_state == 512 and 0 < info.mm_tile_max_rows <= 512, (info.mm_tile_state, info.mm_tile_max_rows)
-                    first = False
-                Bd, C0d, Cd = (M.reshape(m, ld)[:, :n] for M in (B, C0, Cm))
-                want = alpha * (A @ Bd.astype(np.complex128))
-                den = abs(alpha) * (Aabs @ np.abs(Bd))
-                if beta != 0:
-                    want = want + beta * C0d
-                    den = den + abs(beta) * np.abs(C0d)
-                assert rel_err(Cd, want, den) <= 4 * tol, (p, n, pad, alpha)
-                if beta != 0 and pad:
-                    assert np.array_equal(Cm.reshape(m, ld)[:, n:], C0.reshape(m, ld)[:, n:])  # padding untouched
-    # new values, same pattern: the tile plan stays
-    val2 = (val * 2).astype(dt)
-    assert lib.update_values(p, h, len(val2), val2) == 0
-    n = 32
-    B = rng.normal(size=m * n).astype(dt)
-    Cm = np.zeros(m * n, dt)
-    assert lib.csrmm(p, 111, 1.0, h, d, 0, B, n, n, 0.0, Cm, n) == 0
-    assert lib.matrix_info(h).mm_tile_state == 512
-    assert rel_err(Cm.reshape(m, n), 2 * (A @ B.reshape(m, n).astype(np.complex128)), 2 * (Aabs @ np.abs(B.reshape(m, n)))) <= 4 * tol
-    lib.destroy(h)
-    # scattered columns: analysed, not used
-    rp, col, val = gen_np.random_csr(rng, 5000, 5000, 0.004, dt, "full", base=0)
-    st, h = lib.create_csr(p, 0, 5000, 5000, len(col), rp, col, val)
-    assert lib.set_mm_hint(h, 111, d, 100) == 0 and lib.optimize(h) == 0
-    B = rng.normal(size=5000 * 32).astype(dt)
-    Cm = np.zeros(5000 * 32, dt)
-    assert lib.csrmm(p, 111, 1.0, h, d, 0, B, 32, 32, 0.0, Cm, 32) == 0
-    assert lib.matrix_info(h).mm_tile_state == -1
     lib.destroy(h)
     lib.destroy_descr(d)
 
