@@ -50,7 +50,8 @@ class MatrixInfo(C.Structure):
                 ("block_nnz", C.c_int32), ("block_rows", C.c_int32), ("n_blocks", C.c_int32),
                 ("n_thread_blocks", C.c_int32), ("n_warp_blocks", C.c_int32),
                 ("n_product_blocks", C.c_int32), ("n_long_segments", C.c_int32),
-                ("n_long_rows", C.c_int32), ("n_diag_codes", C.c_int32), ("sorted_blocks", C.c_int32)]
+                ("n_long_rows", C.c_int32), ("n_diag_codes", C.c_int32), ("hot_entries", C.c_int32),
+                ("hot_mass_ppm", C.c_int32)]
 
 
 class HaloCtl(C.Structure):
@@ -152,6 +153,7 @@ class AoclSparse:
             L.aoclsparse_b200_get_matrix_info.argtypes = [vp, C.POINTER(MatrixInfo)]
             L.aoclsparse_b200_get_plan.argtypes = [vp, i32, vp, vp, C.POINTER(i32)]
             L.aoclsparse_b200_doid.argtypes = [vp, ci, ci]
+            L.aoclsparse_b200_get_diag_codes.argtypes = [vp, C.POINTER(i32), vp, vp]
             L.aoclsparse_b200_get_clean_csr.argtypes = [vp, C.POINTER(i32), C.POINTER(ci), vp, vp, vp, vp, vp]
             L.aoclsparse_b200_set_x_window.argtypes = [vp, i32, i32]
             L.aoclsparse_b200_set_row_cuts.argtypes = [vp, i32, vp]
@@ -166,6 +168,17 @@ class AoclSparse:
             L.aoclsparse_b200_ipc_close.argtypes = [vp]
             L.aoclsparse_b200_ipc_free.argtypes = [vp]
             L.aoclsparse_b200_memcpy.argtypes = [vp, vp, C.c_size_t]
+            if hasattr(L, "aoclsparse_b200_shard_create"):
+                L.aoclsparse_b200_shard_create.argtypes = [C.POINTER(vp), vp, vp, ci, ci, i32, i32]
+                L.aoclsparse_b200_shard_export.argtypes = [vp, C.c_char_p]
+                L.aoclsparse_b200_shard_connect.argtypes = [vp, C.c_char_p, C.c_char_p]
+                L.aoclsparse_b200_shard_set_x.argtypes = [vp, vp]
+                L.aoclsparse_b200_shard_x_ptr.argtypes = [vp, C.POINTER(vp)]
+                L.aoclsparse_b200_shard_publish.argtypes = [vp]
+                L.aoclsparse_b200_shard_iterate.argtypes = [vp, C.c_double, ci]
+                L.aoclsparse_b200_shard_get_x.argtypes = [vp, vp]
+                L.aoclsparse_b200_shard_synchronize.argtypes = [vp]
+                L.aoclsparse_b200_shard_destroy.argtypes = [C.POINTER(vp)]
             L.aoclsparse_b200_gen_stencil.argtypes = [ci, i32, i32, i32, C.c_longlong, C.c_longlong,
                                                       C.POINTER(C.c_longlong), vp, vp, vp]
             L.aoclsparse_b200_gen_uniform.argtypes = [C.c_ulonglong, C.c_longlong, C.c_longlong, ci, vp]
@@ -350,6 +363,17 @@ class AoclSparse:
         assert st == 0, st
         return desc[: n.value], kind[: n.value]
 
+    def get_diag_codes(self, h, nnz):
+        """(offsets, codes) of the diagonal-code copy, or (None, None) when the handle has none"""
+        n = C.c_int32(0)
+        assert self.lib.aoclsparse_b200_get_diag_codes(h, C.byref(n), None, None) == 0
+        if n.value == 0:
+            return None, None
+        offs = np.zeros(n.value, np.int32)
+        codes = np.zeros(max(nnz, 1), np.uint8)
+        assert self.lib.aoclsparse_b200_get_diag_codes(h, C.byref(n), ptr(offs), ptr(codes)) == 0, self.last_error()
+        return offs, codes[:nnz]
+
     def get_clean_csr(self, h, m, dtype=np.float64):
         nnz, isint = C.c_int32(0), C.c_int(0)
         st = self.lib.aoclsparse_b200_get_clean_csr(h, C.byref(nnz), C.byref(isint), None, None, None, None, None)
@@ -388,6 +412,28 @@ class AoclSparse:
     def mv_sharded_step(self, alpha, h, descr, x, y, ctl):
         a = _scalar_by_ref("d", alpha)
         return self.lib.aoclsparse_b200_dmv_sharded_step(ptr(a), h, descr, ptr(x), ptr(y), C.byref(ctl))
+
+    # ---- the row-sharded iteration as one object (csrc/shard.cu) ------------------------------------
+    SHARD_LINK_BYTES = 320
+
+    def shard_create(self, h, descr, rank, world, row_lo, halo):
+        s = C.c_void_p()
+        st = self.lib.aoclsparse_b200_shard_create(C.byref(s), h, descr, rank, world, row_lo, halo)
+        return st, s
+
+    def shard_export(self, s):
+        buf = C.create_string_buffer(self.SHARD_LINK_BYTES)
+        st = self.lib.aoclsparse_b200_shard_export(s, buf)
+        assert st == 0, (st, self.last_error())
+        return buf.raw
+
+    def shard_connect(self, s, left, right):
+        return self.lib.aoclsparse_b200_shard_connect(s, left, right)
+
+    def shard_x_ptr(self, s):
+        p = C.c_void_p()
+        assert self.lib.aoclsparse_b200_shard_x_ptr(s, C.byref(p)) == 0
+        return p.value
 
     def signal(self, flag_ptr, value):
         return self.lib.aoclsparse_b200_signal(C.c_void_p(flag_ptr), value)

@@ -341,6 +341,20 @@ aoclsparse_status aoclsparse_b200_set_stream(void *cuda_stream)
     return aoclsparse_status_success;
 }
 
+// device selection for callers that do not link the CUDA runtime themselves (a C program driving several GPUs)
+aoclsparse_status aoclsparse_b200_device_count(int *count)
+{
+    if(!count)
+        return aoclsparse_status_invalid_pointer;
+    B200_CUDA(cudaGetDeviceCount(count));
+    return aoclsparse_status_success;
+}
+aoclsparse_status aoclsparse_b200_set_device(int device)
+{
+    B200_CUDA(cudaSetDevice(device));
+    return aoclsparse_status_success;
+}
+
 void *aoclsparse_b200_get_stream(void)
 {
     return tl_stream;
@@ -554,6 +568,36 @@ aoclsparse_status aoclsparse_set_mm_hint(aoclsparse_matrix          mat,
 {
     return set_hint(mat, 3, trans, descr, expected_no_of_calls, -1);
 }
+// Hints for operations next to the path (aoclsparse_analysis.h:102-161,202-206): recorded with the same validation
+// (aoclsparse_analysis.cpp:568-670; action numbering of aoclsparse_hinted_action, aoclsparse_mat_structures.hpp:32-48).
+// A dotmv hint is a multiply hint for aoclsparse_optimize; the solver-side ones (triangular solve, smoothers, sparse
+// products) only take their place in the list -- those operations are outside this library's path or need no copy.
+aoclsparse_status aoclsparse_set_sv_hint(aoclsparse_matrix mat, aoclsparse_operation trans, const aoclsparse_mat_descr descr, aoclsparse_int expected_no_of_calls)
+{
+    return set_hint(mat, 2, trans, descr, expected_no_of_calls, -1);
+}
+aoclsparse_status aoclsparse_set_2m_hint(aoclsparse_matrix mat, aoclsparse_operation trans, const aoclsparse_mat_descr descr, aoclsparse_int expected_no_of_calls)
+{
+    return set_hint(mat, 4, trans, descr, expected_no_of_calls, -1);
+}
+aoclsparse_status aoclsparse_set_lu_smoother_hint(aoclsparse_matrix mat, aoclsparse_operation trans, const aoclsparse_mat_descr descr, aoclsparse_int expected_no_of_calls)
+{
+    return set_hint(mat, 5, trans, descr, expected_no_of_calls, -1);
+}
+aoclsparse_status aoclsparse_set_sm_hint(aoclsparse_matrix mat, aoclsparse_operation trans, const aoclsparse_mat_descr descr, const aoclsparse_order order, const aoclsparse_int expected_no_of_calls)
+{
+    if(order != aoclsparse_order_row && order != aoclsparse_order_column)
+        return aoclsparse_status_invalid_value;
+    return set_hint(mat, order == aoclsparse_order_row ? 6 : 7, trans, descr, expected_no_of_calls, -1);
+}
+aoclsparse_status aoclsparse_set_dotmv_hint(aoclsparse_matrix mat, aoclsparse_operation trans, const aoclsparse_mat_descr descr, aoclsparse_int expected_no_of_calls)
+{
+    return set_hint(mat, 8, trans, descr, expected_no_of_calls, -1);
+}
+aoclsparse_status aoclsparse_set_symgs_hint(aoclsparse_matrix mat, aoclsparse_operation trans, const aoclsparse_mat_descr descr, aoclsparse_int expected_no_of_calls)
+{
+    return set_hint(mat, 9, trans, descr, expected_no_of_calls, -1);
+}
 aoclsparse_status aoclsparse_set_memory_hint(aoclsparse_matrix mat, const aoclsparse_memory_usage policy)
 {
     if(mat == nullptr)
@@ -586,8 +630,39 @@ aoclsparse_status aoclsparse_optimize(aoclsparse_matrix A)
         }
     if(const char *e = getenv("AOCLSPARSE_B200_FORCE_KID")) // tuning knob for experiments
         forced = atoi(e);
-    if(!M.plan.valid || forced >= 0)
+    // a multiply was hinted and memory is not restricted: banded / stencil matrices also get the diagonal-code copy of
+    // their column indices (one byte per entry; the reference's optimize builds format copies at this point too,
+    // aoclsparse_analysis.cpp:192-385), and a plan whose block size suits it
+    const bool want_codes = A->mem_policy == aoclsparse_memory_usage_unrestricted && !A->hints.empty();
+    if(want_codes && (!M.plan.valid || forced >= 0 || M.plan.code_state == 0))
+        B200_TRY(build_plan_with_codes(M, value_size(A->val_type), A->max_row_nnz, forced, A->row_cuts, st));
+    else if(!M.plan.valid || forced >= 0)
         B200_TRY(build_plan(M, value_size(A->val_type), A->max_row_nnz, forced, A->row_cuts, st));
+
+    // power-law matrices with a plain general mv hint: hot-column table + the persistent kernel that uses it (hot.cu),
+    // on a plan with the larger blocks that kernel stages
+    {
+        bool gn_mv_hint = false;
+        for(const hint &h : A->hints)
+            gn_mv_hint = gn_mv_hint || ((h.act == 1 || h.act == 8) && h.doid == DOID_GN);
+        const long long mean   = A->m > 0 ? (long long)A->nnz / A->m : 0;
+        const bool      skewed = (long long)A->max_row_nnz > 16 * (mean > 1 ? mean : 1);
+        const char     *e      = getenv("AOCLSPARSE_B200_HOT"); // A/B knob
+        const bool      want   = e ? atoi(e) != 0 : true;
+        const bool      real   = A->val_type == aoclsparse_smat || A->val_type == aoclsparse_dmat;
+        if(want && real && gn_mv_hint && !A->is_csc && skewed && forced < 0 && A->mem_policy == aoclsparse_memory_usage_unrestricted
+           && A->win_hi < 0 && A->row_cuts.empty() && M.plan.hot_entries == 0 && M.plan.hot_state == 0 && A->nnz >= (1 << 22))
+        {
+            const size_t         es    = value_size(A->val_type);
+            const aoclsparse_int hot_T = getenv("AOCLSPARSE_B200_BLOCK_NNZ") ? 0 : (aoclsparse_int)((24576 / (es + 4)) / 512 * 512);
+            const aoclsparse_int old_T = M.plan.block_nnz;
+            B200_TRY(build_plan(M, es, A->max_row_nnz, -1, A->row_cuts, st, hot_T));
+            B200_TRY(build_hot_table(M, es, st));
+            if(M.plan.hot_entries == 0 && M.plan.block_nnz != old_T) // flat column distribution: back to the default plan
+                B200_TRY(build_plan(M, es, A->max_row_nnz, -1, A->row_cuts, st));
+            M.plan.hot_state = 1;
+        }
+    }
 
     // transposed device copies for general transposed mv / mm hints (memory policy permitting):
     // they turn the atomic scatter into a streaming gather
@@ -599,7 +674,7 @@ aoclsparse_status aoclsparse_optimize(aoclsparse_matrix A)
                 continue;
             // a CSC handle stores the transpose: its plain product is the transposed product of what is stored
             const int want = A->is_csc ? (h.doid == DOID_GN ? DOID_GT : DOID_LEN) : h.doid;
-            if((h.act == 1 || h.act == 3) && (want == DOID_GT || want == DOID_GH))
+            if((h.act == 1 || h.act == 3 || h.act == 8) && (want == DOID_GT || want == DOID_GH))
             {
                 bool have = false;
                 for(size_t i = 1; i < A->mats.size(); ++i)
@@ -611,7 +686,7 @@ aoclsparse_status aoclsparse_optimize(aoclsparse_matrix A)
                         return aoclsparse_status_memory_error;
                     aoclsparse_status s = transpose_csr(M, A->val_type, want == DOID_GH, *C, st);
                     if(s == aoclsparse_status_success)
-                        s = build_plan(*C, value_size(A->val_type), -1, -1, std::vector<aoclsparse_int>(), st);
+                        s = build_plan_with_codes(*C, value_size(A->val_type), -1, -1, std::vector<aoclsparse_int>(), st);
                     if(s != aoclsparse_status_success)
                     {
                         delete C;
@@ -659,6 +734,9 @@ aoclsparse_status aoclsparse_b200_get_matrix_info(const aoclsparse_matrix A, aoc
         info->n_product_blocks = P.n_strat[STRAT_PRODUCT];
         info->n_long_segments  = P.n_long_segments;
         info->n_long_rows      = P.n_long_rows;
+        info->n_diag_codes     = P.n_codes;
+        info->hot_entries      = P.hot_entries;
+        info->hot_mass_ppm     = (aoclsparse_int)(P.hot_mass * 1e6);
     }
     return aoclsparse_status_success;
 }
@@ -683,6 +761,27 @@ aoclsparse_status aoclsparse_b200_get_plan(const aoclsparse_matrix A,
         B200_CUDA(cudaMemcpyAsync(block_desc, P.desc.p, sizeof(int4) * (size_t)P.n_blocks, cudaMemcpyDeviceToHost, st));
     if(block_kind && P.n_blocks > 0)
         B200_CUDA(cudaMemcpyAsync(block_kind, P.kind.p, sizeof(int) * (size_t)P.n_blocks, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    return aoclsparse_status_success;
+}
+
+aoclsparse_status aoclsparse_b200_get_diag_codes(const aoclsparse_matrix A,
+                                                 aoclsparse_int         *n_codes,
+                                                 aoclsparse_int         *offsets,
+                                                 unsigned char          *codes)
+{
+    if(!A || !n_codes)
+        return aoclsparse_status_invalid_pointer;
+    std::shared_lock<std::shared_mutex> rl(A->guard);
+    const row_block_plan               &P = A->mats[0]->plan;
+    *n_codes                              = P.valid ? P.n_codes : 0;
+    if(*n_codes == 0 || (!offsets && !codes))
+        return aoclsparse_status_success;
+    cudaStream_t st = current_stream();
+    if(offsets)
+        B200_CUDA(cudaMemcpyAsync(offsets, P.code_offsets.p, sizeof(int) * (size_t)P.n_codes, cudaMemcpyDeviceToHost, st));
+    if(codes)
+        B200_CUDA(cudaMemcpyAsync(codes, P.codes.p, (size_t)A->mats[0]->nnz, cudaMemcpyDeviceToHost, st));
     B200_CUDA(cudaStreamSynchronize(st));
     return aoclsparse_status_success;
 }

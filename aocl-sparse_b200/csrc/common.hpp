@@ -331,6 +331,7 @@ namespace b200
     int get_doid(bool complex_type, int descr_type, int fill_mode, int op);
 
     // ---------------------------------------------------------------- plan (analysis result)
+    constexpr int CODE_TABLE_MAX = 256; // entries of the diagonal-code table (one byte per code)
     enum : int
     {
         STRAT_THREAD  = 0, // one thread per row, operands read from the staged chunk
@@ -349,6 +350,21 @@ namespace b200
         aoclsparse_int n_strat[4] = {0, 0, 0, 0};
         aoclsparse_int max_block_rows = 0; // most rows any block holds (sizes the staged row_ptr slice)
         int            pdl              = 1; // programmatic dependent launch of the multiply kernel (tuning knob)
+        // hot-column table for gather-bound (power-law) matrices (hot.cu): 0 entries = not built
+        aoclsparse_int hot_entries = 0;
+        int            hot_stages  = 3;
+        int            hot_state   = 0; // 0 not analysed, 1 analysed (built or rejected)
+        double         hot_mass    = 0.0; // fraction of stored entries whose column is in the table
+        dev_buf        hot_cols;          // int[hot_entries]: column of every table slot
+        dev_buf        col_hot;           // int[nnz]: column array with the hot columns replaced by HOT_BIT | slot
+        // diagonal-code copy of col_idx (plan.cu, build_diag_codes): one byte per stored entry indexing the table of the
+        // matrix's distinct (col - row) offsets.  Built by aoclsparse_optimize when every block is thread-per-row and
+        // there are at most 256 distinct offsets (stencils, banded matrices); the multiply then streams 1 instead of 4
+        // index bytes per entry and decodes the identical column.
+        aoclsparse_int n_codes = 0; // table entries in use; 0 = not built / not applicable
+        int            code_state = 0; // 0 not analysed, 1 analysed (built or found not applicable)
+        dev_buf        codes;        // unsigned char[nnz]
+        dev_buf        code_offsets; // int[256], ascending, unused tail repeats the last entry
         int            threads     = 256; // CTA size of the multiply kernel (tuning knob)
         int            stream_hint = 1;   // tag the val/col stream evict-first in L2 (tuning knob)
         dev_buf        desc;      // int4 per block: first row, end row, first nnz, end nnz
@@ -471,13 +487,26 @@ namespace b200
                                  aoclsparse_int                     forced_strategy,
                                  const std::vector<aoclsparse_int> &row_cuts,
                                  cudaStream_t                       st,
-                                 aoclsparse_int                     block_nnz_override = 0);
+                                 aoclsparse_int                     block_nnz_override = 0,
+                                 bool                               coded              = false);
+    // plan + (when the matrix has at most 256 distinct col - row offsets and every block comes out thread-per-row) the
+    // diagonal-code copy, with the block size that copy wants; falls back to the plain plan otherwise
+    aoclsparse_status build_plan_with_codes(dev_csr                           &A,
+                                            size_t                             elem_size,
+                                            aoclsparse_int                     max_row_nnz,
+                                            aoclsparse_int                     forced_strategy,
+                                            const std::vector<aoclsparse_int> &row_cuts,
+                                            cudaStream_t                       st);
+    aoclsparse_status probe_diag_offsets(const dev_csr &A, std::vector<int> &offs, cudaStream_t st);
+    // optional second pass of the analysis: the diagonal-code copy of A's column indices (needs a valid plan)
+    aoclsparse_status build_diag_codes(dev_csr &A, cudaStream_t st);
     void              plan_parameters(size_t          elem_size,
                                       aoclsparse_int  m,
                                       aoclsparse_int  nnz,
                                       aoclsparse_int  max_row_nnz,
                                       aoclsparse_int &block_nnz,
-                                      aoclsparse_int &block_rows);
+                                      aoclsparse_int &block_rows,
+                                      bool            coded = false);
 
     // transpose.cu -- device csr -> csc (= transposed csr), optional conjugation
     aoclsparse_status transpose_csr(const dev_csr &A, int val_type, bool conj, dev_csr &out, cudaStream_t st);
@@ -501,6 +530,11 @@ namespace b200
                                       const aoclsparse_int *col_idx,
                                       const void           *val);
 
+    // hot.cu -- hot-column table (analysis) and the persistent warp-specialised kernel that uses it
+    aoclsparse_status build_hot_table(dev_csr &A, size_t elem_size, cudaStream_t st);
+    template <typename T>
+    aoclsparse_status launch_hot(const dev_csr &A, const T *x, T *y, T alpha, T beta, cudaStream_t st);
+
     // clean.cu
     aoclsparse_status ensure_clean(aoclsparse_matrix A, cudaStream_t st);
 
@@ -508,6 +542,15 @@ namespace b200
     // dropped, hints become pending again; the row-block plan depends on the pattern only and stays (caller holds the
     // write lock)
     void drop_derived_copies(aoclsparse_matrix A);
+
+    // spmv.cu -- one launch of the fused multiply + halo push + flags kernel (aoclsparse_b200_dmv_sharded_step)
+    aoclsparse_status sharded_step_launch(const double                   *alpha,
+                                          aoclsparse_matrix               A,
+                                          const aoclsparse_mat_descr      descr,
+                                          const double                   *x,
+                                          double                         *y,
+                                          const aoclsparse_b200_halo_ctl *ctl,
+                                          unsigned                        kc);
 
     // obtains (building on first use) the plan of mats[0]
     aoclsparse_status ensure_plan(aoclsparse_matrix A, cudaStream_t st);

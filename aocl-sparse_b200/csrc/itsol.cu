@@ -90,6 +90,25 @@ namespace b200
             int  gm_restart    = 20;
             bool locked        = false;
 
+            // the registered options with their current values (aoclsparse_itsol_handle_prn_options)
+            void print() const
+            {
+                static const char *methods[] = {"cg", "gmres"};
+                static const char *pre[]     = {"none", "user", "gs", "sym gs", "sgs", "ilu0"};
+                printf("Begin Options\n");
+                printf("   cg iteration limit            = %d\n", cg_maxit);
+                printf("   cg rel tolerance              = %.6e\n", (double)cg_rtol);
+                printf("   cg abs tolerance              = %.6e\n", (double)cg_atol);
+                printf("   cg preconditioner             = %s\n", pre[cg_precond >= 0 && cg_precond < 6 ? cg_precond : 0]);
+                printf("   gmres iteration limit         = %d\n", gm_maxit);
+                printf("   gmres rel tolerance           = %.6e\n", (double)gm_rtol);
+                printf("   gmres abs tolerance           = %.6e\n", (double)gm_atol);
+                printf("   gmres restart iterations      = %d\n", gm_restart);
+                printf("   gmres preconditioner          = %s\n", pre[gm_precond >= 0 && gm_precond < 6 ? gm_precond : 0]);
+                printf("   iterative method              = %s\n", methods[solver == 1 ? 1 : 0]);
+                printf("End Options\n");
+            }
+
             // 0 ok, 1 out of range, 2 bad value, 3 unknown option, 4 locked (OptionRegistry::SetOption return codes)
             int set(const std::string &name, const char *raw)
             {
@@ -1122,6 +1141,17 @@ void aoclsparse_itsol_destroy(aoclsparse_itsol_handle *handle)
         delete *handle;
         *handle = nullptr;
     }
+}
+
+// aoclsparse_solvers.h:147: prints the option registry of the handle to the standard output
+void aoclsparse_itsol_handle_prn_options(aoclsparse_itsol_handle handle)
+{
+    if(!handle)
+        return;
+    if(handle->type == aoclsparse_dmat && handle->d)
+        handle->d->opts.print();
+    else if(handle->type == aoclsparse_smat && handle->s)
+        handle->s->opts.print();
 }
 
 aoclsparse_status aoclsparse_itsol_option_set(aoclsparse_itsol_handle handle, const char *option, const char *value)

@@ -34,7 +34,8 @@ namespace b200
                          aoclsparse_int  nnz,
                          aoclsparse_int  max_row_nnz,
                          aoclsparse_int &block_nnz,
-                         aoclsparse_int &block_rows)
+                         aoclsparse_int &block_rows,
+                         bool            coded)
     {
         // staged bytes per entry = elem_size + 4 (column index); ~24 KB per CTA keeps 8 CTAs resident per SM,
         // which measured best on the 27-point stencil (profiles/r01_sweep_c2.txt): 2048 entries for 8-byte
@@ -42,6 +43,11 @@ namespace b200
         aoclsparse_int T = (aoclsparse_int)((24576 / (elem_size + 4)) / 512 * 512);
         // 16-byte values (double complex): 1536 entries (30 KB) measured best on the 27-point stencil, together with
         // 128-thread CTAs (build_plan): 4 109 -> 5 779 GB/s (tools/z_sweep.py, profiles/r01_summary.md)
+        // with the diagonal-code copy an entry stages elem_size + 1 bytes: the same ~24 KB per CTA hold more entries,
+        // which keeps as many bytes in flight per SM as the 32-bit column stream did (2048 entries of 9 bytes left
+        // HBM under-used: 8 TB/s-class bandwidth needs ~180 KB in flight per SM; profiles/r02_dcc_sweep.txt)
+        if(coded)
+            T = (aoclsparse_int)((24576 / (elem_size + 1) - 32) / 256 * 256);
         if(elem_size >= 16)
             T = 1536;
         // skewed row lengths (longest row > 16x the mean): x[col] is a random gather and the multiply is bound by
@@ -212,9 +218,10 @@ namespace b200
     }
 
     // CTAs of the multiply kernel that are resident at once on the whole chip for block size T
-    long long ctas_per_wave(size_t elem_size, aoclsparse_int T)
+    long long ctas_per_wave(size_t elem_size, aoclsparse_int T, bool coded)
     {
-        const long long smem = 16 + (long long)(T + 8) * (long long)(elem_size + 4) + 1024; // + 1 KB reserved per CTA
+        const long long smem = coded ? 16 + (long long)(T + 32) * (long long)(elem_size + 1) + 1024 + 1024
+                                     : 16 + (long long)(T + 8) * (long long)(elem_size + 4) + 1024; // + 1 KB reserved per CTA
         long long       c    = 232448 / smem;
         if(c > 8)
             c = 8; // 2048 threads per SM / 256
@@ -222,9 +229,10 @@ namespace b200
             c = 1;
         return 148 * c;
     }
-    bool wave_search_applies(size_t elem_size, aoclsparse_int nnz, aoclsparse_int T)
+    bool wave_search_applies(size_t elem_size, aoclsparse_int nnz, aoclsparse_int T, bool coded)
     {
-        return (long long)nnz < 8 * ctas_per_wave(elem_size, T) * (long long)T && (long long)nnz >= ctas_per_wave(elem_size, T) * (long long)T;
+        return (long long)nnz < 8 * ctas_per_wave(elem_size, T, coded) * (long long)T
+               && (long long)nnz >= ctas_per_wave(elem_size, T, coded) * (long long)T;
     }
 
     namespace
@@ -287,11 +295,12 @@ namespace b200
                                  aoclsparse_int                     forced_strategy,
                                  const std::vector<aoclsparse_int> &row_cuts,
                                  cudaStream_t                       st,
-                                 aoclsparse_int                     block_nnz_override)
+                                 aoclsparse_int                     block_nnz_override,
+                                 bool                               coded)
     {
         row_block_plan &P = A.plan;
         P                 = row_block_plan();
-        plan_parameters(elem_size, A.m, A.nnz, max_row_nnz, P.block_nnz, P.block_rows);
+        plan_parameters(elem_size, A.m, A.nnz, max_row_nnz, P.block_nnz, P.block_rows, coded);
         if(block_nnz_override > 0)
             P.block_nnz = block_nnz_override;
         // few rows per block (long rows or wide values): the thread-per-row strategy keeps only one lane per row busy, so
@@ -327,7 +336,7 @@ namespace b200
         dev_buf                     d_seg, d_grid, d_cnt;
         aoclsparse_int              T = P.block_nnz;
         const aoclsparse_int        R = P.block_rows;
-        if(block_nnz_override <= 0 && wave_search_applies(elem_size, A.nnz, T) && !getenv("AOCLSPARSE_B200_BLOCK_NNZ"))
+        if(block_nnz_override <= 0 && wave_search_applies(elem_size, A.nnz, T, coded) && !getenv("AOCLSPARSE_B200_BLOCK_NNZ"))
         {
             long long      best_cost = -1;
             aoclsparse_int best_T    = T;
@@ -338,7 +347,7 @@ namespace b200
                 long long nbk = 0;
                 for(const int3 &c : counts)
                     nbk += c.x;
-                const long long wave  = ctas_per_wave(elem_size, Tk);
+                const long long wave  = ctas_per_wave(elem_size, Tk, coded);
                 // 1.5 % slack: a last wave that is only just full still ends late (measured, profiles/r01_summary.md)
                 const long long cost  = (((nbk * 203 + 199) / 200 + wave - 1) / wave) * (long long)Tk;
                 if(best_cost < 0 || cost < best_cost)
@@ -411,6 +420,179 @@ namespace b200
         P.max_block_rows = sc[8] > 1 ? sc[8] : 1;
 
         P.valid = true;
+        return aoclsparse_status_success;
+    }
+
+    // ------------------------------------------------------------------------------------------------------------
+    // Diagonal-code copy.  SPEC (restated by oracle/csr_oracle.c::oracle_diag_codes, compared bit for bit):
+    //   D = sorted (ascending) set of the distinct values col_idx[p] - r over all stored entries p of all rows r
+    //   if 1 <= |D| <= 256: codes[p] = index of (col_idx[p] - r) in D, code_offsets[i] = D[i] (i >= |D|: D[|D|-1])
+    //   else: not applicable (n_codes = 0).
+    // ------------------------------------------------------------------------------------------------------------
+    namespace
+    {
+        constexpr int OFFSET_SLOTS = 1024;
+        constexpr int OFFSET_EMPTY = (int)0x80000000;
+
+        // ctl[0] = distinct offsets inserted so far, ctl[1] = 1 once there are more than 256 (everyone gives up)
+        __global__ void collect_offsets_kernel(aoclsparse_int m,
+                                               const aoclsparse_int *__restrict__ rp,
+                                               const aoclsparse_int *__restrict__ col,
+                                               int *table,
+                                               int *ctl)
+        {
+            const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+            if(r >= m || *(volatile int *)(ctl + 1))
+                return;
+            int last = OFFSET_EMPTY; // consecutive rows of a stencil repeat the same offsets: skip the re-probe
+            for(aoclsparse_int p = rp[r]; p < rp[r + 1]; ++p)
+            {
+                const int off = col[p] - (int)r;
+                if(off == last)
+                    continue;
+                last       = off;
+                unsigned h = ((unsigned)off * 2654435761u) >> 22; // 10 bits
+                for(int probe = 0; probe < OFFSET_SLOTS; ++probe, h = (h + 1) & (OFFSET_SLOTS - 1))
+                {
+                    int cur = *(volatile int *)(table + h);
+                    if(cur == off)
+                        break;
+                    if(cur == OFFSET_EMPTY)
+                    {
+                        cur = atomicCAS(table + h, OFFSET_EMPTY, off);
+                        if(cur == OFFSET_EMPTY)
+                        {
+                            if(atomicAdd(ctl, 1) + 1 > CODE_TABLE_MAX)
+                                atomicExch(ctl + 1, 1);
+                            break;
+                        }
+                        if(cur == off)
+                            break;
+                    }
+                }
+                if(*(volatile int *)(ctl + 1))
+                    return;
+            }
+        }
+
+        __global__ void encode_offsets_kernel(aoclsparse_int m,
+                                              const aoclsparse_int *__restrict__ rp,
+                                              const aoclsparse_int *__restrict__ col,
+                                              const int *__restrict__ sorted_off,
+                                              int            n_off,
+                                              unsigned char *codes)
+        {
+            __shared__ int so[CODE_TABLE_MAX];
+            for(int i = threadIdx.x; i < CODE_TABLE_MAX; i += blockDim.x)
+                so[i] = sorted_off[i];
+            __syncthreads();
+            const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+            if(r >= m)
+                return;
+            for(aoclsparse_int p = rp[r]; p < rp[r + 1]; ++p)
+            {
+                const int off = col[p] - (int)r;
+                int       lo = 0, hi = n_off - 1;
+                while(lo < hi)
+                {
+                    const int mid = (lo + hi) >> 1;
+                    if(so[mid] < off)
+                        lo = mid + 1;
+                    else
+                        hi = mid;
+                }
+                codes[p] = (unsigned char)lo;
+            }
+        }
+    }
+
+    // the sorted distinct (col - row) offsets of A, empty when there are none or more than 256 (or the knob is off)
+    aoclsparse_status probe_diag_offsets(const dev_csr &A, std::vector<int> &offs, cudaStream_t st)
+    {
+        offs.clear();
+        if(A.nnz <= 0 || A.m <= 0)
+            return aoclsparse_status_success;
+        if(const char *e = getenv("AOCLSPARSE_B200_DIAG_CODES")) // A/B knob
+            if(atoi(e) == 0)
+                return aoclsparse_status_success;
+        dev_buf work;
+        B200_TRY(work.alloc(sizeof(int) * (OFFSET_SLOTS + 2)));
+        int *table = work.as<int>(), *ctl = table + OFFSET_SLOTS;
+        std::vector<int> h((size_t)OFFSET_SLOTS + 2, OFFSET_EMPTY);
+        h[OFFSET_SLOTS] = h[OFFSET_SLOTS + 1] = 0;
+        B200_CUDA(cudaMemcpyAsync(table, h.data(), sizeof(int) * h.size(), cudaMemcpyHostToDevice, st));
+        const unsigned grid = (unsigned)(((long long)A.m + 255) / 256);
+        collect_offsets_kernel<<<grid, 256, 0, st>>>(A.m, A.row_ptr.as<aoclsparse_int>(), A.col_idx.as<aoclsparse_int>(), table, ctl);
+        B200_LAUNCHED();
+        B200_CUDA(cudaMemcpyAsync(h.data(), table, sizeof(int) * h.size(), cudaMemcpyDeviceToHost, st));
+        B200_CUDA(cudaStreamSynchronize(st));
+        if(h[OFFSET_SLOTS + 1] != 0 || h[OFFSET_SLOTS] <= 0 || h[OFFSET_SLOTS] > CODE_TABLE_MAX)
+            return aoclsparse_status_success; // too many distinct diagonals: keep the 32-bit column stream
+        for(int i = 0; i < OFFSET_SLOTS; ++i)
+            if(h[i] != OFFSET_EMPTY)
+                offs.push_back(h[i]);
+        if((int)offs.size() != h[OFFSET_SLOTS])
+        {
+            offs.clear();
+            return aoclsparse_status_internal_error;
+        }
+        std::sort(offs.begin(), offs.end());
+        return aoclsparse_status_success;
+    }
+
+    aoclsparse_status build_diag_codes(dev_csr &A, cudaStream_t st)
+    {
+        row_block_plan &P = A.plan;
+        P.n_codes         = 0;
+        P.code_state      = 1;
+        P.codes.release();
+        P.code_offsets.release();
+        if(!P.valid || P.n_blocks <= 0 || A.nnz <= 0 || P.n_strat[STRAT_THREAD] != P.n_blocks)
+            return aoclsparse_status_success;
+        std::vector<int> offs;
+        B200_TRY(probe_diag_offsets(A, offs, st));
+        if(offs.empty())
+            return aoclsparse_status_success;
+        const unsigned grid  = (unsigned)(((long long)A.m + 255) / 256);
+        const int      n_off = (int)offs.size();
+        offs.resize(CODE_TABLE_MAX, offs.back());
+        B200_TRY(P.code_offsets.alloc(sizeof(int) * CODE_TABLE_MAX));
+        B200_TRY(P.codes.alloc((size_t)A.nnz));
+        B200_CUDA(cudaMemcpyAsync(P.code_offsets.p, offs.data(), sizeof(int) * CODE_TABLE_MAX, cudaMemcpyHostToDevice, st));
+        encode_offsets_kernel<<<grid, 256, 0, st>>>(A.m,
+                                                   A.row_ptr.as<aoclsparse_int>(),
+                                                   A.col_idx.as<aoclsparse_int>(),
+                                                   P.code_offsets.as<int>(),
+                                                   n_off,
+                                                   P.codes.as<unsigned char>());
+        B200_LAUNCHED();
+        B200_CUDA(cudaStreamSynchronize(st)); // offs (host) is read by the copy above
+        P.n_codes = n_off;
+        return aoclsparse_status_success;
+    }
+
+    aoclsparse_status build_plan_with_codes(dev_csr                           &A,
+                                            size_t                             elem_size,
+                                            aoclsparse_int                     max_row_nnz,
+                                            aoclsparse_int                     forced_strategy,
+                                            const std::vector<aoclsparse_int> &row_cuts,
+                                            cudaStream_t                       st)
+    {
+        std::vector<int> offs;
+        if(forced_strategy < 0 || forced_strategy == STRAT_THREAD)
+            B200_TRY(probe_diag_offsets(A, offs, st));
+        B200_TRY(build_plan(A, elem_size, max_row_nnz, forced_strategy, row_cuts, st, 0, !offs.empty()));
+        if(offs.empty())
+        {
+            A.plan.code_state = 1;
+            return aoclsparse_status_success;
+        }
+        B200_TRY(build_diag_codes(A, st));
+        if(A.plan.n_codes == 0) // some block is not thread-per-row: the plain plan with its own block size
+        {
+            B200_TRY(build_plan(A, elem_size, max_row_nnz, forced_strategy, row_cuts, st));
+            A.plan.code_state = 1;
+        }
         return aoclsparse_status_success;
     }
 }

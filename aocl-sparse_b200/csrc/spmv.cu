@@ -62,7 +62,7 @@ namespace b200
             return cache[key] = (long long)per_sm * sms;
         }
 
-        template <typename T, bool GENERIC, int NT, bool PUSH = false>
+        template <typename T, bool GENERIC, int NT, bool PUSH = false, bool CODED = false>
         aoclsparse_status launch_row_blocks(const dev_csr &A,
                                             int            b0,
                                             int            b1,
@@ -76,13 +76,13 @@ namespace b200
                                             int            push_row0 = 0)
         {
             const row_block_plan &P    = A.plan;
-            const int             cap  = P.block_nnz + 8;
-            const size_t          smem = spmv_smem_bytes(sizeof(T), P.block_nnz);
+            const int             cap  = P.block_nnz + (CODED ? 32 : 8);
+            const size_t          smem = CODED ? spmv_coded_smem_bytes(sizeof(T), P.block_nnz) : spmv_smem_bytes(sizeof(T), P.block_nnz);
             static std::atomic<size_t> configured{0};
             if(configured.load(std::memory_order_acquire) < smem)
             {
                 B200_CUDA(cudaFuncSetAttribute(
-                    spmv_row_blocks_kernel<T, GENERIC, NT, PUSH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    spmv_row_blocks_kernel<T, GENERIC, NT, PUSH, CODED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 configured.store(smem, std::memory_order_release);
             }
             cudaLaunchConfig_t cfg = {};
@@ -100,9 +100,9 @@ namespace b200
             // could leave lines in an SM's L1 that launch k then hits through ld.global.nc after its
             // griddepcontrol.wait.  With more CTAs than fit the chip, the last CTA of launch k-1 cannot start before
             // launch k-2 has completed, so launch k (which starts after it) never overlaps k-2.
-            cfg.numAttrs = (P.pdl && (long long)(b1 - b0) > resident_ctas(spmv_row_blocks_kernel<T, GENERIC, NT, PUSH>, NT, smem)) ? 1 : 0;
+            cfg.numAttrs = (P.pdl && (long long)(b1 - b0) > resident_ctas(spmv_row_blocks_kernel<T, GENERIC, NT, PUSH, CODED>, NT, smem)) ? 1 : 0;
             B200_CUDA(cudaLaunchKernelEx(&cfg,
-                                         spmv_row_blocks_kernel<T, GENERIC, NT, PUSH>,
+                                         spmv_row_blocks_kernel<T, GENERIC, NT, PUSH, CODED>,
                                          (const int4 *)P.desc.as<int4>(),
                                          (const int *)P.kind.as<int>(),
                                          b0,
@@ -120,7 +120,9 @@ namespace b200
                                          (int)A.n,
                                          P.stream_hint,
                                          push_dst,
-                                         push_row0));
+                                         push_row0,
+                                         (const unsigned char *)P.codes.as<unsigned char>(),
+                                         (const int *)P.code_offsets.as<int>()));
             B200_LAUNCHED();
             return aoclsparse_status_success;
         }
@@ -145,7 +147,32 @@ namespace b200
             if(b1 <= b0)
                 return aoclsparse_status_success;
             const int bz = is_zero(beta) ? 1 : 0;
-            if(push_dst)
+            // hot-column table (aoclsparse_optimize on a power-law matrix): persistent warp-specialised kernel, whole
+            // matrix only (real value types)
+            if constexpr(!vt<T>::is_complex)
+            {
+                if(!generic && !push_dst && P.hot_entries > 0 && b0 == 0 && b1 == P.n_blocks)
+                {
+                    B200_TRY(launch_hot<T>(A, x, y, alpha, beta, st));
+                    if(P.n_long_rows > 0)
+                    {
+                        const long long threads = (long long)P.n_long_rows * 32;
+                        finish_long_rows_kernel<T><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(
+                            P.n_long_rows, P.long_rows.as<int4>(), P.partials.as<T>(), x, y, alpha, beta, bz, 0, A.n, row_lo, row_hi);
+                        B200_LAUNCHED();
+                    }
+                    return aoclsparse_status_success;
+                }
+            }
+            // diagonal-code copy (aoclsparse_optimize on a banded / stencil matrix): 1 instead of 4 index bytes per entry
+            const bool coded = !generic && P.n_codes > 0 && P.n_strat[STRAT_THREAD] == P.n_blocks;
+            if(coded && push_dst)
+                B200_TRY((launch_row_blocks<T, false, 256, true, true>(A, b0, b1, x, y, alpha, beta, rule, st, push_dst, row_lo)));
+            else if(coded && P.threads == 128)
+                B200_TRY((launch_row_blocks<T, false, 128, false, true>(A, b0, b1, x, y, alpha, beta, rule, st)));
+            else if(coded)
+                B200_TRY((launch_row_blocks<T, false, 256, false, true>(A, b0, b1, x, y, alpha, beta, rule, st)));
+            else if(push_dst)
                 B200_TRY((launch_row_blocks<T, false, 256, true>(A, b0, b1, x, y, alpha, beta, rule, st, push_dst, row_lo)));
             else if(generic)
                 B200_TRY((launch_row_blocks<T, true, 256>(A, b0, b1, x, y, alpha, beta, rule, st)));
@@ -241,7 +268,7 @@ namespace b200
             {
                 std::shared_lock<std::shared_mutex> rl0(A->guard);
                 for(const hint &h : A->hints)
-                    hinted = hinted || (h.act == 1 && h.doid == d_id && h.done);
+                    hinted = hinted || ((h.act == 1 || h.act == 8) && h.doid == d_id && h.done);
             }
             // no hint, but the same kind of product keeps coming: build the copy after a few calls, as the reference's
             // mv lazily builds its optimised CSR (csr_util.hpp:812-825).  Gather + atomic scatter costs ~3.7x the
@@ -437,6 +464,10 @@ namespace b200
             // 16 chunks 0.62 ms; un-pipelined 0.755 ms)
             int n_chunks = (int)(vec_bytes / (size_t)(4u << 20));
             n_chunks     = n_chunks < 2 ? 2 : (n_chunks > 8 ? 8 : n_chunks);
+            // very long vectors (config 5: 2 x 1 GB): the copies dominate and the un-overlapped tail is the last chunk's
+            // kernel + read-back, so cut finer
+            if(vec_bytes >= ((size_t)512u << 20))
+                n_chunks = 16;
             if(const char *e = getenv("AOCLSPARSE_B200_HOST_CHUNKS"))
                 n_chunks = atoi(e) < 1 ? 1 : (atoi(e) > 16 ? 16 : atoi(e));
             int run_max  = -1;
@@ -1214,13 +1245,18 @@ aoclsparse_status aoclsparse_b200_ipc_free(void *dptr)
     return aoclsparse_status_success;
 }
 
+}
+
 // One launch per iteration of the row-sharded product: multiply + halo push + flags (spmv_sharded.cuh).
-aoclsparse_status aoclsparse_b200_dmv_sharded_step(const double                  *alpha,
-                                                   aoclsparse_matrix              A,
-                                                   const aoclsparse_mat_descr     descr,
-                                                   const double                  *x,
-                                                   double                        *y,
-                                                   const aoclsparse_b200_halo_ctl *ctl)
+// kc = launches of this kernel on these counters so far, this one included (the flags carry ctl->k, which may run ahead
+// of kc when other events -- the initial halo publication of shard.cu -- take a number as well)
+aoclsparse_status b200::sharded_step_launch(const double                  *alpha,
+                                            aoclsparse_matrix              A,
+                                            const aoclsparse_mat_descr     descr,
+                                            const double                  *x,
+                                            double                        *y,
+                                            const aoclsparse_b200_halo_ctl *ctl,
+                                            unsigned                        kc)
 {
     if(!alpha || !A || !descr || !x || !y || !ctl || !ctl->counters)
         return aoclsparse_status_invalid_pointer;
@@ -1249,6 +1285,7 @@ aoclsparse_status aoclsparse_b200_dmv_sharded_step(const double                 
     hc.to_right_done = static_cast<unsigned *>(ctl->to_right_done);
     hc.counters      = static_cast<unsigned *>(ctl->counters);
     hc.k                 = ctl->k;
+    hc.kc                = kc;
     hc.n_first           = P.cut_block[0];
     hc.last_begin        = P.cut_block[1];
     hc.n_last            = P.n_blocks - P.cut_block[1];
@@ -1259,13 +1296,15 @@ aoclsparse_status aoclsparse_b200_dmv_sharded_step(const double                 
         return aoclsparse_status_invalid_pointer;
     if(A->win_hi >= 0)
         x = x - A->win_lo;
-    const int    cap  = P.block_nnz + 8;
-    const size_t smem = spmv_smem_bytes(sizeof(double), P.block_nnz);
-    static std::atomic<size_t> configured{0};
-    if(configured.load() < smem)
+    const bool   coded = P.n_codes > 0;
+    const int    cap   = P.block_nnz + (coded ? 32 : 8);
+    const size_t smem  = coded ? spmv_coded_smem_bytes(sizeof(double), P.block_nnz) : spmv_smem_bytes(sizeof(double), P.block_nnz);
+    auto         kern  = coded ? spmv_sharded_step_kernel<double, true> : spmv_sharded_step_kernel<double, false>;
+    static std::atomic<size_t> configured[2] = {{0}, {0}};
+    if(configured[coded].load() < smem)
     {
-        B200_CUDA(cudaFuncSetAttribute(spmv_sharded_step_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured.store(smem);
+        B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[coded].store(smem);
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim            = dim3((unsigned)P.n_blocks);
@@ -1277,9 +1316,9 @@ aoclsparse_status aoclsparse_b200_dmv_sharded_step(const double                 
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs                                          = attr;
     // more than one wave only: see launch_row_blocks
-    cfg.numAttrs = (P.pdl && (long long)P.n_blocks > resident_ctas(spmv_sharded_step_kernel<double>, 256, smem)) ? 1 : 0;
+    cfg.numAttrs = (P.pdl && (long long)P.n_blocks > resident_ctas(kern, 256, smem)) ? 1 : 0;
     B200_CUDA(cudaLaunchKernelEx(&cfg,
-                                 spmv_sharded_step_kernel<double>,
+                                 kern,
                                  (const int4 *)P.desc.as<int4>(),
                                  cap,
                                  (const aoclsparse_int *)M.row_ptr.as<aoclsparse_int>(),
@@ -1290,8 +1329,23 @@ aoclsparse_status aoclsparse_b200_dmv_sharded_step(const double                 
                                  *alpha,
                                  static_cast<double *>(ctl->push_left),
                                  static_cast<double *>(ctl->push_right),
-                                 hc));
+                                 hc,
+                                 (const unsigned char *)P.codes.as<unsigned char>(),
+                                 (const int *)P.code_offsets.as<int>()));
     B200_LAUNCHED();
     return aoclsparse_status_success;
+}
+
+extern "C" {
+aoclsparse_status aoclsparse_b200_dmv_sharded_step(const double                  *alpha,
+                                                   aoclsparse_matrix              A,
+                                                   const aoclsparse_mat_descr     descr,
+                                                   const double                  *x,
+                                                   double                        *y,
+                                                   const aoclsparse_b200_halo_ctl *ctl)
+{
+    if(!ctl)
+        return aoclsparse_status_invalid_pointer;
+    return b200::sharded_step_launch(alpha, A, descr, x, y, ctl, ctl->k);
 }
 }

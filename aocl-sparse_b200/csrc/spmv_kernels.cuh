@@ -169,13 +169,23 @@ namespace b200
     {
         return SMEM_HEADER + (size_t)(block_nnz + 8) * (elem_size + 4);
     }
+    // CODED variant: values, one code byte per entry (16-entry alignment slack at both ends), the offset table
+    constexpr int CODE_TABLE = CODE_TABLE_MAX;
+    inline size_t spmv_coded_smem_bytes(size_t elem_size, aoclsparse_int block_nnz)
+    {
+        return SMEM_HEADER + (size_t)(block_nnz + 32) * (elem_size + 1) + CODE_TABLE * sizeof(int);
+    }
 
     // GENERIC == false: general matrix, no conjugation (the measured hot path)
     // GENERIC == true : entries filtered / conjugated by `rule` (triangular, symmetric, hermitian parts)
     // PUSH == true: every computed y[r] is also stored to push_dst[r - push_row0], a buffer that may live in a
     //                PEER GPU's memory (mapped over NVLink): the boundary rows of a row-sharded matrix write the
     //                neighbour's halo of the next x directly from this epilogue -- no separate copy or collective.
-    template <typename T, bool GENERIC, int NT, bool PUSH = false>
+    // CODED == true (never with GENERIC; every block thread-per-row): the column stream is the DIAGONAL-CODE copy
+    //                built by aoclsparse_optimize (plan.cu, build_diag_codes): one byte per stored entry, an index
+    //                into the table of the matrix's distinct (col - row) offsets, so col = row + code_off[code] --
+    //                the same column, bit for bit, from a quarter of the bytes.  `col` is then unused.
+    template <typename T, bool GENERIC, int NT, bool PUSH = false, bool CODED = false>
     __global__ void __launch_bounds__(NT) spmv_row_blocks_kernel(const int4 *__restrict__ desc,
                                                                           const int *__restrict__ kind,
                                                                           int block_first,
@@ -193,12 +203,85 @@ namespace b200
                                                                           int       n_cols,
                                                                           int       stream_hint,
                                                                           T        *push_dst  = nullptr,
-                                                                          int       push_row0 = 0)
+                                                                          int       push_row0 = 0,
+                                                                          const unsigned char *__restrict__ codes = nullptr,
+                                                                          const int *__restrict__ code_off = nullptr)
     {
         extern __shared__ __align__(16) unsigned char smem_raw[];
         uint64_t       *bar  = reinterpret_cast<uint64_t *>(smem_raw);
         T              *sval = reinterpret_cast<T *>(smem_raw + SMEM_HEADER);
         aoclsparse_int *scol = reinterpret_cast<aoclsparse_int *>(smem_raw + SMEM_HEADER + (size_t)cap * sizeof(T));
+
+        if constexpr(CODED)
+        {
+            static_assert(!GENERIC, "the diagonal-code copy serves the plain general product only");
+            const unsigned char *scode = smem_raw + SMEM_HEADER + (size_t)cap * sizeof(T);
+            int                 *soff  = reinterpret_cast<int *>(smem_raw + SMEM_HEADER + (size_t)cap * (sizeof(T) + 1));
+            const int            tid   = threadIdx.x;
+            const int4           d     = desc[blockIdx.x + block_first];
+            asm volatile("griddepcontrol.launch_dependents;");
+            // staged window [a, a+cnt): 16-entry granules keep both bulk copies 16-byte aligned
+            const int a   = d.z & ~15;
+            const int cnt = ((d.w - a) + 15) & ~15;
+            if(tid == 0)
+            {
+                mbar_init(bar, 1);
+                mbar_init_fence();
+                if(cnt > 0)
+                {
+                    mbar_expect_tx(bar, (unsigned)(cnt * (sizeof(T) + 1)));
+                    if(stream_hint)
+                    {
+                        bulk_load_stream(sval, val + a, (unsigned)(cnt * sizeof(T)), bar);
+                        bulk_load_stream(const_cast<unsigned char *>(scode), codes + a, (unsigned)cnt, bar);
+                    }
+                    else
+                    {
+                        bulk_load(sval, val + a, (unsigned)(cnt * sizeof(T)), bar);
+                        bulk_load(const_cast<unsigned char *>(scode), codes + a, (unsigned)cnt, bar);
+                    }
+                }
+            }
+            for(int i = tid; i < CODE_TABLE; i += NT)
+                soff[i] = code_off[i];
+            __syncthreads();
+            int pre_s = 0, pre_e = 0;
+            T   pre_y = vt<T>::zero();
+            if(d.x + tid < d.y)
+            {
+                pre_s = rp[d.x + tid];
+                pre_e = rp[d.x + tid + 1];
+            }
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            if(d.x + tid < d.y && !beta_zero)
+                pre_y = y[d.x + tid];
+            if(cnt > 0)
+                mbar_wait(bar, 0);
+            for(int r = d.x + tid; r < d.y; r += NT)
+            {
+                const bool first = r == d.x + tid;
+                int        j     = (first ? pre_s : rp[r]) - a;
+                const int  e     = (first ? pre_e : rp[r + 1]) - a;
+                T          acc   = vt<T>::zero();
+                const T   *xr    = x + r; // x[col] = xr[col - row]
+                for(; j + 4 <= e; j += 4)
+                {
+                    const int o0 = soff[scode[j]], o1 = soff[scode[j + 1]], o2 = soff[scode[j + 2]], o3 = soff[scode[j + 3]];
+                    const T   x0 = ldg_ro(xr + o0), x1 = ldg_ro(xr + o1), x2 = ldg_ro(xr + o2), x3 = ldg_ro(xr + o3);
+                    acc          = mad(sval[j], x0, acc);
+                    acc          = mad(sval[j + 1], x1, acc);
+                    acc          = mad(sval[j + 2], x2, acc);
+                    acc          = mad(sval[j + 3], x3, acc);
+                }
+                for(; j < e; ++j)
+                    acc = mad(sval[j], ldg_ro(xr + soff[scode[j]]), acc);
+                const T out = axpby_out(alpha, acc, beta, beta_zero != 0, first ? &pre_y : y + r);
+                y[r]        = out;
+                if constexpr(PUSH)
+                    push_dst[r - push_row0] = out;
+            }
+            return;
+        }
 
         const int  tid  = threadIdx.x;
         const int  lane = tid & 31;

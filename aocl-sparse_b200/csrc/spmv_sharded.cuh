@@ -26,7 +26,8 @@ namespace b200
         // signals (addresses in the NEIGHBOURS' memory)
         unsigned *to_left_done, *to_right_done;
         unsigned *counters; // [0] first-boundary CTAs done, [1] last-boundary CTAs done, [3] a flag wait gave up
-        unsigned  k;        // iteration number, 1-based
+        unsigned  k;        // iteration number, 1-based: the value the flags carry
+        unsigned  kc;       // launches of this kernel so far, this one included: the counters' target is kc * CTAs
         int       n_first, n_last, n_blocks; // blocks in the first boundary, the last boundary, in total
         int       last_begin;                // index of the first block of the last boundary
         int       first_rows, last_row0;     // rows in the first boundary; first row of the last boundary
@@ -49,7 +50,9 @@ namespace b200
         return true;
     }
 
-    template <typename T>
+    // CODED: the column stream is the diagonal-code copy (one byte per entry, col = row + code_off[code]; see
+    // spmv_row_blocks_kernel)
+    template <typename T, bool CODED = false>
     __global__ void __launch_bounds__(256) spmv_sharded_step_kernel(const int4 *__restrict__ desc,
                                                                    int cap,
                                                                    const aoclsparse_int *__restrict__ rp,
@@ -60,13 +63,17 @@ namespace b200
                                                                    T        alpha,
                                                                    T       *push_left,  // neighbour's halo for my first rows
                                                                    T       *push_right, // neighbour's halo for my last rows
-                                                                   halo_ctl hc)
+                                                                   halo_ctl hc,
+                                                                   const unsigned char *__restrict__ codes = nullptr,
+                                                                   const int *__restrict__ code_off = nullptr)
     {
         constexpr int NT = 256;
         extern __shared__ __align__(16) unsigned char smem_raw[];
-        uint64_t       *bar  = reinterpret_cast<uint64_t *>(smem_raw);
-        T              *sval = reinterpret_cast<T *>(smem_raw + SMEM_HEADER);
-        aoclsparse_int *scol = reinterpret_cast<aoclsparse_int *>(smem_raw + SMEM_HEADER + (size_t)cap * sizeof(T));
+        uint64_t            *bar   = reinterpret_cast<uint64_t *>(smem_raw);
+        T                   *sval  = reinterpret_cast<T *>(smem_raw + SMEM_HEADER);
+        aoclsparse_int      *scol  = reinterpret_cast<aoclsparse_int *>(smem_raw + SMEM_HEADER + (size_t)cap * sizeof(T));
+        const unsigned char *scode = smem_raw + SMEM_HEADER + (size_t)cap * sizeof(T);
+        int                 *soff  = reinterpret_cast<int *>(smem_raw + SMEM_HEADER + (size_t)cap * (sizeof(T) + 1));
 
         const int tid = threadIdx.x;
         // launch order -> block: first boundary, last boundary, then the interior
@@ -89,19 +96,32 @@ namespace b200
         }
         const int4 d = desc[b];
         asm volatile("griddepcontrol.launch_dependents;");
-        const int a   = d.z & ~3;
-        const int cnt = ((d.w - a) + 3) & ~3;
+        constexpr int GR  = CODED ? 16 : 4; // entries per 16-byte granule of the narrowest staged array
+        const int     a   = d.z & ~(GR - 1);
+        const int     cnt = ((d.w - a) + GR - 1) & ~(GR - 1);
         if(tid == 0)
         {
             mbar_init(bar, 1);
             mbar_init_fence();
             if(cnt > 0)
             {
-                mbar_expect_tx(bar, (unsigned)(cnt * (sizeof(T) + sizeof(aoclsparse_int))));
-                bulk_load_stream(sval, val + a, (unsigned)(cnt * sizeof(T)), bar);
-                bulk_load_stream(scol, col + a, (unsigned)(cnt * sizeof(aoclsparse_int)), bar);
+                if constexpr(CODED)
+                {
+                    mbar_expect_tx(bar, (unsigned)(cnt * (sizeof(T) + 1)));
+                    bulk_load_stream(sval, val + a, (unsigned)(cnt * sizeof(T)), bar);
+                    bulk_load_stream(const_cast<unsigned char *>(scode), codes + a, (unsigned)cnt, bar);
+                }
+                else
+                {
+                    mbar_expect_tx(bar, (unsigned)(cnt * (sizeof(T) + sizeof(aoclsparse_int))));
+                    bulk_load_stream(sval, val + a, (unsigned)(cnt * sizeof(T)), bar);
+                    bulk_load_stream(scol, col + a, (unsigned)(cnt * sizeof(aoclsparse_int)), bar);
+                }
             }
         }
+        if constexpr(CODED)
+            for(int i = tid; i < CODE_TABLE; i += NT)
+                soff[i] = code_off[i];
         __syncthreads();
         int pre_s = 0, pre_e = 0;
         if(d.x + tid < d.y)
@@ -125,6 +145,13 @@ namespace b200
         if(cnt > 0)
             mbar_wait(bar, 0);
 
+        // column of staged entry j of row r
+        auto col_at = [&](int r, int j) -> int {
+            if constexpr(CODED)
+                return r + soff[scode[j]];
+            else
+                return scol[j];
+        };
         T *push = side == 0 ? push_left : (side == 1 ? push_right : nullptr);
         const int push_row0 = side == 0 ? 0 : hc.last_row0;
         if(side == 2)
@@ -139,7 +166,7 @@ namespace b200
                 T          acc   = vt<T>::zero();
                 for(; j + 4 <= e; j += 4)
                 {
-                    const int c0 = scol[j], c1 = scol[j + 1], c2 = scol[j + 2], c3 = scol[j + 3];
+                    const int c0 = col_at(r, j), c1 = col_at(r, j + 1), c2 = col_at(r, j + 2), c3 = col_at(r, j + 3);
                     const T   x0 = ldg_ro(x + c0), x1 = ldg_ro(x + c1), x2 = ldg_ro(x + c2), x3 = ldg_ro(x + c3);
                     acc          = mad(sval[j], x0, acc);
                     acc          = mad(sval[j + 1], x1, acc);
@@ -147,7 +174,7 @@ namespace b200
                     acc          = mad(sval[j + 3], x3, acc);
                 }
                 for(; j < e; ++j)
-                    acc = mad(sval[j], ldg_ro(x + scol[j]), acc);
+                    acc = mad(sval[j], ldg_ro(x + col_at(r, j)), acc);
                 y[r] = mul(alpha, acc);
             }
         }
@@ -164,7 +191,7 @@ namespace b200
                 T          acc   = vt<T>::zero();
                 for(; j + 4 <= e; j += 4)
                 {
-                    const int c0 = scol[j], c1 = scol[j + 1], c2 = scol[j + 2], c3 = scol[j + 3];
+                    const int c0 = col_at(r, j), c1 = col_at(r, j + 1), c2 = col_at(r, j + 2), c3 = col_at(r, j + 3);
                     const T   x0 = __ldcg(x + c0), x1 = __ldcg(x + c1), x2 = __ldcg(x + c2), x3 = __ldcg(x + c3);
                     acc          = mad(sval[j], x0, acc);
                     acc          = mad(sval[j + 1], x1, acc);
@@ -172,7 +199,7 @@ namespace b200
                     acc          = mad(sval[j + 3], x3, acc);
                 }
                 for(; j < e; ++j)
-                    acc = mad(sval[j], __ldcg(x + scol[j]), acc);
+                    acc = mad(sval[j], __ldcg(x + col_at(r, j)), acc);
                 const T out = mul(alpha, acc);
                 y[r]        = out;
                 if(push)
@@ -189,7 +216,7 @@ namespace b200
                 __threadfence_system(); // this CTA's stores (peer stores included) before the counter / flag
                 const unsigned n_side = side == 0 ? (unsigned)hc.n_first : (unsigned)hc.n_last;
                 const unsigned done   = atomicAdd(hc.counters + side, 1u) + 1u;
-                if(done == hc.k * n_side)
+                if(done == hc.kc * n_side)
                 {
                     unsigned *flag = side == 0 ? hc.to_left_done : hc.to_right_done;
                     if(flag)

@@ -57,6 +57,9 @@ WORKLOADS = {
     "c5": dict(name="c5: 3D 7-point stencil 512^3, CSR double, row-sharded, x<-A*x/12 iterated, halo exchange",
                kind="mv", stencil=(7, 512, 512, 512), prefix="d", alpha=1.0 / 12.0, beta=0.0, sharded=True),
 }
+# diagnostic only (not a BASELINE configuration): the slab one of 8 ranks owns, alone on one GPU, un-sharded
+WORKLOADS["c5slab8"] = dict(name="diagnostic: 512x512x64 slab of c5's grid on one GPU", kind="mv", stencil=(7, 512, 512, 64),
+                            prefix="d", alpha=1.0 / 12.0, beta=0.0)
 ELEM = {"s": 4, "d": 8, "c": 8, "z": 16}
 L2_BYTES = 126 * 1000 * 1000
 C5_SAMPLE_PLANES = 64  # CPU arm on c5: the slab one of 8 ranks owns (1/8 of the matrix, 16.8 M rows, 117 M entries)
@@ -343,7 +346,20 @@ def device_matrix(lib, wl, row_lo=None, row_hi=None):
     return n, n, nnz, rp, col, val
 
 
-def sharded_parity(lib, wl, slab, A, d, peer_factory, iters):
+def make_shard(lib, A, d, slab, rank, world):
+    """aoclsparse_b200_shard_* object for this rank's slab, linked to its neighbours (the 320-byte link records travel
+    through torch.distributed; the library itself links no collective)"""
+    import torch.distributed as dist
+    st, S = lib.shard_create(A, d, rank, world, slab.row_lo, slab.halo)
+    assert st == 0, (st, lib.last_error())
+    links = [None] * world
+    dist.all_gather_object(links, lib.shard_export(S))
+    st = lib.shard_connect(S, links[rank - 1] if rank > 0 else None, links[rank + 1] if rank < world - 1 else None)
+    assert st == 0, (st, lib.last_error())
+    return S
+
+
+def sharded_parity(lib, wl, slab, A, d, fused_runner, iters):
     """fused multiply + halo push (one launch per iteration, flags in-kernel) against the un-fused path (plain
     aoclsparse_dmv on the windowed handle + NCCL send/recv of the halos) from the same x_0 for `iters` iterations:
     the two own slices must be bit-identical on every rank.  Returns the parity object of the JSON line."""
@@ -369,23 +385,10 @@ def sharded_parity(lib, wl, slab, A, d, peer_factory, iters):
     torch.cuda.synchronize()
     plain = bufs[cur][off: off + m]
     # fused: fresh windows and flags
-    peer = peer_factory()
-    lib.lib.aoclsparse_b200_gen_uniform(1, slab.row_lo, m, elem, C.c_void_p(peer.own_ptr(0)))
-    torch.cuda.synchronize()
-    dist.barrier()
-    peer.initial_push(0)
-    dist.barrier()
-    for k in range(1, iters + 1):
-        s = peer.iteration_fused(k, alpha, A, d)
-        assert s == 0, (s, lib.last_error())
-    torch.cuda.synchronize()
-    dist.barrier()
-    fused = torch.empty(m, dtype=torch.float64, device="cuda")
-    assert lib.memcpy(fused.data_ptr(), peer.own_ptr(iters % 2), m * elem) == 0
-    torch.cuda.synchronize()
+    fused, timed_out = fused_runner(iters)
     mism = int((fused.view(torch.int64) != plain.view(torch.int64)).sum().item())
     err = float((fused - plain).abs().max().item())
-    stats = torch.tensor([float(mism), err, float(peer.timed_out())], dtype=torch.float64, device="cuda")
+    stats = torch.tensor([float(mism), err, float(timed_out)], dtype=torch.float64, device="cuda")
     dist.all_reduce(stats, op=dist.ReduceOp.MAX)
     nrm = torch.tensor([float((fused * fused).sum().item())], dtype=torch.float64, device="cuda")
     dist.all_reduce(nrm)
@@ -412,10 +415,13 @@ def measure(args, key, primary):
     p = wl["prefix"]
     tdt = torch.float64 if p == "d" else torch.float32
     elem = ELEM[p]
-    stream = torch.cuda.current_stream()
+    # one explicit (non-default) stream for everything: the library's calls, torch's helpers and the timing events
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     lib.set_stream(stream.cuda_stream)
-    steps = args.steps if primary else min(args.steps, 50)
-    warmup = args.warmup if primary else min(args.warmup, 10)
+    # the small configurations run tens of microseconds per step: give them enough steps for a stable average
+    steps = args.steps if (primary or key == "c3") else max(args.steps, 100)
+    warmup = args.warmup if primary else max(args.warmup, 10)
 
     # ---- matrix, handle, analysis (outside the timed region; their times are reported)
     sharded = bool(wl.get("sharded"))
@@ -449,24 +455,33 @@ def measure(args, key, primary):
     del rp, col, val  # the handle owns device copies
     torch.cuda.empty_cache()
     d = lib.create_descr()
-    if sharded:
-        info0 = lib.matrix_info(A)
-        assert sharding.halo_needed(info0.min_col, info0.max_col, slab.row_lo, slab.row_hi) <= slab.halo
-        if slab.win_lo != 0 or slab.win_hi != n_glob:
-            assert lib.set_x_window(A, slab.win_lo, slab.win_hi) == 0
-        cuts = [c for c in (plane, m - plane) if 0 < c < m] if world > 1 else []
-        if cuts:
-            assert lib.set_row_cuts(A, sorted(set(cuts))) == 0
+    # halo exchange of the sharded workload: shard-c-abi (default) = the library's own C object (csrc/shard.cu): one
+    # kernel per iteration that multiplies, stores the boundary rows into the neighbours' x windows over NVLink and
+    # hands over the flags; p2p-fused = the same kernel driven from sharding.py; p2p-push = same stores, separate
+    # boundary / interior launches and flag kernels; nccl = send/recv baseline
+    halo_mode = "none" if (not sharded or world == 1) else os.environ.get("BENCH_HALO", "shard-c-abi")
+    shard = None
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    assert lib.set_mv_hint(A, 111, d, 1000) == 0 if wl["kind"] == "mv" else lib.set_mm_hint(A, 111, d, 1000) == 0
-    assert lib.optimize(A) == 0, lib.last_error()
+    if halo_mode == "shard-c-abi":
+        shard = make_shard(lib, A, d, slab, rank, world)  # window, cuts, hint, optimize + windows, flags, peer maps
+    else:
+        if sharded:
+            info0 = lib.matrix_info(A)
+            assert sharding.halo_needed(info0.min_col, info0.max_col, slab.row_lo, slab.row_hi) <= slab.halo
+            if slab.win_lo != 0 or slab.win_hi != n_glob:
+                assert lib.set_x_window(A, slab.win_lo, slab.win_hi) == 0
+            cuts = [c for c in (plane, m - plane) if 0 < c < m] if world > 1 else []
+            if cuts:
+                assert lib.set_row_cuts(A, sorted(set(cuts))) == 0
+        assert lib.set_mv_hint(A, 111, d, 1000) == 0 if wl["kind"] == "mv" else lib.set_mm_hint(A, 111, d, 1000) == 0
+        assert lib.optimize(A) == 0, lib.last_error()
     torch.cuda.synchronize()
     optimize_ms = (time.perf_counter() - t0) * 1e3
     info = lib.matrix_info(A)
 
     alpha, beta = wl["alpha"], wl["beta"]
-    halo_mode, peer, bufs, n_sets = "none", None, None, 1
+    peer, bufs, n_sets = None, None, 1
     # ---- operands resident in HBM
     if wl["kind"] == "mm":
         nr = wl["n_rhs"]
@@ -512,11 +527,11 @@ def measure(args, key, primary):
     else:
         wlen = slab.win_hi - slab.win_lo
         off = slab.own_offset
-        # halo exchange: p2p-fused (default) = one kernel per iteration that multiplies, stores the boundary rows into
-        # the neighbours' x windows over NVLink and publishes the flags; p2p-push = same stores, separate boundary /
-        # interior launches and flag kernels; nccl = send/recv baseline
-        halo_mode = "none" if world == 1 else os.environ.get("BENCH_HALO", "p2p-fused")
-        if halo_mode in ("p2p-push", "p2p-fused"):
+        if shard is not None:
+            lib.lib.aoclsparse_b200_gen_uniform(1, slab.row_lo, m, elem, C.c_void_p(lib.shard_x_ptr(shard)))
+            torch.cuda.synchronize()
+            assert lib.lib.aoclsparse_b200_shard_publish(shard) == 0, lib.last_error()
+        elif halo_mode in ("p2p-push", "p2p-fused"):
             # x windows live in ipc memory; boundary rows store into the neighbours' halos from the kernel epilogue
             peer = sharding.PeerHalo(lib, slab, elem)
             lib.lib.aoclsparse_b200_gen_uniform(1, slab.row_lo, m, elem, C.c_void_p(peer.own_ptr(0)))
@@ -529,13 +544,17 @@ def measure(args, key, primary):
             lib.lib.aoclsparse_b200_gen_uniform(1, slab.row_lo, m, elem, bufs[0][off:].data_ptr())
         comm_stream = torch.cuda.Stream()
         state = {"cur": 0, "k": 0}
-        if world > 1 and peer is None:
+        if world > 1 and peer is None and shard is None:
             for r in sharding.exchange_halo(slab, bufs[0]):
                 r.wait()
             torch.cuda.synchronize()
             dist.barrier()
 
         def step(i):
+            if shard is not None:
+                s = lib.lib.aoclsparse_b200_shard_iterate(shard, alpha, 1)
+                assert s == 0, (s, lib.last_error())
+                return
             if peer is not None:
                 state["k"] += 1
                 if halo_mode == "p2p-fused":
@@ -570,7 +589,7 @@ def measure(args, key, primary):
             dist.all_reduce(nnz_t)
         g_nnz = int(nnz_t.item())
         g_bytes, g_flops = spmv_bytes_flops(n_glob, n_glob, g_nnz, elem, beta != 0)
-        launches_per_step = 1 if (world == 1 or halo_mode == "p2p-fused") else (
+        launches_per_step = 1 if (world == 1 or halo_mode in ("p2p-fused", "shard-c-abi")) else (
             3 if peer is None else 3 + 4 * len(peer.peer) + 2 * len(peer.peer))
 
     def barrier():
@@ -625,7 +644,10 @@ def measure(args, key, primary):
         xlen = (slab.win_hi - slab.win_lo) if sharded else n_glob
         hx = torch.empty(xlen, dtype=tdt).pin_memory()
         hy = torch.zeros(m, dtype=tdt).pin_memory()
-        if sharded and bufs is None and peer is not None:
+        if shard is not None:
+            assert lib.memcpy(hx.data_ptr(), lib.shard_x_ptr(shard) - off * elem, xlen * elem) == 0
+            torch.cuda.synchronize()
+        elif sharded and bufs is None and peer is not None:
             assert lib.memcpy(hx.data_ptr(), peer.w_ptr[0], xlen * elem) == 0
             torch.cuda.synchronize()
         else:
@@ -668,8 +690,38 @@ def measure(args, key, primary):
 
     # ---- N > 1: bitwise check of the fused path against the un-fused one (both from x_0, >= 100 iterations)
     parity = None
-    if sharded and world > 1 and halo_mode == "p2p-fused":
-        parity = sharded_parity(lib, wl, slab, A, d, lambda: sharding.PeerHalo(lib, slab, elem), max(100, steps))
+    if sharded and world > 1 and halo_mode in ("p2p-fused", "shard-c-abi"):
+        def fused_runner(iters):
+            out = torch.empty(m, dtype=torch.float64, device="cuda")
+            if halo_mode == "shard-c-abi":
+                dist.barrier()  # every rank is done with the timed shard before the windows are refilled
+                lib.lib.aoclsparse_b200_gen_uniform(1, slab.row_lo, m, elem, C.c_void_p(lib.shard_x_ptr(shard)))
+                torch.cuda.synchronize()
+                dist.barrier()
+                assert lib.lib.aoclsparse_b200_shard_publish(shard) == 0
+                assert lib.lib.aoclsparse_b200_shard_iterate(shard, alpha, iters) == 0, lib.last_error()
+                st = lib.lib.aoclsparse_b200_shard_get_x(shard, C.c_void_p(out.data_ptr()))
+                return out, 0 if st == 0 else 1
+            peer2 = sharding.PeerHalo(lib, slab, elem)
+            lib.lib.aoclsparse_b200_gen_uniform(1, slab.row_lo, m, elem, C.c_void_p(peer2.own_ptr(0)))
+            torch.cuda.synchronize()
+            dist.barrier()
+            peer2.initial_push(0)
+            dist.barrier()
+            for k in range(1, iters + 1):
+                s = peer2.iteration_fused(k, alpha, A, d)
+                assert s == 0, (s, lib.last_error())
+            torch.cuda.synchronize()
+            dist.barrier()
+            assert lib.memcpy(out.data_ptr(), peer2.own_ptr(iters % 2), m * elem) == 0
+            torch.cuda.synchronize()
+            return out, peer2.timed_out()
+        parity = sharded_parity(lib, wl, slab, A, d, fused_runner, max(100, steps))
+    if shard is not None:
+        lib.lib.aoclsparse_b200_shard_synchronize(shard)
+        if world > 1:
+            dist.barrier()
+        lib.lib.aoclsparse_b200_shard_destroy(C.byref(shard))
 
     for hdl in handles:
         lib.destroy(hdl)
@@ -693,8 +745,9 @@ def measure(args, key, primary):
                        "capture of this kernel, " + str(tj.get("_captured", "round 1")) + "); not re-measured in this run")
     roof = {"bound": "hbm", "unit": "GB/s", "peak": peak, "peak_source": peak_src, "traffic": traffic,
             "traffic_source": traffic_src,
-            "kernel": ("spmv_sharded_step_kernel" if (sharded and world > 1 and halo_mode == "p2p-fused")
-                       else "spmv_row_blocks_kernel") if wl["kind"] == "mv" else "csrmm_row_major_vec_kernel",
+            "kernel": ("spmv_hot_pipeline_kernel" if info.hot_entries else
+                       ("spmv_sharded_step_kernel" if (sharded and world > 1 and halo_mode in ("p2p-fused", "shard-c-abi"))
+                        else "spmv_row_blocks_kernel")) if wl["kind"] == "mv" else "csrmm_row_major_vec_kernel",
             "algorithmic_bytes_per_launch": int(l_bytes)}
     if kern_ms:
         roof["achieved"] = round(l_bytes / (kern_ms * 1e-3) / 1e9, 1)
@@ -706,6 +759,16 @@ def measure(args, key, primary):
         roof["note"] = "per-GPU share of the step (interior + boundary CTAs of one launch overlap the halo exchange)"
     roof["frac"] = round(roof["achieved"] / peak, 4)
     roof["frac_of_nominal_8TBs"] = round(roof["achieved"] / 8000.0, 4)
+    if info.n_diag_codes > 0 and wl["kind"] == "mv":
+        # disclosure: aoclsparse_optimize built the diagonal-code copy of col_idx (1 byte per entry instead of 4, the
+        # decoded columns are bit-identical), so the kernel STREAMS fewer bytes than the reference's byte model counts;
+        # `achieved` / `frac` stay on the algorithmic bytes (they may exceed 1), `streamed_frac` is the honest
+        # utilisation of HBM
+        streamed = l_bytes - 3 * nnz
+        roof["streamed_bytes_per_launch"] = int(streamed)
+        roof["streamed_frac"] = round(streamed / (l_bytes / roof["achieved"]) / peak, 4)
+        roof["compression"] = ("diagonal-code column stream: %d distinct col-row offsets, 1 index byte per entry"
+                               % info.n_diag_codes)
 
     out = {
         "metric": METRIC,
@@ -720,7 +783,9 @@ def measure(args, key, primary):
                    ("rotating over %d independent (A,x,y) sets, %.0f MB in total vs 126 MB L2" % (n_sets, n_sets * l_bytes / 1e6)),
                    "plan": {"block_nnz": info.block_nnz, "blocks": info.n_blocks, "thread": info.n_thread_blocks,
                             "warp": info.n_warp_blocks, "product": info.n_product_blocks,
-                            "long_segments": info.n_long_segments, "long_rows": info.n_long_rows},
+                            "long_segments": info.n_long_segments, "long_rows": info.n_long_rows,
+                            "diag_code_table": info.n_diag_codes, "hot_table_entries": info.hot_entries,
+                            "hot_table_mass": info.hot_mass_ppm / 1e6},
                    "optimize_ms": round(optimize_ms, 2),
                    "create_ms": round(create_ms, 2),
                    "create_from_pageable_host_ms": None if create_host_ms is None else round(create_host_ms, 2)},

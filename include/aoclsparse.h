@@ -336,6 +336,34 @@ DLL_PUBLIC aoclsparse_status aoclsparse_set_mm_hint(aoclsparse_matrix          m
                                                     aoclsparse_int             expected_no_of_calls);
 DLL_PUBLIC aoclsparse_status aoclsparse_set_memory_hint(aoclsparse_matrix             mat,
                                                         const aoclsparse_memory_usage policy);
+/* Hints for operations next to the path (aoclsparse_analysis.h:102-161,202-206): validated and recorded like the
+ * ones above; a dotmv hint counts as a multiply hint for aoclsparse_optimize, the others only take their place in
+ * the hint list (triangular solves, smoothers and the LU / SOR preconditioners are outside this library's path). */
+DLL_PUBLIC aoclsparse_status aoclsparse_set_sv_hint(aoclsparse_matrix          mat,
+                                                    aoclsparse_operation       trans,
+                                                    const aoclsparse_mat_descr descr,
+                                                    aoclsparse_int             expected_no_of_calls);
+DLL_PUBLIC aoclsparse_status aoclsparse_set_2m_hint(aoclsparse_matrix          mat,
+                                                    aoclsparse_operation       trans,
+                                                    const aoclsparse_mat_descr descr,
+                                                    aoclsparse_int             expected_no_of_calls);
+DLL_PUBLIC aoclsparse_status aoclsparse_set_lu_smoother_hint(aoclsparse_matrix          mat,
+                                                             aoclsparse_operation       trans,
+                                                             const aoclsparse_mat_descr descr,
+                                                             aoclsparse_int             expected_no_of_calls);
+DLL_PUBLIC aoclsparse_status aoclsparse_set_sm_hint(aoclsparse_matrix          mat,
+                                                    aoclsparse_operation       trans,
+                                                    const aoclsparse_mat_descr descr,
+                                                    const aoclsparse_order     order,
+                                                    const aoclsparse_int       expected_no_of_calls);
+DLL_PUBLIC aoclsparse_status aoclsparse_set_dotmv_hint(aoclsparse_matrix          mat,
+                                                       aoclsparse_operation       trans,
+                                                       const aoclsparse_mat_descr descr,
+                                                       aoclsparse_int             expected_no_of_calls);
+DLL_PUBLIC aoclsparse_status aoclsparse_set_symgs_hint(aoclsparse_matrix          mat,
+                                                       aoclsparse_operation       trans,
+                                                       const aoclsparse_mat_descr descr,
+                                                       aoclsparse_int             expected_no_of_calls);
 
 /* ------------------------------------------------------------------------------------------
  * Sparse matrix - vector product  y = alpha * op(A) * x + beta * y.
@@ -635,6 +663,8 @@ DLL_PUBLIC aoclsparse_status aoclsparse_itsol_d_init(aoclsparse_itsol_handle *ha
 DLL_PUBLIC aoclsparse_status aoclsparse_itsol_c_init(aoclsparse_itsol_handle *handle);
 DLL_PUBLIC aoclsparse_status aoclsparse_itsol_z_init(aoclsparse_itsol_handle *handle);
 DLL_PUBLIC void              aoclsparse_itsol_destroy(aoclsparse_itsol_handle *handle);
+/* aoclsparse_solvers.h:147 -- prints the handle's options and their values to the standard output */
+DLL_PUBLIC void              aoclsparse_itsol_handle_prn_options(aoclsparse_itsol_handle handle);
 DLL_PUBLIC aoclsparse_status aoclsparse_itsol_option_set(aoclsparse_itsol_handle handle,
                                                          const char             *option,
                                                          const char             *value);

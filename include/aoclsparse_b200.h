@@ -52,9 +52,19 @@ typedef struct aoclsparse_b200_matrix_info_
     aoclsparse_int n_long_rows;     /* rows split across CTAs                                   */
     aoclsparse_int n_diag_codes;    /* diagonal-code copy of col_idx (one byte per entry indexing a table of the
                                        distinct col - row offsets): table entries, 0 = not built / not applicable */
-    aoclsparse_int sorted_blocks;   /* product blocks whose entries are also stored sorted by column (gather
-                                       locality for skewed matrices), 0 = not built                              */
+    aoclsparse_int hot_entries;     /* hot-column table for power-law matrices (csrc/hot.cu): entries of x the persistent
+                                       kernel keeps in shared memory, 0 = not built                              */
+    aoclsparse_int hot_mass_ppm;    /* stored entries whose column is in that table, parts per million            */
 } aoclsparse_b200_matrix_info;
+
+/* Diagonal-code copy of the stored column indices, built by aoclsparse_optimize for banded / stencil matrices (every
+ * row block thread-per-row, at most 256 distinct col - row offsets): offsets[0..*n_codes) ascending, codes[p] = index of
+ * (col_idx[p] - row of p) in that table.  *n_codes = 0 when it was not built.  offsets / codes may be NULL.  Integer
+ * metadata with no counterpart in the reference: pinned bit for bit by oracle/csr_oracle.c::oracle_diag_codes. */
+DLL_PUBLIC aoclsparse_status aoclsparse_b200_get_diag_codes(const aoclsparse_matrix A,
+                                                            aoclsparse_int         *n_codes,
+                                                            aoclsparse_int         *offsets,
+                                                            unsigned char          *codes);
 
 /* value type of a handle (aoclsparse_matrix_data_type), -1 for NULL */
 DLL_PUBLIC int aoclsparse_b200_value_type(const aoclsparse_matrix A);
@@ -195,6 +205,60 @@ DLL_PUBLIC aoclsparse_status aoclsparse_b200_ipc_close(void *dptr);
 /* cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault) on the calling thread's stream (local or ipc-mapped memory) */
 DLL_PUBLIC aoclsparse_status aoclsparse_b200_memcpy(void *dst, const void *src, size_t bytes);
 DLL_PUBLIC aoclsparse_status aoclsparse_b200_ipc_free(void *dptr);
+
+/* ---- the row-sharded iteration as one object (csrc/shard.cu) -------------------------------------------------------
+ * x <- alpha * A * x, iterated, A split by rows over `world` GPUs of one node, for banded matrices (every stored column
+ * within `halo` of its row, e.g. one grid plane of a stencil).  The reference has no multi-device interface (SURVEY.md
+ * section 2a); this is the small C extension section 8(e) asks for: create-sharded, iterate-k, gather.
+ *
+ * Each rank -- a process with its own GPU, or a device driven by the same process -- creates an ordinary handle for
+ * its rows [row_lo, row_lo + m) of the n x n matrix (aoclsparse_create_dcsr with m x n and GLOBAL column indices, on
+ * the device that is current), then:
+ *     aoclsparse_b200_shard_create   sets the x window and row cuts, hints + optimizes the handle, allocates the two
+ *                                    x windows and the flag block
+ *     aoclsparse_b200_shard_export   fills a 256-byte link record; ranks exchange these by whatever transport they have
+ *                                    (MPI_Allgather, torch.distributed, a file): no collective library is linked here
+ *     aoclsparse_b200_shard_connect  maps the two neighbours' windows and flags (cudaIpc for other processes, peer
+ *                                    access inside one process)
+ *     aoclsparse_b200_shard_set_x    own slice of x_0 from a host or device array (or _x_ptr to fill it in place)
+ *     aoclsparse_b200_shard_publish  boundary planes of x_0 into the neighbours' halos (stream-ordered, flagged)
+ *     aoclsparse_b200_shard_iterate  k iterations, each ONE kernel launch that multiplies, stores the boundary rows into
+ *                                    the neighbours' halos over NVLink and hands over the flags (no collective, no
+ *                                    host synchronisation; asynchronous on the calling thread's stream, or the shard's
+ *                                    own stream when none was set with aoclsparse_b200_set_stream)
+ *     aoclsparse_b200_shard_get_x    own slice of the current iterate to a host or device array (synchronises;
+ *                                    internal_error if a neighbour never showed up and a flag wait gave up)
+ * Ranks need no barrier between these calls; they only must all have finished iterating (get_x / synchronize on every
+ * rank) before any of them calls set_x again.  A host thread that drives several shards itself must interleave
+ * iterate calls of at most a few dozen iterations per shard (a device queue holds a bounded number of launches, and a
+ * launch of one shard waits in-kernel for the previous iteration of its neighbours).
+ * double only; world = 1 degenerates to plain aoclsparse_dmv ping-pong. */
+DLL_PUBLIC aoclsparse_status aoclsparse_b200_device_count(int *count);
+/* cudaSetDevice for callers that do not link the CUDA runtime: handles are created on the device that is current */
+DLL_PUBLIC aoclsparse_status aoclsparse_b200_set_device(int device);
+typedef struct _aoclsparse_b200_shard *aoclsparse_b200_shard;
+#define AOCLSPARSE_B200_SHARD_LINK_BYTES 320
+DLL_PUBLIC aoclsparse_status aoclsparse_b200_shard_create(aoclsparse_b200_shard     *shard,
+                                                          aoclsparse_matrix          A,
+                                                          const aoclsparse_mat_descr descr,
+                                                          int                        rank,
+                                                          int                        world,
+                                                          aoclsparse_int             row_lo,
+                                                          aoclsparse_int             halo);
+DLL_PUBLIC aoclsparse_status aoclsparse_b200_shard_export(aoclsparse_b200_shard shard,
+                                                          unsigned char         link[AOCLSPARSE_B200_SHARD_LINK_BYTES]);
+DLL_PUBLIC aoclsparse_status aoclsparse_b200_shard_connect(aoclsparse_b200_shard shard,
+                                                           const unsigned char  *left_link,
+                                                           const unsigned char  *right_link);
+DLL_PUBLIC aoclsparse_status aoclsparse_b200_shard_set_x(aoclsparse_b200_shard shard, const double *x_own);
+/* device address of the own slice of the current iterate (m doubles), to be filled / read in place */
+DLL_PUBLIC aoclsparse_status aoclsparse_b200_shard_x_ptr(aoclsparse_b200_shard shard, double **own);
+DLL_PUBLIC aoclsparse_status aoclsparse_b200_shard_publish(aoclsparse_b200_shard shard);
+DLL_PUBLIC aoclsparse_status aoclsparse_b200_shard_iterate(aoclsparse_b200_shard shard, double alpha, int iterations);
+DLL_PUBLIC aoclsparse_status aoclsparse_b200_shard_get_x(aoclsparse_b200_shard shard, double *dst);
+DLL_PUBLIC aoclsparse_status aoclsparse_b200_shard_synchronize(aoclsparse_b200_shard shard);
+/* frees the windows and flags; the matrix handle stays the caller's */
+DLL_PUBLIC aoclsparse_status aoclsparse_b200_shard_destroy(aoclsparse_b200_shard *shard);
 
 /* ---- synthetic matrices of BASELINE.json, generated directly in device memory --------------- */
 

@@ -376,9 +376,10 @@ int oracle_plan(int m, const int *rp, int T, int R, int forced, int n_cuts, cons
 }
 
 /* plan_parameters + wave-aware block size of plan.cu (same arithmetic, same candidate order) */
-static long long ctas_per_wave(int elem_size, int T)
+static long long ctas_per_wave(int elem_size, int T, int coded)
 {
-    const long long smem = 16 + (long long)(T + 8) * (long long)(elem_size + 4) + 1024;
+    const long long smem = coded ? 16 + (long long)(T + 32) * (long long)(elem_size + 1) + 1024 + 1024
+                                 : 16 + (long long)(T + 8) * (long long)(elem_size + 4) + 1024;
     long long       c    = 232448 / smem;
     if(c > 8)
         c = 8;
@@ -387,10 +388,13 @@ static long long ctas_per_wave(int elem_size, int T)
     return 148 * c;
 }
 
+/* coded != 0: the plan serves the diagonal-code copy (elem_size + 1 staged bytes per entry) */
 void oracle_plan_parameters(int elem_size, int m, int nnz, int max_row_nnz, const int *rp, int n_cuts, const int *cuts,
-                            int *T, int *R)
+                            int coded, int *T, int *R)
 {
     int             t    = (24576 / (elem_size + 4)) / 512 * 512;
+    if(coded)
+        t = (24576 / (elem_size + 1) - 32) / 256 * 256;
     if(elem_size >= 16)
         t = 1536; /* 16-byte values: measured best, with 128-thread CTAs */
     const long long mean = m > 0 ? (long long)nnz / m : 0;
@@ -401,8 +405,8 @@ void oracle_plan_parameters(int elem_size, int m, int nnz, int max_row_nnz, cons
     while(t > 512 && (long long)nnz < (long long)t * 148 * 8)
         t -= 512;
     *R = 1024;
-    if(m > 0 && rp && (long long)nnz < 8 * ctas_per_wave(elem_size, t) * (long long)t
-       && (long long)nnz >= ctas_per_wave(elem_size, t) * (long long)t)
+    if(m > 0 && rp && (long long)nnz < 8 * ctas_per_wave(elem_size, t, coded) * (long long)t
+       && (long long)nnz >= ctas_per_wave(elem_size, t, coded) * (long long)t)
     {
         long long best_cost = -1;
         int       best_t    = t;
@@ -411,7 +415,7 @@ void oracle_plan_parameters(int elem_size, int m, int nnz, int max_row_nnz, cons
             const int       tk = t + 32 * k;
             int             a, b;
             const long long nb   = oracle_plan(m, rp, tk, *R, -1, n_cuts, cuts, 0, 0, 0, &a, &b);
-            const long long wave = ctas_per_wave(elem_size, tk);
+            const long long wave = ctas_per_wave(elem_size, tk, coded);
             const long long cost = (((nb * 203 + 199) / 200 + wave - 1) / wave) * (long long)tk;
             if(best_cost < 0 || cost < best_cost)
             {
@@ -425,6 +429,51 @@ void oracle_plan_parameters(int elem_size, int m, int nnz, int max_row_nnz, cons
 }
 
 /* ---- multiply kernels, instantiated for the four value types ---- */
+/* Diagonal-code copy built by aoclsparse_optimize (aocl-sparse_b200/csrc/plan.cu, build_diag_codes): GPU-only
+ * integer metadata with no counterpart in the reference, so the written SPEC is restated here:
+ *   D = ascending distinct values of col[p] - r over all stored entries (0-based arrays); if 1 <= |D| <= 256,
+ *   codes[p] = index of (col[p] - r) in D; otherwise not applicable (returns 0).
+ * Returns |D| (0: not applicable); offsets[256] and codes[nnz] are written when it is not 0. */
+static int cmp_int(const void *a, const void *b)
+{
+    const int x = *(const int *)a, y = *(const int *)b;
+    return (x > y) - (x < y);
+}
+int oracle_diag_codes(int m, const int *rp, const int *col, int *offsets, unsigned char *codes)
+{
+    int d[257];
+    int nd = 0;
+    for(int r = 0; r < m; ++r)
+        for(int p = rp[r]; p < rp[r + 1]; ++p)
+        {
+            const int off = col[p] - r;
+            int       k   = 0;
+            while(k < nd && d[k] != off)
+                ++k;
+            if(k == nd)
+            {
+                if(nd == 256)
+                    return 0;
+                d[nd++] = off;
+            }
+        }
+    if(nd == 0)
+        return 0;
+    qsort(d, (size_t)nd, sizeof(int), cmp_int);
+    for(int i = 0; i < nd; ++i)
+        offsets[i] = d[i];
+    for(int r = 0; r < m; ++r)
+        for(int p = rp[r]; p < rp[r + 1]; ++p)
+        {
+            const int off = col[p] - r;
+            int       k   = 0;
+            while(d[k] != off)
+                ++k;
+            codes[p] = (unsigned char)k;
+        }
+    return nd;
+}
+
 /* Row pointers of C = A B for two CSR operands in the orientation of the product: the number of distinct column
  * indices reached from every row of A (aoclsparse_csr2m_nnz_count, library/src/level3/aoclsparse_csr2m.cpp:46-305),
  * then a 64-bit prefix sum.  Returns 0, or 3 (invalid size) when the total does not fit a 32-bit int (:236-241). */

@@ -49,7 +49,7 @@ class Oracle:
         self.lib.oracle_doid.argtypes = [ci, ci, ci, ci]
         self.lib.oracle_csr2m_count.argtypes = [ci, ci, ci, vp, vp, ci, vp, vp, vp]
         self.lib.oracle_plan.argtypes = [ci, vp, ci, ci, ci, ci, vp, ci, vp, vp, C.POINTER(ci), C.POINTER(ci)]
-        self.lib.oracle_plan_parameters.argtypes = [ci, ci, ci, ci, vp, ci, vp, C.POINTER(ci), C.POINTER(ci)]
+        self.lib.oracle_plan_parameters.argtypes = [ci, ci, ci, ci, vp, ci, vp, ci, C.POINTER(ci), C.POINTER(ci)]
         for suf, ct in (("s", C.c_float), ("d", C.c_double), ("c", FC), ("z", DC)):
             getattr(self.lib, f"oracle_csrmv_{suf}").argtypes = [ci, ct, ci, ci, ci, vp, vp, vp, ci, ci, ci, vp, ct, vp]
             getattr(self.lib, f"oracle_csrmm_{suf}").argtypes = [ci, ct, ci, ci, ci, vp, vp, vp, ci, ci, ci, ci, vp, ci,
@@ -88,7 +88,7 @@ class Oracle:
     def doid(self, is_complex, mtype, fill, op):
         return self.lib.oracle_doid(int(is_complex), mtype, fill, op)
 
-    def plan_parameters(self, elem_size, rp0, cuts=()):
+    def plan_parameters(self, elem_size, rp0, cuts=(), coded=False):
         """block nnz / row capacity the analysis picks for a 0-based row_ptr (incl. the wave-aware search)"""
         rp0 = np.ascontiguousarray(rp0, dtype=np.int32)
         cuts = np.ascontiguousarray(cuts, dtype=np.int32)
@@ -97,8 +97,20 @@ class Oracle:
         mx = int(np.max(np.diff(rp0))) if m > 0 else 0
         t, r = C.c_int(0), C.c_int(0)
         self.lib.oracle_plan_parameters(elem_size, m, nnz, mx, rp0.ctypes.data, len(cuts), cuts.ctypes.data,
-                                        C.byref(t), C.byref(r))
+                                        1 if coded else 0, C.byref(t), C.byref(r))
         return t.value, r.value
+
+    def diag_codes(self, rp0, col0):
+        """(offsets, codes) of the diagonal-code copy of a 0-based CSR pattern, or (None, None) if not applicable"""
+        rp0 = np.ascontiguousarray(rp0, dtype=np.int32)
+        col0 = np.ascontiguousarray(col0, dtype=np.int32)
+        offs = np.zeros(256, np.int32)
+        codes = np.zeros(max(len(col0), 1), np.uint8)
+        self.lib.oracle_diag_codes.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        n = self.lib.oracle_diag_codes(len(rp0) - 1, rp0.ctypes.data, col0.ctypes.data, offs.ctypes.data, codes.ctypes.data)
+        if n == 0:
+            return None, None
+        return offs[:n], codes[: len(col0)]
 
     def plan(self, rp0, T, R, forced=-1, cuts=()):
         """rp0: 0-based row_ptr.  Returns (desc[nb,4], kind[nb], n_long_rows, n_long_segments)"""

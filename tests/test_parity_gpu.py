@@ -734,7 +734,11 @@ def test_plan_bit_exact(lib, oracle):
                 assert lib.set_mv_hint(h, 111, d, 1) == 0
             assert lib.optimize(h) == 0, lib.last_error()
             info = lib.matrix_info(h)
-            T, R = oracle.plan_parameters(8, rp, cuts)
+            # stencils get the diagonal-code copy and the block size that goes with it (not when a strategy is forced
+            # to something other than thread-per-row, nor for irregular matrices)
+            ooffs, _ = oracle.diag_codes(rp, col)
+            assert (info.n_diag_codes > 0) == (ooffs is not None and idx in (0, 1, 5) and forced < 0), (idx, forced)
+            T, R = oracle.plan_parameters(8, rp, cuts, coded=info.n_diag_codes > 0)
             assert (info.block_nnz, info.block_rows) == (T, R)
             desc, kind = lib.get_plan(h)
             odesc, okind, nlr, nls = oracle.plan(rp, T, R, forced, cuts)
@@ -747,6 +751,125 @@ def test_plan_bit_exact(lib, oracle):
             assert info.min_col == int(col.min()) and info.max_col == int(col.max())
             lib.destroy(h)
             lib.destroy_descr(d)
+
+
+def test_diag_codes_bit_exact_and_products(lib, oracle):
+    """the diagonal-code copy aoclsparse_optimize builds for banded / stencil matrices: table and codes bit-exact
+    against the CPU restatement of the spec (oracle_diag_codes); products through the coded kernel identical, bit for
+    bit, to the ones through the 32-bit column stream (AOCLSPARSE_B200_DIAG_CODES=0), for all four value types, with
+    an x window + row cuts, through mv_rows and with host vectors; not built for irregular matrices, under the
+    minimal-memory policy, or without a hint"""
+    import torch
+    rng = np.random.default_rng(11)
+    cases = [gen_np.stencil(27, 20, 19, 18), gen_np.stencil(7, 40, 40, 40), gen_np.stencil(5, 300, 300)]
+    # banded with 300 distinct offsets (> 256: not applicable) and one with exactly 256
+    for nd in (300, 256):
+        m = 4000
+        offs = np.sort(rng.choice(np.arange(-1500, 1500), size=nd, replace=False))
+        rows, cols = [], []
+        for k, o in enumerate(offs):
+            r = np.arange(m)[k % 7::7][:64] if k >= 6 else np.arange(m)   # six full diagonals + scattered short ones
+            c = r + o
+            ok = (c >= 0) & (c < m)
+            rows.append(r[ok]); cols.append(c[ok])
+        rows, cols = np.concatenate(rows), np.concatenate(cols)
+        order = np.lexsort((cols, rows))
+        rows, cols = rows[order], cols[order]
+        rp = np.searchsorted(rows, np.arange(m + 1)).astype(np.int32)
+        cases.append((rp, cols.astype(np.int32), rng.normal(size=len(cols))))
+    for idx, (rp, col, val) in enumerate(cases):
+        m = len(rp) - 1
+        for p in ("d", "s", "z", "c"):
+            dt = DT[p]
+            v = val.astype(dt)
+            if p in "cz":
+                v = (v + 1j * rng.normal(size=len(v))).astype(dt)
+            x = rng.normal(size=m).astype(dt)
+            y0 = rng.normal(size=m).astype(dt)
+            outs = {}
+            for mode in ("coded", "plain"):
+                if mode == "plain":
+                    os.environ["AOCLSPARSE_B200_DIAG_CODES"] = "0"
+                try:
+                    st, h = lib.create_csr(p, 0, m, m, len(col), rp, col, v)
+                    assert st == 0
+                    d = lib.create_descr()
+                    assert lib.set_mv_hint(h, 111, d, 10) == 0 and lib.optimize(h) == 0, lib.last_error()
+                finally:
+                    os.environ.pop("AOCLSPARSE_B200_DIAG_CODES", None)
+                info = lib.matrix_info(h)
+                offs, codes = lib.get_diag_codes(h, len(col))
+                if mode == "coded":
+                    ooffs, ocodes = oracle.diag_codes(rp, col)
+                    if info.n_thread_blocks == info.n_blocks and ooffs is not None:
+                        assert info.n_diag_codes == len(ooffs), (idx, info.n_diag_codes)
+                        assert np.array_equal(offs, ooffs) and np.array_equal(codes, ocodes), idx
+                        rows_of = np.repeat(np.arange(m), np.diff(rp))
+                        assert np.array_equal(rows_of + offs[codes], col)  # decodes to the identical column
+                    else:
+                        assert info.n_diag_codes == 0 and offs is None, idx
+                else:
+                    assert info.n_diag_codes == 0
+                y = y0.copy()
+                assert lib.mv(p, 111, 1.5, h, d, x, -0.5, y) == 0, lib.last_error()
+                dx, dy = torch.from_numpy(x).cuda(), torch.full((m,), float("nan"), dtype=torch.from_numpy(y0).dtype, device="cuda")
+                assert lib.mv(p, 111, 1.0, h, d, dx.data_ptr(), 0.0, dy.data_ptr()) == 0
+                torch.cuda.synchronize()
+                outs[mode] = (y, dy.cpu().numpy())
+                lib.destroy(h)
+                lib.destroy_descr(d)
+            assert np.array_equal(outs["coded"][0], outs["plain"][0]), (idx, p)
+            assert np.array_equal(outs["coded"][1], outs["plain"][1]), (idx, p)
+    # irregular rows (product / warp / split blocks): never coded; minimal memory policy / no hint: not built
+    rp, col, val = _skewed(rng, 5000, 4)
+    st, h = lib.create_csr("d", 0, 5000, 5000, len(col), rp, col, val)
+    d = lib.create_descr()
+    assert lib.set_mv_hint(h, 111, d, 10) == 0 and lib.optimize(h) == 0
+    assert lib.matrix_info(h).n_diag_codes == 0
+    lib.destroy(h)
+    rp, col, val = gen_np.stencil(7, 30, 30, 30)
+    m = len(rp) - 1
+    st, h = lib.create_csr("d", 0, m, m, len(col), rp, col, val)
+    assert lib.optimize(h) == 0 and lib.matrix_info(h).n_diag_codes == 0          # no hint: plan only
+    assert lib.set_memory_hint(h, 0) == 0 and lib.set_mv_hint(h, 111, d, 10) == 0 and lib.optimize(h) == 0
+    assert lib.matrix_info(h).n_diag_codes == 0                                    # minimal memory: no extra copy
+    assert lib.set_memory_hint(h, 1) == 0 and lib.optimize(h) == 0
+    assert lib.matrix_info(h).n_diag_codes == 7
+    # a windowed slab with row cuts (the sharded iteration's handle) and mv_rows
+    lib.destroy(h)
+    nx, ny, nz = 24, 20, 30
+    plane, total = nx * ny, nx * ny * nz
+    lo, hi = 8 * plane, 19 * plane
+    rp, col, val = gen_np.stencil(7, nx, ny, nz, lo, hi)
+    ms = hi - lo
+    xg = gen_np.uniform(1, 0, total)
+    res = []
+    for mode in ("coded", "plain"):
+        if mode == "plain":
+            os.environ["AOCLSPARSE_B200_DIAG_CODES"] = "0"
+        try:
+            st, h = lib.create_csr("d", 0, ms, total, len(col), rp, col, val)
+            assert st == 0
+            assert lib.set_x_window(h, lo - plane, hi + plane) == 0 and lib.set_row_cuts(h, [plane, ms - plane]) == 0
+            assert lib.set_mv_hint(h, 111, d, 10) == 0 and lib.optimize(h) == 0
+        finally:
+            os.environ.pop("AOCLSPARSE_B200_DIAG_CODES", None)
+        assert lib.matrix_info(h).n_diag_codes == (7 if mode == "coded" else 0)
+        xw = torch.from_numpy(xg[lo - plane: hi + plane].copy()).cuda()
+        yw = torch.zeros(ms, dtype=torch.float64, device="cuda")
+        assert lib.mv("d", 111, 0.25, h, d, xw.data_ptr(), 0.0, yw.data_ptr()) == 0
+        yr = torch.zeros(ms, dtype=torch.float64, device="cuda")
+        for r0, r1 in ((0, plane), (ms - plane, ms), (plane, ms - plane)):
+            assert lib.mv_rows("d", 0.25, h, d, xw.data_ptr(), 0.0, yr.data_ptr(), r0, r1) == 0
+        torch.cuda.synchronize()
+        assert torch.equal(yw, yr)
+        res.append(yw.cpu().numpy())
+        lib.destroy(h)
+    assert np.array_equal(res[0], res[1])
+    yo = np.zeros(ms)
+    oracle.csrmv(111, 0.25, ms, total, 0, rp, col, val, 0, 0, 0, xg, 0.0, yo)
+    assert np.max(np.abs(res[0] - yo) / (0.25 * oracle_py.row_scale(rp, col, val, xg))) <= 1e-12
+    lib.destroy_descr(d)
 
 
 @pytest.mark.parametrize("p", ["s", "d", "c", "z"])
@@ -866,6 +989,62 @@ def test_config3_rmat_float(lib, oracle):
     oracle.csrmv(111, 1.0, m, m, 0, rp, col, val.astype(np.float64), 0, 0, 0, x.astype(np.float64), 0.0, y64)
     assert np.max(np.abs(y - y64) / np.where(den > 0, den, 1)) <= 1e-5
     assert info.n_long_rows > 0 and info.n_product_blocks > 0  # hub rows are split, skewed blocks use product
+
+
+@pytest.mark.parametrize("p", ["s", "d"])
+def test_hot_table_pipeline_kernel(lib, p):
+    """power-law matrix large enough for the hot-column table (R-MAT scale 19, ~8 M entries): aoclsparse_optimize builds
+    the table, aoclsparse_?mv runs the persistent warp-specialised kernel (hot.cu); result against an fp64 accumulation
+    and against the row-block kernel (AOCLSPARSE_B200_HOT=0) to the parity tolerance, beta != 0, reproducible run to run"""
+    import torch
+
+    import bench
+    wl = dict(bench.WORKLOADS["c3"], rmat=19)
+    m, n, nnz, rp_t, col_t, val_t = bench.device_matrix(lib, wl)
+    tdt = torch.float32 if p == "s" else torch.float64
+    val_t = val_t.to(tdt)
+    x_t = torch.empty(n, dtype=tdt, device="cuda")
+    lib.lib.aoclsparse_b200_gen_uniform(1, 0, n, x_t.element_size(), x_t.data_ptr())
+    y0_t = torch.empty(m, dtype=tdt, device="cuda")
+    lib.lib.aoclsparse_b200_gen_uniform(2, 0, m, y0_t.element_size(), y0_t.data_ptr())
+    rows = torch.repeat_interleave(torch.arange(m, device="cuda"), (rp_t[1:] - rp_t[:-1]).long())
+    prods = val_t.double() * x_t.double()[col_t.long()]
+    y64 = torch.zeros(m, dtype=torch.float64, device="cuda").index_add_(0, rows, prods)
+    den = torch.zeros(m, dtype=torch.float64, device="cuda").index_add_(0, rows, prods.abs())
+    tol = 1e-5 if p == "s" else 1e-12
+    outs = {}
+    for mode in ("hot", "plain"):
+        if mode == "plain":
+            os.environ["AOCLSPARSE_B200_HOT"] = "0"
+        try:
+            st, h = lib.create_csr(p, 0, m, n, nnz, rp_t.data_ptr(), col_t.data_ptr(), val_t.data_ptr())
+            assert st == 0, lib.last_error()
+            d = lib.create_descr()
+            assert lib.set_mv_hint(h, 111, d, 100) == 0 and lib.optimize(h) == 0, lib.last_error()
+        finally:
+            os.environ.pop("AOCLSPARSE_B200_HOT", None)
+        info = lib.matrix_info(h)
+        if mode == "hot":
+            assert info.hot_entries >= 8192 and info.hot_mass_ppm > 200000, (info.hot_entries, info.hot_mass_ppm)
+            assert info.n_long_rows > 0
+        else:
+            assert info.hot_entries == 0
+        y = torch.full((m,), float("nan"), dtype=tdt, device="cuda")
+        assert lib.mv(p, 111, 1.0, h, d, x_t.data_ptr(), 0.0, y.data_ptr()) == 0, lib.last_error()
+        y2 = y0_t.clone()
+        assert lib.mv(p, 111, -0.5, h, d, x_t.data_ptr(), 2.0, y2.data_ptr()) == 0, lib.last_error()
+        y3 = torch.empty_like(y)
+        assert lib.mv(p, 111, 1.0, h, d, x_t.data_ptr(), 0.0, y3.data_ptr()) == 0
+        torch.cuda.synchronize()
+        assert torch.equal(y, y3), mode  # fixed summation order
+        safe = torch.where(den > 0, den, torch.ones_like(den))
+        assert float(torch.max((y.double() - y64).abs() / safe)) <= tol, mode
+        want2 = -0.5 * y64 + 2.0 * y0_t.double()
+        assert float(torch.max((y2.double() - want2).abs() / (0.5 * den + 2.0 * y0_t.double().abs()))) <= tol, mode
+        outs[mode] = y
+        lib.destroy(h)
+        lib.destroy_descr(d)
+    assert float(torch.max((outs["hot"].double() - outs["plain"].double()).abs() / torch.where(den > 0, den, torch.ones_like(den)))) <= tol
 
 
 def test_config5_iterated_1_10_100(lib):
