@@ -50,8 +50,7 @@ class MatrixInfo(C.Structure):
                 ("block_nnz", C.c_int32), ("block_rows", C.c_int32), ("n_blocks", C.c_int32),
                 ("n_thread_blocks", C.c_int32), ("n_warp_blocks", C.c_int32),
                 ("n_product_blocks", C.c_int32), ("n_long_segments", C.c_int32),
-                ("n_long_rows", C.c_int32), ("n_diag_codes", C.c_int32), ("hot_entries", C.c_int32),
-                ("hot_mass_ppm", C.c_int32)]
+                ("n_long_rows", C.c_int32), ("n_diag_codes", C.c_int32)]
 
 
 class HaloCtl(C.Structure):

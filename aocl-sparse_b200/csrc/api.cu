@@ -639,31 +639,6 @@ aoclsparse_status aoclsparse_optimize(aoclsparse_matrix A)
     else if(!M.plan.valid || forced >= 0)
         B200_TRY(build_plan(M, value_size(A->val_type), A->max_row_nnz, forced, A->row_cuts, st));
 
-    // power-law matrices with a plain general mv hint: hot-column table + the persistent kernel that uses it (hot.cu),
-    // on a plan with the larger blocks that kernel stages
-    {
-        bool gn_mv_hint = false;
-        for(const hint &h : A->hints)
-            gn_mv_hint = gn_mv_hint || ((h.act == 1 || h.act == 8) && h.doid == DOID_GN);
-        const long long mean   = A->m > 0 ? (long long)A->nnz / A->m : 0;
-        const bool      skewed = (long long)A->max_row_nnz > 16 * (mean > 1 ? mean : 1);
-        const char     *e      = getenv("AOCLSPARSE_B200_HOT"); // A/B knob
-        const bool      want   = e ? atoi(e) != 0 : true;
-        const bool      real   = A->val_type == aoclsparse_smat || A->val_type == aoclsparse_dmat;
-        if(want && real && gn_mv_hint && !A->is_csc && skewed && forced < 0 && A->mem_policy == aoclsparse_memory_usage_unrestricted
-           && A->win_hi < 0 && A->row_cuts.empty() && M.plan.hot_entries == 0 && M.plan.hot_state == 0 && A->nnz >= (1 << 22))
-        {
-            const size_t         es    = value_size(A->val_type);
-            const aoclsparse_int hot_T = getenv("AOCLSPARSE_B200_BLOCK_NNZ") ? 0 : (aoclsparse_int)((24576 / (es + 4)) / 512 * 512);
-            const aoclsparse_int old_T = M.plan.block_nnz;
-            B200_TRY(build_plan(M, es, A->max_row_nnz, -1, A->row_cuts, st, hot_T));
-            B200_TRY(build_hot_table(M, es, st));
-            if(M.plan.hot_entries == 0 && M.plan.block_nnz != old_T) // flat column distribution: back to the default plan
-                B200_TRY(build_plan(M, es, A->max_row_nnz, -1, A->row_cuts, st));
-            M.plan.hot_state = 1;
-        }
-    }
-
     // transposed device copies for general transposed mv / mm hints (memory policy permitting):
     // they turn the atomic scatter into a streaming gather
     if(A->mem_policy == aoclsparse_memory_usage_unrestricted && A->win_hi < 0)
@@ -735,8 +710,6 @@ aoclsparse_status aoclsparse_b200_get_matrix_info(const aoclsparse_matrix A, aoc
         info->n_long_segments  = P.n_long_segments;
         info->n_long_rows      = P.n_long_rows;
         info->n_diag_codes     = P.n_codes;
-        info->hot_entries      = P.hot_entries;
-        info->hot_mass_ppm     = (aoclsparse_int)(P.hot_mass * 1e6);
     }
     return aoclsparse_status_success;
 }

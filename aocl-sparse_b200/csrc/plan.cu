@@ -54,12 +54,17 @@ namespace b200
         // L1 misses (profiles/r01_microbench_gather.txt: 0.9 sectors/clk/SM on a miss, 2.7 on a hit), so leave
         // more of the 228 KB to L1: ~16 KB staged per CTA (profiles/r01_sweep_c3.txt: 1.09 ms vs 2.03 ms on R-MAT)
         const long long mean = m > 0 ? (long long)nnz / m : 0;
+        // Measured on R-MAT scale 24 (profiles/r02_c3_l1_lines.txt): every gather that misses L1 holds an L1 line until its
+        // sector arrives, so the gathers an SM keeps in flight -- hence its gather rate -- scale with the L1 that the
+        // shared-memory carve-out leaves.  8 CTAs of <= 7 KB (+1 KB the system reserves each) fit the 64 KB carve-out
+        // and leave 192 KB of L1: 768 entries for 4-byte values, 512 for 8-byte ones (1.011 ms against 1.092 ms with
+        // 16 KB per CTA and 2.03 ms with 24 KB).
         if((long long)max_row_nnz > 16 * (mean > 1 ? mean : 1))
-            T = (aoclsparse_int)((16384 / (elem_size + 4)) / 512 * 512);
+            T = (aoclsparse_int)(((7152 / (elem_size + 4)) - 8) / 128 * 128);
         if(T < 512)
             T = 512;
         // small matrices: keep at least ~8 CTAs per SM in the grid
-        while(T > 512 && (long long)nnz < (long long)T * 148 * 8)
+        while(T >= 1024 && (long long)nnz < (long long)T * 148 * 8)
             T -= 512;
         // tuning knob for experiments (never set in tests / bench defaults)
         if(const char *e = getenv("AOCLSPARSE_B200_BLOCK_NNZ"))

@@ -745,9 +745,8 @@ def measure(args, key, primary):
                        "capture of this kernel, " + str(tj.get("_captured", "round 1")) + "); not re-measured in this run")
     roof = {"bound": "hbm", "unit": "GB/s", "peak": peak, "peak_source": peak_src, "traffic": traffic,
             "traffic_source": traffic_src,
-            "kernel": ("spmv_hot_pipeline_kernel" if info.hot_entries else
-                       ("spmv_sharded_step_kernel" if (sharded and world > 1 and halo_mode in ("p2p-fused", "shard-c-abi"))
-                        else "spmv_row_blocks_kernel")) if wl["kind"] == "mv" else "csrmm_row_major_vec_kernel",
+            "kernel": ("spmv_sharded_step_kernel" if (sharded and world > 1 and halo_mode in ("p2p-fused", "shard-c-abi"))
+                       else "spmv_row_blocks_kernel") if wl["kind"] == "mv" else "csrmm_row_major_vec_kernel",
             "algorithmic_bytes_per_launch": int(l_bytes)}
     if kern_ms:
         roof["achieved"] = round(l_bytes / (kern_ms * 1e-3) / 1e9, 1)
@@ -784,8 +783,7 @@ def measure(args, key, primary):
                    "plan": {"block_nnz": info.block_nnz, "blocks": info.n_blocks, "thread": info.n_thread_blocks,
                             "warp": info.n_warp_blocks, "product": info.n_product_blocks,
                             "long_segments": info.n_long_segments, "long_rows": info.n_long_rows,
-                            "diag_code_table": info.n_diag_codes, "hot_table_entries": info.hot_entries,
-                            "hot_table_mass": info.hot_mass_ppm / 1e6},
+                            "diag_code_table": info.n_diag_codes},
                    "optimize_ms": round(optimize_ms, 2),
                    "create_ms": round(create_ms, 2),
                    "create_from_pageable_host_ms": None if create_host_ms is None else round(create_host_ms, 2)},

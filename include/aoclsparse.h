@@ -19,12 +19,18 @@
 #define DLL_PUBLIC __attribute__((__visibility__("default")))
 #endif
 
-/* aoclsparse_types.h:54-58 -- LP64 build (int32 indices); -Daoclsparse_ILP64 widens them. */
+/* aoclsparse_types.h:54-58 -- the reference is built either LP64 (aoclsparse_int = int32, the default) or ILP64
+ * (-Daoclsparse_ILP64: int64).  This library is the drop-in for the LP64 build ONLY: the device kernels stage 32-bit
+ * column indices and 32-bit row-pointer windows (int4 block descriptors, 4-byte TMA granules), which is what lets every
+ * BASELINE configuration stream 4 (or 1, with the diagonal-code copy) index bytes per stored entry.  The largest
+ * configuration (937 951 232 entries) fits; byte offsets are formed in 64 bits.  A caller compiled for the ILP64
+ * variant would pass 64-bit arrays to entry points that read 32-bit ones, so that combination is refused here at
+ * compile time rather than failing at run time.  An ILP64 variant would be a second set of kernel instantiations (not a
+ * recompile), and matrices that need it (> 2^31-1 entries, > 25 GB of indices) are sharded by rows first (shard.cu). */
 #if defined(aoclsparse_ILP64)
-typedef int64_t aoclsparse_int;
-#else
-typedef int32_t aoclsparse_int;
+#error "libaoclsparse_b200 replaces the LP64 build of AOCL-Sparse (aoclsparse_int = int32_t); do not define aoclsparse_ILP64"
 #endif
+typedef int32_t aoclsparse_int;
 
 /* aoclsparse_types.h:77-99 -- interleaved (re, im) pairs, layout-compatible with C99 / std::complex. */
 typedef struct

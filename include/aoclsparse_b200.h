@@ -52,9 +52,6 @@ typedef struct aoclsparse_b200_matrix_info_
     aoclsparse_int n_long_rows;     /* rows split across CTAs                                   */
     aoclsparse_int n_diag_codes;    /* diagonal-code copy of col_idx (one byte per entry indexing a table of the
                                        distinct col - row offsets): table entries, 0 = not built / not applicable */
-    aoclsparse_int hot_entries;     /* hot-column table for power-law matrices (csrc/hot.cu): entries of x the persistent
-                                       kernel keeps in shared memory, 0 = not built                              */
-    aoclsparse_int hot_mass_ppm;    /* stored entries whose column is in that table, parts per million            */
 } aoclsparse_b200_matrix_info;
 
 /* Diagonal-code copy of the stored column indices, built by aoclsparse_optimize for banded / stencil matrices (every

@@ -399,10 +399,10 @@ void oracle_plan_parameters(int elem_size, int m, int nnz, int max_row_nnz, cons
         t = 1536; /* 16-byte values: measured best, with 128-thread CTAs */
     const long long mean = m > 0 ? (long long)nnz / m : 0;
     if((long long)max_row_nnz > 16 * (mean > 1 ? mean : 1))
-        t = (16384 / (elem_size + 4)) / 512 * 512;
+        t = ((7152 / (elem_size + 4)) - 8) / 128 * 128; /* skewed rows: 8 CTAs inside the 64 KB carve-out, L1 kept large */
     if(t < 512)
         t = 512;
-    while(t > 512 && (long long)nnz < (long long)t * 148 * 8)
+    while(t >= 1024 && (long long)nnz < (long long)t * 148 * 8)
         t -= 512;
     *R = 1024;
     if(m > 0 && rp && (long long)nnz < 8 * ctas_per_wave(elem_size, t, coded) * (long long)t

@@ -143,3 +143,18 @@ def test_cxx_caller_links_and_validates(tmp_path):
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.split() == ["2", "2", "2", "2"]
+
+
+def test_ilp64_is_refused_at_compile_time(tmp_path):
+    """the library replaces the LP64 build only (include/aoclsparse.h): a caller compiled with -Daoclsparse_ILP64 must
+    fail to compile instead of passing 64-bit index arrays to 32-bit entry points"""
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc") or "/usr/bin/gcc"
+    src = tmp_path / "t.c"
+    src.write_text('#include "aoclsparse.h"\nint main(void){return 0;}\n')
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    ok = subprocess.run([cc, "-fsyntax-only", "-I", inc, str(src)], capture_output=True, text=True)
+    assert ok.returncode == 0, ok.stderr
+    bad = subprocess.run([cc, "-fsyntax-only", "-Daoclsparse_ILP64", "-I", inc, str(src)], capture_output=True, text=True)
+    assert bad.returncode != 0 and "LP64" in bad.stderr

@@ -991,62 +991,6 @@ def test_config3_rmat_float(lib, oracle):
     assert info.n_long_rows > 0 and info.n_product_blocks > 0  # hub rows are split, skewed blocks use product
 
 
-@pytest.mark.parametrize("p", ["s", "d"])
-def test_hot_table_pipeline_kernel(lib, p):
-    """power-law matrix large enough for the hot-column table (R-MAT scale 19, ~8 M entries): aoclsparse_optimize builds
-    the table, aoclsparse_?mv runs the persistent warp-specialised kernel (hot.cu); result against an fp64 accumulation
-    and against the row-block kernel (AOCLSPARSE_B200_HOT=0) to the parity tolerance, beta != 0, reproducible run to run"""
-    import torch
-
-    import bench
-    wl = dict(bench.WORKLOADS["c3"], rmat=19)
-    m, n, nnz, rp_t, col_t, val_t = bench.device_matrix(lib, wl)
-    tdt = torch.float32 if p == "s" else torch.float64
-    val_t = val_t.to(tdt)
-    x_t = torch.empty(n, dtype=tdt, device="cuda")
-    lib.lib.aoclsparse_b200_gen_uniform(1, 0, n, x_t.element_size(), x_t.data_ptr())
-    y0_t = torch.empty(m, dtype=tdt, device="cuda")
-    lib.lib.aoclsparse_b200_gen_uniform(2, 0, m, y0_t.element_size(), y0_t.data_ptr())
-    rows = torch.repeat_interleave(torch.arange(m, device="cuda"), (rp_t[1:] - rp_t[:-1]).long())
-    prods = val_t.double() * x_t.double()[col_t.long()]
-    y64 = torch.zeros(m, dtype=torch.float64, device="cuda").index_add_(0, rows, prods)
-    den = torch.zeros(m, dtype=torch.float64, device="cuda").index_add_(0, rows, prods.abs())
-    tol = 1e-5 if p == "s" else 1e-12
-    outs = {}
-    for mode in ("hot", "plain"):
-        if mode == "plain":
-            os.environ["AOCLSPARSE_B200_HOT"] = "0"
-        try:
-            st, h = lib.create_csr(p, 0, m, n, nnz, rp_t.data_ptr(), col_t.data_ptr(), val_t.data_ptr())
-            assert st == 0, lib.last_error()
-            d = lib.create_descr()
-            assert lib.set_mv_hint(h, 111, d, 100) == 0 and lib.optimize(h) == 0, lib.last_error()
-        finally:
-            os.environ.pop("AOCLSPARSE_B200_HOT", None)
-        info = lib.matrix_info(h)
-        if mode == "hot":
-            assert info.hot_entries >= 8192 and info.hot_mass_ppm > 200000, (info.hot_entries, info.hot_mass_ppm)
-            assert info.n_long_rows > 0
-        else:
-            assert info.hot_entries == 0
-        y = torch.full((m,), float("nan"), dtype=tdt, device="cuda")
-        assert lib.mv(p, 111, 1.0, h, d, x_t.data_ptr(), 0.0, y.data_ptr()) == 0, lib.last_error()
-        y2 = y0_t.clone()
-        assert lib.mv(p, 111, -0.5, h, d, x_t.data_ptr(), 2.0, y2.data_ptr()) == 0, lib.last_error()
-        y3 = torch.empty_like(y)
-        assert lib.mv(p, 111, 1.0, h, d, x_t.data_ptr(), 0.0, y3.data_ptr()) == 0
-        torch.cuda.synchronize()
-        assert torch.equal(y, y3), mode  # fixed summation order
-        safe = torch.where(den > 0, den, torch.ones_like(den))
-        assert float(torch.max((y.double() - y64).abs() / safe)) <= tol, mode
-        want2 = -0.5 * y64 + 2.0 * y0_t.double()
-        assert float(torch.max((y2.double() - want2).abs() / (0.5 * den + 2.0 * y0_t.double().abs()))) <= tol, mode
-        outs[mode] = y
-        lib.destroy(h)
-        lib.destroy_descr(d)
-    assert float(torch.max((outs["hot"].double() - outs["plain"].double()).abs() / torch.where(den > 0, den, torch.ones_like(den)))) <= tol
-
-
 def test_config5_iterated_1_10_100(lib):
     """SURVEY 8(d) parity protocol for the iterated case: x <- A x / 12 on a 7-point stencil, compared with the host
     product after 1, 10 and 100 iterations; the tolerance grows with the iteration count (every iteration adds one

@@ -43,10 +43,10 @@ namespace b200
         constexpr int HP_REDUCE_WARPS = 8;                                 // warps 1..8
         constexpr int HP_GATHER_WARP0 = 1 + HP_REDUCE_WARPS;               // warps 9..31
         constexpr int HP_GATHER_WARPS = HP_THREADS / 32 - HP_GATHER_WARP0; // 23
-        constexpr int HP_GT           = HP_GATHER_WARPS * 32;              // 736 gather threads
+        constexpr int HP_U            = 8;                                 // gathers in flight per gather thread
         constexpr int HP_RT           = HP_REDUCE_WARPS * 32;              // 256 reduce threads
-        constexpr int HP_MAX_STAGES   = 4;
-        constexpr int HP_HEADER       = 256; // 3 x 4 mbarriers, 8 partial sums
+        constexpr int HP_MAX_STAGES   = 8;
+        constexpr int HP_HEADER       = 512; // 3 x 8 mbarriers (192 B), 8 partial sums (64 B), 8 descriptors, 8 kinds
         constexpr int HOT_BIT         = (int)0x80000000;
 
         inline unsigned grid_for(long long n, int tpb)
@@ -106,6 +106,7 @@ namespace b200
                                                                                  int cap,  // staged entries per stage
                                                                                  int rcap, // staged row_ptr entries per stage
                                                                                  int n_stages,
+                                                                                 int n_teams, // gather teams: blocks in the gather phase at once
                                                                                  const aoclsparse_int *__restrict__ rp,
                                                                                  const aoclsparse_int *__restrict__ col_hot,
                                                                                  const T *__restrict__ val,
@@ -122,9 +123,9 @@ namespace b200
             uint64_t *full     = reinterpret_cast<uint64_t *>(smem_raw);
             uint64_t *gathered = full + HP_MAX_STAGES;
             uint64_t *freeb    = gathered + HP_MAX_STAGES;
-            T        *s_part   = reinterpret_cast<T *>(smem_raw + 128); // 8 partial sums of a split-row segment
-            int4     *s_desc   = reinterpret_cast<int4 *>(smem_raw + 192); // [stage]: the block's descriptor, .. (64 bytes)
-            int      *s_kind   = reinterpret_cast<int *>(smem_raw + HP_HEADER); // [stage]
+            T        *s_part   = reinterpret_cast<T *>(smem_raw + 192); // 8 partial sums of a split-row segment
+            int4     *s_desc   = reinterpret_cast<int4 *>(smem_raw + 256); // [stage]: the block's descriptor (128 bytes)
+            int      *s_kind   = reinterpret_cast<int *>(smem_raw + 384); // [stage]
             T        *xs       = reinterpret_cast<T *>(smem_raw + HP_HEADER + 16);
             const size_t   table_bytes = (((size_t)table_entries * sizeof(T)) + 15) & ~(size_t)15;
             unsigned char *ring        = smem_raw + HP_HEADER + 16 + table_bytes;
@@ -136,7 +137,7 @@ namespace b200
                 for(int s = 0; s < n_stages; ++s)
                 {
                     mbar_init(&full[s], 1);
-                    mbar_init(&gathered[s], HP_GATHER_WARPS);
+                    mbar_init(&gathered[s], HP_GATHER_WARPS / n_teams);
                     mbar_init(&freeb[s], HP_REDUCE_WARPS);
                 }
                 mbar_init_fence();
@@ -193,37 +194,46 @@ namespace b200
             else if(warp >= HP_GATHER_WARP0)
             {
                 // ------------------------------------------------------------------ gatherers
-                const int gt = tid - HP_GATHER_WARP0 * 32;
-                int       i  = 0;
+                // n_teams teams of wpt warps; team g takes the blocks i = g, g + n_teams, ... so that several blocks are
+                // in their gather phase at once (the gathers are latency-bound: what counts is how many are in flight)
+                const int wpt  = HP_GATHER_WARPS / n_teams;
+                const int team = (warp - HP_GATHER_WARP0) / wpt;
+                if(team >= n_teams)
+                    return;
+                const int gt    = tid - (HP_GATHER_WARP0 + team * wpt) * 32;
+                const int HP_GT = wpt * 32;
+                int       i     = 0;
                 for(int b = blockIdx.x; b < n_blocks; b += gridDim.x, ++i)
                 {
+                    if(i % n_teams != team)
+                        continue;
                     const int s = i % n_stages, use = i / n_stages;
                     mbar_wait(&full[s], (unsigned)(use & 1));
                     const int4            d    = s_desc[s];
                     T                    *sval = stage_val(s);
                     const aoclsparse_int *scol = stage_col(s);
                     const int             f0 = d.z - (d.z & ~3), total = d.w - d.z;
-                    for(int q = gt; q < total; q += 4 * HP_GT)
+                    for(int q = gt; q < total; q += HP_U * HP_GT)
                     {
-                        int  c[4];
-                        bool ok[4];
-                        T    xv[4];
+                        int  c[HP_U];
+                        bool ok[HP_U];
+                        T    xv[HP_U];
 #pragma unroll
-                        for(int u = 0; u < 4; ++u)
+                        for(int u = 0; u < HP_U; ++u)
                         {
                             ok[u] = q + u * HP_GT < total;
                             c[u]  = ok[u] ? scol[f0 + q + u * HP_GT] : 0;
                         }
                         // the L1/L2 gathers of the cold columns are issued together, then the table reads
 #pragma unroll
-                        for(int u = 0; u < 4; ++u)
+                        for(int u = 0; u < HP_U; ++u)
                             xv[u] = (ok[u] && c[u] >= 0) ? ldg_ro(x + c[u]) : vt<T>::zero();
 #pragma unroll
-                        for(int u = 0; u < 4; ++u)
+                        for(int u = 0; u < HP_U; ++u)
                             if(ok[u] && c[u] < 0)
                                 xv[u] = xs[c[u] & 0x7fffffff];
 #pragma unroll
-                        for(int u = 0; u < 4; ++u)
+                        for(int u = 0; u < HP_U; ++u)
                             if(ok[u])
                                 sval[f0 + q + u * HP_GT] = mul(sval[f0 + q + u * HP_GT], xv[u]);
                     }
@@ -323,9 +333,13 @@ namespace b200
         P.col_hot.release();
         if(!P.valid || A.nnz < (1 << 22) || A.n < (1 << 16) || elem_size > 8)
             return aoclsparse_status_success; // small problems: x lives in L1/L2 anyway
-        int stages = 3;
+        int stages = 5, teams = 2;
         if(const char *e = getenv("AOCLSPARSE_B200_HOT_STAGES"))
             stages = atoi(e) < 2 ? 2 : (atoi(e) > HP_MAX_STAGES ? HP_MAX_STAGES : atoi(e));
+        if(const char *e = getenv("AOCLSPARSE_B200_HOT_TEAMS"))
+            teams = atoi(e) < 1 ? 1 : (atoi(e) > 4 ? 4 : atoi(e));
+        if(stages < teams + 1)
+            stages = teams + 1;
         const int cap = P.block_nnz + 8, rcap = P.block_rows + 8;
         // the table gets what one CTA per SM can spare: 227 KB - header - stages
         const size_t budget = 232448 - 1024;
@@ -376,6 +390,7 @@ namespace b200
         B200_CUDA(cudaStreamSynchronize(st));
         P.hot_entries = (aoclsparse_int)K;
         P.hot_stages  = stages;
+        P.hot_teams   = teams;
         P.hot_mass    = (double)mass / (double)nnz;
         return aoclsparse_status_success;
     }
@@ -402,6 +417,7 @@ namespace b200
                                                                       cap,
                                                                       rcap,
                                                                       P.hot_stages,
+                                                                      P.hot_teams,
                                                                       A.row_ptr.as<aoclsparse_int>(),
                                                                       P.col_hot.as<aoclsparse_int>(),
                                                                       A.val.as<T>(),
