@@ -540,6 +540,25 @@ namespace b200
                                           const aoclsparse_b200_halo_ctl *ctl,
                                           unsigned                        kc);
 
+    // spmv.cu -- k iterations in one cooperative launch (spmv_sharded_iterate_kernel); see shard.cu
+    struct sharded_iterate_args
+    {
+        const void *left_done = nullptr, *right_done = nullptr;     // local flags the neighbours write
+        void       *to_left_done = nullptr, *to_right_done = nullptr; // the neighbours' flags
+        void       *counters = nullptr;                              // 4 words: boundary counts, grid barrier, timeout
+        void       *push_left[2] = {nullptr, nullptr}, *push_right[2] = {nullptr, nullptr}; // [0] neighbour's window `cur`, [1] `nxt`
+        unsigned    k0 = 0, kc0 = 0, bar0 = 0;
+    };
+    aoclsparse_status sharded_iterate_launch(double                      alpha,
+                                             aoclsparse_matrix           A,
+                                             const aoclsparse_mat_descr  descr,
+                                             double                     *w_cur,
+                                             double                     *w_nxt,
+                                             long long                   own_offset,
+                                             const sharded_iterate_args &args,
+                                             int                         iterations,
+                                             int                        *grid_out);
+
     // obtains (building on first use) the plan of mats[0]
     aoclsparse_status ensure_plan(aoclsparse_matrix A, cudaStream_t st);
 }

@@ -34,6 +34,7 @@ namespace
         long long          own_offset, rows, halo, win_len;
         void              *w[2], *flags;          // addresses in the owner's process (same-process neighbours use them)
         cudaIpcMemHandle_t hw[2], hflags;         // handles for neighbours in other processes
+        int                pci[3];                // domain / bus / device of the owner's GPU: do two shards share one?
     };
     static_assert(sizeof(link_record) <= AOCLSPARSE_B200_SHARD_LINK_BYTES, "link record must fit the public blob");
 
@@ -43,6 +44,7 @@ namespace
         double *w[2]   = {nullptr, nullptr};
         unsigned *flags = nullptr;
         long long own_offset = 0, rows = 0;
+        bool      same_gpu = false; // the neighbour's shard lives on the GPU this shard lives on
     };
 }
 
@@ -56,8 +58,10 @@ struct _aoclsparse_b200_shard
     unsigned             *flags = nullptr; // [4] left neighbour done, [5] right neighbour done, [16..19] counters
     peer_map              left, right;
     unsigned              k = 0, kc = 0; // events / kernel iterations so far
+    unsigned              bar = 0;       // arrivals counted so far by the persistent kernel's grid barrier (flags[18])
     int                   cur = 0;       // window holding the current x
     bool                  fused = false, connected = false, has_x = false;
+    bool                  own_gpu = false; // no other shard of the job runs on this GPU (set by connect)
     cudaStream_t          own_stream = nullptr;
 
     long long own_offset() const
@@ -105,6 +109,13 @@ namespace
             return aoclsparse_status_invalid_value;
         P.own_offset = L.own_offset;
         P.rows       = L.rows;
+        {
+            int mine[3] = {0, 0, 0};
+            cudaDeviceGetAttribute(&mine[0], cudaDevAttrPciDomainId, S->device);
+            cudaDeviceGetAttribute(&mine[1], cudaDevAttrPciBusId, S->device);
+            cudaDeviceGetAttribute(&mine[2], cudaDevAttrPciDeviceId, S->device);
+            P.same_gpu = mine[0] == L.pci[0] && mine[1] == L.pci[1] && mine[2] == L.pci[2];
+        }
         if(L.pid == (int)getpid())
         {
             // same process: the neighbour's allocations are directly addressable once peer access is on
@@ -264,6 +275,9 @@ aoclsparse_status aoclsparse_b200_shard_export(aoclsparse_b200_shard shard, unsi
     L.w[0]       = shard->w[0];
     L.w[1]       = shard->w[1];
     L.flags      = shard->flags;
+    cudaDeviceGetAttribute(&L.pci[0], cudaDevAttrPciDomainId, shard->device);
+    cudaDeviceGetAttribute(&L.pci[1], cudaDevAttrPciBusId, shard->device);
+    cudaDeviceGetAttribute(&L.pci[2], cudaDevAttrPciDeviceId, shard->device);
     B200_CUDA(cudaIpcGetMemHandle(&L.hw[0], shard->w[0]));
     B200_CUDA(cudaIpcGetMemHandle(&L.hw[1], shard->w[1]));
     B200_CUDA(cudaIpcGetMemHandle(&L.hflags, shard->flags));
@@ -287,6 +301,18 @@ aoclsparse_status aoclsparse_b200_shard_connect(aoclsparse_b200_shard shard, con
     if(need_r)
         B200_TRY(map_peer(shard, right_link, shard->rank + 1, shard->right));
     shard->connected = true;
+    // the persistent k-iteration kernel keeps every SM of its GPU busy until its neighbours have advanced, so it needs
+    // a GPU of its own: never when a neighbour shares this GPU, and for shards driven from one process only when that
+    // process has a device per shard
+    {
+        int ndev = 1;
+        cudaGetDeviceCount(&ndev);
+        bool ok = true;
+        for(const peer_map *P : {&shard->left, &shard->right})
+            if(P->present && (P->same_gpu || (!P->ipc && shard->world > ndev)))
+                ok = false;
+        shard->own_gpu = ok;
+    }
     return aoclsparse_status_success;
 }
 
@@ -348,6 +374,43 @@ aoclsparse_status aoclsparse_b200_shard_iterate(aoclsparse_b200_shard shard, dou
     shard_scope  sc(shard);
     const double zero = 0.0;
     const long long h = shard->halo, m = shard->m;
+    // several iterations on the fused path: ONE cooperative launch of the persistent kernel runs them all (grid barrier
+    // between iterations instead of a launch; AOCLSPARSE_B200_SHARD_PERSISTENT=0 keeps one launch per iteration)
+    static const bool persistent = [] {
+        const char *e = getenv("AOCLSPARSE_B200_SHARD_PERSISTENT");
+        return !(e && atoi(e) == 0);
+    }();
+    if(shard->world > 1 && shard->fused && shard->own_gpu && persistent && iterations >= 2)
+    {
+        const int            cur = shard->cur, nxt = cur ^ 1;
+        sharded_iterate_args a;
+        if(shard->left.present)
+        {
+            a.left_done    = shard->flags + 4;
+            a.to_left_done = shard->left.flags + 5;
+            a.push_left[0] = left_dst(shard, cur);
+            a.push_left[1] = left_dst(shard, nxt);
+        }
+        if(shard->right.present)
+        {
+            a.right_done    = shard->flags + 5;
+            a.to_right_done = shard->right.flags + 4;
+            a.push_right[0] = right_dst(shard, cur);
+            a.push_right[1] = right_dst(shard, nxt);
+        }
+        a.counters = shard->flags + 16;
+        a.k0       = shard->k + 1;
+        a.kc0      = shard->kc;
+        a.bar0     = shard->bar;
+        int grid   = 0;
+        B200_TRY(sharded_iterate_launch(alpha, shard->A, &shard->descr, shard->w[cur], shard->w[nxt], shard->own_offset(), a, iterations, &grid));
+        shard->k += (unsigned)iterations;
+        shard->kc += (unsigned)iterations;
+        shard->bar += (unsigned)(iterations - 1) * (unsigned)grid;
+        if(iterations & 1)
+            shard->cur = nxt;
+        return aoclsparse_status_success;
+    }
     for(int it = 0; it < iterations; ++it)
     {
         const int cur = shard->cur, nxt = cur ^ 1;

@@ -1319,6 +1319,96 @@ aoclsparse_status b200::sharded_step_launch(const double                  *alpha
     return aoclsparse_status_success;
 }
 
+// k iterations of the row-sharded product in ONE cooperative launch (spmv_sharded_iterate_kernel).  w_cur / w_nxt are
+// the two x windows (the current iterate lives in w_cur); push_*[i] are the neighbours' halo slots of window i
+// (0 = the window w_cur maps to in the neighbour, 1 = the other one).  *grid_out = CTAs launched (the grid barrier
+// counter advances by (iterations - 1) * grid).
+aoclsparse_status b200::sharded_iterate_launch(double                     alpha,
+                                               aoclsparse_matrix          A,
+                                               const aoclsparse_mat_descr descr,
+                                               double                    *w_cur,
+                                               double                    *w_nxt,
+                                               long long                  own_offset,
+                                               const sharded_iterate_args &args,
+                                               int                        iterations,
+                                               int                       *grid_out)
+{
+    if(!A || !descr || !w_cur || !w_nxt || !args.counters || !grid_out)
+        return aoclsparse_status_invalid_pointer;
+    if(A->mats.empty() || A->mats[0] == nullptr)
+        return aoclsparse_status_invalid_pointer;
+    if(descr->base != A->base)
+        return aoclsparse_status_invalid_value;
+    if(A->val_type != aoclsparse_dmat)
+        return aoclsparse_status_wrong_type;
+    if(descr->type != aoclsparse_matrix_type_general || args.k0 == 0 || iterations < 1)
+        return aoclsparse_status_invalid_value;
+    if(A->is_csc)
+        return aoclsparse_status_not_implemented;
+    cudaStream_t st = current_stream();
+    B200_TRY(ensure_plan(A, st));
+    std::shared_lock<std::shared_mutex> rl(A->guard);
+    const dev_csr                      &M = *A->mats[0];
+    const row_block_plan               &P = M.plan;
+    if(A->row_cuts.size() != 2 || P.cut_block.size() != 2 || P.n_strat[STRAT_THREAD] != P.n_blocks || P.n_blocks < 1)
+        return aoclsparse_status_not_implemented;
+    iterate_ctl hc;
+    hc.left_done     = static_cast<const unsigned *>(args.left_done);
+    hc.right_done    = static_cast<const unsigned *>(args.right_done);
+    hc.to_left_done  = static_cast<unsigned *>(args.to_left_done);
+    hc.to_right_done = static_cast<unsigned *>(args.to_right_done);
+    hc.counters      = static_cast<unsigned *>(args.counters);
+    hc.k0            = args.k0;
+    hc.kc0           = args.kc0;
+    hc.bar0          = args.bar0;
+    hc.iters         = iterations;
+    hc.n_first       = P.cut_block[0];
+    hc.last_begin    = P.cut_block[1];
+    hc.n_last        = P.n_blocks - P.cut_block[1];
+    hc.n_blocks      = P.n_blocks;
+    hc.last_row0     = A->row_cuts[1];
+    if((hc.left_done && (!args.push_left[0] || !args.push_left[1])) || (hc.right_done && (!args.push_right[0] || !args.push_right[1])))
+        return aoclsparse_status_invalid_pointer;
+    const long long shift = A->win_hi >= 0 ? (long long)A->win_lo : 0;
+    // iteration 0 reads w_cur and writes the own rows of w_nxt; the neighbours receive into THEIR w_nxt (slot 1)
+    const double *x0 = w_cur - shift, *x1 = w_nxt - shift;
+    double       *y0 = w_nxt + own_offset, *y1 = w_cur + own_offset;
+    const bool   coded = P.n_codes > 0;
+    int          cap   = P.block_nnz + (coded ? 32 : 8);
+    const size_t smem  = coded ? spmv_coded_smem_bytes(sizeof(double), P.block_nnz) : spmv_smem_bytes(sizeof(double), P.block_nnz);
+    auto         kern  = coded ? spmv_sharded_iterate_kernel<double, true> : spmv_sharded_iterate_kernel<double, false>;
+    static std::atomic<size_t> configured[2] = {{0}, {0}};
+    if(configured[coded].load() < smem)
+    {
+        B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[coded].store(smem);
+    }
+    long long grid = resident_ctas(kern, 256, smem);
+    if(const char *e = getenv("AOCLSPARSE_B200_ITER_GRID"))
+    {
+        const long long v = atoll(e);
+        if(v > 0 && v < grid)
+            grid = v;
+    }
+    if(grid > P.n_blocks)
+        grid = P.n_blocks;
+    const int4           *p_desc  = P.desc.as<int4>();
+    const aoclsparse_int *p_rp    = M.row_ptr.as<aoclsparse_int>();
+    const aoclsparse_int *p_col   = M.col_idx.as<aoclsparse_int>();
+    const double         *p_val   = M.val.as<double>();
+    double               *pl0     = static_cast<double *>(args.push_left[1]); // iteration 0 stores into the neighbours' "next" window
+    double               *pl1     = static_cast<double *>(args.push_left[0]);
+    double               *pr0     = static_cast<double *>(args.push_right[1]);
+    double               *pr1     = static_cast<double *>(args.push_right[0]);
+    const unsigned char  *p_codes = P.codes.as<unsigned char>();
+    const int            *p_off   = P.code_offsets.as<int>();
+    void *params[] = {&p_desc, &cap, &p_rp, &p_col, &p_val, &x0, &x1, &y0, &y1, &alpha, &pl0, &pl1, &pr0, &pr1, &hc, &p_codes, &p_off};
+    B200_CUDA(cudaLaunchCooperativeKernel((const void *)kern, dim3((unsigned)grid), dim3(256), params, smem, st));
+    B200_LAUNCHED();
+    *grid_out = (int)grid;
+    return aoclsparse_status_success;
+}
+
 extern "C" {
 aoclsparse_status aoclsparse_b200_dmv_sharded_step(const double                  *alpha,
                                                    aoclsparse_matrix              A,

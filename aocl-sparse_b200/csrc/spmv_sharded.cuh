@@ -228,4 +228,259 @@ namespace b200
             }
         }
     }
+
+    // ---------------------------------------------------------------------------------------------------------------
+    // k iterations in ONE launch: a persistent grid (every CTA resident: cooperative launch) walks the row blocks of
+    // every iteration itself, so an iteration costs neither a launch nor the drain / refill of the device between two
+    // grids.  Per iteration:
+    //   * CTA c takes blocks c, c+G, c+2G, ... of the order [first boundary | last boundary | interior]; the boundary
+    //     blocks behave exactly as in spmv_sharded_step_kernel (flag wait, peer stores, last one publishes the flag);
+    //   * the matrix slice of the NEXT block -- also when it belongs to the next iteration -- is requested (TMA bulk
+    //     copies) as soon as the staging buffer is free, i.e. before the grid barrier: the barrier's latency and the
+    //     refill of the pipeline overlap;
+    //   * between iterations the grid meets at one counter in device memory (arrive: fence + atomicAdd; wait: spin on a
+    //     volatile load, then fence.acq_rel.gpu, which also invalidates this SM's L1).  x of iteration k+1 is what other
+    //     CTAs stored during iteration k, so the gathers use ld.global.ca (coherent after the acquire) instead of the
+    //     non-coherent path; halo entries, stored by the peer GPU while this iteration runs, are read at L2 (ld.cg).
+    // Results are bit-identical to k launches of the step kernel (same blocks, same per-row order of operations).
+    struct iterate_ctl
+    {
+        const unsigned *left_done, *right_done;
+        unsigned       *to_left_done, *to_right_done;
+        unsigned       *counters; // [0] / [1] boundary CTAs done, [2] grid barrier arrivals, [3] a wait gave up
+        unsigned        k0;       // flag value of this launch's first iteration
+        unsigned        kc0;      // iterations run on these counters before this launch
+        unsigned        bar0;     // value of counters[2] before this launch
+        int             iters;
+        int             n_first, n_last, n_blocks, last_begin, last_row0;
+    };
+
+    template <typename T, bool CODED>
+    __global__ void __launch_bounds__(256) spmv_sharded_iterate_kernel(const int4 *__restrict__ desc,
+                                                                      int cap,
+                                                                      const aoclsparse_int *__restrict__ rp,
+                                                                      const aoclsparse_int *__restrict__ col,
+                                                                      const T *__restrict__ val,
+                                                                      const T *x0, // x of even iterations (0, 2, ...)
+                                                                      const T *x1, // x of odd iterations
+                                                                      T       *y0, // y of even iterations (own rows of x1's window)
+                                                                      T       *y1,
+                                                                      T        alpha,
+                                                                      T       *push_left0,
+                                                                      T       *push_left1,
+                                                                      T       *push_right0,
+                                                                      T       *push_right1,
+                                                                      iterate_ctl hc,
+                                                                      const unsigned char *__restrict__ codes,
+                                                                      const int *__restrict__ code_off)
+    {
+        constexpr int NT = 256;
+        extern __shared__ __align__(16) unsigned char smem_raw[];
+        uint64_t            *bar   = reinterpret_cast<uint64_t *>(smem_raw);
+        T                   *sval  = reinterpret_cast<T *>(smem_raw + SMEM_HEADER);
+        aoclsparse_int      *scol  = reinterpret_cast<aoclsparse_int *>(smem_raw + SMEM_HEADER + (size_t)cap * sizeof(T));
+        const unsigned char *scode = smem_raw + SMEM_HEADER + (size_t)cap * sizeof(T);
+        int                 *soff  = reinterpret_cast<int *>(smem_raw + SMEM_HEADER + (size_t)cap * (sizeof(T) + 1));
+        constexpr int        GR    = CODED ? 16 : 4;
+
+        const int tid = threadIdx.x;
+        const int G   = (int)gridDim.x;
+
+        // launch order -> (block, side); side 0 first boundary, 1 last boundary, 2 interior
+        auto locate = [&](int bid, int &b, int &side) {
+            if(bid < hc.n_first)
+            {
+                b    = bid;
+                side = 0;
+            }
+            else if(bid < hc.n_first + hc.n_last)
+            {
+                b    = hc.last_begin + (bid - hc.n_first);
+                side = 1;
+            }
+            else
+            {
+                b    = hc.n_first + (bid - hc.n_first - hc.n_last);
+                side = 2;
+            }
+        };
+        // thread 0: request the matrix slice of block descriptor d into the staging buffer
+        auto request = [&](const int4 &d) {
+            const int a   = d.z & ~(GR - 1);
+            const int cnt = ((d.w - a) + GR - 1) & ~(GR - 1);
+            if(cnt <= 0)
+                return;
+            if constexpr(CODED)
+            {
+                mbar_expect_tx(bar, (unsigned)(cnt * (sizeof(T) + 1)));
+                bulk_load_stream(sval, val + a, (unsigned)(cnt * sizeof(T)), bar);
+                bulk_load_stream(const_cast<unsigned char *>(scode), codes + a, (unsigned)cnt, bar);
+            }
+            else
+            {
+                mbar_expect_tx(bar, (unsigned)(cnt * (sizeof(T) + sizeof(aoclsparse_int))));
+                bulk_load_stream(sval, val + a, (unsigned)(cnt * sizeof(T)), bar);
+                bulk_load_stream(scol, col + a, (unsigned)(cnt * sizeof(aoclsparse_int)), bar);
+            }
+        };
+        auto col_at = [&](int r, int j) -> int {
+            if constexpr(CODED)
+                return r + soff[scode[j]];
+            else
+                return scol[j];
+        };
+
+        if(tid == 0)
+        {
+            mbar_init(bar, 1);
+            mbar_init_fence();
+        }
+        if constexpr(CODED)
+            for(int i = tid; i < CODE_TABLE; i += NT)
+                soff[i] = code_off[i];
+        __syncthreads();
+        if((int)blockIdx.x >= hc.n_blocks || hc.iters <= 0)
+            return; // host launches G <= n_blocks
+        unsigned parity = 0;
+        int      b, side;
+        locate((int)blockIdx.x, b, side);
+        int4 d = desc[b];
+        if(tid == 0)
+            request(d);
+
+        for(int it = 0; it < hc.iters; ++it)
+        {
+            const T *x          = (it & 1) ? x1 : x0;
+            T       *y          = (it & 1) ? y1 : y0;
+            T       *push_left  = (it & 1) ? push_left1 : push_left0;
+            T       *push_right = (it & 1) ? push_right1 : push_right0;
+            const unsigned k    = hc.k0 + (unsigned)it;
+            for(int bid = (int)blockIdx.x; bid < hc.n_blocks; bid += G)
+            {
+                // (b, side, d) describe block `bid`; its slice has been requested
+                const int a   = d.z & ~(GR - 1);
+                const int cnt = ((d.w - a) + GR - 1) & ~(GR - 1);
+                int       pre_s = 0, pre_e = 0;
+                if(d.x + tid < d.y)
+                {
+                    pre_s = rp[d.x + tid];
+                    pre_e = rp[d.x + tid + 1];
+                }
+                if(side != 2)
+                {
+                    if(tid == 0)
+                    {
+                        const unsigned *done = side == 0 ? hc.left_done : hc.right_done;
+                        if(done)
+                            spin_until(done, k - 1, hc.counters + 3);
+                    }
+                    __syncthreads();
+                }
+                if(cnt > 0)
+                {
+                    mbar_wait(bar, parity);
+                    parity ^= 1u;
+                }
+                if(side == 2)
+                {
+                    for(int r = d.x + tid; r < d.y; r += NT)
+                    {
+                        const bool first = r == d.x + tid;
+                        int        j     = (first ? pre_s : rp[r]) - a;
+                        const int  e     = (first ? pre_e : rp[r + 1]) - a;
+                        T          acc   = vt<T>::zero();
+                        for(; j + 4 <= e; j += 4)
+                        {
+                            const int c0 = col_at(r, j), c1 = col_at(r, j + 1), c2 = col_at(r, j + 2), c3 = col_at(r, j + 3);
+                            const T   v0 = __ldca(x + c0), v1 = __ldca(x + c1), v2 = __ldca(x + c2), v3 = __ldca(x + c3);
+                            acc          = mad(sval[j], v0, acc);
+                            acc          = mad(sval[j + 1], v1, acc);
+                            acc          = mad(sval[j + 2], v2, acc);
+                            acc          = mad(sval[j + 3], v3, acc);
+                        }
+                        for(; j < e; ++j)
+                            acc = mad(sval[j], __ldca(x + col_at(r, j)), acc);
+                        y[r] = mul(alpha, acc);
+                    }
+                }
+                else
+                {
+                    T        *push      = side == 0 ? push_left : push_right;
+                    const int push_row0 = side == 0 ? 0 : hc.last_row0;
+                    for(int r = d.x + tid; r < d.y; r += NT)
+                    {
+                        const bool first = r == d.x + tid;
+                        int        j     = (first ? pre_s : rp[r]) - a;
+                        const int  e     = (first ? pre_e : rp[r + 1]) - a;
+                        T          acc   = vt<T>::zero();
+                        for(; j + 4 <= e; j += 4)
+                        {
+                            const int c0 = col_at(r, j), c1 = col_at(r, j + 1), c2 = col_at(r, j + 2), c3 = col_at(r, j + 3);
+                            const T   v0 = __ldcg(x + c0), v1 = __ldcg(x + c1), v2 = __ldcg(x + c2), v3 = __ldcg(x + c3);
+                            acc          = mad(sval[j], v0, acc);
+                            acc          = mad(sval[j + 1], v1, acc);
+                            acc          = mad(sval[j + 2], v2, acc);
+                            acc          = mad(sval[j + 3], v3, acc);
+                        }
+                        for(; j < e; ++j)
+                            acc = mad(sval[j], __ldcg(x + col_at(r, j)), acc);
+                        const T out = mul(alpha, acc);
+                        y[r]        = out;
+                        if(push)
+                            push[r - push_row0] = out;
+                    }
+                }
+                __syncthreads(); // the staging buffer is free; this CTA's stores are ordered before thread 0's fences
+                const int  done_side = side;
+                // next block of this CTA: in this iteration, or the first one of the next iteration
+                const bool wraps = bid + G >= hc.n_blocks;
+                const bool more  = !wraps || it + 1 < hc.iters;
+                if(more)
+                {
+                    locate(wraps ? (int)blockIdx.x : bid + G, b, side);
+                    d = desc[b];
+                    if(tid == 0)
+                        request(d);
+                }
+                if(done_side != 2 && tid == 0)
+                {
+                    __threadfence_system(); // this CTA's stores (peer stores included) before the counter / flag
+                    const unsigned n_side = done_side == 0 ? (unsigned)hc.n_first : (unsigned)hc.n_last;
+                    const unsigned cntd   = atomicAdd(hc.counters + done_side, 1u) + 1u;
+                    if(cntd == (hc.kc0 + (unsigned)it + 1u) * n_side)
+                    {
+                        unsigned *flag = done_side == 0 ? hc.to_left_done : hc.to_right_done;
+                        if(flag)
+                        {
+                            __threadfence_system();
+                            *reinterpret_cast<volatile unsigned *>(flag) = k;
+                        }
+                    }
+                }
+            }
+            if(it + 1 < hc.iters)
+            {
+                // grid barrier: every y of this iteration is stored before any CTA gathers it as the next x
+                if(tid == 0)
+                {
+                    __threadfence();
+                    atomicAdd(hc.counters + 2, 1u);
+                    const unsigned           target = hc.bar0 + (unsigned)(it + 1) * (unsigned)G;
+                    const volatile unsigned *c      = hc.counters + 2;
+                    long long                spins  = 0;
+                    while((int)(*c - target) < 0)
+                    {
+                        __nanosleep(32);
+                        if(++spins > 100000000LL)
+                        {
+                            hc.counters[3] = 1;
+                            break;
+                        }
+                    }
+                    __threadfence(); // acquire: also drops this SM's L1 lines of the buffer that was just rewritten
+                }
+                __syncthreads();
+            }
+        }
+    }
 }
