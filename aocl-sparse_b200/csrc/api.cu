@@ -256,6 +256,7 @@ namespace b200
         for(size_t i = 1; i < A->mats.size(); ++i)
             delete A->mats[i];
         A->mats.resize(1);
+        A->mats[0]->tiles = b200::mesh_tiles(); // holds a copy of the values
         A->clean = b200::clean_csr();
         for(auto &h : A->hints)
             h.done = false;

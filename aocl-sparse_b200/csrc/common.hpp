@@ -376,6 +376,27 @@ namespace b200
         bool           valid = false;
     };
 
+    // box tiles of a lattice-structured (stencil) matrix for csrmm: see mesh_tiles.cu
+    struct mesh_tiles
+    {
+        int       state = 0;             // 0 not analysed, 1 analysed and not usable, 2 ready
+        int       box[3]    = {0, 0, 0}; // tile extent along the three grid directions
+        long long stride[3] = {0, 0, 0}; // row-index strides of the directions (stride[0] == 1)
+        int       dims[3]   = {0, 0, 0}; // grid extent
+        int       rows_per_tile = 0, n_tiles = 0, max_distinct = 0, max_len = 0, max_runs = 0;
+        size_t    row_bytes    = 0; // n * sizeof(T) the box was sized for
+        long long entries      = 0; // ELL slots of all tiles (padding included)
+        long long n_runs_total = 0; // runs of all tiles + one terminator per tile
+        double    reuse = 0.0, fill = 0.0; // stored entries per staged B row; stored entries per ELL slot
+        dev_buf   desc;    // int4 per tile: distinct B rows, runs, longest row, first run
+        dev_buf   ent_off; // long long per tile: first ELL slot
+        dev_buf   val;     // T[entries]:  tile t, plane j, row lr at ent_off[t] + j * rows_per_tile + lr
+        dev_buf   slot;    // unsigned short[entries], same layout: position of the column among the tile's distinct ones
+        dev_buf   rows;    // int[n_tiles * rows_per_tile]: matrix row of (tile, lr) or -1
+        dev_buf   len;     // unsigned char[n_tiles * rows_per_tile]: stored entries of that row
+        dev_buf   runs;    // int2[n_runs_total]: first column, first slot of every run; terminator (-1, distinct)
+    };
+
     // one device-resident CSR (always 0-based on the device)
     struct dev_csr
     {
@@ -383,6 +404,10 @@ namespace b200
         int            doid = DOID_GN; // what this copy represents relative to the user's matrix
         dev_buf        row_ptr, col_idx, val;
         row_block_plan plan;
+        // csrmm's tile copy, built on the first row-major multiply that can use it (under tiles_mu; immutable once
+        // ready, dropped under the handle's write lock when the values change)
+        mutable mesh_tiles tiles;
+        mutable std::mutex tiles_mu;
     };
 
     // "clean CSR" of the reference's analysis (clean.cu): rows grouped lower | diagonal | upper, diagonals present
@@ -558,6 +583,13 @@ namespace b200
                                              const sharded_iterate_args &args,
                                              int                         iterations,
                                              int                        *grid_out);
+
+    // mesh_tiles.cu
+    bool              detect_lattice(const std::vector<int> &offs, long long m, long long &s1, long long &s2, int &ndim);
+    aoclsparse_status build_mesh_tiles(const dev_csr &A, size_t elem_size, size_t row_bytes, cudaStream_t st);
+    size_t            mesh_tiles_smem(const mesh_tiles &M, size_t row_bytes, size_t elem_size);
+    template <typename T>
+    aoclsparse_status launch_mm_tiles(const dev_csr &A, const T *B, long long ldb, T *C, long long ldc, int n, T alpha, T beta, cudaStream_t st);
 
     // obtains (building on first use) the plan of mats[0]
     aoclsparse_status ensure_plan(aoclsparse_matrix A, cudaStream_t st);

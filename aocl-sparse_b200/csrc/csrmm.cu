@@ -593,6 +593,24 @@ namespace b200
             constexpr int VEC = 16 / (int)sizeof(T);
             const bool    vec_ok = order == aoclsparse_order_row && (n % VEC) == 0 && (ldb % VEC) == 0 && (ldc % VEC) == 0
                                 && ((uintptr_t)B % 16) == 0 && ((uintptr_t)C % 16) == 0;
+            // stencil / grid matrices: box tiles with their distinct B rows staged once in shared memory (mesh_tiles.cu).
+            // AOCLSPARSE_B200_MM_TILES: 0 never, 1 (default) matrices of at least 32768 entries, 2 any size
+            const size_t row_bytes = (size_t)n * sizeof(T);
+            if(vec_ok && !CONJ && P.n_long_rows == 0 && (row_bytes == 128 || row_bytes == 256 || row_bytes == 512))
+            {
+                const char *e    = getenv("AOCLSPARSE_B200_MM_TILES");
+                const int   mode = e ? atoi(e) : 1;
+                if(mode >= 2 || (mode == 1 && A.nnz >= 32768))
+                {
+                    {
+                        std::lock_guard<std::mutex> lk(A.tiles_mu);
+                        if(A.tiles.state == 0)
+                            B200_TRY(build_mesh_tiles(A, sizeof(T), row_bytes, st));
+                    }
+                    if(A.tiles.state == 2 && mesh_tiles_smem(A.tiles, row_bytes, sizeof(T)) <= (size_t)227 * 1024)
+                        return launch_mm_tiles<T>(A, B, ldb, C, ldc, n, alpha, beta, st);
+                }
+            }
             if(vec_ok)
             {
                 const int vecs = n / VEC; // 16-byte vectors per row; LPR lanes x 2 vectors per pass

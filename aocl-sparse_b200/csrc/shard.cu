@@ -398,6 +398,24 @@ aoclsparse_status aoclsparse_b200_shard_iterate(aoclsparse_b200_shard shard, dou
             a.push_right[0] = right_dst(shard, cur);
             a.push_right[1] = right_dst(shard, nxt);
         }
+        // timing experiments only (results are wrong): 1 = boundary rows store into this GPU's own halo instead of the
+        // neighbours', 2 = no flag waits / signals
+        static const int debug = getenv("AOCLSPARSE_B200_SHARD_DEBUG") ? atoi(getenv("AOCLSPARSE_B200_SHARD_DEBUG")) : 0;
+        if(debug & 1)
+        {
+            if(shard->left.present)
+            {
+                a.push_left[0] = shard->w[cur];
+                a.push_left[1] = shard->w[nxt];
+            }
+            if(shard->right.present)
+            {
+                a.push_right[0] = shard->w[cur] + shard->own_offset() + shard->m;
+                a.push_right[1] = shard->w[nxt] + shard->own_offset() + shard->m;
+            }
+        }
+        if(debug & 2)
+            a.left_done = a.right_done = a.to_left_done = a.to_right_done = nullptr;
         a.counters = shard->flags + 16;
         a.k0       = shard->k + 1;
         a.kc0      = shard->kc;

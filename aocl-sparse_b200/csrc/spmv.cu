@@ -1275,6 +1275,9 @@ aoclsparse_status b200::sharded_step_launch(const double                  *alpha
     hc.n_blocks          = P.n_blocks;
     hc.first_rows        = A->row_cuts[0];
     hc.last_row0         = A->row_cuts[1];
+    // the window holds a halo of row_cuts[0] entries on every side that has a neighbour
+    hc.own_lo = (A->win_hi >= 0 ? (int)A->win_lo : 0) + (hc.left_done ? (int)A->row_cuts[0] : 0);
+    hc.own_hi = hc.own_lo + (int)A->m;
     if((hc.left_done && !ctl->push_left) || (hc.right_done && !ctl->push_right))
         return aoclsparse_status_invalid_pointer;
     if(A->win_hi >= 0)
@@ -1367,6 +1370,8 @@ aoclsparse_status b200::sharded_iterate_launch(double                     alpha,
     hc.n_last        = P.n_blocks - P.cut_block[1];
     hc.n_blocks      = P.n_blocks;
     hc.last_row0     = A->row_cuts[1];
+    hc.own_lo        = (A->win_hi >= 0 ? (int)A->win_lo : 0) + (hc.left_done ? (int)A->row_cuts[0] : 0);
+    hc.own_hi        = hc.own_lo + (int)A->m;
     if((hc.left_done && (!args.push_left[0] || !args.push_left[1])) || (hc.right_done && (!args.push_right[0] || !args.push_right[1])))
         return aoclsparse_status_invalid_pointer;
     const long long shift = A->win_hi >= 0 ? (long long)A->win_lo : 0;

@@ -31,7 +31,28 @@ namespace b200
         int       n_first, n_last, n_blocks; // blocks in the first boundary, the last boundary, in total
         int       last_begin;                // index of the first block of the last boundary
         int       first_rows, last_row0;     // rows in the first boundary; first row of the last boundary
+        int       own_lo, own_hi;            // columns of x this rank computes itself; the rest of its window is halo
     };
+
+    // acquire / release fence at system scope (lighter than the sequentially consistent __threadfence_system())
+    __device__ __forceinline__ void fence_acq_rel_sys()
+    {
+        asm volatile("fence.acq_rel.sys;" ::: "memory");
+    }
+
+    // x[c] for a BOUNDARY row: halo entries (columns outside the rank's own rows [own_lo, own_hi)) are stored by the peer
+    // GPU while this grid runs -> read at L2 (ld.global.cg), the coherence point those stores arrive at; own entries
+    // take the cached path like interior rows do
+    template <typename T, bool PERSISTENT>
+    __device__ __forceinline__ T boundary_x(const T *x, int c, int own_lo, int own_hi)
+    {
+        if(c < own_lo || c >= own_hi)
+            return __ldcg(x + c);
+        if constexpr(PERSISTENT)
+            return __ldca(x + c);
+        else
+            return ldg_ro(x + c);
+    }
 
     __device__ __forceinline__ bool spin_until(const unsigned *flag, unsigned value, unsigned *timeout)
     {
@@ -46,7 +67,7 @@ namespace b200
                 return false;
             }
         }
-        __threadfence_system();
+        fence_acq_rel_sys(); // acquire: the peer's stores that preceded its flag store are visible from here on
         return true;
     }
 
@@ -192,14 +213,15 @@ namespace b200
                 for(; j + 4 <= e; j += 4)
                 {
                     const int c0 = col_at(r, j), c1 = col_at(r, j + 1), c2 = col_at(r, j + 2), c3 = col_at(r, j + 3);
-                    const T   x0 = __ldcg(x + c0), x1 = __ldcg(x + c1), x2 = __ldcg(x + c2), x3 = __ldcg(x + c3);
+                    const T   x0 = boundary_x<T, false>(x, c0, hc.own_lo, hc.own_hi), x1 = boundary_x<T, false>(x, c1, hc.own_lo, hc.own_hi),
+                            x2 = boundary_x<T, false>(x, c2, hc.own_lo, hc.own_hi), x3 = boundary_x<T, false>(x, c3, hc.own_lo, hc.own_hi);
                     acc          = mad(sval[j], x0, acc);
                     acc          = mad(sval[j + 1], x1, acc);
                     acc          = mad(sval[j + 2], x2, acc);
                     acc          = mad(sval[j + 3], x3, acc);
                 }
                 for(; j < e; ++j)
-                    acc = mad(sval[j], __ldcg(x + col_at(r, j)), acc);
+                    acc = mad(sval[j], boundary_x<T, false>(x, col_at(r, j), hc.own_lo, hc.own_hi), acc);
                 const T out = mul(alpha, acc);
                 y[r]        = out;
                 if(push)
@@ -213,7 +235,7 @@ namespace b200
             __syncthreads();
             if(tid == 0)
             {
-                __threadfence_system(); // this CTA's stores (peer stores included) before the counter / flag
+                fence_acq_rel_sys(); // this CTA's stores (peer stores included) before the counter / flag
                 const unsigned n_side = side == 0 ? (unsigned)hc.n_first : (unsigned)hc.n_last;
                 const unsigned done   = atomicAdd(hc.counters + side, 1u) + 1u;
                 if(done == hc.kc * n_side)
@@ -221,7 +243,7 @@ namespace b200
                     unsigned *flag = side == 0 ? hc.to_left_done : hc.to_right_done;
                     if(flag)
                     {
-                        __threadfence_system();
+                        fence_acq_rel_sys();
                         *reinterpret_cast<volatile unsigned *>(flag) = hc.k;
                     }
                 }
@@ -253,6 +275,7 @@ namespace b200
         unsigned        bar0;     // value of counters[2] before this launch
         int             iters;
         int             n_first, n_last, n_blocks, last_begin, last_row0;
+        int             own_lo, own_hi; // columns of x this rank computes itself; the rest of its window is halo
     };
 
     template <typename T, bool CODED>
@@ -416,14 +439,15 @@ namespace b200
                         for(; j + 4 <= e; j += 4)
                         {
                             const int c0 = col_at(r, j), c1 = col_at(r, j + 1), c2 = col_at(r, j + 2), c3 = col_at(r, j + 3);
-                            const T   v0 = __ldcg(x + c0), v1 = __ldcg(x + c1), v2 = __ldcg(x + c2), v3 = __ldcg(x + c3);
+                            const T   v0 = boundary_x<T, true>(x, c0, hc.own_lo, hc.own_hi), v1 = boundary_x<T, true>(x, c1, hc.own_lo, hc.own_hi),
+                                    v2 = boundary_x<T, true>(x, c2, hc.own_lo, hc.own_hi), v3 = boundary_x<T, true>(x, c3, hc.own_lo, hc.own_hi);
                             acc          = mad(sval[j], v0, acc);
                             acc          = mad(sval[j + 1], v1, acc);
                             acc          = mad(sval[j + 2], v2, acc);
                             acc          = mad(sval[j + 3], v3, acc);
                         }
                         for(; j < e; ++j)
-                            acc = mad(sval[j], __ldcg(x + col_at(r, j)), acc);
+                            acc = mad(sval[j], boundary_x<T, true>(x, col_at(r, j), hc.own_lo, hc.own_hi), acc);
                         const T out = mul(alpha, acc);
                         y[r]        = out;
                         if(push)
@@ -444,7 +468,7 @@ namespace b200
                 }
                 if(done_side != 2 && tid == 0)
                 {
-                    __threadfence_system(); // this CTA's stores (peer stores included) before the counter / flag
+                    fence_acq_rel_sys(); // this CTA's stores (peer stores included) before the counter / flag
                     const unsigned n_side = done_side == 0 ? (unsigned)hc.n_first : (unsigned)hc.n_last;
                     const unsigned cntd   = atomicAdd(hc.counters + done_side, 1u) + 1u;
                     if(cntd == (hc.kc0 + (unsigned)it + 1u) * n_side)
@@ -452,7 +476,7 @@ namespace b200
                         unsigned *flag = done_side == 0 ? hc.to_left_done : hc.to_right_done;
                         if(flag)
                         {
-                            __threadfence_system();
+                            fence_acq_rel_sys();
                             *reinterpret_cast<volatile unsigned *>(flag) = k;
                         }
                     }

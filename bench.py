@@ -60,6 +60,9 @@ WORKLOADS = {
 # diagnostic only (not a BASELINE configuration): the slab one of 8 ranks owns, alone on one GPU, un-sharded
 WORKLOADS["c5slab8"] = dict(name="diagnostic: 512x512x64 slab of c5's grid on one GPU", kind="mv", stencil=(7, 512, 512, 64),
                             prefix="d", alpha=1.0 / 12.0, beta=0.0)
+# diagnostic only: c5's grid with 64 planes per rank at ANY world size (what one of 8 ranks owns at the full size)
+WORKLOADS["c5q"] = dict(name="diagnostic: 7-point stencil 512x512x(64*ranks), row-sharded, 64 planes per rank", kind="mv",
+                        stencil=(7, 512, 512, 64), prefix="d", alpha=1.0 / 12.0, beta=0.0, sharded=True, planes_per_rank=64)
 ELEM = {"s": 4, "d": 8, "c": 8, "z": 16}
 L2_BYTES = 126 * 1000 * 1000
 C5_SAMPLE_PLANES = 64  # CPU arm on c5: the slab one of 8 ranks owns (1/8 of the matrix, 16.8 M rows, 117 M entries)
@@ -427,6 +430,9 @@ def measure(args, key, primary):
     sharded = bool(wl.get("sharded"))
     if sharded:
         pts, nx, ny, nz = wl["stencil"]
+        if wl.get("planes_per_rank"):
+            nz = wl["planes_per_rank"] * world
+            wl = dict(wl, stencil=(pts, nx, ny, nz))
         plane = nx * ny
         slab = sharding.make_slab(nx * ny * nz, world, rank, halo=plane, granularity=plane)
         m, n_glob, nnz, rp, col, val = device_matrix(lib, wl, slab.row_lo, slab.row_hi)
@@ -635,6 +641,27 @@ def measure(args, key, primary):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_per_step = float(t.item()) / steps
 
+    # ---- N > 1: every rank's slab ALONE (plain aoclsparse_dmv on its window, no flags, no peer stores), all ranks at the
+    # same time: separates device-to-device variation and the lock-step with the slowest rank from the cost of the exchange
+    rank_alone_ms = None
+    if sharded and world > 1 and shard is not None:
+        xa = lib.shard_x_ptr(shard) - slab.own_offset * elem
+        ya = torch.empty(m, dtype=tdt, device="cuda")
+        for _ in range(5):
+            assert lib.mv(p, 111, alpha, A, d, xa, beta, ya.data_ptr()) == 0
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(stream)
+        for _ in range(50):
+            assert lib.mv(p, 111, alpha, A, d, xa, beta, ya.data_ptr()) == 0
+        a1.record(stream)
+        barrier()
+        t = torch.tensor([a0.elapsed_time(a1) / 50.0], dtype=torch.float64, device="cuda")
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        rank_alone_ms = [round(float(v.item()), 5) for v in allt]
+        del ya
+
     # ---- launch duration for the roofline: a step is one launch of the dominant kernel (plus, for split rows,
     # the small finish kernel), so the average over the timed region (CUDA events on the launch stream) is the
     # kernel's average launch duration; isolated launches are timed as well and reported beside it
@@ -811,6 +838,10 @@ def measure(args, key, primary):
     }
     if parity is not None:
         out["parity"] = parity
+    if rank_alone_ms is not None:
+        out["rank_alone_ms"] = {"per_rank": rank_alone_ms, "max": max(rank_alone_ms),
+                                "what": "each rank's slab alone (plain aoclsparse_dmv on its window, no exchange), all ranks "
+                                        "concurrently: the lock-step iteration cannot be faster than the slowest of these"}
     return out
 
 
