@@ -56,9 +56,10 @@ class MatrixInfo(C.Structure):
 class MmTilesInfo(C.Structure):
     """aoclsparse_b200_mm_tiles_info (include/aoclsparse_b200.h)"""
     _fields_ = [("state", C.c_int), ("box", C.c_int * 3), ("stride", C.c_longlong * 3), ("dims", C.c_int * 3),
-                ("rows_per_tile", C.c_int), ("n_tiles", C.c_int), ("max_distinct", C.c_int), ("max_len", C.c_int),
-                ("max_runs", C.c_int), ("entries", C.c_longlong), ("n_runs_total", C.c_longlong),
-                ("row_bytes", C.c_longlong), ("reuse", C.c_double), ("fill", C.c_double)]
+                ("rows_per_tile", C.c_int), ("rows_per_group", C.c_int), ("n_tiles", C.c_int), ("max_distinct", C.c_int),
+                ("max_walk", C.c_int), ("max_vals", C.c_int), ("max_runs", C.c_int), ("walk_entries", C.c_longlong),
+                ("val_entries", C.c_longlong), ("n_runs_total", C.c_longlong), ("row_bytes", C.c_longlong),
+                ("reuse", C.c_double), ("fill", C.c_double)]
 
 
 class HaloCtl(C.Structure):
@@ -367,26 +368,26 @@ class AoclSparse:
         st = self.lib.aoclsparse_b200_get_mm_tiles_info(h, C.byref(i))
         assert st == 0, st
         return {"state": i.state, "box": list(i.box), "strides": list(i.stride), "dims": list(i.dims),
-                "rows_per_tile": i.rows_per_tile, "n_tiles": i.n_tiles, "max_distinct": i.max_distinct,
-                "max_len": i.max_len, "max_runs": i.max_runs, "entries": i.entries, "n_runs_total": i.n_runs_total,
+                "rows_per_tile": i.rows_per_tile, "rows_per_group": i.rows_per_group, "n_tiles": i.n_tiles,
+                "max_distinct": i.max_distinct, "max_walk": i.max_walk, "max_vals": i.max_vals, "max_runs": i.max_runs,
+                "walk_entries": i.walk_entries, "val_entries": i.val_entries, "n_runs_total": i.n_runs_total,
                 "row_bytes": i.row_bytes, "reuse": i.reuse, "fill": i.fill}
 
     def mm_tiles(self, h, val_dtype):
-        """host copies of the tile arrays: (info, desc[n_tiles,4], ent_off, val, slot, rows, len, runs[n,2])"""
+        """host copies of the tile arrays: dict(info, desc[n_tiles,4], off[n_tiles,2], walk, val, rows, runs[n,2])"""
         info = self.mm_tiles_info(h)
         assert info["state"] == 2
         nt, rt = info["n_tiles"], info["rows_per_tile"]
         desc = np.zeros((nt, 4), dtype=np.int32)
-        ent = np.zeros(nt, dtype=np.int64)
-        val = np.zeros(info["entries"], dtype=val_dtype)
-        slot = np.zeros(info["entries"], dtype=np.uint16)
+        off = np.zeros((nt, 2), dtype=np.int64)
+        walk = np.zeros(info["walk_entries"], dtype=np.uint32)
+        val = np.zeros(info["val_entries"], dtype=val_dtype)
         rows = np.zeros(nt * rt, dtype=np.int32)
-        ln = np.zeros(nt * rt, dtype=np.uint8)
         runs = np.zeros((info["n_runs_total"], 2), dtype=np.int32)
-        self.lib.aoclsparse_b200_get_mm_tiles.argtypes = [C.c_void_p] * 8
-        st = self.lib.aoclsparse_b200_get_mm_tiles(h, ptr(desc), ptr(ent), ptr(val), ptr(slot), ptr(rows), ptr(ln), ptr(runs))
+        self.lib.aoclsparse_b200_get_mm_tiles.argtypes = [C.c_void_p] * 7
+        st = self.lib.aoclsparse_b200_get_mm_tiles(h, ptr(desc), ptr(off), ptr(walk), ptr(val), ptr(rows), ptr(runs))
         assert st == 0, st
-        return info, desc, ent, val, slot, rows, ln, runs
+        return {"info": info, "desc": desc, "off": off, "walk": walk, "val": val, "rows": rows, "runs": runs}
 
     def get_plan(self, h):
         n = C.c_int32(0)

@@ -383,18 +383,18 @@ namespace b200
         int       box[3]    = {0, 0, 0}; // tile extent along the three grid directions
         long long stride[3] = {0, 0, 0}; // row-index strides of the directions (stride[0] == 1)
         int       dims[3]   = {0, 0, 0}; // grid extent
-        int       rows_per_tile = 0, n_tiles = 0, max_distinct = 0, max_len = 0, max_runs = 0;
+        int       rows_per_tile = 0, n_tiles = 0, max_distinct = 0, max_walk = 0, max_vals = 0, max_runs = 0;
         size_t    row_bytes    = 0; // n * sizeof(T) the box was sized for
-        long long entries      = 0; // ELL slots of all tiles (padding included)
+        long long walk_entries = 0; // slots of all walk planes (padding included)
+        long long val_entries  = 0; // slots of all value planes (padding included)
         long long n_runs_total = 0; // runs of all tiles + one terminator per tile
-        double    reuse = 0.0, fill = 0.0; // stored entries per staged B row; stored entries per ELL slot
-        dev_buf   desc;    // int4 per tile: distinct B rows, runs, longest row, first run
-        dev_buf   ent_off; // long long per tile: first ELL slot
-        dev_buf   val;     // T[entries]:  tile t, plane j, row lr at ent_off[t] + j * rows_per_tile + lr
-        dev_buf   slot;    // unsigned short[entries], same layout: position of the column among the tile's distinct ones
-        dev_buf   rows;    // int[n_tiles * rows_per_tile]: matrix row of (tile, lr) or -1
-        dev_buf   len;     // unsigned char[n_tiles * rows_per_tile]: stored entries of that row
-        dev_buf   runs;    // int2[n_runs_total]: first column, first slot of every run; terminator (-1, distinct)
+        double    reuse = 0.0, fill = 0.0; // stored entries per staged B row; stored entries per value-plane slot
+        dev_buf   desc; // int4 per tile: distinct B rows, runs, U | V << 16 (longest walk / value stream of a group), first run
+        dev_buf   off;  // 2 long long per tile: first walk slot, first value slot
+        dev_buf   walk; // unsigned[walk_entries]: tile t, entry j, group g at off[2t] + j * groups + g: slot | rowmask << 16
+        dev_buf   val;  // T[val_entries]: tile t, i-th value of group g at off[2t+1] + i * groups + g
+        dev_buf   rows; // int[n_tiles * rows_per_tile]: matrix row of (tile, lr) or -1
+        dev_buf   runs; // int2[n_runs_total]: first column, first slot of every run; terminator (-1, distinct)
     };
 
     // one device-resident CSR (always 0-based on the device)

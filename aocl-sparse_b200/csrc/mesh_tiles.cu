@@ -87,7 +87,10 @@ namespace b200
                 }
         }
 
-        // columns of the tile's rows into keys[row * lmax + j]; returns nothing, fills s_info: [0] longest row, [1] rows
+        constexpr int GRP = 2; // rows of a row group: consecutive rows of a tile that share one walk over their columns
+
+        // columns of the tile's rows into keys[row * lmax + j]; s_info: [0] longest row, [1] rows, [4] a row is not
+        // strictly ascending (the group walk needs every row's columns in ascending order, without repeats)
         __device__ void gather_keys(const lattice &g,
                                     int            tile,
                                     int            RT,
@@ -99,7 +102,7 @@ namespace b200
         {
             for(int i = threadIdx.x; i < KCAP; i += TILE_NT)
                 keys[i] = KEY_EMPTY;
-            if(threadIdx.x < 4)
+            if(threadIdx.x < 8)
                 s_info[threadIdx.x] = 0;
             __syncthreads();
             for(int lr = threadIdx.x; lr < RT; lr += TILE_NT)
@@ -110,67 +113,48 @@ namespace b200
                 const int s = rp[r], len = rp[r + 1] - s;
                 atomicMax(&s_info[0], len);
                 atomicAdd(&s_info[1], 1);
+                int prev = -1;
                 for(int j = 0; j < len && j < lmax; ++j)
-                    keys[lr * lmax + j] = col[s + j];
+                {
+                    const int c        = col[s + j];
+                    keys[lr * lmax + j] = c;
+                    if(c <= prev)
+                        s_info[4] = 1;
+                    prev = c;
+                }
             }
             __syncthreads();
         }
 
-        // counts[tile] = {distinct columns, runs, longest row, rows}
-        __global__ void __launch_bounds__(TILE_NT) tile_count_kernel(lattice g,
+        // One CTA per tile.  FILL == false: counts[tile] = {distinct columns, runs, U | V << 16, rows | unusable << 30}
+        // (U / V = longest union walk / value stream of a row group).  FILL == true: writes the tile's arrays.
+        //   distinct columns: the tile's columns sorted, repeats removed (ukeys); a RUN is a maximal stretch of consecutive
+        //   columns, stored as (first column, first slot), the tile's list closed by (-1, distinct).
+        //   row group grp = rows GRP*grp .. GRP*grp+GRP-1 of the tile: its WALK is the ascending list of the columns at
+        //   least one of its rows stores, each as slot | rowmask << 16; its VALUE STREAM holds, walk entry by walk entry
+        //   and row by row (ascending), the stored values.  Both are laid out as planes over the groups:
+        //   walk[j][grp] at sm_off + j*NG + grp (zero = padding), val[i][grp] at val_off + i*NG + grp.
+        template <int ES, bool FILL>
+        __global__ void __launch_bounds__(TILE_NT) tile_build_kernel(lattice g,
                                                                      int     RT,
                                                                      int     lmax,
                                                                      const aoclsparse_int *__restrict__ rp,
                                                                      const aoclsparse_int *__restrict__ col,
-                                                                     int4 *counts)
-        {
-            __shared__ int keys[KCAP];
-            __shared__ int s_info[4];
-            const int      tile = blockIdx.x;
-            gather_keys(g, tile, RT, lmax, rp, col, keys, s_info);
-            sort_keys(keys);
-            int distinct = 0, runs = 0;
-            for(int i = threadIdx.x; i < KCAP; i += TILE_NT)
-            {
-                const int k = keys[i];
-                if(k == KEY_EMPTY)
-                    continue;
-                const int prev = i > 0 ? keys[i - 1] : KEY_EMPTY;
-                if(i == 0 || k != prev)
-                {
-                    ++distinct;
-                    if(i == 0 || k != prev + 1)
-                        ++runs;
-                }
-            }
-            atomicAdd(&s_info[2], distinct);
-            atomicAdd(&s_info[3], runs);
-            __syncthreads();
-            if(threadIdx.x == 0)
-                counts[tile] = make_int4(s_info[2], s_info[3], s_info[0], s_info[1]);
-        }
-
-        // the tile's ELL planes, slots, row list and runs.  ES = sizeof(value)
-        template <int ES>
-        __global__ void __launch_bounds__(TILE_NT) tile_fill_kernel(lattice g,
-                                                                    int     RT,
-                                                                    int     lmax,
-                                                                    const aoclsparse_int *__restrict__ rp,
-                                                                    const aoclsparse_int *__restrict__ col,
-                                                                    const unsigned char *__restrict__ val,
-                                                                    const int4 *__restrict__ tdesc,
-                                                                    const long long *__restrict__ tent,
-                                                                    unsigned char  *tval,
-                                                                    unsigned short *tslot,
-                                                                    int            *trows,
-                                                                    unsigned char  *tlen,
-                                                                    int2           *truns)
+                                                                     const unsigned char *__restrict__ val,
+                                                                     int4 *counts,
+                                                                     const int4 *__restrict__ tdesc,
+                                                                     const long long *__restrict__ toff,
+                                                                     unsigned      *twalk,
+                                                                     unsigned char *tval,
+                                                                     int           *trows,
+                                                                     int2          *truns)
         {
             __shared__ int keys[KCAP];
             __shared__ int ukeys[KCAP];
-            __shared__ int s_info[4];
+            __shared__ int s_info[8];
             __shared__ int s_scan[TILE_NT + 1], s_rscan[TILE_NT + 1];
             const int      tile = blockIdx.x, tid = threadIdx.x;
+            const int      NG   = RT / GRP;
             gather_keys(g, tile, RT, lmax, rp, col, keys, s_info);
             sort_keys(keys);
             // compaction: thread t owns keys[t*PER, (t+1)*PER)
@@ -201,7 +185,10 @@ namespace b200
                     s_rscan[t] += s_rscan[t - 1];
                 }
             __syncthreads();
-            const int4 d = tdesc[tile]; // {distinct, runs, longest row, first run}
+            const int n_distinct = s_scan[TILE_NT], n_runs = s_rscan[TILE_NT];
+            int4      d          = make_int4(0, 0, 0, 0);
+            if(FILL)
+                d = tdesc[tile]; // {distinct, runs, U | V << 16, first run}
             {
                 int u = s_scan[tid], rn = s_rscan[tid];
                 for(int q = 0; q < PER; ++q)
@@ -214,34 +201,47 @@ namespace b200
                     {
                         ukeys[u] = k;
                         if(i == 0 || k != prev + 1)
-                            truns[d.w + rn++] = make_int2(k, u); // first column of the run, its first slot
+                        {
+                            if(FILL)
+                                truns[d.w + rn] = make_int2(k, u); // first column of the run, its first slot
+                            ++rn;
+                        }
                         ++u;
                     }
                 }
             }
-            if(tid == 0)
-                truns[d.w + d.y] = make_int2(-1, d.x); // terminator: the slot one past the last run
+            if(FILL && tid == 0)
+                truns[d.w + n_runs] = make_int2(-1, n_distinct); // terminator: the slot one past the last run
             __syncthreads();
-            const int       n_distinct = d.x, L = d.z;
-            const long long base       = tent[tile];
-            for(int lr = tid; lr < RT; lr += TILE_NT)
+            // one thread per row group: k-way merge of its rows' (strictly ascending) column lists
+            const int       Ut = FILL ? (d.z & 0xffff) : 0, Vt = FILL ? (int)((unsigned)d.z >> 16) : 0;
+            const long long sm_off = FILL ? toff[2 * tile] : 0, val_off = FILL ? toff[2 * tile + 1] : 0;
+            for(int grp = tid; grp < NG; grp += TILE_NT)
             {
-                const long long r = tile_row(g, tile, lr);
-                trows[(long long)tile * RT + lr] = (int)r;
-                int s = 0, len = 0;
-                if(r >= 0)
+                int U = 0, V = 0;
+                int start[GRP], len[GRP], used[GRP];
+                for(int i = 0; i < GRP; ++i)
                 {
-                    s   = rp[r];
-                    len = rp[r + 1] - s;
+                    const long long r = tile_row(g, tile, grp * GRP + i);
+                    start[i]          = r >= 0 ? rp[r] : 0;
+                    len[i]            = r >= 0 ? min(rp[r + 1] - rp[r], lmax) : 0;
+                    used[i]           = 0;
                 }
-                tlen[(long long)tile * RT + lr] = (unsigned char)len;
-                for(int j = 0; j < L; ++j)
+                for(;;)
                 {
-                    const long long e = base + (long long)j * RT + lr;
-                    if(j < len)
+                    int c = KEY_EMPTY;
+                    for(int i = 0; i < GRP; ++i)
+                        if(used[i] < len[i])
+                            c = min(c, col[start[i] + used[i]]);
+                    if(c == KEY_EMPTY)
+                        break;
+                    unsigned m = 0;
+                    for(int i = 0; i < GRP; ++i)
+                        if(used[i] < len[i] && col[start[i] + used[i]] == c)
+                            m |= 1u << i;
+                    if(FILL)
                     {
-                        const int c  = col[s + j];
-                        int       lo = 0, hi = n_distinct - 1;
+                        int lo = 0, hi = n_distinct - 1;
                         while(lo < hi)
                         {
                             const int mid = (lo + hi) >> 1;
@@ -250,17 +250,44 @@ namespace b200
                             else
                                 hi = mid;
                         }
-                        tslot[e] = (unsigned short)lo;
-                        for(int b = 0; b < ES; b += 4)
-                            *reinterpret_cast<unsigned *>(tval + e * ES + b) = *reinterpret_cast<const unsigned *>(val + (long long)(s + j) * ES + b);
+                        twalk[sm_off + (long long)U * NG + grp] = (unsigned)lo | (m << 16);
                     }
-                    else
-                    {
-                        tslot[e] = 0;
-                        for(int b = 0; b < ES; b += 4)
-                            *reinterpret_cast<unsigned *>(tval + e * ES + b) = 0u;
-                    }
+                    for(int i = 0; i < GRP; ++i)
+                        if(m & (1u << i))
+                        {
+                            if(FILL)
+                            {
+                                const long long src = (long long)(start[i] + used[i]) * ES, dst = (val_off + (long long)V * NG + grp) * ES;
+                                for(int b = 0; b < ES; b += 4)
+                                    *reinterpret_cast<unsigned *>(tval + dst + b) = *reinterpret_cast<const unsigned *>(val + src + b);
+                            }
+                            ++used[i];
+                            ++V;
+                        }
+                    ++U;
                 }
+                if(FILL)
+                {
+                    for(int j = U; j < Ut; ++j)
+                        twalk[sm_off + (long long)j * NG + grp] = 0u;
+                    for(int i = V; i < Vt; ++i)
+                        for(int b = 0; b < ES; b += 4)
+                            *reinterpret_cast<unsigned *>(tval + (val_off + (long long)i * NG + grp) * ES + b) = 0u;
+                }
+                else
+                {
+                    atomicMax(&s_info[5], U);
+                    atomicMax(&s_info[6], V);
+                }
+            }
+            if(FILL)
+                for(int lr = tid; lr < RT; lr += TILE_NT)
+                    trows[(long long)tile * RT + lr] = (int)tile_row(g, tile, lr);
+            __syncthreads();
+            if(!FILL && tid == 0)
+            {
+                const int bad = (s_info[4] || s_info[0] > lmax) ? 1 : 0;
+                counts[tile]  = make_int4(n_distinct, n_runs, s_info[5] | (s_info[6] << 16), s_info[1] | (bad << 30));
             }
         }
 
@@ -279,22 +306,25 @@ namespace b200
 
         // PERSISTENT, DOUBLE BUFFERED, WARP SPECIALISED: a CTA (one per SM) walks tiles blockIdx.x, blockIdx.x + gridDim.x,
         // ...  Its last warp is the PRODUCER: for every tile it waits until the staging buffer is empty, announces the
-        // tile's byte count on the buffer's "full" mbarrier and issues the TMA copies (val / slot planes, row list, one copy
-        // per run of B rows).  The other warps are CONSUMERS: wait for "full", multiply out of shared memory, store their
-        // part of C, and arrive (one lane per warp) on the buffer's "empty" mbarrier.  No CTA-wide barrier: a warp that
+        // tile's byte count on the buffer's "full" mbarrier and issues the TMA copies (walk / value planes, row list, one
+        // copy per run of B rows).  The other warps are CONSUMERS: wait for "full", multiply out of shared memory, arrive
+        // (one lane per warp) on the buffer's "empty" mbarrier, store their part of C.  No CTA-wide barrier: a warp that
         // finishes a tile early starts the next one while the others still multiply or store, and the copies of tile i+1
         // overlap the multiply of tile i.
-        // consumer thread (row, h): CH of the W = TPR * CH 16-byte chunks of output row `row`, namely (CH*h + k + row) mod W
-        // for k < CH -- a rotation by `row`, so the 8 lanes of a quarter-warp (8 consecutive rows, same h and k) read 8
-        // different bank groups of shared memory whatever B rows (slots) they look at
-        template <typename T, int TPR, int CH>
-        __global__ void __launch_bounds__(RT_MAX * TPR + 32, 1)
+        // A TEAM of 8 lanes (a quarter-warp) owns one row group: lane h holds the 16-byte chunks h, h+8, ... of the GRP
+        // output rows.  Per walk entry the team reads ONE B row out of shared memory (8 lanes x 16 bytes = one 128-byte
+        // wavefront per chunk index, conflict-free) and uses it for every row of the group that stores that column: B rows
+        // are re-used in registers across the rows of a group (a 27-point stencil: 36 B-row reads per 2 rows instead of 54).
+        // Values are broadcast loads (the 8 lanes of a team read the same address).
+        // Every output entry is formed by the multiply-adds of its row in ascending column order, the order the row-block
+        // kernel uses for sorted rows: identical bits.
+        template <typename T, int CH>
+        __global__ void __launch_bounds__(RT_MAX / GRP * 8 + 32, 1)
             csrmm_mesh_tiles_kernel(const int4 *__restrict__ tdesc,
-                                    const long long *__restrict__ tent,
+                                    const long long *__restrict__ toff,
+                                    const unsigned *__restrict__ twalk,
                                     const T *__restrict__ tval,
-                                    const unsigned short *__restrict__ tslot,
                                     const int *__restrict__ trows,
-                                    const unsigned char *__restrict__ tlen,
                                     const int2 *__restrict__ truns,
                                     const T *__restrict__ B,
                                     long long ldb,
@@ -303,7 +333,8 @@ namespace b200
                                     int       n_tiles,
                                     int       RT,
                                     int       btile_rows, // rows of a staged B tile buffer
-                                    int       max_len,
+                                    int       max_walk,
+                                    int       max_vals,
                                     int       n_buf,      // staging buffers: 2, or 1 when two do not fit
                                     T         alpha,
                                     T         beta,
@@ -311,16 +342,17 @@ namespace b200
                                     int       b_contiguous)
         {
             constexpr int VEC       = chunk16<T>::N;
-            constexpr int W         = TPR * CH; // 16-byte chunks per B / C row
+            constexpr int W         = 8 * CH; // 16-byte chunks per B / C row
             constexpr int ROW_BYTES = W * 16;
             extern __shared__ __align__(128) unsigned char smem_raw[];
-            uint64_t    *full     = reinterpret_cast<uint64_t *>(smem_raw);      // full[0], full[1]
-            uint64_t    *empty    = reinterpret_cast<uint64_t *>(smem_raw) + 2;  // empty[0], empty[1]
-            const size_t a_bytes  = (size_t)max_len * RT * (sizeof(T) + 2) + (size_t)RT * 5;
-            const size_t buf_size = ((size_t)btile_rows * ROW_BYTES + a_bytes + 127) & ~(size_t)127;
+            uint64_t    *full     = reinterpret_cast<uint64_t *>(smem_raw);     // full[0], full[1]
+            uint64_t    *empty    = reinterpret_cast<uint64_t *>(smem_raw) + 2; // empty[0], empty[1]
+            const int    NG       = RT / GRP;
+            const size_t walk_b   = (size_t)max_walk * NG * 4, vals_b = (size_t)max_vals * NG * sizeof(T);
+            const size_t buf_size = ((size_t)btile_rows * ROW_BYTES + walk_b + vals_b + (size_t)RT * 4 + 127) & ~(size_t)127;
             auto         btile_of = [&](int q) { return smem_raw + 128 + (size_t)q * buf_size; };
 
-            const int tid = threadIdx.x, n_cons = RT * TPR, lane = tid & 31;
+            const int tid = threadIdx.x, n_cons = NG * 8, lane = tid & 31;
             const int stride = (int)gridDim.x;
             if(tid == 0)
             {
@@ -342,25 +374,22 @@ namespace b200
                     const int u = n_buf == 2 ? (it >> 1) : it; // how often buffer q has been used before
                     if(u > 0)
                         mbar_wait(empty + q, (unsigned)(u - 1) & 1u);
-                    unsigned char  *btile = btile_of(q);
-                    T              *sval  = reinterpret_cast<T *>(btile + (size_t)btile_rows * ROW_BYTES);
-                    unsigned short *sslot = reinterpret_cast<unsigned short *>(reinterpret_cast<unsigned char *>(sval) + (size_t)max_len * RT * sizeof(T));
-                    int            *srows = reinterpret_cast<int *>(reinterpret_cast<unsigned char *>(sslot) + (size_t)max_len * RT * 2);
-                    unsigned char  *slen  = reinterpret_cast<unsigned char *>(srows + RT);
-                    const int4      d     = tdesc[tile]; // {distinct, runs, longest row, first run}
+                    unsigned char *btile = btile_of(q);
+                    unsigned      *swalk = reinterpret_cast<unsigned *>(btile + (size_t)btile_rows * ROW_BYTES);
+                    T             *sval  = reinterpret_cast<T *>(reinterpret_cast<unsigned char *>(swalk) + walk_b);
+                    int           *srows = reinterpret_cast<int *>(reinterpret_cast<unsigned char *>(sval) + vals_b);
+                    const int4     d     = tdesc[tile]; // {distinct, runs, U | V << 16, first run}
                     if(lane == 0)
                     {
-                        const long long base  = tent[tile];
-                        const int       L     = d.z;
-                        const unsigned  total = (unsigned)d.x * ROW_BYTES + (unsigned)(L * RT) * (unsigned)(sizeof(T) + 2) + (unsigned)RT * 5u;
+                        const long long sm_off = toff[2 * tile], val_off = toff[2 * tile + 1];
+                        const unsigned  U = (unsigned)d.z & 0xffffu, V = (unsigned)d.z >> 16;
+                        const unsigned  total = (unsigned)d.x * ROW_BYTES + U * (unsigned)NG * 4u + V * (unsigned)NG * (unsigned)sizeof(T) + (unsigned)RT * 4u;
                         mbar_expect_tx(full + q, total);
-                        if(L > 0)
-                        {
-                            bulk_load_stream(sval, tval + base, (unsigned)(L * RT * sizeof(T)), full + q);
-                            bulk_load_stream(sslot, tslot + base, (unsigned)(L * RT * 2), full + q);
-                        }
+                        if(U > 0)
+                            bulk_load_stream(swalk, twalk + sm_off, U * (unsigned)NG * 4u, full + q);
+                        if(V > 0)
+                            bulk_load_stream(sval, tval + val_off, V * (unsigned)NG * (unsigned)sizeof(T), full + q);
                         bulk_load_stream(srows, trows + (long long)tile * RT, (unsigned)(RT * 4), full + q);
-                        bulk_load_stream(slen, tlen + (long long)tile * RT, (unsigned)RT, full + q);
                     }
                     __syncwarp(); // the byte count is announced before any other lane's copy can complete
                     // B rows: one bulk copy per run of consecutive columns (per row when B's rows are not adjacent in memory)
@@ -378,62 +407,84 @@ namespace b200
                 return;
             }
 
-            // ---------------- consumer warps
-            const int r = tid % RT, h = tid / RT;
-            unsigned  off[CH];
-#pragma unroll
-            for(int k = 0; k < CH; ++k)
-                off[k] = (unsigned)((CH * h + k + r) % W) * 16u;
-            int it = 0;
+            // ---------------- consumer warps: team = tid / 8 owns row group `team`, lane h = tid % 8
+            const int grp = tid >> 3, h = tid & 7;
+            int       it  = 0;
             for(int tile = (int)blockIdx.x; tile < n_tiles; tile += stride, ++it)
             {
-                const int             q     = n_buf == 2 ? (it & 1) : 0;
-                const int             u     = n_buf == 2 ? (it >> 1) : it;
-                const unsigned char  *btile = btile_of(q);
-                const T              *sval  = reinterpret_cast<const T *>(btile + (size_t)btile_rows * ROW_BYTES);
-                const unsigned short *sslot = reinterpret_cast<const unsigned short *>(reinterpret_cast<const unsigned char *>(sval) + (size_t)max_len * RT * sizeof(T));
-                const int            *srows = reinterpret_cast<const int *>(reinterpret_cast<const unsigned char *>(sslot) + (size_t)max_len * RT * 2);
-                const unsigned char  *slen  = reinterpret_cast<const unsigned char *>(srows + RT);
+                const int            q     = n_buf == 2 ? (it & 1) : 0;
+                const int            u     = n_buf == 2 ? (it >> 1) : it;
+                const unsigned char *btile = btile_of(q);
+                const unsigned      *swalk = reinterpret_cast<const unsigned *>(btile + (size_t)btile_rows * ROW_BYTES);
+                const T             *sval  = reinterpret_cast<const T *>(reinterpret_cast<const unsigned char *>(swalk) + walk_b);
+                const int           *srows = reinterpret_cast<const int *>(reinterpret_cast<const unsigned char *>(sval) + vals_b);
+                const int            U     = tdesc[tile].z & 0xffff;
                 mbar_wait(full + q, (unsigned)u & 1u);
 
-                const int  len = slen[r];
-                const int  row = srows[r];
-                chunk16<T> acc[CH];
+                int rows[GRP];
 #pragma unroll
-                for(int k = 0; k < CH; ++k)
+                for(int i = 0; i < GRP; ++i)
+                    rows[i] = srows[grp * GRP + i];
+                chunk16<T> acc[GRP][CH];
 #pragma unroll
-                    for(int qq = 0; qq < VEC; ++qq)
-                        acc[k].v[qq] = vt<T>::zero();
-                for(int j = 0; j < len; ++j)
-                {
-                    const T              v    = sval[j * RT + r];
-                    const unsigned char *rowp = btile + (size_t)sslot[j * RT + r] * ROW_BYTES;
-                    chunk16<T>           x[CH];
-#pragma unroll
-                    for(int k = 0; k < CH; ++k)
-                        x[k] = *reinterpret_cast<const chunk16<T> *>(rowp + off[k]);
+                for(int i = 0; i < GRP; ++i)
 #pragma unroll
                     for(int k = 0; k < CH; ++k)
 #pragma unroll
                         for(int qq = 0; qq < VEC; ++qq)
-                            acc[k].v[qq] = mad(v, x[k].v[qq], acc[k].v[qq]);
+                            acc[i][k].v[qq] = vt<T>::zero();
+                const unsigned      *wp = swalk + grp;
+                const T             *vp = sval + grp;
+                const unsigned char *bh = btile + h * 16;
+                unsigned             w  = U > 0 ? wp[0] : 0u;
+                for(int j = 0; j < U; ++j)
+                {
+                    const unsigned m = w >> 16;
+                    if(m == 0)
+                        break; // padding: this group's walk is over
+                    const unsigned char *rowp = bh + (size_t)(w & 0xffffu) * ROW_BYTES;
+                    w                         = j + 1 < U ? wp[(j + 1) * NG] : 0u; // next walk entry, in flight during the multiply-adds
+                    chunk16<T> x[CH];
+#pragma unroll
+                    for(int k = 0; k < CH; ++k)
+                        x[k] = *reinterpret_cast<const chunk16<T> *>(rowp + k * 128);
+                    // the values of this entry sit at vp[0 .. popc(m)) (plane stride NG), in row order; loads past the
+                    // group's stream stay inside the staging buffer and are never used
+                    T v[GRP];
+#pragma unroll
+                    for(int i = 0; i < GRP; ++i)
+                        v[i] = vp[__popc(m & ((1u << i) - 1u)) * NG];
+                    vp += __popc(m) * NG;
+#pragma unroll
+                    for(int i = 0; i < GRP; ++i)
+                        if(m & (1u << i))
+                        {
+#pragma unroll
+                            for(int k = 0; k < CH; ++k)
+#pragma unroll
+                                for(int qq = 0; qq < VEC; ++qq)
+                                    acc[i][k].v[qq] = mad(v[i], x[k].v[qq], acc[i][k].v[qq]);
+                        }
                 }
                 // this warp is done with the buffer
                 __syncwarp();
                 if(lane == 0)
                     mbar_arrive(empty + q);
-                // the thread's CH chunks of C row `row`, straight from registers (16-byte stores; L2 merges the sectors)
-                if(row >= 0)
+                // the team's rows of C: 8 lanes x 16 bytes = 128 contiguous bytes per store
+#pragma unroll
+                for(int i = 0; i < GRP; ++i)
                 {
-                    T *crow = C + (long long)row * ldc;
+                    if(rows[i] < 0)
+                        continue;
+                    T *crow = C + (long long)rows[i] * ldc;
 #pragma unroll
                     for(int k = 0; k < CH; ++k)
                     {
-                        T         *cp = crow + (off[k] / 16u) * VEC;
+                        T         *cp = crow + (h + 8 * k) * VEC;
                         chunk16<T> o;
 #pragma unroll
                         for(int qq = 0; qq < VEC; ++qq)
-                            o.v[qq] = mul(alpha, acc[k].v[qq]);
+                            o.v[qq] = mul(alpha, acc[i][k].v[qq]);
                         if(!beta_zero)
                         {
                             const chunk16<T> old = *reinterpret_cast<const chunk16<T> *>(cp);
@@ -447,14 +498,15 @@ namespace b200
             }
         }
 
-        // one staging buffer (B tile + the tile's val / slot planes, row list, row lengths), rounded to 128 bytes
-        size_t tile_buffer_bytes(int RT, int max_distinct, int max_len, size_t row_bytes, size_t elem_size)
+        // one staging buffer (B tile + the tile's walk / value planes + row list), rounded to 128 bytes
+        size_t tile_buffer_bytes(int RT, int max_distinct, int max_walk, int max_vals, size_t row_bytes, size_t elem_size)
         {
-            return ((size_t)max_distinct * row_bytes + (size_t)max_len * RT * (elem_size + 2) + (size_t)RT * 5 + 127) & ~(size_t)127;
+            const size_t NG = (size_t)RT / GRP;
+            return ((size_t)max_distinct * row_bytes + (size_t)max_walk * NG * 4 + (size_t)max_vals * NG * elem_size + (size_t)RT * 4 + 127) & ~(size_t)127;
         }
-        size_t tile_smem_bytes(int RT, int max_distinct, int max_len, size_t row_bytes, size_t elem_size)
+        size_t tile_smem_bytes(int RT, int max_distinct, int max_walk, int max_vals, size_t row_bytes, size_t elem_size)
         {
-            return 128 + tile_buffer_bytes(RT, max_distinct, max_len, row_bytes, elem_size);
+            return 128 + tile_buffer_bytes(RT, max_distinct, max_walk, max_vals, row_bytes, elem_size);
         }
     }
 
@@ -543,7 +595,9 @@ namespace b200
     namespace
     {
         // box extents for a grid of `ndim` directions: X = 8 along the unit-stride direction, (Y, Z) the pair with the
-        // fewest distinct B rows per matrix row (estimated with a one-point halo) whose tile fits `budget` bytes
+        // fewest distinct B rows per matrix row (estimated with a one-point halo) whose tile fits `budget` bytes; the walk
+        // of a row group is estimated as max_len * (GRP + 2) / 3 entries (a row of a radius-1 stencil shares two thirds of
+        // its columns with its neighbour), its value stream as GRP * max_len
         void choose_box(int ndim, int nx, int ny, int nz, int max_len, size_t row_bytes, size_t elem_size, size_t budget, int box[3])
         {
             if(ndim == 1)
@@ -559,6 +613,7 @@ namespace b200
             box[2]          = 1;
             const int ys[]  = {1, 2, 4, 8, 16};
             const int zs[]  = {1, 2, 3, 4, 6, 8};
+            const int walk  = (max_len * (GRP + 2) + 2) / 3, vals = GRP * max_len;
             for(int Y : ys)
                 for(int Z : zs)
                 {
@@ -570,7 +625,7 @@ namespace b200
                     if(Y > std::max(ny, 1) * 2 || Z > std::max(nz, 1) * 2)
                         continue;
                     const int    distinct = (X + 2) * (Y + 2) * (ndim == 3 ? Z + 2 : 1);
-                    const size_t smem     = tile_smem_bytes(RT, distinct, max_len, row_bytes, elem_size);
+                    const size_t smem     = tile_smem_bytes(RT, distinct, walk, vals, row_bytes, elem_size);
                     if(smem > budget)
                         continue;
                     const double cost = (double)distinct / RT;
@@ -586,7 +641,7 @@ namespace b200
 
     size_t mesh_tiles_smem(const mesh_tiles &M, size_t row_bytes, size_t elem_size)
     {
-        return tile_smem_bytes(M.rows_per_tile, M.max_distinct, M.max_len, row_bytes, elem_size);
+        return tile_smem_bytes(M.rows_per_tile, M.max_distinct, M.max_walk, M.max_vals, row_bytes, elem_size);
     }
 
     aoclsparse_status build_mesh_tiles(const dev_csr &A, size_t elem_size, size_t row_bytes, cudaStream_t st)
@@ -605,7 +660,7 @@ namespace b200
         int       ndim = 0;
         if(!detect_lattice(offs, A.m, s1, s2, ndim))
             return aoclsparse_status_success;
-        // longest row: the offsets are distinct per row, so their number bounds it
+        // longest row: the offsets are distinct per row (rows without repeated columns), so their number bounds it
         const int lmax = (int)offs.size();
         if(lmax > 64)
             return aoclsparse_status_success;
@@ -631,9 +686,9 @@ namespace b200
                 box[2] = c;
             }
         }
-        dev_buf             d_counts;
-        std::vector<int4>   counts;
-        int                 RT = 0;
+        dev_buf           d_counts;
+        std::vector<int4> counts;
+        int               RT = 0;
         for(int attempt = 0; attempt < 4; ++attempt)
         {
             g.X = box[0];
@@ -642,34 +697,40 @@ namespace b200
             RT  = g.X * g.Y * g.Z;
             if(RT % 32 != 0 || RT > RT_MAX || (long long)RT * lmax > KCAP)
                 return aoclsparse_status_success;
-            g.tx                = (g.nx + g.X - 1) / g.X;
-            g.ty                = (g.ny + g.Y - 1) / g.Y;
-            g.tz                = (g.nz + g.Z - 1) / g.Z;
-            const long long nt  = (long long)g.tx * g.ty * g.tz;
+            g.tx               = (g.nx + g.X - 1) / g.X;
+            g.ty               = (g.ny + g.Y - 1) / g.Y;
+            g.tz               = (g.nz + g.Z - 1) / g.Z;
+            const long long nt = (long long)g.tx * g.ty * g.tz;
             if(nt <= 0 || nt > (1ll << 30))
                 return aoclsparse_status_success;
             B200_TRY(d_counts.alloc(sizeof(int4) * (size_t)nt));
-            tile_count_kernel<<<(unsigned)nt, TILE_NT, 0, st>>>(g, RT, lmax, A.row_ptr.as<aoclsparse_int>(), A.col_idx.as<aoclsparse_int>(), d_counts.as<int4>());
+            tile_build_kernel<4, false><<<(unsigned)nt, TILE_NT, 0, st>>>(g, RT, lmax, A.row_ptr.as<aoclsparse_int>(),
+                                                                          A.col_idx.as<aoclsparse_int>(), nullptr, d_counts.as<int4>(),
+                                                                          nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
             B200_LAUNCHED();
             counts.resize((size_t)nt);
             B200_CUDA(cudaMemcpyAsync(counts.data(), d_counts.p, sizeof(int4) * (size_t)nt, cudaMemcpyDeviceToHost, st));
             B200_CUDA(cudaStreamSynchronize(st));
-            int       max_d = 0, max_l = 0, max_r = 0;
+            int       max_d = 0, max_u = 0, max_v = 0, max_r = 0, bad = 0;
             long long rows = 0;
             for(const int4 &c : counts)
             {
                 max_d = std::max(max_d, c.x);
                 max_r = std::max(max_r, c.y);
-                max_l = std::max(max_l, c.z);
-                rows += c.w;
+                max_u = std::max(max_u, c.z & 0xffff);
+                max_v = std::max(max_v, (int)((unsigned)c.z >> 16));
+                rows += c.w & 0x3fffffff;
+                bad |= c.w >> 30;
             }
-            if(rows != A.m || max_l > lmax || max_d > 65535)
-                return aoclsparse_status_success; // not a partition of the rows / a row longer than the offset table: no tiles
+            // not a partition of the rows, a row that is not strictly ascending or longer than the offset table: no tiles
+            if(rows != A.m || bad || max_d > 65535)
+                return aoclsparse_status_success;
             M.max_distinct = max_d;
-            M.max_len      = max_l;
+            M.max_walk     = max_u;
+            M.max_vals     = max_v;
             M.max_runs     = max_r;
             M.n_tiles      = (int)nt;
-            if(tile_smem_bytes(RT, max_d, max_l, row_bytes, elem_size) <= budget)
+            if(tile_smem_bytes(RT, max_d, max_u, max_v, row_bytes, elem_size) <= budget)
                 break;
             // the real tiles need more than the estimate: halve the box along its last direction that is > 1
             if(box[2] > 1)
@@ -691,51 +752,54 @@ namespace b200
         M.dims[1]       = g.ny;
         M.dims[2]       = g.nz;
         M.rows_per_tile = RT;
+        const int NG    = RT / GRP;
         // staging is only worth it when a tile re-uses its B rows: distinct rows per matrix row well below the row length
         {
-            double sum_d = 0, sum_e = 0;
+            double sum_d = 0, sum_v = 0;
             for(const int4 &c : counts)
             {
                 sum_d += c.x;
-                sum_e += (double)c.z * RT;
+                sum_v += (double)((unsigned)c.z >> 16) * NG;
             }
-            M.entries = (long long)sum_e;
-            const double reuse = (double)A.nnz / std::max(1.0, sum_d);  // stored entries per staged B row
-            const double fill  = (double)A.nnz / std::max(1.0, sum_e);  // ELL fill of the tiles
+            const double reuse = (double)A.nnz / std::max(1.0, sum_d); // stored entries per staged B row
+            const double fill  = (double)A.nnz / std::max(1.0, sum_v); // stored entries per slot of the value planes
             M.reuse            = reuse;
             M.fill             = fill;
             if(reuse < 3.0 || fill < 0.7)
                 return aoclsparse_status_success;
         }
-        // per-tile descriptors: {distinct, runs, longest row, first run (+1 terminator per tile)}, first ELL slot
+        // per-tile descriptors: {distinct, runs, U | V << 16, first run (+1 terminator per tile)}; first walk / value slot
         std::vector<int4>      hdesc(counts.size());
-        std::vector<long long> hent(counts.size());
-        long long              ent = 0, run = 0;
+        std::vector<long long> hoff(2 * counts.size());
+        long long              walk = 0, vals = 0, run = 0;
         for(size_t t = 0; t < counts.size(); ++t)
         {
-            hdesc[t] = make_int4(counts[t].x, counts[t].y, counts[t].z, (int)run);
-            hent[t]  = ent;
-            ent += (long long)counts[t].z * RT;
+            hdesc[t]        = make_int4(counts[t].x, counts[t].y, counts[t].z, (int)run);
+            hoff[2 * t]     = walk;
+            hoff[2 * t + 1] = vals;
+            walk += (long long)(counts[t].z & 0xffff) * NG;
+            vals += (long long)((unsigned)counts[t].z >> 16) * NG;
             run += counts[t].y + 1;
             if(run > INT_MAX - 4096)
                 return aoclsparse_status_success;
         }
+        M.walk_entries = walk;
+        M.val_entries  = vals;
         B200_TRY(M.desc.alloc(sizeof(int4) * hdesc.size()));
-        B200_TRY(M.ent_off.alloc(sizeof(long long) * hent.size()));
-        B200_TRY(M.val.alloc((size_t)std::max<long long>(ent, 1) * elem_size));
-        B200_TRY(M.slot.alloc((size_t)std::max<long long>(ent, 1) * 2));
+        B200_TRY(M.off.alloc(sizeof(long long) * hoff.size()));
+        B200_TRY(M.walk.alloc((size_t)std::max<long long>(walk, 1) * 4));
+        B200_TRY(M.val.alloc((size_t)std::max<long long>(vals, 1) * elem_size));
         B200_TRY(M.rows.alloc(sizeof(int) * (size_t)M.n_tiles * RT));
-        B200_TRY(M.len.alloc((size_t)M.n_tiles * RT));
         B200_TRY(M.runs.alloc(sizeof(int2) * (size_t)run));
         M.n_runs_total = run;
         B200_CUDA(cudaMemcpyAsync(M.desc.p, hdesc.data(), sizeof(int4) * hdesc.size(), cudaMemcpyHostToDevice, st));
-        B200_CUDA(cudaMemcpyAsync(M.ent_off.p, hent.data(), sizeof(long long) * hent.size(), cudaMemcpyHostToDevice, st));
-#define B200_TILE_FILL(ES)                                                                                                  \
-    tile_fill_kernel<ES><<<(unsigned)M.n_tiles, TILE_NT, 0, st>>>(g, RT, lmax, A.row_ptr.as<aoclsparse_int>(),            \
-                                                                    A.col_idx.as<aoclsparse_int>(), A.val.as<unsigned char>(), \
-                                                                    M.desc.as<int4>(), M.ent_off.as<long long>(),           \
-                                                                    M.val.as<unsigned char>(), M.slot.as<unsigned short>(), \
-                                                                    M.rows.as<int>(), M.len.as<unsigned char>(), M.runs.as<int2>())
+        B200_CUDA(cudaMemcpyAsync(M.off.p, hoff.data(), sizeof(long long) * hoff.size(), cudaMemcpyHostToDevice, st));
+#define B200_TILE_FILL(ES)                                                                                                      \
+    tile_build_kernel<ES, true><<<(unsigned)M.n_tiles, TILE_NT, 0, st>>>(g, RT, lmax, A.row_ptr.as<aoclsparse_int>(),          \
+                                                                          A.col_idx.as<aoclsparse_int>(), A.val.as<unsigned char>(), \
+                                                                          nullptr, M.desc.as<int4>(), M.off.as<long long>(),      \
+                                                                          M.walk.as<unsigned>(), M.val.as<unsigned char>(),       \
+                                                                          M.rows.as<int>(), M.runs.as<int2>())
         if(elem_size == 4)
             B200_TILE_FILL(4);
         else if(elem_size == 8)
@@ -744,7 +808,7 @@ namespace b200
             B200_TILE_FILL(16);
 #undef B200_TILE_FILL
         B200_LAUNCHED();
-        B200_CUDA(cudaStreamSynchronize(st)); // hdesc / hent are read by the copies above
+        B200_CUDA(cudaStreamSynchronize(st)); // hdesc / hoff are read by the copies above
         M.state = 2;
         return aoclsparse_status_success;
     }
@@ -755,8 +819,7 @@ namespace b200
         const mesh_tiles &M         = A.tiles;
         const size_t      row_bytes = (size_t)n * sizeof(T);
         const int         RT        = M.rows_per_tile;
-        const int         brows     = M.max_distinct;
-        const size_t      one       = tile_buffer_bytes(RT, M.max_distinct, M.max_len, row_bytes, sizeof(T));
+        const size_t      one       = tile_buffer_bytes(RT, M.max_distinct, M.max_walk, M.max_vals, row_bytes, sizeof(T));
         const int         n_buf     = (128 + 2 * one <= (size_t)227 * 1024) ? 2 : 1;
         const size_t      smem      = 128 + (size_t)n_buf * one;
         const int         bz        = is_zero(beta) ? 1 : 0;
@@ -764,32 +827,27 @@ namespace b200
         int               sms       = 148, dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        const int grid = std::min(M.n_tiles, sms);
-#define B200_MM_TILES(TPR, CH)                                                                                           \
+        const int grid    = std::min(M.n_tiles, sms);
+        const int threads = RT / GRP * 8 + 32;
+#define B200_MM_TILES(CH)                                                                                                \
     {                                                                                                                    \
         static std::atomic<size_t> cfg{0};                                                                               \
         if(cfg.load() < smem)                                                                                            \
         {                                                                                                                \
-            B200_CUDA(cudaFuncSetAttribute(csrmm_mesh_tiles_kernel<T, TPR, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            B200_CUDA(cudaFuncSetAttribute(csrmm_mesh_tiles_kernel<T, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
             cfg.store(smem);                                                                                             \
         }                                                                                                                \
-        csrmm_mesh_tiles_kernel<T, TPR, CH><<<(unsigned)grid, RT * TPR + 32, smem, st>>>(                                \
-            M.desc.as<int4>(), M.ent_off.as<long long>(), M.val.as<T>(), M.slot.as<unsigned short>(), M.rows.as<int>(),   \
-            M.len.as<unsigned char>(), M.runs.as<int2>(), B, ldb, C, ldc, M.n_tiles, RT, brows, M.max_len, n_buf, alpha,  \
-            beta, bz, contig);                                                                                           \
+        csrmm_mesh_tiles_kernel<T, CH><<<(unsigned)grid, threads, smem, st>>>(                                           \
+            M.desc.as<int4>(), M.off.as<long long>(), M.walk.as<unsigned>(), M.val.as<T>(), M.rows.as<int>(),             \
+            M.runs.as<int2>(), B, ldb, C, ldc, M.n_tiles, RT, M.max_distinct, M.max_walk, M.max_vals, n_buf, alpha, beta, \
+            bz, contig);                                                                                                 \
     }
-        // threads per row x chunks per thread (AOCLSPARSE_B200_MM_TILE_CH=8: fewer, fatter threads -- A/B knob)
-        static const int env_ch = getenv("AOCLSPARSE_B200_MM_TILE_CH") ? atoi(getenv("AOCLSPARSE_B200_MM_TILE_CH")) : 4;
-        if(row_bytes == 128 && env_ch == 8)
-            B200_MM_TILES(1, 8)
-        else if(row_bytes == 128)
-            B200_MM_TILES(2, 4)
-        else if(row_bytes == 256 && env_ch == 8)
-            B200_MM_TILES(2, 8)
+        if(row_bytes == 128)
+            B200_MM_TILES(1)
         else if(row_bytes == 256)
-            B200_MM_TILES(4, 4)
+            B200_MM_TILES(2)
         else if(row_bytes == 512)
-            B200_MM_TILES(4, 8)
+            B200_MM_TILES(4)
         else
             return aoclsparse_status_internal_error;
 #undef B200_MM_TILES
@@ -822,27 +880,23 @@ aoclsparse_status aoclsparse_b200_get_mm_tiles_info(const aoclsparse_matrix A, a
         info->stride[i] = M.stride[i];
         info->dims[i]   = M.dims[i];
     }
-    info->rows_per_tile = M.rows_per_tile;
-    info->n_tiles       = M.n_tiles;
-    info->max_distinct  = M.max_distinct;
-    info->max_len       = M.max_len;
-    info->max_runs      = M.max_runs;
-    info->entries       = M.entries;
-    info->n_runs_total  = M.n_runs_total;
-    info->row_bytes     = (long long)M.row_bytes;
-    info->reuse         = M.reuse;
-    info->fill          = M.fill;
+    info->rows_per_tile  = M.rows_per_tile;
+    info->rows_per_group = 2;
+    info->n_tiles        = M.n_tiles;
+    info->max_distinct   = M.max_distinct;
+    info->max_walk       = M.max_walk;
+    info->max_vals       = M.max_vals;
+    info->max_runs       = M.max_runs;
+    info->walk_entries   = M.walk_entries;
+    info->val_entries    = M.val_entries;
+    info->n_runs_total   = M.n_runs_total;
+    info->row_bytes      = (long long)M.row_bytes;
+    info->reuse          = M.reuse;
+    info->fill           = M.fill;
     return aoclsparse_status_success;
 }
 
-aoclsparse_status aoclsparse_b200_get_mm_tiles(const aoclsparse_matrix A,
-                                               int                   *desc,
-                                               long long             *ent_off,
-                                               void                  *val,
-                                               unsigned short        *slot,
-                                               int                   *rows,
-                                               unsigned char         *len,
-                                               int                   *runs)
+aoclsparse_status aoclsparse_b200_get_mm_tiles(const aoclsparse_matrix A, int *desc, long long *off, unsigned *walk, void *val, int *rows, int *runs)
 {
     if(!A || A->mats.empty() || A->mats[0] == nullptr)
         return aoclsparse_status_invalid_pointer;
@@ -857,20 +911,17 @@ aoclsparse_status aoclsparse_b200_get_mm_tiles(const aoclsparse_matrix A,
     const size_t tr = (size_t)M.n_tiles * M.rows_per_tile;
     if(desc)
         B200_CUDA(cudaMemcpyAsync(desc, M.desc.p, sizeof(int4) * (size_t)M.n_tiles, cudaMemcpyDeviceToHost, st));
-    if(ent_off)
-        B200_CUDA(cudaMemcpyAsync(ent_off, M.ent_off.p, sizeof(long long) * (size_t)M.n_tiles, cudaMemcpyDeviceToHost, st));
+    if(off)
+        B200_CUDA(cudaMemcpyAsync(off, M.off.p, sizeof(long long) * 2 * (size_t)M.n_tiles, cudaMemcpyDeviceToHost, st));
+    if(walk)
+        B200_CUDA(cudaMemcpyAsync(walk, M.walk.p, 4 * (size_t)M.walk_entries, cudaMemcpyDeviceToHost, st));
     if(val)
-        B200_CUDA(cudaMemcpyAsync(val, M.val.p, es * (size_t)M.entries, cudaMemcpyDeviceToHost, st));
-    if(slot)
-        B200_CUDA(cudaMemcpyAsync(slot, M.slot.p, 2 * (size_t)M.entries, cudaMemcpyDeviceToHost, st));
+        B200_CUDA(cudaMemcpyAsync(val, M.val.p, es * (size_t)M.val_entries, cudaMemcpyDeviceToHost, st));
     if(rows)
         B200_CUDA(cudaMemcpyAsync(rows, M.rows.p, sizeof(int) * tr, cudaMemcpyDeviceToHost, st));
-    if(len)
-        B200_CUDA(cudaMemcpyAsync(len, M.len.p, tr, cudaMemcpyDeviceToHost, st));
     if(runs)
         B200_CUDA(cudaMemcpyAsync(runs, M.runs.p, sizeof(int2) * (size_t)M.n_runs_total, cudaMemcpyDeviceToHost, st));
     B200_CUDA(cudaStreamSynchronize(st));
     return aoclsparse_status_success;
 }
 }
-

@@ -418,6 +418,7 @@ namespace b200
                 out[b] = mx;
         }
 
+        constexpr int HOST_CHUNKS_MAX = 32;
         // builds (once per plan) the chunk table of the host-staged pipeline
         aoclsparse_status ensure_host_chunks(aoclsparse_matrix A, size_t elem_size, cudaStream_t st)
         {
@@ -450,9 +451,9 @@ namespace b200
             // very long vectors (config 5: 2 x 1 GB): the copies dominate and the un-overlapped tail is the last chunk's
             // kernel + read-back, so cut finer
             if(vec_bytes >= ((size_t)512u << 20))
-                n_chunks = 16;
+                n_chunks = 32;
             if(const char *e = getenv("AOCLSPARSE_B200_HOST_CHUNKS"))
-                n_chunks = atoi(e) < 1 ? 1 : (atoi(e) > 16 ? 16 : atoi(e));
+                n_chunks = atoi(e) < 1 ? 1 : (atoi(e) > HOST_CHUNKS_MAX ? HOST_CHUNKS_MAX : atoi(e));
             int run_max  = -1;
             for(int c = 0; c < n_chunks; ++c)
             {
@@ -476,8 +477,8 @@ namespace b200
         struct host_pipe
         {
             cudaStream_t h2d = nullptr, d2h = nullptr;
-            cudaEvent_t  ev_x[16] = {}, ev_k[16] = {}, ev_start = nullptr;
-            cudaEvent_t  tr_x[16] = {}, tr_k[16] = {}, tr_y[16] = {}, tr_0 = nullptr; // AOCLSPARSE_B200_HOST_TRACE=1 only
+            cudaEvent_t  ev_x[HOST_CHUNKS_MAX] = {}, ev_k[HOST_CHUNKS_MAX] = {}, ev_start = nullptr;
+            cudaEvent_t  tr_x[HOST_CHUNKS_MAX] = {}, tr_k[HOST_CHUNKS_MAX] = {}, tr_y[HOST_CHUNKS_MAX] = {}, tr_0 = nullptr; // AOCLSPARSE_B200_HOST_TRACE=1 only
             bool         ready = false, trace = false;
             aoclsparse_status init()
             {
@@ -485,7 +486,7 @@ namespace b200
                     return aoclsparse_status_success;
                 B200_CUDA(cudaStreamCreateWithFlags(&h2d, cudaStreamNonBlocking));
                 B200_CUDA(cudaStreamCreateWithFlags(&d2h, cudaStreamNonBlocking));
-                for(int i = 0; i < 16; ++i)
+                for(int i = 0; i < HOST_CHUNKS_MAX; ++i)
                 {
                     B200_CUDA(cudaEventCreateWithFlags(&ev_x[i], cudaEventDisableTiming));
                     B200_CUDA(cudaEventCreateWithFlags(&ev_k[i], cudaEventDisableTiming));
@@ -495,7 +496,7 @@ namespace b200
                 if(trace)
                 {
                     B200_CUDA(cudaEventCreate(&tr_0));
-                    for(int i = 0; i < 16; ++i)
+                    for(int i = 0; i < HOST_CHUNKS_MAX; ++i)
                     {
                         B200_CUDA(cudaEventCreate(&tr_x[i]));
                         B200_CUDA(cudaEventCreate(&tr_k[i]));
@@ -1230,6 +1231,17 @@ aoclsparse_status aoclsparse_b200_ipc_free(void *dptr)
 
 }
 
+// AOCLSPARSE_B200_SHARD_FENCE: 1 (default) boundary CTAs release at GPU scope and only the last one of a side fences at
+// system scope; 0 every boundary CTA fences at system scope (spmv_sharded.cuh, boundary_release)
+static int shard_cta_fence_gpu()
+{
+    static const int v = [] {
+        const char *e = getenv("AOCLSPARSE_B200_SHARD_FENCE");
+        return e ? (atoi(e) != 0 ? 1 : 0) : 1;
+    }();
+    return v;
+}
+
 // One launch per iteration of the row-sharded product: multiply + halo push + flags (spmv_sharded.cuh).
 // kc = launches of this kernel on these counters so far, this one included (the flags carry ctl->k, which may run ahead
 // of kc when other events -- the initial halo publication of shard.cu -- take a number as well)
@@ -1278,6 +1290,7 @@ aoclsparse_status b200::sharded_step_launch(const double                  *alpha
     // the window holds a halo of row_cuts[0] entries on every side that has a neighbour
     hc.own_lo = (A->win_hi >= 0 ? (int)A->win_lo : 0) + (hc.left_done ? (int)A->row_cuts[0] : 0);
     hc.own_hi = hc.own_lo + (int)A->m;
+    hc.cta_fence_gpu = shard_cta_fence_gpu();
     if((hc.left_done && !ctl->push_left) || (hc.right_done && !ctl->push_right))
         return aoclsparse_status_invalid_pointer;
     if(A->win_hi >= 0)
@@ -1372,6 +1385,7 @@ aoclsparse_status b200::sharded_iterate_launch(double                     alpha,
     hc.last_row0     = A->row_cuts[1];
     hc.own_lo        = (A->win_hi >= 0 ? (int)A->win_lo : 0) + (hc.left_done ? (int)A->row_cuts[0] : 0);
     hc.own_hi        = hc.own_lo + (int)A->m;
+    hc.cta_fence_gpu = shard_cta_fence_gpu();
     if((hc.left_done && (!args.push_left[0] || !args.push_left[1])) || (hc.right_done && (!args.push_right[0] || !args.push_right[1])))
         return aoclsparse_status_invalid_pointer;
     const long long shift = A->win_hi >= 0 ? (long long)A->win_lo : 0;
@@ -1397,6 +1411,12 @@ aoclsparse_status b200::sharded_iterate_launch(double                     alpha,
     }
     if(grid > P.n_blocks)
         grid = P.n_blocks;
+    // every CTA walks blocks c, c+G, ...: with G = ceil(blocks / rounds) all CTAs do the same number of rounds (the last
+    // one short by < rounds blocks in total) instead of some doing a whole extra block while the others wait at the barrier
+    {
+        const long long rounds = (P.n_blocks + grid - 1) / grid;
+        grid                   = (P.n_blocks + rounds - 1) / rounds;
+    }
     const int4           *p_desc  = P.desc.as<int4>();
     const aoclsparse_int *p_rp    = M.row_ptr.as<aoclsparse_int>();
     const aoclsparse_int *p_col   = M.col_idx.as<aoclsparse_int>();

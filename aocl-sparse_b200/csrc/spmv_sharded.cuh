@@ -32,12 +32,27 @@ namespace b200
         int       last_begin;                // index of the first block of the last boundary
         int       first_rows, last_row0;     // rows in the first boundary; first row of the last boundary
         int       own_lo, own_hi;            // columns of x this rank computes itself; the rest of its window is halo
+        int       cta_fence_gpu;             // see boundary_release
     };
 
     // acquire / release fence at system scope (lighter than the sequentially consistent __threadfence_system())
     __device__ __forceinline__ void fence_acq_rel_sys()
     {
         asm volatile("fence.acq_rel.sys;" ::: "memory");
+    }
+
+    // What a boundary CTA does between its last store and its arrival on the side's counter.  The peer must see every
+    // boundary row before it sees the flag.  cta_fence_gpu == 0: every CTA fences at system scope.  cta_fence_gpu == 1:
+    // a CTA only releases at GPU scope (fence + relaxed atomic = release pattern, observed by the last CTA's atomic +
+    // its fence.acq_rel.sys = acquire pattern at a scope that includes both); the last CTA's system-scope fence before
+    // the flag store is then cumulative over the stores of all CTAs it synchronised with (PTX memory model, causality
+    // order) -- one system-scope fence per side and iteration instead of one per CTA.
+    __device__ __forceinline__ void boundary_release(int cta_fence_gpu)
+    {
+        if(cta_fence_gpu)
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        else
+            fence_acq_rel_sys();
     }
 
     // x[c] for a BOUNDARY row: halo entries (columns outside the rank's own rows [own_lo, own_hi)) are stored by the peer
@@ -235,7 +250,7 @@ namespace b200
             __syncthreads();
             if(tid == 0)
             {
-                fence_acq_rel_sys(); // this CTA's stores (peer stores included) before the counter / flag
+                boundary_release(hc.cta_fence_gpu); // this CTA's stores (peer stores included) before the counter / flag
                 const unsigned n_side = side == 0 ? (unsigned)hc.n_first : (unsigned)hc.n_last;
                 const unsigned done   = atomicAdd(hc.counters + side, 1u) + 1u;
                 if(done == hc.kc * n_side)
@@ -276,6 +291,7 @@ namespace b200
         int             iters;
         int             n_first, n_last, n_blocks, last_begin, last_row0;
         int             own_lo, own_hi; // columns of x this rank computes itself; the rest of its window is halo
+        int             cta_fence_gpu;  // see boundary_release
     };
 
     template <typename T, bool CODED>
@@ -468,7 +484,7 @@ namespace b200
                 }
                 if(done_side != 2 && tid == 0)
                 {
-                    fence_acq_rel_sys(); // this CTA's stores (peer stores included) before the counter / flag
+                    boundary_release(hc.cta_fence_gpu); // this CTA's stores (peer stores included) before the counter / flag
                     const unsigned n_side = done_side == 0 ? (unsigned)hc.n_first : (unsigned)hc.n_last;
                     const unsigned cntd   = atomicAdd(hc.counters + done_side, 1u) + 1u;
                     if(cntd == (hc.kc0 + (unsigned)it + 1u) * n_side)

@@ -65,34 +65,37 @@ DLL_PUBLIC aoclsparse_status aoclsparse_b200_get_diag_codes(const aoclsparse_mat
 
 /* Box-tile copy used by row-major aoclsparse_?csrmm on grid (stencil) matrices (csrc/mesh_tiles.cu): built on the first
  * multiply that can use it.  The matrix's distinct col - row offsets are read as a lattice {a + b*stride[1] + c*stride[2]},
- * rows are grouped into boxes box[0] x box[1] x box[2] of that grid (rows_per_tile rows), and every tile stores its
- * entries as ELL planes val[j][row in tile] / slot[j][row in tile], slot = position of the entry's column among the
- * tile's distinct columns, which the kernel stages (as runs of consecutive B rows) in shared memory.
- * state: 0 not analysed yet, 1 analysed and not usable (no lattice, too little re-use), 2 ready.
- * Integer metadata with no counterpart in the reference: pinned bit for bit by tests/oracle_py.py::mesh_tiles. */
+ * rows are grouped into boxes box[0] x box[1] x box[2] of that grid (rows_per_tile rows).  A tile stores
+ *   - its distinct columns as RUNS of consecutive columns (the kernel stages those B rows in shared memory; an entry's
+ *     SLOT is the position of its column among them),
+ *   - per ROW GROUP (rows_per_group consecutive rows of the tile) a WALK: the ascending columns at least one row of the
+ *     group stores, each as slot | rowmask << 16, and a VALUE STREAM: walk entry by walk entry, row by row, the values.
+ *     Both are planes over the tile's groups: walk[j][g], val[i][g].
+ * state: 0 not analysed yet, 1 analysed and not usable (no lattice, unsorted rows, too little re-use), 2 ready.
+ * Integer metadata with no counterpart in the reference: pinned bit for bit by tests/mesh_tiles_ref.py. */
 typedef struct aoclsparse_b200_mm_tiles_info_
 {
     int       state;
     int       box[3];
     long long stride[3];
     int       dims[3];
-    int       rows_per_tile, n_tiles, max_distinct, max_len, max_runs;
-    long long entries;      /* ELL slots of all tiles, padding included                  */
+    int       rows_per_tile, rows_per_group, n_tiles, max_distinct, max_walk, max_vals, max_runs;
+    long long walk_entries; /* slots of all walk planes, padding included               */
+    long long val_entries;  /* slots of all value planes, padding included              */
     long long n_runs_total; /* runs of all tiles plus one terminator per tile            */
     long long row_bytes;    /* n * sizeof(T) of the multiply the boxes were sized for    */
-    double    reuse, fill;  /* stored entries per staged B row; per ELL slot             */
+    double    reuse, fill;  /* stored entries per staged B row; per value-plane slot     */
 } aoclsparse_b200_mm_tiles_info;
 DLL_PUBLIC aoclsparse_status aoclsparse_b200_get_mm_tiles_info(const aoclsparse_matrix A, aoclsparse_b200_mm_tiles_info *info);
-/* host copies of the tile arrays (any pointer may be NULL): desc 4 ints per tile {distinct, runs, longest row, first
- * run}; ent_off per tile; val / slot per ELL slot; rows / len per (tile, row in tile); runs 2 ints per run {first
- * column, first slot}, each tile's list closed by {-1, distinct} */
+/* host copies of the tile arrays (any pointer may be NULL): desc 4 ints per tile {distinct, runs, U | V << 16, first
+ * run}; off 2 per tile {first walk slot, first value slot}; walk / val per slot; rows per (tile, row in tile); runs 2 ints
+ * per run {first column, first slot}, each tile's list closed by {-1, distinct} */
 DLL_PUBLIC aoclsparse_status aoclsparse_b200_get_mm_tiles(const aoclsparse_matrix A,
                                                           int                   *desc,
-                                                          long long             *ent_off,
+                                                          long long             *off,
+                                                          unsigned              *walk,
                                                           void                  *val,
-                                                          unsigned short        *slot,
                                                           int                   *rows,
-                                                          unsigned char         *len,
                                                           int                   *runs);
 
 /* value type of a handle (aoclsparse_matrix_data_type), -1 for NULL */

@@ -8,8 +8,11 @@ pinned bit for bit against this restatement of the same written spec:
   * box          = choose_box(...): extent of a tile along the directions, RT = X*Y*Z rows (multiple of 32, <= 96)
   * tile t       = box (t % tx, (t / tx) % ty, t / (tx*ty)); its row lr = (lr % X, (lr / X) % Y, lr / (X*Y)) inside it
   * per tile     : distinct = ascending distinct columns of its rows; runs = maximal runs of consecutive columns, each
-                   (first column, first slot), closed by (-1, number of distinct columns); L = longest row;
-                   ELL planes val / slot at ent_off + j * RT + lr (slot = index of the column in `distinct`, zero padding)
+                   (first column, first slot), closed by (-1, number of distinct columns)
+  * per row group: GRP consecutive rows of the tile; WALK = ascending columns at least one of them stores, each as
+                   slot | rowmask << 16 (slot = index of the column in `distinct`); VALUE STREAM = walk entry by walk
+                   entry, row by row, the stored values; both as planes over the tile's groups, zero padded:
+                   walk[j][g] at off[t][0] + j*NG + g (j < U), val[i][g] at off[t][1] + i*NG + g (i < V)
 """
 import numpy as np
 
@@ -85,12 +88,16 @@ def detect_lattice(offs, m):
     return True, 3, s1, s2
 
 
-def buffer_bytes(RT, max_distinct, max_len, row_bytes, elem_size):
-    return (max_distinct * row_bytes + max_len * RT * (elem_size + 2) + RT * 5 + 127) & ~127
+GRP = 2  # rows of a row group
 
 
-def smem_bytes(RT, max_distinct, max_len, row_bytes, elem_size):
-    return 128 + buffer_bytes(RT, max_distinct, max_len, row_bytes, elem_size)
+def buffer_bytes(RT, max_distinct, max_walk, max_vals, row_bytes, elem_size):
+    NG = RT // GRP
+    return (max_distinct * row_bytes + max_walk * NG * 4 + max_vals * NG * elem_size + RT * 4 + 127) & ~127
+
+
+def smem_bytes(RT, max_distinct, max_walk, max_vals, row_bytes, elem_size):
+    return 128 + buffer_bytes(RT, max_distinct, max_walk, max_vals, row_bytes, elem_size)
 
 
 def grid_of(m, ndim, s1, s2):
@@ -118,7 +125,8 @@ def choose_box(ndim, nx, ny, nz, max_len, row_bytes, elem_size, budget=112 * 102
             if Y > max(ny, 1) * 2 or Z > max(nz, 1) * 2:
                 continue
             distinct = (X + 2) * (Y + 2) * (Z + 2 if ndim == 3 else 1)
-            if smem_bytes(RT, distinct, max_len, row_bytes, elem_size) > budget:
+            walk, vals = (max_len * (GRP + 2) + 2) // 3, GRP * max_len
+            if smem_bytes(RT, distinct, walk, vals, row_bytes, elem_size) > budget:
                 continue
             cost = distinct / RT
             if cost < best - 1e-9:
@@ -143,46 +151,62 @@ def tile_rows(m, gs1, gs2, nx, ny, nz, box):
 
 
 def build(rp, col, val, box, ndim, s1, s2):
-    """-> dict of the arrays aoclsparse_b200_get_mm_tiles returns, or None when the rows are not partitioned"""
+    """-> dict of the arrays aoclsparse_b200_get_mm_tiles returns, or None when the rows are not partitioned or a row is
+    not strictly ascending"""
     m = len(rp) - 1
     rp = np.asarray(rp, dtype=np.int64)
     gs1, gs2, nx, ny, nz = grid_of(m, ndim, s1, s2)
     rows = tile_rows(m, gs1, gs2, nx, ny, nz, box)
     nt, RT = rows.shape
+    NG = RT // GRP
     if np.count_nonzero(rows >= 0) != m:
         return None
     desc = np.zeros((nt, 4), dtype=np.int32)
-    ent = np.zeros(nt, dtype=np.int64)
-    lens = np.zeros((nt, RT), dtype=np.uint8)
-    runs, vals, slots = [], [], []
-    e = 0
-    nrun = 0
+    off = np.zeros((nt, 2), dtype=np.int64)
+    runs, walks, vals = [], [], []
+    w_off = v_off = nrun = 0
     for t in range(nt):
         rr = rows[t]
-        ln = np.where(rr >= 0, rp[np.maximum(rr, 0) + 1] - rp[np.maximum(rr, 0)], 0)
-        lens[t] = ln
-        L = int(ln.max())
-        cols = np.concatenate([col[rp[r]:rp[r + 1]] for r in rr if r >= 0]) if L else np.zeros(0, dtype=np.int32)
-        distinct = np.unique(cols)
+        cols = [col[rp[r]:rp[r + 1]] if r >= 0 else np.zeros(0, dtype=col.dtype) for r in rr]
+        for c in cols:
+            if len(c) > 1 and np.any(np.diff(c.astype(np.int64)) <= 0):
+                return None
+        allc = np.concatenate(cols) if cols else np.zeros(0, dtype=col.dtype)
+        distinct = np.unique(allc)
         starts = [i for i in range(len(distinct)) if i == 0 or distinct[i] != distinct[i - 1] + 1]
-        desc[t] = (len(distinct), len(starts), L, nrun)
-        ent[t] = e
+        gw, gv = [], []
+        for g in range(NG):
+            members = [(i, rr[g * GRP + i], cols[g * GRP + i]) for i in range(GRP)]
+            union = np.unique(np.concatenate([c for _, _, c in members]))
+            w, v = [], []
+            for c in union:
+                mask = 0
+                for i, r, cc in members:
+                    k = np.searchsorted(cc, c)
+                    if k < len(cc) and cc[k] == c:
+                        mask |= 1 << i
+                        v.append(val[rp[r] + k])
+                w.append(int(np.searchsorted(distinct, c)) | (mask << 16))
+            gw.append(w)
+            gv.append(v)
+        U = max((len(w) for w in gw), default=0)
+        V = max((len(v) for v in gv), default=0)
+        desc[t] = (len(distinct), len(starts), U | (V << 16), nrun)
+        off[t] = (w_off, v_off)
         for i in starts:
             runs.append((int(distinct[i]), i))
         runs.append((-1, len(distinct)))
         nrun += len(starts) + 1
-        tv = np.zeros((L, RT), dtype=val.dtype)
-        ts = np.zeros((L, RT), dtype=np.uint16)
-        for lr, r in enumerate(rr):
-            if r < 0:
-                continue
-            c = col[rp[r]:rp[r + 1]]
-            tv[:len(c), lr] = val[rp[r]:rp[r + 1]]
-            ts[:len(c), lr] = np.searchsorted(distinct, c)
+        tw = np.zeros((U, NG), dtype=np.uint32)
+        tv = np.zeros((V, NG), dtype=val.dtype)
+        for g in range(NG):
+            tw[:len(gw[g]), g] = gw[g]
+            tv[:len(gv[g]), g] = gv[g]
+        walks.append(tw.reshape(-1))
         vals.append(tv.reshape(-1))
-        slots.append(ts.reshape(-1))
-        e += L * RT
-    return {"desc": desc, "ent_off": ent, "rows": rows.astype(np.int32).reshape(-1), "len": lens.reshape(-1),
+        w_off += U * NG
+        v_off += V * NG
+    return {"desc": desc, "off": off, "rows": rows.astype(np.int32).reshape(-1),
             "runs": np.array(runs, dtype=np.int32).reshape(-1, 2),
-            "val": np.concatenate(vals) if vals else np.zeros(0, dtype=val.dtype),
-            "slot": np.concatenate(slots) if slots else np.zeros(0, dtype=np.uint16)}
+            "walk": np.concatenate(walks) if walks else np.zeros(0, dtype=np.uint32),
+            "val": np.concatenate(vals) if vals else np.zeros(0, dtype=val.dtype)}

@@ -153,3 +153,50 @@ def test_update_values_refreshes_the_tiles(lib):
         lib.destroy_descr(d)
     finally:
         os.environ.pop("AOCLSPARSE_B200_MM_TILES", None)
+
+
+@pytest.mark.parametrize("p", ["s", "d", "z"])
+@pytest.mark.parametrize("grid", [(27, 24, 12, 9), (7, 16, 16, 9), (5, 33, 21, 1), (27, 24, 9, 5)], ids=["27pt", "7pt", "5pt", "27pt-ragged"])
+def test_tile_arrays_bit_exact_against_the_cpu_restatement(lib, p, grid):
+    """the tile analysis is integer work with no counterpart in the reference: lattice strides, box, runs, walks, row
+    lists and the re-ordered values must equal tests/mesh_tiles_ref.py bit for bit"""
+    import torch
+    import mesh_tiles_ref as ref
+    pts, nx, ny, nz = grid
+    rng = np.random.default_rng(17)
+    dt = DT[p]
+    rp, col, val = gen_np.stencil(pts, nx, ny, nz)
+    val = _values(rng, val, dt)
+    m = len(rp) - 1
+    elem = np.dtype(dt).itemsize
+    n = 256 // elem
+    os.environ["AOCLSPARSE_B200_MM_TILES"] = "2"
+    try:
+        st, h = lib.create_csr(p, 0, m, m, len(col), rp, col, val)
+        assert st == 0
+        d = lib.create_descr()
+        B = torch.zeros(m * n, dtype=torch.from_numpy(np.zeros(1, dtype=dt)).dtype, device="cuda")
+        Cc = torch.zeros_like(B)
+        assert lib.csrmm(p, 111, 1.0, h, d, 0, B.data_ptr(), n, n, 0.0, Cc.data_ptr(), n) == 0, lib.last_error()
+        torch.cuda.synchronize()
+        info = lib.mm_tiles_info(h)
+        offs = ref.diag_offsets(rp, col)
+        ok, ndim, s1, s2 = ref.detect_lattice(offs, m)
+        assert ok
+        gs1, gs2, gx, gy, gz = ref.grid_of(m, ndim, s1, s2)
+        assert info["strides"] == [1, gs1, gs2] and info["dims"] == [gx, gy, gz]
+        box = ref.choose_box(ndim, gx, gy, gz, len(offs), 256, elem)
+        want = ref.build(rp, col, val, box, ndim, s1, s2)
+        if info["state"] != 2:
+            # the library declined (too little re-use, or too much padding on a grid the boxes do not divide)
+            assert (pts, nx, ny, nz) != (27, 24, 12, 9)
+            return
+        assert info["box"] == box and info["rows_per_group"] == ref.GRP
+        got = lib.mm_tiles(h, dt)
+        for k in ("desc", "off", "rows", "runs", "walk"):
+            assert np.array_equal(got[k].reshape(-1), want[k].reshape(-1)), k
+        assert np.array_equal(got["val"].view(np.uint8), want["val"].view(np.uint8))
+        lib.destroy(h)
+        lib.destroy_descr(d)
+    finally:
+        os.environ.pop("AOCLSPARSE_B200_MM_TILES", None)

@@ -40,25 +40,46 @@ def test_tiles_decode_to_the_matrix(pts, nx, ny, nz, box):
     assert ok
     t = ref.build(rp, col, val, box, ndim, s1, s2)
     RT = box[0] * box[1] * box[2]
+    NG = RT // ref.GRP
     rows = t["rows"].reshape(-1, RT)
     assert sorted(rows[rows >= 0].tolist()) == list(range(m))
     seen = 0
     for ti in range(rows.shape[0]):
-        nd, nr, L, r0 = t["desc"][ti]
+        nd, nr, uv, r0 = (int(v) for v in t["desc"][ti])
+        U, V = uv & 0xffff, uv >> 16
         runs = t["runs"][r0:r0 + nr + 1]
         assert runs[-1][0] == -1 and runs[-1][1] == nd
         distinct = np.concatenate([np.arange(runs[i][0], runs[i][0] + runs[i + 1][1] - runs[i][1]) for i in range(nr)]) \
             if nr else np.zeros(0, dtype=np.int64)
         assert len(distinct) == nd and np.all(np.diff(distinct) > 0)
-        for lr in range(RT):
-            r = rows[ti, lr]
-            ln = int(t["len"][ti * RT + lr])
-            if r < 0:
-                assert ln == 0
-                continue
-            assert ln == rp[r + 1] - rp[r]
-            idx = t["ent_off"][ti] + np.arange(ln) * RT + lr
-            assert np.array_equal(distinct[t["slot"][idx]], col[rp[r]:rp[r + 1]])
-            assert np.array_equal(t["val"][idx], val[rp[r]:rp[r + 1]])
-            seen += ln
+        w_off, v_off = (int(v) for v in t["off"][ti])
+        for g in range(NG):
+            got = {i: ([], []) for i in range(ref.GRP)}
+            vp = 0
+            for j in range(U):
+                w = int(t["walk"][w_off + j * NG + g])
+                if w >> 16 == 0:
+                    assert all(int(t["walk"][w_off + jj * NG + g]) == 0 for jj in range(j, U))
+                    break
+                for i in range(ref.GRP):
+                    if (w >> 16) & (1 << i):
+                        got[i][0].append(distinct[w & 0xffff])
+                        got[i][1].append(t["val"][v_off + vp * NG + g])
+                        vp += 1
+            assert vp <= V
+            for i in range(ref.GRP):
+                r = rows[ti, g * ref.GRP + i]
+                if r < 0:
+                    assert not got[i][0]
+                    continue
+                assert np.array_equal(np.array(got[i][0]), col[rp[r]:rp[r + 1]])
+                assert np.array_equal(np.array(got[i][1]), val[rp[r]:rp[r + 1]])
+                seen += len(got[i][0])
     assert seen == len(col)
+
+
+def test_unsorted_rows_give_no_tiles():
+    rp, col, val = gen_np.stencil(7, 8, 8, 4)
+    col = col.copy()
+    col[rp[10]], col[rp[10] + 1] = col[rp[10] + 1], col[rp[10]]
+    assert ref.build(rp, col, val, [8, 4, 1], 3, 8, 64) is None
