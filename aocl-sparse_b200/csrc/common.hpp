@@ -391,7 +391,7 @@ namespace b200
         double    reuse = 0.0, fill = 0.0; // stored entries per staged B row; stored entries per value-plane slot
         dev_buf   desc; // int4 per tile: distinct B rows, runs, U | V << 16 (longest walk / value stream of a group), first run
         dev_buf   off;  // 2 long long per tile: first walk slot, first value slot
-        dev_buf   walk; // unsigned[walk_entries]: tile t, entry j, group g at off[2t] + j * groups + g: slot | rowmask << 16
+        dev_buf   walk; // unsigned[walk_entries]: tile t, entry j, group g at off[2t] + j * groups + g: slot | rowmask << 16 | first value << 20
         dev_buf   val;  // T[val_entries]: tile t, i-th value of group g at off[2t+1] + i * groups + g
         dev_buf   rows; // int[n_tiles * rows_per_tile]: matrix row of (tile, lr) or -1
         dev_buf   runs; // int2[n_runs_total]: first column, first slot of every run; terminator (-1, distinct)

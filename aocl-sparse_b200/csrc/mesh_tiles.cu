@@ -131,7 +131,8 @@ namespace b200
         //   distinct columns: the tile's columns sorted, repeats removed (ukeys); a RUN is a maximal stretch of consecutive
         //   columns, stored as (first column, first slot), the tile's list closed by (-1, distinct).
         //   row group grp = rows GRP*grp .. GRP*grp+GRP-1 of the tile: its WALK is the ascending list of the columns at
-        //   least one of its rows stores, each as slot | rowmask << 16; its VALUE STREAM holds, walk entry by walk entry
+        //   least one of its rows stores, each as slot | rowmask << 16 | (position of its first value) << 20, closed by a
+        //   zero entry; its VALUE STREAM holds, walk entry by walk entry
         //   and row by row (ascending), the stored values.  Both are laid out as planes over the groups:
         //   walk[j][grp] at sm_off + j*NG + grp (zero = padding), val[i][grp] at val_off + i*NG + grp.
         template <int ES, bool FILL>
@@ -250,7 +251,7 @@ namespace b200
                             else
                                 hi = mid;
                         }
-                        twalk[sm_off + (long long)U * NG + grp] = (unsigned)lo | (m << 16);
+                        twalk[sm_off + (long long)U * NG + grp] = (unsigned)lo | (m << 16) | ((unsigned)V << 20);
                     }
                     for(int i = 0; i < GRP; ++i)
                         if(m & (1u << i))
@@ -276,7 +277,7 @@ namespace b200
                 }
                 else
                 {
-                    atomicMax(&s_info[5], U);
+                    atomicMax(&s_info[5], U + 1); // + the all-zero entry that ends the walk
                     atomicMax(&s_info[6], V);
                 }
             }
@@ -418,7 +419,6 @@ namespace b200
                 const unsigned      *swalk = reinterpret_cast<const unsigned *>(btile + (size_t)btile_rows * ROW_BYTES);
                 const T             *sval  = reinterpret_cast<const T *>(reinterpret_cast<const unsigned char *>(swalk) + walk_b);
                 const int           *srows = reinterpret_cast<const int *>(reinterpret_cast<const unsigned char *>(sval) + vals_b);
-                const int            U     = tdesc[tile].z & 0xffff;
                 mbar_wait(full + q, (unsigned)u & 1u);
 
                 int rows[GRP];
@@ -434,27 +434,28 @@ namespace b200
                         for(int qq = 0; qq < VEC; ++qq)
                             acc[i][k].v[qq] = vt<T>::zero();
                 const unsigned      *wp = swalk + grp;
-                const T             *vp = sval + grp;
+                const T             *vg = sval + grp;
                 const unsigned char *bh = btile + h * 16;
-                unsigned             w  = U > 0 ? wp[0] : 0u;
-                for(int j = 0; j < U; ++j)
+                unsigned             w  = *wp;
+                // a walk entry: slot (bits 0-15) | row mask (16-19) | position of its first value in the group's value
+                // stream (20-31); an all-zero entry ends the walk (every tile stores one after its longest walk)
+                while(w >> 16)
                 {
-                    const unsigned m = w >> 16;
-                    if(m == 0)
-                        break; // padding: this group's walk is over
                     const unsigned char *rowp = bh + (size_t)(w & 0xffffu) * ROW_BYTES;
-                    w                         = j + 1 < U ? wp[(j + 1) * NG] : 0u; // next walk entry, in flight during the multiply-adds
+                    const T             *vp   = vg + (w >> 20) * NG;
+                    const unsigned       m    = w >> 16;
+                    wp += NG;
+                    w = *wp; // next walk entry, in flight during the multiply-adds
                     chunk16<T> x[CH];
 #pragma unroll
                     for(int k = 0; k < CH; ++k)
                         x[k] = *reinterpret_cast<const chunk16<T> *>(rowp + k * 128);
-                    // the values of this entry sit at vp[0 .. popc(m)) (plane stride NG), in row order; loads past the
-                    // group's stream stay inside the staging buffer and are never used
+                    // the entry's values sit at vp[0 .. popc(mask)) (plane stride NG), in row order; a load past the group's
+                    // stream stays inside the staging buffer and is never used
                     T v[GRP];
 #pragma unroll
                     for(int i = 0; i < GRP; ++i)
                         v[i] = vp[__popc(m & ((1u << i) - 1u)) * NG];
-                    vp += __popc(m) * NG;
 #pragma unroll
                     for(int i = 0; i < GRP; ++i)
                         if(m & (1u << i))

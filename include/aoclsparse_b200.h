@@ -69,7 +69,8 @@ DLL_PUBLIC aoclsparse_status aoclsparse_b200_get_diag_codes(const aoclsparse_mat
  *   - its distinct columns as RUNS of consecutive columns (the kernel stages those B rows in shared memory; an entry's
  *     SLOT is the position of its column among them),
  *   - per ROW GROUP (rows_per_group consecutive rows of the tile) a WALK: the ascending columns at least one row of the
- *     group stores, each as slot | rowmask << 16, and a VALUE STREAM: walk entry by walk entry, row by row, the values.
+ *     group stores, each as slot | rowmask << 16 | (position of its first value) << 20 and closed by a zero entry, and a
+ *     VALUE STREAM: walk entry by walk entry, row by row, the values.
  *     Both are planes over the tile's groups: walk[j][g], val[i][g].
  * state: 0 not analysed yet, 1 analysed and not usable (no lattice, unsorted rows, too little re-use), 2 ready.
  * Integer metadata with no counterpart in the reference: pinned bit for bit by tests/mesh_tiles_ref.py. */

@@ -10,7 +10,8 @@ pinned bit for bit against this restatement of the same written spec:
   * per tile     : distinct = ascending distinct columns of its rows; runs = maximal runs of consecutive columns, each
                    (first column, first slot), closed by (-1, number of distinct columns)
   * per row group: GRP consecutive rows of the tile; WALK = ascending columns at least one of them stores, each as
-                   slot | rowmask << 16 (slot = index of the column in `distinct`); VALUE STREAM = walk entry by walk
+                   slot | rowmask << 16 | (position of its first value) << 20, closed by a zero entry (slot = index of the
+                   column in `distinct`); VALUE STREAM = walk entry by walk
                    entry, row by row, the stored values; both as planes over the tile's groups, zero padded:
                    walk[j][g] at off[t][0] + j*NG + g (j < U), val[i][g] at off[t][1] + i*NG + g (i < V)
 """
@@ -181,15 +182,16 @@ def build(rp, col, val, box, ndim, s1, s2):
             w, v = [], []
             for c in union:
                 mask = 0
+                first = len(v)
                 for i, r, cc in members:
                     k = np.searchsorted(cc, c)
                     if k < len(cc) and cc[k] == c:
                         mask |= 1 << i
                         v.append(val[rp[r] + k])
-                w.append(int(np.searchsorted(distinct, c)) | (mask << 16))
+                w.append(int(np.searchsorted(distinct, c)) | (mask << 16) | (first << 20))
             gw.append(w)
             gv.append(v)
-        U = max((len(w) for w in gw), default=0)
+        U = max((len(w) for w in gw), default=0) + 1  # + the all-zero entry that ends the walk
         V = max((len(v) for v in gv), default=0)
         desc[t] = (len(distinct), len(starts), U | (V << 16), nrun)
         off[t] = (w_off, v_off)

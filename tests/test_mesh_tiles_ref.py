@@ -61,6 +61,8 @@ def test_tiles_decode_to_the_matrix(pts, nx, ny, nz, box):
                 if w >> 16 == 0:
                     assert all(int(t["walk"][w_off + jj * NG + g]) == 0 for jj in range(j, U))
                     break
+                assert w >> 20 == vp
+                w &= 0xfffff
                 for i in range(ref.GRP):
                     if (w >> 16) & (1 << i):
                         got[i][0].append(distinct[w & 0xffff])
