@@ -840,19 +840,27 @@ namespace b200
         const T        *dB = B;
         T              *dC = C;
         mm_staging     &sg = tls_mm_staging();
+        // host operands: only the rows x columns the product names travel (pitched copies), so neither the bytes after
+        // the last row of a sub-matrix view are read (a BLAS-style caller only guarantees (rows-1)*ld + cols elements)
+        // nor is C's padding touched; with beta == 0 C is not read, so it is not uploaded either
+        const long long b_lines = order == aoclsparse_order_column ? n : b_rows, b_inner = order == aoclsparse_order_column ? b_rows : n;
+        const long long c_lines = order == aoclsparse_order_column ? n : m_c, c_inner = order == aoclsparse_order_column ? m_c : n;
         if(!b_dev)
         {
             if(sg.B.bytes < (size_t)b_elems * sizeof(T))
                 B200_TRY(sg.B.alloc((size_t)b_elems * sizeof(T)));
-            B200_CUDA(cudaMemcpyAsync(sg.B.p, B, (size_t)b_elems * sizeof(T), cudaMemcpyHostToDevice, st));
+            if(b_lines > 0 && b_inner > 0)
+                B200_CUDA(cudaMemcpy2DAsync(sg.B.p, (size_t)ldb * sizeof(T), B, (size_t)ldb * sizeof(T), (size_t)b_inner * sizeof(T),
+                                            (size_t)b_lines, cudaMemcpyHostToDevice, st));
             dB = sg.B.as<T>();
         }
         if(!c_dev)
         {
             if(sg.C.bytes < (size_t)c_elems * sizeof(T))
                 B200_TRY(sg.C.alloc((size_t)c_elems * sizeof(T)));
-            // padding elements must come back unchanged, so C always travels up
-            B200_CUDA(cudaMemcpyAsync(sg.C.p, C, (size_t)c_elems * sizeof(T), cudaMemcpyHostToDevice, st));
+            if(!is_zero(beta) && c_lines > 0 && c_inner > 0)
+                B200_CUDA(cudaMemcpy2DAsync(sg.C.p, (size_t)ldc * sizeof(T), C, (size_t)ldc * sizeof(T), (size_t)c_inner * sizeof(T),
+                                            (size_t)c_lines, cudaMemcpyHostToDevice, st));
             dC = sg.C.as<T>();
         }
 
@@ -922,7 +930,9 @@ namespace b200
             return status;
         if(!c_dev)
         {
-            B200_CUDA(cudaMemcpyAsync(C, dC, (size_t)c_elems * sizeof(T), cudaMemcpyDeviceToHost, st));
+            if(c_lines > 0 && c_inner > 0)
+                B200_CUDA(cudaMemcpy2DAsync(C, (size_t)ldc * sizeof(T), dC, (size_t)ldc * sizeof(T), (size_t)c_inner * sizeof(T),
+                                            (size_t)c_lines, cudaMemcpyDeviceToHost, st));
             B200_CUDA(cudaStreamSynchronize(st));
         }
         else if(!b_dev)

@@ -641,6 +641,8 @@ def measure(args, key, primary):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_per_step = float(t.item()) / steps
 
+    tiles = lib.mm_tiles_info(A) if wl["kind"] == "mm" else None
+
     # ---- N > 1: every rank's slab ALONE (plain aoclsparse_dmv on its window, no flags, no peer stores), all ranks at the
     # same time: separates device-to-device variation and the lock-step with the slowest rank from the cost of the exchange
     rank_alone_ms = None
@@ -788,7 +790,8 @@ def measure(args, key, primary):
             "traffic_source": traffic_src,
             "kernel": (("spmv_sharded_iterate_kernel" if batched else "spmv_sharded_step_kernel")
                        if (sharded and world > 1 and halo_mode in ("p2p-fused", "shard-c-abi"))
-                       else "spmv_row_blocks_kernel") if wl["kind"] == "mv" else "csrmm_row_major_vec_kernel",
+                       else "spmv_row_blocks_kernel") if wl["kind"] == "mv" else
+            ("csrmm_mesh_tiles_kernel" if (tiles and tiles["state"] == 2) else "csrmm_row_major_vec_kernel"),
             "algorithmic_bytes_per_launch": int(l_bytes)}
     if kern_ms:
         roof["achieved"] = round(l_bytes / (kern_ms * 1e-3) / 1e9, 1)
@@ -800,6 +803,13 @@ def measure(args, key, primary):
         roof["note"] = "per-GPU share of the step (interior + boundary CTAs of one launch overlap the halo exchange)"
     roof["frac"] = round(roof["achieved"] / peak, 4)
     roof["frac_of_nominal_8TBs"] = round(roof["achieved"] / 8000.0, 4)
+    if tiles and tiles["state"] == 2:
+        roof["tiles"] = {k: tiles[k] for k in ("box", "strides", "rows_per_tile", "rows_per_group", "n_tiles", "max_distinct",
+                                               "max_walk", "max_vals", "reuse", "fill")}
+        roof["tiles"]["what"] = ("box tiles of the grid (csrc/mesh_tiles.cu): a tile's distinct B rows are staged once in shared "
+                                 "memory; entries are stored as 16-bit slots + values re-ordered per row pair, "
+                                 "%.1f bytes per stored entry instead of 12" %
+                                 ((tiles["walk_entries"] * 4 + tiles["val_entries"] * elem) / max(1, nnz)))
     if info.n_diag_codes > 0 and wl["kind"] == "mv":
         # disclosure: aoclsparse_optimize built the diagonal-code copy of col_idx (1 byte per entry instead of 4, the
         # decoded columns are bit-identical), so the kernel STREAMS fewer bytes than the reference's byte model counts;
