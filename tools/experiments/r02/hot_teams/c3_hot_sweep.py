@@ -61,7 +61,7 @@ if __name__ == "__main__":
         ref = None  # the summation order depends on the block size: compare within one block size
         for entries in tables:
             for team in (teams if entries else [0]):
-                if team and T > 8 * team:
+                if team and T > 768:
                     continue  # a thread of the team gathers all of its (at most 8) entries of a block at once
                 assert lib.set_hot_table(A, entries, team) == 0, lib.last_error()
                 ms, info = run("")

@@ -93,9 +93,28 @@ namespace b200
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         }
 
-        inline size_t ht_stage_bytes(size_t elem, int cap)
+        // 4-byte values: only the column slice is staged; the gatherers read the values straight from global memory
+        // (coalesced) and a product takes the place of its column.  8-byte values: values + columns are staged, the
+        // product takes the place of the value.
+        __host__ __device__ inline size_t ht_stage_bytes(size_t elem, int cap)
         {
-            return (size_t)cap * (elem + 4);
+            return (size_t)cap * (elem == 4 ? 4 : elem + 4);
+        }
+        template <typename T>
+        __device__ __forceinline__ T ldg_stream(const T *p, uint64_t policy);
+        template <>
+        __device__ __forceinline__ float ldg_stream<float>(const float *p, uint64_t policy)
+        {
+            float v;
+            asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(policy));
+            return v;
+        }
+        template <>
+        __device__ __forceinline__ double ldg_stream<double>(const double *p, uint64_t policy)
+        {
+            double v;
+            asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(policy));
+            return v;
         }
         // two stages per team: the next block's slice arrives while the current one is reduced
         inline size_t ht_smem_bytes(size_t elem, int entries, int teams, int cap)
@@ -103,7 +122,21 @@ namespace b200
             return HT_HEADER + ((((size_t)entries * elem) + 15) & ~(size_t)15) + (size_t)teams * 2 * ht_stage_bytes(elem, cap);
         }
 
-        template <typename T, int TEAM>
+        __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+        {
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+        }
+
+        // One CTA of 1024 threads per SM = 8 teams of 4 warps.  Warp 0 of a team is its REDUCER (it also issues the team's
+        // bulk copies), warps 1..3 are its GATHERERS; the team walks the plan's row blocks b = first, first + stride, ...
+        // through a ring of two stages:
+        //     reducer, lane 0 : bulk copy of block i+2's val / col_hot slice into stage i & 1  -> full[s]
+        //     gatherers       : wait full[s]; every staged entry becomes its product with x in place, all of a thread's
+        //                       (<= HT_U) gathers issued together, hot columns from the table  -> gathered[s] (3 arrivals)
+        //     reducer         : wait gathered[s]; per-row sums, alpha / beta, y; then refills the stage
+        // No barrier couples the two roles: the gatherers of a team have gathers outstanding for as long as the reducer
+        // keeps up, and the 8 teams are independent of each other.
+        template <typename T>
         __global__ void __launch_bounds__(HT_THREADS, 1) spmv_hot_teams_kernel(const int4 *__restrict__ desc,
                                                                               const int *__restrict__ kind,
                                                                               int n_blocks,
@@ -120,18 +153,22 @@ namespace b200
                                                                               const aoclsparse_int *__restrict__ hot_cols,
                                                                               int table_entries)
         {
+            constexpr int TEAM   = 128;
             constexpr int NTEAMS = HT_THREADS / TEAM;
-            constexpr int TW     = TEAM / 32;
-            constexpr int U      = HT_U; // gathers a thread keeps in flight = entries per thread of one block
+            constexpr int GT     = TEAM - 32; // gather threads of a team
+            constexpr int U      = HT_U;
+            constexpr bool COLONLY = sizeof(T) == 4;
             extern __shared__ __align__(16) unsigned char smem_raw[];
-            uint64_t      *bars        = reinterpret_cast<uint64_t *>(smem_raw);                // [team][stage]
+            uint64_t      *bars        = reinterpret_cast<uint64_t *>(smem_raw); // [team]: full[2], gathered[2]
             T             *table       = reinterpret_cast<T *>(smem_raw + HT_HEADER);
             const size_t   table_bytes = (((size_t)table_entries * sizeof(T)) + 15) & ~(size_t)15;
             const int      tid = threadIdx.x, team = tid / TEAM, t = tid % TEAM, lane = t & 31, warp = t >> 5;
-            const size_t   stage_bytes = (size_t)cap * (sizeof(T) + 4);
+            const size_t   stage_bytes = ht_stage_bytes(sizeof(T), cap);
+            const size_t   col_off     = COLONLY ? 0 : (size_t)cap * sizeof(T); // the columns inside a stage
             unsigned char *stage0      = smem_raw + HT_HEADER + table_bytes + (size_t)team * 2 * stage_bytes;
-            uint64_t      *bar         = bars + 2 * team;
-            T             *s_part      = reinterpret_cast<T *>(smem_raw + 256) + team * 2 * TW; // [parity][warp]
+            uint64_t      *full        = bars + 4 * team;
+            uint64_t      *gathered    = full + 2;
+            T             *s_part      = reinterpret_cast<T *>(smem_raw + 512) + team * 8; // [stage][gather warp]
 
             const int total_teams = gridDim.x * NTEAMS;
             const int b0          = blockIdx.x * NTEAMS + team;
@@ -142,173 +179,198 @@ namespace b200
                 if(cnt > 0)
                 {
                     unsigned char *st = stage0 + (size_t)s * stage_bytes;
-                    mbar_expect_tx(bar + s, (unsigned)(cnt * (sizeof(T) + sizeof(aoclsparse_int))));
-                    bulk_load_stream(st, val + a, (unsigned)(cnt * sizeof(T)), bar + s);
-                    bulk_load_stream(st + (size_t)cap * sizeof(T), col_hot + a, (unsigned)(cnt * sizeof(aoclsparse_int)), bar + s);
+                    mbar_expect_tx(full + s, (unsigned)(cnt * ((COLONLY ? 0 : sizeof(T)) + sizeof(aoclsparse_int))));
+                    if(!COLONLY)
+                        bulk_load_stream(st, val + a, (unsigned)(cnt * sizeof(T)), full + s);
+                    bulk_load_stream(st + col_off, col_hot + a, (unsigned)(cnt * sizeof(aoclsparse_int)), full + s);
                 }
+                else
+                    mbar_arrive(full + s); // nothing to copy: the phase still completes
             };
-            const int4 zero4 = make_int4(0, 0, 0, 0);
-            // block whose products are being formed (`n`: next) and block whose rows are being summed (`c`: current)
-            int  bn = b0;
-            int4 dn = bn < n_blocks ? desc[bn] : zero4;
-            int  kn = bn < n_blocks ? kind[bn] : 0;
-            int4 dc = zero4;
-            int  kc = 0;
-            bool have_c = false;
             if(t == 0)
             {
-                mbar_init(bar, 1);
-                mbar_init(bar + 1, 1);
+                mbar_init(full, 1);
+                mbar_init(full + 1, 1);
+                mbar_init(gathered, 3);
+                mbar_init(gathered + 1, 3);
                 mbar_init_fence();
-                if(bn < n_blocks)
-                    issue(dn, 0); // the matrix slices do not depend on x: they fly while the table is filled
-                if(bn + total_teams < n_blocks)
-                    issue(desc[bn + total_teams], 1);
+                // the matrix slices do not depend on x: they fly while the table is filled
+                if(b0 < n_blocks)
+                    issue(desc[b0], 0);
+                if(b0 + total_teams < n_blocks)
+                    issue(desc[b0 + total_teams], 1);
             }
             for(int i = tid; i < table_entries; i += HT_THREADS)
                 table[i] = ldg_ro(x + hot_cols[i]);
             __syncthreads();
 
-            auto xv = [&](int c) -> T { return c < 0 ? table[c & 0x7fffffff] : ldg_ro(x + c); };
-
-            unsigned ph = 0; // phase parity of the two stage barriers (bit s)
-            int      sn = 0; // stage of block bn (block bc sits in the other one)
-            unsigned it = 0;
-            // Software pipeline over the team's blocks: the gathers of block bn are issued, the rows of the previous
-            // block bc are summed while they fly, then the products of bn are written -- ONE team barrier per block,
-            // and a warp has gathers outstanding for most of its time.
-            while(bn < n_blocks || have_c)
+            if(warp != 0)
             {
-                const bool have_n = bn < n_blocks;
-                // descriptor of the block after bn: its bulk copy is issued at the end of this iteration
-                int4 dnn = zero4;
-                int  knn = 0;
-                if(have_n && bn + total_teams < n_blocks)
+                // ------------------------------------------------------------------ gatherers
+                const int gt = t - 32, gw = warp - 1;
+                uint64_t  policy;
+                asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+                int4      d  = b0 < n_blocks ? desc[b0] : make_int4(0, 0, 0, 0);
+                int       k  = b0 < n_blocks ? kind[b0] : 0;
+                unsigned  i  = 0;
+                for(int b = b0; b < n_blocks; b += total_teams, ++i)
                 {
-                    dnn = desc[bn + total_teams];
-                    knn = kind[bn + total_teams];
-                }
-                // ---- (1) block bn: wait for its slice, read the columns, issue the gathers
-                const int a_n     = dn.z & ~3;
-                const int first_n = dn.z - a_n, total_n = have_n ? dn.w - dn.z : 0;
-                T        *sval_n  = reinterpret_cast<T *>(stage0 + (size_t)sn * stage_bytes);
-                int      *scol_n  = reinterpret_cast<int *>(stage0 + (size_t)sn * stage_bytes + (size_t)cap * sizeof(T));
-                T         xx[U];
-                if(have_n)
-                {
-                    if((((dn.w - a_n) + 3) & ~3) > 0)
+                    int4 dn = make_int4(0, 0, 0, 0);
+                    int  kn = 0;
+                    if(b + total_teams < n_blocks)
                     {
-                        mbar_wait(bar + sn, (ph >> sn) & 1u);
-                        ph ^= 1u << sn;
+                        dn = desc[b + total_teams];
+                        kn = kind[b + total_teams];
                     }
-                    int c[U];
-#pragma unroll
-                    for(int u = 0; u < U; ++u)
-                        c[u] = t + u * TEAM < total_n ? scol_n[first_n + t + u * TEAM] : HOT_BIT;
-#pragma unroll
-                    for(int u = 0; u < U; ++u)
-                        xx[u] = xv(c[u]);
-                }
-                // ---- (2) block bc: per-row sums of its finished products; 32 consecutive rows per warp pass
-                if(have_c && (kc & 15) != STRAT_LONG)
-                {
-                    const int a_c    = dc.z & ~3;
-                    const T  *sval_c = reinterpret_cast<const T *>(stage0 + (size_t)(sn ^ 1) * stage_bytes);
-                    for(int rb = dc.x + warp * 32; rb < dc.y; rb += TEAM)
+                    const int s = i & 1u;
+                    const int first = d.z - (d.z & ~3), total = d.w - d.z;
+                    T         vv[U];
+                    if constexpr(COLONLY)
                     {
-                        const int  r     = rb + lane;
-                        const bool valid = r < dc.y;
-                        int        ss = 0, ee = 0;
-                        if(valid)
-                        {
-                            ss = rp[r] - a_c;
-                            ee = rp[r + 1] - a_c;
-                        }
+                        // the block's values, coalesced, straight from global memory (read once: evict-first in L2)
+#pragma unroll
+                        for(int u = 0; u < U; ++u)
+                            vv[u] = gt + u * GT < total ? ldg_stream(val + d.z + gt + u * GT, policy) : vt<T>::zero();
+                    }
+                    mbar_wait(full + s, (i >> 1) & 1u);
+                    T        *sval  = reinterpret_cast<T *>(stage0 + (size_t)s * stage_bytes); // products (COLONLY: over the columns)
+                    int      *scol  = reinterpret_cast<int *>(stage0 + (size_t)s * stage_bytes + col_off);
+                    int       c[U];
+                    T         xx[U];
+#pragma unroll
+                    for(int u = 0; u < U; ++u)
+                        c[u] = gt + u * GT < total ? scol[first + gt + u * GT] : HOT_BIT;
+#pragma unroll
+                    for(int u = 0; u < U; ++u)
+                        xx[u] = c[u] < 0 ? table[c[u] & 0x7fffffff] : ldg_ro(x + c[u]);
+                    if constexpr(!COLONLY)
+                    {
+#pragma unroll
+                        for(int u = 0; u < U; ++u)
+                            vv[u] = gt + u * GT < total ? sval[first + gt + u * GT] : vt<T>::zero();
+                    }
+                    if((k & 15) != STRAT_LONG)
+                    {
+#pragma unroll
+                        for(int u = 0; u < U; ++u)
+                            if(gt + u * GT < total)
+                                sval[first + gt + u * GT] = mul(vv[u], xx[u]);
+                    }
+                    else
+                    {
                         T acc = vt<T>::zero();
-                        if(ee - ss <= SHORT_ROW)
-                            for(int j = ss; j < ee; ++j)
-                                acc = add(acc, sval_c[j]);
-                        unsigned pending = __ballot_sync(0xffffffffu, valid && (ee - ss > SHORT_ROW));
-                        while(pending)
-                        {
-                            const int src = __ffs(pending) - 1;
-                            pending &= pending - 1;
-                            const int js   = __shfl_sync(0xffffffffu, ss, src);
-                            const int je   = __shfl_sync(0xffffffffu, ee, src);
-                            T         part = vt<T>::zero();
-                            for(int j = js + lane; j < je; j += 32)
-                                part = add(part, sval_c[j]);
-                            part = warp_sum(part);
-                            if(lane == src)
-                                acc = part;
-                        }
-                        if(valid)
-                            y[r] = axpby_out(alpha, acc, beta, beta_zero != 0, y + r);
+#pragma unroll
+                        for(int u = 0; u < U; ++u)
+                            if(gt + u * GT < total)
+                                acc = mad(vv[u], xx[u], acc);
+                        acc = warp_sum(acc);
+                        if(lane == 0)
+                            s_part[s * 4 + gw] = acc;
                     }
-                }
-                // ---- (3) block bn: products in place (or, for a segment of a split row, the segment's partial sum)
-                const bool long_n = have_n && (kn & 15) == STRAT_LONG;
-                if(have_n && !long_n)
-                {
-#pragma unroll
-                    for(int u = 0; u < U; ++u)
-                        if(t + u * TEAM < total_n)
-                            sval_n[first_n + t + u * TEAM] = mul(sval_n[first_n + t + u * TEAM], xx[u]);
-                }
-                else if(long_n)
-                {
-                    T acc = vt<T>::zero();
-#pragma unroll
-                    for(int u = 0; u < U; ++u)
-                        if(t + u * TEAM < total_n)
-                            acc = mad(sval_n[first_n + t + u * TEAM], xx[u], acc);
-                    acc = warp_sum(acc);
+                    __syncwarp();
                     if(lane == 0)
-                        s_part[(it & 1u) * TW + warp] = acc;
+                        mbar_arrive(gathered + s);
+                    d = dn;
+                    k = kn;
                 }
-                // ---- (4) the products of bn are visible to the team, everybody is done with bc's stage
-                fence_proxy_async_smem();
-                team_sync<TEAM>(team);
-                if(t == 0)
+            }
+            else
+            {
+                // ------------------------------------------------------------------ reducer (+ the team's bulk copies)
+                int4     d = b0 < n_blocks ? desc[b0] : make_int4(0, 0, 0, 0);
+                int      k = b0 < n_blocks ? kind[b0] : 0;
+                unsigned i = 0;
+                for(int b = b0; b < n_blocks; b += total_teams, ++i)
                 {
-                    if(have_c && have_n && bn + total_teams < n_blocks)
-                        issue(dnn, sn ^ 1); // block after bn goes where bc was
-                    if(long_n)
+                    int4 dn = make_int4(0, 0, 0, 0);
+                    int  kn = 0;
+                    if(b + total_teams < n_blocks)
                     {
-                        T tot = s_part[(it & 1u) * TW];
-#pragma unroll
-                        for(int w = 1; w < TW; ++w)
-                            tot = add(tot, s_part[(it & 1u) * TW + w]);
-                        partials[kn >> 4] = tot;
+                        dn = desc[b + total_teams];
+                        kn = kind[b + total_teams];
                     }
+                    int4 dnn = make_int4(0, 0, 0, 0);
+                    if(b + 2 * total_teams < n_blocks)
+                        dnn = desc[b + 2 * total_teams];
+                    const int  s       = i & 1u;
+                    const int  a       = d.z & ~3;
+                    const bool is_long = (k & 15) == STRAT_LONG;
+                    // bounds of the first 32 rows, requested before the wait
+                    int s0 = 0, e0 = 0;
+                    if(!is_long && d.x + lane < d.y)
+                    {
+                        s0 = rp[d.x + lane] - a;
+                        e0 = rp[d.x + lane + 1] - a;
+                    }
+                    mbar_wait(gathered + s, (i >> 1) & 1u);
+                    const T *sval = reinterpret_cast<const T *>(stage0 + (size_t)s * stage_bytes);
+                    if(!is_long)
+                    {
+                        for(int rb = d.x; rb < d.y; rb += 32)
+                        {
+                            const int  r     = rb + lane;
+                            const bool valid = r < d.y;
+                            int        ss = s0, ee = e0;
+                            if(rb != d.x)
+                            {
+                                ss = ee = 0;
+                                if(valid)
+                                {
+                                    ss = rp[r] - a;
+                                    ee = rp[r + 1] - a;
+                                }
+                            }
+                            T acc = vt<T>::zero();
+                            if(ee - ss <= SHORT_ROW)
+                                for(int j = ss; j < ee; ++j)
+                                    acc = add(acc, sval[j]);
+                            unsigned pending = __ballot_sync(0xffffffffu, valid && (ee - ss > SHORT_ROW));
+                            while(pending)
+                            {
+                                const int src = __ffs(pending) - 1;
+                                pending &= pending - 1;
+                                const int js   = __shfl_sync(0xffffffffu, ss, src);
+                                const int je   = __shfl_sync(0xffffffffu, ee, src);
+                                T         part = vt<T>::zero();
+                                for(int j = js + lane; j < je; j += 32)
+                                    part = add(part, sval[j]);
+                                part = warp_sum(part);
+                                if(lane == src)
+                                    acc = part;
+                            }
+                            if(valid)
+                                y[r] = axpby_out(alpha, acc, beta, beta_zero != 0, y + r);
+                        }
+                    }
+                    else if(lane == 0)
+                        partials[k >> 4] = add(add(s_part[s * 4], s_part[s * 4 + 1]), s_part[s * 4 + 2]);
+                    // the stage is free: refill it with the block after next
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if(lane == 0 && b + 2 * total_teams < n_blocks)
+                        issue(dnn, s);
+                    d = dn;
+                    k = kn;
                 }
-                dc     = dn;
-                kc     = kn;
-                have_c = have_n;
-                dn     = dnn;
-                kn     = knn;
-                bn     = have_n ? bn + total_teams : bn;
-                sn ^= 1;
-                ++it;
             }
         }
 
-        template <typename T, int TEAM>
+        template <typename T>
         aoclsparse_status launch_hot_teams(const dev_csr &A, const T *x, T *y, T alpha, T beta, cudaStream_t st)
         {
             const row_block_plan &P      = A.plan;
-            constexpr int         NTEAMS = HT_THREADS / TEAM;
+            constexpr int         NTEAMS = HT_THREADS / 128;
             const int             cap    = P.block_nnz + 8;
             const size_t          smem   = ht_smem_bytes(sizeof(T), P.hot_entries, NTEAMS, cap);
             static std::atomic<size_t> configured{0};
             if(configured.load(std::memory_order_acquire) != smem)
             {
-                B200_CUDA(cudaFuncSetAttribute(spmv_hot_teams_kernel<T, TEAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                B200_CUDA(cudaFuncSetAttribute(spmv_hot_teams_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 // the smallest carve-out that holds one CTA: everything else stays L1 (see the header)
                 int pct = (int)((smem + 1024 + 2047) * 100 / (228 * 1024)) + 1;
                 if(pct > 100)
                     pct = 100;
-                B200_CUDA(cudaFuncSetAttribute(spmv_hot_teams_kernel<T, TEAM>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+                B200_CUDA(cudaFuncSetAttribute(spmv_hot_teams_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
                 configured.store(smem, std::memory_order_release);
             }
             int sms = 148, dev = 0;
@@ -316,21 +378,21 @@ namespace b200
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
             const int want = (P.n_blocks + NTEAMS - 1) / NTEAMS;
             const int grid = want < sms ? want : sms;
-            spmv_hot_teams_kernel<T, TEAM><<<grid, HT_THREADS, smem, st>>>(P.desc.as<int4>(),
-                                                                            P.kind.as<int>(),
-                                                                            (int)P.n_blocks,
-                                                                            cap,
-                                                                            A.row_ptr.as<aoclsparse_int>(),
-                                                                            P.col_hot.as<aoclsparse_int>(),
-                                                                            A.val.as<T>(),
-                                                                            x,
-                                                                            y,
-                                                                            alpha,
-                                                                            beta,
-                                                                            is_zero(beta) ? 1 : 0,
-                                                                            P.partials.as<T>(),
-                                                                            P.hot_cols.as<aoclsparse_int>(),
-                                                                            (int)P.hot_entries);
+            spmv_hot_teams_kernel<T><<<grid, HT_THREADS, smem, st>>>(P.desc.as<int4>(),
+                                                                      P.kind.as<int>(),
+                                                                      (int)P.n_blocks,
+                                                                      cap,
+                                                                      A.row_ptr.as<aoclsparse_int>(),
+                                                                      P.col_hot.as<aoclsparse_int>(),
+                                                                      A.val.as<T>(),
+                                                                      x,
+                                                                      y,
+                                                                      alpha,
+                                                                      beta,
+                                                                      is_zero(beta) ? 1 : 0,
+                                                                      P.partials.as<T>(),
+                                                                      P.hot_cols.as<aoclsparse_int>(),
+                                                                      (int)P.hot_entries);
             B200_LAUNCHED();
             return aoclsparse_status_success;
         }
@@ -349,12 +411,9 @@ namespace b200
             return aoclsparse_status_success;
         if(!force && (A.nnz < (1 << 22) || (size_t)A.n * elem_size < (size_t)(8u << 20)))
             return aoclsparse_status_success; // small problems: x lives in L1 / L2 lines that are re-used anyway
-        if(team_threads != 64 && team_threads != 128 && team_threads != 256)
-            team_threads = 128;
-        // a thread gathers all of its entries of a block at once: HT_U per thread
-        while(team_threads < 256 && P.block_nnz > HT_U * team_threads)
-            team_threads *= 2;
-        if(P.block_nnz > HT_U * team_threads)
+        team_threads = 128; // 1 reducer warp + 3 gather warps
+        // a gather thread takes all of its entries of a block at once: at most HT_U
+        if(P.block_nnz > HT_U * (team_threads - 32))
             return aoclsparse_status_success;
         const int    teams = HT_THREADS / team_threads;
         const int    cap   = P.block_nnz + 8;
@@ -415,11 +474,7 @@ namespace b200
     template <typename T>
     aoclsparse_status launch_hot(const dev_csr &A, const T *x, T *y, T alpha, T beta, cudaStream_t st)
     {
-        if(A.plan.hot_team == 256)
-            return launch_hot_teams<T, 256>(A, x, y, alpha, beta, st);
-        if(A.plan.hot_team == 64)
-            return launch_hot_teams<T, 64>(A, x, y, alpha, beta, st);
-        return launch_hot_teams<T, 128>(A, x, y, alpha, beta, st);
+        return launch_hot_teams<T>(A, x, y, alpha, beta, st);
     }
 
     template aoclsparse_status launch_hot<float>(const dev_csr &, const float *, float *, float, float, cudaStream_t);
