@@ -50,8 +50,7 @@ class MatrixInfo(C.Structure):
                 ("block_nnz", C.c_int32), ("block_rows", C.c_int32), ("n_blocks", C.c_int32),
                 ("n_thread_blocks", C.c_int32), ("n_warp_blocks", C.c_int32),
                 ("n_product_blocks", C.c_int32), ("n_long_segments", C.c_int32),
-                ("n_long_rows", C.c_int32), ("n_diag_codes", C.c_int32), ("hot_entries", C.c_int32),
-                ("hot_mass_ppm", C.c_int32)]
+                ("n_long_rows", C.c_int32), ("n_diag_codes", C.c_int32)]
 
 
 class MmTilesInfo(C.Structure):
@@ -166,7 +165,6 @@ class AoclSparse:
             L.aoclsparse_b200_get_clean_csr.argtypes = [vp, C.POINTER(i32), C.POINTER(ci), vp, vp, vp, vp, vp]
             L.aoclsparse_b200_set_x_window.argtypes = [vp, i32, i32]
             L.aoclsparse_b200_set_row_cuts.argtypes = [vp, i32, vp]
-            L.aoclsparse_b200_set_hot_table.argtypes = [vp, i32, i32]
             L.aoclsparse_b200_dmv_rows.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32]
             L.aoclsparse_b200_smv_rows.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32]
             L.aoclsparse_b200_dmv_rows_push.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, vp]
@@ -436,9 +434,6 @@ class AoclSparse:
     def set_row_cuts(self, h, cuts):
         cuts = np.ascontiguousarray(cuts, dtype=np.int32)
         return self.lib.aoclsparse_b200_set_row_cuts(h, len(cuts), ptr(cuts))
-
-    def set_hot_table(self, h, entries, team_threads=0):
-        return self.lib.aoclsparse_b200_set_hot_table(h, entries, team_threads)
 
     def mv_rows(self, prefix, alpha, h, descr, x, beta, y, r0, r1):
         a = _scalar_by_ref(prefix, alpha)

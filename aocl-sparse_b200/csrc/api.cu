@@ -640,30 +640,6 @@ aoclsparse_status aoclsparse_optimize(aoclsparse_matrix A)
     else if(!M.plan.valid || forced >= 0)
         B200_TRY(build_plan(M, value_size(A->val_type), A->max_row_nnz, forced, A->row_cuts, st));
 
-    // power-law matrices with a plain general mv hint: hot-column table for the persistent kernel of hot.cu (the most
-    // frequent columns' x entries live in shared memory for the whole multiply)
-    {
-        bool gn_mv_hint = false;
-        for(const hint &h : A->hints)
-            gn_mv_hint = gn_mv_hint || ((h.act == 1 || h.act == 8) && h.doid == DOID_GN);
-        const long long mean   = A->m > 0 ? (long long)A->nnz / A->m : 0;
-        const bool      skewed = (long long)A->max_row_nnz > 16 * (mean > 1 ? mean : 1);
-        const char     *e      = getenv("AOCLSPARSE_B200_HOT"); // A/B knob
-        const bool      want   = e ? atoi(e) != 0 : HOT_BY_DEFAULT;
-        const bool      real   = A->val_type == aoclsparse_smat || A->val_type == aoclsparse_dmat;
-        if(want && real && gn_mv_hint && !A->is_csc && skewed && forced < 0 && A->mem_policy == aoclsparse_memory_usage_unrestricted
-           && A->win_hi < 0 && A->row_cuts.empty() && M.plan.valid && M.plan.hot_state == 0)
-        {
-            long long entries = 0;
-            int       team    = 128;
-            if(const char *t = getenv("AOCLSPARSE_B200_HOT_TABLE"))
-                entries = atoll(t);
-            if(const char *t = getenv("AOCLSPARSE_B200_HOT_TEAM"))
-                team = atoi(t);
-            B200_TRY(build_hot_table(M, value_size(A->val_type), entries, team, false, st));
-        }
-    }
-
     // transposed device copies for general transposed mv / mm hints (memory policy permitting):
     // they turn the atomic scatter into a streaming gather
     if(A->mem_policy == aoclsparse_memory_usage_unrestricted && A->win_hi < 0)
@@ -735,8 +711,6 @@ aoclsparse_status aoclsparse_b200_get_matrix_info(const aoclsparse_matrix A, aoc
         info->n_long_segments  = P.n_long_segments;
         info->n_long_rows      = P.n_long_rows;
         info->n_diag_codes     = P.n_codes;
-        info->hot_entries      = P.hot_entries;
-        info->hot_mass_ppm     = (aoclsparse_int)(P.hot_mass * 1e6);
     }
     return aoclsparse_status_success;
 }
@@ -843,32 +817,6 @@ aoclsparse_status aoclsparse_b200_set_x_window(aoclsparse_matrix A, aoclsparse_i
     A->win_lo = col_lo;
     A->win_hi = col_hi;
     return aoclsparse_status_success;
-}
-
-aoclsparse_status aoclsparse_b200_set_hot_table(aoclsparse_matrix A, aoclsparse_int entries, aoclsparse_int team_threads)
-{
-    if(!A)
-        return aoclsparse_status_invalid_pointer;
-    if(entries < 0 || (team_threads != 0 && team_threads != 64 && team_threads != 128 && team_threads != 256))
-        return aoclsparse_status_invalid_value;
-    if(A->mats.empty() || A->mats[0] == nullptr)
-        return aoclsparse_status_invalid_pointer;
-    if(A->val_type != aoclsparse_smat && A->val_type != aoclsparse_dmat)
-        return aoclsparse_status_not_implemented;
-    cudaStream_t st = current_stream();
-    B200_TRY(ensure_plan(A, st));
-    std::unique_lock<std::shared_mutex> wl(A->guard);
-    row_block_plan                     &P = A->mats[0]->plan;
-    if(entries == 0)
-    {
-        P.hot_entries = 0;
-        P.hot_mass    = 0.0;
-        P.hot_cols.release();
-        P.col_hot.release();
-        P.hot_state = 1;
-        return aoclsparse_status_success;
-    }
-    return build_hot_table(*A->mats[0], value_size(A->val_type), entries, team_threads ? team_threads : 128, true, st);
 }
 
 aoclsparse_status aoclsparse_b200_set_row_cuts(aoclsparse_matrix A, aoclsparse_int n_cuts, const aoclsparse_int *cuts)

@@ -350,13 +350,6 @@ namespace b200
         aoclsparse_int n_strat[4] = {0, 0, 0, 0};
         aoclsparse_int max_block_rows = 0; // most rows any block holds (sizes the staged row_ptr slice)
         int            pdl              = 1; // programmatic dependent launch of the multiply kernel (tuning knob)
-        // hot-column table for gather-bound (power-law) matrices (hot.cu): 0 entries = not built
-        aoclsparse_int hot_entries = 0;
-        int            hot_team    = 128; // threads per team of the persistent kernel (128 or 256)
-        int            hot_state   = 0;   // 0 not analysed, 1 analysed (built or rejected)
-        double         hot_mass    = 0.0; // fraction of stored entries whose column is in the table
-        dev_buf        hot_cols;          // int[hot_entries]: column of every table slot
-        dev_buf        col_hot;           // int[nnz]: column array with the hot columns replaced by HOT_BIT | slot
         // diagonal-code copy of col_idx (plan.cu, build_diag_codes): one byte per stored entry indexing the table of the
         // matrix's distinct (col - row) offsets.  Built by aoclsparse_optimize when every block is thread-per-row and
         // there are at most 256 distinct offsets (stencils, banded matrices); the multiply then streams 1 instead of 4
@@ -554,14 +547,6 @@ namespace b200
                                       const aoclsparse_int *row_ptr,
                                       const aoclsparse_int *col_idx,
                                       const void           *val);
-
-    // hot.cu -- hot-column table (analysis) and the persistent kernel that keeps it in shared memory
-    constexpr size_t HOT_TABLE_BYTES  = 65536; // default table size
-    constexpr bool   HOT_BY_DEFAULT   = false; // aoclsparse_optimize builds the table without being asked (AOCLSPARSE_B200_HOT overrides)
-    constexpr int    HOT_MIN_MASS_PCT = 15;    // the table must cover at least this share of the stored entries
-    aoclsparse_status build_hot_table(dev_csr &A, size_t elem_size, long long entries, int team_threads, bool force, cudaStream_t st);
-    template <typename T>
-    aoclsparse_status launch_hot(const dev_csr &A, const T *x, T *y, T alpha, T beta, cudaStream_t st);
 
     // clean.cu
     aoclsparse_status ensure_clean(aoclsparse_matrix A, cudaStream_t st);

@@ -147,23 +147,6 @@ namespace b200
             if(b1 <= b0)
                 return aoclsparse_status_success;
             const int bz = is_zero(beta) ? 1 : 0;
-            // hot-column table (aoclsparse_optimize on a power-law matrix, hot.cu): persistent kernel with the table in
-            // shared memory; whole matrix only, real value types
-            if constexpr(!vt<T>::is_complex)
-            {
-                if(!generic && !push_dst && P.hot_entries > 0 && b0 == 0 && b1 == P.n_blocks)
-                {
-                    B200_TRY(launch_hot<T>(A, x, y, alpha, beta, st));
-                    if(P.n_long_rows > 0)
-                    {
-                        const long long threads = (long long)P.n_long_rows * 32;
-                        finish_long_rows_kernel<T><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(
-                            P.n_long_rows, P.long_rows.as<int4>(), P.partials.as<T>(), x, y, alpha, beta, bz, 0, A.n, row_lo, row_hi);
-                        B200_LAUNCHED();
-                    }
-                    return aoclsparse_status_success;
-                }
-            }
             // diagonal-code copy (aoclsparse_optimize on a banded / stencil matrix): 1 instead of 4 index bytes per entry
             const bool coded = !generic && P.n_codes > 0 && P.n_strat[STRAT_THREAD] == P.n_blocks;
             if(coded && push_dst)

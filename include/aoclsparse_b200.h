@@ -52,9 +52,6 @@ typedef struct aoclsparse_b200_matrix_info_
     aoclsparse_int n_long_rows;     /* rows split across CTAs                                   */
     aoclsparse_int n_diag_codes;    /* diagonal-code copy of col_idx (one byte per entry indexing a table of the
                                        distinct col - row offsets): table entries, 0 = not built / not applicable */
-    aoclsparse_int hot_entries;     /* hot-column table for power-law matrices (csrc/hot.cu): entries of x the persistent
-                                       kernel keeps in shared memory, 0 = not built                              */
-    aoclsparse_int hot_mass_ppm;    /* stored entries whose column is in that table, parts per million            */
 } aoclsparse_b200_matrix_info;
 
 /* Diagonal-code copy of the stored column indices, built by aoclsparse_optimize for banded / stencil matrices (every
@@ -165,15 +162,6 @@ DLL_PUBLIC int aoclsparse_b200_effective_doid(int mat_doid, int req_doid);
 DLL_PUBLIC aoclsparse_status aoclsparse_b200_set_x_window(aoclsparse_matrix A,
                                                           aoclsparse_int    col_lo,
                                                           aoclsparse_int    col_hi);
-
-/* Hot-column table of a real-valued handle (csrc/hot.cu): the `entries` most frequently stored columns get a slot in a
- * table the plain general product then keeps in shared memory (one persistent CTA per SM, `team_threads` = 128 or 256
- * threads per team, 0 = default).  aoclsparse_optimize builds it by itself for power-law matrices with an mv hint; this
- * call builds it unconditionally (any size, any column distribution) or, with entries = 0, drops it.  The stored matrix is
- * not changed and products are bit-identical with and without the table. */
-DLL_PUBLIC aoclsparse_status aoclsparse_b200_set_hot_table(aoclsparse_matrix A,
-                                                           aoclsparse_int    entries,
-                                                           aoclsparse_int    team_threads);
 
 /* Forces row-block boundaries at the given rows (ascending, within (0, m)) so that row ranges can
  * be multiplied separately; must be called before aoclsparse_optimize. */

@@ -991,61 +991,6 @@ def test_config3_rmat_float(lib, oracle):
     assert info.n_long_rows > 0 and info.n_product_blocks > 0  # hub rows are split, skewed blocks use product
 
 
-@pytest.mark.parametrize("p,team,entries", [("s", 128, 2048), ("s", 256, 1000), ("s", 64, 3000), ("d", 128, 4096), ("d", 256, 512)])
-@pytest.mark.parametrize("beta", [0.0, -0.5])
-def test_hot_column_table_kernel(lib, oracle, p, team, entries, beta):
-    """csrc/hot.cu: the persistent kernel that keeps the x entries of the most frequent columns in shared memory against
-    the row-block kernel (same products; row sums may be associated differently, so a few ulps of the row scale) and
-    against the oracle; every row strategy occurs in the R-MAT plan (thread, warp, product, split rows)"""
-    import torch
-    dt = np.float32 if p == "s" else np.float64
-    rp, col, val = gen_np.rmat_csr(15)
-    val = val.astype(dt)
-    m = len(rp) - 1
-    x = gen_np.uniform(1, 0, m, dt)
-    y0 = gen_np.uniform(2, 0, m, dt) if beta else np.full(m, np.nan, dt)
-    st, h = lib.create_csr(p, 0, m, m, len(col), rp, col, val)
-    assert st == 0
-    d = lib.create_descr()
-    assert lib.set_mv_hint(h, 111, d, 1000) == 0 and lib.optimize(h) == 0
-    dx = torch.from_numpy(x).cuda()
-
-    def product():
-        dy = torch.from_numpy(y0.copy()).cuda()
-        assert lib.mv(p, 111, 1.5, h, d, dx.data_ptr(), beta, dy.data_ptr()) == 0, lib.last_error()
-        torch.cuda.synchronize()
-        return dy.cpu().numpy()
-    assert lib.set_hot_table(h, 0) == 0
-    plain = product()
-    assert lib.matrix_info(h).hot_entries == 0
-    assert lib.set_hot_table(h, entries, team) == 0, lib.last_error()
-    info = lib.matrix_info(h)
-    assert info.hot_entries == (entries & ~3) and info.hot_mass_ppm > 0
-    assert info.n_long_rows > 0 and info.n_product_blocks > 0 and info.n_warp_blocks > 0
-    before = lib.launch_count()
-    hot = product()
-    assert lib.launch_count() - before == 2  # the persistent kernel + the split rows' finish kernel
-    yo = y0.astype(dt).copy() if beta else np.zeros(m, dt)
-    oracle.csrmv(111, 1.5, m, m, 0, rp, col, val, 0, 0, 0, x, beta, yo)
-    den = oracle_py.row_scale(rp, col, val.astype(np.float64), x.astype(np.float64), 0, beta, y0 if beta else None) * 1.5
-    den = np.where(den > 0, den, 1)
-    tol = 1e-5 if p == "s" else 1e-12
-    assert np.max(np.abs(hot.astype(np.float64) - yo) / den) <= tol
-    assert np.max(np.abs(hot.astype(np.float64) - plain.astype(np.float64)) / den) <= 16 * np.finfo(dt).eps
-    # values change, pattern stays: the table (pattern-only) survives aoclsparse_?update_values
-    assert lib.update_values(p, h, len(col), (val * 2).astype(dt)) == 0
-    twice = product()
-    assert lib.matrix_info(h).hot_entries == (entries & ~3)
-    if not beta:
-        assert np.array_equal(twice.view(np.uint8), (hot * 2).astype(dt).view(np.uint8))
-    # complex handles have no table
-    lib.destroy(h)
-    st, hz = lib.create_csr("z", 0, m, m, len(col), rp, col, val.astype(np.complex128))
-    assert st == 0 and lib.set_hot_table(hz, 64) == 1  # aoclsparse_status_not_implemented
-    lib.destroy(hz)
-    lib.destroy_descr(d)
-
-
 def test_config5_iterated_1_10_100(lib):
     """SURVEY 8(d) parity protocol for the iterated case: x <- A x / 12 on a 7-point stencil, compared with the host
     product after 1, 10 and 100 iterations; the tolerance grows with the iteration count (every iteration adds one
