@@ -50,7 +50,8 @@ class MatrixInfo(C.Structure):
                 ("block_nnz", C.c_int32), ("block_rows", C.c_int32), ("n_blocks", C.c_int32),
                 ("n_thread_blocks", C.c_int32), ("n_warp_blocks", C.c_int32),
                 ("n_product_blocks", C.c_int32), ("n_long_segments", C.c_int32),
-                ("n_long_rows", C.c_int32), ("n_diag_codes", C.c_int32)]
+                ("n_long_rows", C.c_int32), ("n_diag_codes", C.c_int32), ("n_entry_codes", C.c_int32), ("e_block_nnz", C.c_int32),
+                ("e_block_rows", C.c_int32), ("e_n_blocks", C.c_int32)]
 
 
 class MmTilesInfo(C.Structure):
@@ -162,6 +163,8 @@ class AoclSparse:
             L.aoclsparse_b200_get_plan.argtypes = [vp, i32, vp, vp, C.POINTER(i32)]
             L.aoclsparse_b200_doid.argtypes = [vp, ci, ci]
             L.aoclsparse_b200_get_diag_codes.argtypes = [vp, C.POINTER(i32), vp, vp]
+            L.aoclsparse_b200_get_entry_codes.argtypes = [vp, C.POINTER(i32), vp, vp, vp]
+            L.aoclsparse_b200_get_entry_plan.argtypes = [vp, i32, vp, vp, C.POINTER(i32)]
             L.aoclsparse_b200_get_clean_csr.argtypes = [vp, C.POINTER(i32), C.POINTER(ci), vp, vp, vp, vp, vp]
             L.aoclsparse_b200_set_x_window.argtypes = [vp, i32, i32]
             L.aoclsparse_b200_set_row_cuts.argtypes = [vp, i32, vp]
@@ -399,6 +402,16 @@ class AoclSparse:
         assert st == 0, st
         return desc[: n.value], kind[: n.value]
 
+    def get_entry_plan(self, h):
+        """(desc, kind) of the block plan of the entry-coded kernels; empty arrays when there is none"""
+        n = C.c_int32(0)
+        assert self.lib.aoclsparse_b200_get_entry_plan(h, 0, None, None, C.byref(n)) == 0
+        desc = np.zeros((max(n.value, 1), 4), dtype=np.int32)
+        kind = np.zeros(max(n.value, 1), dtype=np.int32)
+        if n.value:
+            assert self.lib.aoclsparse_b200_get_entry_plan(h, n.value, ptr(desc), ptr(kind), C.byref(n)) == 0
+        return desc[: n.value], kind[: n.value]
+
     def get_diag_codes(self, h, nnz):
         """(offsets, codes) of the diagonal-code copy, or (None, None) when the handle has none"""
         n = C.c_int32(0)
@@ -409,6 +422,18 @@ class AoclSparse:
         codes = np.zeros(max(nnz, 1), np.uint8)
         assert self.lib.aoclsparse_b200_get_diag_codes(h, C.byref(n), ptr(offs), ptr(codes)) == 0, self.last_error()
         return offs, codes[:nnz]
+
+    def get_entry_codes(self, h, nnz, dtype):
+        """(offsets, values, ecodes) of the entry-code copy (values as elements of `dtype`), or (None, None, None)"""
+        n = C.c_int32(0)
+        assert self.lib.aoclsparse_b200_get_entry_codes(h, C.byref(n), None, None, None) == 0
+        if n.value == 0:
+            return None, None, None
+        offs = np.zeros(n.value, np.int32)
+        vals = np.zeros(n.value, dtype)
+        ecodes = np.zeros(max(nnz, 1), np.uint8)
+        assert self.lib.aoclsparse_b200_get_entry_codes(h, C.byref(n), ptr(offs), ptr(vals), ptr(ecodes)) == 0, self.last_error()
+        return offs, vals, ecodes[:nnz]
 
     def get_clean_csr(self, h, m, dtype=np.float64):
         nnz, isint = C.c_int32(0), C.c_int(0)

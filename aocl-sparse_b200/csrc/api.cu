@@ -98,13 +98,21 @@ namespace b200
     {
         {
             std::shared_lock<std::shared_mutex> rl(A->guard);
-            if(A->mats[0]->plan.valid)
+            if(A->mats[0]->plan.valid && !A->mats[0]->plan.ecodes_stale)
                 return aoclsparse_status_success;
         }
         std::unique_lock<std::shared_mutex> wl(A->guard);
-        if(A->mats[0]->plan.valid)
+        dev_csr                            &M = *A->mats[0];
+        if(M.plan.valid && M.plan.ecodes_stale)
+        {
+            // the stored values changed (aoclsparse_?update_values, aoclsparse_?set_value) since the entry-code copy was
+            // built: encode them again; if they no longer fit a 256-entry table the multiply goes back to the kernel that
+            // streams the values (diagonal-code copy, the handle's main plan)
+            B200_TRY(build_entry_codes(M, value_size(A->val_type), A->max_row_nnz, A->row_cuts, st));
+        }
+        if(M.plan.valid)
             return aoclsparse_status_success;
-        return build_plan(*A->mats[0], value_size(A->val_type), A->max_row_nnz, -1, A->row_cuts, st);
+        return build_plan(M, value_size(A->val_type), A->max_row_nnz, -1, A->row_cuts, st);
     }
 
     namespace
@@ -257,6 +265,8 @@ namespace b200
             delete A->mats[i];
         A->mats.resize(1);
         A->mats[0]->tiles = b200::mesh_tiles(); // holds a copy of the values
+        if(A->mats[0]->plan.n_ecodes > 0)
+            A->mats[0]->plan.ecodes_stale = true; // the entry-code copy is re-encoded before the next multiply (ensure_plan)
         A->clean = b200::clean_csr();
         for(auto &h : A->hints)
             h.done = false;
@@ -711,6 +721,13 @@ aoclsparse_status aoclsparse_b200_get_matrix_info(const aoclsparse_matrix A, aoc
         info->n_long_segments  = P.n_long_segments;
         info->n_long_rows      = P.n_long_rows;
         info->n_diag_codes     = P.n_codes;
+        info->n_entry_codes    = P.ecodes_stale ? 0 : P.n_ecodes;
+        if(P.eplan && P.n_ecodes > 0)
+        {
+            info->e_block_nnz  = P.eplan->block_nnz;
+            info->e_block_rows = P.eplan->block_rows;
+            info->e_n_blocks   = P.eplan->n_blocks;
+        }
     }
     return aoclsparse_status_success;
 }
@@ -739,6 +756,32 @@ aoclsparse_status aoclsparse_b200_get_plan(const aoclsparse_matrix A,
     return aoclsparse_status_success;
 }
 
+aoclsparse_status aoclsparse_b200_get_entry_plan(const aoclsparse_matrix A,
+                                                 aoclsparse_int          capacity,
+                                                 aoclsparse_int         *block_desc,
+                                                 aoclsparse_int         *block_kind,
+                                                 aoclsparse_int         *n_blocks)
+{
+    if(!A || !n_blocks)
+        return aoclsparse_status_invalid_pointer;
+    std::shared_lock<std::shared_mutex> rl(A->guard);
+    const row_block_plan               &M = A->mats[0]->plan;
+    *n_blocks                             = 0;
+    if(!M.valid || !M.eplan || M.n_ecodes <= 0)
+        return aoclsparse_status_success;
+    const row_block_plan &P = *M.eplan;
+    *n_blocks               = P.n_blocks;
+    if(capacity < P.n_blocks)
+        return (block_desc || block_kind) ? aoclsparse_status_invalid_size : aoclsparse_status_success;
+    cudaStream_t st = current_stream();
+    if(block_desc && P.n_blocks > 0)
+        B200_CUDA(cudaMemcpyAsync(block_desc, P.desc.p, sizeof(int4) * (size_t)P.n_blocks, cudaMemcpyDeviceToHost, st));
+    if(block_kind && P.n_blocks > 0)
+        B200_CUDA(cudaMemcpyAsync(block_kind, P.kind.p, sizeof(int) * (size_t)P.n_blocks, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    return aoclsparse_status_success;
+}
+
 aoclsparse_status aoclsparse_b200_get_diag_codes(const aoclsparse_matrix A,
                                                  aoclsparse_int         *n_codes,
                                                  aoclsparse_int         *offsets,
@@ -756,6 +799,30 @@ aoclsparse_status aoclsparse_b200_get_diag_codes(const aoclsparse_matrix A,
         B200_CUDA(cudaMemcpyAsync(offsets, P.code_offsets.p, sizeof(int) * (size_t)P.n_codes, cudaMemcpyDeviceToHost, st));
     if(codes)
         B200_CUDA(cudaMemcpyAsync(codes, P.codes.p, (size_t)A->mats[0]->nnz, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    return aoclsparse_status_success;
+}
+
+aoclsparse_status aoclsparse_b200_get_entry_codes(const aoclsparse_matrix A,
+                                                  aoclsparse_int         *n_pairs,
+                                                  aoclsparse_int         *offsets,
+                                                  void                   *values,
+                                                  unsigned char          *ecodes)
+{
+    if(!A || !n_pairs)
+        return aoclsparse_status_invalid_pointer;
+    std::shared_lock<std::shared_mutex> rl(A->guard);
+    const row_block_plan               &P = A->mats[0]->plan;
+    *n_pairs                              = (P.valid && !P.ecodes_stale) ? P.n_ecodes : 0;
+    if(*n_pairs == 0 || (!offsets && !values && !ecodes))
+        return aoclsparse_status_success;
+    cudaStream_t st = current_stream();
+    if(offsets)
+        B200_CUDA(cudaMemcpyAsync(offsets, P.etab_off.p, sizeof(int) * (size_t)P.n_ecodes, cudaMemcpyDeviceToHost, st));
+    if(values)
+        B200_CUDA(cudaMemcpyAsync(values, P.etab_val.p, value_size(A->val_type) * (size_t)P.n_ecodes, cudaMemcpyDeviceToHost, st));
+    if(ecodes)
+        B200_CUDA(cudaMemcpyAsync(ecodes, P.ecodes.p, (size_t)A->mats[0]->nnz, cudaMemcpyDeviceToHost, st));
     B200_CUDA(cudaStreamSynchronize(st));
     return aoclsparse_status_success;
 }

@@ -358,6 +358,19 @@ namespace b200
         int            code_state = 0; // 0 not analysed, 1 analysed (built or found not applicable)
         dev_buf        codes;        // unsigned char[nnz]
         dev_buf        code_offsets; // int[256], ascending, unused tail repeats the last entry
+        // entry-code copy (plan.cu, build_entry_codes), only next to the diagonal-code copy: one byte per stored entry
+        // indexing the table of the matrix's distinct (col - row, value) pairs (<= 256; a constant-coefficient stencil has
+        // as many as it has points).  The multiply then streams 1 instead of 4 + sizeof(T) bytes per entry and decodes the
+        // identical column and value.  Depends on the VALUES: marked stale when they change and rebuilt before the next
+        // multiply (api.cu, ensure_plan).
+        aoclsparse_int n_ecodes     = 0;     // table entries in use; 0 = not built / not applicable
+        bool           ecodes_stale = false; // the stored values changed since the copy was built
+        dev_buf        ecodes;               // unsigned char[nnz]
+        dev_buf        etab_off;             // int[256]: col - row of every pair (ascending; ties by value pattern)
+        dev_buf        etab_val;             // T[256]: value of every pair
+        // the entry-coded kernels run on a block plan of their own (one staged byte per entry: much larger blocks,
+        // bounded by rows); everything else -- other kernels, sub-range launches -- keeps this plan
+        std::unique_ptr<row_block_plan> eplan;
         int            threads     = 256; // CTA size of the multiply kernel (tuning knob)
         int            stream_hint = 1;   // tag the val/col stream evict-first in L2 (tuning knob)
         dev_buf        desc;      // int4 per block: first row, end row, first nnz, end nnz
@@ -506,7 +519,8 @@ namespace b200
                                  const std::vector<aoclsparse_int> &row_cuts,
                                  cudaStream_t                       st,
                                  aoclsparse_int                     block_nnz_override = 0,
-                                 bool                               coded              = false);
+                                 int                                coded              = 0, // block size for: 0 val + col, 1 val + column codes, 2 entry codes
+                                 row_block_plan                    *target             = nullptr); // default: A.plan
     // plan + (when the matrix has at most 256 distinct col - row offsets and every block comes out thread-per-row) the
     // diagonal-code copy, with the block size that copy wants; falls back to the plain plan otherwise
     aoclsparse_status build_plan_with_codes(dev_csr                           &A,
@@ -518,13 +532,17 @@ namespace b200
     aoclsparse_status probe_diag_offsets(const dev_csr &A, std::vector<int> &offs, cudaStream_t st);
     // optional second pass of the analysis: the diagonal-code copy of A's column indices (needs a valid plan)
     aoclsparse_status build_diag_codes(dev_csr &A, cudaStream_t st);
+    // optional third pass: the entry-code copy (needs the diagonal-code copy); (re)probes the values
+    aoclsparse_status build_entry_codes(dev_csr &A, size_t elem_size, aoclsparse_int max_row_nnz, const std::vector<aoclsparse_int> &row_cuts, cudaStream_t st);
+    // the sorted distinct bit patterns of A's values (zero-extended to 64 bits), empty when there are more than 256
+    aoclsparse_status probe_values(const dev_csr &A, size_t elem_size, std::vector<unsigned long long> &vals, cudaStream_t st);
     void              plan_parameters(size_t          elem_size,
                                       aoclsparse_int  m,
                                       aoclsparse_int  nnz,
                                       aoclsparse_int  max_row_nnz,
                                       aoclsparse_int &block_nnz,
                                       aoclsparse_int &block_rows,
-                                      bool            coded = false);
+                                      int             coded = 0);
 
     // transpose.cu -- device csr -> csc (= transposed csr), optional conjugation
     aoclsparse_status transpose_csr(const dev_csr &A, int val_type, bool conj, dev_csr &out, cudaStream_t st);

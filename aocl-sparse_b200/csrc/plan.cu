@@ -29,14 +29,42 @@
 
 namespace b200
 {
+    long long ctas_per_wave(size_t elem_size, aoclsparse_int T, int coded);
+
     void plan_parameters(size_t          elem_size,
                          aoclsparse_int  m,
                          aoclsparse_int  nnz,
                          aoclsparse_int  max_row_nnz,
                          aoclsparse_int &block_nnz,
                          aoclsparse_int &block_rows,
-                         bool            coded)
+                         int             coded)
     {
+        if(coded == 2)
+        {
+            // Entry codes: 1 staged byte per entry, so ~20 KB hold 20 224 entries and a block is bounded by its ROWS; T only
+            // caps blocks of long rows.  Measured on the 7-point 512^3 matrix (profiles/r02_entry_codes.txt): 1.17 ms with
+            // 512 rows per block, 0.95 ms with 2048 -- a CTA's prologue (descriptor, bulk copy, table, barrier) is latency
+            // that only larger blocks amortise -- while matrices of a few waves want the wave-fitted ~400-500 rows
+            // (build_plan).  So: as many rows as still leave 8 waves of CTAs, within [512, 2048]; matrices of less than one
+            // wave: one block per resident CTA (at least 64 rows).
+            block_nnz             = (aoclsparse_int)((24576 - 4096 - 32) / 256 * 256);
+            const long long slots = ctas_per_wave(elem_size, block_nnz, 2);
+            long long       r     = (long long)m / (8 * slots) / 64 * 64;
+            r                     = r < 512 ? 512 : (r > 2048 ? 2048 : r);
+            if((long long)m < slots * 512)
+            {
+                r = (((long long)m + slots - 1) / slots + 31) / 32 * 32;
+                r = r < 64 ? 64 : r;
+            }
+            block_rows = (aoclsparse_int)r;
+            if(const char *e = getenv("AOCLSPARSE_B200_BLOCK_ROWS")) // tuning knob for experiments
+            {
+                const long v = atol(e);
+                if(v >= 32 && v <= 4096)
+                    block_rows = (aoclsparse_int)v;
+            }
+            return;
+        }
         // staged bytes per entry = elem_size + 4 (column index); ~24 KB per CTA keeps 8 CTAs resident per SM,
         // which measured best on the 27-point stencil (profiles/r01_sweep_c2.txt): 2048 entries for 8-byte
         // values, 3072 for 4-byte, 1024 for 16-byte
@@ -223,10 +251,11 @@ namespace b200
     }
 
     // CTAs of the multiply kernel that are resident at once on the whole chip for block size T
-    long long ctas_per_wave(size_t elem_size, aoclsparse_int T, bool coded)
+    long long ctas_per_wave(size_t elem_size, aoclsparse_int T, int coded)
     {
-        const long long smem = coded ? 16 + (long long)(T + 32) * (long long)(elem_size + 1) + 1024 + 1024
-                                     : 16 + (long long)(T + 8) * (long long)(elem_size + 4) + 1024; // + 1 KB reserved per CTA
+        const long long smem = coded == 2 ? 16 + (long long)((T + 32 + 15) & ~15) + 256 * (elem_size >= 8 ? 16LL : 8LL) + 1024
+                               : coded    ? 16 + (long long)(T + 32) * (long long)(elem_size + 1) + 1024 + 1024
+                                          : 16 + (long long)(T + 8) * (long long)(elem_size + 4) + 1024; // + 1 KB reserved per CTA
         long long       c    = 232448 / smem;
         if(c > 8)
             c = 8; // 2048 threads per SM / 256
@@ -234,10 +263,15 @@ namespace b200
             c = 1;
         return 148 * c;
     }
-    bool wave_search_applies(size_t elem_size, aoclsparse_int nnz, aoclsparse_int T, bool coded)
+    bool wave_search_applies(size_t elem_size, aoclsparse_int nnz, aoclsparse_int T, int coded)
     {
         return (long long)nnz < 8 * ctas_per_wave(elem_size, T, coded) * (long long)T
                && (long long)nnz >= ctas_per_wave(elem_size, T, coded) * (long long)T;
+    }
+    // value-coded plans are bounded by rows: the same test on rows
+    bool row_wave_search_applies(size_t elem_size, aoclsparse_int m, aoclsparse_int T, aoclsparse_int R)
+    {
+        return R >= 512 && (long long)m < 8 * ctas_per_wave(elem_size, T, 2) * (long long)R && (long long)m >= ctas_per_wave(elem_size, T, 2) * (long long)R;
     }
 
     namespace
@@ -301,9 +335,10 @@ namespace b200
                                  const std::vector<aoclsparse_int> &row_cuts,
                                  cudaStream_t                       st,
                                  aoclsparse_int                     block_nnz_override,
-                                 bool                               coded)
+                                 int                                coded,
+                                 row_block_plan                    *target)
     {
-        row_block_plan &P = A.plan;
+        row_block_plan &P = target ? *target : A.plan;
         P                 = row_block_plan();
         plan_parameters(elem_size, A.m, A.nnz, max_row_nnz, P.block_nnz, P.block_rows, coded);
         if(block_nnz_override > 0)
@@ -340,8 +375,31 @@ namespace b200
         std::vector<int3>           counts;
         dev_buf                     d_seg, d_grid, d_cnt;
         aoclsparse_int              T = P.block_nnz;
-        const aoclsparse_int        R = P.block_rows;
-        if(block_nnz_override <= 0 && wave_search_applies(elem_size, A.nnz, T, coded) && !getenv("AOCLSPARSE_B200_BLOCK_NNZ"))
+        aoclsparse_int              R = P.block_rows;
+        if(coded == 2 && block_nnz_override <= 0 && row_wave_search_applies(elem_size, A.m, T, R) && !getenv("AOCLSPARSE_B200_BLOCK_ROWS")
+           && !getenv("AOCLSPARSE_B200_BLOCK_NNZ"))
+        {
+            // value-coded plan: blocks end at R rows, so the candidates are row counts R0 - 8k (same cost function)
+            long long      best_cost = -1;
+            aoclsparse_int best_R    = R;
+            for(int k = 0; k <= 24; ++k)
+            {
+                const aoclsparse_int Rk = R - 8 * k;
+                B200_TRY(count_pass(A, T, Rk, row_cuts, st, bounds, counts, d_seg, d_grid, d_cnt));
+                long long nbk = 0;
+                for(const int3 &c : counts)
+                    nbk += c.x;
+                const long long wave = ctas_per_wave(elem_size, T, 2);
+                const long long cost = (((nbk * 203 + 199) / 200 + wave - 1) / wave) * (long long)Rk;
+                if(best_cost < 0 || cost < best_cost)
+                {
+                    best_cost = cost;
+                    best_R    = Rk;
+                }
+            }
+            R = P.block_rows = best_R;
+        }
+        else if(coded != 2 && block_nnz_override <= 0 && wave_search_applies(elem_size, A.nnz, T, coded) && !getenv("AOCLSPARSE_B200_BLOCK_NNZ"))
         {
             long long      best_cost = -1;
             aoclsparse_int best_T    = T;
@@ -576,6 +634,238 @@ namespace b200
         return aoclsparse_status_success;
     }
 
+    // ------------------------------------------------------------------------------------------------------------
+    // Entry-code copy.  SPEC (restated by oracle/csr_oracle.c::oracle_entry_codes, compared bit for bit):
+    //   needs the diagonal-code copy (offset table D, at most 256 distinct col - row offsets) and a 4- or 8-byte value type
+    //   V = sorted (ascending, as unsigned integers) set of the distinct BIT PATTERNS of val[p] over all stored entries
+    //       (-0.0 and 0.0, and different NaNs, are different patterns); not applicable if |V| > 256 or a value has the
+    //       all-ones pattern
+    //   Q = sorted set of the distinct pairs (index of col[p] - r in D, index of val[p] in V), ascending by the first,
+    //       then by the second component; not applicable if |Q| > 256
+    //   ecodes[p] = index of p's pair in Q;  etab_off[i] = D[Q[i].first], etab_val[i] = V[Q[i].second]  (i < |Q|)
+    //   else: not applicable (n_ecodes = 0).
+    // ------------------------------------------------------------------------------------------------------------
+    namespace
+    {
+        constexpr int                VALUE_SLOTS = 1024;
+        constexpr unsigned long long VALUE_EMPTY = 0xffffffffffffffffull; // a value with this pattern: not applicable
+
+        template <typename U> // unsigned / unsigned long long: the value's bit pattern
+        __global__ void collect_values_kernel(long long nnz, const U *__restrict__ val, unsigned long long *table, int *ctl)
+        {
+            long long       i      = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+            const long long stride = (long long)gridDim.x * blockDim.x;
+            unsigned long long last0 = VALUE_EMPTY, last1 = VALUE_EMPTY; // the patterns seen last: skip the re-probe
+            for(; i < nnz; i += stride)
+            {
+                const unsigned long long v = (unsigned long long)val[i];
+                if(v == last0 || v == last1)
+                    continue;
+                if(*(volatile int *)(ctl + 1))
+                    return;
+                if(v == VALUE_EMPTY)
+                {
+                    atomicExch(ctl + 1, 1);
+                    return;
+                }
+                last1      = last0;
+                last0      = v;
+                unsigned h = (unsigned)((v * 0x9e3779b97f4a7c15ull) >> 54); // 10 bits
+                for(int probe = 0; probe < VALUE_SLOTS; ++probe, h = (h + 1) & (VALUE_SLOTS - 1))
+                {
+                    unsigned long long cur = *(volatile unsigned long long *)(table + h);
+                    if(cur == v)
+                        break;
+                    if(cur == VALUE_EMPTY)
+                    {
+                        cur = atomicCAS(table + h, VALUE_EMPTY, v);
+                        if(cur == VALUE_EMPTY)
+                        {
+                            if(atomicAdd(ctl, 1) + 1 > CODE_TABLE_MAX)
+                                atomicExch(ctl + 1, 1);
+                            break;
+                        }
+                        if(cur == v)
+                            break;
+                    }
+                }
+            }
+        }
+
+        __device__ __forceinline__ int value_index(const unsigned long long *sv, int n_vals, unsigned long long v)
+        {
+            int lo = 0, hi = n_vals - 1;
+            while(lo < hi)
+            {
+                const int mid = (lo + hi) >> 1;
+                if(sv[mid] < v)
+                    lo = mid + 1;
+                else
+                    hi = mid;
+            }
+            return lo;
+        }
+
+        // pass 1 (rank == nullptr): seen[diag code << 8 | value index] = 1 for every stored entry
+        // pass 2: ecodes[p] = rank[diag code << 8 | value index]
+        template <typename U>
+        __global__ void entry_pairs_kernel(long long nnz,
+                                           const U *__restrict__ val,
+                                           const unsigned char *__restrict__ dcodes,
+                                           const unsigned long long *__restrict__ sorted_vals,
+                                           int                  n_vals,
+                                           unsigned char       *seen,
+                                           const unsigned char *__restrict__ rank,
+                                           unsigned char       *ecodes)
+        {
+            __shared__ unsigned long long sv[CODE_TABLE_MAX];
+            for(int i = threadIdx.x; i < CODE_TABLE_MAX; i += blockDim.x)
+                sv[i] = sorted_vals[i];
+            __syncthreads();
+            long long       i      = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+            const long long stride = (long long)gridDim.x * blockDim.x;
+            for(; i < nnz; i += stride)
+            {
+                const int pair = ((int)dcodes[i] << 8) | value_index(sv, n_vals, (unsigned long long)val[i]);
+                if(rank)
+                    ecodes[i] = rank[pair];
+                else if(!seen[pair])
+                    seen[pair] = 1;
+            }
+        }
+
+        inline unsigned value_grid(long long nnz)
+        {
+            long long b = (nnz + 255) / 256;
+            if(b > 148LL * 16)
+                b = 148LL * 16;
+            return (unsigned)(b < 1 ? 1 : b);
+        }
+    }
+
+    aoclsparse_status probe_values(const dev_csr &A, size_t elem_size, std::vector<unsigned long long> &vals, cudaStream_t st)
+    {
+        vals.clear();
+        if(A.nnz <= 0 || (elem_size != 4 && elem_size != 8))
+            return aoclsparse_status_success;
+        if(const char *e = getenv("AOCLSPARSE_B200_ENTRY_CODES")) // A/B knob
+            if(atoi(e) == 0)
+                return aoclsparse_status_success;
+        dev_buf work;
+        B200_TRY(work.alloc(sizeof(unsigned long long) * (VALUE_SLOTS + 1)));
+        unsigned long long *table = work.as<unsigned long long>();
+        int                *ctl   = reinterpret_cast<int *>(table + VALUE_SLOTS);
+        std::vector<unsigned long long> h((size_t)VALUE_SLOTS + 1, VALUE_EMPTY);
+        h[VALUE_SLOTS] = 0; // ctl[0] = distinct patterns so far, ctl[1] = give up
+        B200_CUDA(cudaMemcpyAsync(table, h.data(), sizeof(unsigned long long) * h.size(), cudaMemcpyHostToDevice, st));
+        if(elem_size == 8)
+            collect_values_kernel<unsigned long long><<<value_grid(A.nnz), 256, 0, st>>>(A.nnz, A.val.as<unsigned long long>(), table, ctl);
+        else
+            collect_values_kernel<unsigned><<<value_grid(A.nnz), 256, 0, st>>>(A.nnz, A.val.as<unsigned>(), table, ctl);
+        B200_LAUNCHED();
+        B200_CUDA(cudaMemcpyAsync(h.data(), table, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost, st));
+        B200_CUDA(cudaStreamSynchronize(st));
+        const int n_seen = (int)(h[VALUE_SLOTS] & 0xffffffffull), gave_up = (int)(h[VALUE_SLOTS] >> 32);
+        if(gave_up != 0 || n_seen <= 0 || n_seen > CODE_TABLE_MAX)
+            return aoclsparse_status_success; // too many distinct values: keep the value stream
+        for(int i = 0; i < VALUE_SLOTS; ++i)
+            if(h[i] != VALUE_EMPTY)
+                vals.push_back(h[i]);
+        if((int)vals.size() != n_seen)
+        {
+            vals.clear();
+            return aoclsparse_status_internal_error;
+        }
+        std::sort(vals.begin(), vals.end());
+        return aoclsparse_status_success;
+    }
+
+    aoclsparse_status build_entry_codes(dev_csr &A, size_t elem_size, aoclsparse_int max_row_nnz, const std::vector<aoclsparse_int> &row_cuts, cudaStream_t st)
+    {
+        row_block_plan &P = A.plan;
+        P.n_ecodes        = 0;
+        P.ecodes_stale    = false;
+        P.ecodes.release();
+        P.etab_off.release();
+        P.etab_val.release();
+        if(!P.valid || P.n_codes <= 0 || A.nnz <= 0)
+        {
+            P.eplan.reset();
+            return aoclsparse_status_success;
+        }
+        // the block plan of the entry-coded kernels depends on the pattern only: kept across re-encodings
+        if(!P.eplan)
+        {
+            std::unique_ptr<row_block_plan> E(new(std::nothrow) row_block_plan);
+            if(!E)
+                return aoclsparse_status_memory_error;
+            B200_TRY(build_plan(A, elem_size, max_row_nnz, -1, row_cuts, st, 0, 2, E.get()));
+            if(E->n_blocks <= 0 || E->n_strat[STRAT_THREAD] != E->n_blocks)
+                return aoclsparse_status_success; // some block is not thread-per-row at that block size
+            P.eplan = std::move(E);
+        }
+        std::vector<unsigned long long> vals;
+        B200_TRY(probe_values(A, elem_size, vals, st));
+        if(vals.empty())
+            return aoclsparse_status_success;
+        const int n_vals = (int)vals.size();
+        vals.resize(CODE_TABLE_MAX, vals.back());
+        dev_buf d_vals, d_seen, d_rank;
+        B200_TRY(d_vals.alloc(8 * CODE_TABLE_MAX));
+        B200_TRY(d_seen.alloc(65536));
+        B200_TRY(d_rank.alloc(65536));
+        B200_CUDA(cudaMemcpyAsync(d_vals.p, vals.data(), 8 * CODE_TABLE_MAX, cudaMemcpyHostToDevice, st));
+        B200_CUDA(cudaMemsetAsync(d_seen.p, 0, 65536, st));
+        auto pass = [&](const unsigned char *rank, unsigned char *out) -> aoclsparse_status {
+            if(elem_size == 8)
+                entry_pairs_kernel<unsigned long long><<<value_grid(A.nnz), 256, 0, st>>>(A.nnz, A.val.as<unsigned long long>(), P.codes.as<unsigned char>(),
+                                                                                      d_vals.as<unsigned long long>(), n_vals, d_seen.as<unsigned char>(), rank, out);
+            else
+                entry_pairs_kernel<unsigned><<<value_grid(A.nnz), 256, 0, st>>>(A.nnz, A.val.as<unsigned>(), P.codes.as<unsigned char>(),
+                                                                            d_vals.as<unsigned long long>(), n_vals, d_seen.as<unsigned char>(), rank, out);
+            B200_LAUNCHED();
+            return aoclsparse_status_success;
+        };
+        B200_TRY(pass(nullptr, nullptr));
+        std::vector<unsigned char> seen(65536), rank(65536, 0);
+        std::vector<int>           offs(CODE_TABLE_MAX);
+        B200_CUDA(cudaMemcpyAsync(seen.data(), d_seen.p, 65536, cudaMemcpyDeviceToHost, st));
+        B200_CUDA(cudaMemcpyAsync(offs.data(), P.code_offsets.p, sizeof(int) * CODE_TABLE_MAX, cudaMemcpyDeviceToHost, st));
+        B200_CUDA(cudaStreamSynchronize(st));
+        std::vector<int> pairs; // ascending pair ids = ascending (offset, value pattern)
+        for(int q = 0; q < 65536; ++q)
+            if(seen[q])
+                pairs.push_back(q);
+        if(pairs.empty() || pairs.size() > (size_t)CODE_TABLE_MAX)
+            return aoclsparse_status_success; // more than 256 distinct (offset, value) pairs
+        std::vector<int>                t_off(CODE_TABLE_MAX);
+        std::vector<unsigned long long> t_val(CODE_TABLE_MAX);
+        for(size_t i = 0; i < (size_t)CODE_TABLE_MAX; ++i)
+        {
+            const int q = pairs[i < pairs.size() ? i : pairs.size() - 1];
+            t_off[i]    = offs[q >> 8];
+            t_val[i]    = vals[q & 255];
+            if(i < pairs.size())
+                rank[q] = (unsigned char)i;
+        }
+        B200_TRY(P.etab_off.alloc(sizeof(int) * CODE_TABLE_MAX));
+        B200_TRY(P.etab_val.alloc(elem_size * CODE_TABLE_MAX));
+        B200_TRY(P.ecodes.alloc((size_t)A.nnz));
+        std::vector<unsigned> t_val32(CODE_TABLE_MAX);
+        for(int i = 0; i < CODE_TABLE_MAX; ++i)
+            t_val32[i] = (unsigned)t_val[i];
+        B200_CUDA(cudaMemcpyAsync(d_rank.p, rank.data(), 65536, cudaMemcpyHostToDevice, st));
+        B200_CUDA(cudaMemcpyAsync(P.etab_off.p, t_off.data(), sizeof(int) * CODE_TABLE_MAX, cudaMemcpyHostToDevice, st));
+        if(elem_size == 8)
+            B200_CUDA(cudaMemcpyAsync(P.etab_val.p, t_val.data(), 8 * CODE_TABLE_MAX, cudaMemcpyHostToDevice, st));
+        else
+            B200_CUDA(cudaMemcpyAsync(P.etab_val.p, t_val32.data(), 4 * CODE_TABLE_MAX, cudaMemcpyHostToDevice, st));
+        B200_TRY(pass(d_rank.as<unsigned char>(), P.ecodes.as<unsigned char>()));
+        B200_CUDA(cudaStreamSynchronize(st)); // host staging vectors are read by the copies above
+        P.n_ecodes = (aoclsparse_int)pairs.size();
+        return aoclsparse_status_success;
+    }
+
     aoclsparse_status build_plan_with_codes(dev_csr                           &A,
                                             size_t                             elem_size,
                                             aoclsparse_int                     max_row_nnz,
@@ -583,10 +873,13 @@ namespace b200
                                             const std::vector<aoclsparse_int> &row_cuts,
                                             cudaStream_t                       st)
     {
-        std::vector<int> offs;
+        std::vector<int>                offs;
+        std::vector<unsigned long long> vals;
         if(forced_strategy < 0 || forced_strategy == STRAT_THREAD)
             B200_TRY(probe_diag_offsets(A, offs, st));
-        B200_TRY(build_plan(A, elem_size, max_row_nnz, forced_strategy, row_cuts, st, 0, !offs.empty()));
+        if(!offs.empty())
+            B200_TRY(probe_values(A, elem_size, vals, st));
+        B200_TRY(build_plan(A, elem_size, max_row_nnz, forced_strategy, row_cuts, st, 0, offs.empty() ? 0 : 1));
         if(offs.empty())
         {
             A.plan.code_state = 1;
@@ -597,7 +890,10 @@ namespace b200
         {
             B200_TRY(build_plan(A, elem_size, max_row_nnz, forced_strategy, row_cuts, st));
             A.plan.code_state = 1;
+            return aoclsparse_status_success;
         }
+        if(!vals.empty())
+            B200_TRY(build_entry_codes(A, elem_size, max_row_nnz, row_cuts, st));
         return aoclsparse_status_success;
     }
 }

@@ -62,7 +62,7 @@ namespace b200
             return cache[key] = (long long)per_sm * sms;
         }
 
-        template <typename T, bool GENERIC, int NT, bool PUSH = false, bool CODED = false>
+        template <typename T, bool GENERIC, int NT, bool PUSH = false, bool CODED = false, bool ECODED = false>
         aoclsparse_status launch_row_blocks(const dev_csr &A,
                                             int            b0,
                                             int            b1,
@@ -75,14 +75,16 @@ namespace b200
                                             T             *push_dst  = nullptr,
                                             int            push_row0 = 0)
         {
-            const row_block_plan &P    = A.plan;
-            const int             cap  = P.block_nnz + (CODED ? 32 : 8);
-            const size_t          smem = CODED ? spmv_coded_smem_bytes(sizeof(T), P.block_nnz) : spmv_smem_bytes(sizeof(T), P.block_nnz);
+            const row_block_plan &M    = A.plan;                       // owns the code arrays
+            const row_block_plan &P    = ECODED ? *A.plan.eplan : A.plan; // the blocks this launch walks
+            const int             cap  = ECODED ? spmv_ecoded_cap(P.block_nnz) : P.block_nnz + (CODED ? 32 : 8);
+            const size_t          smem = ECODED ? spmv_ecoded_smem_bytes(sizeof(T), P.block_nnz)
+                                                : (CODED ? spmv_coded_smem_bytes(sizeof(T), P.block_nnz) : spmv_smem_bytes(sizeof(T), P.block_nnz));
             static std::atomic<size_t> configured{0};
             if(configured.load(std::memory_order_acquire) < smem)
             {
                 B200_CUDA(cudaFuncSetAttribute(
-                    spmv_row_blocks_kernel<T, GENERIC, NT, PUSH, CODED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    spmv_row_blocks_kernel<T, GENERIC, NT, PUSH, CODED, ECODED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 configured.store(smem, std::memory_order_release);
             }
             cudaLaunchConfig_t cfg = {};
@@ -100,9 +102,9 @@ namespace b200
             // could leave lines in an SM's L1 that launch k then hits through ld.global.nc after its
             // griddepcontrol.wait.  With more CTAs than fit the chip, the last CTA of launch k-1 cannot start before
             // launch k-2 has completed, so launch k (which starts after it) never overlaps k-2.
-            cfg.numAttrs = (P.pdl && (long long)(b1 - b0) > resident_ctas(spmv_row_blocks_kernel<T, GENERIC, NT, PUSH, CODED>, NT, smem)) ? 1 : 0;
+            cfg.numAttrs = (P.pdl && (long long)(b1 - b0) > resident_ctas(spmv_row_blocks_kernel<T, GENERIC, NT, PUSH, CODED, ECODED>, NT, smem)) ? 1 : 0;
             B200_CUDA(cudaLaunchKernelEx(&cfg,
-                                         spmv_row_blocks_kernel<T, GENERIC, NT, PUSH, CODED>,
+                                         spmv_row_blocks_kernel<T, GENERIC, NT, PUSH, CODED, ECODED>,
                                          (const int4 *)P.desc.as<int4>(),
                                          (const int *)P.kind.as<int>(),
                                          b0,
@@ -121,8 +123,10 @@ namespace b200
                                          P.stream_hint,
                                          push_dst,
                                          push_row0,
-                                         (const unsigned char *)P.codes.as<unsigned char>(),
-                                         (const int *)P.code_offsets.as<int>()));
+                                         (const unsigned char *)(ECODED ? M.ecodes.as<unsigned char>() : M.codes.as<unsigned char>()),
+                                         (const int *)(ECODED ? M.etab_off.as<int>() : M.code_offsets.as<int>()),
+                                         (const T *)M.etab_val.as<T>(),
+                                         (int)(ECODED ? M.n_ecodes : M.n_codes)));
             B200_LAUNCHED();
             return aoclsparse_status_success;
         }
@@ -148,8 +152,20 @@ namespace b200
                 return aoclsparse_status_success;
             const int bz = is_zero(beta) ? 1 : 0;
             // diagonal-code copy (aoclsparse_optimize on a banded / stencil matrix): 1 instead of 4 index bytes per entry
-            const bool coded = !generic && P.n_codes > 0 && P.n_strat[STRAT_THREAD] == P.n_blocks;
-            if(coded && push_dst)
+            const bool coded  = !generic && P.n_codes > 0 && P.n_strat[STRAT_THREAD] == P.n_blocks;
+            // entry-code copy (constant-coefficient stencils): 1 byte per entry instead of 4 + sizeof(T)
+            // (whole-matrix launches only: the entry-coded kernels walk a block plan of their own, P.eplan)
+            const bool ecoded = coded && P.n_ecodes > 0 && !P.ecodes_stale && P.eplan && sizeof(T) <= 8 && b0 == 0 && b1 == P.n_blocks && !push_dst;
+            if constexpr(sizeof(T) <= 8)
+            {
+                if(ecoded && P.eplan->threads == 128)
+                    B200_TRY((launch_row_blocks<T, false, 128, false, false, true>(A, 0, P.eplan->n_blocks, x, y, alpha, beta, rule, st)));
+                else if(ecoded)
+                    B200_TRY((launch_row_blocks<T, false, 256, false, false, true>(A, 0, P.eplan->n_blocks, x, y, alpha, beta, rule, st)));
+            }
+            if(ecoded)
+                ;
+            else if(coded && push_dst)
                 B200_TRY((launch_row_blocks<T, false, 256, true, true>(A, b0, b1, x, y, alpha, beta, rule, st, push_dst, row_lo)));
             else if(coded && P.threads == 128)
                 B200_TRY((launch_row_blocks<T, false, 128, false, true>(A, b0, b1, x, y, alpha, beta, rule, st)));
@@ -1269,7 +1285,10 @@ aoclsparse_status b200::sharded_step_launch(const double                  *alpha
     B200_TRY(ensure_plan(A, st));
     std::shared_lock<std::shared_mutex> rl(A->guard);
     const dev_csr                      &M = *A->mats[0];
-    const row_block_plan               &P = M.plan;
+    const row_block_plan               &P0 = M.plan;
+    // entry-code copy: the kernel walks the block plan built for it (same cuts)
+    const bool                          ec = P0.n_codes > 0 && P0.n_ecodes > 0 && !P0.ecodes_stale && P0.eplan && P0.eplan->cut_block.size() == 2;
+    const row_block_plan               &P  = ec ? *P0.eplan : P0;
     // needs exactly the cuts [h, m-h] and a plan whose blocks are all thread-per-row
     if(A->row_cuts.size() != 2 || P.cut_block.size() != 2 || P.n_strat[STRAT_THREAD] != P.n_blocks)
         return aoclsparse_status_not_implemented;
@@ -1295,15 +1314,18 @@ aoclsparse_status b200::sharded_step_launch(const double                  *alpha
         return aoclsparse_status_invalid_pointer;
     if(A->win_hi >= 0)
         x = x - A->win_lo;
-    const bool   coded = P.n_codes > 0;
-    const int    cap   = P.block_nnz + (coded ? 32 : 8);
-    const size_t smem  = coded ? spmv_coded_smem_bytes(sizeof(double), P.block_nnz) : spmv_smem_bytes(sizeof(double), P.block_nnz);
-    auto         kern  = coded ? spmv_sharded_step_kernel<double, true> : spmv_sharded_step_kernel<double, false>;
-    static std::atomic<size_t> configured[2] = {{0}, {0}};
-    if(configured[coded].load() < smem)
+    const bool   coded = P0.n_codes > 0 && !ec;
+    const int    cap   = ec ? spmv_ecoded_cap(P.block_nnz) : P.block_nnz + (coded ? 32 : 8);
+    const size_t smem  = ec ? spmv_ecoded_smem_bytes(sizeof(double), P.block_nnz)
+                            : (coded ? spmv_coded_smem_bytes(sizeof(double), P.block_nnz) : spmv_smem_bytes(sizeof(double), P.block_nnz));
+    auto         kern  = ec ? spmv_sharded_step_kernel<double, false, true>
+                            : (coded ? spmv_sharded_step_kernel<double, true, false> : spmv_sharded_step_kernel<double, false, false>);
+    static std::atomic<size_t> configured[3] = {{0}, {0}, {0}};
+    const int                  variant       = ec ? 2 : (coded ? 1 : 0);
+    if(configured[variant].load() < smem)
     {
         B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[coded].store(smem);
+        configured[variant].store(smem);
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim            = dim3((unsigned)P.n_blocks);
@@ -1329,8 +1351,10 @@ aoclsparse_status b200::sharded_step_launch(const double                  *alpha
                                  static_cast<double *>(ctl->push_left),
                                  static_cast<double *>(ctl->push_right),
                                  hc,
-                                 (const unsigned char *)P.codes.as<unsigned char>(),
-                                 (const int *)P.code_offsets.as<int>()));
+                                 (const unsigned char *)(ec ? P0.ecodes.as<unsigned char>() : P0.codes.as<unsigned char>()),
+                                 (const int *)(ec ? P0.etab_off.as<int>() : P0.code_offsets.as<int>()),
+                                 (const double *)P0.etab_val.as<double>(),
+                                 (int)(ec ? P0.n_ecodes : P0.n_codes)));
     B200_LAUNCHED();
     return aoclsparse_status_success;
 }
@@ -1365,7 +1389,10 @@ aoclsparse_status b200::sharded_iterate_launch(double                     alpha,
     B200_TRY(ensure_plan(A, st));
     std::shared_lock<std::shared_mutex> rl(A->guard);
     const dev_csr                      &M = *A->mats[0];
-    const row_block_plan               &P = M.plan;
+    const row_block_plan               &P0 = M.plan;
+    // entry-code copy: the kernel walks the block plan built for it (same cuts)
+    const bool                          ec = P0.n_codes > 0 && P0.n_ecodes > 0 && !P0.ecodes_stale && P0.eplan && P0.eplan->cut_block.size() == 2;
+    const row_block_plan               &P  = ec ? *P0.eplan : P0;
     if(A->row_cuts.size() != 2 || P.cut_block.size() != 2 || P.n_strat[STRAT_THREAD] != P.n_blocks || P.n_blocks < 1)
         return aoclsparse_status_not_implemented;
     iterate_ctl hc;
@@ -1392,15 +1419,18 @@ aoclsparse_status b200::sharded_iterate_launch(double                     alpha,
     // iteration 0 reads w_cur and writes the own rows of w_nxt; the neighbours receive into THEIR w_nxt (slot 1)
     const double *x0 = w_cur - shift, *x1 = w_nxt - shift;
     double       *y0 = w_nxt + own_offset, *y1 = w_cur + own_offset;
-    const bool   coded = P.n_codes > 0;
-    int          cap   = P.block_nnz + (coded ? 32 : 8);
-    const size_t smem  = coded ? spmv_coded_smem_bytes(sizeof(double), P.block_nnz) : spmv_smem_bytes(sizeof(double), P.block_nnz);
-    auto         kern  = coded ? spmv_sharded_iterate_kernel<double, true> : spmv_sharded_iterate_kernel<double, false>;
-    static std::atomic<size_t> configured[2] = {{0}, {0}};
-    if(configured[coded].load() < smem)
+    const bool   coded = P0.n_codes > 0 && !ec;
+    int          cap   = ec ? spmv_ecoded_cap(P.block_nnz) : P.block_nnz + (coded ? 32 : 8);
+    const size_t smem  = ec ? spmv_ecoded_smem_bytes(sizeof(double), P.block_nnz)
+                            : (coded ? spmv_coded_smem_bytes(sizeof(double), P.block_nnz) : spmv_smem_bytes(sizeof(double), P.block_nnz));
+    auto         kern  = ec ? spmv_sharded_iterate_kernel<double, false, true>
+                            : (coded ? spmv_sharded_iterate_kernel<double, true, false> : spmv_sharded_iterate_kernel<double, false, false>);
+    static std::atomic<size_t> configured[3] = {{0}, {0}, {0}};
+    const int                  variant       = ec ? 2 : (coded ? 1 : 0);
+    if(configured[variant].load() < smem)
     {
         B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[coded].store(smem);
+        configured[variant].store(smem);
     }
     long long grid = resident_ctas(kern, 256, smem);
     if(const char *e = getenv("AOCLSPARSE_B200_ITER_GRID"))
@@ -1425,9 +1455,11 @@ aoclsparse_status b200::sharded_iterate_launch(double                     alpha,
     double               *pl1     = static_cast<double *>(args.push_left[0]);
     double               *pr0     = static_cast<double *>(args.push_right[1]);
     double               *pr1     = static_cast<double *>(args.push_right[0]);
-    const unsigned char  *p_codes = P.codes.as<unsigned char>();
-    const int            *p_off   = P.code_offsets.as<int>();
-    void *params[] = {&p_desc, &cap, &p_rp, &p_col, &p_val, &x0, &x1, &y0, &y1, &alpha, &pl0, &pl1, &pr0, &pr1, &hc, &p_codes, &p_off};
+    const unsigned char  *p_codes = ec ? P0.ecodes.as<unsigned char>() : P0.codes.as<unsigned char>();
+    const int            *p_off   = ec ? P0.etab_off.as<int>() : P0.code_offsets.as<int>();
+    const double         *p_cval  = P0.etab_val.as<double>();
+    int                   n_table = (int)(ec ? P0.n_ecodes : P0.n_codes);
+    void *params[] = {&p_desc, &cap, &p_rp, &p_col, &p_val, &x0, &x1, &y0, &y1, &alpha, &pl0, &pl1, &pr0, &pr1, &hc, &p_codes, &p_off, &p_cval, &n_table};
     B200_CUDA(cudaLaunchCooperativeKernel((const void *)kern, dim3((unsigned)grid), dim3(256), params, smem, st));
     B200_LAUNCHED();
     *grid_out = (int)grid;

@@ -176,6 +176,22 @@ namespace b200
         return SMEM_HEADER + (size_t)(block_nnz + 32) * (elem_size + 1) + CODE_TABLE * sizeof(int);
     }
 
+    // ECODED variant (see spmv_row_blocks_kernel): one code byte per entry, then the table of (value, col - row) pairs
+    template <typename T>
+    struct alignas(sizeof(T) >= 8 ? 16 : 8) entry_pair
+    {
+        T   v;
+        int off;
+    };
+    inline int spmv_ecoded_cap(aoclsparse_int block_nnz)
+    {
+        return ((int)block_nnz + 32 + 15) & ~15;
+    }
+    inline size_t spmv_ecoded_smem_bytes(size_t elem_size, aoclsparse_int block_nnz)
+    {
+        return SMEM_HEADER + (size_t)spmv_ecoded_cap(block_nnz) + (size_t)CODE_TABLE * (elem_size >= 8 ? 16 : 8);
+    }
+
     // GENERIC == false: general matrix, no conjugation (the measured hot path)
     // GENERIC == true : entries filtered / conjugated by `rule` (triangular, symmetric, hermitian parts)
     // PUSH == true: every computed y[r] is also stored to push_dst[r - push_row0], a buffer that may live in a
@@ -185,7 +201,12 @@ namespace b200
     //                built by aoclsparse_optimize (plan.cu, build_diag_codes): one byte per stored entry, an index
     //                into the table of the matrix's distinct (col - row) offsets, so col = row + code_off[code] --
     //                the same column, bit for bit, from a quarter of the bytes.  `col` is then unused.
-    template <typename T, bool GENERIC, int NT, bool PUSH = false, bool CODED = false>
+    // ECODED == true (instead of CODED; 4- and 8-byte value types): the ENTRY-CODE copy (plan.cu, build_entry_codes): ONE
+    //                byte per stored entry, an index into the table of the matrix's distinct (col - row, value) pairs
+    //                (<= 256; a constant-coefficient stencil has as many as it has points), so col = row + pair.off and
+    //                val = pair.v -- the same column and the same value, bit for bit, from 1 instead of 4 + sizeof(T)
+    //                bytes.  `codes` is then that copy, `code_off` / `code_val` the table; `col` and `val` are unused.
+    template <typename T, bool GENERIC, int NT, bool PUSH = false, bool CODED = false, bool ECODED = false>
     __global__ void __launch_bounds__(NT) spmv_row_blocks_kernel(const int4 *__restrict__ desc,
                                                                           const int *__restrict__ kind,
                                                                           int block_first,
@@ -205,12 +226,114 @@ namespace b200
                                                                           T        *push_dst  = nullptr,
                                                                           int       push_row0 = 0,
                                                                           const unsigned char *__restrict__ codes = nullptr,
-                                                                          const int *__restrict__ code_off = nullptr)
+                                                                          const int *__restrict__ code_off = nullptr,
+                                                                          const T *__restrict__ code_val = nullptr,
+                                                                          int n_table = CODE_TABLE_MAX)
     {
         extern __shared__ __align__(16) unsigned char smem_raw[];
         uint64_t       *bar  = reinterpret_cast<uint64_t *>(smem_raw);
         T              *sval = reinterpret_cast<T *>(smem_raw + SMEM_HEADER);
         aoclsparse_int *scol = reinterpret_cast<aoclsparse_int *>(smem_raw + SMEM_HEADER + (size_t)cap * sizeof(T));
+
+        if constexpr(ECODED)
+        {
+            static_assert(!GENERIC && !CODED && sizeof(T) <= 8, "entry codes: plain general product, 4- / 8-byte values");
+            using pair_t                = entry_pair<T>;
+            const unsigned char *secode = smem_raw + SMEM_HEADER;
+            pair_t              *stab   = reinterpret_cast<pair_t *>(smem_raw + SMEM_HEADER + (size_t)cap);
+            const int            tid    = threadIdx.x;
+            const int4           d      = desc[blockIdx.x + block_first];
+            asm volatile("griddepcontrol.launch_dependents;");
+            // staged window [a, a+cnt): 16-entry granules keep the bulk copy 16-byte aligned
+            const int a   = d.z & ~15;
+            const int cnt = ((d.w - a) + 15) & ~15;
+            if(tid == 0)
+            {
+                mbar_init(bar, 1);
+                mbar_init_fence();
+                if(cnt > 0)
+                {
+                    mbar_expect_tx(bar, (unsigned)cnt);
+                    if(stream_hint)
+                        bulk_load_stream(const_cast<unsigned char *>(secode), codes + a, (unsigned)cnt, bar);
+                    else
+                        bulk_load(const_cast<unsigned char *>(secode), codes + a, (unsigned)cnt, bar);
+                }
+            }
+            for(int i = tid; i < n_table; i += NT)
+            {
+                pair_t pr;
+                pr.v    = code_val[i];
+                pr.off  = code_off[i];
+                stab[i] = pr;
+            }
+            __syncthreads();
+            // bounds (and y for beta != 0) of a thread's NEXT row are requested before its current row is reduced
+            int r     = d.x + tid;
+            int cur_s = 0, cur_e = 0;
+            T   cur_y = vt<T>::zero();
+            if(r < d.y)
+            {
+                cur_s = rp[r];
+                cur_e = rp[r + 1];
+            }
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            if(r < d.y && !beta_zero)
+                cur_y = y[r];
+            if(cnt > 0)
+                mbar_wait(bar, 0);
+            while(r < d.y)
+            {
+                const int rn    = r + NT;
+                int       nxt_s = 0, nxt_e = 0;
+                T         nxt_y = vt<T>::zero();
+                if(rn < d.y)
+                {
+                    nxt_s = rp[rn];
+                    nxt_e = rp[rn + 1];
+                    if(!beta_zero)
+                        nxt_y = y[rn];
+                }
+                int       j   = cur_s - a;
+                const int e   = cur_e - a;
+                T         acc = vt<T>::zero();
+                const T  *xr  = x + r; // x[col] = xr[col - row]
+                for(; j + 4 <= e; j += 4)
+                {
+                    const pair_t p0 = stab[secode[j]], p1 = stab[secode[j + 1]], p2 = stab[secode[j + 2]], p3 = stab[secode[j + 3]];
+                    const T      x0 = ldg_ro(xr + p0.off), x1 = ldg_ro(xr + p1.off), x2 = ldg_ro(xr + p2.off), x3 = ldg_ro(xr + p3.off);
+                    acc             = mad(p0.v, x0, acc);
+                    acc             = mad(p1.v, x1, acc);
+                    acc             = mad(p2.v, x2, acc);
+                    acc             = mad(p3.v, x3, acc);
+                }
+                if(j < e)
+                {
+                    // 1-3 entries left: issued together as well
+                    const int    n  = e - j;
+                    const pair_t p0 = stab[secode[j]];
+                    const pair_t p1 = stab[n > 1 ? secode[j + 1] : 0];
+                    const pair_t p2 = stab[n > 2 ? secode[j + 2] : 0];
+                    const T      x0 = ldg_ro(xr + p0.off);
+                    const T      x1 = n > 1 ? ldg_ro(xr + p1.off) : vt<T>::zero();
+                    const T      x2 = n > 2 ? ldg_ro(xr + p2.off) : vt<T>::zero();
+                    acc             = mad(p0.v, x0, acc);
+                    if(n > 1)
+                        acc = mad(p1.v, x1, acc);
+                    if(n > 2)
+                        acc = mad(p2.v, x2, acc);
+                }
+                const T out = axpby_out(alpha, acc, beta, beta_zero != 0, &cur_y);
+                y[r]        = out;
+                if constexpr(PUSH)
+                    push_dst[r - push_row0] = out;
+                r     = rn;
+                cur_s = nxt_s;
+                cur_e = nxt_e;
+                cur_y = nxt_y;
+            }
+            return;
+        }
 
         if constexpr(CODED)
         {
@@ -242,7 +365,7 @@ namespace b200
                     }
                 }
             }
-            for(int i = tid; i < CODE_TABLE; i += NT)
+            for(int i = tid; i < n_table; i += NT)
                 soff[i] = code_off[i];
             __syncthreads();
             int pre_s = 0, pre_e = 0;

@@ -88,7 +88,9 @@ namespace b200
 
     // CODED: the column stream is the diagonal-code copy (one byte per entry, col = row + code_off[code]; see
     // spmv_row_blocks_kernel)
-    template <typename T, bool CODED = false>
+    // EC (instead of CODED): the entry-code copy (one byte per entry indexing the table of the matrix's distinct
+    // (col - row, value) pairs; see spmv_row_blocks_kernel): `codes` is that copy, `code_off` / `code_val` the table
+    template <typename T, bool CODED = false, bool EC = false>
     __global__ void __launch_bounds__(256) spmv_sharded_step_kernel(const int4 *__restrict__ desc,
                                                                    int cap,
                                                                    const aoclsparse_int *__restrict__ rp,
@@ -101,15 +103,21 @@ namespace b200
                                                                    T       *push_right, // neighbour's halo for my last rows
                                                                    halo_ctl hc,
                                                                    const unsigned char *__restrict__ codes = nullptr,
-                                                                   const int *__restrict__ code_off = nullptr)
+                                                                   const int *__restrict__ code_off = nullptr,
+                                                                   const T *__restrict__ code_val = nullptr,
+                                                                   int n_table = CODE_TABLE_MAX)
     {
         constexpr int NT = 256;
+        static_assert(!(CODED && EC), "one code stream at a time");
+        using pair_t = entry_pair<T>;
         extern __shared__ __align__(16) unsigned char smem_raw[];
-        uint64_t            *bar   = reinterpret_cast<uint64_t *>(smem_raw);
-        T                   *sval  = reinterpret_cast<T *>(smem_raw + SMEM_HEADER);
-        aoclsparse_int      *scol  = reinterpret_cast<aoclsparse_int *>(smem_raw + SMEM_HEADER + (size_t)cap * sizeof(T));
-        const unsigned char *scode = smem_raw + SMEM_HEADER + (size_t)cap * sizeof(T);
-        int                 *soff  = reinterpret_cast<int *>(smem_raw + SMEM_HEADER + (size_t)cap * (sizeof(T) + 1));
+        uint64_t            *bar    = reinterpret_cast<uint64_t *>(smem_raw);
+        T                   *sval   = reinterpret_cast<T *>(smem_raw + SMEM_HEADER);
+        aoclsparse_int      *scol   = reinterpret_cast<aoclsparse_int *>(smem_raw + SMEM_HEADER + (size_t)cap * sizeof(T));
+        const unsigned char *scode  = smem_raw + SMEM_HEADER + (size_t)cap * sizeof(T);
+        int                 *soff   = reinterpret_cast<int *>(smem_raw + SMEM_HEADER + (size_t)cap * (sizeof(T) + 1));
+        const unsigned char *secode = smem_raw + SMEM_HEADER;                                          // EC
+        pair_t              *stab   = reinterpret_cast<pair_t *>(smem_raw + SMEM_HEADER + (size_t)cap); // EC
 
         const int tid = threadIdx.x;
         // launch order -> block: first boundary, last boundary, then the interior
@@ -132,7 +140,7 @@ namespace b200
         }
         const int4 d = desc[b];
         asm volatile("griddepcontrol.launch_dependents;");
-        constexpr int GR  = CODED ? 16 : 4; // entries per 16-byte granule of the narrowest staged array
+        constexpr int GR  = (CODED || EC) ? 16 : 4; // entries per 16-byte granule of the narrowest staged array
         const int     a   = d.z & ~(GR - 1);
         const int     cnt = ((d.w - a) + GR - 1) & ~(GR - 1);
         if(tid == 0)
@@ -141,7 +149,12 @@ namespace b200
             mbar_init_fence();
             if(cnt > 0)
             {
-                if constexpr(CODED)
+                if constexpr(EC)
+                {
+                    mbar_expect_tx(bar, (unsigned)cnt);
+                    bulk_load_stream(const_cast<unsigned char *>(secode), codes + a, (unsigned)cnt, bar);
+                }
+                else if constexpr(CODED)
                 {
                     mbar_expect_tx(bar, (unsigned)(cnt * (sizeof(T) + 1)));
                     bulk_load_stream(sval, val + a, (unsigned)(cnt * sizeof(T)), bar);
@@ -156,8 +169,16 @@ namespace b200
             }
         }
         if constexpr(CODED)
-            for(int i = tid; i < CODE_TABLE; i += NT)
+            for(int i = tid; i < n_table; i += NT)
                 soff[i] = code_off[i];
+        if constexpr(EC)
+            for(int i = tid; i < n_table; i += NT)
+            {
+                pair_t pr;
+                pr.v    = code_val[i];
+                pr.off  = code_off[i];
+                stab[i] = pr;
+            }
         __syncthreads();
         int pre_s = 0, pre_e = 0;
         if(d.x + tid < d.y)
@@ -181,12 +202,24 @@ namespace b200
         if(cnt > 0)
             mbar_wait(bar, 0);
 
-        // column of staged entry j of row r
-        auto col_at = [&](int r, int j) -> int {
-            if constexpr(CODED)
-                return r + soff[scode[j]];
+        // column and value of staged entry j of row r
+        auto entry_at = [&](int r, int j, int &c, T &v) {
+            if constexpr(EC)
+            {
+                const pair_t pr = stab[secode[j]];
+                c               = r + pr.off;
+                v               = pr.v;
+            }
+            else if constexpr(CODED)
+            {
+                c = r + soff[scode[j]];
+                v = sval[j];
+            }
             else
-                return scol[j];
+            {
+                c = scol[j];
+                v = sval[j];
+            }
         };
         T *push = side == 0 ? push_left : (side == 1 ? push_right : nullptr);
         const int push_row0 = side == 0 ? 0 : hc.last_row0;
@@ -202,15 +235,25 @@ namespace b200
                 T          acc   = vt<T>::zero();
                 for(; j + 4 <= e; j += 4)
                 {
-                    const int c0 = col_at(r, j), c1 = col_at(r, j + 1), c2 = col_at(r, j + 2), c3 = col_at(r, j + 3);
-                    const T   x0 = ldg_ro(x + c0), x1 = ldg_ro(x + c1), x2 = ldg_ro(x + c2), x3 = ldg_ro(x + c3);
-                    acc          = mad(sval[j], x0, acc);
-                    acc          = mad(sval[j + 1], x1, acc);
-                    acc          = mad(sval[j + 2], x2, acc);
-                    acc          = mad(sval[j + 3], x3, acc);
+                    int c0, c1, c2, c3;
+                    T   a0, a1, a2, a3;
+                    entry_at(r, j, c0, a0);
+                    entry_at(r, j + 1, c1, a1);
+                    entry_at(r, j + 2, c2, a2);
+                    entry_at(r, j + 3, c3, a3);
+                    const T x0 = ldg_ro(x + c0), x1 = ldg_ro(x + c1), x2 = ldg_ro(x + c2), x3 = ldg_ro(x + c3);
+                    acc        = mad(a0, x0, acc);
+                    acc        = mad(a1, x1, acc);
+                    acc        = mad(a2, x2, acc);
+                    acc        = mad(a3, x3, acc);
                 }
                 for(; j < e; ++j)
-                    acc = mad(sval[j], ldg_ro(x + col_at(r, j)), acc);
+                {
+                    int c0;
+                    T   a0;
+                    entry_at(r, j, c0, a0);
+                    acc = mad(a0, ldg_ro(x + c0), acc);
+                }
                 y[r] = mul(alpha, acc);
             }
         }
@@ -227,16 +270,25 @@ namespace b200
                 T          acc   = vt<T>::zero();
                 for(; j + 4 <= e; j += 4)
                 {
-                    const int c0 = col_at(r, j), c1 = col_at(r, j + 1), c2 = col_at(r, j + 2), c3 = col_at(r, j + 3);
-                    const T   x0 = boundary_x<T, false>(x, c0, hc.own_lo, hc.own_hi), x1 = boundary_x<T, false>(x, c1, hc.own_lo, hc.own_hi),
-                            x2 = boundary_x<T, false>(x, c2, hc.own_lo, hc.own_hi), x3 = boundary_x<T, false>(x, c3, hc.own_lo, hc.own_hi);
-                    acc          = mad(sval[j], x0, acc);
-                    acc          = mad(sval[j + 1], x1, acc);
-                    acc          = mad(sval[j + 2], x2, acc);
-                    acc          = mad(sval[j + 3], x3, acc);
+                    int c0, c1, c2, c3;
+                    T   a0, a1, a2, a3;
+                    entry_at(r, j, c0, a0);
+                    entry_at(r, j + 1, c1, a1);
+                    entry_at(r, j + 2, c2, a2);
+                    entry_at(r, j + 3, c3, a3);
+                    const T x0 = boundary_x<T, false>(x, c0, hc.own_lo, hc.own_hi), x1 = boundary_x<T, false>(x, c1, hc.own_lo, hc.own_hi), x2 = boundary_x<T, false>(x, c2, hc.own_lo, hc.own_hi), x3 = boundary_x<T, false>(x, c3, hc.own_lo, hc.own_hi);
+                    acc        = mad(a0, x0, acc);
+                    acc        = mad(a1, x1, acc);
+                    acc        = mad(a2, x2, acc);
+                    acc        = mad(a3, x3, acc);
                 }
                 for(; j < e; ++j)
-                    acc = mad(sval[j], boundary_x<T, false>(x, col_at(r, j), hc.own_lo, hc.own_hi), acc);
+                {
+                    int c0;
+                    T   a0;
+                    entry_at(r, j, c0, a0);
+                    acc = mad(a0, boundary_x<T, false>(x, c0, hc.own_lo, hc.own_hi), acc);
+                }
                 const T out = mul(alpha, acc);
                 y[r]        = out;
                 if(push)
@@ -294,7 +346,7 @@ namespace b200
         int             cta_fence_gpu;  // see boundary_release
     };
 
-    template <typename T, bool CODED>
+    template <typename T, bool CODED, bool EC = false>
     __global__ void __launch_bounds__(256) spmv_sharded_iterate_kernel(const int4 *__restrict__ desc,
                                                                       int cap,
                                                                       const aoclsparse_int *__restrict__ rp,
@@ -311,16 +363,22 @@ namespace b200
                                                                       T       *push_right1,
                                                                       iterate_ctl hc,
                                                                       const unsigned char *__restrict__ codes,
-                                                                      const int *__restrict__ code_off)
+                                                                      const int *__restrict__ code_off,
+                                                                      const T *__restrict__ code_val,
+                                                                      int n_table)
     {
         constexpr int NT = 256;
+        static_assert(!(CODED && EC), "one code stream at a time");
+        using pair_t = entry_pair<T>;
         extern __shared__ __align__(16) unsigned char smem_raw[];
-        uint64_t            *bar   = reinterpret_cast<uint64_t *>(smem_raw);
-        T                   *sval  = reinterpret_cast<T *>(smem_raw + SMEM_HEADER);
-        aoclsparse_int      *scol  = reinterpret_cast<aoclsparse_int *>(smem_raw + SMEM_HEADER + (size_t)cap * sizeof(T));
-        const unsigned char *scode = smem_raw + SMEM_HEADER + (size_t)cap * sizeof(T);
-        int                 *soff  = reinterpret_cast<int *>(smem_raw + SMEM_HEADER + (size_t)cap * (sizeof(T) + 1));
-        constexpr int        GR    = CODED ? 16 : 4;
+        uint64_t            *bar    = reinterpret_cast<uint64_t *>(smem_raw);
+        T                   *sval   = reinterpret_cast<T *>(smem_raw + SMEM_HEADER);
+        aoclsparse_int      *scol   = reinterpret_cast<aoclsparse_int *>(smem_raw + SMEM_HEADER + (size_t)cap * sizeof(T));
+        const unsigned char *scode  = smem_raw + SMEM_HEADER + (size_t)cap * sizeof(T);
+        int                 *soff   = reinterpret_cast<int *>(smem_raw + SMEM_HEADER + (size_t)cap * (sizeof(T) + 1));
+        const unsigned char *secode = smem_raw + SMEM_HEADER;                                          // EC
+        pair_t              *stab   = reinterpret_cast<pair_t *>(smem_raw + SMEM_HEADER + (size_t)cap); // EC
+        constexpr int        GR     = (CODED || EC) ? 16 : 4;
 
         const int tid = threadIdx.x;
         const int G   = (int)gridDim.x;
@@ -349,7 +407,12 @@ namespace b200
             const int cnt = ((d.w - a) + GR - 1) & ~(GR - 1);
             if(cnt <= 0)
                 return;
-            if constexpr(CODED)
+            if constexpr(EC)
+            {
+                mbar_expect_tx(bar, (unsigned)cnt);
+                bulk_load_stream(const_cast<unsigned char *>(secode), codes + a, (unsigned)cnt, bar);
+            }
+            else if constexpr(CODED)
             {
                 mbar_expect_tx(bar, (unsigned)(cnt * (sizeof(T) + 1)));
                 bulk_load_stream(sval, val + a, (unsigned)(cnt * sizeof(T)), bar);
@@ -362,11 +425,23 @@ namespace b200
                 bulk_load_stream(scol, col + a, (unsigned)(cnt * sizeof(aoclsparse_int)), bar);
             }
         };
-        auto col_at = [&](int r, int j) -> int {
-            if constexpr(CODED)
-                return r + soff[scode[j]];
+        auto entry_at = [&](int r, int j, int &c, T &v) {
+            if constexpr(EC)
+            {
+                const pair_t pr = stab[secode[j]];
+                c               = r + pr.off;
+                v               = pr.v;
+            }
+            else if constexpr(CODED)
+            {
+                c = r + soff[scode[j]];
+                v = sval[j];
+            }
             else
-                return scol[j];
+            {
+                c = scol[j];
+                v = sval[j];
+            }
         };
 
         if(tid == 0)
@@ -375,8 +450,16 @@ namespace b200
             mbar_init_fence();
         }
         if constexpr(CODED)
-            for(int i = tid; i < CODE_TABLE; i += NT)
+            for(int i = tid; i < n_table; i += NT)
                 soff[i] = code_off[i];
+        if constexpr(EC)
+            for(int i = tid; i < n_table; i += NT)
+            {
+                pair_t pr;
+                pr.v    = code_val[i];
+                pr.off  = code_off[i];
+                stab[i] = pr;
+            }
         __syncthreads();
         if((int)blockIdx.x >= hc.n_blocks || hc.iters <= 0)
             return; // host launches G <= n_blocks
@@ -430,15 +513,25 @@ namespace b200
                         T          acc   = vt<T>::zero();
                         for(; j + 4 <= e; j += 4)
                         {
-                            const int c0 = col_at(r, j), c1 = col_at(r, j + 1), c2 = col_at(r, j + 2), c3 = col_at(r, j + 3);
-                            const T   v0 = __ldca(x + c0), v1 = __ldca(x + c1), v2 = __ldca(x + c2), v3 = __ldca(x + c3);
-                            acc          = mad(sval[j], v0, acc);
-                            acc          = mad(sval[j + 1], v1, acc);
-                            acc          = mad(sval[j + 2], v2, acc);
-                            acc          = mad(sval[j + 3], v3, acc);
+                            int c0, c1, c2, c3;
+                            T   a0, a1, a2, a3;
+                            entry_at(r, j, c0, a0);
+                            entry_at(r, j + 1, c1, a1);
+                            entry_at(r, j + 2, c2, a2);
+                            entry_at(r, j + 3, c3, a3);
+                            const T x0 = __ldca(x + c0), x1 = __ldca(x + c1), x2 = __ldca(x + c2), x3 = __ldca(x + c3);
+                            acc        = mad(a0, x0, acc);
+                            acc        = mad(a1, x1, acc);
+                            acc        = mad(a2, x2, acc);
+                            acc        = mad(a3, x3, acc);
                         }
                         for(; j < e; ++j)
-                            acc = mad(sval[j], __ldca(x + col_at(r, j)), acc);
+                        {
+                            int c0;
+                            T   a0;
+                            entry_at(r, j, c0, a0);
+                            acc = mad(a0, __ldca(x + c0), acc);
+                        }
                         y[r] = mul(alpha, acc);
                     }
                 }
@@ -454,16 +547,25 @@ namespace b200
                         T          acc   = vt<T>::zero();
                         for(; j + 4 <= e; j += 4)
                         {
-                            const int c0 = col_at(r, j), c1 = col_at(r, j + 1), c2 = col_at(r, j + 2), c3 = col_at(r, j + 3);
-                            const T   v0 = boundary_x<T, true>(x, c0, hc.own_lo, hc.own_hi), v1 = boundary_x<T, true>(x, c1, hc.own_lo, hc.own_hi),
-                                    v2 = boundary_x<T, true>(x, c2, hc.own_lo, hc.own_hi), v3 = boundary_x<T, true>(x, c3, hc.own_lo, hc.own_hi);
-                            acc          = mad(sval[j], v0, acc);
-                            acc          = mad(sval[j + 1], v1, acc);
-                            acc          = mad(sval[j + 2], v2, acc);
-                            acc          = mad(sval[j + 3], v3, acc);
+                            int c0, c1, c2, c3;
+                            T   a0, a1, a2, a3;
+                            entry_at(r, j, c0, a0);
+                            entry_at(r, j + 1, c1, a1);
+                            entry_at(r, j + 2, c2, a2);
+                            entry_at(r, j + 3, c3, a3);
+                            const T x0 = boundary_x<T, true>(x, c0, hc.own_lo, hc.own_hi), x1 = boundary_x<T, true>(x, c1, hc.own_lo, hc.own_hi), x2 = boundary_x<T, true>(x, c2, hc.own_lo, hc.own_hi), x3 = boundary_x<T, true>(x, c3, hc.own_lo, hc.own_hi);
+                            acc        = mad(a0, x0, acc);
+                            acc        = mad(a1, x1, acc);
+                            acc        = mad(a2, x2, acc);
+                            acc        = mad(a3, x3, acc);
                         }
                         for(; j < e; ++j)
-                            acc = mad(sval[j], boundary_x<T, true>(x, col_at(r, j), hc.own_lo, hc.own_hi), acc);
+                        {
+                            int c0;
+                            T   a0;
+                            entry_at(r, j, c0, a0);
+                            acc = mad(a0, boundary_x<T, true>(x, c0, hc.own_lo, hc.own_hi), acc);
+                        }
                         const T out = mul(alpha, acc);
                         y[r]        = out;
                         if(push)

@@ -815,11 +815,17 @@ def measure(args, key, primary):
         # decoded columns are bit-identical), so the kernel STREAMS fewer bytes than the reference's byte model counts;
         # `achieved` / `frac` stay on the algorithmic bytes (they may exceed 1), `streamed_frac` is the honest
         # utilisation of HBM
-        streamed = l_bytes - 3 * nnz
+        # ... and, for matrices with at most 256 distinct (col - row, value) pairs (constant-coefficient stencils), the
+        # entry-code copy: ONE byte per stored entry instead of 4 + sizeof(value); decoded columns and values are
+        # bit-identical
+        entry_coded = info.n_entry_codes > 0
+        streamed = l_bytes - (3 + elem if entry_coded else 3) * nnz
         roof["streamed_bytes_per_launch"] = int(streamed)
         roof["streamed_frac"] = round(streamed / (l_bytes / roof["achieved"]) / peak, 4)
-        roof["compression"] = ("diagonal-code column stream: %d distinct col-row offsets, 1 index byte per entry"
-                               % info.n_diag_codes)
+        roof["compression"] = (("entry-code stream: %d distinct (col-row offset, value) pairs, 1 byte per stored entry instead of %d"
+                                % (info.n_entry_codes, 4 + elem)) if entry_coded else
+                               ("diagonal-code column stream: %d distinct col-row offsets, 1 index byte per entry"
+                                % info.n_diag_codes))
 
     out = {
         "metric": METRIC,
@@ -838,7 +844,9 @@ def measure(args, key, primary):
                    "plan": {"block_nnz": info.block_nnz, "blocks": info.n_blocks, "thread": info.n_thread_blocks,
                             "warp": info.n_warp_blocks, "product": info.n_product_blocks,
                             "long_segments": info.n_long_segments, "long_rows": info.n_long_rows,
-                            "diag_code_table": info.n_diag_codes},
+                            "diag_code_table": info.n_diag_codes, "entry_code_table": info.n_entry_codes,
+                            "entry_plan": ({"block_nnz": info.e_block_nnz, "block_rows": info.e_block_rows, "blocks": info.e_n_blocks}
+                                           if info.n_entry_codes > 0 else None)},
                    "optimize_ms": round(optimize_ms, 2),
                    "create_ms": round(create_ms, 2),
                    "create_from_pageable_host_ms": None if create_host_ms is None else round(create_host_ms, 2)},

@@ -52,6 +52,11 @@ typedef struct aoclsparse_b200_matrix_info_
     aoclsparse_int n_long_rows;     /* rows split across CTAs                                   */
     aoclsparse_int n_diag_codes;    /* diagonal-code copy of col_idx (one byte per entry indexing a table of the
                                        distinct col - row offsets): table entries, 0 = not built / not applicable */
+    aoclsparse_int n_entry_codes;   /* entry-code copy (one byte per entry indexing a table of the distinct (col - row, value)
+                                       pairs), only next to the diagonal-code copy: table entries, 0 = not built         */
+    aoclsparse_int e_block_nnz;     /* block plan of the entry-coded kernels (0 when there is no entry-code copy): entry   */
+    aoclsparse_int e_block_rows;    /* capacity, row capacity and number of blocks; every block is thread-per-row         */
+    aoclsparse_int e_n_blocks;
 } aoclsparse_b200_matrix_info;
 
 /* Diagonal-code copy of the stored column indices, built by aoclsparse_optimize for banded / stencil matrices (every
@@ -62,6 +67,28 @@ DLL_PUBLIC aoclsparse_status aoclsparse_b200_get_diag_codes(const aoclsparse_mat
                                                             aoclsparse_int         *n_codes,
                                                             aoclsparse_int         *offsets,
                                                             unsigned char          *codes);
+
+/* Entry-code copy of the stored entries, built by aoclsparse_optimize next to the diagonal-code copy when the matrix holds
+ * at most 256 distinct (col - row, value) pairs (values compared as bit patterns; 4- and 8-byte value types) -- a
+ * constant-coefficient stencil holds as many as it has points: pair i is (offsets[i], values[i]), ascending by offset, then
+ * by value pattern; ecodes[p] = index of entry p's pair.  The multiply then streams ONE byte per stored entry and decodes
+ * the identical column and value.  *n_pairs = 0 when it was not built.  offsets / values (elements of the handle's value
+ * type) / ecodes may be NULL.  aoclsparse_?update_values / aoclsparse_?set_value make the copy stale; it is encoded again
+ * before the next multiply.  Integer metadata with no counterpart in the reference: pinned bit for bit by
+ * oracle/csr_oracle.c::oracle_entry_codes. */
+DLL_PUBLIC aoclsparse_status aoclsparse_b200_get_entry_codes(const aoclsparse_matrix A,
+                                                             aoclsparse_int         *n_pairs,
+                                                             aoclsparse_int         *offsets,
+                                                             void                   *values,
+                                                             unsigned char          *ecodes);
+/* Row blocks the entry-coded kernels run on (same layout as aoclsparse_b200_get_plan; *n_blocks = 0 when there is no
+ * entry-code copy).  One staged byte per entry allows much larger blocks than the handle's main plan, which the other
+ * kernels keep using. */
+DLL_PUBLIC aoclsparse_status aoclsparse_b200_get_entry_plan(const aoclsparse_matrix A,
+                                                            aoclsparse_int          capacity,
+                                                            aoclsparse_int         *block_desc,
+                                                            aoclsparse_int         *block_kind,
+                                                            aoclsparse_int         *n_blocks);
 
 /* Box-tile copy used by row-major aoclsparse_?csrmm on grid (stencil) matrices (csrc/mesh_tiles.cu): built on the first
  * multiply that can use it.  The matrix's distinct col - row offsets are read as a lattice {a + b*stride[1] + c*stride[2]},

@@ -378,8 +378,9 @@ int oracle_plan(int m, const int *rp, int T, int R, int forced, int n_cuts, cons
 /* plan_parameters + wave-aware block size of plan.cu (same arithmetic, same candidate order) */
 static long long ctas_per_wave(int elem_size, int T, int coded)
 {
-    const long long smem = coded ? 16 + (long long)(T + 32) * (long long)(elem_size + 1) + 1024 + 1024
-                                 : 16 + (long long)(T + 8) * (long long)(elem_size + 4) + 1024;
+    const long long smem = coded == 2 ? 16 + (long long)((T + 32 + 15) & ~15) + 256 * (elem_size >= 8 ? 16LL : 8LL) + 1024
+                           : coded    ? 16 + (long long)(T + 32) * (long long)(elem_size + 1) + 1024 + 1024
+                                      : 16 + (long long)(T + 8) * (long long)(elem_size + 4) + 1024;
     long long       c    = 232448 / smem;
     if(c > 8)
         c = 8;
@@ -388,10 +389,47 @@ static long long ctas_per_wave(int elem_size, int T, int coded)
     return 148 * c;
 }
 
-/* coded != 0: the plan serves the diagonal-code copy (elem_size + 1 staged bytes per entry) */
+/* coded == 1: the plan serves the diagonal-code copy (elem_size + 1 staged bytes per entry)
+ * coded == 2: the block plan of the entry-coded kernels (1 staged byte per entry): blocks end at a row count -- as many
+ *             rows as still leave 8 waves of CTAs, within [512, 2048]; matrices of 1..8 waves: the row count 512 - 8k
+ *             (k = 0..24) minimising ceil(1.015 blocks / CTAs per wave) * rows; less than one wave: one block per
+ *             resident CTA, at least 64 rows */
 void oracle_plan_parameters(int elem_size, int m, int nnz, int max_row_nnz, const int *rp, int n_cuts, const int *cuts,
                             int coded, int *T, int *R)
 {
+    if(coded == 2)
+    {
+        const int       t     = (24576 - 4096 - 32) / 256 * 256;
+        const long long slots = ctas_per_wave(elem_size, t, 2);
+        long long       r     = (long long)m / (8 * slots) / 64 * 64;
+        r                     = r < 512 ? 512 : (r > 2048 ? 2048 : r);
+        if((long long)m < slots * 512) /* less than one wave: one block per resident CTA, at least 64 rows */
+        {
+            r = (((long long)m + slots - 1) / slots + 31) / 32 * 32;
+            r = r < 64 ? 64 : r;
+        }
+        *T                    = t;
+        *R                    = (int)r;
+        if(m > 0 && rp && r >= 512 && (long long)m < 8 * slots * r && (long long)m >= slots * r)
+        {
+            long long best_cost = -1;
+            int       best_r    = (int)r;
+            for(int k = 0; k <= 24; ++k)
+            {
+                const int       rk = (int)r - 8 * k;
+                int             a, b;
+                const long long nb   = oracle_plan(m, rp, t, rk, -1, n_cuts, cuts, 0, 0, 0, &a, &b);
+                const long long cost = (((nb * 203 + 199) / 200 + slots - 1) / slots) * (long long)rk;
+                if(best_cost < 0 || cost < best_cost)
+                {
+                    best_cost = cost;
+                    best_r    = rk;
+                }
+            }
+            *R = best_r;
+        }
+        return;
+    }
     int             t    = (24576 / (elem_size + 4)) / 512 * 512;
     if(coded)
         t = (24576 / (elem_size + 1) - 32) / 256 * 256;
@@ -472,6 +510,87 @@ int oracle_diag_codes(int m, const int *rp, const int *col, int *offsets, unsign
             codes[p] = (unsigned char)k;
         }
     return nd;
+}
+
+/* Entry-code copy built by aoclsparse_optimize next to the diagonal-code copy (aocl-sparse_b200/csrc/plan.cu,
+ * build_entry_codes): GPU-only integer metadata with no counterpart in the reference, so the written SPEC is restated here:
+ *   D = the diagonal-code table (above); V = ascending distinct bit patterns of the stored values (passed zero-extended to
+ *   64 bits); Q = ascending distinct pairs (index in D, index in V) over all stored entries, ordered by the first, then
+ *   the second component.  Applicable iff 1 <= |D|, |V|, |Q| <= 256 and no value has the all-ones 64-bit pattern:
+ *   ecodes[p] = index of p's pair in Q, pair_off[i] = D[Q[i].first], pair_val[i] = V[Q[i].second].
+ * Returns |Q| (0: not applicable). */
+static int cmp_u64(const void *a, const void *b)
+{
+    const unsigned long long x = *(const unsigned long long *)a, y = *(const unsigned long long *)b;
+    return (x > y) - (x < y);
+}
+int oracle_entry_codes(int m, const int *rp, const int *col, const unsigned long long *val_bits, int *pair_off,
+                       unsigned long long *pair_val, unsigned char *ecodes)
+{
+    const int nnz = rp[m];
+    if(nnz <= 0)
+        return 0;
+    int            d[256];
+    unsigned char *dc = (unsigned char *)malloc((size_t)nnz);
+    const int      nd = oracle_diag_codes(m, rp, col, d, dc);
+    if(nd == 0)
+    {
+        free(dc);
+        return 0;
+    }
+    unsigned long long v[257];
+    int                nv = 0;
+    for(int p = 0; p < nnz; ++p)
+    {
+        if(val_bits[p] == 0xffffffffffffffffull)
+        {
+            free(dc);
+            return 0;
+        }
+        int k = 0;
+        while(k < nv && v[k] != val_bits[p])
+            ++k;
+        if(k == nv)
+        {
+            if(nv == 256)
+            {
+                free(dc);
+                return 0;
+            }
+            v[nv++] = val_bits[p];
+        }
+    }
+    qsort(v, (size_t)nv, sizeof(v[0]), cmp_u64);
+    unsigned char *seen = (unsigned char *)calloc(65536, 1);
+    int           *pid  = (int *)malloc(sizeof(int) * (size_t)nnz);
+    for(int p = 0; p < nnz; ++p)
+    {
+        int k = 0;
+        while(v[k] != val_bits[p])
+            ++k;
+        pid[p]       = ((int)dc[p] << 8) | k;
+        seen[pid[p]] = 1;
+    }
+    int rank[65536];
+    int nq = 0;
+    for(int q = 0; q < 65536; ++q)
+        if(seen[q])
+            rank[q] = nq++;
+    if(nq <= 256)
+    {
+        for(int q = 0; q < 65536; ++q)
+            if(seen[q])
+            {
+                pair_off[rank[q]] = d[q >> 8];
+                pair_val[rank[q]] = v[q & 255];
+            }
+        for(int p = 0; p < nnz; ++p)
+            ecodes[p] = (unsigned char)rank[pid[p]];
+    }
+    free(dc);
+    free(seen);
+    free(pid);
+    return nq <= 256 ? nq : 0;
 }
 
 /* Row pointers of C = A B for two CSR operands in the orientation of the product: the number of distinct column

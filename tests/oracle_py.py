@@ -88,6 +88,24 @@ class Oracle:
     def doid(self, is_complex, mtype, fill, op):
         return self.lib.oracle_doid(int(is_complex), mtype, fill, op)
 
+    def entry_codes(self, rp0, col0, val):
+        """(offsets, values, ecodes) of the entry-code copy of a 0-based CSR matrix with 4- or 8-byte values, or
+        (None, None, None) if not applicable"""
+        rp0 = np.ascontiguousarray(rp0, dtype=np.int32)
+        col0 = np.ascontiguousarray(col0, dtype=np.int32)
+        val = np.ascontiguousarray(val)
+        bits = val.view(np.uint32 if val.dtype.itemsize == 4 else np.uint64).astype(np.uint64)
+        offs = np.zeros(256, np.int32)
+        vals = np.zeros(256, np.uint64)
+        codes = np.zeros(max(len(col0), 1), np.uint8)
+        self.lib.oracle_entry_codes.argtypes = [C.c_int] + [C.c_void_p] * 6
+        n = self.lib.oracle_entry_codes(len(rp0) - 1, rp0.ctypes.data, col0.ctypes.data, bits.ctypes.data, offs.ctypes.data,
+                                        vals.ctypes.data, codes.ctypes.data)
+        if n == 0:
+            return None, None, None
+        v = vals[:n].astype(np.uint32).view(val.dtype) if val.dtype.itemsize == 4 else vals[:n].view(val.dtype)
+        return offs[:n], v, codes[: len(col0)]
+
     def plan_parameters(self, elem_size, rp0, cuts=(), coded=False):
         """block nnz / row capacity the analysis picks for a 0-based row_ptr (incl. the wave-aware search)"""
         rp0 = np.ascontiguousarray(rp0, dtype=np.int32)
@@ -97,7 +115,7 @@ class Oracle:
         mx = int(np.max(np.diff(rp0))) if m > 0 else 0
         t, r = C.c_int(0), C.c_int(0)
         self.lib.oracle_plan_parameters(elem_size, m, nnz, mx, rp0.ctypes.data, len(cuts), cuts.ctypes.data,
-                                        1 if coded else 0, C.byref(t), C.byref(r))
+                                        int(coded), C.byref(t), C.byref(r))
         return t.value, r.value
 
     def diag_codes(self, rp0, col0):

@@ -872,6 +872,125 @@ def test_diag_codes_bit_exact_and_products(lib, oracle):
     lib.destroy_descr(d)
 
 
+def test_entry_codes_bit_exact_and_products(lib, oracle):
+    """the entry-code copy aoclsparse_optimize builds for matrices with at most 256 distinct (col - row, value) pairs
+    (constant-coefficient stencils): pair table, codes and the block plan of the entry-coded kernels bit-exact against
+    the CPU restatement of the spec; products through the entry-coded kernel identical, bit for bit, to the ones that
+    stream values and column codes (AOCLSPARSE_B200_ENTRY_CODES=0) for s / d / c, device and host vectors, beta != 0,
+    an x window + row cuts; re-encoded after aoclsparse_?update_values; dropped when the values stop repeating; not built
+    for double complex, variable coefficients or more than 256 pairs"""
+    import torch
+    rng = np.random.default_rng(23)
+    for idx, (rp, col, val) in enumerate((gen_np.stencil(27, 20, 19, 18), gen_np.stencil(7, 40, 40, 40), gen_np.stencil(5, 300, 300))):
+        m = len(rp) - 1
+        for p in ("d", "s", "c", "z"):
+            dt = DT[p]
+            v = val.astype(dt)
+            if p in "cz":
+                v = (v + 1j * np.sign(val)).astype(dt)
+            x = rng.normal(size=m).astype(dt)
+            y0 = rng.normal(size=m).astype(dt)
+            outs = {}
+            for mode in ("entry", "stream"):
+                if mode == "stream":
+                    os.environ["AOCLSPARSE_B200_ENTRY_CODES"] = "0"
+                try:
+                    st, h = lib.create_csr(p, 0, m, m, len(col), rp, col, v)
+                    assert st == 0
+                    d = lib.create_descr()
+                    assert lib.set_mv_hint(h, 111, d, 10) == 0 and lib.optimize(h) == 0, lib.last_error()
+                finally:
+                    os.environ.pop("AOCLSPARSE_B200_ENTRY_CODES", None)
+                info = lib.matrix_info(h)
+                assert info.n_diag_codes > 0
+                if mode == "entry" and p != "z":
+                    ooffs, ovals, ocodes = oracle.entry_codes(rp, col, v)
+                    offs, vals, codes = lib.get_entry_codes(h, len(col), dt)
+                    assert info.n_entry_codes == len(ooffs) == len(offs)
+                    ut = np.uint32 if dt == np.float32 else np.uint64
+                    assert np.array_equal(offs, ooffs) and np.array_equal(vals.view(ut), ovals.view(ut)) and np.array_equal(codes, ocodes)
+                    T, R = oracle.plan_parameters(np.dtype(dt).itemsize, rp, (), coded=2)
+                    assert (info.e_block_nnz, info.e_block_rows) == (T, R), (idx, p)
+                    desc, kind = lib.get_entry_plan(h)
+                    odesc, okind, nlr, nls = oracle.plan(rp, T, R)
+                    assert info.e_n_blocks == len(odesc) and nlr == 0 and np.array_equal(desc, odesc) and np.array_equal(kind, okind)
+                    assert np.all((kind & 15) == 0)
+                else:
+                    assert info.n_entry_codes == 0 and info.e_n_blocks == 0
+                    assert lib.get_entry_codes(h, len(col), dt) == (None, None, None)
+                y = y0.copy()
+                assert lib.mv(p, 111, 1.5, h, d, x, -0.5, y) == 0, lib.last_error()
+                dx = torch.from_numpy(x).cuda()
+                dy = torch.full((m,), float("nan"), dtype=dx.dtype, device="cuda")
+                before = lib.launch_count()
+                assert lib.mv(p, 111, 1.0, h, d, dx.data_ptr(), 0.0, dy.data_ptr()) == 0
+                assert lib.launch_count() - before == 1
+                dyb = torch.from_numpy(y0.copy()).cuda()
+                assert lib.mv(p, 111, -2.0, h, d, dx.data_ptr(), 0.25, dyb.data_ptr()) == 0
+                # the values change: three times the old ones (same number of pairs), then values that do not repeat
+                assert lib.update_values(p, h, len(col), (v * 3).astype(dt)) == 0
+                dy3 = torch.zeros(m, dtype=dx.dtype, device="cuda")
+                assert lib.mv(p, 111, 1.0, h, d, dx.data_ptr(), 0.0, dy3.data_ptr()) == 0
+                info3 = lib.matrix_info(h)
+                assert info3.n_entry_codes == info.n_entry_codes and info3.n_diag_codes == info.n_diag_codes
+                vr = (np.arange(len(col)) % 1000 + 1).astype(dt)
+                assert lib.update_values(p, h, len(col), vr) == 0
+                dyr = torch.zeros(m, dtype=dx.dtype, device="cuda")
+                assert lib.mv(p, 111, 1.0, h, d, dx.data_ptr(), 0.0, dyr.data_ptr()) == 0
+                torch.cuda.synchronize()
+                infor = lib.matrix_info(h)
+                assert infor.n_entry_codes == 0 and infor.n_diag_codes == info.n_diag_codes
+                outs[mode] = (y, dy.cpu().numpy(), dyb.cpu().numpy(), dy3.cpu().numpy(), dyr.cpu().numpy())
+                lib.destroy(h)
+                lib.destroy_descr(d)
+            for a, b in zip(outs["entry"], outs["stream"]):
+                assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), (idx, p)
+            # and against the oracle (the streamed path is pinned elsewhere; once here for the entry-coded one)
+            yo = y0.copy()
+            oracle.csrmv(111, 1.5, m, m, 0, rp, col, v, 0, 0, 0, x, -0.5, yo)
+            den = 1.5 * oracle_py.row_scale(rp, col, np.abs(v), np.abs(x), 0, -0.5, y0)
+            assert np.max(np.abs(outs["entry"][0] - yo) / den) <= (1e-5 if p in "sc" else 1e-12)
+    d = lib.create_descr()
+    # variable coefficients: column codes only; 27 offsets x 19 values: too many pairs
+    rp, col, val = gen_np.stencil(27, 16, 16, 16)
+    for v in (rng.normal(size=len(col)), rng.integers(1, 20, size=len(col)).astype(np.float64)):
+        st, h = lib.create_csr("d", 0, len(rp) - 1, len(rp) - 1, len(col), rp, col, v)
+        assert lib.set_mv_hint(h, 111, d, 10) == 0 and lib.optimize(h) == 0
+        info = lib.matrix_info(h)
+        assert info.n_diag_codes == 27 and info.n_entry_codes == 0
+        lib.destroy(h)
+    # a windowed slab with row cuts (the sharded iteration's handle): whole product entry-coded, mv_rows on the main plan
+    nx, ny, nz = 24, 20, 30
+    plane, total = nx * ny, nx * ny * nz
+    lo, hi = 8 * plane, 19 * plane
+    rp, col, val = gen_np.stencil(7, nx, ny, nz, lo, hi)
+    ms = hi - lo
+    xg = gen_np.uniform(1, 0, total)
+    st, h = lib.create_csr("d", 0, ms, total, len(col), rp, col, val)
+    assert st == 0
+    assert lib.set_x_window(h, lo - plane, hi + plane) == 0 and lib.set_row_cuts(h, [plane, ms - plane]) == 0
+    assert lib.set_mv_hint(h, 111, d, 10) == 0 and lib.optimize(h) == 0
+    info = lib.matrix_info(h)
+    assert info.n_entry_codes == 7
+    desc, kind = lib.get_entry_plan(h)
+    T, R = oracle.plan_parameters(8, rp, (plane, ms - plane), coded=2)
+    odesc, okind, _, _ = oracle.plan(rp, T, R, -1, (plane, ms - plane))
+    assert np.array_equal(desc, odesc) and (info.e_block_nnz, info.e_block_rows) == (T, R)
+    xw = torch.from_numpy(xg[lo - plane: hi + plane].copy()).cuda()
+    yw = torch.zeros(ms, dtype=torch.float64, device="cuda")
+    assert lib.mv("d", 111, 0.25, h, d, xw.data_ptr(), 0.0, yw.data_ptr()) == 0
+    yr = torch.zeros(ms, dtype=torch.float64, device="cuda")
+    for r0, r1 in ((0, plane), (ms - plane, ms), (plane, ms - plane)):
+        assert lib.mv_rows("d", 0.25, h, d, xw.data_ptr(), 0.0, yr.data_ptr(), r0, r1) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(yw, yr)
+    yo = np.zeros(ms)
+    oracle.csrmv(111, 0.25, ms, total, 0, rp, col, val, 0, 0, 0, xg, 0.0, yo)
+    assert np.max(np.abs(yw.cpu().numpy() - yo) / (0.25 * oracle_py.row_scale(rp, col, val, xg))) <= 1e-12
+    lib.destroy(h)
+    lib.destroy_descr(d)
+
+
 @pytest.mark.parametrize("p", ["s", "d", "c", "z"])
 def test_every_strategy_matches_oracle(lib, oracle, p):
     """forced thread / warp / product strategies and the split-row path on a skewed matrix"""
