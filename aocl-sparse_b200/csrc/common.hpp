@@ -349,6 +349,7 @@ namespace b200
         aoclsparse_int n_long_segments = 0;
         aoclsparse_int n_strat[4] = {0, 0, 0, 0};
         aoclsparse_int max_block_rows = 0; // most rows any block holds (sizes the staged row_ptr slice)
+        aoclsparse_int max_block_nnz  = 0; // most entries any non-split block holds (<= block_nnz; sizes entry-code buffers)
         int            pdl              = 1; // programmatic dependent launch of the multiply kernel (tuning knob)
         // diagonal-code copy of col_idx (plan.cu, build_diag_codes): one byte per stored entry indexing the table of the
         // matrix's distinct (col - row) offsets.  Built by aoclsparse_optimize when every block is thread-per-row and

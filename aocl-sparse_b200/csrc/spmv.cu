@@ -77,8 +77,10 @@ namespace b200
         {
             const row_block_plan &M    = A.plan;                       // owns the code arrays
             const row_block_plan &P    = ECODED ? *A.plan.eplan : A.plan; // the blocks this launch walks
-            const int             cap  = ECODED ? spmv_ecoded_cap(P.block_nnz) : P.block_nnz + (CODED ? 32 : 8);
-            const size_t          smem = ECODED ? spmv_ecoded_smem_bytes(sizeof(T), P.block_nnz)
+            // (entry codes: blocks end at a row count, so the buffer is sized by the largest block, not by the capacity)
+            const aoclsparse_int  e_nnz = ECODED ? (P.max_block_nnz > 0 ? P.max_block_nnz : P.block_nnz) : 0;
+            const int             cap  = ECODED ? spmv_ecoded_cap(e_nnz) : P.block_nnz + (CODED ? 32 : 8);
+            const size_t          smem = ECODED ? spmv_ecoded_smem_bytes(sizeof(T), e_nnz)
                                                 : (CODED ? spmv_coded_smem_bytes(sizeof(T), P.block_nnz) : spmv_smem_bytes(sizeof(T), P.block_nnz));
             static std::atomic<size_t> configured{0};
             if(configured.load(std::memory_order_acquire) < smem)
@@ -1315,8 +1317,9 @@ aoclsparse_status b200::sharded_step_launch(const double                  *alpha
     if(A->win_hi >= 0)
         x = x - A->win_lo;
     const bool   coded = P0.n_codes > 0 && !ec;
-    const int    cap   = ec ? spmv_ecoded_cap(P.block_nnz) : P.block_nnz + (coded ? 32 : 8);
-    const size_t smem  = ec ? spmv_ecoded_smem_bytes(sizeof(double), P.block_nnz)
+    const aoclsparse_int e_nnz = P.max_block_nnz > 0 ? P.max_block_nnz : P.block_nnz; // entry codes: the largest block sizes the buffer
+    const int    cap   = ec ? spmv_ecoded_cap(e_nnz) : P.block_nnz + (coded ? 32 : 8);
+    const size_t smem  = ec ? spmv_ecoded_smem_bytes(sizeof(double), e_nnz)
                             : (coded ? spmv_coded_smem_bytes(sizeof(double), P.block_nnz) : spmv_smem_bytes(sizeof(double), P.block_nnz));
     auto         kern  = ec ? spmv_sharded_step_kernel<double, false, true>
                             : (coded ? spmv_sharded_step_kernel<double, true, false> : spmv_sharded_step_kernel<double, false, false>);
@@ -1420,8 +1423,10 @@ aoclsparse_status b200::sharded_iterate_launch(double                     alpha,
     const double *x0 = w_cur - shift, *x1 = w_nxt - shift;
     double       *y0 = w_nxt + own_offset, *y1 = w_cur + own_offset;
     const bool   coded = P0.n_codes > 0 && !ec;
-    int          cap   = ec ? spmv_ecoded_cap(P.block_nnz) : P.block_nnz + (coded ? 32 : 8);
-    const size_t smem  = ec ? spmv_ecoded_smem_bytes(sizeof(double), P.block_nnz)
+    const aoclsparse_int e_nnz = P.max_block_nnz > 0 ? P.max_block_nnz : P.block_nnz; // entry codes: the largest block sizes the buffers
+    int          cap   = ec ? spmv_ecoded_cap(e_nnz) : P.block_nnz + (coded ? 32 : 8);
+    // entry codes: two code buffers (the next block's slice arrives while the current block is reduced)
+    const size_t smem  = ec ? spmv_ecoded_smem_bytes(sizeof(double), e_nnz) + (size_t)cap
                             : (coded ? spmv_coded_smem_bytes(sizeof(double), P.block_nnz) : spmv_smem_bytes(sizeof(double), P.block_nnz));
     auto         kern  = ec ? spmv_sharded_iterate_kernel<double, false, true>
                             : (coded ? spmv_sharded_iterate_kernel<double, true, false> : spmv_sharded_iterate_kernel<double, false, false>);

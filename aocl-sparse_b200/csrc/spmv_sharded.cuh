@@ -227,11 +227,20 @@ namespace b200
         {
             // interior rows: every x entry they name was written by the previous LOCAL launch, which has completed
             // (griddepcontrol.wait) -> read-only path through L1
+            // the bounds of a thread's NEXT row are requested before its current row is reduced
+            int cur_s = pre_s, cur_e = pre_e;
             for(int r = d.x + tid; r < d.y; r += NT)
             {
-                const bool first = r == d.x + tid;
-                int        j     = (first ? pre_s : rp[r]) - a;
-                const int  e     = (first ? pre_e : rp[r + 1]) - a;
+                int nxt_s = 0, nxt_e = 0;
+                if(r + NT < d.y)
+                {
+                    nxt_s = rp[r + NT];
+                    nxt_e = rp[r + NT + 1];
+                }
+                int       j = cur_s - a;
+                const int e = cur_e - a;
+                cur_s       = nxt_s;
+                cur_e       = nxt_e;
                 T          acc   = vt<T>::zero();
                 for(; j + 4 <= e; j += 4)
                 {
@@ -247,12 +256,21 @@ namespace b200
                     acc        = mad(a2, x2, acc);
                     acc        = mad(a3, x3, acc);
                 }
-                for(; j < e; ++j)
+                if(j < e)
                 {
-                    int c0;
-                    T   a0;
+                    // 1-3 entries left: issued together as well (an absent entry re-reads the row's first one and is not added)
+                    const int n = e - j;
+                    int       c0, c1, c2;
+                    T         a0, a1, a2;
                     entry_at(r, j, c0, a0);
-                    acc = mad(a0, ldg_ro(x + c0), acc);
+                    entry_at(r, n > 1 ? j + 1 : j, c1, a1);
+                    entry_at(r, n > 2 ? j + 2 : j, c2, a2);
+                    const T x0 = ldg_ro(x + c0), x1 = ldg_ro(x + c1), x2 = ldg_ro(x + c2);
+                    acc        = mad(a0, x0, acc);
+                    if(n > 1)
+                        acc = mad(a1, x1, acc);
+                    if(n > 2)
+                        acc = mad(a2, x2, acc);
                 }
                 y[r] = mul(alpha, acc);
             }
@@ -262,11 +280,20 @@ namespace b200
             // boundary rows: the halo part of x is stored by the PEER GPU while this grid is already running, so it
             // must not go through the non-coherent path (ld.global.nc requires the data to be read-only for the
             // kernel's lifetime): ld.global.cg reads at the L2, the coherence point the peer's stores arrive at
+            // the bounds of a thread's NEXT row are requested before its current row is reduced
+            int cur_s = pre_s, cur_e = pre_e;
             for(int r = d.x + tid; r < d.y; r += NT)
             {
-                const bool first = r == d.x + tid;
-                int        j     = (first ? pre_s : rp[r]) - a;
-                const int  e     = (first ? pre_e : rp[r + 1]) - a;
+                int nxt_s = 0, nxt_e = 0;
+                if(r + NT < d.y)
+                {
+                    nxt_s = rp[r + NT];
+                    nxt_e = rp[r + NT + 1];
+                }
+                int       j = cur_s - a;
+                const int e = cur_e - a;
+                cur_s       = nxt_s;
+                cur_e       = nxt_e;
                 T          acc   = vt<T>::zero();
                 for(; j + 4 <= e; j += 4)
                 {
@@ -282,12 +309,21 @@ namespace b200
                     acc        = mad(a2, x2, acc);
                     acc        = mad(a3, x3, acc);
                 }
-                for(; j < e; ++j)
+                if(j < e)
                 {
-                    int c0;
-                    T   a0;
+                    // 1-3 entries left: issued together as well (an absent entry re-reads the row's first one and is not added)
+                    const int n = e - j;
+                    int       c0, c1, c2;
+                    T         a0, a1, a2;
                     entry_at(r, j, c0, a0);
-                    acc = mad(a0, boundary_x<T, false>(x, c0, hc.own_lo, hc.own_hi), acc);
+                    entry_at(r, n > 1 ? j + 1 : j, c1, a1);
+                    entry_at(r, n > 2 ? j + 2 : j, c2, a2);
+                    const T x0 = boundary_x<T, false>(x, c0, hc.own_lo, hc.own_hi), x1 = boundary_x<T, false>(x, c1, hc.own_lo, hc.own_hi), x2 = boundary_x<T, false>(x, c2, hc.own_lo, hc.own_hi);
+                    acc        = mad(a0, x0, acc);
+                    if(n > 1)
+                        acc = mad(a1, x1, acc);
+                    if(n > 2)
+                        acc = mad(a2, x2, acc);
                 }
                 const T out = mul(alpha, acc);
                 y[r]        = out;
@@ -376,8 +412,11 @@ namespace b200
         aoclsparse_int      *scol   = reinterpret_cast<aoclsparse_int *>(smem_raw + SMEM_HEADER + (size_t)cap * sizeof(T));
         const unsigned char *scode  = smem_raw + SMEM_HEADER + (size_t)cap * sizeof(T);
         int                 *soff   = reinterpret_cast<int *>(smem_raw + SMEM_HEADER + (size_t)cap * (sizeof(T) + 1));
-        const unsigned char *secode = smem_raw + SMEM_HEADER;                                          // EC
-        pair_t              *stab   = reinterpret_cast<pair_t *>(smem_raw + SMEM_HEADER + (size_t)cap); // EC
+        // EC: TWO code buffers (one staged byte per entry is cheap), so the next block's slice is requested BEFORE the
+        // current block is reduced and its latency never shows; the header holds one mbarrier per buffer
+        const unsigned char *secode = smem_raw + SMEM_HEADER;                                              // EC: current buffer
+        pair_t              *stab   = reinterpret_cast<pair_t *>(smem_raw + SMEM_HEADER + 2 * (size_t)cap); // EC
+        int                  buf    = 0;                                                                   // EC: index of the current buffer
         constexpr int        GR     = (CODED || EC) ? 16 : 4;
 
         const int tid = threadIdx.x;
@@ -401,16 +440,16 @@ namespace b200
                 side = 2;
             }
         };
-        // thread 0: request the matrix slice of block descriptor d into the staging buffer
-        auto request = [&](const int4 &d) {
+        // thread 0: request the matrix slice of block descriptor d into the staging buffer (EC: into buffer `into`)
+        auto request = [&](const int4 &d, int into) {
             const int a   = d.z & ~(GR - 1);
             const int cnt = ((d.w - a) + GR - 1) & ~(GR - 1);
             if(cnt <= 0)
                 return;
             if constexpr(EC)
             {
-                mbar_expect_tx(bar, (unsigned)cnt);
-                bulk_load_stream(const_cast<unsigned char *>(secode), codes + a, (unsigned)cnt, bar);
+                mbar_expect_tx(bar + into, (unsigned)cnt);
+                bulk_load_stream(smem_raw + SMEM_HEADER + (size_t)into * (size_t)cap, codes + a, (unsigned)cnt, bar + into);
             }
             else if constexpr(CODED)
             {
@@ -447,6 +486,8 @@ namespace b200
         if(tid == 0)
         {
             mbar_init(bar, 1);
+            if constexpr(EC)
+                mbar_init(bar + 1, 1);
             mbar_init_fence();
         }
         if constexpr(CODED)
@@ -463,12 +504,24 @@ namespace b200
         __syncthreads();
         if((int)blockIdx.x >= hc.n_blocks || hc.iters <= 0)
             return; // host launches G <= n_blocks
-        unsigned parity = 0;
-        int      b, side;
-        locate((int)blockIdx.x, b, side);
-        int4 d = desc[b];
-        if(tid == 0)
-            request(d);
+        // This CTA's blocks of one iteration, in launch-order numbering (see locate): c, c+G, c+2G, ...  (Giving every CTA one
+        // contiguous chunk of interior blocks instead -- for L1 reuse of x between consecutive grid lines -- measured SLOWER,
+        // 0.600 against 0.575 ms per iteration on 2 GPUs: a thousand scattered streams cost more in HBM than the reuse saves.)
+        const int c_id   = (int)blockIdx.x;
+        const int n_mine = hc.n_blocks > c_id ? (hc.n_blocks - c_id + G - 1) / G : 0;
+        auto      nth    = [&](int i) -> int { return c_id + i * G; };
+        // (a CTA without blocks -- possible only when there are about as many CTAs as blocks -- still takes part in
+        // every grid barrier below)
+        unsigned parity = 0; // bit i: phase of buffer i's barrier
+        int      b = 0, side = 2;
+        int4     d = make_int4(0, 0, 0, 0);
+        if(n_mine > 0)
+        {
+            locate(nth(0), b, side);
+            d = desc[b];
+            if(tid == 0)
+                request(d, 0);
+        }
 
         for(int it = 0; it < hc.iters; ++it)
         {
@@ -477,11 +530,24 @@ namespace b200
             T       *push_left  = (it & 1) ? push_left1 : push_left0;
             T       *push_right = (it & 1) ? push_right1 : push_right0;
             const unsigned k    = hc.k0 + (unsigned)it;
-            for(int bid = (int)blockIdx.x; bid < hc.n_blocks; bid += G)
+            for(int ib = 0; ib < n_mine; ++ib)
             {
-                // (b, side, d) describe block `bid`; its slice has been requested
+                // (b, side, d) describe this CTA's ib-th block; its slice has been requested
                 const int a   = d.z & ~(GR - 1);
                 const int cnt = ((d.w - a) + GR - 1) & ~(GR - 1);
+                // next block of this CTA: in this iteration, or the first one of the next iteration
+                const bool wraps = ib + 1 >= n_mine;
+                const bool more  = !wraps || it + 1 < hc.iters;
+                int        bn = b, side_n = side;
+                int4       dn = d;
+                if(more)
+                {
+                    locate(wraps ? nth(0) : nth(ib + 1), bn, side_n);
+                    dn = desc[bn];
+                    if constexpr(EC)
+                        if(tid == 0)
+                            request(dn, buf ^ 1); // everybody left that buffer at the end of the previous block
+                }
                 int       pre_s = 0, pre_e = 0;
                 if(d.x + tid < d.y)
                 {
@@ -500,16 +566,25 @@ namespace b200
                 }
                 if(cnt > 0)
                 {
-                    mbar_wait(bar, parity);
-                    parity ^= 1u;
+                    mbar_wait(bar + buf, (parity >> buf) & 1u);
+                    parity ^= 1u << buf;
                 }
                 if(side == 2)
                 {
+                    // the bounds of a thread's NEXT row are requested before its current row is reduced
+                    int cur_s = pre_s, cur_e = pre_e;
                     for(int r = d.x + tid; r < d.y; r += NT)
                     {
-                        const bool first = r == d.x + tid;
-                        int        j     = (first ? pre_s : rp[r]) - a;
-                        const int  e     = (first ? pre_e : rp[r + 1]) - a;
+                        int nxt_s = 0, nxt_e = 0;
+                        if(r + NT < d.y)
+                        {
+                            nxt_s = rp[r + NT];
+                            nxt_e = rp[r + NT + 1];
+                        }
+                        int       j = cur_s - a;
+                        const int e = cur_e - a;
+                        cur_s       = nxt_s;
+                        cur_e       = nxt_e;
                         T          acc   = vt<T>::zero();
                         for(; j + 4 <= e; j += 4)
                         {
@@ -525,12 +600,21 @@ namespace b200
                             acc        = mad(a2, x2, acc);
                             acc        = mad(a3, x3, acc);
                         }
-                        for(; j < e; ++j)
+                        if(j < e)
                         {
-                            int c0;
-                            T   a0;
+                            // 1-3 entries left: issued together as well (an absent entry re-reads the row's first one and is not added)
+                            const int n = e - j;
+                            int       c0, c1, c2;
+                            T         a0, a1, a2;
                             entry_at(r, j, c0, a0);
-                            acc = mad(a0, __ldca(x + c0), acc);
+                            entry_at(r, n > 1 ? j + 1 : j, c1, a1);
+                            entry_at(r, n > 2 ? j + 2 : j, c2, a2);
+                            const T x0 = __ldca(x + c0), x1 = __ldca(x + c1), x2 = __ldca(x + c2);
+                            acc        = mad(a0, x0, acc);
+                            if(n > 1)
+                                acc = mad(a1, x1, acc);
+                            if(n > 2)
+                                acc = mad(a2, x2, acc);
                         }
                         y[r] = mul(alpha, acc);
                     }
@@ -539,11 +623,20 @@ namespace b200
                 {
                     T        *push      = side == 0 ? push_left : push_right;
                     const int push_row0 = side == 0 ? 0 : hc.last_row0;
+                    // the bounds of a thread's NEXT row are requested before its current row is reduced
+                    int cur_s = pre_s, cur_e = pre_e;
                     for(int r = d.x + tid; r < d.y; r += NT)
                     {
-                        const bool first = r == d.x + tid;
-                        int        j     = (first ? pre_s : rp[r]) - a;
-                        const int  e     = (first ? pre_e : rp[r + 1]) - a;
+                        int nxt_s = 0, nxt_e = 0;
+                        if(r + NT < d.y)
+                        {
+                            nxt_s = rp[r + NT];
+                            nxt_e = rp[r + NT + 1];
+                        }
+                        int       j = cur_s - a;
+                        const int e = cur_e - a;
+                        cur_s       = nxt_s;
+                        cur_e       = nxt_e;
                         T          acc   = vt<T>::zero();
                         for(; j + 4 <= e; j += 4)
                         {
@@ -559,12 +652,21 @@ namespace b200
                             acc        = mad(a2, x2, acc);
                             acc        = mad(a3, x3, acc);
                         }
-                        for(; j < e; ++j)
+                        if(j < e)
                         {
-                            int c0;
-                            T   a0;
+                            // 1-3 entries left: issued together as well (an absent entry re-reads the row's first one and is not added)
+                            const int n = e - j;
+                            int       c0, c1, c2;
+                            T         a0, a1, a2;
                             entry_at(r, j, c0, a0);
-                            acc = mad(a0, boundary_x<T, true>(x, c0, hc.own_lo, hc.own_hi), acc);
+                            entry_at(r, n > 1 ? j + 1 : j, c1, a1);
+                            entry_at(r, n > 2 ? j + 2 : j, c2, a2);
+                            const T x0 = boundary_x<T, true>(x, c0, hc.own_lo, hc.own_hi), x1 = boundary_x<T, true>(x, c1, hc.own_lo, hc.own_hi), x2 = boundary_x<T, true>(x, c2, hc.own_lo, hc.own_hi);
+                            acc        = mad(a0, x0, acc);
+                            if(n > 1)
+                                acc = mad(a1, x1, acc);
+                            if(n > 2)
+                                acc = mad(a2, x2, acc);
                         }
                         const T out = mul(alpha, acc);
                         y[r]        = out;
@@ -574,15 +676,18 @@ namespace b200
                 }
                 __syncthreads(); // the staging buffer is free; this CTA's stores are ordered before thread 0's fences
                 const int  done_side = side;
-                // next block of this CTA: in this iteration, or the first one of the next iteration
-                const bool wraps = bid + G >= hc.n_blocks;
-                const bool more  = !wraps || it + 1 < hc.iters;
                 if(more)
                 {
-                    locate(wraps ? (int)blockIdx.x : bid + G, b, side);
-                    d = desc[b];
-                    if(tid == 0)
-                        request(d);
+                    b    = bn;
+                    side = side_n;
+                    d    = dn;
+                    if constexpr(EC)
+                    {
+                        buf ^= 1;
+                        secode = smem_raw + SMEM_HEADER + (size_t)buf * (size_t)cap;
+                    }
+                    else if(tid == 0)
+                        request(d, 0);
                 }
                 if(done_side != 2 && tid == 0)
                 {
