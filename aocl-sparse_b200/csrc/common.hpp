@@ -593,6 +593,7 @@ namespace b200
         void       *push_left[2] = {nullptr, nullptr}, *push_right[2] = {nullptr, nullptr}; // [0] neighbour's window `cur`, [1] `nxt`
         unsigned    k0 = 0, kc0 = 0, bar0 = 0;
     };
+    bool              sharded_prefers_steps(aoclsparse_matrix A);
     aoclsparse_status sharded_iterate_launch(double                      alpha,
                                              aoclsparse_matrix           A,
                                              const aoclsparse_mat_descr  descr,

@@ -344,16 +344,6 @@ namespace b200
         plan_parameters(elem_size, A.m, A.nnz, max_row_nnz, P.block_nnz, P.block_rows, coded);
         if(block_nnz_override > 0)
             P.block_nnz = block_nnz_override;
-        // Row cuts mean the handle is a shard of a row-sharded iteration (shard.cu): its entry-coded blocks are walked by
-        // the PERSISTENT kernel, whose CTAs each take every G-th block between two grid barriers -- they finish together only
-        // if each takes many blocks.  Blocks as large as still leave 24 rounds, within [512, 2048] rows (2 GPUs, 7-point
-        // 512^3: 2048 rows = 28 rounds; 8 GPUs: 576 rows = 25 rounds instead of 8 rounds of 1728 rows, 9 for some CTAs).
-        if(coded == 2 && !row_cuts.empty() && P.block_rows >= 512 && !getenv("AOCLSPARSE_B200_BLOCK_ROWS"))
-        {
-            const long long slots = ctas_per_wave(elem_size, P.block_nnz, 2);
-            long long       r     = (long long)A.m / (24 * slots) / 64 * 64;
-            P.block_rows          = (aoclsparse_int)(r < 512 ? 512 : (r > 2048 ? 2048 : r));
-        }
         // few rows per block (long rows or wide values): the thread-per-row strategy keeps only one lane per row busy, so
         // smaller CTAs put more of them -- hence more rows in flight -- on an SM
         {

@@ -380,7 +380,7 @@ aoclsparse_status aoclsparse_b200_shard_iterate(aoclsparse_b200_shard shard, dou
         const char *e = getenv("AOCLSPARSE_B200_SHARD_PERSISTENT");
         return !(e && atoi(e) == 0);
     }();
-    if(shard->world > 1 && shard->fused && shard->own_gpu && persistent && iterations >= 2)
+    if(shard->world > 1 && shard->fused && shard->own_gpu && persistent && iterations >= 2 && !sharded_prefers_steps(shard->A))
     {
         const int            cur = shard->cur, nxt = cur ^ 1;
         sharded_iterate_args a;

@@ -1366,6 +1366,19 @@ aoclsparse_status b200::sharded_step_launch(const double                  *alpha
 // the two x windows (the current iterate lives in w_cur); push_*[i] are the neighbours' halo slots of window i
 // (0 = the window w_cur maps to in the neighbour, 1 = the other one).  *grid_out = CTAs launched (the grid barrier
 // counter advances by (iterations - 1) * grid).
+// true when the shard's multiply runs on the entry-code copy: its iterations are launched one step kernel each
+// (see the note at spmv_sharded_iterate_kernel)
+bool b200::sharded_prefers_steps(aoclsparse_matrix A)
+{
+    if(!A || A->mats.empty() || A->mats[0] == nullptr)
+        return true;
+    if(ensure_plan(A, current_stream()) != aoclsparse_status_success)
+        return true;
+    std::shared_lock<std::shared_mutex> rl(A->guard);
+    const row_block_plan               &P0 = A->mats[0]->plan;
+    return P0.n_codes > 0 && P0.n_ecodes > 0 && !P0.ecodes_stale && P0.eplan && P0.eplan->cut_block.size() == 2;
+}
+
 aoclsparse_status b200::sharded_iterate_launch(double                     alpha,
                                                aoclsparse_matrix          A,
                                                const aoclsparse_mat_descr descr,
@@ -1393,9 +1406,8 @@ aoclsparse_status b200::sharded_iterate_launch(double                     alpha,
     std::shared_lock<std::shared_mutex> rl(A->guard);
     const dev_csr                      &M = *A->mats[0];
     const row_block_plan               &P0 = M.plan;
-    // entry-code copy: the kernel walks the block plan built for it (same cuts)
-    const bool                          ec = P0.n_codes > 0 && P0.n_ecodes > 0 && !P0.ecodes_stale && P0.eplan && P0.eplan->cut_block.size() == 2;
-    const row_block_plan               &P  = ec ? *P0.eplan : P0;
+    // (entry-coded shards run one step kernel per iteration: sharded_prefers_steps)
+    const row_block_plan               &P  = P0;
     if(A->row_cuts.size() != 2 || P.cut_block.size() != 2 || P.n_strat[STRAT_THREAD] != P.n_blocks || P.n_blocks < 1)
         return aoclsparse_status_not_implemented;
     iterate_ctl hc;
@@ -1422,16 +1434,12 @@ aoclsparse_status b200::sharded_iterate_launch(double                     alpha,
     // iteration 0 reads w_cur and writes the own rows of w_nxt; the neighbours receive into THEIR w_nxt (slot 1)
     const double *x0 = w_cur - shift, *x1 = w_nxt - shift;
     double       *y0 = w_nxt + own_offset, *y1 = w_cur + own_offset;
-    const bool   coded = P0.n_codes > 0 && !ec;
-    const aoclsparse_int e_nnz = P.max_block_nnz > 0 ? P.max_block_nnz : P.block_nnz; // entry codes: the largest block sizes the buffers
-    int          cap   = ec ? spmv_ecoded_cap(e_nnz) : P.block_nnz + (coded ? 32 : 8);
-    // entry codes: two code buffers (the next block's slice arrives while the current block is reduced)
-    const size_t smem  = ec ? spmv_ecoded_smem_bytes(sizeof(double), e_nnz) + (size_t)cap
-                            : (coded ? spmv_coded_smem_bytes(sizeof(double), P.block_nnz) : spmv_smem_bytes(sizeof(double), P.block_nnz));
-    auto         kern  = ec ? spmv_sharded_iterate_kernel<double, false, true>
-                            : (coded ? spmv_sharded_iterate_kernel<double, true, false> : spmv_sharded_iterate_kernel<double, false, false>);
-    static std::atomic<size_t> configured[3] = {{0}, {0}, {0}};
-    const int                  variant       = ec ? 2 : (coded ? 1 : 0);
+    const bool   coded = P0.n_codes > 0;
+    int          cap   = P.block_nnz + (coded ? 32 : 8);
+    const size_t smem  = coded ? spmv_coded_smem_bytes(sizeof(double), P.block_nnz) : spmv_smem_bytes(sizeof(double), P.block_nnz);
+    auto         kern  = coded ? spmv_sharded_iterate_kernel<double, true> : spmv_sharded_iterate_kernel<double, false>;
+    static std::atomic<size_t> configured[2] = {{0}, {0}};
+    const int                  variant       = coded ? 1 : 0;
     if(configured[variant].load() < smem)
     {
         B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1460,11 +1468,10 @@ aoclsparse_status b200::sharded_iterate_launch(double                     alpha,
     double               *pl1     = static_cast<double *>(args.push_left[0]);
     double               *pr0     = static_cast<double *>(args.push_right[1]);
     double               *pr1     = static_cast<double *>(args.push_right[0]);
-    const unsigned char  *p_codes = ec ? P0.ecodes.as<unsigned char>() : P0.codes.as<unsigned char>();
-    const int            *p_off   = ec ? P0.etab_off.as<int>() : P0.code_offsets.as<int>();
-    const double         *p_cval  = P0.etab_val.as<double>();
-    int                   n_table = (int)(ec ? P0.n_ecodes : P0.n_codes);
-    void *params[] = {&p_desc, &cap, &p_rp, &p_col, &p_val, &x0, &x1, &y0, &y1, &alpha, &pl0, &pl1, &pr0, &pr1, &hc, &p_codes, &p_off, &p_cval, &n_table};
+    const unsigned char  *p_codes = P0.codes.as<unsigned char>();
+    const int            *p_off   = P0.code_offsets.as<int>();
+    int                   n_table = (int)P0.n_codes;
+    void *params[] = {&p_desc, &cap, &p_rp, &p_col, &p_val, &x0, &x1, &y0, &y1, &alpha, &pl0, &pl1, &pr0, &pr1, &hc, &p_codes, &p_off, &n_table};
     B200_CUDA(cudaLaunchCooperativeKernel((const void *)kern, dim3((unsigned)grid), dim3(256), params, smem, st));
     B200_LAUNCHED();
     *grid_out = (int)grid;

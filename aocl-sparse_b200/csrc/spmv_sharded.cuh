@@ -368,6 +368,10 @@ namespace b200
     //     CTAs stored during iteration k, so the gathers use ld.global.ca (coherent after the acquire) instead of the
     //     non-coherent path; halo entries, stored by the peer GPU while this iteration runs, are read at L2 (ld.cg).
     // Results are bit-identical to k launches of the step kernel (same blocks, same per-row order of operations).
+    // Plain and diagonal-coded streams only.  ENTRY-CODED shards (one staged byte per entry) run one step kernel per
+    // iteration instead: that multiply is bound by the L1 pipeline, not by HBM, and hardware-scheduled CTAs of the step
+    // kernel beat this statically scheduled grid by 25-35 % there (2 GPUs, 7-point 512^3: 0.440 ms per iteration against
+    // 0.551-0.677 ms; 64 planes per rank: 0.122 against 0.145 ms; profiles/r02_sharded_entry_codes.txt).
     struct iterate_ctl
     {
         const unsigned *left_done, *right_done;
@@ -382,7 +386,7 @@ namespace b200
         int             cta_fence_gpu;  // see boundary_release
     };
 
-    template <typename T, bool CODED, bool EC = false>
+    template <typename T, bool CODED>
     __global__ void __launch_bounds__(256) spmv_sharded_iterate_kernel(const int4 *__restrict__ desc,
                                                                       int cap,
                                                                       const aoclsparse_int *__restrict__ rp,
@@ -400,24 +404,16 @@ namespace b200
                                                                       iterate_ctl hc,
                                                                       const unsigned char *__restrict__ codes,
                                                                       const int *__restrict__ code_off,
-                                                                      const T *__restrict__ code_val,
                                                                       int n_table)
     {
         constexpr int NT = 256;
-        static_assert(!(CODED && EC), "one code stream at a time");
-        using pair_t = entry_pair<T>;
         extern __shared__ __align__(16) unsigned char smem_raw[];
         uint64_t            *bar    = reinterpret_cast<uint64_t *>(smem_raw);
         T                   *sval   = reinterpret_cast<T *>(smem_raw + SMEM_HEADER);
         aoclsparse_int      *scol   = reinterpret_cast<aoclsparse_int *>(smem_raw + SMEM_HEADER + (size_t)cap * sizeof(T));
         const unsigned char *scode  = smem_raw + SMEM_HEADER + (size_t)cap * sizeof(T);
         int                 *soff   = reinterpret_cast<int *>(smem_raw + SMEM_HEADER + (size_t)cap * (sizeof(T) + 1));
-        // EC: TWO code buffers (one staged byte per entry is cheap), so the next block's slice is requested BEFORE the
-        // current block is reduced and its latency never shows; the header holds one mbarrier per buffer
-        const unsigned char *secode = smem_raw + SMEM_HEADER;                                              // EC: current buffer
-        pair_t              *stab   = reinterpret_cast<pair_t *>(smem_raw + SMEM_HEADER + 2 * (size_t)cap); // EC
-        int                  buf    = 0;                                                                   // EC: index of the current buffer
-        constexpr int        GR     = (CODED || EC) ? 16 : 4;
+        constexpr int        GR     = CODED ? 16 : 4;
 
         const int tid = threadIdx.x;
         const int G   = (int)gridDim.x;
@@ -440,18 +436,13 @@ namespace b200
                 side = 2;
             }
         };
-        // thread 0: request the matrix slice of block descriptor d into the staging buffer (EC: into buffer `into`)
-        auto request = [&](const int4 &d, int into) {
+        // thread 0: request the matrix slice of block descriptor d into the staging buffer
+        auto request = [&](const int4 &d) {
             const int a   = d.z & ~(GR - 1);
             const int cnt = ((d.w - a) + GR - 1) & ~(GR - 1);
             if(cnt <= 0)
                 return;
-            if constexpr(EC)
-            {
-                mbar_expect_tx(bar + into, (unsigned)cnt);
-                bulk_load_stream(smem_raw + SMEM_HEADER + (size_t)into * (size_t)cap, codes + a, (unsigned)cnt, bar + into);
-            }
-            else if constexpr(CODED)
+            if constexpr(CODED)
             {
                 mbar_expect_tx(bar, (unsigned)(cnt * (sizeof(T) + 1)));
                 bulk_load_stream(sval, val + a, (unsigned)(cnt * sizeof(T)), bar);
@@ -465,13 +456,7 @@ namespace b200
             }
         };
         auto entry_at = [&](int r, int j, int &c, T &v) {
-            if constexpr(EC)
-            {
-                const pair_t pr = stab[secode[j]];
-                c               = r + pr.off;
-                v               = pr.v;
-            }
-            else if constexpr(CODED)
+            if constexpr(CODED)
             {
                 c = r + soff[scode[j]];
                 v = sval[j];
@@ -486,21 +471,11 @@ namespace b200
         if(tid == 0)
         {
             mbar_init(bar, 1);
-            if constexpr(EC)
-                mbar_init(bar + 1, 1);
             mbar_init_fence();
         }
         if constexpr(CODED)
             for(int i = tid; i < n_table; i += NT)
                 soff[i] = code_off[i];
-        if constexpr(EC)
-            for(int i = tid; i < n_table; i += NT)
-            {
-                pair_t pr;
-                pr.v    = code_val[i];
-                pr.off  = code_off[i];
-                stab[i] = pr;
-            }
         __syncthreads();
         if((int)blockIdx.x >= hc.n_blocks || hc.iters <= 0)
             return; // host launches G <= n_blocks
@@ -512,7 +487,7 @@ namespace b200
         auto      nth    = [&](int i) -> int { return c_id + i * G; };
         // (a CTA without blocks -- possible only when there are about as many CTAs as blocks -- still takes part in
         // every grid barrier below)
-        unsigned parity = 0; // bit i: phase of buffer i's barrier
+        unsigned parity = 0;
         int      b = 0, side = 2;
         int4     d = make_int4(0, 0, 0, 0);
         if(n_mine > 0)
@@ -520,7 +495,7 @@ namespace b200
             locate(nth(0), b, side);
             d = desc[b];
             if(tid == 0)
-                request(d, 0);
+                request(d);
         }
 
         for(int it = 0; it < hc.iters; ++it)
@@ -544,9 +519,6 @@ namespace b200
                 {
                     locate(wraps ? nth(0) : nth(ib + 1), bn, side_n);
                     dn = desc[bn];
-                    if constexpr(EC)
-                        if(tid == 0)
-                            request(dn, buf ^ 1); // everybody left that buffer at the end of the previous block
                 }
                 int       pre_s = 0, pre_e = 0;
                 if(d.x + tid < d.y)
@@ -566,8 +538,8 @@ namespace b200
                 }
                 if(cnt > 0)
                 {
-                    mbar_wait(bar + buf, (parity >> buf) & 1u);
-                    parity ^= 1u << buf;
+                    mbar_wait(bar, parity);
+                    parity ^= 1u;
                 }
                 if(side == 2)
                 {
@@ -681,13 +653,8 @@ namespace b200
                     b    = bn;
                     side = side_n;
                     d    = dn;
-                    if constexpr(EC)
-                    {
-                        buf ^= 1;
-                        secode = smem_raw + SMEM_HEADER + (size_t)buf * (size_t)cap;
-                    }
-                    else if(tid == 0)
-                        request(d, 0);
+                    if(tid == 0)
+                        request(d);
                 }
                 if(done_side != 2 && tid == 0)
                 {

@@ -788,7 +788,7 @@ def measure(args, key, primary):
                        "capture of this kernel, " + str(tj.get("_captured", "round 1")) + "); not re-measured in this run")
     roof = {"bound": "hbm", "unit": "GB/s", "peak": peak, "peak_source": peak_src, "traffic": traffic,
             "traffic_source": traffic_src,
-            "kernel": (("spmv_sharded_iterate_kernel" if batched else "spmv_sharded_step_kernel")
+            "kernel": (("spmv_sharded_iterate_kernel" if (batched and launches < steps) else "spmv_sharded_step_kernel")
                        if (sharded and world > 1 and halo_mode in ("p2p-fused", "shard-c-abi"))
                        else "spmv_row_blocks_kernel") if wl["kind"] == "mv" else
             ("csrmm_mesh_tiles_kernel" if (tiles and tiles["state"] == 2) else "csrmm_row_major_vec_kernel"),
@@ -836,8 +836,11 @@ def measure(args, key, primary):
         "dtype": {"s": "f32", "d": "f64"}[p], "data": "synthetic",
         "config": {"workload": wl["name"], "rows": int(n_glob if sharded else m), "nnz": int(g_nnz),
                    "parallelism": ((f"row slabs x{world}, halo: {halo_mode}"
-                                    + (", all timed iterations in ONE aoclsparse_b200_shard_iterate call (persistent kernel, "
-                                       "grid barrier between iterations)" if batched else "")) if sharded else "single GPU"),
+                                    + ((", all timed iterations in ONE aoclsparse_b200_shard_iterate call ("
+                                        + ("persistent kernel, grid barrier between iterations" if launches < steps else
+                                           "entry-coded shard: one fused step kernel per iteration, launched back to back "
+                                           "by the call, no host synchronisation") + ")") if batched else ""))
+                                   if sharded else "single GPU"),
                    "l2": ("operands larger than L2: %.0f MB streamed per step vs 126 MB L2" % (l_bytes / 1e6))
                    if (sharded or wl["kind"] == "mm" or n_sets == 1) else
                    ("rotating over %d independent (A,x,y) sets, %.0f MB in total vs 126 MB L2" % (n_sets, n_sets * l_bytes / 1e6)),

@@ -408,11 +408,6 @@ void oracle_plan_parameters(int elem_size, int m, int nnz, int max_row_nnz, cons
             r = (((long long)m + slots - 1) / slots + 31) / 32 * 32;
             r = r < 64 ? 64 : r;
         }
-        if(n_cuts > 0 && r >= 512) /* a shard of a row-sharded iteration (persistent kernel): at least 24 rounds of blocks */
-        {
-            r = (long long)m / (24 * slots) / 64 * 64;
-            r = r < 512 ? 512 : (r > 2048 ? 2048 : r);
-        }
         *T                    = t;
         *R                    = (int)r;
         if(m > 0 && rp && r >= 512 && (long long)m < 8 * slots * r && (long long)m >= slots * r)
