@@ -142,7 +142,9 @@ class AoclSparse:
         L.aoclsparse_spmm.argtypes = [ci, vp, vp, C.POINTER(vp)]
         L.aoclsparse_sp2m.argtypes = [ci, vp, vp, ci, vp, vp, ci, C.POINTER(vp)]
         if hasattr(L, "aoclsparse_itsol_d_init"):
-            for p in "sd":
+            for p in "sdcz":
+                if not hasattr(L, f"aoclsparse_itsol_{p}_solve"):
+                    continue
                 getattr(L, f"aoclsparse_itsol_{p}_init").argtypes = [C.POINTER(vp)]
                 getattr(L, f"aoclsparse_itsol_{p}_rci_input").argtypes = [vp, i32, vp]
                 getattr(L, f"aoclsparse_itsol_{p}_rci_solve").argtypes = [vp, C.POINTER(ci), C.POINTER(vp), C.POINTER(vp), vp, vp]
@@ -286,15 +288,20 @@ class AoclSparse:
 
     def itsol_solve(self, prefix, h, n, mat, descr, b, x, rinfo, precond=None, monit=None):
         """precond(flag, n, u, v) / monit(n, x, r, rinfo) are Python callables on numpy views; both return an int"""
-        ct = C.c_double if prefix == "d" else C.c_float
-        dt = np.float64 if prefix == "d" else np.float32
+        ct = C.c_double if prefix in "dz" else C.c_float          # real scalar type (rinfo; vectors of s / d)
+        dt = np.float64 if prefix in "dz" else np.float32
+        cplx = prefix in "cz"                                      # vectors are (re, im) pairs of ct
         PT = C.POINTER(ct)
         keep = []
 
-        def view(ptr, count):
+        def view(ptr, count, vector=True):
             if not ptr:
                 return None  # the reference hands its monitor a NULL residual pointer (see DESIGN.md)
-            return np.ctypeslib.as_array(ptr, shape=(count,)) if count else np.zeros(0, dt)
+            if not count:
+                return np.zeros(0, dt)
+            if cplx and vector:
+                return np.ctypeslib.as_array(ptr, shape=(2 * count,)).view(np.complex128 if prefix == "z" else np.complex64)
+            return np.ctypeslib.as_array(ptr, shape=(count,))
         cb_p = cb_m = None
         if precond is not None:
             cb_p = C.CFUNCTYPE(C.c_int, C.c_int, C.c_int, PT, PT, C.c_void_p)(
@@ -302,7 +309,7 @@ class AoclSparse:
             keep.append(cb_p)
         if monit is not None:
             cb_m = C.CFUNCTYPE(C.c_int, C.c_int, PT, PT, PT, C.c_void_p)(
-                lambda nn, xx, rr, ri, ud: int(monit(nn, view(xx, nn), view(rr, nn), view(ri, 100))))
+                lambda nn, xx, rr, ri, ud: int(monit(nn, view(xx, nn), view(rr, nn), view(ri, 100, False))))
             keep.append(cb_m)
         as_vp = lambda f: C.cast(f, C.c_void_p) if f is not None else None  # noqa: E731
         return getattr(self.lib, f"aoclsparse_itsol_{prefix}_solve")(

@@ -3,11 +3,12 @@
 // Reference: the iterative-solver suite of library/src/solvers/aoclsparse_itsol_functions.{hpp,cpp}: a handle with an
 // option registry (aoclsparse_itsol_list_options.hpp:63-239), a reverse-communication CG state machine
 // (aoclsparse_cg_rci_solve, itsol_functions.hpp:633-870) and a forward interface that drives it with aoclsparse::mv on a
-// symmetric / lower descriptor (aoclsparse_cg_solve, :1369-1500).  Kept here: aoclsparse_itsol_{s,d}_init,
+// symmetric / lower descriptor (aoclsparse_cg_solve, :1369-1500).  Kept here: aoclsparse_itsol_{s,d,c,z}_init,
 // aoclsparse_itsol_destroy, aoclsparse_itsol_option_set (all registered options, same names, bounds, defaults and
-// normalisation), aoclsparse_itsol_{s,d}_rci_input, aoclsparse_itsol_{s,d}_rci_solve and aoclsparse_itsol_{s,d}_solve for
-// the CG method with no or a user preconditioner.  GMRES, the symmetric Gauss-Seidel preconditioner and the complex
-// variants return aoclsparse_status_not_implemented.
+// normalisation), aoclsparse_itsol_{s,d,c,z}_rci_input, aoclsparse_itsol_{s,d,c,z}_rci_solve and
+// aoclsparse_itsol_{s,d,c,z}_solve for the CG method with no or a user preconditioner (complex handles: the section
+// "complex conjugate gradients" below).  GMRES and the symmetric Gauss-Seidel preconditioner return
+// aoclsparse_status_not_implemented.
 //
 // B200: the state machine and its scalar logic (tolerances, iteration limit, breakdown tests, rinfo) are the reference's;
 // every vector operation is a CUDA kernel on vectors that never leave the device in the forward interface:
@@ -27,6 +28,7 @@
 #include <algorithm>
 #include <cctype>
 #include <cmath>
+#include <complex>
 #include <limits>
 #include <string>
 
@@ -859,6 +861,33 @@ namespace b200
                 return aoclsparse_status_invalid_pointer;
             }
             aoclsparse_status status;
+            if(!it->solving && !it->vectors_managed)
+            {
+                // The last forward solve ran without callbacks and left the work vectors in plain device memory; this
+                // interface hands *u / *v to a caller who may read and write them from the host (the reference allows
+                // rci_solve after solve without a new rci_input): move b to managed memory, re-allocate the others.
+                cudaStream_t    st    = current_stream();
+                const size_t    bytes = sizeof(T) * (size_t)it->n;
+                managed_buf     nb;
+                status = nb.alloc(bytes, st, true);
+                if(status == aoclsparse_status_success && bytes
+                   && cudaMemcpyAsync(nb.p, it->b.p, bytes, cudaMemcpyDefault, st) != cudaSuccess)
+                    status = aoclsparse_status_internal_error;
+                if(status == aoclsparse_status_success && cudaStreamSynchronize(st) != cudaSuccess)
+                    status = aoclsparse_status_internal_error;
+                for(managed_buf *m : {&it->r, &it->p, &it->q, &it->z})
+                    if(status == aoclsparse_status_success)
+                        status = m->alloc(bytes, st, true);
+                if(status != aoclsparse_status_success)
+                {
+                    *ircomm = aoclsparse_rci_stop;
+                    return status;
+                }
+                std::swap(it->b.p, nb.p);
+                std::swap(it->b.bytes, nb.bytes);
+                it->vectors_managed = true;
+                it->xw.release();
+            }
             if(!it->solving)
             {
                 status = solver_init(it);
@@ -1069,6 +1098,572 @@ namespace b200
             it->opts.locked = false;
             return exit_status;
         }
+
+        // ================================================================ complex conjugate gradients (c / z handles)
+        // The reference instantiates the SAME state machine for std::complex (itsol_functions.hpp:633-870, handles made by
+        // aoclsparse_itsol_{c,z}_init, itsol_functions.cpp:168-230).  What that means for complex data, restated here:
+        //   * r.z and p.q are UNCONJUGATED sums of products (:795-797, :822-824); with a complex SYMMETRIC matrix -- the
+        //     forward interface insists on a symmetric, lower descriptor (:1411-1417) -- that is the conjugate-orthogonal
+        //     recurrence, not the Hermitian one;
+        //   * rz starts at (1, 1) (:718-725); the breakdown tests compare |rz| and |p.q| with the near-zero bound
+        //     (aoclsparse_utils.hpp:627-640); tolerances, norms and rinfo are real.
+        // Host-driven: the scalar logic runs on the host as in cg_rci, every vector operation is a kernel; two complex
+        // scalars and one norm per iteration travel back through mapped memory.  Work vectors are managed memory (a host
+        // caller of the reverse-communication interface reads and writes *u / *v as ordinary memory).
+        template <typename R>
+        struct cplx_types;
+        template <>
+        struct cplx_types<float>
+        {
+            using dev = float2;
+            using api = aoclsparse_float_complex;
+        };
+        template <>
+        struct cplx_types<double>
+        {
+            using dev = double2;
+            using api = aoclsparse_double_complex;
+        };
+
+        template <typename C>
+        __device__ __forceinline__ C c_mul(C a, C b)
+        {
+            C r;
+            r.x = a.x * b.x - a.y * b.y;
+            r.y = a.x * b.y + a.y * b.x;
+            return r;
+        }
+
+        // two block sums -> partial[2 b], partial[2 b + 1]; the LAST block adds the partials in index order and stores
+        // both sums into result[0..1] (mapped host memory)
+        __device__ __forceinline__ void block_sum_store2(double s0, double s1, reduce_out o)
+        {
+            __shared__ double sh[2][RED_THREADS / 32];
+            __shared__ bool   last;
+            __shared__ double fin[2][RED_THREADS];
+#pragma unroll
+            for(int k = 16; k > 0; k >>= 1)
+            {
+                s0 += __shfl_down_sync(0xffffffffu, s0, k);
+                s1 += __shfl_down_sync(0xffffffffu, s1, k);
+            }
+            if((threadIdx.x & 31) == 0)
+            {
+                sh[0][threadIdx.x >> 5] = s0;
+                sh[1][threadIdx.x >> 5] = s1;
+            }
+            __syncthreads();
+            if(threadIdx.x < 32)
+            {
+                s0 = threadIdx.x < RED_THREADS / 32 ? sh[0][threadIdx.x] : 0.0;
+                s1 = threadIdx.x < RED_THREADS / 32 ? sh[1][threadIdx.x] : 0.0;
+#pragma unroll
+                for(int k = 16; k > 0; k >>= 1)
+                {
+                    s0 += __shfl_down_sync(0xffffffffu, s0, k);
+                    s1 += __shfl_down_sync(0xffffffffu, s1, k);
+                }
+                if(threadIdx.x == 0)
+                {
+                    o.partial[2 * blockIdx.x]     = s0;
+                    o.partial[2 * blockIdx.x + 1] = s1;
+                    __threadfence();
+                    last = atomicAdd(o.ticket, 1u) == gridDim.x - 1;
+                }
+            }
+            __syncthreads();
+            if(!last)
+                return;
+            __threadfence();
+            double t0 = 0, t1 = 0;
+            for(int i = threadIdx.x; i < (int)gridDim.x; i += RED_THREADS)
+            {
+                t0 += __ldcg(o.partial + 2 * i);
+                t1 += __ldcg(o.partial + 2 * i + 1);
+            }
+            fin[0][threadIdx.x] = t0;
+            fin[1][threadIdx.x] = t1;
+            __syncthreads();
+            for(int k = RED_THREADS / 2; k > 0; k >>= 1)
+            {
+                if(threadIdx.x < k)
+                {
+                    fin[0][threadIdx.x] += fin[0][threadIdx.x + k];
+                    fin[1][threadIdx.x] += fin[1][threadIdx.x + k];
+                }
+                __syncthreads();
+            }
+            if(threadIdx.x == 0)
+            {
+                o.result[0] = fin[0][0];
+                o.result[1] = fin[1][0];
+                *o.ticket   = 0;
+                __threadfence_system();
+            }
+        }
+
+#define B200_GRID_STRIDE(i, n) \
+    for(long long i = (long long)blockIdx.x * RED_THREADS + threadIdx.x; i < (n); i += (long long)gridDim.x * RED_THREADS)
+
+        // r = -b, p = x, |b|^2
+        template <typename C>
+        __global__ void __launch_bounds__(RED_THREADS) ccg_start_kernel(long long n, const C *__restrict__ b, const C *__restrict__ x,
+                                                                       C *__restrict__ r, C *__restrict__ p, reduce_out out)
+        {
+            double s = 0;
+            B200_GRID_STRIDE(i, n)
+            {
+                const C bi = b[i];
+                C       ri;
+                ri.x = -bi.x;
+                ri.y = -bi.y;
+                r[i] = ri;
+                p[i] = x[i];
+                s += (double)bi.x * (double)bi.x + (double)bi.y * (double)bi.y;
+            }
+            block_sum_store2(s, 0.0, out);
+        }
+
+        // r += q, p = 0, |r|^2
+        template <typename C>
+        __global__ void __launch_bounds__(RED_THREADS) ccg_residual_kernel(long long n, C *__restrict__ r, const C *__restrict__ q,
+                                                                          C *__restrict__ p, reduce_out out)
+        {
+            double s = 0;
+            B200_GRID_STRIDE(i, n)
+            {
+                C       ri = r[i];
+                const C qi = q[i];
+                ri.x += qi.x;
+                ri.y += qi.y;
+                r[i] = ri;
+                C zero;
+                zero.x = 0;
+                zero.y = 0;
+                p[i]   = zero;
+                s += (double)ri.x * (double)ri.x + (double)ri.y * (double)ri.y;
+            }
+            block_sum_store2(s, 0.0, out);
+        }
+
+        // sum of a[i] * b[i], NOT conjugated
+        template <typename C>
+        __global__ void __launch_bounds__(RED_THREADS) cdot_kernel(long long n, const C *__restrict__ a, const C *__restrict__ b, reduce_out out)
+        {
+            double s0 = 0, s1 = 0;
+            B200_GRID_STRIDE(i, n)
+            {
+                const C ai = a[i], bi = b[i];
+                s0 += (double)ai.x * (double)bi.x - (double)ai.y * (double)bi.y;
+                s1 += (double)ai.x * (double)bi.y + (double)ai.y * (double)bi.x;
+            }
+            block_sum_store2(s0, s1, out);
+        }
+
+        // p = beta p - z
+        template <typename C>
+        __global__ void __launch_bounds__(RED_THREADS) ccg_direction_kernel(long long n, C beta, C *__restrict__ p, const C *__restrict__ z)
+        {
+            B200_GRID_STRIDE(i, n)
+            {
+                C       t  = c_mul(beta, p[i]);
+                const C zi = z[i];
+                t.x -= zi.x;
+                t.y -= zi.y;
+                p[i] = t;
+            }
+        }
+
+        // x += alpha p, r += alpha q, |r|^2
+        template <typename C>
+        __global__ void __launch_bounds__(RED_THREADS) ccg_step_kernel(long long n, C alpha, const C *__restrict__ p, const C *__restrict__ q,
+                                                                      C *__restrict__ x, C *__restrict__ r, reduce_out out)
+        {
+            double s = 0;
+            B200_GRID_STRIDE(i, n)
+            {
+                const C ap = c_mul(alpha, p[i]), aq = c_mul(alpha, q[i]);
+                C       xi = x[i], ri = r[i];
+                xi.x += ap.x;
+                xi.y += ap.y;
+                ri.x += aq.x;
+                ri.y += aq.y;
+                x[i] = xi;
+                r[i] = ri;
+                s += (double)ri.x * (double)ri.x + (double)ri.y * (double)ri.y;
+            }
+            block_sum_store2(s, 0.0, out);
+        }
+#undef B200_GRID_STRIDE
+
+        template <typename R>
+        struct itsol_cdata
+        {
+            using C = typename cplx_types<R>::dev;
+            options<R>      opts;
+            aoclsparse_int  n       = 0;
+            bool            have_b  = false;
+            bool            solving = false;
+            managed_buf     b, r, p, q, z, xw;
+            dev_buf         partial, ticket;
+            double         *h_result = nullptr, *d_result = nullptr; // two mapped page-locked doubles
+            int             task = task_start, niter = 0, precond = 0, maxit = 500;
+            R               rtol = 0, atol = 0, rnorm2 = 0, bnorm2 = 0, brtol = 0;
+            std::complex<R> rz, alpha, beta;
+            C              *x_dev = nullptr, *x_user = nullptr;
+            ~itsol_cdata()
+            {
+                if(h_result)
+                    cudaFreeHost(h_result);
+            }
+        };
+
+        template <typename R>
+        aoclsparse_status crci_input(itsol_cdata<R> *it, aoclsparse_int n, const void *b)
+        {
+            using C = typename cplx_types<R>::dev;
+            if(it == nullptr)
+                return aoclsparse_status_internal_error;
+            if(n < 0)
+                return aoclsparse_status_invalid_value;
+            if(!b)
+                return aoclsparse_status_invalid_pointer;
+            cudaStream_t st = current_stream();
+            it->have_b      = false;
+            if(it->n != n || !it->b.p)
+            {
+                for(managed_buf *m : {&it->b, &it->r, &it->p, &it->q, &it->z})
+                    B200_TRY(m->alloc(sizeof(C) * (size_t)n, st, true));
+                it->xw.release();
+            }
+            B200_TRY(it->partial.alloc(sizeof(double) * 2 * RED_BLOCKS));
+            B200_TRY(it->ticket.alloc(sizeof(unsigned)));
+            B200_CUDA(cudaMemsetAsync(it->ticket.p, 0, sizeof(unsigned), st));
+            if(!it->h_result)
+            {
+                B200_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&it->h_result), 2 * sizeof(double), cudaHostAllocMapped));
+                B200_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void **>(&it->d_result), it->h_result, 0));
+            }
+            if(n > 0)
+                B200_CUDA(cudaMemcpyAsync(it->b.p, b, sizeof(C) * (size_t)n, cudaMemcpyDefault, st));
+            B200_CUDA(cudaStreamSynchronize(st));
+            it->n       = n;
+            it->have_b  = true;
+            it->solving = false;
+            return aoclsparse_status_success;
+        }
+
+        template <typename R>
+        aoclsparse_status ccg_rci(itsol_cdata<R> *it, aoclsparse_itsol_rci_job *ircomm, void **u, void **v, void *x_, R rinfo[100])
+        {
+            using C  = typename cplx_types<R>::dev;
+            using SC = std::complex<R>;
+            cudaStream_t        st = current_stream();
+            const aoclsparse_int n  = it->n;
+            C                  *x  = static_cast<C *>(x_);
+            C *r = it->r.template as<C>(), *p = it->p.template as<C>(), *q = it->q.template as<C>(), *z = it->z.template as<C>();
+            reduce_out out{it->partial.template as<double>(), it->ticket.template as<unsigned>(), it->d_result};
+            auto       fetch = [&](double &re, double &im) -> aoclsparse_status {
+                B200_CUDA(cudaStreamSynchronize(st));
+                re = static_cast<volatile double *>(it->h_result)[0];
+                im = static_cast<volatile double *>(it->h_result)[1];
+                return aoclsparse_status_success;
+            };
+            auto sync_x = [&]() -> aoclsparse_status {
+                if(it->x_user && n > 0)
+                    B200_CUDA(cudaMemcpyAsync(it->x_user, it->x_dev, sizeof(C) * (size_t)n, cudaMemcpyDeviceToHost, st));
+                B200_CUDA(cudaStreamSynchronize(st));
+                return aoclsparse_status_success;
+            };
+            const R eps_tol = (R)1e-2 * (R)2.0 * std::numeric_limits<R>::epsilon();
+            if(it->task != task_start && *ircomm == aoclsparse_rci_interrupt)
+            {
+                B200_TRY(sync_x());
+                *ircomm = aoclsparse_rci_stop;
+                return aoclsparse_status_user_stop;
+            }
+            aoclsparse_status exit_status = aoclsparse_status_success;
+            bool              loop;
+            double            re = 0, im = 0;
+            do
+            {
+                loop = false;
+                switch(it->task)
+                {
+                case task_start:
+                    for(int i = 0; i < 100; ++i)
+                        rinfo[i] = (R)0;
+                    it->niter = 0;
+                    if(is_device_accessible(x))
+                    {
+                        it->x_dev  = x;
+                        it->x_user = nullptr;
+                    }
+                    else
+                    {
+                        B200_TRY(it->xw.alloc(sizeof(C) * (size_t)n, st, true));
+                        if(n > 0)
+                            B200_CUDA(cudaMemcpyAsync(it->xw.p, x, sizeof(C) * (size_t)n, cudaMemcpyHostToDevice, st));
+                        it->x_dev  = it->xw.template as<C>();
+                        it->x_user = x;
+                    }
+                    ccg_start_kernel<C><<<RED_BLOCKS, RED_THREADS, 0, st>>>(n, it->b.template as<C>(), it->x_dev, r, p, out);
+                    B200_LAUNCHED();
+                    B200_TRY(fetch(re, im));
+                    it->bnorm2 = (R)std::sqrt(re);
+                    if(it->bnorm2 != it->bnorm2)
+                        return aoclsparse_status_invalid_value; // b is rubbish
+                    rinfo[1]  = it->bnorm2;
+                    it->brtol = it->rtol * it->bnorm2;
+                    *ircomm   = aoclsparse_rci_mv;
+                    it->task  = task_init_res;
+                    *u        = p;
+                    *v        = q;
+                    break;
+
+                case task_init_res:
+                    ccg_residual_kernel<C><<<RED_BLOCKS, RED_THREADS, 0, st>>>(n, r, q, p, out);
+                    B200_LAUNCHED();
+                    B200_TRY(fetch(re, im));
+                    it->rnorm2 = (R)std::sqrt(re);
+                    if(it->rnorm2 != it->rnorm2)
+                    {
+                        exit_status = aoclsparse_status_numerical_error;
+                        break;
+                    }
+                    rinfo[0] = it->rnorm2;
+                    it->rz   = SC((R)1, (R)1);
+                    it->task = task_check_conv;
+                    // fall through
+                case task_check_conv:
+                    *u = r;
+                    *v = nullptr;
+                    if((R)0 < it->atol && it->rnorm2 <= it->atol)
+                    {
+                        *ircomm = aoclsparse_rci_stop;
+                        break;
+                    }
+                    if((R)0 < it->rtol && it->rnorm2 <= it->brtol)
+                    {
+                        *ircomm = aoclsparse_rci_stop;
+                        break;
+                    }
+                    if(it->maxit > 0 && it->niter > it->maxit)
+                    {
+                        *ircomm     = aoclsparse_rci_stop;
+                        exit_status = aoclsparse_status_maxit;
+                        break;
+                    }
+                    it->task = task_start_iter;
+                    *ircomm  = aoclsparse_rci_stopping_criterion;
+                    break;
+
+                case task_start_iter:
+                    it->niter++;
+                    rinfo[30] = (R)it->niter;
+                    it->task  = task_compute_beta;
+                    if(it->precond)
+                    {
+                        *ircomm = aoclsparse_rci_precond;
+                        *u      = r;
+                        *v      = z;
+                        break;
+                    }
+                    // unpreconditioned: z = r (no copy; the dot product below reads r twice)
+                    // fall through
+                case task_compute_beta:
+                {
+                    const C *zz = it->precond ? z : r;
+                    cdot_kernel<C><<<RED_BLOCKS, RED_THREADS, 0, st>>>(n, r, zz, out);
+                    B200_LAUNCHED();
+                    B200_TRY(fetch(re, im));
+                    const SC rz_new((R)re, (R)im);
+                    if(std::abs(it->rz) <= eps_tol)
+                        return aoclsparse_status_numerical_error;
+                    it->beta = rz_new / it->rz;
+                    it->rz   = rz_new;
+                    C beta;
+                    beta.x = it->beta.real();
+                    beta.y = it->beta.imag();
+                    ccg_direction_kernel<C><<<RED_BLOCKS, RED_THREADS, 0, st>>>(n, beta, p, zz);
+                    B200_LAUNCHED();
+                    *ircomm  = aoclsparse_rci_mv;
+                    it->task = task_take_step;
+                    *u       = p;
+                    *v       = q;
+                    break;
+                }
+
+                case task_take_step:
+                {
+                    cdot_kernel<C><<<RED_BLOCKS, RED_THREADS, 0, st>>>(n, p, q, out);
+                    B200_LAUNCHED();
+                    B200_TRY(fetch(re, im));
+                    const SC pq((R)re, (R)im);
+                    if(std::abs(pq) <= eps_tol || pq == SC((R)0, (R)0))
+                        return aoclsparse_status_numerical_error;
+                    it->alpha = it->rz / pq;
+                    C alpha;
+                    alpha.x = it->alpha.real();
+                    alpha.y = it->alpha.imag();
+                    ccg_step_kernel<C><<<RED_BLOCKS, RED_THREADS, 0, st>>>(n, alpha, p, q, it->x_dev, r, out);
+                    B200_LAUNCHED();
+                    B200_TRY(fetch(re, im));
+                    it->rnorm2 = (R)std::sqrt(re);
+                    if(it->rnorm2 != it->rnorm2)
+                    {
+                        exit_status = aoclsparse_status_numerical_error;
+                        break;
+                    }
+                    rinfo[0] = it->rnorm2;
+                    loop     = true;
+                    it->task = task_check_conv;
+                    break;
+                }
+
+                default:
+                    *ircomm = aoclsparse_rci_stop;
+                    return aoclsparse_status_internal_error;
+                }
+            } while(loop);
+            if(*ircomm == aoclsparse_rci_stop || *ircomm == aoclsparse_rci_stopping_criterion || exit_status != aoclsparse_status_success)
+                B200_TRY(sync_x());
+            else
+                B200_CUDA(cudaStreamSynchronize(st));
+            return exit_status;
+        }
+
+        template <typename R>
+        aoclsparse_status crci_solve(itsol_cdata<R> *it, aoclsparse_itsol_rci_job *ircomm, void **u, void **v, void *x, R rinfo[100])
+        {
+            if(ircomm == nullptr)
+                return aoclsparse_status_invalid_pointer;
+            if(it == nullptr)
+            {
+                *ircomm = aoclsparse_rci_stop;
+                return aoclsparse_status_internal_error;
+            }
+            if(u == nullptr || v == nullptr || x == nullptr || rinfo == nullptr || !it->have_b)
+            {
+                *ircomm = aoclsparse_rci_stop;
+                return aoclsparse_status_invalid_pointer;
+            }
+            aoclsparse_status status;
+            if(!it->solving)
+            {
+                if(it->opts.solver != 0)
+                {
+                    *ircomm = aoclsparse_rci_stop;
+                    return aoclsparse_status_not_implemented; // GMRES
+                }
+                it->task        = task_start;
+                it->precond     = it->opts.cg_precond;
+                it->rtol        = it->opts.cg_rtol;
+                it->atol        = it->opts.cg_atol;
+                it->maxit       = it->opts.cg_maxit;
+                it->solving     = true;
+                it->opts.locked = true;
+            }
+            status = ccg_rci(it, ircomm, u, v, x, rinfo);
+            if(status != aoclsparse_status_success)
+                *ircomm = aoclsparse_rci_stop;
+            if(*ircomm == aoclsparse_rci_stop)
+            {
+                it->solving     = false;
+                it->opts.locked = false;
+            }
+            return status;
+        }
+
+        inline aoclsparse_status cmv_call(float, aoclsparse_matrix A, const aoclsparse_mat_descr d, const void *x, void *y)
+        {
+            const aoclsparse_float_complex one{1.0f, 0.0f}, zero{0.0f, 0.0f};
+            return aoclsparse_cmv(aoclsparse_operation_none, &one, A, d, static_cast<const aoclsparse_float_complex *>(x), &zero,
+                                  static_cast<aoclsparse_float_complex *>(y));
+        }
+        inline aoclsparse_status cmv_call(double, aoclsparse_matrix A, const aoclsparse_mat_descr d, const void *x, void *y)
+        {
+            const aoclsparse_double_complex one{1.0, 0.0}, zero{0.0, 0.0};
+            return aoclsparse_zmv(aoclsparse_operation_none, &one, A, d, static_cast<const aoclsparse_double_complex *>(x), &zero,
+                                  static_cast<aoclsparse_double_complex *>(y));
+        }
+
+        // aoclsparse_cg_solve for complex data, itsol_functions.hpp:1369-1500 (same checks in the same order as forward_solve)
+        template <typename R>
+        aoclsparse_status cforward_solve(itsol_cdata<R>            *it,
+                                         aoclsparse_int             n,
+                                         aoclsparse_matrix          mat,
+                                         const aoclsparse_mat_descr descr,
+                                         const void                *b,
+                                         void                      *x,
+                                         R                          rinfo[100],
+                                         aoclsparse_int (*precond)(aoclsparse_int, aoclsparse_int, const void *, void *, void *),
+                                         aoclsparse_int (*monit)(aoclsparse_int, const void *, const void *, R *, void *),
+                                         void *udata)
+        {
+            using C = typename cplx_types<R>::dev;
+            if(it == nullptr)
+                return aoclsparse_status_internal_error;
+            if(x == nullptr || rinfo == nullptr)
+                return aoclsparse_status_invalid_pointer;
+            for(int i = 0; i < 100; ++i)
+                rinfo[i] = (R)0;
+            B200_TRY(crci_input(it, n, b));
+            if(it->opts.solver != 0)
+                return aoclsparse_status_not_implemented; // GMRES
+            if(mat == nullptr || descr == nullptr)
+                return aoclsparse_status_invalid_pointer;
+            if(mat->m != n || mat->n != n)
+                return aoclsparse_status_invalid_size;
+            if(descr->type != aoclsparse_matrix_type_symmetric || descr->fill_mode != aoclsparse_fill_mode_lower)
+                return aoclsparse_status_invalid_value;
+            if(it->opts.cg_precond == 1 && precond == nullptr)
+                return aoclsparse_status_invalid_pointer;
+            if(it->opts.cg_precond == 3)
+                return aoclsparse_status_not_implemented; // symmetric Gauss-Seidel
+            {
+                const int want  = get_doid(true, descr->type, descr->fill_mode, aoclsparse_operation_none);
+                bool      ready = false;
+                {
+                    std::shared_lock<std::shared_mutex> rl(mat->guard);
+                    for(const hint &hh : mat->hints)
+                        ready = ready || (hh.act == 1 && hh.doid == want && hh.done);
+                }
+                if(!ready && aoclsparse_set_mv_hint(mat, aoclsparse_operation_none, descr, 100) == aoclsparse_status_success)
+                    aoclsparse_optimize(mat);
+            }
+            aoclsparse_itsol_rci_job ircomm      = aoclsparse_rci_start;
+            void                    *u = nullptr, *v = nullptr;
+            aoclsparse_status        exit_status = aoclsparse_status_success;
+            while(ircomm != aoclsparse_rci_stop)
+            {
+                exit_status = crci_solve(it, &ircomm, &u, &v, x, rinfo);
+                if(exit_status != aoclsparse_status_success && ircomm != aoclsparse_rci_stop)
+                    break;
+                if(ircomm == aoclsparse_rci_mv)
+                {
+                    if(cmv_call(R(), mat, descr, u, v) != aoclsparse_status_success)
+                    {
+                        exit_status = aoclsparse_status_internal_error;
+                        break;
+                    }
+                }
+                else if(ircomm == aoclsparse_rci_precond)
+                {
+                    if(precond(0, n, u, v, udata) != 0)
+                        ircomm = aoclsparse_rci_interrupt;
+                }
+                else if(ircomm == aoclsparse_rci_stopping_criterion && monit)
+                {
+                    if(monit(n, it->x_user ? static_cast<const void *>(it->x_user) : static_cast<const void *>(it->x_dev), u, rinfo, udata) != 0)
+                        ircomm = aoclsparse_rci_interrupt;
+                }
+            }
+            it->solving     = false;
+            it->opts.locked = false;
+            (void)sizeof(C);
+            return exit_status;
+        }
     }
 }
 
@@ -1079,6 +1674,8 @@ struct _aoclsparse_itsol_handle
     aoclsparse_matrix_data_type type;
     itsol_data<float>          *s = nullptr;
     itsol_data<double>         *d = nullptr;
+    itsol_cdata<float>         *c = nullptr;
+    itsol_cdata<double>        *z = nullptr;
 };
 
 extern "C" {
@@ -1116,20 +1713,38 @@ aoclsparse_status aoclsparse_itsol_d_init(aoclsparse_itsol_handle *handle)
     return aoclsparse_status_success;
 }
 
-// complex conjugate gradients are not provided (itsol_functions.cpp:168-230 create the handles in the reference)
+// complex handles (itsol_functions.cpp:168-230): conjugate gradients only, host-driven (see ccg_rci)
 aoclsparse_status aoclsparse_itsol_c_init(aoclsparse_itsol_handle *handle)
 {
     if(handle == nullptr)
         return aoclsparse_status_invalid_pointer;
-    *handle = nullptr;
-    return aoclsparse_status_not_implemented;
+    *handle = new(std::nothrow) _aoclsparse_itsol_handle;
+    if(!*handle)
+        return aoclsparse_status_memory_error;
+    (*handle)->type = aoclsparse_cmat;
+    (*handle)->c    = new(std::nothrow) itsol_cdata<float>;
+    if(!(*handle)->c)
+    {
+        aoclsparse_itsol_destroy(handle);
+        return aoclsparse_status_memory_error;
+    }
+    return aoclsparse_status_success;
 }
 aoclsparse_status aoclsparse_itsol_z_init(aoclsparse_itsol_handle *handle)
 {
     if(handle == nullptr)
         return aoclsparse_status_invalid_pointer;
-    *handle = nullptr;
-    return aoclsparse_status_not_implemented;
+    *handle = new(std::nothrow) _aoclsparse_itsol_handle;
+    if(!*handle)
+        return aoclsparse_status_memory_error;
+    (*handle)->type = aoclsparse_zmat;
+    (*handle)->z    = new(std::nothrow) itsol_cdata<double>;
+    if(!(*handle)->z)
+    {
+        aoclsparse_itsol_destroy(handle);
+        return aoclsparse_status_memory_error;
+    }
+    return aoclsparse_status_success;
 }
 
 void aoclsparse_itsol_destroy(aoclsparse_itsol_handle *handle)
@@ -1138,6 +1753,8 @@ void aoclsparse_itsol_destroy(aoclsparse_itsol_handle *handle)
     {
         delete(*handle)->s;
         delete(*handle)->d;
+        delete(*handle)->c;
+        delete(*handle)->z;
         delete *handle;
         *handle = nullptr;
     }
@@ -1152,6 +1769,10 @@ void aoclsparse_itsol_handle_prn_options(aoclsparse_itsol_handle handle)
         handle->d->opts.print();
     else if(handle->type == aoclsparse_smat && handle->s)
         handle->s->opts.print();
+    else if(handle->type == aoclsparse_cmat && handle->c)
+        handle->c->opts.print();
+    else if(handle->type == aoclsparse_zmat && handle->z)
+        handle->z->opts.print();
 }
 
 aoclsparse_status aoclsparse_itsol_option_set(aoclsparse_itsol_handle handle, const char *option, const char *value)
@@ -1159,12 +1780,28 @@ aoclsparse_status aoclsparse_itsol_option_set(aoclsparse_itsol_handle handle, co
     // handle_parse_option, itsol_functions.hpp:1622-1715: every failure of the registry maps to invalid_value
     if(handle == nullptr)
         return aoclsparse_status_invalid_pointer;
-    if((handle->type == aoclsparse_dmat && !handle->d) || (handle->type == aoclsparse_smat && !handle->s))
+    if((handle->type == aoclsparse_dmat && !handle->d) || (handle->type == aoclsparse_smat && !handle->s)
+       || (handle->type == aoclsparse_cmat && !handle->c) || (handle->type == aoclsparse_zmat && !handle->z))
         return aoclsparse_status_internal_error;
     if(!option || !value)
         return aoclsparse_status_invalid_pointer;
     const std::string name = prepare(option);
-    const int         flag = handle->type == aoclsparse_dmat ? handle->d->opts.set(name, value) : handle->s->opts.set(name, value);
+    int               flag;
+    switch(handle->type)
+    {
+    case aoclsparse_dmat:
+        flag = handle->d->opts.set(name, value);
+        break;
+    case aoclsparse_smat:
+        flag = handle->s->opts.set(name, value);
+        break;
+    case aoclsparse_cmat:
+        flag = handle->c->opts.set(name, value);
+        break;
+    default:
+        flag = handle->z->opts.set(name, value);
+        break;
+    }
     return flag == 0 ? aoclsparse_status_success : aoclsparse_status_invalid_value;
 }
 
@@ -1235,5 +1872,89 @@ aoclsparse_status aoclsparse_itsol_s_solve(aoclsparse_itsol_handle    handle,
     if(handle->type != aoclsparse_smat)
         return aoclsparse_status_wrong_type;
     return forward_solve<float>(handle->s, n, mat, descr, b, x, rinfo, precond, monit, udata);
+}
+
+// ---- complex entry points (aoclsparse_solvers.h:276-283, 395-408, 537-575)
+aoclsparse_status aoclsparse_itsol_c_rci_input(aoclsparse_itsol_handle handle, aoclsparse_int n, const aoclsparse_float_complex *b)
+{
+    if(!handle)
+        return aoclsparse_status_invalid_pointer;
+    if(handle->type != aoclsparse_cmat)
+        return aoclsparse_status_wrong_type;
+    return crci_input(handle->c, n, b);
+}
+aoclsparse_status aoclsparse_itsol_z_rci_input(aoclsparse_itsol_handle handle, aoclsparse_int n, const aoclsparse_double_complex *b)
+{
+    if(!handle)
+        return aoclsparse_status_invalid_pointer;
+    if(handle->type != aoclsparse_zmat)
+        return aoclsparse_status_wrong_type;
+    return crci_input(handle->z, n, b);
+}
+aoclsparse_status aoclsparse_itsol_c_rci_solve(aoclsparse_itsol_handle    handle,
+                                               aoclsparse_itsol_rci_job  *ircomm,
+                                               aoclsparse_float_complex **u,
+                                               aoclsparse_float_complex **v,
+                                               aoclsparse_float_complex  *x,
+                                               float                      rinfo[100])
+{
+    if(!handle)
+        return aoclsparse_status_invalid_pointer;
+    if(handle->type != aoclsparse_cmat)
+        return aoclsparse_status_wrong_type;
+    return crci_solve(handle->c, ircomm, reinterpret_cast<void **>(u), reinterpret_cast<void **>(v), x, rinfo);
+}
+aoclsparse_status aoclsparse_itsol_z_rci_solve(aoclsparse_itsol_handle     handle,
+                                               aoclsparse_itsol_rci_job   *ircomm,
+                                               aoclsparse_double_complex **u,
+                                               aoclsparse_double_complex **v,
+                                               aoclsparse_double_complex  *x,
+                                               double                      rinfo[100])
+{
+    if(!handle)
+        return aoclsparse_status_invalid_pointer;
+    if(handle->type != aoclsparse_zmat)
+        return aoclsparse_status_wrong_type;
+    return crci_solve(handle->z, ircomm, reinterpret_cast<void **>(u), reinterpret_cast<void **>(v), x, rinfo);
+}
+aoclsparse_status aoclsparse_itsol_c_solve(
+    aoclsparse_itsol_handle         handle,
+    aoclsparse_int                  n,
+    aoclsparse_matrix               mat,
+    const aoclsparse_mat_descr      descr,
+    const aoclsparse_float_complex *b,
+    aoclsparse_float_complex       *x,
+    float                           rinfo[100],
+    aoclsparse_int precond(aoclsparse_int flag, aoclsparse_int n, const aoclsparse_float_complex *u, aoclsparse_float_complex *v, void *udata),
+    aoclsparse_int monit(aoclsparse_int n, const aoclsparse_float_complex *x, const aoclsparse_float_complex *r, float rinfo[100], void *udata),
+    void *udata)
+{
+    if(!handle)
+        return aoclsparse_status_invalid_pointer;
+    if(handle->type != aoclsparse_cmat)
+        return aoclsparse_status_wrong_type;
+    return cforward_solve<float>(handle->c, n, mat, descr, b, x, rinfo,
+                                 reinterpret_cast<aoclsparse_int (*)(aoclsparse_int, aoclsparse_int, const void *, void *, void *)>(precond),
+                                 reinterpret_cast<aoclsparse_int (*)(aoclsparse_int, const void *, const void *, float *, void *)>(monit), udata);
+}
+aoclsparse_status aoclsparse_itsol_z_solve(
+    aoclsparse_itsol_handle          handle,
+    aoclsparse_int                   n,
+    aoclsparse_matrix                mat,
+    const aoclsparse_mat_descr       descr,
+    const aoclsparse_double_complex *b,
+    aoclsparse_double_complex       *x,
+    double                           rinfo[100],
+    aoclsparse_int precond(aoclsparse_int flag, aoclsparse_int n, const aoclsparse_double_complex *u, aoclsparse_double_complex *v, void *udata),
+    aoclsparse_int monit(aoclsparse_int n, const aoclsparse_double_complex *x, const aoclsparse_double_complex *r, double rinfo[100], void *udata),
+    void *udata)
+{
+    if(!handle)
+        return aoclsparse_status_invalid_pointer;
+    if(handle->type != aoclsparse_zmat)
+        return aoclsparse_status_wrong_type;
+    return cforward_solve<double>(handle->z, n, mat, descr, b, x, rinfo,
+                                  reinterpret_cast<aoclsparse_int (*)(aoclsparse_int, aoclsparse_int, const void *, void *, void *)>(precond),
+                                  reinterpret_cast<aoclsparse_int (*)(aoclsparse_int, const void *, const void *, double *, void *)>(monit), udata);
 }
 }

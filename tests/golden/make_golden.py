@@ -27,7 +27,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import capi  # noqa: E402
 import gen_np  # noqa: E402
 sys.path.insert(0, HERE)
-from make_golden_itsol import itsol_cases, itsol_matrix, run_itsol_case, itsol_status_table  # noqa: E402
+from make_golden_itsol import (itsol_cases, itsol_complex_cases, itsol_matrix, run_itsol_case,  # noqa: E402
+                                itsol_status_table)
 from conftest import TOL, apply_op, effective_dense, mv_denominator, rel_err  # noqa: E402
 
 REF = capi.AoclSparse(os.path.join(ROOT, "oracle", "_ref", "libaoclsparse_ref.so"))
@@ -605,6 +606,22 @@ def itsol_sweep():
           [m["iters"] for m in meta], "; status table", res)
 
 
+def itsol_complex_sweep():
+    """the same for c / z handles (complex symmetric matrices; the reference's own tests do not cover complex CG, so these
+    recorded runs of its build are the only pin there is)"""
+    out, meta = {}, []
+    for c in itsol_complex_cases():
+        status, rinfo, x, trace, b = run_itsol_case(REF, c)
+        out[c["key"] + "_x"] = x
+        out[c["key"] + "_trace"] = np.array(trace, dtype=np.float64).reshape(-1, 2)
+        meta.append(dict(c, status=int(status), res=float(rinfo[0]), bnorm=float(rinfo[1]), iters=int(rinfo[30])))
+    np.savez_compressed(os.path.join(HERE, "ref_itsol_complex.npz"), **out)
+    json.dump(dict(cases=meta), open(os.path.join(HERE, "ref_itsol_complex.json"), "w"), indent=0)
+    from collections import Counter
+    print("complex itsol sweep:", len(meta), "cases; statuses", Counter(m["status"] for m in meta), "iterations",
+          [m["iters"] for m in meta], "residuals", ["%.1e" % (m["res"] / max(m["bnorm"], 1e-300)) for m in meta])
+
+
 def create_table(rng):
     """status / sort / fulldiag of the reference's create on valid, unsorted and corrupted inputs"""
     cases = []
@@ -756,6 +773,9 @@ if __name__ == "__main__":
     if "--only-csc" in sys.argv:
         csc_sweep(np.random.default_rng(69070))
         sys.exit(0)
+    if "--only-itsol-complex" in sys.argv:
+        itsol_complex_sweep()
+        sys.exit(0)
     if "--only-itsol" in sys.argv:
         itsol_sweep()
         sys.exit(0)
@@ -775,4 +795,5 @@ if __name__ == "__main__":
     csc_sweep(np.random.default_rng(69070))
     sp2m_sweep(np.random.default_rng(69071))
     itsol_sweep()
+    itsol_complex_sweep()
     print("golden fixtures written to", HERE)

@@ -6,7 +6,8 @@ import numpy as np
 
 import gen_np
 
-DT = {"s": np.float32, "d": np.float64}
+DT = {"s": np.float32, "d": np.float64, "c": np.complex64, "z": np.complex128}
+RT = {"s": np.float32, "d": np.float64, "c": np.float32, "z": np.float64}  # tolerances, norms, rinfo
 
 
 def itsol_cases():
@@ -33,9 +34,49 @@ def itsol_cases():
     return cases
 
 
+def itsol_complex_cases():
+    """CG on c / z handles: the reference runs the same state machine on std::complex with UNCONJUGATED dot products
+    (itsol_functions.hpp:795-797, 822-824), i.e. the recurrence for complex SYMMETRIC matrices"""
+    cases = []
+    k = 0
+    for p in "zc":
+        for mat in ("csym_lap2d_full", "csym_lap3d_lower", "csym_random"):
+            for variant in ("defaults", "tight", "jacobi", "maxit", "monit_stop", "x0_random"):
+                opts, precond, stop_at, x0 = {}, "none", None, "zeros"
+                if variant == "tight":
+                    # (not tighter: the reference's breakdown test is ABSOLUTE, |r.z| <= 4.4e-18 for double, and the
+                    # unconjugated r.z of a residual of norm ~ 4e-9 falls below it -- with rtol = 1e-10 its own build
+                    # stops with numerical_error at a relative residual of 1.7e-10; a threshold crossing is no fixture)
+                    opts = {"CG Rel Tolerance": "1e-8" if p == "z" else "1e-5", "cg abs tolerance": "0"}
+                elif variant == "jacobi":
+                    opts, precond = {"cg preconditioner": " User "}, "jacobi"
+                elif variant == "maxit":
+                    opts = {"cg iteration limit": "4", "cg rel tolerance": "1e-30", "cg abs tolerance": "0"}
+                elif variant == "monit_stop":
+                    stop_at = 3
+                elif variant == "x0_random":
+                    x0 = "random"
+                cases.append(dict(key=f"z{k}", p=p, mat=mat, variant=variant, opts=opts, precond=precond, stop_at=stop_at,
+                                  x0=x0))
+                k += 1
+    return cases
+
+
 def itsol_matrix(kind, dt):
-    """(n, rp, col, val) of a symmetric positive definite test matrix; 'lower' variants store one triangle only"""
+    """(n, rp, col, val) of a symmetric positive definite test matrix; 'lower' variants store one triangle only.
+    'csym_*': complex SYMMETRIC (not Hermitian) matrices = a real SPD matrix + i * (a positive diagonal and, for the random
+    one, a small symmetric off-diagonal part)"""
     import scipy.sparse as sp
+    if kind.startswith("csym_"):
+        n, rp, col, val = itsol_matrix(kind[5:], np.float64)
+        rows = np.repeat(np.arange(n), np.diff(rp))
+        im = np.zeros(len(val))
+        on = col == rows
+        im[on] = 0.3 * val[on] * (1.0 + rows[on] / n)
+        if kind == "csym_random":
+            lo, hi = np.minimum(rows, col), np.maximum(rows, col)
+            im[~on] = 0.1 * val[~on] * np.cos(0.7 * lo[~on] + 1.3 * hi[~on])  # depends on {i, j} only: symmetric
+        return n, rp, col, (val + 1j * im).astype(dt)
     if kind == "lap2d_full":
         rp, col, val = gen_np.stencil(5, 18, 17, 1)
         return len(rp) - 1, rp, col, val.astype(dt)
@@ -68,11 +109,13 @@ def run_itsol_case(lib, c, callbacks=True):
     for o, v in c["opts"].items():
         assert lib.itsol_option_set(h, o, v) == 0, (o, v)
     rng = np.random.default_rng(17)
-    b = rng.normal(size=n).astype(dt)
-    x = rng.normal(size=n).astype(dt) if c["x0"] == "random" else np.zeros(n, dt)
-    rinfo = np.zeros(100, dt)
+    cplx = c["p"] in "cz"
+    draw = (lambda: rng.normal(size=n) + 1j * rng.normal(size=n)) if cplx else (lambda: rng.normal(size=n))
+    b = draw().astype(dt)
+    x = draw().astype(dt) if c["x0"] == "random" else np.zeros(n, dt)
+    rinfo = np.zeros(100, RT[c["p"]])
     import scipy.sparse as sp
-    diag = np.ones(n)
+    diag = np.ones(n, np.complex128 if cplx else np.float64)
     rows = np.repeat(np.arange(n), np.diff(rp))
     diag[rows[col == rows]] = val[col == rows]
     trace = []

@@ -129,3 +129,127 @@ def test_cg_device_resident_and_reverse_communication(lib):
     for dd in (d, dgen):
         lib.destroy_descr(dd)
     lib.destroy(h)
+
+
+@pytest.mark.gpu
+def test_cg_reverse_communication_right_after_a_forward_solve(lib):
+    """aoclsparse_itsol_?_rci_solve without a new rci_input is legal after aoclsparse_itsol_?_solve (the handle keeps b;
+    itsol_functions.hpp:296-330 only rci_input replaces it).  The forward solve without callbacks keeps its work vectors
+    in plain device memory, so the reverse-communication entry must move them to managed memory before it hands *u / *v
+    to a HOST caller -- who here reads u and writes v as ordinary numpy arrays (round-1 advisor finding)."""
+    import scipy.sparse as sp
+    import gen_np
+    rp, col, val = gen_np.stencil(7, 16, 16, 16)
+    n = len(rp) - 1
+    A = sp.csr_matrix((val, col, rp))
+    st, h = lib.create_csr("d", 0, n, n, len(col), rp, col, val)
+    assert st == 0
+    d = lib.create_descr(1, 0, 0, 0)
+    rng = np.random.default_rng(11)
+    b = A @ rng.normal(size=n)
+    st, it = lib.itsol_init("d")
+    assert st == 0 and lib.itsol_option_set(it, "cg rel tolerance", "1e-11") == 0
+    x1, rinfo1 = np.zeros(n), np.zeros(100)
+    assert lib.itsol_solve("d", it, n, h, d, b, x1, rinfo1) == 0, lib.last_error()  # device-driven: no callbacks
+    iters = int(rinfo1[30])
+    assert iters > 5
+    x2, rinfo2 = np.zeros(n), np.zeros(100)
+    ircomm, u, v = C.c_int(1), C.c_void_p(), C.c_void_p()
+    products = 0
+    while True:
+        st = lib.itsol_rci_solve("d", it, ircomm, u, v, x2, rinfo2)
+        assert st == 0, (st, lib.last_error())
+        if ircomm.value == 0:
+            break
+        if ircomm.value == 2:  # v = A u computed by the HOST on the handed-out vectors
+            uu = np.ctypeslib.as_array(C.cast(u, C.POINTER(C.c_double)), shape=(n,))
+            vv = np.ctypeslib.as_array(C.cast(v, C.POINTER(C.c_double)), shape=(n,))
+            vv[:] = A @ uu
+            products += 1
+        else:
+            assert ircomm.value == 4
+    assert int(rinfo2[30]) == iters and products == iters + 1
+    assert np.max(np.abs(x2 - x1)) <= 1e-9 * max(1.0, np.max(np.abs(x1)))
+    lib.itsol_destroy(it)
+    lib.destroy_descr(d)
+    lib.destroy(h)
+
+
+def test_complex_cg_cases_match_reference(lib):
+    """c / z handles: the reference's conjugate gradients on std::complex (unconjugated dot products, complex symmetric
+    matrices; library/src/solvers/aoclsparse_itsol_functions.hpp:633-870, handles aoclsparse_solvers.h:222-225) -- status,
+    iteration count, |b|, the residual history the monitor sees and the solution against recorded runs of the
+    reference's own build (tests/golden/ref_itsol_complex.*, make_golden.py --only-itsol-complex)."""
+    cases = json.load(open(os.path.join(GOLDEN, "ref_itsol_complex.json")))["cases"]
+    data = np.load(os.path.join(GOLDEN, "ref_itsol_complex.npz"))
+    for c in cases:
+        status, rinfo, x, trace, b = mg.run_itsol_case(lib, c)
+        eps = 1e-9 if c["p"] == "z" else 2e-4
+        assert status == c["status"], (c, status, lib.last_error())
+        assert int(rinfo[30]) == c["iters"], (c, rinfo[30])
+        assert abs(rinfo[1] - c["bnorm"]) <= 1e-6 * c["bnorm"]
+        ref_trace = data[c["key"] + "_trace"]
+        got = np.array(trace, dtype=np.float64).reshape(-1, 2)
+        assert got.shape == ref_trace.shape, c
+        assert np.array_equal(got[:, 0], ref_trace[:, 0])
+        assert np.max(np.abs(got[:, 1] - ref_trace[:, 1])) <= 50 * eps * c["bnorm"], c
+        xr = data[c["key"] + "_x"]
+        assert x.dtype == xr.dtype
+        assert np.max(np.abs(x - xr)) <= 200 * eps * max(1.0, np.max(np.abs(xr))), (c, np.max(np.abs(x - xr)))
+        if c["status"] == 0:
+            # and the result solves the system: ||A x - b|| as small as the solver says
+            import scipy.sparse as sp
+            n, rp, col, val = mg.itsol_matrix(c["mat"], np.complex128)
+            A = sp.csr_matrix((val, col, rp), shape=(n, n))
+            if "lower" in c["mat"]:
+                A = A + sp.tril(A, -1).T  # symmetric, NOT Hermitian
+            res = np.linalg.norm(A @ x.astype(np.complex128) - b.astype(np.complex128))
+            assert res <= max(2.0 * c["res"], 50 * eps * c["bnorm"]), (c, res)
+
+
+def test_complex_cg_status_and_reverse_communication(lib):
+    """wrong-type / argument checks of the complex entry points and the reverse-communication loop with the product done by
+    aoclsparse_zmv on the managed work vectors"""
+    n, rp, col, val = mg.itsol_matrix("csym_lap2d_full", np.complex128)
+    st, A = lib.create_csr("z", 0, n, n, len(col), rp, col, val)
+    assert st == 0
+    dsym, dgen = lib.create_descr(1, 0, 0, 0), lib.create_descr()
+    st, hz = lib.itsol_init("z")
+    assert st == 0
+    st, hd = lib.itsol_init("d")
+    assert st == 0
+    rng = np.random.default_rng(5)
+    b = (rng.normal(size=n) + 1j * rng.normal(size=n)).astype(np.complex128)
+    x, rinfo = np.zeros(n, np.complex128), np.zeros(100)
+    assert lib.itsol_solve("z", hd, n, A, dsym, b, x, rinfo) == capi.ST["wrong_type"]
+    assert lib.itsol_solve("d", hz, n, A, dsym, b.real.copy(), x.real.copy(), rinfo) == capi.ST["wrong_type"]
+    assert lib.itsol_rci_input("z", hd, n, b) == capi.ST["wrong_type"]
+    assert lib.itsol_solve("z", hz, n, A, dgen, b, x, rinfo) == capi.ST["invalid_value"]
+    assert lib.itsol_solve("z", hz, n - 1, A, dsym, b, x, rinfo) == capi.ST["invalid_size"]
+    assert lib.itsol_solve("z", hz, n, A, dsym, None, x, rinfo) == capi.ST["invalid_pointer"]
+    assert lib.itsol_option_set(hz, "iterative method", "gmres") == 0
+    assert lib.itsol_solve("z", hz, n, A, dsym, b, x, rinfo) == capi.ST["not_implemented"]
+    assert lib.itsol_option_set(hz, "iterative method", "cg") == 0
+    assert lib.itsol_solve("z", hz, n, A, dsym, b, x, rinfo) == 0, lib.last_error()
+    iters = int(rinfo[30])
+    # reverse communication, products by the library on the handed-out (managed) vectors
+    assert lib.itsol_rci_input("z", hz, n, b) == 0
+    x2, rinfo2 = np.zeros(n, np.complex128), np.zeros(100)
+    ircomm, u, v = C.c_int(1), C.c_void_p(), C.c_void_p()
+    import torch
+    while True:
+        st = lib.itsol_rci_solve("z", hz, ircomm, u, v, x2, rinfo2)
+        assert st == 0, (st, lib.last_error())
+        if ircomm.value == 0:
+            break
+        if ircomm.value == 2:
+            assert lib.mv("z", 111, 1.0, A, dsym, u.value, 0.0, v.value) == 0
+            torch.cuda.synchronize()
+        else:
+            assert ircomm.value == 4
+    assert int(rinfo2[30]) == iters and np.max(np.abs(x2 - x)) <= 1e-9 * max(1.0, np.max(np.abs(x)))
+    lib.itsol_destroy(hz)
+    lib.itsol_destroy(hd)
+    for dd in (dsym, dgen):
+        lib.destroy_descr(dd)
+    lib.destroy(A)
