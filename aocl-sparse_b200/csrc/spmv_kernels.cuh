@@ -207,7 +207,7 @@ namespace b200
     //                val = pair.v -- the same column and the same value, bit for bit, from 1 instead of 4 + sizeof(T)
     //                bytes.  `codes` is then that copy, `code_off` / `code_val` the table; `col` and `val` are unused.
     template <typename T, bool GENERIC, int NT, bool PUSH = false, bool CODED = false, bool ECODED = false>
-    __global__ void __launch_bounds__(NT) spmv_row_blocks_kernel(const int4 *__restrict__ desc,
+    __global__ void __launch_bounds__(NT, ECODED ? 2048 / NT : 1) spmv_row_blocks_kernel(const int4 *__restrict__ desc,
                                                                           const int *__restrict__ kind,
                                                                           int block_first,
                                                                           int cap, // staged capacity in entries
@@ -298,6 +298,31 @@ namespace b200
                 const int e   = cur_e - a;
                 T         acc = vt<T>::zero();
                 const T  *xr  = x + r; // x[col] = xr[col - row]
+                // Rows of >= 12 entries read their code bytes as aligned 32-bit words (the staged buffer is 16-byte aligned
+                // and padded): four codes = funnel shift of two neighbouring words by the row's byte phase, the second
+                // word of one group being the first of the next -- one word load per four entries instead of four byte
+                // loads: 27-point 128^3 50.8 -> 42.7 us.  Short rows keep the byte loads (the shift chain costs a 5- or
+                // 7-entry row more latency than the loads it saves: 7-point 512^3 0.903 -> 0.986 ms;
+                // profiles/r02_entry_codes.txt).  Same codes either way, hence the same bits.  (8-byte values only: with
+                // 4-byte values both paths do not fit the 32 registers that 8 resident CTAs leave.)
+                if(sizeof(T) == 8 && e - j >= 12)
+                {
+                    const unsigned *cw = reinterpret_cast<const unsigned *>(secode) + (j >> 2);
+                    const unsigned  sh = (unsigned)(j & 3) * 8u;
+                    unsigned        lo = cw[0];
+                    for(; j + 4 <= e; j += 4)
+                    {
+                        const unsigned hi = *++cw;
+                        const unsigned c4 = __funnelshift_r(lo, hi, sh);
+                        lo                = hi;
+                        const pair_t p0 = stab[c4 & 255u], p1 = stab[(c4 >> 8) & 255u], p2 = stab[(c4 >> 16) & 255u], p3 = stab[c4 >> 24];
+                        const T      x0 = ldg_ro(xr + p0.off), x1 = ldg_ro(xr + p1.off), x2 = ldg_ro(xr + p2.off), x3 = ldg_ro(xr + p3.off);
+                        acc             = mad(p0.v, x0, acc);
+                        acc             = mad(p1.v, x1, acc);
+                        acc             = mad(p2.v, x2, acc);
+                        acc             = mad(p3.v, x3, acc);
+                    }
+                }
                 for(; j + 4 <= e; j += 4)
                 {
                     const pair_t p0 = stab[secode[j]], p1 = stab[secode[j + 1]], p2 = stab[secode[j + 2]], p3 = stab[secode[j + 3]];
