@@ -14,18 +14,20 @@
 //      row r is the grid point (r % s1, (r / s1) % (s2 / s1), r / s2).  A matrix without that structure keeps the
 //      row-block kernel.  Correctness never depends on the guess: tiles are built from the stored columns.
 //   2. rows are grouped into boxes X x Y x Z of that grid (RT = X*Y*Z rows, a multiple of 32, <= 96).  Per tile the
-//      device collects the columns of its rows, sorts them, keeps the distinct ones (= the B rows the tile needs, in
-//      ascending order, cut into RUNS of consecutive columns) and rewrites the tile's entries as
-//            val[j][row in tile]  (ELL inside the tile: plane j holds the j-th stored entry of every row)
-//            slot[j][row in tile] (16 bit: position of the entry's column among the tile's distinct columns)
-//      so the multiply needs neither col_idx nor row_ptr.  Entries keep their stored order inside a row.
-//   3. csrmm_mesh_tiles_kernel: one CTA per tile.  TMA bulk copies bring the tile's val / slot planes and -- one copy per
-//      run -- its B rows into shared memory (mbarrier completion); thread (row, h) then walks the row's entries and
-//      accumulates 128 bytes of the output row in registers, reading B out of shared memory with 128-bit loads.  Lane
-//      `row` reads the 16-byte chunks of its 128 bytes in the rotated order (k + row) mod 8, so the 8 lanes of a
-//      quarter-warp always hit 8 different bank groups whatever their slots are (no padding, hence one contiguous TMA
-//      copy per run).  Results go through shared memory to be written as whole contiguous C rows.
-//      Two CTAs per SM: one stages while the other multiplies.
+//      device collects the columns of its rows (k-way merge of the sorted rows), keeps the distinct ones (= the B rows the
+//      tile needs, in ascending order, cut into RUNS of consecutive columns) and rewrites the tile's entries per ROW
+//      GROUP (GRP = 2 rows) as a WALK over the union of the group's columns:
+//            walk[j][group]  32 bit: 16-bit slot (position of the column among the tile's distinct columns), which rows
+//                            of the group store that column, and where their values start; an all-zero entry ends a walk
+//            val[i][group]   the values in walk order
+//      so the multiply needs neither col_idx nor row_ptr, and one B row read from shared memory serves both rows of a
+//      group.  Entries keep their stored (ascending) order inside a row.
+//   3. csrmm_mesh_tiles_kernel: PERSISTENT, double-buffered, warp-specialised -- one CTA per SM walks tiles
+//      blockIdx.x + k * gridDim.x; its last warp is the producer (TMA bulk copies of the walk / value planes, the row list
+//      and -- one copy per run -- the tile's B rows, mbarrier "full" / "empty" per buffer), the other warps are consumers:
+//      a team of 8 lanes owns a row group, lane h holds the 16-byte chunks h, h + 8, ... of the group's output rows and
+//      reads B out of shared memory with conflict-free 128-byte wavefronts; C rows are stored as whole 128-byte lines.
+//      The copies of tile i + 1 overlap the multiply of tile i (see the comment at the kernel).
 // Per-row arithmetic (order of the multiply-adds, alpha / beta handling) is that of csrmm_row_major_vec_kernel, so both
 // kernels return identical bits.
 #include "spmv_kernels.cuh"

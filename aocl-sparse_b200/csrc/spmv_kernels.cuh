@@ -207,7 +207,7 @@ namespace b200
     //                val = pair.v -- the same column and the same value, bit for bit, from 1 instead of 4 + sizeof(T)
     //                bytes.  `codes` is then that copy, `code_off` / `code_val` the table; `col` and `val` are unused.
     template <typename T, bool GENERIC, int NT, bool PUSH = false, bool CODED = false, bool ECODED = false>
-    __global__ void __launch_bounds__(NT, ECODED ? 2048 / NT : 1) spmv_row_blocks_kernel(const int4 *__restrict__ desc,
+    __global__ void __launch_bounds__(NT, (ECODED && NT <= 256 && std::is_same<T, double>::value) ? 2048 / NT : 0) spmv_row_blocks_kernel(const int4 *__restrict__ desc,
                                                                           const int *__restrict__ kind,
                                                                           int block_first,
                                                                           int cap, // staged capacity in entries
