@@ -158,3 +158,19 @@ def test_ilp64_is_refused_at_compile_time(tmp_path):
     assert ok.returncode == 0, ok.stderr
     bad = subprocess.run([cc, "-fsyntax-only", "-Daoclsparse_ILP64", "-I", inc, str(src)], capture_output=True, text=True)
     assert bad.returncode != 0 and "LP64" in bad.stderr
+
+
+def test_c_callers_of_the_extensions_link(tmp_path):
+    """the plain-C drivers of the B200 extensions (tests/shard_check.c: the row-sharded iteration object;
+    examples/spmv_c.c) compile with -Wall -Werror against include/ and link against the library -- the CPU gate for the
+    C boundary; the GPU tests run them"""
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc") or "/usr/bin/gcc"
+    libdir = os.path.dirname(capi.LIB_PATH)
+    for src in (os.path.join(ROOT, "tests", "shard_check.c"), os.path.join(ROOT, "examples", "spmv_c.c")):
+        exe = str(tmp_path / os.path.basename(src)[:-2])
+        out = subprocess.run([cc, "-O1", "-Wall", "-Werror", src, "-I", os.path.join(ROOT, "include"), "-L", libdir,
+                              "-laoclsparse_b200", "-lm", f"-Wl,-rpath,{libdir}", "-o", exe], capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr[-3000:]
+        assert os.path.exists(exe)
